@@ -1,0 +1,203 @@
+// Alpha compositing along rays and its backward (kernel 4 of the north star).
+//
+// Restates raw2outputs_nerf_color with occupancy=True (reference src/common.py:385-428) fused with the
+// no-neighbour overwrite raw[~point_mask, -1] = -100 (src/utils/Renderer.py:237-239):
+//     alpha_s = sigmoid(coef * occ_s),  T_s = prod_{j<s} (1 - alpha_j + 1e-10),  w_s = alpha_s * T_s
+//     rgb = sum w rgb / (sum w + 1e-10), depth = sum w z / (sum w + 1e-10), var = sum w (z - depth)^2
+// One lane per sample, G lanes per ray (G = 8 for the reference's S = 5, G = 32 for S up to 32), so the
+// packed (R,S,4) raw tensor is read with unit-stride, fully coalesced loads.  The exclusive transmittance
+// product and the sums are taken in sample order through shuffles (same association as the reference's
+// sequential cumprod / sum, so results agree to the last bits).
+//
+// Backward (only depth and rgb carry gradient):
+//     gw_s = (g_depth (z_s - depth) + sum_c g_c (rgb_sc - rgb_c)) / wsum
+//     d alpha_s = gw_s T_s - (sum_{k>s} gw_k w_k) / (1 - alpha_s + 1e-10)
+//     d occ_s = d alpha_s * coef * alpha_s (1 - alpha_s)       (straight-through for masked points, A6)
+#include "hps_common.cuh"
+
+namespace hps {
+
+struct RaySample {
+    float alpha, trans, w, z, r, g, b;
+};
+
+template <int G>
+__device__ __forceinline__ float group_bcast(float v, int src, int lane_base) {
+    return __shfl_sync(kFull, v, lane_base + src);
+}
+
+// Forward quantities shared by fwd and bwd.  Every lane of the group returns the same sums.
+template <int G>
+__device__ __forceinline__ void composite_core(const float* __restrict__ rgb, int rgb_stride,
+                                               const float* __restrict__ occ, int occ_stride,
+                                               const uint8_t* __restrict__ point_mask,
+                                               const float* __restrict__ z, int64_t ray, int S, int s,
+                                               bool active, float coef, int lane_base, RaySample& me,
+                                               float& wsum, float& depth, float& cr, float& cg, float& cb,
+                                               float& var) {
+    me = RaySample{0.f, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float t = 1.f;
+    if (active) {
+        const int64_t i = ray * S + s;
+        float o = __ldg(occ + i * occ_stride);
+        if (point_mask != nullptr && point_mask[i] == 0) o = -100.0f;
+        me.alpha = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-__fmul_rn(coef, o))));
+        t = __fadd_rn(__fsub_rn(1.0f, me.alpha), 1e-10f);
+        me.z = __ldg(z + i);
+        if (rgb != nullptr) {
+            me.r = __ldg(rgb + i * rgb_stride + 0);
+            me.g = __ldg(rgb + i * rgb_stride + 1);
+            me.b = __ldg(rgb + i * rgb_stride + 2);
+        }
+    }
+    float T = 1.f;
+    for (int j = 0; j < S - 1; ++j) {
+        const float tj = group_bcast<G>(t, j, lane_base);
+        if (j < s) T = __fmul_rn(T, tj);
+    }
+    me.trans = T;
+    me.w = active ? __fmul_rn(me.alpha, T) : 0.f;
+    float sw = 0.f, swz = 0.f, sr = 0.f, sg = 0.f, sb = 0.f;
+    for (int j = 0; j < S; ++j) {
+        const float wj = group_bcast<G>(me.w, j, lane_base);
+        sw = __fadd_rn(sw, wj);
+        swz = __fadd_rn(swz, __fmul_rn(wj, group_bcast<G>(me.z, j, lane_base)));
+        sr = __fadd_rn(sr, __fmul_rn(wj, group_bcast<G>(me.r, j, lane_base)));
+        sg = __fadd_rn(sg, __fmul_rn(wj, group_bcast<G>(me.g, j, lane_base)));
+        sb = __fadd_rn(sb, __fmul_rn(wj, group_bcast<G>(me.b, j, lane_base)));
+    }
+    wsum = __fadd_rn(sw, 1e-10f);
+    depth = __fdiv_rn(swz, wsum);
+    cr = __fdiv_rn(sr, wsum);
+    cg = __fdiv_rn(sg, wsum);
+    cb = __fdiv_rn(sb, wsum);
+    const float dz = __fsub_rn(me.z, depth);
+    const float mine = __fmul_rn(__fmul_rn(me.w, dz), dz);
+    var = 0.f;
+    for (int j = 0; j < S; ++j) var = __fadd_rn(var, group_bcast<G>(mine, j, lane_base));
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+composite_fwd_kernel(const float* __restrict__ rgb, int rgb_stride, const float* __restrict__ occ,
+                     int occ_stride, const uint8_t* __restrict__ point_mask, const float* __restrict__ z,
+                     int64_t R, int S, float coef, float* __restrict__ depth_out, float* __restrict__ var_out,
+                     float* __restrict__ color_out, float* __restrict__ weights_out) {
+    constexpr int RPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int sub = lane / G, s = lane % G;
+    const int64_t ray_raw = warp * RPW + sub;
+    if (warp * RPW >= R) return;
+    const int64_t ray = ray_raw < R ? ray_raw : R - 1;   // keep whole warp converged for shuffles
+    const bool live = ray_raw < R;
+    const bool active = s < S;
+    RaySample me;
+    float wsum, depth, cr, cg, cb, var;
+    composite_core<G>(rgb, rgb_stride, occ, occ_stride, point_mask, z, ray, S, s, active, coef, sub * G, me,
+                      wsum, depth, cr, cg, cb, var);
+    if (!live) return;
+    if (active && weights_out != nullptr) weights_out[ray * S + s] = me.w;
+    if (s == 0) {
+        depth_out[ray] = depth;
+        var_out[ray] = var;
+        color_out[ray * 3 + 0] = cr;
+        color_out[ray * 3 + 1] = cg;
+        color_out[ray * 3 + 2] = cb;
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(256)
+composite_bwd_kernel(const float* __restrict__ rgb, int rgb_stride, const float* __restrict__ occ,
+                     int occ_stride, const uint8_t* __restrict__ point_mask, const float* __restrict__ z,
+                     int64_t R, int S, float coef, const float* __restrict__ g_depth,
+                     const float* __restrict__ g_color, float* __restrict__ d_rgb, int d_rgb_stride,
+                     float* __restrict__ d_occ, int d_occ_stride) {
+    constexpr int RPW = 32 / G;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int sub = lane / G, s = lane % G;
+    const int64_t ray_raw = warp * RPW + sub;
+    if (warp * RPW >= R) return;
+    const int64_t ray = ray_raw < R ? ray_raw : R - 1;
+    const bool live = ray_raw < R;
+    const bool active = s < S;
+    const int lane_base = sub * G;
+    RaySample me;
+    float wsum, depth, cr, cg, cb, var;
+    composite_core<G>(rgb, rgb_stride, occ, occ_stride, point_mask, z, ray, S, s, active, coef, lane_base, me,
+                      wsum, depth, cr, cg, cb, var);
+    const float gd = g_depth != nullptr ? __ldg(g_depth + ray) : 0.f;
+    float gr = 0.f, gg = 0.f, gb = 0.f;
+    if (g_color != nullptr) {
+        gr = __ldg(g_color + ray * 3 + 0);
+        gg = __ldg(g_color + ray * 3 + 1);
+        gb = __ldg(g_color + ray * 3 + 2);
+    }
+    const float gw = active ? (gd * (me.z - depth) + gr * (me.r - cr) + gg * (me.g - cg) + gb * (me.b - cb)) / wsum
+                            : 0.f;
+    const float gww = gw * me.w;
+    float suffix = 0.f;
+    for (int j = S - 1; j > 0; --j) {
+        const float v = group_bcast<G>(gww, j, lane_base);
+        if (j > s) suffix += v;
+    }
+    if (!live || !active) return;
+    const int64_t i = ray * S + s;
+    const float t = __fadd_rn(__fsub_rn(1.0f, me.alpha), 1e-10f);
+    const float dalpha = gw * me.trans - suffix / t;
+    d_occ[i * d_occ_stride] = dalpha * coef * me.alpha * (1.0f - me.alpha);
+    if (d_rgb != nullptr) {
+        const float k = me.w / wsum;
+        d_rgb[i * d_rgb_stride + 0] = gr * k;
+        d_rgb[i * d_rgb_stride + 1] = gg * k;
+        d_rgb[i * d_rgb_stride + 2] = gb * k;
+    }
+}
+
+}  // namespace hps
+
+extern "C" int hps_composite_fwd(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
+                                 const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
+                                 float* depth, float* var, float* color, float* weights, void* stream) {
+    using namespace hps;
+    HPS_REQUIRE(R >= 0 && S >= 1 && S <= 32, "need 1 <= S <= 32");
+    if (R == 0) return 0;
+    HPS_REQUIRE(occ && z && depth && var && color, "null buffer");
+    const int tb = 256;
+    if (S <= 8) {
+        const int64_t warps = ceil_div(R, 4);
+        composite_fwd_kernel<8><<<(unsigned)ceil_div(warps * 32, tb), tb, 0, (cudaStream_t)stream>>>(
+            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, depth, var, color, weights);
+    } else {
+        composite_fwd_kernel<32><<<(unsigned)ceil_div(R * 32, tb), tb, 0, (cudaStream_t)stream>>>(
+            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, depth, var, color, weights);
+    }
+    HPS_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int hps_composite_bwd(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
+                                 const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
+                                 const float* g_depth, const float* g_color, float* d_rgb, int d_rgb_stride,
+                                 float* d_occ, int d_occ_stride, void* stream) {
+    using namespace hps;
+    HPS_REQUIRE(R >= 0 && S >= 1 && S <= 32, "need 1 <= S <= 32");
+    if (R == 0) return 0;
+    HPS_REQUIRE(occ && z && d_occ, "null buffer");
+    HPS_REQUIRE(d_rgb == nullptr || rgb != nullptr, "d_rgb needs rgb");
+    const int tb = 256;
+    if (S <= 8) {
+        const int64_t warps = ceil_div(R, 4);
+        composite_bwd_kernel<8><<<(unsigned)ceil_div(warps * 32, tb), tb, 0, (cudaStream_t)stream>>>(
+            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, g_depth, g_color, d_rgb, d_rgb_stride,
+            d_occ, d_occ_stride);
+    } else {
+        composite_bwd_kernel<32><<<(unsigned)ceil_div(R * 32, tb), tb, 0, (cudaStream_t)stream>>>(
+            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, g_depth, g_color, d_rgb, d_rgb_stride,
+            d_occ, d_occ_stride);
+    }
+    HPS_LAUNCH_OK();
+    return 0;
+}

@@ -1,0 +1,183 @@
+"""Drop-in for the reference's src/conv_onet/models/decoder.py (NICER and its four point decoders).
+
+The nn.Modules stay the *parameter owners* with the reference's parameter names
+(`geo_decoder_{mid,fine}`, `color_decoder_{mid,fine}` . `fc_c.N`, `pts_linears.N`, `output_linear`,
+`embedder._B`, `embedder_rel_pos._B`, `mlp_col_neighbor.*`, `mlp_exposure.*`) so
+optimisers, state_dict() and checkpoints keep working; construction order and initialisers follow
+decoder.py:127-193 / :418-489 so that setup_seed(1219) yields the same random init.  All arithmetic of
+forward/backward is done by the hps_b200 kernels through ops.py:
+
+    NICER.forward(p, npc, stage, npc_geo_feats, npc_col_feats, pts_num, is_tracker, cloud_pos, normals,
+                  pts_views_d, dynamic_r_query, exposure_feat) -> raw (P,4), ray_mask (R,), point_mask (P,)
+
+follows decoder.py:660-723 for the four live stages; one neighbour query feeds the geometry and the
+colour interpolation (the reference issues two identical ones).
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+STAGES = ("geometry_mid", "geometry_fine", "color_mid", "color_fine")
+
+
+class FourierEmbedder(nn.Module):
+    """Holder of the projection matrix _B (decoder.py:24-34).  Learnable => Parameter; otherwise a plain
+    tensor attribute that is (as in the reference) absent from state_dict()."""
+
+    def __init__(self, dim, mapping_size, scale, learnable):
+        super().__init__()
+        self.mapping_size = mapping_size
+        b = torch.randn((dim, mapping_size)) * scale
+        self._B = nn.Parameter(b) if learnable else b
+
+    def matrix(self, device):
+        if self._B.device != device:
+            if isinstance(self._B, nn.Parameter):
+                raise RuntimeError("move the decoders to %s before rendering" % device)
+            self._B = self._B.to(device)
+        return self._B
+
+    def forward(self, x):   # kept for completeness (host-side use on small inputs only)
+        x = x.squeeze(0)
+        x = (2 * math.pi * x) @ self.matrix(x.device)
+        return torch.sin(x)
+
+
+class XavierLinear(nn.Linear):
+    """nn.Linear with xavier_uniform(gain(activation)) weights and zero bias (decoder.py:86-95)."""
+
+    def __init__(self, in_dim, out_dim, activation="relu"):
+        self._gain = nn.init.calculate_gain(activation)
+        super().__init__(in_dim, out_dim)
+
+    def reset_parameters(self):
+        nn.init.xavier_uniform_(self.weight, gain=self._gain)
+        nn.init.zeros_(self.bias)
+
+
+class _TwoLayer(nn.Module):
+    """linear1 -> Softplus(100) -> linear2 (MLP_col_neighbor decoder.py:361-377, MLP_exposure :380-396)."""
+
+    def __init__(self, n_in, hidden, n_out, init):
+        super().__init__()
+        self.linear1 = nn.Linear(n_in, hidden)
+        self.linear2 = nn.Linear(hidden, n_out)
+        self.act_fn = nn.Softplus(beta=100)
+        for lin in (self.linear1, self.linear2):
+            init(lin.weight)
+
+    def forward(self, x):
+        return self.linear2(self.act_fn(self.linear1(x)))
+
+
+class PointDecoder(nn.Module):
+    """MLP_geometry (kind 'geo') / MLP_color (kind 'col') as a parameter owner + kernel caller."""
+
+    def __init__(self, cfg, kind, name, level, c_dim=32, hidden_size=128, n_blocks=5, skips=(2,)):
+        super().__init__()
+        assert kind in ("geo", "col") and n_blocks == 5 and tuple(skips) == (2,) and c_dim == ops.C_DIM
+        self.kind, self.name, self.level = kind, name, level
+        self.c_dim, self.n_blocks, self.skips = c_dim, n_blocks, list(skips)
+        self.min_nn_num = cfg["pointcloud"]["min_nn_num"]
+        self.N_surface = cfg["rendering"]["N_surface"]
+        self.use_dynamic_radius = cfg["use_dynamic_radius"]
+        self.encode_exposure = cfg["model"].get("encode_exposure", False) if kind == "col" else False
+        if cfg["pointcloud"]["nn_weighting"] != "distance":
+            raise NotImplementedError("only nn_weighting='distance' is built (the ScanNet configuration)")
+        if cfg["model"].get("encode_rel_pos_in_col" if kind == "col" else "encode_rel_pos_in_geo", False):
+            raise NotImplementedError("encode_rel_pos_* is off in the ScanNet configuration and not built")
+        if cfg.get("use_normals", False) or cfg.get("use_view_direction", False):
+            raise NotImplementedError("normals / view directions are off in the ScanNet configuration")
+        # --- construction order == reference (RNG-stream parity under a fixed seed) ---
+        self.fc_c = nn.ModuleList([nn.Linear(c_dim, hidden_size) for _ in range(n_blocks)])
+        if kind == "geo":
+            emb = 93
+            self.embedder = FourierEmbedder(3, emb, 25, learnable=True)
+            embedding_input = emb
+        else:
+            emb = 20
+            self.embedder = FourierEmbedder(3, emb, 32, learnable=False)
+            embedding_input = 2 * emb
+        self.embedder_rel_pos = FourierEmbedder(3, 10, 32, learnable=True)
+        self.mlp_col_neighbor = _TwoLayer(c_dim + 20, hidden_size, c_dim, nn.init.xavier_uniform_)
+        if self.encode_exposure:
+            self.mlp_exposure = _TwoLayer(cfg["model"]["exposure_dim"], hidden_size, 12,
+                                          lambda w: nn.init.normal_(w, mean=0, std=0.01))
+        self.pts_linears = nn.ModuleList(
+            [XavierLinear(embedding_input, hidden_size)] +
+            [XavierLinear(hidden_size + (embedding_input if i in self.skips else 0), hidden_size)
+             for i in range(n_blocks - 1)])
+        self.output_linear = XavierLinear(hidden_size, 1 if kind == "geo" else 3,
+                                          activation="relu" if kind == "geo" else "linear")
+        self.hidden_size = hidden_size
+        expect = 32 if kind == "geo" else 128
+        if hidden_size != expect:
+            raise NotImplementedError("kernels are built for hidden sizes 32 (geometry) / 128 (colour)")
+
+    def kernel_params(self, device):
+        """[B, (W_i, b_i, Wc_i, bc_i) x5, Wo, bo] - the tensors themselves (autograd leaves)."""
+        out = [self.embedder.matrix(device)]
+        for i in range(self.n_blocks):
+            out += [self.pts_linears[i].weight, self.pts_linears[i].bias, self.fc_c[i].weight, self.fc_c[i].bias]
+        out += [self.output_linear.weight, self.output_linear.bias]
+        return out
+
+    def forward(self, p, c, exposure_feat=None):
+        """p (P,3), c (P,32) already interpolated.  geo -> occ (P,);  col -> rgb (P,3)."""
+        affine = None
+        if self.kind == "col" and self.encode_exposure:
+            if exposure_feat is not None:
+                affine = self.mlp_exposure(exposure_feat)          # (12,)  decoder.py:608
+        elif self.kind == "col":
+            raise NotImplementedError("encode_exposure=False colour tail is not built")
+        return ops.mlp(ops.MLP_GEO if self.kind == "geo" else ops.MLP_COL, p, c,
+                       self.kernel_params(c.device), affine)
+
+
+class NICER(nn.Module):
+    """Stage dispatcher (decoder.py:621-723)."""
+
+    def __init__(self, cfg, dim=3, c_dim=32, hidden_size=128, pos_embedding_method="fourier",
+                 use_normals=False, use_view_direction=False):
+        super().__init__()
+        assert dim == 3 and pos_embedding_method == "fourier"
+        self.geo_decoder_mid = PointDecoder(cfg, "geo", "geometry_mid", "mid", c_dim, 32)
+        self.geo_decoder_fine = PointDecoder(cfg, "geo", "geometry_fine", "fine", c_dim, 32)
+        self.color_decoder_mid = PointDecoder(cfg, "col", "color_mid", "mid", c_dim, hidden_size)
+        self.color_decoder_fine = PointDecoder(cfg, "col", "color_fine", "fine", c_dim, hidden_size)
+        # Explicit stand-in for the reference's per-call normal_(0, 0.01) draws for no-neighbour points
+        # (decoder.py:262-263, 549-550).  None => drawn per call on the device like the reference.
+        self.c_fill_geo = None
+        self.c_fill_col = None
+
+    def _fill(self, which, device):
+        v = self.c_fill_geo if which == "geo" else self.c_fill_col
+        if v is None:
+            return torch.zeros(ops.C_DIM, device=device).normal_(mean=0, std=0.01)
+        return v.to(device=device, dtype=torch.float32)
+
+    def forward(self, p, npc, stage, npc_geo_feats, npc_col_feats, pts_num=16, is_tracker=False, cloud_pos=None,
+                normals=None, pts_views_d=None, dynamic_r_query=None, exposure_feat=None):
+        if stage not in STAGES:
+            raise NotImplementedError("stage %r: only %s are live in the reference" % (stage, STAGES))
+        level = "mid" if stage.endswith("mid") else "fine"
+        p = p.reshape(-1, 3)
+        radius = dynamic_r_query[level] if dynamic_r_query is not None else None
+        q = npc.query_neighbors(p.detach(), step="query", dynamic_radius=radius, level=level)
+        geo = getattr(self, "geo_decoder_" + level)
+        color_stage = stage.startswith("color")
+        pos = cloud_pos[level] if is_tracker else None
+        c_geo, c_col, has = ops.interpolate(
+            p, npc_geo_feats[level], npc_col_feats[level] if color_stage else None, pos,
+            q.I, q.D, q.t_dn, q.count, self._fill("geo", p.device),
+            self._fill("col", p.device) if color_stage else None, geo.min_nn_num, is_tracker)
+        ray_mask = ~(has.view(-1, pts_num).sum(1) < int(geo.N_surface / 2 + 1))      # decoder.py:310-311
+        occ = geo(p, c_geo)
+        if not color_stage:
+            raw = torch.cat([torch.zeros(occ.shape[0], 3, device=occ.device), occ[:, None]], -1)
+            return raw, ray_mask, has
+        rgb = getattr(self, "color_decoder_" + level)(p, c_col, exposure_feat)
+        return torch.cat([rgb, occ[:, None]], -1), ray_mask, has

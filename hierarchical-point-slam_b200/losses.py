@@ -1,0 +1,25 @@
+"""Mapper / Tracker losses of the hot path (reference Mapper.py:791-856, Tracker.py:213-231) as small
+torch expressions over the renderer's outputs; backward() then drives the kernels' backward passes."""
+import torch
+
+
+def mapper_loss(depth, color, valid_ray_mask, gt_depth, gt_color, stage, w_color_loss=0.1, affine=None):
+    """affine: (12,) exposure tensor of the (single) frame the batch comes from, or None."""
+    mask = (gt_depth > 0) & valid_ray_mask & (~torch.isnan(depth))
+    loss = torch.abs(gt_depth[mask] - depth[mask]).sum()
+    if stage.startswith("color"):
+        if affine is not None:
+            color = torch.matmul(color, affine[:9].reshape(3, 3)) + affine[-3:]
+        color = torch.sigmoid(color)
+        loss = loss + w_color_loss * torch.abs(gt_color[mask] - color[mask]).sum()
+    return loss
+
+
+def tracker_loss(depth, uncertainty, color, gt_depth, gt_color, w_color_loss=0.5):
+    uncertainty = uncertainty.detach()
+    nan_mask = (~torch.isnan(depth)) & (~torch.isnan(uncertainty))
+    tmp = torch.abs(gt_depth - depth) / torch.sqrt(uncertainty + 1e-10)
+    mask = (tmp < 10 * tmp.mean()) & (gt_depth > 0) & nan_mask
+    geo_loss = torch.clamp(tmp, min=0.0, max=1e3)[mask].sum()
+    color_loss = torch.abs(gt_color - color)[mask].sum()
+    return geo_loss + w_color_loss * color_loss

@@ -1,0 +1,315 @@
+"""Drop-in for the reference's src/neural_point.py: NeuralPointCloud with a device-resident store and an
+exact hashed-voxel-grid neighbour index instead of faiss IVFFlat.
+
+Kept from the reference: constructor argument (cfg), the per-level dict state
+(`geo_feats`, `col_feats`, `index`, `_pts_num`), and the methods other reference modules call:
+`find_neighbors_faiss(pos, step, retrain, is_pts_grad, dynamic_radius, level) -> (D f32 (P,8), I i64 (P,8),
+neighbor_num i32 (P,))`, `add_neural_points(...)`, `cloud_pos(level)`, `get_geo_feats/get_col_feats`,
+`update_geo_feats/update_col_feats`, `index_ntotal(level)`, `get_index(level)` and the index object's
+faiss-like surface (`is_trained`, `train`, `add`, `search`, `ntotal`, `nprobe`).
+
+Changed on purpose: positions live in one (N,3) fp32 device tensor per level (the reference keeps a
+Python list of lists and re-tensorises it every iteration, neural_point.py:301, Mapper.py:779); the
+search is exact (== the reference with nprobe = nlist) and returns -1 / FLT_MAX in slots outside the
+query radius, which the reference always weights with 0 (decoder.py:235-236, SURVEY 7 "hard parts").
+"""
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from . import ops
+
+NeighborQuery = namedtuple("NeighborQuery", "I D count t_up t_dn")
+
+
+class CloudPositions(torch.Tensor):
+    """(N,3) device tensor that still converts like the reference's list: np.array(x) / x.tolist()."""
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.detach().cpu().as_subclass(torch.Tensor).numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+
+class GridIndex:
+    """faiss-like facade over ops.VoxelHashGrid for one level."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.is_trained = False
+        self.nprobe = 1                       # accepted and ignored: the search is exact
+        self._pos = torch.zeros(0, 3, dtype=torch.float32, device=self.device)
+        self._grid = None
+        self._grid_n = -1
+        self._cell = None
+        # Voxel edge.  When set (NeuralPointCloud derives it from the level's largest query radius) no
+        # host sync is needed per query; when None it is derived from each batch's largest radius.
+        self.cell_hint = None
+
+    @property
+    def ntotal(self):
+        return int(self._pos.shape[0])
+
+    def train(self, x=None):
+        self.is_trained = True
+
+    def add(self, x):
+        x = torch.as_tensor(x, dtype=torch.float32, device=self.device).reshape(-1, 3)
+        self._pos = torch.cat([self._pos, x.detach()], 0)
+
+    def reset(self, pos):
+        self._pos = torch.as_tensor(pos, dtype=torch.float32, device=self.device).reshape(-1, 3).detach().clone()
+        self.is_trained = True
+        self._grid_n = -1
+
+    @property
+    def positions(self):
+        return self._pos
+
+    def _ensure_grid(self, t_dn):
+        """(Re)build when points were appended or the cell size is badly matched to the query radius."""
+        stale = self._grid is None or self._grid_n != self.ntotal
+        if self.cell_hint is not None:
+            want = float(self.cell_hint)
+            stale = stale or want != self._cell
+        else:
+            r_max = float(torch.sqrt(t_dn.max()).item()) if t_dn.numel() else 1.0   # one scalar sync
+            want = max(r_max * 0.5, 1e-4)
+            if not stale and not (0.5 * self._cell <= want <= 2.0 * self._cell):
+                stale = True
+            elif not stale:
+                want = self._cell
+        if stale:
+            if self._grid is None:
+                self._grid = ops.VoxelHashGrid()
+            self._grid.build(self._pos, want)
+            self._grid_n, self._cell = self.ntotal, want
+        return self._grid
+
+    def radius_search(self, q, radius, want_cand=False):
+        """Exact 8-NN limited to `radius` (float or per-query tensor, float64 semantics)."""
+        q = q.detach().to(device=self.device, dtype=torch.float32).reshape(-1, 3)
+        t_up, t_dn = ops.radius_thresholds(radius, q.shape[0], self.device)
+        grid = self._ensure_grid(t_dn)
+        res = grid.query(q, t_up, t_dn, want_cand)
+        out = NeighborQuery(res[0], res[1], res[2], t_up, t_dn)
+        return (out, res[3]) if want_cand else out
+
+    def search(self, x, k=ops.K_NN):
+        """Unbounded k-NN (faiss Index.search semantics) by doubling the radius until every query has k
+        neighbours or the radius covers the whole cloud."""
+        assert k == ops.K_NN, "the kernels are built for nn_num = 8"
+        x = x.detach().to(device=self.device, dtype=torch.float32).reshape(-1, 3)
+        Q = x.shape[0]
+        D = torch.full((Q, k), torch.finfo(torch.float32).max, device=self.device)
+        I = torch.full((Q, k), -1, dtype=torch.int64, device=self.device)
+        if Q == 0 or self.ntotal == 0:
+            return D, I
+        lo, hi = self._pos.min(0).values, self._pos.max(0).values
+        span = float(torch.maximum((hi - lo).norm() + (x - lo).norm(dim=1).max(), torch.tensor(1e-3)).item())
+        todo = torch.arange(Q, device=self.device)
+        r = max(span / 64.0, 1e-3)
+        while todo.numel():
+            nq = self.radius_search(x[todo], r)
+            full = (nq.count >= min(k, self.ntotal)) | (r > span)
+            done = todo[full]
+            D[done], I[done] = nq.D[full], nq.I[full].long()
+            todo = todo[~full]
+            r *= 2.0
+        return D, I
+
+
+class NeuralPointCloud(object):
+    def __init__(self, cfg):
+        self.cfg = cfg
+        self.c_dim = cfg["model"]["c_dim"]
+        self.device = cfg["mapping"]["device"]
+        self.cuda_id = 0
+        self.use_dynamic_radius = cfg["use_dynamic_radius"]
+        pc = cfg["pointcloud"]
+        self.nn_num = pc["nn_num"]
+        if self.nn_num != ops.K_NN or self.c_dim != ops.C_DIM:
+            raise NotImplementedError("kernels are built for nn_num=8, c_dim=32 (the reference configuration)")
+        self.nlist, self.nprobe = pc["nlist"], pc["nprobe"]
+        self.radius_add, self.radius_min = pc["radius_add"], pc["radius_min"]
+        self.radius_query, self.radius_mesh = pc["radius_query"], pc["radius_mesh"]
+        self.add_along_normals = pc["add_along_normals"]
+        self.fix_interval_when_add_along_ray = pc["fix_interval_when_add_along_ray"]
+        self.N_add = pc["N_add"]
+        self.near_end_surface, self.far_end_surface = pc["near_end_surface"], pc["far_end_surface"]
+        self.radius_hierarchy = pc["radius_hierarchy"]
+        self.N_samples, self.N_surface = cfg["rendering"]["N_samples"], cfg["rendering"]["N_surface"]
+        self._pts_num = {}
+        self.geo_feats = {}
+        self.col_feats = {}
+        self.index = {}
+        self._cloud_normal = {}
+        self._input_pos = []
+        self._input_rgb = []
+        self.keyframe_dict = []
+
+    # ---- reference accessors ----------------------------------------------------------------
+    def cloud_pos(self, level, index=None):
+        pos = self.index[level].positions.as_subclass(CloudPositions)
+        return pos if index is None else pos[index]
+
+    def cloud_pos_tensor(self, level):
+        """The (N,3) device tensor itself (what Mapper.py:779 / Tracker.py:257 rebuild every time)."""
+        return self.index[level].positions
+
+    def cloud_normal(self, level=None):
+        return self._cloud_normal[level]
+
+    def input_pos(self):
+        return torch.cat(self._input_pos).tolist() if self._input_pos else []
+
+    def input_rgb(self):
+        return torch.cat(self._input_rgb).tolist() if self._input_rgb else []
+
+    def pts_num(self):
+        return self._pts_num
+
+    def set_keyframe_dict(self, value):
+        self.keyframe_dict = value
+
+    def get_keyframe_dict(self):
+        return self.keyframe_dict
+
+    def get_index(self, level=None):
+        return self.index[level]
+
+    def index_ntotal(self, level):
+        return self.index[level].ntotal
+
+    def get_device(self):
+        return self.device
+
+    def get_c_dim(self):
+        return self.c_dim
+
+    def get_radius_query(self):
+        return self.radius_query
+
+    def get_radius_add(self):
+        return self.radius_add
+
+    def get_geo_feats(self, level=None):
+        return self.geo_feats[level]
+
+    def get_col_feats(self, level=None):
+        return self.col_feats[level]
+
+    def _update(self, table, feats, indices, level):
+        assert torch.is_tensor(feats), "use tensor to update features"
+        if indices is not None:
+            table[level][indices] = feats.clone().detach()
+        else:
+            assert feats.shape[0] == table[level].shape[0], "feature shape[0] mismatch"
+            table[level] = feats.clone().detach()
+
+    def update_geo_feats(self, feats, indices=None, level=None):
+        self._update(self.geo_feats, feats, indices, level)
+
+    def update_col_feats(self, feats, indices=None, level=None):
+        self._update(self.col_feats, feats, indices, level)
+
+    # ---- building ------------------------------------------------------------------------------
+    def _init_level(self, level):
+        self._cloud_normal.setdefault(level, [])
+        self._pts_num.setdefault(level, 0)
+        if level not in self.index:
+            self.index[level] = GridIndex(self.device)
+            self.index[level].nprobe = self.nprobe
+            self.index[level].cell_hint = self._cell_for(level)
+        self.geo_feats.setdefault(level, None)
+        self.col_feats.setdefault(level, None)
+
+    def _cell_for(self, level):
+        """Voxel edge = half the largest query radius of the level (fine 0.16 m -> 0.08 m cells, mid
+        0.96 m -> 0.48 m): a query ball then overlaps at most 5 cells per axis."""
+        if self.use_dynamic_radius and level in self.radius_hierarchy:
+            r_max = self.cfg["pointcloud"]["radius_query_ratio"] * max(self.radius_hierarchy[level].values())
+        else:
+            r_max = self.radius_query
+        return 0.5 * float(r_max)
+
+    def set_cloud(self, level, pos, geo_feats=None, col_feats=None):
+        """Install a whole level at once (tests / benchmarks / checkpoint restore)."""
+        self._init_level(level)
+        self.index[level].reset(pos)
+        n = self.index[level].ntotal
+        self._pts_num[level] = n
+        dev = self.index[level].device
+        mk = lambda: torch.zeros(n, self.c_dim, device=dev).normal_(mean=0, std=0.1)
+        self.geo_feats[level] = mk() if geo_feats is None else geo_feats.to(dev).float().contiguous()
+        self.col_feats[level] = mk() if col_feats is None else col_feats.to(dev).float().contiguous()
+
+    def add_neural_points(self, batch_rays_o, batch_rays_d, batch_gt_depth, batch_gt_color, normals=None,
+                          train=False, is_pts_grad=False, dynamic_radius=None, level=None, idx=None):
+        """Reference neural_point.py:193-334, entirely on the device: unproject, density test with the
+        'add' radius, append N_add points per accepted location, extend the feature tables."""
+        if idx == 0 or level not in self.index:
+            self._init_level(level)
+        if normals is not None:
+            raise NotImplementedError("use_normals is off in the ScanNet configuration and not built")
+        if self.add_along_normals or self.fix_interval_when_add_along_ray:
+            raise NotImplementedError("only the depth-proportional add-along-ray mode is built")
+        if not batch_rays_o.shape[0]:
+            return 0
+        index = self.index[level]
+        dev = index.device
+        mask = batch_gt_depth > 0
+        o, d = batch_rays_o[mask].float(), batch_rays_d[mask].float()
+        depth, color = batch_gt_depth[mask].float(), (batch_gt_color * 255)[mask]
+        if dynamic_radius is not None:
+            dynamic_radius = dynamic_radius.reshape(-1)[mask] if dynamic_radius.numel() == mask.numel() \
+                else dynamic_radius
+        pts_gt = (o[..., None, :] + d[..., None, :] * depth[..., None, None]).reshape(-1, 3)
+        self._input_pos.append(pts_gt.detach())
+        self._input_rgb.append(color.detach())
+        t = torch.linspace(0.0, 1.0, steps=self.N_add, device=dev)
+        gds = depth.unsqueeze(-1).repeat(1, self.N_add)
+        z_vals = self.near_end_surface * gds * (1.0 - t) + self.far_end_surface * gds * t \
+            if self.N_add > 1 else depth.unsqueeze(-1)
+        keep = torch.ones(pts_gt.shape[0], dtype=torch.bool, device=dev)
+        if index.is_trained and index.ntotal > 0:
+            _, _, n_near = self.find_neighbors_faiss(pts_gt, step="add", is_pts_grad=is_pts_grad,
+                                                     dynamic_radius=dynamic_radius, level=level)
+            keep = n_near == 0
+        pts = (o[..., None, :] + d[..., None, :] * z_vals[..., :, None])[keep].reshape(-1, 3)
+        index.train()
+        index.add(pts)
+        self._pts_num[level] += pts.shape[0]
+        new = lambda: torch.zeros(pts.shape[0], self.c_dim, device=dev).normal_(mean=0, std=0.1)
+        if self.geo_feats[level] is None:
+            self.geo_feats[level], self.col_feats[level] = new(), new()
+        else:
+            self.geo_feats[level] = torch.cat([self.geo_feats[level], new()], 0)
+            self.col_feats[level] = torch.cat([self.col_feats[level], new()], 0)
+        return torch.sum(keep)
+
+    # ---- neighbour queries -----------------------------------------------------------------------
+    def _radius_for(self, step, is_pts_grad):
+        assert step in ["add", "query", "mesh"]
+        if step == "query":
+            return self.radius_query
+        if step == "add":
+            return self.radius_min if is_pts_grad else self.radius_add
+        return self.radius_mesh
+
+    def query_neighbors(self, pos, step="query", is_pts_grad=False, dynamic_radius=None, level=None,
+                        want_cand=False):
+        """Kernel-facing form: NeighborQuery(I i32 (P,8), D, count, t_up, t_dn)."""
+        radius = dynamic_radius if dynamic_radius is not None else self._radius_for(step, is_pts_grad)
+        if dynamic_radius is not None:
+            assert pos.shape[0] == dynamic_radius.shape[0], "shape mis-match for input points and dynamic radius"
+        return self.index[level].radius_search(pos, radius, want_cand)
+
+    def find_neighbors_faiss(self, pos, step="add", retrain=False, is_pts_grad=False, dynamic_radius=None,
+                             level=None):
+        """Reference signature (neural_point.py:366-417)."""
+        q = self.query_neighbors(pos, step, is_pts_grad, dynamic_radius, level)
+        return q.D, q.I.long(), q.count
+
+    def sample_near_pcl(self, *a, **k):
+        raise NotImplementedError("rendering.sample_near_pcl is False in the ScanNet configuration (SURVEY 8f-4)")

@@ -1,0 +1,292 @@
+"""Operator layer: torch tensors in, C-ABI kernel calls out, autograd wiring around them.
+
+PyTorch is plumbing here (device memory, streams, autograd graph); every floating-point operation of
+the hot path runs in libhps_b200.so.  No op has a fallback: non-CUDA tensors raise.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+K_NN = 8
+C_DIM = 32
+MLP_GEO, MLP_COL = 0, 1
+N_PARAM = 23
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.HpsError("hps_b200 ops need CUDA tensors (got %s); there is no CPU fallback" % t.device)
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# radius thresholds: fp32 equivalents of the reference's float64 comparisons
+# --------------------------------------------------------------------------------------------------
+def radius_thresholds(radius, n, device):
+    """radius: python float or tensor ((n,), (n,1); float64 in the reference) -> (t_up, t_dn) fp32 (n,).
+
+    D < r64^2  <=>  D < t_up ;   D > r64^2  <=>  D > t_dn   for every fp32 D."""
+    if torch.is_tensor(radius):
+        r2 = radius.detach().to(device=device, dtype=torch.float64).reshape(-1) ** 2
+        if r2.numel() != n:
+            raise ValueError("shape mis-match for input points and dynamic radius")
+    else:
+        r2 = torch.full((n,), float(radius) ** 2, dtype=torch.float64, device=device)
+    t = r2.to(torch.float32)
+    inf = torch.tensor(float("inf"), device=device)
+    t_dn = torch.where(t.double() > r2, torch.nextafter(t, -inf), t)
+    t_up = torch.where(t.double() < r2, torch.nextafter(t, inf), t)
+    return t_up.contiguous(), t_dn.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# neighbour index
+# --------------------------------------------------------------------------------------------------
+class VoxelHashGrid:
+    """Owner of one hps_grid_t handle (one per hierarchy level)."""
+
+    def __init__(self):
+        lib = _lib.load()
+        h = ctypes.c_void_p()
+        _lib.check(lib.hps_grid_create(ctypes.byref(h)))
+        self._h = h
+        self.n = 0
+        self.cell = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                _lib.load().hps_grid_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def build(self, pos, cell):
+        _need_cuda(pos)
+        pos = _f32c(pos).reshape(-1, 3)
+        with torch.cuda.device(pos.device):
+            _lib.check(_lib.load().hps_grid_build(self._h, _lib.ptr(pos), pos.shape[0], float(cell), _stream()))
+        self._keep = pos            # keep the source alive until the stream has consumed it
+        self.n = pos.shape[0]
+        self.cell = float(cell)
+
+    def info(self):
+        n, T, nc, cell, st = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_float(), ctypes.c_int()
+        _lib.check(_lib.load().hps_grid_info(self._h, ctypes.byref(n), ctypes.byref(T), ctypes.byref(nc),
+                                             ctypes.byref(cell), ctypes.byref(st), _stream()))
+        return dict(n_points=n.value, table_size=T.value, n_cells=nc.value, cell_size=cell.value, status=st.value)
+
+    def query(self, q, t_up, t_dn, want_cand=False):
+        """q (Q,3) -> I (Q,8) int32, D (Q,8) f32, count (Q,) int32 [, cand (Q,) int32]."""
+        _need_cuda(q, t_up, t_dn)
+        q = _f32c(q).reshape(-1, 3)
+        Q = q.shape[0]
+        I = torch.empty(Q, K_NN, dtype=torch.int32, device=q.device)
+        D = torch.empty(Q, K_NN, dtype=torch.float32, device=q.device)
+        cnt = torch.empty(Q, dtype=torch.int32, device=q.device)
+        cand = torch.empty(Q, dtype=torch.int32, device=q.device) if want_cand else None
+        with torch.cuda.device(q.device):
+            _lib.check(_lib.load().hps_knn_query(self._h, _lib.ptr(q), _lib.ptr(t_up), _lib.ptr(t_dn), Q,
+                                                 _lib.ptr(I), _lib.ptr(D), _lib.ptr(cnt), _lib.ptr(cand), _stream()))
+        return (I, D, cnt, cand) if want_cand else (I, D, cnt)
+
+
+# --------------------------------------------------------------------------------------------------
+# inverse-distance interpolation
+# --------------------------------------------------------------------------------------------------
+class _Interp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, feats_a, feats_b, cloud_pos, I, D, t_dn, count, fill_a, fill_b, min_nn, tracker):
+        _need_cuda(p, feats_a, feats_b, I, D, t_dn, count, fill_a)
+        P = I.shape[0]
+        dev = I.device
+        p_c = _f32c(p).reshape(-1, 3)
+        fa = _f32c(feats_a)
+        fb = _f32c(feats_b) if feats_b is not None else None
+        pos = _f32c(cloud_pos).reshape(-1, 3) if tracker else None
+        w = torch.empty(P, K_NN, dtype=torch.float32, device=dev)
+        c_a = torch.empty(P, C_DIM, dtype=torch.float32, device=dev)
+        c_b = torch.empty(P, C_DIM, dtype=torch.float32, device=dev) if fb is not None else None
+        has = torch.empty(P, dtype=torch.uint8, device=dev)
+        fill_a = _f32c(fill_a)
+        fill_b = _f32c(fill_b) if fill_b is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().hps_interp_fwd(
+                _lib.ptr(p_c), _lib.ptr(I), _lib.ptr(D), _lib.ptr(t_dn), _lib.ptr(count), _lib.ptr(pos),
+                _lib.ptr(fa), _lib.ptr(fb), _lib.ptr(fill_a), _lib.ptr(fill_b), P, int(min_nn),
+                _lib.ptr(w), _lib.ptr(c_a), _lib.ptr(c_b), _lib.ptr(has), _stream()))
+        ctx.save_for_backward(p_c, fa, fb, pos, I, w, has, c_a, c_b)
+        ctx.tracker = tracker
+        ctx.mark_non_differentiable(has)
+        if c_b is None:
+            c_b = torch.empty(0, device=dev)
+            ctx.mark_non_differentiable(c_b)
+        return c_a, c_b, has
+
+    @staticmethod
+    def backward(ctx, dc_a, dc_b, _dhas):
+        p_c, fa, fb, pos, I, w, has, c_a, c_b = ctx.saved_tensors
+        P = I.shape[0]
+        need_p, need_a, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        dc_a = _f32c(dc_a) if dc_a is not None else None
+        dc_b = _f32c(dc_b) if (dc_b is not None and fb is not None) else None
+        dfa = torch.zeros_like(fa) if (need_a and dc_a is not None) else None
+        dfb = torch.zeros_like(fb) if (need_b and dc_b is not None) else None
+        dp = torch.empty(P, 3, dtype=torch.float32, device=I.device) if (need_p and ctx.tracker) else None
+        if dfa is not None or dfb is not None or dp is not None:
+            with torch.cuda.device(I.device):
+                _lib.check(_lib.load().hps_interp_bwd(
+                    _lib.ptr(p_c), _lib.ptr(I), _lib.ptr(w), _lib.ptr(has), _lib.ptr(pos), _lib.ptr(fa),
+                    _lib.ptr(fb), _lib.ptr(c_a), _lib.ptr(c_b), _lib.ptr(dc_a), _lib.ptr(dc_b), P,
+                    _lib.ptr(dfa), _lib.ptr(dfb), _lib.ptr(dp), _stream()))
+        return dp, dfa, dfb, None, None, None, None, None, None, None, None, None
+
+
+def interpolate(p, feats_a, feats_b, cloud_pos, I, D, t_dn, count, fill_a, fill_b, min_nn=2, tracker=False):
+    """IDW features for up to two tables sharing one neighbour list.  Returns c_a, c_b|None, has (bool)."""
+    c_a, c_b, has = _Interp.apply(p, feats_a, feats_b, cloud_pos, I, D, t_dn, count, fill_a, fill_b, min_nn,
+                                  bool(tracker))
+    return c_a, (c_b if feats_b is not None else None), has.bool()
+
+
+# --------------------------------------------------------------------------------------------------
+# decoder MLPs
+# --------------------------------------------------------------------------------------------------
+def _ptr_array(ts):
+    arr = (ctypes.c_void_p * N_PARAM)()
+    for i, t in enumerate(ts):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+_packed_cache = {}
+
+
+def _packed_buffer(kind, device):
+    key = (kind, device)
+    buf = _packed_cache.get(key)
+    if buf is None:
+        buf = torch.empty(int(_lib.load().hps_mlp_packed_floats(kind)), dtype=torch.float32, device=device)
+        _packed_cache[key] = buf
+    return buf
+
+
+class _Mlp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, kind, p, c, affine, *params):
+        _need_cuda(p, c, affine, *params)
+        lib = _lib.load()
+        dev = c.device
+        P = c.shape[0]
+        p_c, c_c = _f32c(p).reshape(-1, 3), _f32c(c)
+        prm = [_f32c(t) for t in params]
+        aff = _f32c(affine) if affine is not None else None
+        nout = 1 if kind == MLP_GEO else 3
+        out = torch.empty((P,) if nout == 1 else (P, 3), dtype=torch.float32, device=dev)
+        need_grad = any(ctx.needs_input_grad)
+        act = None
+        if need_grad:
+            tiles = (P + 63) // 64
+            act = torch.empty(tiles * 64 * int(lib.hps_mlp_act_floats(kind)), dtype=torch.float32, device=dev)
+        packed = _packed_buffer(kind, dev)
+        arr = _ptr_array(prm)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hps_mlp_pack(kind, arr, _lib.ptr(packed), _stream()))
+            _lib.check(lib.hps_mlp_fwd(kind, arr, _lib.ptr(packed), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), P,
+                                       _lib.ptr(out), _lib.ptr(act), _stream()))
+        ctx.kind = kind
+        ctx.has_affine = aff is not None
+        ctx.save_for_backward(p_c, c_c, aff, act, *prm)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        p_c, c_c, aff, act = ctx.saved_tensors[:4]
+        prm = list(ctx.saved_tensors[4:])
+        kind, dev, P = ctx.kind, c_c.device, c_c.shape[0]
+        need = ctx.needs_input_grad          # (kind, p, c, affine, *params)
+        want_w = any(need[4 + i] for i in range(1, N_PARAM))
+        want_b = need[4] and kind == MLP_GEO
+        dprm = [None] * N_PARAM
+        if want_w:
+            dprm = [torch.zeros_like(t) for t in prm]
+            if not want_b:
+                dprm[0] = None
+        elif want_b:
+            raise _lib.HpsError("gradient w.r.t. embedder._B alone is not supported")
+        dc = torch.empty(P, C_DIM, dtype=torch.float32, device=dev)
+        dp = torch.empty(P, 3, dtype=torch.float32, device=dev) if need[1] else None
+        daff = torch.zeros(12, dtype=torch.float32, device=dev) if (ctx.has_affine and need[3]) else None
+        darr = _ptr_array(dprm) if want_w else None
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().hps_mlp_bwd(kind, _ptr_array(prm), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff),
+                                               _lib.ptr(act), _lib.ptr(_f32c(dout)), P, darr, _lib.ptr(dc),
+                                               _lib.ptr(dp), _lib.ptr(daff), _stream()))
+        grads = [g if (g is not None and need[4 + i]) else None for i, g in enumerate(dprm)]
+        return (None, dp, dc if need[2] else None, daff, *grads)
+
+
+def mlp(kind, p, c, params, affine=None):
+    """params: the 23 tensors [B, (W_i, b_i, Wc_i, bc_i) x5, Wo, bo] in the reference layouts."""
+    assert len(params) == N_PARAM
+    return _Mlp.apply(kind, p, c, affine, *params)
+
+
+# --------------------------------------------------------------------------------------------------
+# compositing
+# --------------------------------------------------------------------------------------------------
+class _CompositeRaw(torch.autograd.Function):
+    """raw (R,S,4) packed [rgb, occ]; point_mask (R*S,) uint8/bool or None; z (R,S)."""
+
+    @staticmethod
+    def forward(ctx, raw, z, point_mask, coef, want_weights):
+        _need_cuda(raw, z, point_mask)
+        R, S = z.shape
+        dev = raw.device
+        raw_c, z_c = _f32c(raw).reshape(R, S, 4), _f32c(z)
+        pm = point_mask.detach().to(torch.uint8).contiguous() if point_mask is not None else None
+        depth = torch.empty(R, dtype=torch.float32, device=dev)
+        var = torch.empty(R, dtype=torch.float32, device=dev)
+        color = torch.empty(R, 3, dtype=torch.float32, device=dev)
+        weights = torch.empty(R, S, dtype=torch.float32, device=dev) if want_weights else None
+        base = raw_c.data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().hps_composite_fwd(
+                ctypes.c_void_p(base), 4, ctypes.c_void_p(base + 12), 4, _lib.ptr(pm), _lib.ptr(z_c), R, S,
+                float(coef), _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), _lib.ptr(weights), _stream()))
+        ctx.save_for_backward(raw_c, z_c, pm)
+        ctx.coef = float(coef)
+        ctx.mark_non_differentiable(var)
+        if weights is None:
+            weights = torch.empty(0, device=dev)
+        ctx.mark_non_differentiable(weights)
+        return depth, var, color, weights
+
+    @staticmethod
+    def backward(ctx, g_depth, _g_var, g_color, _g_w):
+        raw_c, z_c, pm = ctx.saved_tensors
+        R, S = z_c.shape
+        d_raw = torch.empty_like(raw_c)
+        gd = _f32c(g_depth) if g_depth is not None else None
+        gc = _f32c(g_color) if g_color is not None else None
+        base, dbase = raw_c.data_ptr(), d_raw.data_ptr()
+        with torch.cuda.device(raw_c.device):
+            _lib.check(_lib.load().hps_composite_bwd(
+                ctypes.c_void_p(base), 4, ctypes.c_void_p(base + 12), 4, _lib.ptr(pm), _lib.ptr(z_c), R, S, ctx.coef,
+                _lib.ptr(gd), _lib.ptr(gc), ctypes.c_void_p(dbase), 4, ctypes.c_void_p(dbase + 12), 4, _stream()))
+        return d_raw, None, None, None, None
+
+
+def composite(raw, z, point_mask=None, coef=0.1, want_weights=False):
+    depth, var, color, w = _CompositeRaw.apply(raw, z, point_mask, coef, want_weights)
+    return depth, var, color, (w if want_weights else None)

@@ -1,0 +1,129 @@
+"""Drop-in for the reference's src/utils/Renderer.py (render_batch_ray / render_img / eval_points).
+
+Same constructor and call signatures.  Depth-guided sampling (Renderer.py:163-220) is kept as
+the same handful of torch elementwise expressions so that sample points are bit-identical to the
+reference's and autograd carries d/d pts into rays_o / rays_d for the tracker; neighbour search,
+interpolation, both decoders and compositing run in the hps_b200 kernels.
+"""
+import torch
+
+from . import ops
+from .common import get_rays
+
+
+class Renderer(object):
+    def __init__(self, cfg, args=None, slam=None, points_batch_size=500000, ray_batch_size=3000):
+        self.ray_batch_size = ray_batch_size
+        self.points_batch_size = points_batch_size
+        r = cfg["rendering"]
+        self.N_samples, self.N_surface = r["N_samples"], r["N_surface"]
+        self.near_end_surface, self.far_end_surface = r["near_end_surface"], r["far_end_surface"]
+        self.sample_near_pcl = r["sample_near_pcl"]
+        self.skip_zero_depth_pixel = r["skip_zero_depth_pixel"]
+        self.near_end = r["near_end"]
+        self.fix_interval = cfg["pointcloud"]["fix_interval_when_add_along_ray"]
+        self.occupancy = cfg["occupancy"]
+        self.use_dynamic_radius = cfg["use_dynamic_radius"]
+        self.use_bound = cfg["use_bound"]
+        self.crop_edge = 0 if cfg["cam"]["crop_edge"] is None else cfg["cam"]["crop_edge"]
+        self.sigmoid_coefficient = r.get("sigmoid_coef_mapper", 0.1)   # owners overwrite it (Mapper.py:51)
+        if self.N_samples > 0 or self.use_bound or self.sample_near_pcl or self.fix_interval or not self.occupancy:
+            raise NotImplementedError("only the reference's ScanNet rendering mode is built: N_samples=0, "
+                                      "use_bound False, sample_near_pcl False, occupancy True")
+        if slam is not None:
+            self.H, self.W, self.fx, self.fy, self.cx, self.cy = slam.H, slam.W, slam.fx, slam.fy, slam.cx, slam.cy
+
+    # Renderer.py:38-82
+    def eval_points(self, p, decoders, npc, stage=None, device=None, npc_geo_feats=None, npc_col_feats=None,
+                    is_tracker=False, cloud_pos=None, normals=None, pts_views_d=None, ray_pts_num=None,
+                    dynamic_r_query=None, exposure_feat=None):
+        assert torch.is_tensor(p)
+        step_pts = (self.points_batch_size // ray_pts_num) * ray_pts_num   # whole rays per chunk
+        rets, ray_masks, point_masks = [], [], []
+        for s in range(0, p.shape[0], step_pts):
+            rq = None
+            if dynamic_r_query is not None:
+                rq = {k: v[s:s + step_pts] for k, v in dynamic_r_query.items()}
+            ret, ray_mask, point_mask = decoders(p[s:s + step_pts], npc, stage, npc_geo_feats, npc_col_feats,
+                                                 ray_pts_num, is_tracker, cloud_pos, normals, pts_views_d, rq,
+                                                 exposure_feat)
+            rets.append(ret)
+            ray_masks.append(ray_mask)
+            point_masks.append(point_mask)
+        if len(rets) == 1:
+            return rets[0], ray_masks[0], point_masks[0]
+        return torch.cat(rets, 0), torch.cat(ray_masks, 0), torch.cat(point_masks, 0)
+
+    def surface_samples(self, gt_depth, device):
+        """z_vals (R,S) and the gt>0 mask: Renderer.py:122-210 for N_samples = 0."""
+        S = self.N_surface
+        gt = gt_depth.reshape(-1, 1)
+        nz = (gt > 0).squeeze(-1)
+        t = torch.linspace(0.0, 1.0, steps=S, device=device)
+        d = gt[nz].repeat(1, S)
+        z = torch.zeros(gt.shape[0], S, device=device)
+        z[nz, :] = self.near_end_surface * d * (1. - t) + self.far_end_surface * d * t
+        return z, nz
+
+    # Renderer.py:84-254
+    def render_batch_ray(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None,
+                         npc_geo_feats=None, npc_col_feats=None, is_tracker=False, cloud_pos=None,
+                         normals=None, dynamic_r_query=None, exposure_feat=None):
+        S = self.N_surface
+        N_rays = rays_o.shape[0]
+        if gt_depth is None or torch.numel(gt_depth) == 0:
+            gt_depth = torch.zeros(N_rays, device=device)
+        z_vals, nz = self.surface_samples(gt_depth, device)
+        n_zero = N_rays - int(nz.sum()) if not bool(nz.all()) else 0
+        if n_zero:                                                       # Renderer.py:133-134,148-153,207-208
+            gt = gt_depth.reshape(-1, 1)
+            far_bb = torch.minimum(5 * gt.mean(), torch.max(gt * 1.2))
+            far = torch.clamp(far_bb, 0, torch.max(gt * 1.2).item()) if torch.max(gt) > 0 else far_bb
+            z_vals[~nz, :] = torch.linspace(self.near_end, float(far), steps=S, device=device).repeat(n_zero, 1)
+        pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]      # Renderer.py:218-219
+        pointsf = pts.reshape(-1, 3)
+        rq = None
+        if self.use_dynamic_radius:
+            rq = {}
+            for key in dynamic_r_query.keys():                           # Renderer.py:226-229 (dict mutated)
+                dynamic_r_query[key] = dynamic_r_query[key].reshape(-1, 1).repeat_interleave(S, dim=0)
+                rq[key] = dynamic_r_query[key]
+        raw, valid_ray_mask, point_mask = self.eval_points(
+            pointsf, decoders, npc, stage, device, npc_geo_feats, npc_col_feats, is_tracker, cloud_pos, normals,
+            None, ray_pts_num=S, dynamic_r_query=rq, exposure_feat=exposure_feat)
+        # -100 overwrite for no-neighbour points and compositing, fused (Renderer.py:237-242)
+        depth, uncertainty, color, _ = ops.composite(raw.reshape(N_rays, S, 4), z_vals, point_mask,
+                                                     self.sigmoid_coefficient)
+        if not self.sample_near_pcl and n_zero:
+            depth = torch.where(nz, depth, torch.zeros_like(depth))     # Renderer.py:250-251
+        if self.skip_zero_depth_pixel and n_zero:
+            color = torch.where(nz[:, None], color, torch.zeros_like(color))
+        return depth, uncertainty, color, valid_ray_mask
+
+    # Renderer.py:256-337
+    def render_img(self, npc, decoders, c2w, device, stage, gt_depth=None, npc_geo_feats=None,
+                   npc_col_feats=None, normals=None, dynamic_r_query=None, cloud_pos=None, exposure_feat=None):
+        with torch.no_grad():
+            H, W = self.H, self.W
+            rays_o, rays_d = get_rays(H, W, self.fx, self.fy, self.cx, self.cy, c2w, device)
+            rays_o, rays_d = rays_o.reshape(-1, 3), rays_d.reshape(-1, 3)
+            if self.use_dynamic_radius:
+                for key in dynamic_r_query.keys():
+                    dynamic_r_query[key] = dynamic_r_query[key].reshape(-1, 1)
+            gt_depth = gt_depth.reshape(-1) if gt_depth is not None else None
+            depths, uncs, colors = [], [], []
+            B = self.ray_batch_size
+            for i in range(0, rays_d.shape[0], B):
+                rq = {k: v[i:i + B] for k, v in dynamic_r_query.items()} if self.use_dynamic_radius else None
+                d, u, c, _ = self.render_batch_ray(
+                    npc, decoders, rays_d[i:i + B], rays_o[i:i + B], device, stage,
+                    gt_depth=None if gt_depth is None else gt_depth[i:i + B], npc_geo_feats=npc_geo_feats,
+                    npc_col_feats=npc_col_feats, normals=normals, cloud_pos=cloud_pos, dynamic_r_query=rq,
+                    exposure_feat=exposure_feat)
+                depths.append(d.double())
+                uncs.append(u.double())
+                colors.append(c)
+            depth = torch.cat(depths, 0).reshape(H, W)
+            uncertainty = torch.cat(uncs, 0).reshape(H, W)
+            color = torch.cat(colors, 0).reshape(H, W, 3)
+            return depth, uncertainty, color

@@ -1,0 +1,121 @@
+/*
+ * hps_b200.h - C ABI of the B200-native render-and-optimise kernels for Hierarchical Point-SLAM.
+ *
+ * The reference (guo-han/Hierarchical-Point-SLAM) is pure Python/PyTorch + faiss-gpu: it has no FFI,
+ * plugin or operator registry for this path.  The seam it does have is its Python call signatures
+ * (SURVEY.md section 8b); each entry point below names the reference call site whose arithmetic it
+ * replaces.  The Python host side (package hierarchical-point-slam_b200) binds these with ctypes and
+ * re-exposes the reference signatures; INTEGRATION.md shows the binding a reference maintainer adds.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the parameter comment says "host";
+ *   - all tensors are contiguous row-major fp32 / int32 / uint8 as documented; sizes are explicit;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, no host sync inside
+ *     unless stated;
+ *   - return 0 on success, negative on error; hps_last_error() gives the message (thread-local);
+ *   - no hidden allocation except inside an hps_grid_t handle (grow-only, owned by the handle).
+ */
+#ifndef HPS_B200_H
+#define HPS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPS_K 8          /* nn_num (configs/point_slam.yaml:189) - compiled in                    */
+#define HPS_C 32         /* c_dim  (configs/point_slam.yaml:15)  - compiled in                    */
+#define HPS_MLP_GEO 0    /* MLP_geometry: E=93 (sin), hidden 32, ReLU, 1 output  (decoder.py:108)  */
+#define HPS_MLP_COL 1    /* MLP_color: E=40 (sin|cos), hidden 128, Softplus(100), 3 outputs (:399) */
+#define HPS_MLP_NPARAM 23 /* [B, (W_i, b_i, Wc_i, bc_i) i=0..4, Wo, bo]                            */
+
+typedef struct hps_grid hps_grid_t;
+
+const char* hps_last_error(void);
+int hps_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Neighbour index.  Replaces faiss.IndexIVFFlat train/add/search (neural_point.py:211-214,322-327,393)
+ * with an exact search: hashed voxel grid built on device + warp-per-query top-8.
+ * ---------------------------------------------------------------------------------------------- */
+int hps_grid_create(hps_grid_t** out);
+int hps_grid_destroy(hps_grid_t* g);
+/* (Re)build over n points pos[n][3].  cell_size > 0.  May cudaMalloc (grow-only).  Stream-ordered.  */
+int hps_grid_build(hps_grid_t* g, const float* pos, int64_t n, float cell_size, void* stream);
+/* Host-visible facts; synchronises `stream` to read the device status word.
+ * status bit0: a point fell outside the 21-bit cell range (cell_size too small for the extent).     */
+int hps_grid_info(const hps_grid_t* g, int64_t* n_points, int64_t* table_size, int64_t* n_cells,
+                  float* cell_size, int* status, void* stream);
+/* Exact radius-limited 8-NN of q[nq][3].
+ *   t_up[nq], t_dn[nq]: fp32 thresholds equivalent to the reference's float64 compares
+ *     (D < r^2  <=>  D < t_up, neural_point.py:412;  D > r^2  <=>  D > t_dn, decoder.py:236).
+ *   I[nq][8]   original point indices, ascending (D, index); unused slots -1
+ *   D[nq][8]   fl(fl(dx*dx+dy*dy)+dz*dz) fp32 without FMA; unused slots FLT_MAX
+ *   count[nq]  number of slots with D < t_up   (== reference neighbor_num)
+ *   cand[nq]   optional (may be NULL): candidates examined per query (for the roofline figure)
+ * Slots j < count are bit-identical to the reference's exhaustive search.                           */
+int hps_knn_query(const hps_grid_t* g, const float* q, const float* t_up, const float* t_dn,
+                  int64_t nq, int32_t* I, float* D, int32_t* count, int32_t* cand, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Inverse-distance interpolation (decoder.py:195-272 and :491-559; K2 in SURVEY 2.2).
+ * One neighbour list feeds up to two feature tables (geometry + colour).
+ *   cloud_pos != NULL selects the tracker variant: D is recomputed from cloud_pos[I]-p (decoder.py:
+ *   209-218) and the backward also produces dp.
+ *   w[P][8]: normalised weights (saved for the backward); has[P]: count >= min_nn.
+ * ---------------------------------------------------------------------------------------------- */
+int hps_interp_fwd(const float* p, const int32_t* I, const float* D, const float* t_dn,
+                   const int32_t* count, const float* cloud_pos,
+                   const float* feats_a, const float* feats_b,
+                   const float* fill_a, const float* fill_b, int64_t P, int min_nn,
+                   float* w, float* c_a, float* c_b, uint8_t* has, void* stream);
+/* dfeats_* (N,32) are ACCUMULATED into (atomic adds); dp (P,3) is written (tracker variant only). */
+int hps_interp_bwd(const float* p, const int32_t* I, const float* w, const uint8_t* has,
+                   const float* cloud_pos, const float* feats_a, const float* feats_b,
+                   const float* c_a, const float* c_b,
+                   const float* dc_a, const float* dc_b, int64_t P,
+                   float* dfeats_a, float* dfeats_b, float* dp, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decoder MLPs (decoder.py:274-342 MLP_geometry.forward, :561-618 MLP_color.forward; K3).
+ *   params: HOST array of HPS_MLP_NPARAM device pointers in the reference's own layouts
+ *           (Linear.weight = (out,in) row-major; embedder._B = (3,E)).
+ *   affine: colour only, may be NULL: 12 floats = mlp_exposure(exposure_feat); when given the output
+ *           is sigmoid(out @ A[:9].view(3,3) + A[9:]) (decoder.py:606-612), else raw rgb (:613-614).
+ *   act:    NULL (inference) or workspace of hps_mlp_act_floats(kind) floats per point, written by
+ *           fwd and consumed by bwd.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t hps_mlp_act_floats(int kind);     /* activation workspace floats per point (P rounded up to 64) */
+int64_t hps_mlp_packed_floats(int kind);  /* size of the transposed-weight workspace in floats          */
+/* Transpose the Linear weights into the k-major layout the forward tiles read (one tiny launch; call
+ * after every optimiser step, before hps_mlp_fwd).                                                  */
+int hps_mlp_pack(int kind, const float* const* params, float* packed, void* stream);
+int hps_mlp_fwd(int kind, const float* const* params, const float* packed, const float* p, const float* c,
+                const float* affine, int64_t P, float* out, float* act, void* stream);
+/* dparams: HOST array of HPS_MLP_NPARAM device pointers (entries or the array may be NULL = skip);
+ * parameter gradients are ACCUMULATED (atomic adds).  dc (P,32) written.  dp (P,3) written if not
+ * NULL.  daffine (12) accumulated if not NULL.                                                     */
+int hps_mlp_bwd(int kind, const float* const* params, const float* p, const float* c,
+                const float* affine, const float* act, const float* dout, int64_t P,
+                float* const* dparams, float* dc, float* dp, float* daffine, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Alpha compositing (common.py:385-428 raw2outputs_nerf_color, occupancy=True; Renderer.py:237-239).
+ *   rgb/occ are addressed as rgb[i*rgb_stride + c], occ[i*occ_stride] for sample i in [0, R*S):
+ *   a packed raw (R,S,4) is (raw, 4, raw+3, 4).  rgb may be NULL (geometry stages: colour = 0).
+ *   point_mask may be NULL; where it is 0 the occupancy logit is taken as -100 in the forward and
+ *   the gradient is passed straight through.
+ * ---------------------------------------------------------------------------------------------- */
+int hps_composite_fwd(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
+                      const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
+                      float* depth, float* var, float* color, float* weights, void* stream);
+int hps_composite_bwd(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
+                      const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
+                      const float* g_depth, const float* g_color,
+                      float* d_rgb, int d_rgb_stride, float* d_occ, int d_occ_stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPS_B200_H */

@@ -1,0 +1,248 @@
+"""-m gpu: every kernel, called through the C ABI, against the CPU oracle on identical seeded inputs."""
+import pytest
+import torch
+
+from oracle import hps_oracle as O
+from tests import parity
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = parity.TOL   # 1e-4 relative, fp32 (BASELINE.json north_star)
+
+
+def _check_knn(hps, pts, q, radius, cell=None):
+    """Product query vs exhaustive oracle: counts equal; slots < #(D <= t_dn) bit-equal; the rest empty."""
+    idx = hps.GridIndex(DEV)
+    idx.reset(pts.to(DEV))
+    idx.cell_hint = cell
+    res = idx.radius_search(q.to(DEV), radius.to(DEV) if torch.is_tensor(radius) else radius)
+    I, D, cnt = res.I.cpu(), res.D.cpu(), res.count.cpu()
+    Q = q.shape[0]
+    k = min(8, pts.shape[0])
+    if pts.shape[0] >= 8:
+        Do, Io = O.exhaustive_knn(pts, q, 8)
+    else:   # oracle needs N >= k: pad with far-away points that can never be in radius
+        pad = torch.full((8 - pts.shape[0], 3), 1e6)
+        Do, Io = O.exhaustive_knn(torch.cat([pts, pad]), q, 8)
+    t_up, t_dn = O.radius_thresholds(radius, Q)
+    n_ref = (Do < t_up[:, None]).sum(1).int()
+    assert torch.equal(cnt, n_ref), "neighbor_num differs on %d queries" % int((cnt != n_ref).sum())
+    keep = Do <= t_dn[:, None]          # slots that can carry weight (decoder.py:236)
+    assert torch.equal(I[keep].long(), Io[keep]), "indices differ"
+    assert torch.equal(D[keep], Do[keep]), "distances differ"
+    assert bool((I[~keep] == -1).all()) and bool((D[~keep] == torch.finfo(torch.float32).max).all())
+    return cnt
+
+
+def test_knn_golden_fixture(hps, golden):
+    scene, knn = golden("scene_small.pt"), golden("knn_small.pt")
+    for level in ("mid", "fine"):
+        k = knn[level]
+        npc = hps.NeuralPointCloud(hps.scannet_cfg(DEV))
+        npc.set_cloud(level, scene["clouds"][level]["points"].to(DEV))
+        D, I, n = npc.find_neighbors_faiss(k["q"].to(DEV), step="query", dynamic_radius=k["r"].to(DEV), level=level)
+        assert D.dtype == torch.float32 and I.dtype == torch.int64 and n.dtype == torch.int32
+        assert torch.equal(n.cpu(), k["n"])
+        _, t_dn = O.radius_thresholds(k["r"])
+        keep = k["D"] <= t_dn[:, None]
+        assert torch.equal(I.cpu()[keep], k["I"].long()[keep]) and torch.equal(D.cpu()[keep], k["D"][keep])
+        _, _, ns = npc.find_neighbors_faiss(k["q"].to(DEV), step="query", level=level)   # scalar radius_query
+        assert torch.equal(ns.cpu(), k["n_scalar"])
+
+
+@pytest.mark.parametrize("n,q,rmin,rmax,cell", [
+    (20000, 3000, 0.04, 0.16, 0.08),
+    (20000, 2000, 0.24, 0.96, 0.48),
+    (5000, 1000, 0.05, 0.3, None),       # cell derived from the batch
+    (5000, 1000, 0.3, 0.3, 0.02),        # cells much smaller than the radius (multi-pass staging)
+    (3, 50, 0.5, 2.0, 0.5),              # fewer points than k
+    (1, 10, 0.5, 2.0, 0.5),
+])
+def test_knn_random_vs_exhaustive(hps, n, q, rmin, rmax, cell):
+    g = torch.Generator().manual_seed(n + q)
+    sc = O.synthetic_scene(max(n, 8), 8, seed=n)
+    pts = sc["points"][:n].contiguous()
+    base = pts[torch.randint(0, n, (q,), generator=g)]
+    qs = base + torch.randn(q, 3, generator=g) * rmax * 0.4
+    r = rmin + (rmax - rmin) * torch.rand(q, generator=g, dtype=torch.float64)
+    cnt = _check_knn(hps, pts, qs, r, cell)
+    if n >= 1000:
+        assert 0 < cnt.float().mean() < 8.01
+
+
+def test_knn_edge_cases(hps):
+    g = torch.Generator().manual_seed(5)
+    pts = torch.rand(4000, 3, generator=g)
+    pts[100:140] = pts[100]                       # 40 coincident points: ties broken by index
+    pts[200:216, 0] = 0.25                        # exactly representable coordinates
+    q = torch.cat([pts[100:101], pts[:200] + 0.01, torch.full((3, 3), 50.0), pts[200:203] + torch.tensor([0.25, 0, 0])])
+    r = torch.full((q.shape[0],), 0.25, dtype=torch.float64)      # r^2 = 0.0625 exactly representable
+    _check_knn(hps, pts, q, r, 0.125)
+    _check_knn(hps, pts, q, 0.08, 0.04)                           # scalar python radius
+    _check_knn(hps, pts, q[:0], r[:0], 0.125)                     # empty query batch
+    idx = hps.GridIndex(DEV)                                      # empty cloud
+    idx.reset(torch.zeros(0, 3))
+    idx.cell_hint = 0.1
+    res = idx.radius_search(q.to(DEV), 0.3)
+    assert bool((res.I == -1).all()) and bool((res.count == 0).all())
+
+
+def test_knn_index_search_is_exact_knn(hps):
+    g = torch.Generator().manual_seed(9)
+    pts = torch.rand(6000, 3, generator=g) * 2
+    q = torch.rand(300, 3, generator=g) * 2.4 - 0.2
+    idx = hps.GridIndex(DEV)
+    idx.train(pts)
+    idx.add(pts[:3000].to(DEV))
+    idx.add(pts[3000:].to(DEV))
+    assert idx.ntotal == 6000 and idx.is_trained
+    D, I = idx.search(q.to(DEV), 8)
+    Do, Io = O.exhaustive_knn(pts, q, 8)
+    assert torch.equal(I.cpu(), Io) and torch.equal(D.cpu(), Do)
+
+
+def test_knn_full_size_properties(hps):
+    """BASELINE configs[1] size (1M fine points, 25k queries): size-independent properties +
+    exhaustive spot check of 64 queries."""
+    sc = O.synthetic_scene(1_000_000, 5000, (0.04, 0.16), seed=77, extent_scale=3.0)
+    z, _ = O.surface_z_vals(sc["gt_depth"])
+    q = (sc["rays_o"][:, None, :] + sc["rays_d"][:, None, :] * z[..., None]).reshape(-1, 3)
+    r = sc["radius"].repeat_interleave(5)
+    idx = hps.GridIndex(DEV)
+    idx.reset(sc["points"].to(DEV))
+    idx.cell_hint = 0.08
+    res, cand = idx.radius_search(q.to(DEV), r.to(DEV), want_cand=True)
+    res2 = idx.radius_search(q.to(DEV), r.to(DEV))
+    assert torch.equal(res.I, res2.I) and torch.equal(res.D, res2.D)                  # idempotent
+    I, D, cnt = res.I.cpu(), res.D.cpu(), res.count.cpu()
+    used = I >= 0
+    assert bool((D[:, 1:] >= D[:, :-1]).all())                                        # ascending
+    assert bool((used[:, 1:] <= used[:, :-1]).all())                                  # used slots are a prefix
+    t_up, t_dn = O.radius_thresholds(r)
+    assert bool((D[used] <= t_dn[:, None].expand_as(D)[used]).all())
+    assert torch.equal(cnt, (D < t_up[:, None]).sum(1).int())
+    pi = I.clamp(min=0).long()
+    d = q[:, None, :] - sc["points"][pi]
+    Dre = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+    assert torch.equal(Dre[used], D[used])                                            # D is the stated formula
+    assert bool((cand.cpu() >= used.sum(1)).all())
+    sel = torch.randperm(q.shape[0], generator=torch.Generator().manual_seed(1))[:64]
+    Do, Io = O.exhaustive_knn(sc["points"], q[sel], 8)
+    keep = Do <= t_dn[sel][:, None]
+    assert torch.equal(I[sel][keep].long(), Io[keep]) and torch.equal(D[sel][keep], Do[keep])
+    info = idx._grid.info()
+    assert info["status"] == 0 and info["n_points"] == 1_000_000
+
+
+@pytest.mark.parametrize("tracker", [False, True])
+def test_interp_fwd_bwd(hps, tracker):
+    sc = O.synthetic_scene(8000, 200, (0.04, 0.16), seed=3)
+    z, _ = O.surface_z_vals(sc["gt_depth"])
+    p = (sc["rays_o"][:, None, :] + sc["rays_d"][:, None, :] * z[..., None]).reshape(-1, 3)
+    r = sc["radius"].repeat_interleave(5).reshape(-1, 1)
+    fill_a, fill_b = torch.randn(32) * 0.01, torch.randn(32) * 0.01
+    # oracle
+    po = p.clone().requires_grad_(tracker)
+    fa, fb = sc["geo_feats"].clone().requires_grad_(True), sc["col_feats"].clone().requires_grad_(True)
+    D, I, n = O.find_neighbors(sc["points"], p, r)
+    ca, has = O.idw_features(po, fa, D, I, n, r, fill_a, 2, tracker, sc["points"])
+    cb, _ = O.idw_features(po, fb, D, I, n, r, fill_b, 2, tracker, sc["points"])
+    ga, gb = torch.randn_like(ca), torch.randn_like(cb)
+    ((ca * ga).sum() + (cb * gb).sum()).backward()
+    # product
+    idx = hps.GridIndex(DEV)
+    idx.reset(sc["points"].to(DEV))
+    idx.cell_hint = 0.08
+    qr = idx.radius_search(p.to(DEV), r.to(DEV))
+    pd = p.to(DEV).clone().requires_grad_(tracker)
+    fad, fbd = sc["geo_feats"].to(DEV).requires_grad_(True), sc["col_feats"].to(DEV).requires_grad_(True)
+    cad, cbd, hasd = hps.ops.interpolate(pd, fad, fbd, idx.positions if tracker else None, qr.I, qr.D, qr.t_dn,
+                                         qr.count, fill_a.to(DEV), fill_b.to(DEV), 2, tracker)
+    ((cad * ga.to(DEV)).sum() + (cbd * gb.to(DEV)).sum()).backward()
+    assert torch.equal(hasd.cpu(), has)
+    assert 0.2 < has.float().mean() < 1.0
+    assert parity.rel(cad, ca) < 1e-5 and parity.rel(cbd, cb) < 1e-5
+    assert parity.rel(fad.grad, fa.grad) < 1e-5 and parity.rel(fbd.grad, fb.grad) < 1e-5
+    if tracker:
+        assert parity.rel(pd.grad, po.grad) < TOL
+    # single-table variant (geometry stages)
+    c1, c2, _ = hps.ops.interpolate(p.to(DEV), sc["geo_feats"].to(DEV), None, None, qr.I, qr.D, qr.t_dn, qr.count,
+                                    fill_a.to(DEV), None, 2, False)
+    assert c2 is None and parity.rel(c1, O.idw_features(p, sc["geo_feats"], D, I, n, r, fill_a)[0]) < 1e-5
+
+
+@pytest.mark.parametrize("kind,P,affine", [("geo", 200, False), ("col", 200, False), ("col", 333, True),
+                                           ("geo", 64, False), ("col", 1, True)])
+def test_mlp_fwd_bwd(hps, golden, kind, P, affine):
+    scene = golden("scene_small.pt")
+    name = "geo_decoder_fine" if kind == "geo" else "color_decoder_fine"
+    prm = scene["decoders"][name]
+    g = torch.Generator().manual_seed(P)
+    p = torch.randn(P, 3, generator=g) * 1.5 + torch.tensor([0.0, 0.0, -2.0])
+    c = torch.randn(P, 32, generator=g) * 0.1
+    ef = torch.randn(8, generator=g) * 0.5
+    # oracle
+    po, co = p.clone().requires_grad_(True), c.clone().requires_grad_(True)
+    prmo = {k: v.clone().requires_grad_(True) for k, v in prm.items()}
+    efo = ef.clone().requires_grad_(True)
+    out_o = O.geo_mlp(po, co, prmo) if kind == "geo" else O.col_mlp(po, co, prmo, efo if affine else None)
+    gout = torch.randn(out_o.shape, generator=g)
+    (out_o * gout).sum().backward()
+    # product
+    _, _, dec, _ = parity.product(scene, DEV)
+    m = getattr(dec, name)
+    pd, cd = p.to(DEV).requires_grad_(True), c.to(DEV).requires_grad_(True)
+    efd = ef.to(DEV).requires_grad_(True)
+    out_d = m(pd, cd, efd if affine else None)
+    assert out_d.shape == out_o.shape
+    (out_d * gout.to(DEV)).sum().backward()
+    assert parity.rel(out_d, out_o) < TOL
+    assert parity.rel(cd.grad, co.grad) < TOL and parity.rel(pd.grad, po.grad) < TOL
+    named = dict(m.named_parameters())
+    for k, v in prmo.items():
+        if v.grad is None:
+            continue
+        if k == "embedder._B" and kind == "col":
+            continue
+        assert named[k].grad is not None, k
+        assert parity.rel(named[k].grad, v.grad) < TOL, k
+    if affine:
+        assert parity.rel(efd.grad, efo.grad) < TOL
+    # inference path (no activation workspace) gives the same output
+    with torch.no_grad():
+        out_i = m(p.to(DEV), c.to(DEV), ef.to(DEV) if affine else None)
+    assert torch.equal(out_i, out_d.detach())
+
+
+@pytest.mark.parametrize("R,S", [(257, 5), (64, 8), (33, 12), (1, 5)])
+def test_composite_fwd_bwd(hps, R, S):
+    g = torch.Generator().manual_seed(R * S)
+    raw = torch.randn(R, S, 4, generator=g)
+    raw[..., 3] *= 30.0
+    z = torch.sort(torch.rand(R, S, generator=g) * 3 + 0.5, dim=1).values
+    mask = torch.rand(R * S, generator=g) > 0.2
+    ro = raw.clone().requires_grad_(True)
+    occ = ro[..., 3].reshape(-1)
+    occ = occ + (torch.where(mask, occ, torch.full_like(occ, -100.0)) - occ).detach()
+    d, v, c, w = O.composite(torch.cat([ro[..., :3], occ.reshape(R, S, 1)], -1), z, 0.1)
+    gd, gc = torch.randn(R, generator=g), torch.randn(R, 3, generator=g)
+    ((d * gd).sum() + (c * gc).sum()).backward()
+    rd = raw.to(DEV).requires_grad_(True)
+    dd, vd, cd, wd = hps.ops.composite(rd, z.to(DEV), mask.to(DEV), 0.1, want_weights=True)
+    ((dd * gd.to(DEV)).sum() + (cd * gc.to(DEV)).sum()).backward()
+    assert parity.rel(dd, d) < 1e-6 and parity.rel(vd, v) < 1e-5 and parity.rel(cd, c) < 1e-6
+    assert parity.rel(wd, w) < 1e-6
+    assert parity.rel(rd.grad, ro.grad) < TOL
+
+
+def test_raw2outputs_dropin(hps):
+    g = torch.Generator().manual_seed(2)
+    raw = torch.randn(100, 5, 4, generator=g)
+    z = torch.sort(torch.rand(100, 5, generator=g) + 1, dim=1).values
+    d, v, c, w = O.composite(raw, z, 0.1)
+    rawd = raw.to(DEV)
+    dd, vd, cd, wd = hps.raw2outputs_nerf_color(rawd, z.to(DEV), None, occupancy=True, device=DEV, coef=0.1)
+    assert parity.rel(dd, d) < 1e-6 and parity.rel(cd, c) < 1e-6 and parity.rel(wd, w) < 1e-6
+    assert parity.rel(rawd[..., 3], torch.sigmoid(0.1 * raw[..., 3])) < 1e-6      # in-place alpha, common.py:414
+    with pytest.raises(NotImplementedError):
+        hps.raw2outputs_nerf_color(rawd, z.to(DEV), None, occupancy=False)
