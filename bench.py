@@ -1,0 +1,371 @@
+"""Benchmark of the render-and-optimise hot path: mapping rays/sec (fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" = one mapper iteration of the reference's inner loop (Mapper.py:783-858) on one batch of
+synthetic rays: render_batch_ray (stage color_fine) -> L1 depth + colour loss -> backward to the point
+features of the level, the colour decoder and (as in the reference) the geometry decoder.
+Workload at every N = BASELINE.json configs[1]: 5,000 rays (25,000 sample points) per GPU against a
+1M-point fine cloud (+250k mid), ScanNet intrinsics, synthetic data, random-init decoders (seed 1219).
+Weak scaling: every rank renders its own 5,000-ray shard of the global batch against the replicated cloud
+and the gradients are all-reduced (NCCL) - SURVEY 8e.
+
+JSON line: see the driver's contract; `value` = rays/s with inputs resident in HBM (CUDA-event timed per
+step, L2 flushed between steps), `e2e` = same through the public API from pinned host buffers with the
+loss read back every step, `roofline` = dominant kernel vs MEASURED_PEAKS.json, `cpu_baseline` = the
+oracle port timed on the host cores on a bounded sample.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+RAYS = 5000
+N_FINE = 1_000_000
+N_MID = 250_000
+N_BATCHES = 8            # distinct ray batches cycled through
+STAGE = "color_fine"
+EXTENT = 10.0            # cloud spread (in image-plane widths): ~2,700 pts/m^2, ScanNet-like
+CPU_SAMPLE_RAYS = 2500
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops"], tf_sus=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf=1590.0, tf_sus=1400.0, src="fallback")
+
+
+def make_scene(seed=1219):
+    from oracle import hps_oracle as O
+    fine = O.synthetic_scene(N_FINE, RAYS * N_BATCHES, (0.04, 0.16), seed=seed, extent_scale=EXTENT)
+    mid = O.synthetic_scene(N_MID, 8, (0.24, 0.96), seed=seed + 1, extent_scale=EXTENT)
+    g = torch.Generator().manual_seed(seed + 2)
+    radius_mid = 0.24 + 0.72 * torch.rand(RAYS * N_BATCHES, generator=g, dtype=torch.float64)
+    return dict(fine=fine, mid=mid, radius_mid=radius_mid,
+                c_fill_geo=torch.randn(32, generator=g) * 0.01, c_fill_col=torch.randn(32, generator=g) * 0.01,
+                exposure_feat=torch.randn(8, generator=g) * 0.1)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_step_fn(scene, n_rays):
+    from oracle import hps_oracle as O
+    torch.manual_seed(1219)
+    hps = importlib.import_module("hierarchical-point-slam_b200")
+    dec_mod = hps.get_model(hps.scannet_cfg("cpu"))
+    dec = {}
+    for name in ("geo_decoder_fine", "color_decoder_fine"):
+        m = getattr(dec_mod, name)
+        d = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items() if v.is_floating_point()}
+        d["embedder._B"] = m.embedder._B.detach().clone().requires_grad_(name.startswith("geo"))
+        dec[name] = d
+    knn = O.KDTreeNeighbors()
+    fine = scene["fine"]
+    pos = {"fine": fine["points"]}
+    gf = {"fine": fine["geo_feats"].clone().requires_grad_(True)}
+    cf = {"fine": fine["col_feats"].clone().requires_grad_(True)}
+
+    def step(b):
+        sl = slice(b * RAYS, b * RAYS + n_rays)
+        for t in (gf["fine"], cf["fine"]):
+            t.grad = None
+        d, v, c, m = O.render_batch_ray(pos, dec, fine["rays_d"][sl], fine["rays_o"][sl], STAGE, fine["gt_depth"][sl],
+                                        gf, cf, {"fine": fine["radius"][sl]}, scene["c_fill_geo"], scene["c_fill_col"],
+                                        knn_fn=knn)
+        aff = O.exposure_affine(dec["color_decoder_fine"], scene["exposure_feat"])
+        loss = O.mapper_loss(d, c, m, fine["gt_depth"][sl], fine["gt_color"][sl], STAGE, 0.1, aff)
+        loss.backward()
+        return float(loss)
+    return step
+
+
+def time_cpu(scene, n_rays, steps, warmup):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_step_fn(scene, n_rays)
+    for i in range(warmup):
+        step(i % N_BATCHES)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i % N_BATCHES)
+    dt = time.perf_counter() - t0
+    return n_rays * steps / dt, dt / steps
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    scene = make_scene()
+    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    rps, sps = time_cpu(scene, CPU_SAMPLE_RAYS, steps, warmup)
+    cores = os.cpu_count() or 1
+    sample = ("%d-ray mapper iteration (stage %s, fwd+loss+bwd) vs the 1M-point fine cloud; oracle port of the "
+              "reference (torch CPU fp32) with scipy cKDTree(workers=-1) standing in for faiss-cpu" % (CPU_SAMPLE_RAYS, STAGE))
+    line = {"impl": "reference", "metric": "mapping rays/sec (fwd+bwd)", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE configs[1]: ScanNet-shaped mapping step, %d sampled rays x 5 samples fwd+bwd (stage %s) "
+                        "against a 1M-point fine cloud (+250k mid), per GPU" % (RAYS, STAGE),
+            "rays_per_gpu": RAYS, "global_rays": RAYS * n_gpus, "fine_points": N_FINE, "mid_points": N_MID,
+            "cloud_density": "extent_scale %.0f (~2.7k pts/m^2)" % EXTENT,
+            "l2": "flushed between steps (256 MiB memset, untimed); %d distinct ray batches cycled" % N_BATCHES,
+            "parallelism": "rays sharded x%d, cloud replicated, gradient all-reduce (NCCL)" % n_gpus if n_gpus > 1 else "single GPU"}
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+    hps = importlib.import_module("hierarchical-point-slam_b200")
+    allreduce_grads = hps.parallel.allreduce_grads
+    dev = "cuda:%d" % local_rank
+    torch.cuda.set_device(local_rank)
+    scene = make_scene()
+    cfg = hps.scannet_cfg(dev)
+    npc = hps.NeuralPointCloud(cfg)
+    for level in ("fine", "mid"):
+        s = scene[level]
+        npc.set_cloud(level, s["points"].to(dev), s["geo_feats"].to(dev), s["col_feats"].to(dev))
+    torch.manual_seed(1219)
+    dec = hps.get_model(cfg).to(dev)
+    dec.c_fill_geo, dec.c_fill_col = scene["c_fill_geo"].to(dev), scene["c_fill_col"].to(dev)
+    import types
+    renderer = hps.Renderer(cfg, None, types.SimpleNamespace(**{k: cfg["cam"][k] for k in ("H", "W", "fx", "fy", "cx", "cy")}))
+    renderer.sigmoid_coefficient = 0.1
+    fine = scene["fine"]
+    # rank r takes every world-th batch offset so that ranks render different rays of the global batch
+    host = {k: fine[k].pin_memory() for k in ("rays_o", "rays_d", "gt_depth", "gt_color", "radius")}
+    host["radius_mid"] = scene["radius_mid"].pin_memory()
+    devb = {k: v.to(dev) for k, v in host.items()}
+    exposure_feat = scene["exposure_feat"].to(dev)
+    gf = {l: npc.get_geo_feats(l).clone().requires_grad_(l == "fine") for l in ("fine", "mid")}
+    cf = {l: npc.get_col_feats(l).clone().requires_grad_(l == "fine") for l in ("fine", "mid")}
+    pos = {l: npc.cloud_pos_tensor(l) for l in ("fine", "mid")}
+    params = [p for p in dec.parameters()]
+    grad_targets = [gf["fine"], cf["fine"]] + params
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def batch_slice(i):
+        b = (i * world + rank) % N_BATCHES
+        return slice(b * RAYS, (b + 1) * RAYS)
+
+    def step(src, sl):
+        for t in grad_targets:
+            t.grad = None
+        rq = {"fine": src["radius"][sl], "mid": src["radius_mid"][sl]}
+        depth, unc, color, valid = renderer.render_batch_ray(
+            npc, dec, src["rays_d"][sl], src["rays_o"][sl], dev, STAGE, gt_depth=src["gt_depth"][sl],
+            npc_geo_feats=gf, npc_col_feats=cf, is_tracker=False, cloud_pos=pos, dynamic_r_query=rq, exposure_feat=None)
+        affine = dec.color_decoder_fine.mlp_exposure(exposure_feat)
+        loss = hps.mapper_loss(depth, color, valid, src["gt_depth"][sl], src["gt_color"][sl], STAGE, 0.1, affine)
+        loss.backward()
+        if world > 1:
+            allreduce_grads(grad_targets, dist)
+        return loss
+
+    def step_e2e(i):
+        sl = batch_slice(i)
+        src = {k: v[sl].to(dev, non_blocking=True) for k, v in host.items()}
+        loss = step(src, slice(0, RAYS))
+        return loss.item()      # device -> host read of the step's result
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up ----
+    for i in range(args.warmup):
+        step(devb, batch_slice(i))
+    sync_all()
+    # ---- timed: K steps, per-step CUDA events, L2 flushed (untimed) between steps ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    hps.ops.LAUNCHES["n"] = 0
+    evs = []
+    sync_all()
+    for i in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step(devb, batch_slice(args.warmup + i))
+        b.record()
+        evs.append((a, b))
+    sync_all()
+    launches = hps.ops.LAUNCHES["n"]
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- e2e: host buffers in, loss out, wall clock around synchronised region ----
+    for i in range(min(3, args.warmup)):
+        step_e2e(i)
+    sync_all()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(args.warmup + i)
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = float(t[0]), float(t[1])
+    # ---- per-kernel timing pass (instrumented, separate from the timed region) ----
+    roof = None
+    if rank == 0:
+        hps.ops.TIMERS = {}
+        for i in range(args.steps):
+            flush.zero_()
+            step(devb, batch_slice(args.warmup + i))
+        torch.cuda.synchronize()
+        per = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in hps.ops.TIMERS.items()}
+        hps.ops.TIMERS = None
+        roof = roofline(per, hps, npc, devb, batch_slice(0))
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    h2d = sum(v[batch_slice(0)].numel() * v.element_size() for v in host.values())
+    line = {"metric": "mapping rays/sec (fwd+bwd)", "value": RAYS * world * args.steps / (dev_ms * 1e-3), "unit": "rays/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world), "clocks": clocks,
+            "e2e": {"value": RAYS * world * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "roofline": roof["roofline"], "kernels_ms_per_step": roof["per_kernel"]}
+    if world == 1:
+        rps, sps = time_cpu(scene, CPU_SAMPLE_RAYS, 3, 1)
+        line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "%d-ray mapper iteration of the same workload, oracle port (torch CPU fp32 + scipy "
+                                          "cKDTree for the neighbour search), 3 timed repeats" % CPU_SAMPLE_RAYS}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline(per, hps, npc, devb, sl):
+    """Dominant kernel of the step vs the measured peak.  Algorithmic work per launch:
+    colour MLP fwd 193,400 FLOP/pt, bwd (dgrad+wgrad) 2 x 193,400; geometry 30,958 / 2 x 30,958;
+    gather 2,432 B/pt (two tables); search (84 + 12*cand) B/query."""
+    P = RAYS * 5
+    pk = peaks()
+    work = {"hps_mlp_fwd[1]": ("tensor", 193400.0 * P), "hps_mlp_bwd[1]": ("tensor", 2 * 193400.0 * P),
+            "hps_mlp_fwd[0]": ("tensor", 30958.0 * P), "hps_mlp_bwd[0]": ("tensor", 2 * 30958.0 * P),
+            "hps_interp_fwd": ("hbm", 2432.0 * P), "hps_interp_bwd": ("hbm", 2432.0 * P)}
+    # measured mean candidate count for the search figure
+    z, _ = None, None
+    q, cand = npc.query_neighbors((devb["rays_o"][sl][:, None, :] + devb["rays_d"][sl][:, None, :] *
+                                   (devb["gt_depth"][sl][:, None, None] * torch.linspace(0.96, 1.04, 5, device=devb["rays_o"].device)[None, :, None])).reshape(-1, 3),
+                                  step="query", dynamic_radius=devb["radius"][sl].repeat_interleave(5), level="fine",
+                                  want_cand=True)
+    mean_cand = float(cand.float().mean())
+    work["hps_knn_query"] = ("hbm", (84.0 + 12.0 * mean_cand) * P)
+    top = max(per, key=per.get)
+    bound, amount = work.get(top, ("hbm", 0.0))
+    ms = per[top]
+    if bound == "tensor":
+        achieved, peak, unit = amount / (ms * 1e-3) / 1e12, pk["tf"], "TFLOP/s"
+    else:
+        achieved, peak, unit = amount / (ms * 1e-3) / 1e9, pk["hbm"], "GB/s"
+    detail = {}
+    for k, (b, amt) in work.items():
+        if k in per and per[k] > 0:
+            detail[k] = {"ms": per[k], "achieved": amt / (per[k] * 1e-3) / (1e12 if b == "tensor" else 1e9),
+                         "unit": "TFLOP/s" if b == "tensor" else "GB/s",
+                         "frac": amt / (per[k] * 1e-3) / (1e12 if b == "tensor" else 1e9) / (pk["tf"] if b == "tensor" else pk["hbm"])}
+    return {"roofline": {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                         "frac": achieved / peak, "traffic": None, "peak_source": pk["src"],
+                         "mean_candidates_per_query": mean_cand, "all": detail},
+            "per_kernel": per}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    if world == 1 and args.gpus > 1:
+        # plain `python bench.py --gpus N`: re-launch under torchrun
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__), "--gpus", str(args.gpus),
+               "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        raise SystemExit(subprocess.call(cmd))
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -19,6 +19,29 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+# ---- instrumentation: kernel-launch counter and optional CUDA-event timers per C-ABI call -----------
+LAUNCHES = {"n": 0}
+_KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_interp_fwd": 1, "hps_interp_bwd": 1,
+                     "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_composite_fwd": 1,
+                     "hps_composite_bwd": 1}
+TIMERS = None   # set to {} to record (start, end) CUDA events per call name on the current stream
+
+
+def _call(name, *args):
+    """Invoke one C-ABI entry point on the current stream (raises on a non-zero return code)."""
+    fn = getattr(_lib.load(), name)
+    LAUNCHES["n"] += _KERNELS_PER_CALL.get(name, 0)
+    if TIMERS is None:
+        _lib.check(fn(*args))
+        return
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    _lib.check(fn(*args))
+    b.record()
+    TIMERS.setdefault(name if name != "hps_mlp_fwd" and name != "hps_mlp_bwd" else "%s[%d]" % (name, args[0]),
+                      []).append((a, b))
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -75,7 +98,7 @@ class VoxelHashGrid:
         _need_cuda(pos)
         pos = _f32c(pos).reshape(-1, 3)
         with torch.cuda.device(pos.device):
-            _lib.check(_lib.load().hps_grid_build(self._h, _lib.ptr(pos), pos.shape[0], float(cell), _stream()))
+            _call("hps_grid_build", self._h, _lib.ptr(pos), pos.shape[0], float(cell), _stream())
         self._keep = pos            # keep the source alive until the stream has consumed it
         self.n = pos.shape[0]
         self.cell = float(cell)
@@ -96,8 +119,8 @@ class VoxelHashGrid:
         cnt = torch.empty(Q, dtype=torch.int32, device=q.device)
         cand = torch.empty(Q, dtype=torch.int32, device=q.device) if want_cand else None
         with torch.cuda.device(q.device):
-            _lib.check(_lib.load().hps_knn_query(self._h, _lib.ptr(q), _lib.ptr(t_up), _lib.ptr(t_dn), Q,
-                                                 _lib.ptr(I), _lib.ptr(D), _lib.ptr(cnt), _lib.ptr(cand), _stream()))
+            _call("hps_knn_query", self._h, _lib.ptr(q), _lib.ptr(t_up), _lib.ptr(t_dn), Q,
+                                                 _lib.ptr(I), _lib.ptr(D), _lib.ptr(cnt), _lib.ptr(cand), _stream())
         return (I, D, cnt, cand) if want_cand else (I, D, cnt)
 
 
@@ -121,10 +144,10 @@ class _Interp(torch.autograd.Function):
         fill_a = _f32c(fill_a)
         fill_b = _f32c(fill_b) if fill_b is not None else None
         with torch.cuda.device(dev):
-            _lib.check(_lib.load().hps_interp_fwd(
+            _call("hps_interp_fwd", 
                 _lib.ptr(p_c), _lib.ptr(I), _lib.ptr(D), _lib.ptr(t_dn), _lib.ptr(count), _lib.ptr(pos),
                 _lib.ptr(fa), _lib.ptr(fb), _lib.ptr(fill_a), _lib.ptr(fill_b), P, int(min_nn),
-                _lib.ptr(w), _lib.ptr(c_a), _lib.ptr(c_b), _lib.ptr(has), _stream()))
+                _lib.ptr(w), _lib.ptr(c_a), _lib.ptr(c_b), _lib.ptr(has), _stream())
         ctx.save_for_backward(p_c, fa, fb, pos, I, w, has, c_a, c_b)
         ctx.tracker = tracker
         ctx.mark_non_differentiable(has)
@@ -145,10 +168,10 @@ class _Interp(torch.autograd.Function):
         dp = torch.empty(P, 3, dtype=torch.float32, device=I.device) if (need_p and ctx.tracker) else None
         if dfa is not None or dfb is not None or dp is not None:
             with torch.cuda.device(I.device):
-                _lib.check(_lib.load().hps_interp_bwd(
+                _call("hps_interp_bwd", 
                     _lib.ptr(p_c), _lib.ptr(I), _lib.ptr(w), _lib.ptr(has), _lib.ptr(pos), _lib.ptr(fa),
                     _lib.ptr(fb), _lib.ptr(c_a), _lib.ptr(c_b), _lib.ptr(dc_a), _lib.ptr(dc_b), P,
-                    _lib.ptr(dfa), _lib.ptr(dfb), _lib.ptr(dp), _stream()))
+                    _lib.ptr(dfa), _lib.ptr(dfb), _lib.ptr(dp), _stream())
         return dp, dfa, dfb, None, None, None, None, None, None, None, None, None
 
 
@@ -201,9 +224,9 @@ class _Mlp(torch.autograd.Function):
         packed = _packed_buffer(kind, dev)
         arr = _ptr_array(prm)
         with torch.cuda.device(dev):
-            _lib.check(lib.hps_mlp_pack(kind, arr, _lib.ptr(packed), _stream()))
-            _lib.check(lib.hps_mlp_fwd(kind, arr, _lib.ptr(packed), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), P,
-                                       _lib.ptr(out), _lib.ptr(act), _stream()))
+            _call("hps_mlp_pack", kind, arr, _lib.ptr(packed), _stream())
+            _call("hps_mlp_fwd", kind, arr, _lib.ptr(packed), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), P,
+                                       _lib.ptr(out), _lib.ptr(act), _stream())
         ctx.kind = kind
         ctx.has_affine = aff is not None
         ctx.save_for_backward(p_c, c_c, aff, act, *prm)
@@ -229,9 +252,9 @@ class _Mlp(torch.autograd.Function):
         daff = torch.zeros(12, dtype=torch.float32, device=dev) if (ctx.has_affine and need[3]) else None
         darr = _ptr_array(dprm) if want_w else None
         with torch.cuda.device(dev):
-            _lib.check(_lib.load().hps_mlp_bwd(kind, _ptr_array(prm), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff),
+            _call("hps_mlp_bwd", kind, _ptr_array(prm), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff),
                                                _lib.ptr(act), _lib.ptr(_f32c(dout)), P, darr, _lib.ptr(dc),
-                                               _lib.ptr(dp), _lib.ptr(daff), _stream()))
+                                               _lib.ptr(dp), _lib.ptr(daff), _stream())
         grads = [g if (g is not None and need[4 + i]) else None for i, g in enumerate(dprm)]
         return (None, dp, dc if need[2] else None, daff, *grads)
 
@@ -261,9 +284,9 @@ class _CompositeRaw(torch.autograd.Function):
         weights = torch.empty(R, S, dtype=torch.float32, device=dev) if want_weights else None
         base = raw_c.data_ptr()
         with torch.cuda.device(dev):
-            _lib.check(_lib.load().hps_composite_fwd(
+            _call("hps_composite_fwd", 
                 ctypes.c_void_p(base), 4, ctypes.c_void_p(base + 12), 4, _lib.ptr(pm), _lib.ptr(z_c), R, S,
-                float(coef), _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), _lib.ptr(weights), _stream()))
+                float(coef), _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), _lib.ptr(weights), _stream())
         ctx.save_for_backward(raw_c, z_c, pm)
         ctx.coef = float(coef)
         ctx.mark_non_differentiable(var)
@@ -281,9 +304,9 @@ class _CompositeRaw(torch.autograd.Function):
         gc = _f32c(g_color) if g_color is not None else None
         base, dbase = raw_c.data_ptr(), d_raw.data_ptr()
         with torch.cuda.device(raw_c.device):
-            _lib.check(_lib.load().hps_composite_bwd(
+            _call("hps_composite_bwd", 
                 ctypes.c_void_p(base), 4, ctypes.c_void_p(base + 12), 4, _lib.ptr(pm), _lib.ptr(z_c), R, S, ctx.coef,
-                _lib.ptr(gd), _lib.ptr(gc), ctypes.c_void_p(dbase), 4, ctypes.c_void_p(dbase + 12), 4, _stream()))
+                _lib.ptr(gd), _lib.ptr(gc), ctypes.c_void_p(dbase), 4, ctypes.c_void_p(dbase + 12), 4, _stream())
         return d_raw, None, None, None, None
 
 

@@ -84,6 +84,29 @@ def radius_thresholds(radius, n=None):
     return t_up, t_dn
 
 
+class KDTreeNeighbors:
+    """Fast exact CPU neighbour search for the *timed* CPU baseline (scipy cKDTree, all cores).  Stands in
+    for faiss-cpu, which is not installable here (SURVEY 8d).  Same return contract as find_neighbors;
+    distances are re-evaluated with the fp32 direct formula so downstream weights match the oracle."""
+
+    def __init__(self):
+        self._trees = {}
+
+    def __call__(self, points, queries, radius, k=K_NN):
+        from scipy.spatial import cKDTree
+        key = (points.data_ptr(), points.shape[0])
+        if key not in self._trees:
+            self._trees[key] = cKDTree(points.detach().numpy())
+        q = queries.detach().float()
+        _, I = self._trees[key].query(q.numpy(), k=k, workers=-1)
+        I = torch.from_numpy(np.ascontiguousarray(I)).long()
+        d = q[:, None, :] - points[I]
+        D = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        D, order = torch.sort(D, dim=1, stable=True)
+        I = torch.gather(I, 1, order)
+        return D, I, neighbor_count(D, radius)
+
+
 # ----------------------------------------------------------------------------------------------
 # inverse-distance interpolation  (decoder.py:195-272 == :491-559)
 # ----------------------------------------------------------------------------------------------
@@ -159,7 +182,7 @@ def col_mlp(p, c, prm, exposure_feat=None, encode_exposure=True):
 
 
 def nicer_forward(p, points, stage, geo_feats, col_feats, radius, dec, c_fill_geo, c_fill_col,
-                  n_surface=5, min_nn=2, is_tracker=False, exposure_feat=None, neighbors=None):
+                  n_surface=5, min_nn=2, is_tracker=False, exposure_feat=None, neighbors=None, knn_fn=None):
     """NICER.forward for the four live stages (decoder.py:660-723).
 
     points / geo_feats / col_feats / radius: dicts level -> tensor (radius: per-point f64).
@@ -167,7 +190,7 @@ def nicer_forward(p, points, stage, geo_feats, col_feats, radius, dec, c_fill_ge
     level = "mid" if stage.endswith("mid") else "fine"
     p = p.reshape(-1, 3)
     if neighbors is None:
-        neighbors = find_neighbors(points[level], p, radius[level])
+        neighbors = (knn_fn or find_neighbors)(points[level], p, radius[level])
     D, I, n = neighbors
     cg, has = idw_features(p, geo_feats[level], D, I, n, radius[level], c_fill_geo, min_nn,
                            is_tracker, points[level])
@@ -224,7 +247,7 @@ def surface_z_vals(gt_depth, near_end_surface=0.96, far_end_surface=1.04, n_surf
 
 def render_batch_ray(points, dec, rays_d, rays_o, stage, gt_depth, geo_feats, col_feats, radius_ray,
                      c_fill_geo, c_fill_col, is_tracker=False, exposure_feat=None, coef=0.1,
-                     near_end_surface=0.96, far_end_surface=1.04, n_surface=5, min_nn=2):
+                     near_end_surface=0.96, far_end_surface=1.04, n_surface=5, min_nn=2, knn_fn=None):
     """Returns depth (R,), uncertainty (R,), color (R,3), valid_ray_mask (R,).
 
     radius_ray: dict level -> per-RAY float64 radii (repeated per sample, Renderer.py:226-229)."""
@@ -233,7 +256,7 @@ def render_batch_ray(points, dec, rays_d, rays_o, stage, gt_depth, geo_feats, co
     radius_pt = {k: v.reshape(-1, 1).repeat_interleave(n_surface, dim=0) for k, v in radius_ray.items()}
     raw, ray_mask, point_mask = nicer_forward(pts.reshape(-1, 3), points, stage, geo_feats, col_feats,
                                               radius_pt, dec, c_fill_geo, c_fill_col, n_surface, min_nn,
-                                              is_tracker, exposure_feat)
+                                              is_tracker, exposure_feat, knn_fn=knn_fn)
     # Renderer.py:237-239: overwrite under no_grad, straight-through for the backward
     occ = raw[:, 3]
     occ = occ + (torch.where(point_mask, occ, torch.full_like(occ, -100.0)) - occ).detach()
