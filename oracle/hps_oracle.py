@@ -156,9 +156,24 @@ def _blocks(e, c, prm, act, n_blocks=5, skips=(2,)):
     return F.linear(h, prm["output_linear.weight"], prm["output_linear.bias"])
 
 
+def geo_preactivations(p, c, prm, n_blocks=5, skips=(2,)):
+    """Pre-activations a_i = W_i x_i + b_i of the ReLU decoder, (P, n_blocks, hidden).  Used by the tests to
+    find sample points that sit on a ReLU kink within fp32 noise (|a| ~ 1e-4 from the rounding of the
+    Fourier arguments 2*pi*p*B ~ 1e3 rad), where the reference's own gradient is discontinuous."""
+    e = fourier_embed(p.reshape(-1, 3), prm["embedder._B"], concat=False)
+    h, out = e, []
+    for i in range(n_blocks):
+        a = F.linear(h, prm["pts_linears.%d.weight" % i], prm["pts_linears.%d.bias" % i])
+        out.append(a)
+        h = F.relu(a) + F.linear(c, prm["fc_c.%d.weight" % i], prm["fc_c.%d.bias" % i])
+        if i in skips:
+            h = torch.cat([e, h], -1)
+    return torch.stack(out, 1)
+
+
 def geo_mlp(p, c, prm):
     """MLP_geometry.forward body (decoder.py:316-341): sin embedding (B learnable, 3x93), ReLU."""
-    e = fourier_embed(p.float().reshape(-1, 3), prm["embedder._B"], concat=False)
+    e = fourier_embed(p.reshape(-1, 3), prm["embedder._B"], concat=False)
     return _blocks(e, c, prm, F.relu).squeeze(-1)
 
 
@@ -171,7 +186,7 @@ def exposure_affine(prm, exposure_feat):
 
 def col_mlp(p, c, prm, exposure_feat=None, encode_exposure=True):
     """MLP_color.forward body (decoder.py:581-618): sin|cos embedding (B fixed 3x20), Softplus(100)."""
-    e = fourier_embed(p.float().reshape(-1, 3), prm["embedder._B"], concat=True)
+    e = fourier_embed(p.reshape(-1, 3), prm["embedder._B"], concat=True)
     out = _blocks(e, c, prm, lambda x: F.softplus(x, beta=100))
     if encode_exposure:
         if exposure_feat is None:
@@ -197,7 +212,7 @@ def nicer_forward(p, points, stage, geo_feats, col_feats, radius, dec, c_fill_ge
     ray_mask = ~(has.view(-1, n_surface).sum(1) < int(n_surface / 2 + 1))  # decoder.py:310-311
     occ = geo_mlp(p, cg, dec["geo_decoder_" + level])
     if stage.startswith("geometry"):                                       # decoder.py:682-699
-        raw = torch.cat([torch.zeros(occ.shape[0], 3), occ[:, None]], -1)
+        raw = torch.cat([torch.zeros(occ.shape[0], 3, dtype=occ.dtype), occ[:, None]], -1)
         return raw, ray_mask, has
     cc, _ = idw_features(p, col_feats[level], D, I, n, radius[level], c_fill_col, min_nn,
                          is_tracker, points[level])
@@ -211,7 +226,7 @@ def nicer_forward(p, points, stage, geo_feats, col_feats, radius, dec, c_fill_ge
 def composite(raw, z_vals, coef=0.1):
     """raw (R,S,4) with the occupancy logit in channel 3.  Returns depth, var, rgb, weights."""
     alpha = torch.sigmoid(coef * raw[..., 3])
-    ones = torch.ones(alpha.shape[0], 1)
+    ones = torch.ones(alpha.shape[0], 1, dtype=alpha.dtype)
     trans = torch.cumprod(torch.cat([ones, 1.0 - alpha + 1e-10], -1), -1)[:, :-1]
     w = alpha * trans
     wsum = w.sum(-1, keepdim=True) + 1e-10
@@ -230,10 +245,10 @@ def surface_z_vals(gt_depth, near_end_surface=0.96, far_end_surface=1.04, n_surf
     """Depth-guided samples (Renderer.py:163-208): z = near*d*(1-t) + far*d*t, t = linspace(0,1,S);
     zero-depth rays get linspace(near_end, max far) with far = clamp(far_bb, 0, max(1.2 d))."""
     gt = gt_depth.reshape(-1, 1)
-    t = torch.linspace(0.0, 1.0, steps=n_surface)
+    t = torch.linspace(0.0, 1.0, steps=n_surface, dtype=gt.dtype)
     nz = gt.squeeze(-1) > 0
     d = gt[nz].repeat(1, n_surface)
-    z = torch.zeros(gt.shape[0], n_surface)
+    z = torch.zeros(gt.shape[0], n_surface, dtype=gt.dtype)
     z[nz] = near_end_surface * d * (1.0 - t) + far_end_surface * d * t
     if nz.sum() < gt.shape[0]:
         far_bb = torch.minimum(5 * gt.mean(), torch.max(gt * 1.2))          # Renderer.py:133-134

@@ -30,7 +30,8 @@ def test_tracker_iteration_matches_reference(built, stage):
     scene, hps, npc, dec, renderer = built
     ref = parity.load("render_tracker_small.pt")
     out = parity.tracker_step(hps, npc, dec, renderer, scene, ref["inputs"], stage, DEV)
-    errs = parity.check_tracker(stage, out, ref[stage])
+    truth = parity.tracker_truth64(scene, ref["inputs"], stage)
+    errs = parity.check_tracker(stage, out, ref[stage], truth, ref["inputs"])
     print(stage, errs)
 
 
