@@ -30,8 +30,7 @@ def test_tracker_iteration_matches_reference(built, stage):
     scene, hps, npc, dec, renderer = built
     ref = parity.load("render_tracker_small.pt")
     out = parity.tracker_step(hps, npc, dec, renderer, scene, ref["inputs"], stage, DEV)
-    truth = parity.tracker_truth64(scene, ref["inputs"], stage)
-    errs = parity.check_tracker(stage, out, ref[stage], truth, ref["inputs"])
+    errs = parity.check_tracker(stage, out, ref[stage], scene, ref["inputs"])
     print(stage, errs)
 
 
