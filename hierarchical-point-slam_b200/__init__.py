@@ -9,7 +9,7 @@ from .config import scannet_cfg  # noqa: F401
 from .common import (get_camera_from_tensor, get_rays, get_rays_from_uv, quad2rotation,  # noqa: F401
                      raw2outputs_nerf_color)
 from .decoder import NICER, PointDecoder  # noqa: F401
-from .losses import mapper_loss, tracker_loss  # noqa: F401
+from .losses import mapper_loss, mapper_loss_torch, tracker_loss, tracker_loss_torch  # noqa: F401
 from .neural_point import GridIndex, NeuralPointCloud  # noqa: F401
 from .renderer import Renderer  # noqa: F401
 

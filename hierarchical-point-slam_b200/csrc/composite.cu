@@ -82,7 +82,8 @@ __global__ void __launch_bounds__(256)
 composite_fwd_kernel(const float* __restrict__ rgb, int rgb_stride, const float* __restrict__ occ,
                      int occ_stride, const uint8_t* __restrict__ point_mask, const float* __restrict__ z,
                      int64_t R, int S, float coef, float* __restrict__ depth_out, float* __restrict__ var_out,
-                     float* __restrict__ color_out, float* __restrict__ weights_out) {
+                     float* __restrict__ color_out, float* __restrict__ weights_out, int min_valid,
+                     uint8_t* __restrict__ valid_ray) {
     constexpr int RPW = 32 / G;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -96,7 +97,14 @@ composite_fwd_kernel(const float* __restrict__ rgb, int rgb_stride, const float*
     float wsum, depth, cr, cg, cb, var;
     composite_core<G>(rgb, rgb_stride, occ, occ_stride, point_mask, z, ray, S, s, active, coef, sub * G, me,
                       wsum, depth, cr, cg, cb, var);
+    int n_has = 0;
+    if (valid_ray != nullptr) {   // decoder.py:310-311: a ray is valid if >= min_valid samples have neighbours
+        const bool pm = active && (point_mask == nullptr || point_mask[ray * S + s] != 0);
+        const unsigned grp = (G == 32) ? kFull : (((1u << G) - 1u) << (sub * G));
+        n_has = __popc(__ballot_sync(kFull, pm) & grp);
+    }
     if (!live) return;
+    if (s == 0 && valid_ray != nullptr) valid_ray[ray] = n_has >= min_valid ? 1 : 0;
     if (active && weights_out != nullptr) weights_out[ray * S + s] = me.w;
     if (s == 0) {
         depth_out[ray] = depth;
@@ -160,7 +168,8 @@ composite_bwd_kernel(const float* __restrict__ rgb, int rgb_stride, const float*
 
 extern "C" int hps_composite_fwd(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
                                  const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
-                                 float* depth, float* var, float* color, float* weights, void* stream) {
+                                 float* depth, float* var, float* color, float* weights, int min_valid,
+                                 uint8_t* valid_ray, void* stream) {
     using namespace hps;
     HPS_REQUIRE(R >= 0 && S >= 1 && S <= 32, "need 1 <= S <= 32");
     if (R == 0) return 0;
@@ -169,10 +178,12 @@ extern "C" int hps_composite_fwd(const float* rgb, int rgb_stride, const float* 
     if (S <= 8) {
         const int64_t warps = ceil_div(R, 4);
         composite_fwd_kernel<8><<<(unsigned)ceil_div(warps * 32, tb), tb, 0, (cudaStream_t)stream>>>(
-            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, depth, var, color, weights);
+            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, depth, var, color, weights, min_valid,
+            valid_ray);
     } else {
         composite_fwd_kernel<32><<<(unsigned)ceil_div(R * 32, tb), tb, 0, (cudaStream_t)stream>>>(
-            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, depth, var, color, weights);
+            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, depth, var, color, weights, min_valid,
+            valid_ray);
     }
     HPS_LAUNCH_OK();
     return 0;

@@ -1,9 +1,17 @@
-"""Mapper / Tracker losses of the hot path (reference Mapper.py:791-856, Tracker.py:213-231) as small
-torch expressions over the renderer's outputs; backward() then drives the kernels' backward passes."""
+"""Mapper / Tracker losses of the hot path (reference Mapper.py:791-856, Tracker.py:213-231).
+
+The default entry points run the fused loss+gradient kernels (ops.mapper_loss / ops.tracker_loss: no boolean
+indexing, no host synchronisation).  The *_torch variants are the same formulas as small torch expressions
+(used by tests as a cross-check of the kernels' autograd wiring)."""
 import torch
 
+from . import ops
 
-def mapper_loss(depth, color, valid_ray_mask, gt_depth, gt_color, stage, w_color_loss=0.1, affine=None):
+mapper_loss = ops.mapper_loss
+tracker_loss = ops.tracker_loss
+
+
+def mapper_loss_torch(depth, color, valid_ray_mask, gt_depth, gt_color, stage, w_color_loss=0.1, affine=None):
     """affine: (12,) exposure tensor of the (single) frame the batch comes from, or None."""
     mask = (gt_depth > 0) & valid_ray_mask & (~torch.isnan(depth))
     loss = torch.abs(gt_depth[mask] - depth[mask]).sum()
@@ -15,7 +23,7 @@ def mapper_loss(depth, color, valid_ray_mask, gt_depth, gt_color, stage, w_color
     return loss
 
 
-def tracker_loss(depth, uncertainty, color, gt_depth, gt_color, w_color_loss=0.5):
+def tracker_loss_torch(depth, uncertainty, color, gt_depth, gt_color, w_color_loss=0.5):
     uncertainty = uncertainty.detach()
     nan_mask = (~torch.isnan(depth)) & (~torch.isnan(uncertainty))
     tmp = torch.abs(gt_depth - depth) / torch.sqrt(uncertainty + 1e-10)

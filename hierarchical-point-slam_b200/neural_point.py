@@ -86,6 +86,14 @@ class GridIndex:
             self._grid_n, self._cell = self.ntotal, want
         return self._grid
 
+    def grid_for(self, radius):
+        """The built grid for a query with the given radius (scalar or tensor)."""
+        if self.cell_hint is None:
+            n = radius.numel() if torch.is_tensor(radius) else 1
+            _, t_dn = ops.radius_thresholds(radius, n, self.device)
+            return self._ensure_grid(t_dn)
+        return self._ensure_grid(None)
+
     def radius_search(self, q, radius, want_cand=False):
         """Exact 8-NN limited to `radius` (float or per-query tensor, float64 semantics)."""
         q = q.detach().to(device=self.device, dtype=torch.float32).reshape(-1, 3)

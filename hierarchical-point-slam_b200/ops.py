@@ -23,7 +23,8 @@ def _stream():
 LAUNCHES = {"n": 0}
 _KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_interp_fwd": 1, "hps_interp_bwd": 1,
                      "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_composite_fwd": 1,
-                     "hps_composite_bwd": 1}
+                     "hps_composite_bwd": 1, "hps_sample_rays": 1, "hps_sample_rays_bwd": 1, "hps_mapper_loss": 1,
+                     "hps_tracker_loss_stats": 1, "hps_tracker_loss": 1}
 TIMERS = None   # set to {} to record (start, end) CUDA events per call name on the current stream
 
 
@@ -286,7 +287,7 @@ class _CompositeRaw(torch.autograd.Function):
         with torch.cuda.device(dev):
             _call("hps_composite_fwd", 
                 ctypes.c_void_p(base), 4, ctypes.c_void_p(base + 12), 4, _lib.ptr(pm), _lib.ptr(z_c), R, S,
-                float(coef), _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), _lib.ptr(weights), _stream())
+                float(coef), _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), _lib.ptr(weights), 0, None, _stream())
         ctx.save_for_backward(raw_c, z_c, pm)
         ctx.coef = float(coef)
         ctx.mark_non_differentiable(var)
@@ -313,3 +314,235 @@ class _CompositeRaw(torch.autograd.Function):
 def composite(raw, z, point_mask=None, coef=0.1, want_weights=False):
     depth, var, color, w = _CompositeRaw.apply(raw, z, point_mask, coef, want_weights)
     return depth, var, color, (w if want_weights else None)
+
+
+# --------------------------------------------------------------------------------------------------
+# fused ray rendering: sampling -> neighbour search -> interpolation -> decoders -> compositing
+# --------------------------------------------------------------------------------------------------
+class RenderSpec:
+    """Non-tensor arguments of render_rays (one per call)."""
+    __slots__ = ("grid", "radius", "z_zero", "S", "near", "far", "coef", "min_nn", "min_valid", "color_stage",
+                 "tracker", "cloud_pos", "fill_geo", "fill_col")
+
+    def __init__(self, **kw):
+        for k in self.__slots__:
+            setattr(self, k, kw.get(k))
+
+
+class _RenderRays(torch.autograd.Function):
+    """depth (R,), var (R,), color (R,3), valid (R,) uint8  =  f(rays_o, rays_d, gt_depth, feats_geo, feats_col,
+    affine, 23 geometry-decoder tensors, 23 colour-decoder tensors).  Ten kernel launches forward, five or
+    six backward; nothing but buffer allocation happens in PyTorch."""
+
+    @staticmethod
+    def forward(ctx, spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, *params):
+        _need_cuda(rays_o, rays_d, gt_depth, feats_geo)
+        dev = rays_o.device
+        R, S = rays_o.shape[0], spec.S
+        P = R * S
+        f32 = dict(dtype=torch.float32, device=dev)
+        ro, rd, gd = _f32c(rays_o).reshape(-1, 3), _f32c(rays_d).reshape(-1, 3), _f32c(gt_depth).reshape(-1)
+        fg = _f32c(feats_geo)
+        fc = _f32c(feats_col) if spec.color_stage else None
+        aff = _f32c(affine) if (affine is not None and spec.color_stage) else None
+        gprm = [_f32c(t) for t in params[:N_PARAM]]
+        cprm = [_f32c(t) for t in params[N_PARAM:]] if spec.color_stage else []
+        rad = spec.radius
+        rad_t = rad.detach().to(device=dev, dtype=torch.float64).reshape(-1).contiguous() if torch.is_tensor(rad) else None
+        if rad_t is not None and rad_t.numel() != R:
+            raise ValueError("shape mis-match for rays and dynamic radius")
+        z = torch.empty(R, S, **f32)
+        pts = torch.empty(P, 3, **f32)
+        t_up, t_dn = torch.empty(P, **f32), torch.empty(P, **f32)
+        I = torch.empty(P, K_NN, dtype=torch.int32, device=dev)
+        D = torch.empty(P, K_NN, **f32)
+        cnt = torch.empty(P, dtype=torch.int32, device=dev)
+        w = torch.empty(P, K_NN, **f32)
+        c_geo = torch.empty(P, C_DIM, **f32)
+        c_col = torch.empty(P, C_DIM, **f32) if spec.color_stage else None
+        has = torch.empty(P, dtype=torch.uint8, device=dev)
+        occ = torch.empty(P, **f32)
+        rgb = torch.empty(P, 3, **f32) if spec.color_stage else None
+        depth, var, color = torch.empty(R, **f32), torch.empty(R, **f32), torch.empty(R, 3, **f32)
+        valid = torch.empty(R, dtype=torch.uint8, device=dev)
+        need_grad = any(ctx.needs_input_grad)
+        lib = _lib.load()
+        tiles = (P + 63) // 64
+        act_g = torch.empty(tiles * 64 * int(lib.hps_mlp_act_floats(MLP_GEO)), **f32) if need_grad else None
+        act_c = torch.empty(tiles * 64 * int(lib.hps_mlp_act_floats(MLP_COL)), **f32) \
+            if (need_grad and spec.color_stage) else None
+        pos = _f32c(spec.cloud_pos).reshape(-1, 3) if spec.tracker else None
+        fill_g, fill_c = _f32c(spec.fill_geo), (_f32c(spec.fill_col) if spec.color_stage else None)
+        zz = _f32c(spec.z_zero) if spec.z_zero is not None else None
+        garr, carr = _ptr_array(gprm), (_ptr_array(cprm) if spec.color_stage else None)
+        st = _stream
+        with torch.cuda.device(dev):
+            _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t),
+                  0.0 if rad_t is not None else float(rad), _lib.ptr(zz), R, S, float(spec.near), float(spec.far),
+                  _lib.ptr(z), _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), st())
+            _call("hps_knn_query", spec.grid._h, _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), P, _lib.ptr(I),
+                  _lib.ptr(D), _lib.ptr(cnt), None, st())
+            _call("hps_interp_fwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(D), _lib.ptr(t_dn), _lib.ptr(cnt),
+                  _lib.ptr(pos), _lib.ptr(fg), _lib.ptr(fc), _lib.ptr(fill_g), _lib.ptr(fill_c), P, int(spec.min_nn),
+                  _lib.ptr(w), _lib.ptr(c_geo), _lib.ptr(c_col), _lib.ptr(has), st())
+            pk = _packed_buffer(MLP_GEO, dev)
+            _call("hps_mlp_pack", MLP_GEO, garr, _lib.ptr(pk), st())
+            _call("hps_mlp_fwd", MLP_GEO, garr, _lib.ptr(pk), _lib.ptr(pts), _lib.ptr(c_geo), None, P, _lib.ptr(occ),
+                  _lib.ptr(act_g), st())
+            if spec.color_stage:
+                pk = _packed_buffer(MLP_COL, dev)
+                _call("hps_mlp_pack", MLP_COL, carr, _lib.ptr(pk), st())
+                _call("hps_mlp_fwd", MLP_COL, carr, _lib.ptr(pk), _lib.ptr(pts), _lib.ptr(c_col), _lib.ptr(aff), P,
+                      _lib.ptr(rgb), _lib.ptr(act_c), st())
+            _call("hps_composite_fwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
+                  float(spec.coef), _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), None, int(spec.min_valid),
+                  _lib.ptr(valid), st())
+        ctx.spec = spec
+        ctx.n_g = len(gprm)
+        ctx.save_for_backward(z, pts, I, w, has, c_geo, c_col, occ, rgb, act_g, act_c, fg, fc, aff, pos, *gprm, *cprm)
+        ctx.mark_non_differentiable(var, valid)
+        return depth, var, color, valid
+
+    @staticmethod
+    def backward(ctx, g_depth, _g_var, g_color, _g_valid):
+        spec = ctx.spec
+        (z, pts, I, w, has, c_geo, c_col, occ, rgb, act_g, act_c, fg, fc, aff, pos) = ctx.saved_tensors[:15]
+        gprm = list(ctx.saved_tensors[15:15 + N_PARAM])
+        cprm = list(ctx.saved_tensors[15 + N_PARAM:])
+        need = ctx.needs_input_grad   # (spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, *params)
+        dev = z.device
+        R, S = z.shape
+        P = R * S
+        f32 = dict(dtype=torch.float32, device=dev)
+        need_p = spec.tracker and (need[1] or need[2])
+        gd = _f32c(g_depth) if g_depth is not None else None
+        gc = _f32c(g_color) if (g_color is not None and spec.color_stage) else None
+        d_occ = torch.empty(P, **f32)
+        d_rgb = torch.empty(P, 3, **f32) if spec.color_stage else None
+        dc_g = torch.empty(P, C_DIM, **f32)
+        dc_c = torch.empty(P, C_DIM, **f32) if spec.color_stage else None
+        want_gw = any(need[7 + i] for i in range(1, N_PARAM))
+        want_cw = spec.color_stage and any(need[7 + N_PARAM + i] for i in range(1, N_PARAM))
+        dg = [torch.zeros_like(t) for t in gprm] if want_gw else None
+        if dg is not None and not need[7]:
+            dg[0] = None
+        dcw = [torch.zeros_like(t) for t in cprm] if want_cw else None
+        if dcw is not None:
+            dcw[0] = None      # the colour embedder matrix is not a parameter (decoder.py:34)
+        dp_g = torch.empty(P, 3, **f32) if need_p else None
+        dp_c = torch.empty(P, 3, **f32) if (need_p and spec.color_stage) else None
+        dp_i = torch.empty(P, 3, **f32) if need_p else None
+        daff = torch.zeros(12, **f32) if (aff is not None and need[6]) else None
+        dfg = torch.zeros_like(fg) if need[4] else None
+        dfc = torch.zeros_like(fc) if (spec.color_stage and need[5]) else None
+        st = _stream
+        with torch.cuda.device(dev):
+            _call("hps_composite_bwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
+                  float(spec.coef), _lib.ptr(gd), _lib.ptr(gc), _lib.ptr(d_rgb), 3, _lib.ptr(d_occ), 1, st())
+            _call("hps_mlp_bwd", MLP_GEO, _ptr_array(gprm), _lib.ptr(pts), _lib.ptr(c_geo), None, _lib.ptr(act_g),
+                  _lib.ptr(d_occ), P, _ptr_array(dg) if dg is not None else None, _lib.ptr(dc_g), _lib.ptr(dp_g), None,
+                  st())
+            if spec.color_stage:
+                _call("hps_mlp_bwd", MLP_COL, _ptr_array(cprm), _lib.ptr(pts), _lib.ptr(c_col), _lib.ptr(aff),
+                      _lib.ptr(act_c), _lib.ptr(d_rgb), P, _ptr_array(dcw) if dcw is not None else None,
+                      _lib.ptr(dc_c), _lib.ptr(dp_c), _lib.ptr(daff), st())
+            if dfg is not None or dfc is not None or need_p:
+                _call("hps_interp_bwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(w), _lib.ptr(has), _lib.ptr(pos),
+                      _lib.ptr(fg), _lib.ptr(fc), _lib.ptr(c_geo), _lib.ptr(c_col), _lib.ptr(dc_g), _lib.ptr(dc_c), P,
+                      _lib.ptr(dfg), _lib.ptr(dfc), _lib.ptr(dp_i), st())
+            g_ro = g_rd = None
+            if need_p:
+                dp = dp_g + dp_i
+                if dp_c is not None:
+                    dp += dp_c
+                g_ro, g_rd = torch.empty(R, 3, **f32), torch.empty(R, 3, **f32)
+                _call("hps_sample_rays_bwd", _lib.ptr(dp), _lib.ptr(z), R, S, _lib.ptr(g_ro), _lib.ptr(g_rd), st())
+        gg = [(g if (g is not None and need[7 + i]) else None) for i, g in enumerate(dg)] if dg else [None] * N_PARAM
+        if spec.color_stage:
+            gcw = [(g if (g is not None and need[7 + N_PARAM + i]) else None) for i, g in enumerate(dcw)] \
+                if dcw else [None] * N_PARAM
+        else:
+            gcw = []
+        return (None, g_ro if need[1] else None, g_rd if need[2] else None, None, dfg, dfc, daff, *gg, *gcw)
+
+
+def render_rays(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, geo_params, col_params):
+    params = list(geo_params) + (list(col_params) if spec.color_stage else [])
+    return _RenderRays.apply(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col if spec.color_stage else None,
+                             affine if spec.color_stage else None, *params)
+
+
+# --------------------------------------------------------------------------------------------------
+# losses
+# --------------------------------------------------------------------------------------------------
+class _MapperLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, color, valid, gt_depth, gt_color, affine, w_color, color_stage):
+        _need_cuda(depth, valid, gt_depth)
+        dev, R = depth.device, depth.shape[0]
+        f32 = dict(dtype=torch.float32, device=dev)
+        d, gdp = _f32c(depth), _f32c(gt_depth).reshape(-1)
+        col = _f32c(color) if color_stage else None
+        gcl = _f32c(gt_color) if color_stage else None
+        aff = _f32c(affine) if (affine is not None and color_stage) else None
+        v = valid.detach().contiguous()
+        v = v.view(torch.uint8) if v.dtype == torch.bool else v.to(torch.uint8)
+        loss = torch.zeros((), **f32)
+        g_depth = torch.empty(R, **f32)
+        g_color = torch.empty(R, 3, **f32) if color_stage else None
+        d_aff = torch.zeros(12, **f32) if aff is not None else None
+        with torch.cuda.device(dev):
+            _call("hps_mapper_loss", _lib.ptr(d), _lib.ptr(col), _lib.ptr(v), _lib.ptr(gdp), _lib.ptr(gcl), _lib.ptr(aff),
+                  float(w_color), R, _lib.ptr(loss), _lib.ptr(g_depth), _lib.ptr(g_color), _lib.ptr(d_aff), _stream())
+        ctx.save_for_backward(g_depth, g_color, d_aff)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        g_depth, g_color, d_aff = ctx.saved_tensors
+        return (g_depth * gout, g_color * gout if g_color is not None else None, None, None, None,
+                d_aff * gout if d_aff is not None else None, None, None)
+
+
+def mapper_loss(depth, color, valid_ray_mask, gt_depth, gt_color, stage, w_color_loss=0.1, affine=None):
+    """Mapper.py:791-856 in one kernel (loss + gradients)."""
+    cs = stage.startswith("color")
+    return _MapperLoss.apply(depth, color if cs else None, valid_ray_mask, gt_depth, gt_color if cs else None,
+                             affine if cs else None, w_color_loss, cs)
+
+
+class _TrackerLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, depth, uncertainty, color, gt_depth, gt_color, w_color, reduce_fn):
+        _need_cuda(depth, uncertainty, gt_depth)
+        dev, R = depth.device, depth.shape[0]
+        f32 = dict(dtype=torch.float32, device=dev)
+        d, u, gdp = _f32c(depth), _f32c(uncertainty), _f32c(gt_depth).reshape(-1)
+        col = _f32c(color) if color is not None else None
+        gcl = _f32c(gt_color) if color is not None else None
+        stats = torch.zeros(2, **f32)
+        stats[1] = R
+        loss = torch.zeros((), **f32)
+        g_depth = torch.empty(R, **f32)
+        g_color = torch.empty(R, 3, **f32) if col is not None else None
+        with torch.cuda.device(dev):
+            _call("hps_tracker_loss_stats", _lib.ptr(d), _lib.ptr(u), _lib.ptr(gdp), R, _lib.ptr(stats), _stream())
+            count = float(R)
+            if reduce_fn is not None:      # rays sharded over ranks: global sum and count (SURVEY 8e)
+                count = float(reduce_fn(stats))
+            _call("hps_tracker_loss", _lib.ptr(d), _lib.ptr(u), _lib.ptr(col), _lib.ptr(gdp), _lib.ptr(gcl),
+                  _lib.ptr(stats), count, float(w_color), R, _lib.ptr(loss), _lib.ptr(g_depth), _lib.ptr(g_color),
+                  _stream())
+        ctx.save_for_backward(g_depth, g_color)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gout):
+        g_depth, g_color = ctx.saved_tensors
+        return g_depth * gout, None, g_color * gout if g_color is not None else None, None, None, None, None
+
+
+def tracker_loss(depth, uncertainty, color, gt_depth, gt_color, w_color_loss=0.5, reduce_fn=None):
+    """Tracker.py:213-231 in two kernels.  reduce_fn(stats[2] = [sum_tmp, n_rays]) all-reduces in place across
+    ranks and returns the global ray count when the batch is sharded."""
+    return _TrackerLoss.apply(depth, uncertainty, color, gt_depth, gt_color, w_color_loss, reduce_fn)

@@ -27,6 +27,9 @@ class Renderer(object):
         self.use_bound = cfg["use_bound"]
         self.crop_edge = 0 if cfg["cam"]["crop_edge"] is None else cfg["cam"]["crop_edge"]
         self.sigmoid_coefficient = r.get("sigmoid_coef_mapper", 0.1)   # owners overwrite it (Mapper.py:51)
+        # Mapper / tracker batches are depth-filtered (common.py:248-254): owners may set this to skip the
+        # zero-depth branch (a handful of tiny device ops per call).
+        self.assume_positive_depth = False
         if self.N_samples > 0 or self.use_bound or self.sample_near_pcl or self.fix_interval or not self.occupancy:
             raise NotImplementedError("only the reference's ScanNet rendering mode is built: N_samples=0, "
                                       "use_bound False, sample_near_pcl False, occupancy True")
@@ -65,38 +68,89 @@ class Renderer(object):
         z[nz, :] = self.near_end_surface * d * (1. - t) + self.far_end_surface * d * t
         return z, nz
 
+    def _z_for_zero_depth(self, gt_depth, device):
+        """linspace(near_end, max(far)) for rays without a depth reading (Renderer.py:133-134,148-153,207-208),
+        evaluated with device ops only (no host synchronisation)."""
+        S = self.N_surface
+        gt = gt_depth.reshape(-1).float()
+        hi = torch.max(gt * 1.2)
+        far_bb = torch.minimum(5 * gt.mean(), hi)
+        far = torch.where(hi > 0, torch.clamp(far_bb, min=0.0).minimum(hi), far_bb)   # clamp(far_bb, 0, max(1.2 d))
+        idx = torch.arange(S, device=device, dtype=torch.float32)
+        step = (far - self.near_end) / (S - 1)
+        return torch.where(idx < S // 2, self.near_end + step * idx, far - step * (S - 1 - idx))
+
     # Renderer.py:84-254
     def render_batch_ray(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None,
                          npc_geo_feats=None, npc_col_feats=None, is_tracker=False, cloud_pos=None,
                          normals=None, dynamic_r_query=None, exposure_feat=None):
+        """One fused kernel sequence (ops.render_rays): sampling, exact neighbour search, interpolation of both
+        feature tables from one neighbour list, both decoders, compositing with the -100 overwrite."""
+        S = self.N_surface
+        N_rays = rays_o.shape[0]
+        if stage not in ("geometry_mid", "color_mid", "geometry_fine", "color_fine"):
+            raise NotImplementedError("stage %r is not live in the reference" % (stage,))
+        level = "mid" if stage.endswith("mid") else "fine"
+        color_stage = stage.startswith("color")
+        if gt_depth is None or torch.numel(gt_depth) == 0:
+            gt_depth = torch.zeros(N_rays, device=device)
+        gt_depth = gt_depth.reshape(-1)
+        if self.use_dynamic_radius:
+            radius = dynamic_r_query[level].reshape(-1)
+            for key in dynamic_r_query.keys():                           # Renderer.py:226-229 (dict mutated)
+                dynamic_r_query[key] = dynamic_r_query[key].reshape(-1, 1).repeat_interleave(S, dim=0)
+        else:
+            radius = npc.get_radius_query()
+        index = npc.get_index(level)
+        geo = getattr(decoders, "geo_decoder_" + level)
+        col = getattr(decoders, "color_decoder_" + level)
+        affine = None
+        if color_stage and exposure_feat is not None and col.encode_exposure:
+            affine = col.mlp_exposure(exposure_feat)                     # decoder.py:608
+        spec = ops.RenderSpec(
+            grid=index.grid_for(radius), radius=radius,
+            z_zero=None if self.assume_positive_depth else self._z_for_zero_depth(gt_depth, device), S=S,
+            near=self.near_end_surface, far=self.far_end_surface, coef=self.sigmoid_coefficient,
+            min_nn=geo.min_nn_num, min_valid=int(S / 2 + 1), color_stage=color_stage, tracker=bool(is_tracker),
+            cloud_pos=cloud_pos[level] if is_tracker else None, fill_geo=decoders._fill("geo", rays_o.device),
+            fill_col=decoders._fill("col", rays_o.device) if color_stage else None)
+        depth, uncertainty, color, valid = ops.render_rays(
+            spec, rays_o, rays_d, gt_depth, npc_geo_feats[level], npc_col_feats[level] if color_stage else None, affine,
+            geo.kernel_params(rays_o.device), col.kernel_params(rays_o.device) if color_stage else None)
+        nz = gt_depth > 0
+        if not self.sample_near_pcl and not self.assume_positive_depth:
+            depth = torch.where(nz, depth, torch.zeros_like(depth))     # Renderer.py:250-251
+        if self.skip_zero_depth_pixel:
+            color = torch.where(nz[:, None], color, torch.zeros_like(color))
+        return depth, uncertainty, color, valid.view(torch.bool)
+
+    def render_batch_ray_modular(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None,
+                                 npc_geo_feats=None, npc_col_feats=None, is_tracker=False, cloud_pos=None,
+                                 normals=None, dynamic_r_query=None, exposure_feat=None):
+        """Same result through the reference's own seams (eval_points -> NICER.forward -> compositing): one autograd
+        Function per kernel.  Kept as the cross-check of the fused path and for callers that hook the seams."""
         S = self.N_surface
         N_rays = rays_o.shape[0]
         if gt_depth is None or torch.numel(gt_depth) == 0:
             gt_depth = torch.zeros(N_rays, device=device)
         z_vals, nz = self.surface_samples(gt_depth, device)
-        n_zero = N_rays - int(nz.sum()) if not bool(nz.all()) else 0
-        if n_zero:                                                       # Renderer.py:133-134,148-153,207-208
-            gt = gt_depth.reshape(-1, 1)
-            far_bb = torch.minimum(5 * gt.mean(), torch.max(gt * 1.2))
-            far = torch.clamp(far_bb, 0, torch.max(gt * 1.2).item()) if torch.max(gt) > 0 else far_bb
-            z_vals[~nz, :] = torch.linspace(self.near_end, float(far), steps=S, device=device).repeat(n_zero, 1)
+        z_vals = torch.where(nz[:, None], z_vals, self._z_for_zero_depth(gt_depth, device)[None, :].expand_as(z_vals))
         pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]      # Renderer.py:218-219
         pointsf = pts.reshape(-1, 3)
         rq = None
         if self.use_dynamic_radius:
             rq = {}
-            for key in dynamic_r_query.keys():                           # Renderer.py:226-229 (dict mutated)
+            for key in dynamic_r_query.keys():
                 dynamic_r_query[key] = dynamic_r_query[key].reshape(-1, 1).repeat_interleave(S, dim=0)
                 rq[key] = dynamic_r_query[key]
         raw, valid_ray_mask, point_mask = self.eval_points(
             pointsf, decoders, npc, stage, device, npc_geo_feats, npc_col_feats, is_tracker, cloud_pos, normals,
             None, ray_pts_num=S, dynamic_r_query=rq, exposure_feat=exposure_feat)
-        # -100 overwrite for no-neighbour points and compositing, fused (Renderer.py:237-242)
         depth, uncertainty, color, _ = ops.composite(raw.reshape(N_rays, S, 4), z_vals, point_mask,
                                                      self.sigmoid_coefficient)
-        if not self.sample_near_pcl and n_zero:
-            depth = torch.where(nz, depth, torch.zeros_like(depth))     # Renderer.py:250-251
-        if self.skip_zero_depth_pixel and n_zero:
+        if not self.sample_near_pcl:
+            depth = torch.where(nz, depth, torch.zeros_like(depth))
+        if self.skip_zero_depth_pixel:
             color = torch.where(nz[:, None], color, torch.zeros_like(color))
         return depth, uncertainty, color, valid_ray_mask
 

@@ -109,11 +109,43 @@ int hps_mlp_bwd(int kind, const float* const* params, const float* p, const floa
  * ---------------------------------------------------------------------------------------------- */
 int hps_composite_fwd(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
                       const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
-                      float* depth, float* var, float* color, float* weights, void* stream);
+                      float* depth, float* var, float* color, float* weights,
+                      int min_valid, uint8_t* valid_ray /* may be NULL: #samples with neighbours >= min_valid */,
+                      void* stream);
 int hps_composite_bwd(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
                       const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
                       const float* g_depth, const float* g_color,
                       float* d_rgb, int d_rgb_stride, float* d_occ, int d_occ_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Depth-guided sampling (Renderer.py:163-229, N_samples = 0) + per-point radius thresholds.
+ *   z[r][s] = near*d*(1-t_s) + far*d*t_s, t = linspace(0,1,S); pts = rays_o + rays_d*z (no FMA);
+ *   rays with gt_depth == 0 take z_zero[s] (S floats on the device, may be NULL -> 0).
+ *   radius: per-RAY float64 radii (may be NULL -> radius_scalar), repeated per sample into t_up/t_dn.
+ * hps_sample_rays_bwd: g_rays_o = sum_s dp, g_rays_d = sum_s dp * z (tracker pose path).
+ * ---------------------------------------------------------------------------------------------- */
+int hps_sample_rays(const float* rays_o, const float* rays_d, const float* gt_depth, const double* radius,
+                    double radius_scalar, const float* z_zero, int64_t R, int S, float near, float far,
+                    float* z, float* pts, float* t_up, float* t_dn, void* stream);
+int hps_sample_rays_bwd(const float* dp, const float* z, int64_t R, int S, float* g_rays_o, float* g_rays_d,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Losses fused with their gradients (Mapper.py:791-856; Tracker.py:213-231).  `loss` (1 float) and
+ * `d_affine` (12 floats) are ACCUMULATED into; g_depth (R) / g_color (R,3) are written.
+ *   mapper: color may be NULL (geometry stages); affine may be NULL (no exposure correction).
+ *   tracker: two passes - hps_tracker_loss_stats accumulates sum_r |gt-d|/sqrt(var+1e-10) into sum_tmp
+ *   (all-reduce it across ranks when rays are sharded), hps_tracker_loss applies the 10*mean outlier mask
+ *   with mean = sum_tmp / count.
+ * ---------------------------------------------------------------------------------------------- */
+int hps_mapper_loss(const float* depth, const float* color, const uint8_t* valid, const float* gt_depth,
+                    const float* gt_color, const float* affine, float w_color, int64_t R, float* loss,
+                    float* g_depth, float* g_color, float* d_affine, void* stream);
+int hps_tracker_loss_stats(const float* depth, const float* var, const float* gt_depth, int64_t R,
+                           float* sum_tmp, void* stream);
+int hps_tracker_loss(const float* depth, const float* var, const float* color, const float* gt_depth,
+                     const float* gt_color, const float* sum_tmp, double count, float w_color, int64_t R,
+                     float* loss, float* g_depth, float* g_color, void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,7 +48,7 @@ def product(scene, device):
     return hps, npc, dec, renderer
 
 
-def mapper_step(hps, npc, dec, renderer, scene, stage, device):
+def mapper_step(hps, npc, dec, renderer, scene, stage, device, modular=False):
     cl, rays, cfg = scene["clouds"], scene["rays"], scene["cfg"]
     level = "mid" if stage.endswith("mid") else "fine"
     gf = {l: cl[l]["geo_feats"].to(device).clone().requires_grad_(True) for l in cl}
@@ -57,14 +57,16 @@ def mapper_step(hps, npc, dec, renderer, scene, stage, device):
     dec.zero_grad()
     rq = {l: cl[l]["radius"].to(device).clone() for l in cl}
     gt_d, gt_c = rays["gt_depth"].to(device), rays["gt_color"].to(device)
-    depth, var, color, valid = renderer.render_batch_ray(
+    render = renderer.render_batch_ray_modular if modular else renderer.render_batch_ray
+    depth, var, color, valid = render(
         npc, dec, rays["rays_d"].to(device), rays["rays_o"].to(device), device, stage, gt_depth=gt_d,
         npc_geo_feats=gf, npc_col_feats=cf, is_tracker=False, cloud_pos=pos, dynamic_r_query=rq,
         exposure_feat=None)
     affine = None
     if stage.startswith("color"):
         affine = getattr(dec, "color_decoder_" + level).mlp_exposure(scene["exposure_feat"].to(device))
-    loss = hps.mapper_loss(depth, color, valid, gt_d, gt_c, stage, cfg["w_color_mapper"], affine)
+    loss_fn = hps.mapper_loss_torch if modular else hps.mapper_loss
+    loss = loss_fn(depth, color, valid, gt_d, gt_c, stage, cfg["w_color_mapper"], affine)
     loss.backward()
     return dict(depth=depth, var=var, color=color, valid=valid, loss=loss, g_geo=gf[level].grad,
                 g_col=cf[level].grad)
@@ -93,7 +95,7 @@ def check_mapper(stage, out, ref, dec, tol=TOL):
     return errs
 
 
-def tracker_step(hps, npc, dec, renderer, scene, ref_inputs, stage, device):
+def tracker_step(hps, npc, dec, renderer, scene, ref_inputs, stage, device, modular=False):
     cl, cfg = scene["clouds"], scene["cfg"]
     K = O.SCANNET_INTRINSICS
     cam = ref_inputs["cam"].to(device).clone().requires_grad_(True)
@@ -106,11 +108,13 @@ def tracker_step(hps, npc, dec, renderer, scene, ref_inputs, stage, device):
     rq = {l: cl[l]["radius"].to(device).clone() for l in cl}
     ro.retain_grad()
     rd.retain_grad()
-    depth, var, color, _ = renderer.render_batch_ray(
+    render = renderer.render_batch_ray_modular if modular else renderer.render_batch_ray
+    depth, var, color, _ = render(
         npc, dec, rd, ro, device, stage, gt_depth=gt_d,
         npc_geo_feats={l: npc.get_geo_feats(l) for l in cl}, npc_col_feats={l: npc.get_col_feats(l) for l in cl},
         is_tracker=True, cloud_pos={l: npc.cloud_pos_tensor(l) for l in cl}, dynamic_r_query=rq, exposure_feat=ef)
-    loss = hps.tracker_loss(depth, var, color, gt_d, gt_c, cfg["w_color_tracker"])
+    loss_fn = hps.tracker_loss_torch if modular else hps.tracker_loss
+    loss = loss_fn(depth, var, color, gt_d, gt_c, cfg["w_color_tracker"])
     loss.backward()
     level = "mid" if stage.endswith("mid") else "fine"
     mexp = getattr(dec, "color_decoder_" + level).mlp_exposure

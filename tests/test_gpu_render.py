@@ -16,20 +16,22 @@ def built(hps):
     return (scene,) + parity.product(scene, DEV)
 
 
+@pytest.mark.parametrize("path", ["fused", "modular"])
 @pytest.mark.parametrize("stage", ["geometry_mid", "color_mid", "geometry_fine", "color_fine"])
-def test_mapper_iteration_matches_reference(built, stage):
+def test_mapper_iteration_matches_reference(built, stage, path):
     scene, hps, npc, dec, renderer = built
     ref = parity.load("render_mapper_small.pt")[stage]
-    out = parity.mapper_step(hps, npc, dec, renderer, scene, stage, DEV)
+    out = parity.mapper_step(hps, npc, dec, renderer, scene, stage, DEV, modular=(path == "modular"))
     errs = parity.check_mapper(stage, out, ref, dec)
     print(stage, errs)
 
 
+@pytest.mark.parametrize("path", ["fused", "modular"])
 @pytest.mark.parametrize("stage", ["color_mid", "color_fine"])
-def test_tracker_iteration_matches_reference(built, stage):
+def test_tracker_iteration_matches_reference(built, stage, path):
     scene, hps, npc, dec, renderer = built
     ref = parity.load("render_tracker_small.pt")
-    out = parity.tracker_step(hps, npc, dec, renderer, scene, ref["inputs"], stage, DEV)
+    out = parity.tracker_step(hps, npc, dec, renderer, scene, ref["inputs"], stage, DEV, modular=(path == "modular"))
     errs = parity.check_tracker(stage, out, ref[stage], scene, ref["inputs"])
     print(stage, errs)
 
@@ -45,6 +47,71 @@ def test_render_batch_does_not_need_dict_copy(built):
                                   npc_geo_feats={l: npc.get_geo_feats(l) for l in cl},
                                   npc_col_feats={l: npc.get_col_feats(l) for l in cl}, dynamic_r_query=rq)
     assert rq["fine"].shape == (rays["rays_d"].shape[0] * 5, 1)
+
+
+def test_sampling_kernel_is_bit_identical_to_torch_ops(built):
+    """hps_sample_rays reproduces the reference's torch expressions bit for bit (points, thresholds)."""
+    scene, hps, npc, dec, renderer = built
+    import ctypes
+    g = torch.Generator().manual_seed(0)
+    R, S = 1000, 5
+    ro = (torch.randn(R, 3, generator=g) * 0.1).to(DEV)
+    rd = torch.randn(R, 3, generator=g).to(DEV)
+    gd = (torch.rand(R, generator=g) * 4 + 0.3).to(DEV)
+    gd[::17] = 0.0
+    rad = (0.04 + 0.12 * torch.rand(R, generator=g, dtype=torch.float64)).to(DEV)
+    rad[::3] = 0.25
+    zz = renderer._z_for_zero_depth(gd, DEV)
+    z = torch.empty(R, S, device=DEV); pts = torch.empty(R * S, 3, device=DEV)
+    t_up = torch.empty(R * S, device=DEV); t_dn = torch.empty(R * S, device=DEV)
+    L = hps._lib
+    hps.ops._call("hps_sample_rays", L.ptr(ro), L.ptr(rd), L.ptr(gd), L.ptr(rad), 0.0, L.ptr(zz), R, S, 0.96, 1.04,
+                  L.ptr(z), L.ptr(pts), L.ptr(t_up), L.ptr(t_dn), hps.ops._stream())
+    z_ref, nz = renderer.surface_samples(gd, DEV)
+    z_ref = torch.where(nz[:, None], z_ref, zz[None, :].expand_as(z_ref))
+    pts_ref = (ro[..., None, :] + rd[..., None, :] * z_ref[..., :, None]).reshape(-1, 3)
+    up_ref, dn_ref = hps.ops.radius_thresholds(rad.repeat_interleave(S), R * S, torch.device(DEV))
+    assert torch.equal(z, z_ref) and torch.equal(pts, pts_ref)
+    assert torch.equal(t_up, up_ref) and torch.equal(t_dn, dn_ref)
+    zc, _ = O.surface_z_vals(gd.cpu())
+    assert torch.equal(z.cpu(), zc)
+
+
+def test_fused_losses_match_torch_expressions(built):
+    scene, hps, npc, dec, renderer = built
+    g = torch.Generator().manual_seed(1)
+    R = 777
+    depth = (torch.rand(R, generator=g) * 3 + 0.5).to(DEV)
+    var = (torch.rand(R, generator=g) * 0.01).to(DEV)
+    color = torch.randn(R, 3, generator=g).to(DEV)
+    gt_d = (depth.cpu() + torch.randn(R, generator=g) * 0.05).to(DEV)
+    gt_d[::11] = 0.0
+    depth[5] = float("nan")
+    gt_c = torch.rand(R, 3, generator=g).to(DEV)
+    valid = (torch.rand(R, generator=g) > 0.1).to(DEV)
+    aff = (torch.tensor([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0.0]) + 0.1 * torch.randn(12, generator=g)).to(DEV)
+    for stage, affine in (("geometry_fine", None), ("color_fine", None), ("color_mid", aff)):
+        outs = []
+        for fn in (hps.mapper_loss, hps.mapper_loss_torch):
+            d, c = depth.clone().requires_grad_(True), color.clone().requires_grad_(True)
+            a = affine.clone().requires_grad_(True) if affine is not None else None
+            loss = fn(d, c, valid, gt_d, gt_c, stage, 0.1, a)
+            (loss * 1.7).backward()
+            outs.append((loss, d.grad, c.grad if stage.startswith("color") else None, a.grad if a is not None else None))
+        assert parity.rel(outs[0][0], outs[1][0]) < 1e-5
+        assert parity.rel(torch.nan_to_num(outs[0][1]), torch.nan_to_num(outs[1][1])) < 1e-6
+        for i in (2, 3):
+            if outs[1][i] is not None:
+                assert parity.rel(outs[0][i], outs[1][i]) < 1e-5
+    depth[5] = 1.0
+    outs = []
+    for fn in (hps.tracker_loss, hps.tracker_loss_torch):
+        d, c = depth.clone().requires_grad_(True), color.clone().requires_grad_(True)
+        loss = fn(d, var, c, gt_d, gt_c, 0.5)
+        loss.backward()
+        outs.append((loss, d.grad, c.grad))
+    assert parity.rel(outs[0][0], outs[1][0]) < 1e-5
+    assert parity.rel(outs[0][1], outs[1][1]) < 1e-5 and parity.rel(outs[0][2], outs[1][2]) < 1e-6
 
 
 def test_render_img_matches_batch_path(built):
