@@ -22,7 +22,7 @@ def _stream():
 # ---- instrumentation: kernel-launch counter and optional CUDA-event timers per C-ABI call -----------
 LAUNCHES = {"n": 0}
 _KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_interp_fwd": 1, "hps_interp_bwd": 1,
-                     "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_composite_fwd": 1,
+                     "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_mlp_tc_pack": 1, "hps_mlp_tc_fwd": 1, "hps_composite_fwd": 1,
                      "hps_composite_bwd": 1, "hps_sample_rays": 1, "hps_sample_rays_bwd": 1, "hps_mapper_loss": 1,
                      "hps_tracker_loss_stats": 1, "hps_tracker_loss": 1}
 TIMERS = None   # set to {} to record (start, end) CUDA events per call name on the current stream
@@ -39,8 +39,8 @@ def _call(name, *args):
     a.record()
     _lib.check(fn(*args))
     b.record()
-    TIMERS.setdefault(name if name != "hps_mlp_fwd" and name != "hps_mlp_bwd" else "%s[%d]" % (name, args[0]),
-                      []).append((a, b))
+    key = "%s[%d]" % (name, args[0]) if name in ("hps_mlp_fwd", "hps_mlp_bwd", "hps_mlp_tc_fwd") else name
+    TIMERS.setdefault(key, []).append((a, b))
 
 
 def _need_cuda(*ts):
@@ -195,14 +195,36 @@ def _ptr_array(ts):
 
 _packed_cache = {}
 
+# Which edition of the decoder forward runs: True = tcgen05 tensor-core kernel (mlp_tc.cu), False = fp32 SIMT
+# kernel (mlp.cu, the parity anchor).  Both fill the same activation workspace for the backward.
+USE_TC = True
 
-def _packed_buffer(kind, device):
-    key = (kind, device)
+
+def _packed_buffer(kind, device, tc=False):
+    key = (kind, device, tc)
     buf = _packed_cache.get(key)
     if buf is None:
-        buf = torch.empty(int(_lib.load().hps_mlp_packed_floats(kind)), dtype=torch.float32, device=device)
+        lib = _lib.load()
+        if tc:
+            buf = torch.empty(int(lib.hps_mlp_tc_packed_bytes(kind)), dtype=torch.uint8, device=device)
+        else:
+            buf = torch.empty(int(lib.hps_mlp_packed_floats(kind)), dtype=torch.float32, device=device)
         _packed_cache[key] = buf
     return buf
+
+
+def _mlp_forward(kind, arr, p_c, c_c, aff, P, out, act, dev):
+    """pack + forward of one decoder on the current stream (tensor-core or SIMT edition)."""
+    if USE_TC:
+        pk = _packed_buffer(kind, dev, tc=True)
+        _call("hps_mlp_tc_pack", kind, arr, _lib.ptr(pk), _stream())
+        _call("hps_mlp_tc_fwd", kind, arr, _lib.ptr(pk), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), P, _lib.ptr(out),
+              _lib.ptr(act), _stream())
+    else:
+        pk = _packed_buffer(kind, dev)
+        _call("hps_mlp_pack", kind, arr, _lib.ptr(pk), _stream())
+        _call("hps_mlp_fwd", kind, arr, _lib.ptr(pk), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), P, _lib.ptr(out),
+              _lib.ptr(act), _stream())
 
 
 class _Mlp(torch.autograd.Function):
@@ -222,12 +244,9 @@ class _Mlp(torch.autograd.Function):
         if need_grad:
             tiles = (P + 63) // 64
             act = torch.empty(tiles * 64 * int(lib.hps_mlp_act_floats(kind)), dtype=torch.float32, device=dev)
-        packed = _packed_buffer(kind, dev)
         arr = _ptr_array(prm)
         with torch.cuda.device(dev):
-            _call("hps_mlp_pack", kind, arr, _lib.ptr(packed), _stream())
-            _call("hps_mlp_fwd", kind, arr, _lib.ptr(packed), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), P,
-                                       _lib.ptr(out), _lib.ptr(act), _stream())
+            _mlp_forward(kind, arr, p_c, c_c, aff, P, out, act, dev)
         ctx.kind = kind
         ctx.has_affine = aff is not None
         ctx.save_for_backward(p_c, c_c, aff, act, *prm)
@@ -385,15 +404,9 @@ class _RenderRays(torch.autograd.Function):
             _call("hps_interp_fwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(D), _lib.ptr(t_dn), _lib.ptr(cnt),
                   _lib.ptr(pos), _lib.ptr(fg), _lib.ptr(fc), _lib.ptr(fill_g), _lib.ptr(fill_c), P, int(spec.min_nn),
                   _lib.ptr(w), _lib.ptr(c_geo), _lib.ptr(c_col), _lib.ptr(has), st())
-            pk = _packed_buffer(MLP_GEO, dev)
-            _call("hps_mlp_pack", MLP_GEO, garr, _lib.ptr(pk), st())
-            _call("hps_mlp_fwd", MLP_GEO, garr, _lib.ptr(pk), _lib.ptr(pts), _lib.ptr(c_geo), None, P, _lib.ptr(occ),
-                  _lib.ptr(act_g), st())
+            _mlp_forward(MLP_GEO, garr, pts, c_geo, None, P, occ, act_g, dev)
             if spec.color_stage:
-                pk = _packed_buffer(MLP_COL, dev)
-                _call("hps_mlp_pack", MLP_COL, carr, _lib.ptr(pk), st())
-                _call("hps_mlp_fwd", MLP_COL, carr, _lib.ptr(pk), _lib.ptr(pts), _lib.ptr(c_col), _lib.ptr(aff), P,
-                      _lib.ptr(rgb), _lib.ptr(act_c), st())
+                _mlp_forward(MLP_COL, carr, pts, c_col, aff, P, rgb, act_c, dev)
             _call("hps_composite_fwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
                   float(spec.coef), _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), None, int(spec.min_valid),
                   _lib.ptr(valid), st())

@@ -214,6 +214,38 @@ def test_mlp_fwd_bwd(hps, golden, kind, P, affine):
     assert torch.equal(out_i, out_d.detach())
 
 
+@pytest.mark.parametrize("kind,P,affine", [("col", 1000, False), ("col", 130, True), ("geo", 1000, False), ("geo", 77, False),
+                                           ("col", 40000, False), ("geo", 40000, False)])
+def test_mlp_tensor_core_forward_matches_simt(hps, golden, kind, P, affine):
+    """tcgen05 edition vs fp32 SIMT edition of the decoder forward: outputs and the activation workspace
+    (consumed by the backward) agree to 1e-5 (split-precision MMA, measured ~1e-6); gradients through the
+    SIMT backward fed by either forward agree to 1e-4."""
+    scene = golden("scene_small.pt")
+    name = "geo_decoder_fine" if kind == "geo" else "color_decoder_fine"
+    g = torch.Generator().manual_seed(P)
+    p = (torch.randn(P, 3, generator=g) * 1.5 + torch.tensor([0.0, 0.0, -2.0])).to(DEV)
+    c = (torch.randn(P, 32, generator=g) * 0.1).to(DEV)
+    ef = (torch.randn(8, generator=g) * 0.5).to(DEV)
+    gout = torch.randn((P,) if kind == "geo" else (P, 3), generator=g).to(DEV)
+    _, _, dec, _ = parity.product(scene, DEV)
+    m = getattr(dec, name)
+    res = {}
+    for tc in (False, True):
+        hps.ops.USE_TC = tc
+        try:
+            m.zero_grad()
+            pd, cd = p.clone().requires_grad_(True), c.clone().requires_grad_(True)
+            out = m(pd, cd, ef if affine else None)
+            (out * gout).sum().backward()
+            res[tc] = (out.detach(), pd.grad, cd.grad, {k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None})
+        finally:
+            hps.ops.USE_TC = True
+    assert parity.rel(res[True][0], res[False][0]) < 1e-5
+    assert parity.rel(res[True][1], res[False][1]) < TOL and parity.rel(res[True][2], res[False][2]) < TOL
+    for k, gq in res[False][3].items():
+        assert parity.rel(res[True][3][k], gq) < TOL, k
+
+
 @pytest.mark.parametrize("R,S", [(257, 5), (64, 8), (33, 12), (1, 5)])
 def test_composite_fwd_bwd(hps, R, S):
     g = torch.Generator().manual_seed(R * S)
