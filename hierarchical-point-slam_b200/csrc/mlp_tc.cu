@@ -4,11 +4,10 @@
 // same inputs / outputs / activation workspace layout, so the two editions are interchangeable and the
 // fp32 SIMT edition stays the parity anchor.
 //
-// Arithmetic: every fp32 operand x is split as x = hi + lo with hi = bf16(x), lo = fp16(x - hi) and each
-// product is evaluated as four tensor-core MMAs  hi*hi + hi*lo + lo*hi + lo*lo  accumulated in fp32 in TMEM.
-// That is a 19-bit-significand product (error ~2^-20 relative, measured 1.3e-6 on the decoder output,
-// see DESIGN.md section 4) - "fp32-faithful" well inside the 1e-4 parity bar, at 4 MMAs instead of the
-// 6 a three-way bf16 split would need.
+// Arithmetic: every fp32 operand x is split as x = hi + lo with hi = fp16(x), lo = fp16(x - hi) (22 significand
+// bits) and each product is evaluated as three tensor-core MMAs  hi*hi + hi*lo + lo*hi  accumulated in fp32 in
+// TMEM: relative error ~2^-22 per product (emulated end to end: 4e-7 on the decoder output, 2e-6 on gradients; a
+// bf16 three-way product gives 1.4e-5 / 8e-5, too close to the 1e-4 parity bar) - see DESIGN.md section 4.
 //
 // Structure (one persistent CTA per SM, 128 sample points per tile, 320 threads):
 //   warp 0      producer: streams pre-swizzled 16 KB weight slabs global -> shared with cp.async.bulk
@@ -24,6 +23,7 @@
 #include "hps_common.cuh"
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 namespace hps {
 namespace tc {
@@ -132,6 +132,20 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// One lane of a converged warp (cute::elect_one_sync).  ptxas recognises elect.sync and issues the following
+// tcgen05 / bulk-copy instructions from a single thread with uniform operands; issuing them under a plain
+// `if (lane == 0)` makes it emit per-thread ELECT/R2UR replay loops (and, with conditional MMAs, miscompiled
+// predicated descriptor moves - observed on CUDA 12.9).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred != 0;
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version 1):
 // start>>4 [0,14) | LBO>>4 [16,30) (=1, unused when swizzled) | SBO>>4 [32,46) (=1024 B between 8-row groups)
 // | version [46,48) = 1 | layout [61,64) = 2 (SWIZZLE_128B)
@@ -150,16 +164,18 @@ __device__ __forceinline__ uint32_t slab_off(int row, int chunk) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
+// x = hi + lo, both fp16 (22 significand bits together).  tcgen05 kind::f16 requires A and B to have the same
+// 16-bit format (a bf16 x fp16 product traps as an illegal instruction on sm_100a), hence fp16 for both halves.
 __device__ __forceinline__ void split16(float x, uint16_t& hi, uint16_t& lo) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    const __half l = __float2half_rn(x - __bfloat162float(h));
-    hi = __bfloat16_as_ushort(h);
+    const __half h = __float2half_rn(x);
+    const __half l = __float2half_rn(x - __half2float(h));
+    hi = __half_as_ushort(h);
     lo = __half_as_ushort(l);
 }
 
 // ---------------------------------------------------------------------------------------------- pack
 // Global image of the weight slabs in consumption order (see Geo::SLABS_PER_TILE):
-//   for layer i: [Wc_i: cols 0..31 bf16 hi, 32..63 fp16 lo]  then for every k-slab s: [W_i hi], [W_i lo]
+//   for layer i: [Wc_i: cols 0..31 fp16 hi, 32..63 fp16 lo]  then for every k-slab s: [W_i hi], [W_i lo]
 //   k-slab order of layer 3 = hidden slabs first, embedding slabs last (matches the A slabs in shared memory)
 //   last slab: output layer, four 16-row mini-slabs [hi s0 | hi s1 | lo s0 | lo s1] (2 KB each; HS of them used)
 template <int KIND>
@@ -252,7 +268,7 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sAhi = smem;                          // AS slabs: [0,HS) hidden, [HS,AS) embedding
     uint8_t* sAlo = sAhi + AS * SLAB;
-    uint8_t* sC = sAlo + AS * SLAB;                // cols 0..31 c hi (bf16), 32..63 c lo (fp16)
+    uint8_t* sC = sAlo + AS * SLAB;                // cols 0..31 c hi, 32..63 c lo (fp16 both)
     uint8_t* sW = sC + SLAB;                       // NST ring stages
     float* sBias = reinterpret_cast<float*>(sW + NST * SLAB);      // [5][2][H]: b_i, bc_i
     uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * 5 * H);
@@ -294,104 +310,111 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        // ================= producer =================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                for (int j = 0; j < G::SLABS_PER_TILE; ++j, ++it) {
-                    const int st = it % NST;
-                    const uint32_t ph = (it / NST) & 1;
-                    mbar_wait(&empty[st], ph ^ 1);
+        // ================= producer (whole warp converged, one elected lane issues) =================
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int j = 0; j < G::SLABS_PER_TILE; ++j, ++it) {
+                const int st = it % NST;
+                mbar_wait(&empty[st], ((it / NST) & 1) ^ 1);
+                if (elect_one()) {
                     mbar_expect_tx(&full[st], SLAB);
                     bulk_g2s(sW + st * SLAB, wimg + (size_t)j * SLAB, SLAB, &full[st]);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t ID_BB = instr_desc(FMT_BF16, FMT_BF16, TILE, H), ID_BF = instr_desc(FMT_BF16, FMT_F16, TILE, H),
-                               ID_FB = instr_desc(FMT_F16, FMT_BF16, TILE, H), ID_FF = instr_desc(FMT_F16, FMT_F16, TILE, H);
-            constexpr uint32_t OD_BB = instr_desc(FMT_BF16, FMT_BF16, TILE, 16), OD_BF = instr_desc(FMT_BF16, FMT_F16, TILE, 16),
-                               OD_FB = instr_desc(FMT_F16, FMT_BF16, TILE, 16), OD_FF = instr_desc(FMT_F16, FMT_F16, TILE, 16);
-            const uint32_t t_a = tmem, t_u = tmem + H, t_o = tmem + 2 * H;
-            const uint32_t aHi = smem_u32(sAhi), aLo = smem_u32(sAlo), aC = smem_u32(sC), aW = smem_u32(sW);
-            uint32_t it = 0, nready = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                for (int layer = 0; layer < 6; ++layer) {
-                    mbar_wait(a_ready, nready & 1);
-                    ++nready;
-                    tc_fence_after();
-                    if (layer < 5) {
-                        // u = c . Wc^T   (K = 32: two k-steps per precision pair)
-                        {
-                            const int st = it % NST;
-                            mbar_wait(&full[st], (it / NST) & 1);
-                            tc_fence_after();
+        // ================= MMA issuer (whole warp converged, one elected lane issues) =================
+        constexpr uint32_t ID = instr_desc(FMT_F16, FMT_F16, TILE, H);
+        constexpr uint32_t OD = instr_desc(FMT_F16, FMT_F16, TILE, 16);
+        const uint32_t t_a = tmem, t_u = tmem + H, t_o = tmem + 2 * H;
+        const uint32_t aHi = smem_u32(sAhi), aLo = smem_u32(sAlo), aC = smem_u32(sC), aW = smem_u32(sW);
+        uint32_t it = 0, nready = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+#pragma unroll 1
+            for (int layer = 0; layer < 6; ++layer) {
+                mbar_wait(a_ready, nready & 1);
+                ++nready;
+                tc_fence_after();
+                if (layer < 5) {
+                    // u = c . Wc^T   (K = 32: two k-steps; c slab / Wc slab hold hi in columns 0..31, lo in 32..63)
+                    {
+                        const int st = it % NST;
+                        mbar_wait(&full[st], (it / NST) & 1);
+                        tc_fence_after();
+                        if (elect_one()) {
                             const uint32_t w = aW + st * SLAB;
 #pragma unroll
                             for (int k = 0; k < 2; ++k) {
                                 const uint64_t ah = smem_desc(aC + k * 32), al = smem_desc(aC + 64 + k * 32);
                                 const uint64_t bh = smem_desc(w + k * 32), bl = smem_desc(w + 64 + k * 32);
-                                tc_mma(t_u, ah, bh, ID_BB, k > 0);
-                                tc_mma(t_u, ah, bl, ID_BF, 1);
-                                tc_mma(t_u, al, bh, ID_FB, 1);
-                                tc_mma(t_u, al, bl, ID_FF, 1);
+                                tc_mma(t_u, ah, bh, ID, k > 0 ? 1u : 0u);
+                                tc_mma(t_u, ah, bl, ID, 1u);
+                                tc_mma(t_u, al, bh, ID, 1u);
                             }
                             tc_commit(&empty[st]);
-                            ++it;
                         }
-                        // a = x . W^T over the layer's k-slabs
-                        const int nks = layer == 0 ? ES : (layer == 3 ? HS + ES : HS);
-                        for (int s = 0; s < nks; ++s) {
-                            // A slab index and number of valid columns
-                            int aslab, cols;
-                            if (layer == 0) { aslab = HS + s; cols = G::e_cols(s); }
-                            else if (layer == 3 && s >= HS) { aslab = s; cols = G::e_cols(s - HS); }
-                            else { aslab = s; cols = G::HCOLS; }
-                            const int st_hi = it % NST;
-                            mbar_wait(&full[st_hi], (it / NST) & 1);
-                            ++it;
-                            const int st_lo = it % NST;
-                            mbar_wait(&full[st_lo], (it / NST) & 1);
-                            ++it;
-                            tc_fence_after();
+                        __syncwarp();
+                        ++it;
+                    }
+                    // a = x . W^T over the layer's k-slabs
+                    const int nks = layer == 0 ? ES : (layer == 3 ? HS + ES : HS);
+#pragma unroll 1
+                    for (int s = 0; s < nks; ++s) {
+                        int aslab, cols;
+                        if (layer == 0) { aslab = HS + s; cols = G::e_cols(s); }
+                        else if (layer == 3 && s >= HS) { aslab = s; cols = G::e_cols(s - HS); }
+                        else { aslab = s; cols = G::HCOLS; }
+                        const int st_hi = it % NST;
+                        mbar_wait(&full[st_hi], (it / NST) & 1);
+                        ++it;
+                        const int st_lo = it % NST;
+                        mbar_wait(&full[st_lo], (it / NST) & 1);
+                        ++it;
+                        tc_fence_after();
+                        if (elect_one()) {
                             const uint32_t wh = aW + st_hi * SLAB, wl = aW + st_lo * SLAB;
                             const uint32_t xh = aHi + aslab * SLAB, xl = aLo + aslab * SLAB;
                             const int nk = G::ksteps(cols);
+#pragma unroll 1
                             for (int k = 0; k < nk; ++k) {
                                 const uint64_t ah = smem_desc(xh + k * 32), al = smem_desc(xl + k * 32);
                                 const uint64_t bh = smem_desc(wh + k * 32), bl = smem_desc(wl + k * 32);
-                                tc_mma(t_a, ah, bh, ID_BB, (s > 0 || k > 0) ? 1u : 0u);
-                                tc_mma(t_a, ah, bl, ID_BF, 1);
-                                tc_mma(t_a, al, bh, ID_FB, 1);
-                                tc_mma(t_a, al, bl, ID_FF, 1);
+                                tc_mma(t_a, ah, bh, ID, (s > 0 || k > 0) ? 1u : 0u);
+                                tc_mma(t_a, ah, bl, ID, 1u);
+                                tc_mma(t_a, al, bh, ID, 1u);
                             }
                             tc_commit(&empty[st_hi]);
                             tc_commit(&empty[st_lo]);
                         }
-                    } else {
-                        // output layer: out[128 x 16] = y_4 . Wo^T
-                        const int st = it % NST;
-                        mbar_wait(&full[st], (it / NST) & 1);
-                        tc_fence_after();
+                        __syncwarp();
+                    }
+                } else {
+                    // output layer: out[128 x 16] = y_4 . Wo^T  (mini-slabs [hi s0 | hi s1 | lo s0 | lo s1], 2 KB each)
+                    const int st = it % NST;
+                    mbar_wait(&full[st], (it / NST) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
                         const uint32_t w = aW + st * SLAB;
+#pragma unroll 1
                         for (int s = 0; s < HS; ++s) {
                             const int nk = G::ksteps(G::HCOLS);
+#pragma unroll 1
                             for (int k = 0; k < nk; ++k) {
                                 const uint64_t ah = smem_desc(aHi + s * SLAB + k * 32), al = smem_desc(aLo + s * SLAB + k * 32);
                                 const uint64_t bh = smem_desc(w + s * 2048 + k * 32), bl = smem_desc(w + (2 + s) * 2048 + k * 32);
-                                tc_mma(t_o, ah, bh, OD_BB, (s > 0 || k > 0) ? 1u : 0u);
-                                tc_mma(t_o, ah, bl, OD_BF, 1);
-                                tc_mma(t_o, al, bh, OD_FB, 1);
-                                tc_mma(t_o, al, bl, OD_FF, 1);
+                                tc_mma(t_o, ah, bh, OD, (s > 0 || k > 0) ? 1u : 0u);
+                                tc_mma(t_o, ah, bl, OD, 1u);
+                                tc_mma(t_o, al, bh, OD, 1u);
                             }
                         }
                         tc_commit(&empty[st]);
-                        ++it;
                     }
-                    tc_commit(acc_ready);
+                    __syncwarp();
+                    ++it;
                 }
+                if (elect_one()) tc_commit(acc_ready);
+                __syncwarp();
             }
         }
     } else {
@@ -565,7 +588,8 @@ int launch_fwd(const float* const* params, const void* img, const float* p, cons
         configured = true;
     }
     const int num_tiles = (int)ceil_div(P, TILE);
-    const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+    int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+    if (const char* e = getenv("HPS_TC_GRID")) grid = atoi(e) < grid ? atoi(e) : grid;   // debug aid
     mlp_fwd_tc_kernel<KIND><<<grid, NTHR, smem, s>>>(prm, reinterpret_cast<const uint8_t*>(img), p, c, affine, P,
                                                      num_tiles, out, act);
     return 0;

@@ -93,7 +93,7 @@ int64_t hps_mlp_packed_floats(int kind);  /* size of the transposed-weight works
 int hps_mlp_pack(int kind, const float* const* params, float* packed, void* stream);
 int hps_mlp_fwd(int kind, const float* const* params, const float* packed, const float* p, const float* c,
                 const float* affine, int64_t P, float* out, float* act, void* stream);
-/* Tensor-core edition of the forward (tcgen05.mma + TMEM, bf16-hi / fp16-lo split operands, four MMAs per
+/* Tensor-core edition of the forward (tcgen05.mma + TMEM, fp16 hi + fp16 lo split operands, three MMAs per
  * product, fp32 accumulation): same inputs, outputs and `act` layout as hps_mlp_fwd, so hps_mlp_bwd consumes
  * its workspace unchanged.  `packed` here is the swizzled 16-bit weight-slab image written by
  * hps_mlp_tc_pack (hps_mlp_tc_packed_bytes(kind) bytes, 16-byte aligned).                             */

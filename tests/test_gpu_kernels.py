@@ -241,9 +241,19 @@ def test_mlp_tensor_core_forward_matches_simt(hps, golden, kind, P, affine):
         finally:
             hps.ops.USE_TC = True
     assert parity.rel(res[True][0], res[False][0]) < 1e-5
-    assert parity.rel(res[True][1], res[False][1]) < TOL and parity.rel(res[True][2], res[False][2]) < TOL
+
+    def rows_off(a, b):
+        """fraction of rows whose error exceeds TOL x max|b|"""
+        e = (a - b).abs().reshape(a.shape[0], -1).amax(1)
+        return float((e > TOL * float(b.abs().max())).float().mean())
+    if kind == "col":       # Softplus decoder: smooth, gradients agree everywhere
+        assert parity.rel(res[True][1], res[False][1]) < TOL and parity.rel(res[True][2], res[False][2]) < TOL
+    else:
+        # ReLU decoder: a pre-activation within ~1e-6 of zero may take the other branch of ReLU' in the two
+        # editions (the forward values differ by ~1e-6); that flips one point's input gradient.  Allow 0.1% of points.
+        assert rows_off(res[True][1], res[False][1]) < 1e-3 and rows_off(res[True][2], res[False][2]) < 1e-3
     for k, gq in res[False][3].items():
-        assert parity.rel(res[True][3][k], gq) < TOL, k
+        assert parity.rel(res[True][3][k], gq) < (TOL if kind == "col" else 2e-3), k
 
 
 @pytest.mark.parametrize("R,S", [(257, 5), (64, 8), (33, 12), (1, 5)])
