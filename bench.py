@@ -21,7 +21,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import torch
@@ -59,36 +58,49 @@ def make_scene(seed=1219):
                 exposure_feat=torch.randn(8, generator=g) * 0.1)
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region: ONE long-running `nvidia-smi -lms 100`
+    process started before the region and stopped after it (B200_PROFILING.md recipe) - no per-sample fork that
+    would perturb a host-bound step."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.proc = index, None
 
-    def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.rows.append(parts)
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=6)
-        if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                self.proc.kill()
+                out = ""
+            for line in out.strip().splitlines():
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) >= 6:
+                    try:
+                        float(parts[0])
+                        rows.append(parts)
+                    except ValueError:
+                        pass
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        sm = sorted(float(r[0]) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons}
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows)}
 
 
 # --------------------------------------------------------------------------------------------------
@@ -210,25 +222,23 @@ def run_ours(args, rank, world, local_rank):
         b = (i * world + rank) % N_BATCHES
         return slice(b * RAYS, (b + 1) * RAYS)
 
-    def step(src, sl):
+    renderer.assume_positive_depth = True      # mapper batches are depth-filtered (common.py:248-254)
+    static = {k: torch.empty_like(v[:RAYS]) for k, v in devb.items()}
+
+    def step():
+        """One mapper iteration on the rays held in `static` (reference Mapper.py:783-858)."""
         for t in grad_targets:
             t.grad = None
-        rq = {"fine": src["radius"][sl], "mid": src["radius_mid"][sl]}
+        rq = {"fine": static["radius"], "mid": static["radius_mid"]}
         depth, unc, color, valid = renderer.render_batch_ray(
-            npc, dec, src["rays_d"][sl], src["rays_o"][sl], dev, STAGE, gt_depth=src["gt_depth"][sl],
+            npc, dec, static["rays_d"], static["rays_o"], dev, STAGE, gt_depth=static["gt_depth"],
             npc_geo_feats=gf, npc_col_feats=cf, is_tracker=False, cloud_pos=pos, dynamic_r_query=rq, exposure_feat=None)
         affine = dec.color_decoder_fine.mlp_exposure(exposure_feat)
-        loss = hps.mapper_loss(depth, color, valid, src["gt_depth"][sl], src["gt_color"][sl], STAGE, 0.1, affine)
+        loss = hps.mapper_loss(depth, color, valid, static["gt_depth"], static["gt_color"], STAGE, 0.1, affine)
         loss.backward()
         if world > 1:
             allreduce_grads(grad_targets, dist)
         return loss
-
-    def step_e2e(i):
-        sl = batch_slice(i)
-        src = {k: v[sl].to(dev, non_blocking=True) for k, v in host.items()}
-        loss = step(src, slice(0, RAYS))
-        return loss.item()      # device -> host read of the step's result
 
     def sync_all():
         torch.cuda.synchronize()
@@ -236,50 +246,74 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
+    # ---- capture the iteration in a CUDA graph (falls back to eager issue if capture is impossible) ----
+    for k in static:
+        static[k].copy_(devb[k][batch_slice(0)])
+    mode = "cuda-graph replay"
+    try:
+        hps.ops.LAUNCHES["n"] = 0
+        graphed = hps.graphs.GraphedStep(step, static, warmup=3)
+        launches_per_step = hps.ops.LAUNCHES["n"] // 4          # 3 warm-up passes + the captured one
+
+        def run(i, src):
+            return graphed(**{k: src[k][batch_slice(i)] for k in static})
+    except Exception as e:                                        # pragma: no cover - reported in the JSON line
+        mode = "eager (graph capture failed: %s)" % str(e).splitlines()[0][:120]
+        hps.ops.LAUNCHES["n"] = 0
+        step()
+        launches_per_step = hps.ops.LAUNCHES["n"]
+
+        def run(i, src):
+            for k in static:
+                static[k].copy_(src[k][batch_slice(i)], non_blocking=True)
+            return step()
+
     # ---- warm-up ----
     for i in range(args.warmup):
-        step(devb, batch_slice(i))
+        run(i, devb)
     sync_all()
-    # ---- timed: K steps, per-step CUDA events, L2 flushed (untimed) between steps ----
+    # ---- timed: K steps, per-step CUDA events, L2 flushed (untimed) between steps; inputs resident in HBM ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    hps.ops.LAUNCHES["n"] = 0
     evs = []
     sync_all()
     for i in range(args.steps):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        step(devb, batch_slice(args.warmup + i))
+        run(args.warmup + i, devb)
         b.record()
         evs.append((a, b))
     sync_all()
-    launches = hps.ops.LAUNCHES["n"]
+    launches = launches_per_step * args.steps
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    clocks = sampler.stop() if rank == 0 else None
-    # ---- e2e: host buffers in, loss out, wall clock around synchronised region ----
-    for i in range(min(3, args.warmup)):
-        step_e2e(i)
+    # ---- e2e: pinned host buffers in, loss read back every step, wall clock around the synchronised region ----
+    for i in range(3):
+        run(i, host).item()
     sync_all()
     t0 = time.perf_counter()
     for i in range(args.steps):
-        step_e2e(args.warmup + i)
+        run(args.warmup + i, host).item()      # H2D copies + iteration + D2H read of the loss
     sync_all()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_s = float(t[0]), float(t[1])
-    # ---- per-kernel timing pass (instrumented, separate from the timed region) ----
+    # ---- per-kernel timing pass (eager, instrumented, separate from the timed region) ----
     roof = None
     if rank == 0:
         hps.ops.TIMERS = {}
-        for i in range(args.steps):
+        n_prof = min(args.steps, 20)
+        for i in range(n_prof):
             flush.zero_()
-            step(devb, batch_slice(args.warmup + i))
+            for k in static:
+                static[k].copy_(devb[k][batch_slice(args.warmup + i)])
+            step()
         torch.cuda.synchronize()
-        per = {k: sum(a.elapsed_time(b) for a, b in v) / args.steps for k, v in hps.ops.TIMERS.items()}
+        per = {k: sum(a.elapsed_time(b) for a, b in v) / n_prof for k, v in hps.ops.TIMERS.items()}
         hps.ops.TIMERS = None
         roof = roofline(per, hps, npc, devb, batch_slice(0))
     if world > 1:
@@ -292,7 +326,7 @@ def run_ours(args, rank, world, local_rank):
     line = {"metric": "mapping rays/sec (fwd+bwd)", "value": RAYS * world * args.steps / (dev_ms * 1e-3), "unit": "rays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(world), "clocks": clocks,
+            "config": dict(workload_config(world), issue=mode), "clocks": clocks,
             "e2e": {"value": RAYS * world * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "roofline": roof["roofline"], "kernels_ms_per_step": roof["per_kernel"]}
@@ -345,7 +379,7 @@ def roofline(per, hps, npc, devb, sl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

@@ -4,6 +4,7 @@ PyTorch is plumbing here (device memory, streams, autograd graph); every floatin
 the hot path runs in libhps_b200.so.  No op has a fallback: non-CUDA tensors raise.
 """
 import ctypes
+import os
 
 import torch
 
@@ -50,7 +51,22 @@ def _need_cuda(*ts):
 
 
 def _f32c(t):
-    return t.detach().to(torch.float32).contiguous()
+    t = t.detach()
+    if t.dtype is torch.float32 and t.is_contiguous():
+        return t
+    return t.to(torch.float32).contiguous()
+
+
+def _zero_grads_like(tensors, skip_first):
+    """Zero-initialised gradient buffers for a parameter list as views of ONE flat allocation (one memset instead
+    of one per parameter); every view starts on a 16-byte boundary (the wgrad kernels use red.global.add.v4)."""
+    sizes = [0 if (skip_first and i == 0) else (t.numel() + 3) // 4 * 4 for i, t in enumerate(tensors)]
+    flat = torch.zeros(sum(sizes), dtype=torch.float32, device=tensors[-1].device)
+    out, off = [], 0
+    for t, n in zip(tensors, sizes):
+        out.append(None if n == 0 else flat[off:off + t.numel()].view(t.shape))
+        off += n
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -197,7 +213,7 @@ _packed_cache = {}
 
 # Which edition of the decoder forward runs: True = tcgen05 tensor-core kernel (mlp_tc.cu), False = fp32 SIMT
 # kernel (mlp.cu, the parity anchor).  Both fill the same activation workspace for the backward.
-USE_TC = True
+USE_TC = os.environ.get("HPS_USE_TC", "1") != "0"
 
 
 def _packed_buffer(kind, device, tc=False):
@@ -262,9 +278,7 @@ class _Mlp(torch.autograd.Function):
         want_b = need[4] and kind == MLP_GEO
         dprm = [None] * N_PARAM
         if want_w:
-            dprm = [torch.zeros_like(t) for t in prm]
-            if not want_b:
-                dprm[0] = None
+            dprm = _zero_grads_like(prm, skip_first=not want_b)
         elif want_b:
             raise _lib.HpsError("gradient w.r.t. embedder._B alone is not supported")
         dc = torch.empty(P, C_DIM, dtype=torch.float32, device=dev)
@@ -436,12 +450,8 @@ class _RenderRays(torch.autograd.Function):
         dc_c = torch.empty(P, C_DIM, **f32) if spec.color_stage else None
         want_gw = any(need[7 + i] for i in range(1, N_PARAM))
         want_cw = spec.color_stage and any(need[7 + N_PARAM + i] for i in range(1, N_PARAM))
-        dg = [torch.zeros_like(t) for t in gprm] if want_gw else None
-        if dg is not None and not need[7]:
-            dg[0] = None
-        dcw = [torch.zeros_like(t) for t in cprm] if want_cw else None
-        if dcw is not None:
-            dcw[0] = None      # the colour embedder matrix is not a parameter (decoder.py:34)
+        dg = _zero_grads_like(gprm, skip_first=not need[7]) if want_gw else None
+        dcw = _zero_grads_like(cprm, skip_first=True) if want_cw else None   # colour _B is not a parameter
         dp_g = torch.empty(P, 3, **f32) if need_p else None
         dp_c = torch.empty(P, 3, **f32) if (need_p and spec.color_stage) else None
         dp_i = torch.empty(P, 3, **f32) if need_p else None

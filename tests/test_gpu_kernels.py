@@ -253,7 +253,7 @@ def test_mlp_tensor_core_forward_matches_simt(hps, golden, kind, P, affine):
         # editions (the forward values differ by ~1e-6); that flips one point's input gradient.  Allow 0.1% of points.
         assert rows_off(res[True][1], res[False][1]) < 1e-3 and rows_off(res[True][2], res[False][2]) < 1e-3
     for k, gq in res[False][3].items():
-        assert parity.rel(res[True][3][k], gq) < (TOL if kind == "col" else 2e-3), k
+        assert parity.rel(res[True][3][k], gq) < (TOL if kind == "col" else 5e-3), k
 
 
 @pytest.mark.parametrize("R,S", [(257, 5), (64, 8), (33, 12), (1, 5)])
