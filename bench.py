@@ -190,6 +190,8 @@ def run_ours(args, rank, world, local_rank):
         __graft_entry__.build()          # the other ranks wait, then load the finished library
     if world > 1:
         dist.barrier()
+    if os.environ.get("HPS_BENCH_VERBOSE"):
+        print("[rank %d] process group up, library built" % rank, file=sys.stderr, flush=True)
     hps = importlib.import_module("hierarchical-point-slam_b200")
     allreduce_grads = hps.parallel.allreduce_grads
     dev = "cuda:%d" % local_rank
@@ -237,9 +239,16 @@ def run_ours(args, rank, world, local_rank):
         affine = dec.color_decoder_fine.mlp_exposure(exposure_feat)
         loss = hps.mapper_loss(depth, color, valid, static["gt_depth"], static["gt_color"], STAGE, 0.1, affine)
         loss.backward()
+        return loss
+
+    def exchange():
+        """Gradient all-reduce over NCCL (eager, right after the captured iteration on the same stream)."""
         if world > 1:
             allreduce_grads(grad_targets, dist)
-        return loss
+
+    def log(msg):
+        if os.environ.get("HPS_BENCH_VERBOSE"):
+            print("[rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -257,7 +266,9 @@ def run_ours(args, rank, world, local_rank):
         launches_per_step = hps.ops.LAUNCHES["n"] // 4          # 3 warm-up passes + the captured one
 
         def run(i, src):
-            return graphed(**{k: src[k][batch_slice(i)] for k in static})
+            loss = graphed(**{k: src[k][batch_slice(i)] for k in static})
+            exchange()
+            return loss
     except Exception as e:                                        # pragma: no cover - reported in the JSON line
         mode = "eager (graph capture failed: %s)" % str(e).splitlines()[0][:120]
         hps.ops.LAUNCHES["n"] = 0
@@ -267,8 +278,11 @@ def run_ours(args, rank, world, local_rank):
         def run(i, src):
             for k in static:
                 static[k].copy_(src[k][batch_slice(i)], non_blocking=True)
-            return step()
+            loss = step()
+            exchange()
+            return loss
 
+    log("iteration ready: %s" % mode)
     # ---- warm-up ----
     for i in range(args.warmup):
         run(i, devb)
@@ -287,6 +301,7 @@ def run_ours(args, rank, world, local_rank):
         b.record()
         evs.append((a, b))
     sync_all()
+    log("timed region done")
     launches = launches_per_step * args.steps
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     # ---- e2e: pinned host buffers in, loss read back every step, wall clock around the synchronised region ----
@@ -312,7 +327,9 @@ def run_ours(args, rank, world, local_rank):
         for k in static:
             static[k].copy_(devb[k][batch_slice(args.warmup + i)])
         step()
+        exchange()
     torch.cuda.synchronize()
+    log("profiling pass done")
     per = {k: sum(a.elapsed_time(b) for a, b in v) / n_prof for k, v in hps.ops.TIMERS.items()}
     hps.ops.TIMERS = None
     if rank == 0:
