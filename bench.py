@@ -173,6 +173,7 @@ def workload_config(n_gpus):
             "rays_per_gpu": RAYS, "global_rays": RAYS * n_gpus, "fine_points": N_FINE, "mid_points": N_MID,
             "cloud_density": "extent_scale %.0f (~2.7k pts/m^2)" % EXTENT,
             "l2": "flushed between steps (256 MiB memset, untimed); %d distinct ray batches cycled" % N_BATCHES,
+            "live_rows": "frustum-selected rows of the fine level are the optimised leaves (reference frustum_feature_selection)",
             "parallelism": "rays sharded x%d, cloud replicated, gradient all-reduce (NCCL)" % n_gpus if n_gpus > 1 else "single GPU"}
 
 
@@ -214,11 +215,21 @@ def run_ours(args, rank, world, local_rank):
     host["radius_mid"] = scene["radius_mid"].pin_memory()
     devb = {k: v.to(dev) for k, v in host.items()}
     exposure_feat = scene["exposure_feat"].to(dev)
-    gf = {l: npc.get_geo_feats(l).clone().requires_grad_(l == "fine") for l in ("fine", "mid")}
-    cf = {l: npc.get_col_feats(l).clone().requires_grad_(l == "fine") for l in ("fine", "mid")}
+    # Frustum feature selection (Mapper.py:194-250, 512-536): the rows of the fine level that project into the
+    # frame (+20 px) are the live, optimised rows; the others are frozen.  Identity pose, ScanNet intrinsics.
+    K = cfg["cam"]
+    pf = npc.cloud_pos_tensor("fine")
+    zc = -pf[:, 2]
+    u = K["cx"] + K["fx"] * pf[:, 0] / zc
+    v = K["cy"] - K["fy"] * pf[:, 1] / zc
+    live = (zc > 0) & (u > -20) & (u < K["W"] + 20) & (v > -20) & (v < K["H"] + 20)
+    live_idx = live.nonzero().flatten()
+    lg, lc = hps.LiveRows.pair(npc.get_geo_feats("fine"), npc.get_col_feats("fine"), live_idx)
+    gf = {"fine": lg, "mid": npc.get_geo_feats("mid")}
+    cf = {"fine": lc, "mid": npc.get_col_feats("mid")}
     pos = {l: npc.cloud_pos_tensor(l) for l in ("fine", "mid")}
     params = [p for p in dec.parameters()]
-    grad_targets = [gf["fine"], cf["fine"]] + params
+    grad_targets = [lg.param, lc.param] + params
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def batch_slice(i):
@@ -344,7 +355,7 @@ def run_ours(args, rank, world, local_rank):
     line = {"metric": "mapping rays/sec (fwd+bwd)", "value": RAYS * world * args.steps / (dev_ms * 1e-3), "unit": "rays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(world), issue=mode), "clocks": clocks,
+            "config": dict(workload_config(world), issue=mode, n_live_rows=int(live_idx.numel())), "clocks": clocks,
             "e2e": {"value": RAYS * world * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "roofline": roof["roofline"], "kernels_ms_per_step": roof["per_kernel"]}

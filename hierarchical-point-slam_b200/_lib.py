@@ -23,7 +23,7 @@ SIGNATURES = {
                              ctypes.POINTER(_f32), ctypes.POINTER(_i32), _vp]),
     "hps_knn_query": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "hps_interp_fwd": (_i32, [_vp] * 10 + [_i64, _i32] + [_vp] * 5),
-    "hps_interp_bwd": (_i32, [_vp] * 11 + [_i64] + [_vp] * 4),
+    "hps_interp_bwd": (_i32, [_vp] * 11 + [_i64] + [_vp] * 5),
     "hps_mlp_act_floats": (_i64, [_i32]),
     "hps_mlp_packed_floats": (_i64, [_i32]),
     "hps_mlp_pack": (_i32, [_i32, _vp, _vp, _vp]),

@@ -91,7 +91,8 @@ interp_bwd_kernel(const float* __restrict__ p, const int32_t* __restrict__ I, co
                   const float* __restrict__ feats_a, const float* __restrict__ feats_b,
                   const float* __restrict__ c_a, const float* __restrict__ c_b,
                   const float* __restrict__ dc_a, const float* __restrict__ dc_b, int64_t P,
-                  float* __restrict__ dfeats_a, float* __restrict__ dfeats_b, float* __restrict__ dp) {
+                  float* __restrict__ dfeats_a, float* __restrict__ dfeats_b, float* __restrict__ dp,
+                  const int32_t* __restrict__ row_map) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t pi = (int64_t)blockIdx.x * kInterpWarps + warp;
     if (pi >= P) return;
@@ -123,9 +124,11 @@ interp_bwd_kernel(const float* __restrict__ p, const int32_t* __restrict__ I, co
         const int ij = __shfl_sync(kFull, idx, j);
         float part = 0.f;
         if (wj != 0.f) {
+            // gradient row: the table row itself, or its slot in the compact live-row buffer (-1 = frozen row)
+            const int gj = row_map != nullptr ? __ldg(row_map + ij) : ij;
             if (dc_a != nullptr) {
-                if (dfeats_a != nullptr)
-                    red_add_v4(dfeats_a + (int64_t)ij * kC + ch * 4,
+                if (dfeats_a != nullptr && gj >= 0)
+                    red_add_v4(dfeats_a + (int64_t)gj * kC + ch * 4,
                                make_float4(wj * ga.x, wj * ga.y, wj * ga.z, wj * ga.w));
                 if (tracker) {
                     const float4 f = ldg4(feats_a + (int64_t)ij * kC + ch * 4);
@@ -133,8 +136,8 @@ interp_bwd_kernel(const float* __restrict__ p, const int32_t* __restrict__ I, co
                 }
             }
             if (dc_b != nullptr) {
-                if (dfeats_b != nullptr)
-                    red_add_v4(dfeats_b + (int64_t)ij * kC + ch * 4,
+                if (dfeats_b != nullptr && gj >= 0)
+                    red_add_v4(dfeats_b + (int64_t)gj * kC + ch * 4,
                                make_float4(wj * gb.x, wj * gb.y, wj * gb.z, wj * gb.w));
                 if (tracker) {
                     const float4 f = ldg4(feats_b + (int64_t)ij * kC + ch * 4);
@@ -204,7 +207,8 @@ extern "C" int hps_interp_fwd(const float* p, const int32_t* I, const float* D, 
 extern "C" int hps_interp_bwd(const float* p, const int32_t* I, const float* w, const uint8_t* has,
                               const float* cloud_pos, const float* feats_a, const float* feats_b,
                               const float* c_a, const float* c_b, const float* dc_a, const float* dc_b,
-                              int64_t P, float* dfeats_a, float* dfeats_b, float* dp, void* stream) {
+                              int64_t P, float* dfeats_a, float* dfeats_b, float* dp, const int32_t* row_map,
+                              void* stream) {
     using namespace hps;
     HPS_REQUIRE(P >= 0, "negative point count");
     if (P == 0) return 0;
@@ -213,7 +217,7 @@ extern "C" int hps_interp_bwd(const float* p, const int32_t* I, const float* w, 
     HPS_REQUIRE(dp == nullptr || dc_a == nullptr || (feats_a && c_a), "dp needs feats_a and c_a");
     HPS_REQUIRE(dp == nullptr || dc_b == nullptr || (feats_b && c_b), "dp needs feats_b and c_b");
     interp_bwd_kernel<<<(unsigned)ceil_div(P, kInterpWarps), kInterpWarps * 32, 0, (cudaStream_t)stream>>>(
-        p, I, w, has, cloud_pos, feats_a, feats_b, c_a, c_b, dc_a, dc_b, P, dfeats_a, dfeats_b, dp);
+        p, I, w, has, cloud_pos, feats_a, feats_b, c_a, c_b, dc_a, dc_b, P, dfeats_a, dfeats_b, dp, row_map);
     HPS_LAUNCH_OK();
     return 0;
 }

@@ -170,8 +170,11 @@ class NICER(nn.Module):
         geo = getattr(self, "geo_decoder_" + level)
         color_stage = stage.startswith("color")
         pos = cloud_pos[level] if is_tracker else None
+        gtab, ctab = npc_geo_feats[level], (npc_col_feats[level] if color_stage else None)
+        gtab = gtab.dense() if isinstance(gtab, ops.LiveRows) else gtab
+        ctab = ctab.dense() if isinstance(ctab, ops.LiveRows) else ctab
         c_geo, c_col, has = ops.interpolate(
-            p, npc_geo_feats[level], npc_col_feats[level] if color_stage else None, pos,
+            p, gtab, ctab, pos,
             q.I, q.D, q.t_dn, q.count, self._fill("geo", p.device),
             self._fill("col", p.device) if color_stage else None, geo.min_nn_num, is_tracker)
         ray_mask = ~(has.view(-1, pts_num).sum(1) < int(geo.N_surface / 2 + 1))      # decoder.py:310-311

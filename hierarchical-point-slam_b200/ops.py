@@ -188,7 +188,7 @@ class _Interp(torch.autograd.Function):
                 _call("hps_interp_bwd", 
                     _lib.ptr(p_c), _lib.ptr(I), _lib.ptr(w), _lib.ptr(has), _lib.ptr(pos), _lib.ptr(fa),
                     _lib.ptr(fb), _lib.ptr(c_a), _lib.ptr(c_b), _lib.ptr(dc_a), _lib.ptr(dc_b), P,
-                    _lib.ptr(dfa), _lib.ptr(dfb), _lib.ptr(dp), _stream())
+                    _lib.ptr(dfa), _lib.ptr(dfb), _lib.ptr(dp), None, _stream())
         return dp, dfa, dfb, None, None, None, None, None, None, None, None, None
 
 
@@ -350,12 +350,50 @@ def composite(raw, z, point_mask=None, coef=0.1, want_weights=False):
 
 
 # --------------------------------------------------------------------------------------------------
+# live (frustum-selected) feature rows
+# --------------------------------------------------------------------------------------------------
+class LiveRows:
+    """The rows of a feature table that are being optimised (reference Mapper.py:512-536: frustum-selected rows are
+    cloned into leaf tensors and written back into the full table every iteration, :615-630, :862-874).
+
+    `param` (M,32) is the autograd leaf the optimiser owns; `table` (N,32) is the full, replicated table the
+    kernels gather from.  Passing a LiveRows as npc_geo_feats[level] / npc_col_feats[level] makes the fused
+    render path (a) refresh the live rows of `table` from `param` with one index copy and (b) scatter feature
+    gradients straight into a compact (M,32) buffer through `row_map` - no (N,32) gradient is materialised, and
+    the multi-GPU exchange shrinks from the whole table to the live rows."""
+
+    def __init__(self, table, indices, row_map=None):
+        self.table = table.detach()
+        assert self.table.is_contiguous() and self.table.dtype is torch.float32
+        self.indices = indices.to(device=table.device, dtype=torch.long)
+        if row_map is None:
+            row_map = torch.full((table.shape[0],), -1, dtype=torch.int32, device=table.device)
+            row_map[self.indices] = torch.arange(self.indices.numel(), dtype=torch.int32, device=table.device)
+        self.row_map = row_map
+        self.param = self.table[self.indices].clone().requires_grad_(True)
+
+    @classmethod
+    def pair(cls, geo_table, col_table, indices):
+        a = cls(geo_table, indices)
+        return a, cls(col_table, indices, a.row_map)
+
+    def refresh(self):
+        """table[indices] = param (no autograd)."""
+        with torch.no_grad():
+            self.table.index_copy_(0, self.indices, self.param)
+
+    def dense(self):
+        """Differentiable (N,32) view for code paths that want a plain tensor (reference semantics)."""
+        return self.table.index_put((self.indices,), self.param)
+
+
+# --------------------------------------------------------------------------------------------------
 # fused ray rendering: sampling -> neighbour search -> interpolation -> decoders -> compositing
 # --------------------------------------------------------------------------------------------------
 class RenderSpec:
     """Non-tensor arguments of render_rays (one per call)."""
     __slots__ = ("grid", "radius", "z_zero", "S", "near", "far", "coef", "min_nn", "min_valid", "color_stage",
-                 "tracker", "cloud_pos", "fill_geo", "fill_col")
+                 "tracker", "cloud_pos", "fill_geo", "fill_col", "live_geo", "live_col")
 
     def __init__(self, **kw):
         for k in self.__slots__:
@@ -375,8 +413,24 @@ class _RenderRays(torch.autograd.Function):
         P = R * S
         f32 = dict(dtype=torch.float32, device=dev)
         ro, rd, gd = _f32c(rays_o).reshape(-1, 3), _f32c(rays_d).reshape(-1, 3), _f32c(gt_depth).reshape(-1)
-        fg = _f32c(feats_geo)
-        fc = _f32c(feats_col) if spec.color_stage else None
+        # live-row mode: feats_* are the compact (M,32) leaves; the kernels gather from the refreshed full tables
+        row_map = None
+        if spec.live_geo is not None:
+            spec.live_geo.refresh()
+            fg = spec.live_geo.table
+            row_map = spec.live_geo.row_map
+        else:
+            fg = _f32c(feats_geo)
+        fc = None
+        if spec.color_stage:
+            if spec.live_col is not None:
+                spec.live_col.refresh()
+                fc = spec.live_col.table
+                row_map = spec.live_col.row_map
+            else:
+                fc = _f32c(feats_col)
+        if (spec.live_geo is None) != (spec.live_col is None) and spec.color_stage:
+            raise _lib.HpsError("pass LiveRows for both feature tables of a level or for neither")
         aff = _f32c(affine) if (affine is not None and spec.color_stage) else None
         gprm = [_f32c(t) for t in params[:N_PARAM]]
         cprm = [_f32c(t) for t in params[N_PARAM:]] if spec.color_stage else []
@@ -426,6 +480,8 @@ class _RenderRays(torch.autograd.Function):
                   _lib.ptr(valid), st())
         ctx.spec = spec
         ctx.n_g = len(gprm)
+        ctx.row_map = row_map
+        ctx.n_live = feats_geo.shape[0] if row_map is not None else None
         ctx.save_for_backward(z, pts, I, w, has, c_geo, c_col, occ, rgb, act_g, act_c, fg, fc, aff, pos, *gprm, *cprm)
         ctx.mark_non_differentiable(var, valid)
         return depth, var, color, valid
@@ -456,8 +512,12 @@ class _RenderRays(torch.autograd.Function):
         dp_c = torch.empty(P, 3, **f32) if (need_p and spec.color_stage) else None
         dp_i = torch.empty(P, 3, **f32) if need_p else None
         daff = torch.zeros(12, **f32) if (aff is not None and need[6]) else None
-        dfg = torch.zeros_like(fg) if need[4] else None
-        dfc = torch.zeros_like(fc) if (spec.color_stage and need[5]) else None
+        if ctx.row_map is not None:
+            dfg = torch.zeros(ctx.n_live, C_DIM, **f32) if need[4] else None
+            dfc = torch.zeros(ctx.n_live, C_DIM, **f32) if (spec.color_stage and need[5]) else None
+        else:
+            dfg = torch.zeros_like(fg) if need[4] else None
+            dfc = torch.zeros_like(fc) if (spec.color_stage and need[5]) else None
         st = _stream
         with torch.cuda.device(dev):
             _call("hps_composite_bwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
@@ -472,7 +532,7 @@ class _RenderRays(torch.autograd.Function):
             if dfg is not None or dfc is not None or need_p:
                 _call("hps_interp_bwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(w), _lib.ptr(has), _lib.ptr(pos),
                       _lib.ptr(fg), _lib.ptr(fc), _lib.ptr(c_geo), _lib.ptr(c_col), _lib.ptr(dc_g), _lib.ptr(dc_c), P,
-                      _lib.ptr(dfg), _lib.ptr(dfc), _lib.ptr(dp_i), st())
+                      _lib.ptr(dfg), _lib.ptr(dfc), _lib.ptr(dp_i), _lib.ptr(ctx.row_map), st())
             g_ro = g_rd = None
             if need_p:
                 dp = dp_g + dp_i
@@ -490,6 +550,12 @@ class _RenderRays(torch.autograd.Function):
 
 
 def render_rays(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, geo_params, col_params):
+    spec.live_geo = feats_geo if isinstance(feats_geo, LiveRows) else None
+    spec.live_col = feats_col if (isinstance(feats_col, LiveRows) and spec.color_stage) else None
+    if spec.live_geo is not None:
+        feats_geo = spec.live_geo.param
+    if isinstance(feats_col, LiveRows):
+        feats_col = feats_col.param
     params = list(geo_params) + (list(col_params) if spec.color_stage else [])
     return _RenderRays.apply(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col if spec.color_stage else None,
                              affine if spec.color_stage else None, *params)

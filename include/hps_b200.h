@@ -70,12 +70,14 @@ int hps_interp_fwd(const float* p, const int32_t* I, const float* D, const float
                    const float* feats_a, const float* feats_b,
                    const float* fill_a, const float* fill_b, int64_t P, int min_nn,
                    float* w, float* c_a, float* c_b, uint8_t* has, void* stream);
-/* dfeats_* (N,32) are ACCUMULATED into (atomic adds); dp (P,3) is written (tracker variant only). */
+/* dfeats_* are ACCUMULATED into (atomic adds); dp (P,3) is written (tracker variant only).
+ * row_map == NULL: dfeats_* are (N,32), row = table row.  row_map (N) int32: dfeats_* are compact (M,32) buffers
+ * of the live (frustum-selected, Mapper.py:512-536) rows, row_map[row] = slot or -1 for frozen rows.          */
 int hps_interp_bwd(const float* p, const int32_t* I, const float* w, const uint8_t* has,
                    const float* cloud_pos, const float* feats_a, const float* feats_b,
                    const float* c_a, const float* c_b,
                    const float* dc_a, const float* dc_b, int64_t P,
-                   float* dfeats_a, float* dfeats_b, float* dp, void* stream);
+                   float* dfeats_a, float* dfeats_b, float* dp, const int32_t* row_map, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Decoder MLPs (decoder.py:274-342 MLP_geometry.forward, :561-618 MLP_color.forward; K3).

@@ -36,6 +36,40 @@ def test_tracker_iteration_matches_reference(built, stage, path):
     print(stage, errs)
 
 
+@pytest.mark.parametrize("stage", ["geometry_fine", "color_fine"])
+def test_live_rows_compact_gradients(built, stage):
+    """LiveRows (frustum-selected rows as compact leaves, Mapper.py:512-536) gives the same forward and, on the
+    live rows, the same gradients as optimising the whole table; frozen rows receive none."""
+    scene, hps, npc, dec, renderer = built
+    cl, rays, cfg = scene["clouds"], scene["rays"], scene["cfg"]
+    level = "fine"
+    ref = parity.mapper_step(hps, npc, dec, renderer, scene, stage, DEV)
+    g = torch.Generator().manual_seed(3)
+    N = cl[level]["points"].shape[0]
+    live_idx = torch.randperm(N, generator=g)[: N * 2 // 3].sort().values.to(DEV)
+    geo_t, col_t = cl[level]["geo_feats"].to(DEV).clone(), cl[level]["col_feats"].to(DEV).clone()
+    lg, lc = hps.LiveRows.pair(geo_t, col_t, live_idx)
+    with torch.no_grad():      # the optimiser moved the live rows since the table was last refreshed
+        geo_t[live_idx] += 1.0
+        col_t[live_idx] -= 1.0
+    gf = {l: (lg if l == level else cl[l]["geo_feats"].to(DEV)) for l in cl}
+    cf = {l: (lc if l == level else cl[l]["col_feats"].to(DEV)) for l in cl}
+    dec.zero_grad()
+    rq = {l: cl[l]["radius"].to(DEV).clone() for l in cl}
+    gt_d, gt_c = rays["gt_depth"].to(DEV), rays["gt_color"].to(DEV)
+    depth, var, color, valid = renderer.render_batch_ray(
+        npc, dec, rays["rays_d"].to(DEV), rays["rays_o"].to(DEV), DEV, stage, gt_depth=gt_d, npc_geo_feats=gf,
+        npc_col_feats=cf, dynamic_r_query=rq)
+    affine = dec.color_decoder_fine.mlp_exposure(scene["exposure_feat"].to(DEV)) if stage.startswith("color") else None
+    hps.mapper_loss(depth, color, valid, gt_d, gt_c, stage, cfg["w_color_mapper"], affine).backward()
+    assert torch.equal(depth, ref["depth"]) and torch.equal(color, ref["color"])
+    assert lg.param.grad.shape == (live_idx.numel(), 32)
+    assert parity.rel(lg.param.grad, ref["g_geo"][live_idx]) < 1e-5
+    if stage.startswith("color"):
+        assert parity.rel(lc.param.grad, ref["g_col"][live_idx]) < 1e-5
+    assert torch.equal(geo_t[live_idx], lg.param.detach())            # table refreshed from the leaves
+
+
 def test_render_batch_does_not_need_dict_copy(built):
     """Renderer.py:226-229 mutates dynamic_r_query in place; the drop-in keeps that visible behaviour."""
     scene, hps, npc, dec, renderer = built
