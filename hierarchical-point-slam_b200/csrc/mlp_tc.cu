@@ -20,158 +20,10 @@
 //               Fourier features and the c tile are produced the same way at the start of a tile.
 // Shared-memory operand layout = the canonical K-major SWIZZLE_128B UMMA layout: slabs of [rows][64 x 16 bit],
 // 8-row / 1024-byte swizzle atoms, 16-byte chunks XORed with (row & 7).
-#include "hps_common.cuh"
-#include <cuda_bf16.h>
-#include <cuda_fp16.h>
-#include <stdlib.h>
+#include "tc_common.cuh"
 
 namespace hps {
 namespace tc {
-
-constexpr int TILE = 128;            // sample points per tile = UMMA M = TMEM lanes
-constexpr int SLAB = 16384;          // bytes: 128 rows x 128 B
-constexpr int NST = 6;               // weight ring stages
-constexpr int NTHR = 320;
-constexpr int EPI_WARP0 = 2;
-constexpr int NEPI = 256;
-constexpr float kTwoPi = 6.283185307179586f;
-
-template <int KIND> struct Cfg;
-template <> struct Cfg<HPS_MLP_GEO> {
-    static constexpr int H = 32, NF = 93, E = 93, NOUT = 1;
-    static constexpr bool CONCAT = false, RELU = true;
-};
-template <> struct Cfg<HPS_MLP_COL> {
-    static constexpr int H = 128, NF = 20, E = 40, NOUT = 3;
-    static constexpr bool CONCAT = true, RELU = false;
-};
-template <int KIND> struct Geo {
-    using C = Cfg<KIND>;
-    static constexpr int HS = (C::H + 63) / 64;                 // hidden slabs
-    static constexpr int ES = (C::E + 63) / 64;                 // embedding slabs
-    static constexpr int AS = HS + ES;                          // A slabs per precision
-    static constexpr int HCOLS = C::H < 64 ? C::H : 64;         // columns used per hidden slab
-    __host__ __device__ static constexpr int e_cols(int s) { return (C::E - 64 * s) < 64 ? (C::E - 64 * s) : 64; }
-    __host__ __device__ static constexpr int ksteps(int cols) { return (cols + 15) / 16; }
-    // slabs consumed per tile: per layer 1 (Wc) + 2 per k-slab, + 1 output slab
-    static constexpr int SLABS_PER_TILE = 5 + 2 * (ES + HS + HS + (HS + ES) + HS) + 1;
-    // TMEM columns: a [0,H), u [H,2H), out [2H, 2H+16)
-    static constexpr int TMEM_COLS = (2 * C::H + 16) <= 128 ? 128 : ((2 * C::H + 16) <= 256 ? 256 : 512);
-    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + (2 * AS + 1 + NST) * SLAB + 2 * 5 * C::H * 4 + 256;
-};
-
-__host__ __device__ constexpr int iW(int i) { return 1 + 4 * i; }
-__host__ __device__ constexpr int iB(int i) { return 2 + 4 * i; }
-__host__ __device__ constexpr int iWc(int i) { return 3 + 4 * i; }
-__host__ __device__ constexpr int iBc(int i) { return 4 + 4 * i; }
-constexpr int iWo = 21, iBo = 22;
-
-struct Ptrs {
-    const float* v[HPS_MLP_NPARAM];
-};
-
-// ---------------------------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    const uint32_t a = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(a), "r"(parity)
-            : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// One lane of a converged warp (cute::elect_one_sync).  ptxas recognises elect.sync and issues the following
-// tcgen05 / bulk-copy instructions from a single thread with uniform operands; issuing them under a plain
-// `if (lane == 0)` makes it emit per-thread ELECT/R2UR replay loops (and, with conditional MMAs, miscompiled
-// predicated descriptor moves - observed on CUDA 12.9).
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred = 0;
-    asm volatile(
-        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
-        "elect.sync rx|px, 0xffffffff;\n\t"
-        "@px mov.s32 %0, 1;\n\t}"
-        : "+r"(pred));
-    return pred != 0;
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version 1):
-// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused when swizzled) | SBO>>4 [32,46) (=1024 B between 8-row groups)
-// | version [46,48) = 1 | layout [61,64) = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A/B 16-bit formats (0 = f16, 1 = bf16), K-major
-__host__ __device__ constexpr uint32_t instr_desc(int afmt, int bfmt, int M, int N) {
-    return (1u << 4) | ((uint32_t)afmt << 7) | ((uint32_t)bfmt << 10) | ((uint32_t)(N >> 3) << 17) |
-           ((uint32_t)(M >> 4) << 24);
-}
-constexpr int FMT_F16 = 0, FMT_BF16 = 1;
-
-// byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a slab
-__device__ __forceinline__ uint32_t slab_off(int row, int chunk) {
-    return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4));
-}
-
-// x = hi + lo, both fp16 (22 significand bits together).  tcgen05 kind::f16 requires A and B to have the same
-// 16-bit format (a bf16 x fp16 product traps as an illegal instruction on sm_100a), hence fp16 for both halves.
-__device__ __forceinline__ void split16(float x, uint16_t& hi, uint16_t& lo) {
-    const __half h = __float2half_rn(x);
-    const __half l = __float2half_rn(x - __half2float(h));
-    hi = __half_as_ushort(h);
-    lo = __half_as_ushort(l);
-}
 
 // ---------------------------------------------------------------------------------------------- pack
 // Global image of the weight slabs in consumption order (see Geo::SLABS_PER_TILE):
@@ -260,9 +112,10 @@ template <int KIND>
 __global__ void __launch_bounds__(NTHR, 1)
 mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __restrict__ p,
                   const float* __restrict__ c, const float* __restrict__ affine, int64_t P, int num_tiles,
-                  float* __restrict__ out, float* __restrict__ act) {
+                  float* __restrict__ out, float* __restrict__ act, uint8_t* __restrict__ ws) {
     using C = Cfg<KIND>;
     using G = Geo<KIND>;
+    using W = Ws<KIND>;
     constexpr int H = C::H, E = C::E, NF = C::NF, NOUT = C::NOUT, HS = G::HS, ES = G::ES, AS = G::AS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -431,6 +284,8 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int64_t pt = (int64_t)tile * TILE + row;
             const bool live = pt < P;
+            uint8_t* xg = ws ? W::x_ptr(ws, tile) : nullptr;          // X slab images of this tile (tensor-core backward)
+            float* ag = ws ? W::a_ptr(ws, tile) : nullptr;
             // ---- tile prologue: Fourier features -> embedding slabs, c -> c slab ----
             {
                 float x0 = 0.f, x1 = 0.f, x2 = 0.f;
@@ -448,17 +303,27 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
                     {
                         split16(s, hi, lo);
                         const int slab = HS + j / 64, cc = j % 64;
-                        const uint32_t off = slab * SLAB + slab_off(row, cc >> 3) + (cc & 7) * 2;
+                        const uint32_t so = slab_off(row, cc >> 3) + (cc & 7) * 2;
+                        const uint32_t off = slab * SLAB + so;
                         *reinterpret_cast<uint16_t*>(sAhi + off) = hi;
                         *reinterpret_cast<uint16_t*>(sAlo + off) = lo;
+                        if (xg) {
+                            *reinterpret_cast<uint16_t*>(xg + W::x_e(0, j / 64) * SLAB + so) = hi;
+                            *reinterpret_cast<uint16_t*>(xg + W::x_e(1, j / 64) * SLAB + so) = lo;
+                        }
                     }
                     if (C::CONCAT) {
                         split16(co, hi, lo);
                         const int e = NF + j;
                         const int slab = HS + e / 64, cc = e % 64;
-                        const uint32_t off = slab * SLAB + slab_off(row, cc >> 3) + (cc & 7) * 2;
+                        const uint32_t so = slab_off(row, cc >> 3) + (cc & 7) * 2;
+                        const uint32_t off = slab * SLAB + so;
                         *reinterpret_cast<uint16_t*>(sAhi + off) = hi;
                         *reinterpret_cast<uint16_t*>(sAlo + off) = lo;
+                        if (xg) {
+                            *reinterpret_cast<uint16_t*>(xg + W::x_e(0, e / 64) * SLAB + so) = hi;
+                            *reinterpret_cast<uint16_t*>(xg + W::x_e(1, e / 64) * SLAB + so) = lo;
+                        }
                     }
                 }
                 // c: this thread converts 16 of the 32 channels
@@ -478,6 +343,10 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
                                                 lo[q * 8 + 4] | (lo[q * 8 + 5] << 16), lo[q * 8 + 6] | (lo[q * 8 + 7] << 16));
                     *reinterpret_cast<uint4*>(sC + slab_off(row, half * 2 + q)) = vh;
                     *reinterpret_cast<uint4*>(sC + slab_off(row, 4 + half * 2 + q)) = vl;
+                    if (xg) {
+                        *reinterpret_cast<uint4*>(xg + W::x_c() * SLAB + slab_off(row, half * 2 + q)) = vh;
+                        *reinterpret_cast<uint4*>(xg + W::x_c() * SLAB + slab_off(row, 4 + half * 2 + q)) = vl;
+                    }
                 }
             }
             fence_proxy_async();
@@ -510,6 +379,7 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
                                 act_tile0[(int64_t)(2 * layer) * H * 64 + n * 64] = av;
                                 act_tile0[(int64_t)(2 * layer + 1) * H * 64 + n * 64] = yv;
                             }
+                            if (ag != nullptr) ag[(layer * H + col0 + cb + j) * TILE + row] = av;
                             split16(yv, hi[j], lo[j]);
                         }
                         const int colabs = col0 + cb;              // first hidden column of this block
@@ -520,9 +390,14 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
                                                         hi[q * 8 + 4] | (hi[q * 8 + 5] << 16), hi[q * 8 + 6] | (hi[q * 8 + 7] << 16));
                             const uint4 vl = make_uint4(lo[q * 8 + 0] | (lo[q * 8 + 1] << 16), lo[q * 8 + 2] | (lo[q * 8 + 3] << 16),
                                                         lo[q * 8 + 4] | (lo[q * 8 + 5] << 16), lo[q * 8 + 6] | (lo[q * 8 + 7] << 16));
-                            const uint32_t off = slab * SLAB + slab_off(row, (cc >> 3) + q);
+                            const uint32_t so = slab_off(row, (cc >> 3) + q);
+                            const uint32_t off = slab * SLAB + so;
                             *reinterpret_cast<uint4*>(sAhi + off) = vh;
                             *reinterpret_cast<uint4*>(sAlo + off) = vl;
+                            if (xg) {
+                                *reinterpret_cast<uint4*>(xg + W::x_y(layer, 0, slab) * SLAB + so) = vh;
+                                *reinterpret_cast<uint4*>(xg + W::x_y(layer, 1, slab) * SLAB + so) = vl;
+                            }
                         }
                     }
                 }
@@ -537,6 +412,11 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
             if (half == 0) {
                 float o[32];
                 tc_ld32(tmem + lane_addr + 2 * H, o);
+                if (ws) {
+                    float* rg = W::raw_ptr(ws, tile) + row * 4;
+#pragma unroll
+                    for (int q = 0; q < NOUT; ++q) rg[q] = o[q] + __ldg(prm.v[iBo] + q);
+                }
                 if (live) {
                     if (NOUT == 1) {
                         out[pt] = o[0] + __ldg(prm.v[iBo]);
@@ -578,7 +458,7 @@ template <int KIND> int launch_pack(const float* const* params, void* img, cudaS
 
 template <int KIND>
 int launch_fwd(const float* const* params, const void* img, const float* p, const float* c, const float* affine,
-               int64_t P, float* out, float* act, cudaStream_t s) {
+               int64_t P, float* out, float* act, void* ws, cudaStream_t s) {
     Ptrs prm;
     for (int i = 0; i < HPS_MLP_NPARAM; ++i) prm.v[i] = params[i];
     const int smem = Geo<KIND>::SMEM_BYTES;
@@ -591,12 +471,18 @@ int launch_fwd(const float* const* params, const void* img, const float* p, cons
     int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
     if (const char* e = getenv("HPS_TC_GRID")) grid = atoi(e) < grid ? atoi(e) : grid;   // debug aid
     mlp_fwd_tc_kernel<KIND><<<grid, NTHR, smem, s>>>(prm, reinterpret_cast<const uint8_t*>(img), p, c, affine, P,
-                                                     num_tiles, out, act);
+                                                     num_tiles, out, act, reinterpret_cast<uint8_t*>(ws));
     return 0;
 }
 
 }  // namespace tc
 }  // namespace hps
+
+extern "C" int64_t hps_mlp_tc_ws_bytes(int kind, int64_t P) {
+    using namespace hps::tc;
+    const int64_t tiles = (P + TILE - 1) / TILE;
+    return tiles * (int64_t)(kind == HPS_MLP_GEO ? Ws<HPS_MLP_GEO>::TILE_BYTES : Ws<HPS_MLP_COL>::TILE_BYTES);
+}
 
 extern "C" int64_t hps_mlp_tc_packed_bytes(int kind) {
     using namespace hps::tc;
@@ -618,7 +504,7 @@ extern "C" int hps_mlp_tc_pack(int kind, const float* const* params, void* packe
 }
 
 extern "C" int hps_mlp_tc_fwd(int kind, const float* const* params, const void* packed, const float* p,
-                              const float* c, const float* affine, int64_t P, float* out, float* act,
+                              const float* c, const float* affine, int64_t P, float* out, float* act, void* ws,
                               void* stream) {
     using namespace hps;
     HPS_REQUIRE(kind == HPS_MLP_GEO || kind == HPS_MLP_COL, "bad decoder kind");
@@ -628,8 +514,8 @@ extern "C" int hps_mlp_tc_fwd(int kind, const float* const* params, const void* 
     HPS_REQUIRE(kind == HPS_MLP_COL || affine == nullptr, "affine is colour-only");
     for (int i = 0; i < HPS_MLP_NPARAM; ++i) HPS_REQUIRE(params[i] != nullptr, "null parameter pointer");
     int rc = kind == HPS_MLP_GEO
-                 ? tc::launch_fwd<HPS_MLP_GEO>(params, packed, p, c, affine, P, out, act, (cudaStream_t)stream)
-                 : tc::launch_fwd<HPS_MLP_COL>(params, packed, p, c, affine, P, out, act, (cudaStream_t)stream);
+                 ? tc::launch_fwd<HPS_MLP_GEO>(params, packed, p, c, affine, P, out, act, ws, (cudaStream_t)stream)
+                 : tc::launch_fwd<HPS_MLP_COL>(params, packed, p, c, affine, P, out, act, ws, (cudaStream_t)stream);
     if (rc) return rc;
     HPS_LAUNCH_OK();
     return 0;

@@ -1,0 +1,786 @@
+// Decoder MLP backward on tcgen05 tensor cores: a dgrad chain kernel and a streaming wgrad kernel.
+//
+// Backward of the 5-block decoders (reference: autograd through src/conv_onet/models/decoder.py:316-341 and
+// :583-605).  With y_i = act(a_i) + Wc_i c + bc_i, a_i = W_i x_i + b_i and dy_i the gradient w.r.t. y_i:
+//     da_i = dy_i * act'(a_i)
+//     dgrad :  dx_i = da_i W_i   (-> dy_{i-1} for the hidden columns, -> dE for the embedding columns),
+//              dc  += dy_i Wc_i
+//     wgrad :  dW_i += da_i^T x_i,  db_i += colsum(da_i),  dWc_i += dy_i^T c,  dbc_i += colsum(dy_i)
+// mlp_dgrad_tc_kernel walks the chain 4..0 per 128-point tile with the same warp-specialised structure as the
+// forward (producer / one MMA lane / 8 epilogue warps): dx and dc accumulate in TMEM, the epilogue turns
+// dx into dy_{i-1}, da_{i-1} (act' from the saved pre-activations), writes them as the next A operands into
+// shared memory and dumps them as fp16 hi/lo slab images for the wgrad kernel; bias gradients are warp column
+// sums.  mlp_wgrad_tc_kernel streams the slab images (da_i, dy_i from dgrad; x_i, c from the forward) with
+// cp.async.bulk and contracts over the points with MN-major operands (the images are stored rows = points, so
+// the contraction dimension is the strided one), accumulating dW_i / dWc_i in TMEM across all tiles of a CTA
+// and flushing once with red.global.add.  Same split-fp16 arithmetic as the forward (three MMAs per product).
+#include "tc_common.cuh"
+
+namespace hps {
+namespace tc {
+
+constexpr int NSTB = 5;   // ring stages of the dgrad kernel
+
+struct GradPtrs {
+    float* v[HPS_MLP_NPARAM];
+};
+
+template <int KIND> struct GeoB {
+    using C = Cfg<KIND>;
+    using G = Geo<KIND>;
+    static constexpr int HS = G::HS, ES = G::ES, H = C::H;
+    static constexpr int SLABS_PER_TILE = 9 + 8 * HS;           // see pack_bwd_kernel
+    static constexpr int NE = 64 * ES;                           // padded embedding width
+    static constexpr int T_H = 0, T_E = H, T_DC = H + NE;        // TMEM columns of the dgrad kernel
+    static constexpr int TMEM_COLS = 256;
+    static constexpr int SMEM_BYTES = 1024 + (4 * HS + NSTB) * SLAB + 256;
+    static constexpr int ECPT = NE / 2;                          // embedding columns per epilogue thread
+};
+
+// ---------------------------------------------------------------------------------------------- pack
+// Image consumed by the dgrad kernel, per tile, in order i = 4..0:
+//   [Wc_i^T : (lo,s) mini-slabs of 32 rows (c channel) x 64 cols (h), 4 KB each]
+//   i >= 1     : for every h-slab s: [W_i^T hidden hi: rows = hidden input r, cols = h], [.. lo]
+//   i in {0,3} : [W_i^T embedding hi: per h-slab s a mini-slab of NE rows (e index) x 64 cols (h)], [.. lo]
+template <int KIND>
+__device__ __forceinline__ int bwd_layer_first_slab(int i) {   // i = 4..0 processing order
+    using B = GeoB<KIND>;
+    int n = 0;
+    for (int j = 4; j > i; --j) n += 1 + (j >= 1 ? 2 * B::HS : 0) + ((j == 0 || j == 3) ? 2 : 0);
+    return n;
+}
+
+template <int KIND>
+__global__ void pack_bwd_kernel(Ptrs prm, uint16_t* __restrict__ img) {
+    using C = Cfg<KIND>;
+    using B = GeoB<KIND>;
+    constexpr int H = C::H, E = C::E, HS = B::HS, NE = B::NE;
+    const int total = B::SLABS_PER_TILE * (SLAB / 2);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int slab = idx / (SLAB / 2);
+        const int byte = (idx % (SLAB / 2)) * 2;
+        int layer = 4;
+        while (layer > 0 && slab >= bwd_layer_first_slab<KIND>(layer - 1)) --layer;
+        const int rel = slab - bwd_layer_first_slab<KIND>(layer);
+        const int K = layer == 0 ? E : (layer == 3 ? E + H : H);
+        float val = 0.f;
+        bool want_lo = false;
+        if (rel == 0) {
+            // Wc^T mini-slabs (4 KB = 32 rows x 128 B)
+            const int mini = byte / 4096, b = byte % 4096;
+            const int row = ((b >> 10) << 3) | ((b >> 7) & 7);
+            const int col = ((((b >> 4) & 7) ^ (row & 7)) << 3) + ((b >> 1) & 7);
+            if (mini < 2 * HS) {
+                want_lo = mini >= HS;
+                const int h = (mini % HS) * 64 + col;
+                if (h < H) val = prm.v[iWc(layer)][h * kC + row];
+            }
+        } else {
+            const int nh = layer >= 1 ? 2 * HS : 0;
+            if (rel - 1 < nh) {
+                const int s = (rel - 1) / 2;
+                want_lo = ((rel - 1) & 1) != 0;
+                const int row = ((byte >> 10) << 3) | ((byte >> 7) & 7);        // hidden input index r
+                const int col = ((((byte >> 4) & 7) ^ (row & 7)) << 3) + ((byte >> 1) & 7);
+                const int h = s * 64 + col;
+                if (row < H && h < H) val = prm.v[iW(layer)][h * K + (layer == 3 ? E + row : row)];
+            } else {
+                want_lo = (rel - 1 - nh) == 1;
+                const int msz = NE * 128;                                         // bytes per mini-slab
+                const int s = byte / msz, b = byte % msz;
+                const int row = ((b >> 10) << 3) | ((b >> 7) & 7);                // embedding index e
+                const int col = ((((b >> 4) & 7) ^ (row & 7)) << 3) + ((b >> 1) & 7);
+                const int h = s * 64 + col;
+                if (s < HS && row < E && h < H) val = prm.v[iW(layer)][h * K + row];
+            }
+        }
+        uint16_t hi, lo;
+        split16(val, hi, lo);
+        img[idx] = want_lo ? lo : hi;
+    }
+}
+
+template <bool RELU> __device__ __forceinline__ float act_grad(float a) {
+    if (RELU) return a > 0.f ? 1.f : 0.f;
+    const float t = a * 100.0f;
+    if (t > 20.0f) return 1.f;
+    const float z = __expf(t);
+    return __fdividef(z, z + 1.0f);
+}
+
+__device__ __forceinline__ uint4 pack8(const uint16_t* v) {
+    return make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+}
+
+// ---------------------------------------------------------------------------------------------- dgrad
+template <int KIND>
+__global__ void __launch_bounds__(NTHR, 1)
+mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, uint8_t* __restrict__ ws,
+                    const float* __restrict__ p, const float* __restrict__ affine,
+                    const float* __restrict__ dout, int64_t P, int num_tiles, float* __restrict__ dc,
+                    float* __restrict__ dp, float* __restrict__ daffine) {
+    using C = Cfg<KIND>;
+    using G = Geo<KIND>;
+    using B = GeoB<KIND>;
+    using W = Ws<KIND>;
+    constexpr int H = C::H, E = C::E, NF = C::NF, NOUT = C::NOUT, HS = G::HS, ES = G::ES, NE = B::NE;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sDYhi = smem;
+    uint8_t* sDYlo = sDYhi + HS * SLAB;
+    uint8_t* sDAhi = sDYlo + HS * SLAB;
+    uint8_t* sDAlo = sDAhi + HS * SLAB;
+    uint8_t* sW = sDAlo + HS * SLAB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + NSTB * SLAB);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NSTB;
+    uint64_t* a_ready = bars + 2 * NSTB;
+    uint64_t* acc_ready = bars + 2 * NSTB + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTB + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool want_w = grd.v[iWo] != nullptr;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NSTB; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(a_ready, NEPI);
+        mbar_init(acc_ready, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)B::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int i = threadIdx.x; i < 4 * HS * SLAB / 16; i += NTHR) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        uint32_t it = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int j = 0; j < B::SLABS_PER_TILE; ++j, ++it) {
+                const int st = it % NSTB;
+                mbar_wait(&empty[st], ((it / NSTB) & 1) ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(&full[st], SLAB);
+                    bulk_g2s(sW + st * SLAB, wimg + (size_t)j * SLAB, SLAB, &full[st]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t ID_H = instr_desc(FMT_F16, FMT_F16, TILE, H);
+        constexpr uint32_t ID_E = instr_desc(FMT_F16, FMT_F16, TILE, NE);
+        constexpr uint32_t ID_C = instr_desc(FMT_F16, FMT_F16, TILE, 32);
+        const uint32_t t_h = tmem + B::T_H, t_e = tmem + B::T_E, t_dc = tmem + B::T_DC;
+        const uint32_t aDYh = smem_u32(sDYhi), aDYl = smem_u32(sDYlo), aDAh = smem_u32(sDAhi), aDAl = smem_u32(sDAlo);
+        const uint32_t aW = smem_u32(sW);
+        constexpr int NK = G::ksteps(G::HCOLS);
+        uint32_t it = 0, nready = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+#pragma unroll 1
+            for (int layer = 4; layer >= 0; --layer) {
+                mbar_wait(a_ready, nready & 1);
+                ++nready;
+                tc_fence_after();
+                {   // dc += dy_i . Wc_i
+                    const int st = it % NSTB;
+                    mbar_wait(&full[st], (it / NSTB) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t w = aW + st * SLAB;
+#pragma unroll 1
+                        for (int s = 0; s < HS; ++s) {
+#pragma unroll 1
+                            for (int k = 0; k < NK; ++k) {
+                                const uint64_t ah = smem_desc(aDYh + s * SLAB + k * 32), al = smem_desc(aDYl + s * SLAB + k * 32);
+                                const uint64_t bh = smem_desc(w + s * 4096 + k * 32), bl = smem_desc(w + (HS + s) * 4096 + k * 32);
+                                tc_mma(t_dc, ah, bh, ID_C, (layer < 4 || s > 0 || k > 0) ? 1u : 0u);
+                                tc_mma(t_dc, ah, bl, ID_C, 1u);
+                                tc_mma(t_dc, al, bh, ID_C, 1u);
+                            }
+                        }
+                        tc_commit(&empty[st]);
+                    }
+                    __syncwarp();
+                    ++it;
+                }
+                if (layer >= 1) {   // dx (hidden columns) = da_i . W_i[:, hidden]
+#pragma unroll 1
+                    for (int s = 0; s < HS; ++s) {
+                        const int st_hi = it % NSTB;
+                        mbar_wait(&full[st_hi], (it / NSTB) & 1);
+                        ++it;
+                        const int st_lo = it % NSTB;
+                        mbar_wait(&full[st_lo], (it / NSTB) & 1);
+                        ++it;
+                        tc_fence_after();
+                        if (elect_one()) {
+                            const uint32_t wh = aW + st_hi * SLAB, wl = aW + st_lo * SLAB;
+#pragma unroll 1
+                            for (int k = 0; k < NK; ++k) {
+                                const uint64_t ah = smem_desc(aDAh + s * SLAB + k * 32), al = smem_desc(aDAl + s * SLAB + k * 32);
+                                const uint64_t bh = smem_desc(wh + k * 32), bl = smem_desc(wl + k * 32);
+                                tc_mma(t_h, ah, bh, ID_H, (s > 0 || k > 0) ? 1u : 0u);
+                                tc_mma(t_h, ah, bl, ID_H, 1u);
+                                tc_mma(t_h, al, bh, ID_H, 1u);
+                            }
+                            tc_commit(&empty[st_hi]);
+                            tc_commit(&empty[st_lo]);
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (layer == 0 || layer == 3) {   // dx (embedding columns) = da_i . W_i[:, embedding]
+                    const int st_hi = it % NSTB;
+                    mbar_wait(&full[st_hi], (it / NSTB) & 1);
+                    ++it;
+                    const int st_lo = it % NSTB;
+                    mbar_wait(&full[st_lo], (it / NSTB) & 1);
+                    ++it;
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t wh = aW + st_hi * SLAB, wl = aW + st_lo * SLAB;
+#pragma unroll 1
+                        for (int s = 0; s < HS; ++s) {
+#pragma unroll 1
+                            for (int k = 0; k < NK; ++k) {
+                                const uint64_t ah = smem_desc(aDAh + s * SLAB + k * 32), al = smem_desc(aDAl + s * SLAB + k * 32);
+                                const uint64_t bh = smem_desc(wh + s * (NE * 128) + k * 32), bl = smem_desc(wl + s * (NE * 128) + k * 32);
+                                tc_mma(t_e, ah, bh, ID_E, (s > 0 || k > 0) ? 1u : 0u);
+                                tc_mma(t_e, ah, bl, ID_E, 1u);
+                                tc_mma(t_e, al, bh, ID_E, 1u);
+                            }
+                        }
+                        tc_commit(&empty[st_hi]);
+                        tc_commit(&empty[st_lo]);
+                    }
+                    __syncwarp();
+                }
+                if (elect_one()) tc_commit(acc_ready);
+                __syncwarp();
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int ew = warp - EPI_WARP0;
+        const int quad = warp & 3;
+        const int half = ew >> 2;
+        const int row = quad * 32 + lane;
+        constexpr int CPT = (H >= 64) ? H / 2 : H;
+        const bool col_owner = (H >= 64) || (half == 0);
+        const int col0 = (H >= 64) ? half * CPT : 0;
+        constexpr int ECPT = B::ECPT;
+        const int ecol0 = half * ECPT;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        uint32_t nacc = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int64_t pt = (int64_t)tile * TILE + row;
+            const bool live = pt < P;
+            uint8_t* xg = W::x_ptr(ws, tile);
+            uint8_t* gg = W::g_ptr(ws, tile);
+            const float* ag = W::a_ptr(ws, tile);
+            float de[ECPT];
+#pragma unroll
+            for (int j = 0; j < ECPT; ++j) de[j] = 0.f;
+
+            // dy (32 columns starting at hidden column c0) of layer `layer` -> da, bias gradients, operands, dumps
+            auto emit = [&](int layer, int c0, const float (&dy)[32]) {
+                float da[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) da[j] = dy[j] * act_grad<C::RELU>(ag[(layer * H + c0 + j) * TILE + row]);
+                if (want_w) {
+                    const float s1 = warp_colsum32(dy, lane), s2 = warp_colsum32(da, lane);
+                    red_add(grd.v[iBc(layer)] + c0 + lane, s1);
+                    red_add(grd.v[iB(layer)] + c0 + lane, s2);
+                }
+                uint16_t yh[32], yl[32], ah[32], al[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    split16(dy[j], yh[j], yl[j]);
+                    split16(da[j], ah[j], al[j]);
+                }
+                const int slab = c0 / 64, cc = c0 % 64;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t so = slab_off(row, (cc >> 3) + q);
+                    const uint4 v0 = pack8(yh + q * 8), v1 = pack8(yl + q * 8), v2 = pack8(ah + q * 8), v3 = pack8(al + q * 8);
+                    *reinterpret_cast<uint4*>(sDYhi + slab * SLAB + so) = v0;
+                    *reinterpret_cast<uint4*>(sDYlo + slab * SLAB + so) = v1;
+                    *reinterpret_cast<uint4*>(sDAhi + slab * SLAB + so) = v2;
+                    *reinterpret_cast<uint4*>(sDAlo + slab * SLAB + so) = v3;
+                    if (want_w) {
+                        *reinterpret_cast<uint4*>(gg + W::g_dy(layer, 0, slab) * SLAB + so) = v0;
+                        *reinterpret_cast<uint4*>(gg + W::g_dy(layer, 1, slab) * SLAB + so) = v1;
+                        *reinterpret_cast<uint4*>(gg + W::g_da(layer, 0, slab) * SLAB + so) = v2;
+                        *reinterpret_cast<uint4*>(gg + W::g_da(layer, 1, slab) * SLAB + so) = v3;
+                    }
+                }
+            };
+
+            // ---- output layer (SIMT): d raw, dWo, dbo, daffine, dy_4 ----
+            {
+                float dr[3] = {0.f, 0.f, 0.f};
+                if (live) {
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o) dr[o] = __ldg(dout + pt * NOUT + o);
+                }
+                if (NOUT == 3 && affine != nullptr) {
+                    const float* rg = W::raw_ptr(ws, tile) + row * 4;
+                    const float r[3] = {rg[0], rg[1], rg[2]};
+                    float dl[3];
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) {
+                        const float lin = r[0] * __ldg(affine + cc) + r[1] * __ldg(affine + 3 + cc) +
+                                          r[2] * __ldg(affine + 6 + cc) + __ldg(affine + 9 + cc);
+                        const float s = 1.0f / (1.0f + expf(-lin));
+                        dl[cc] = dr[cc] * s * (1.0f - s);
+                    }
+                    if (daffine != nullptr && half == 0) {
+                        float v[12];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) v[k * 3 + cc] = r[k] * dl[cc];
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) v[9 + cc] = dl[cc];
+#pragma unroll
+                        for (int k = 0; k < 12; ++k) {
+                            float s = v[k];
+                            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(kFull, s, o);
+                            if (lane == 0) red_add(daffine + k, s);
+                        }
+                    }
+#pragma unroll
+                    for (int k = 0; k < 3; ++k)
+                        dr[k] = dl[0] * __ldg(affine + 3 * k) + dl[1] * __ldg(affine + 3 * k + 1) + dl[2] * __ldg(affine + 3 * k + 2);
+                }
+                if (want_w && half == 0) {
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o) {
+                        float s = dr[o];
+                        for (int q = 16; q; q >>= 1) s += __shfl_xor_sync(kFull, s, q);
+                        if (lane == 0) red_add(grd.v[iBo] + o, s);
+                    }
+                }
+                if (col_owner) {
+#pragma unroll 1
+                    for (int cb = 0; cb < CPT; cb += 32) {
+                        const int c0 = col0 + cb;
+                        float dy[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float s = 0.f;
+#pragma unroll
+                            for (int o = 0; o < NOUT; ++o) s = fmaf(dr[o], __ldg(prm.v[iWo] + o * H + c0 + j), s);
+                            dy[j] = s;
+                        }
+                        if (want_w) {   // dWo[o][h] += sum_pt d raw[pt][o] * y_4[pt][h]
+                            float y4[32];
+                            const int slab = c0 / 64, cc = c0 % 64;
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const uint32_t so = slab_off(row, (cc >> 3) + q);
+                                const uint4 vh = *reinterpret_cast<const uint4*>(xg + W::x_y(4, 0, slab) * SLAB + so);
+                                const uint4 vl = *reinterpret_cast<const uint4*>(xg + W::x_y(4, 1, slab) * SLAB + so);
+                                const __half2* hh = reinterpret_cast<const __half2*>(&vh);
+                                const __half2* hl = reinterpret_cast<const __half2*>(&vl);
+#pragma unroll
+                                for (int e2 = 0; e2 < 4; ++e2) {
+                                    const float2 a2 = __half22float2(hh[e2]), b2 = __half22float2(hl[e2]);
+                                    y4[q * 8 + e2 * 2] = a2.x + b2.x;
+                                    y4[q * 8 + e2 * 2 + 1] = a2.y + b2.y;
+                                }
+                            }
+#pragma unroll
+                            for (int o = 0; o < NOUT; ++o) {
+                                float pr[32];
+#pragma unroll
+                                for (int j = 0; j < 32; ++j) pr[j] = dr[o] * y4[j];
+                                const float s = warp_colsum32(pr, lane);
+                                red_add(grd.v[iWo] + o * H + c0 + lane, s);
+                            }
+                        }
+                        emit(4, c0, dy);
+                    }
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(a_ready);
+
+#pragma unroll 1
+            for (int layer = 4; layer >= 0; --layer) {
+                mbar_wait(acc_ready, nacc & 1);
+                ++nacc;
+                tc_fence_after();
+                if (layer == 0 || layer == 3) {
+#pragma unroll 1
+                    for (int eb = 0; eb < ECPT; eb += 32) {
+                        float v[32];
+                        tc_ld32(tmem + lane_addr + B::T_E + ecol0 + eb, v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) de[eb + j] += v[j];
+                    }
+                }
+                if (layer >= 1) {
+                    if (col_owner) {
+#pragma unroll 1
+                        for (int cb = 0; cb < CPT; cb += 32) {
+                            float dy[32];
+                            tc_ld32(tmem + lane_addr + B::T_H + col0 + cb, dy);
+                            emit(layer - 1, col0 + cb, dy);
+                        }
+                    }
+                    tc_fence_before();
+                    fence_proxy_async();
+                    mbar_arrive(a_ready);
+                }
+            }
+            // ---- dc ----
+            if (half == 0) {
+                float v[32];
+                tc_ld32(tmem + lane_addr + B::T_DC, v);
+                if (live) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        *reinterpret_cast<float4*>(dc + pt * kC + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                }
+            }
+            tc_fence_before();
+            // ---- dE -> dp, dB ----
+            const bool want_b = (KIND == HPS_MLP_GEO) && grd.v[0] != nullptr;
+            if (dp != nullptr || want_b) {
+                float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+                if (live) {
+                    x0 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 0));
+                    x1 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 1));
+                    x2 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 2));
+                }
+                float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll 1
+                for (int eb = 0; eb < ECPT; eb += 32) {
+                    float gb0[32], gb1[32], gb2[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int e = ecol0 + eb + j;
+                        float g = 0.f;
+                        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+                        if (e < E && live) {
+                            const int f = C::CONCAT ? (e < NF ? e : e - NF) : e;
+                            b0 = __ldg(prm.v[0] + f);
+                            b1 = __ldg(prm.v[0] + NF + f);
+                            b2 = __ldg(prm.v[0] + 2 * NF + f);
+                            const float arg = fmaf(x2, b2, fmaf(x1, b1, x0 * b0));
+                            float s, co;
+                            sincosf(arg, &s, &co);
+                            g = (C::CONCAT && e >= NF) ? -de[eb + j] * s : de[eb + j] * co;
+                        }
+                        g0 = fmaf(g * kTwoPi, b0, g0);
+                        g1 = fmaf(g * kTwoPi, b1, g1);
+                        g2 = fmaf(g * kTwoPi, b2, g2);
+                        gb0[j] = g * x0;
+                        gb1[j] = g * x1;
+                        gb2[j] = g * x2;
+                    }
+                    if (want_b) {   // dB[d][f] += sum_pt g * x'_d   (geometry decoder: e == f)
+                        const float s0 = warp_colsum32(gb0, lane), s1 = warp_colsum32(gb1, lane), s2 = warp_colsum32(gb2, lane);
+                        const int e = ecol0 + eb + lane;
+                        if (e < E) {
+                            red_add(grd.v[0] + e, s0);
+                            red_add(grd.v[0] + NF + e, s1);
+                            red_add(grd.v[0] + 2 * NF + e, s2);
+                        }
+                    }
+                }
+                if (dp != nullptr && live) {   // dp is zero-initialised by the caller; both column halves add
+                    red_add(dp + pt * 3 + 0, g0);
+                    red_add(dp + pt * 3 + 1, g1);
+                    red_add(dp + pt * 3 + 2, g2);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)B::TMEM_COLS));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- wgrad
+// MN-major SWIZZLE_128B descriptor for an operand stored rows = contraction index (points), 64 columns per slab:
+// LBO = byte distance between consecutive 64-column slabs, SBO = 1024 (8-row groups along the contraction).
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr, uint32_t lbo) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | (64ull << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t instr_desc_mn(int M, int N) {   // both operands MN-major, fp16, f32 accumulate
+    return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int KIND> struct GeoW {
+    using C = Cfg<KIND>;
+    using G = Geo<KIND>;
+    static constexpr int HS = G::HS, ES = G::ES, H = C::H, NE = 64 * ES, NH = 64 * HS;
+    // shared memory: A region [hi: 2 slabs][lo: 2 slabs] (M = 128 = two 64-column atoms; the second atom of a
+    // 32-wide decoder is a zero slab), B region [hi: up to 2 slabs][lo: up to 2 slabs]
+    static constexpr int SMEM_BYTES = 1024 + 9 * SLAB + 256;
+    // TMEM columns per group: group 0 = layers {0,1,2}, group 1 = layers {3,4}
+    __host__ __device__ static constexpr int col_w_h(int layer) {   // dW_i hidden part
+        return layer == 1 ? 0 : layer == 2 ? NH : layer == 3 ? 0 : layer == 4 ? NH : -1;
+    }
+    __host__ __device__ static constexpr int col_w_e(int layer) { return layer == 0 ? 2 * NH : layer == 3 ? 2 * NH : -1; }
+    // dWc_i accumulates as 64 columns: [sum a*c_hi | sum a*c_lo] (the c slab holds hi in columns 0..31, lo in 32..63)
+    __host__ __device__ static constexpr int col_wc(int layer) {
+        return 2 * NH + NE + 64 * (layer < 3 ? layer : layer - 3);
+    }
+    static constexpr int TMEM_COLS = 512;
+    static_assert(2 * NH + NE + 192 <= 512, "TMEM budget");
+};
+
+template <int KIND>
+__global__ void __launch_bounds__(192, 1)
+mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles) {
+    using C = Cfg<KIND>;
+    using GW = GeoW<KIND>;
+    using W = Ws<KIND>;
+    constexpr int H = C::H, E = C::E, HS = GW::HS, ES = GW::ES, NH = GW::NH, NE = GW::NE;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sAhi = smem;                 // 2 slabs
+    uint8_t* sAlo = smem + 2 * SLAB;      // 2 slabs
+    uint8_t* sBhi = smem + 4 * SLAB;      // 2 slabs
+    uint8_t* sBlo = smem + 6 * SLAB;      // 2 slabs
+    uint8_t* sZero = smem + 8 * SLAB;     // (unused padding keeps descriptors inside the allocation)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 9 * SLAB);
+    uint64_t* full = bars;                // operands landed
+    uint64_t* done = bars + 1;            // MMAs of the job finished (smem reusable)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = blockIdx.x & 1;                       // 0: layers {0,1,2}; 1: layers {3,4}
+    const int gsize = (gridDim.x + 1 - group) / 2;          // CTAs in this group
+    const int grank = blockIdx.x >> 1;
+
+    if (threadIdx.x == 0) {
+        mbar_init(full, 1);
+        mbar_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)GW::TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    for (int i = threadIdx.x; i < 9 * SLAB / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    (void)sZero;
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const int l0 = group == 0 ? 0 : 3, l1 = group == 0 ? 2 : 4;
+    bool any_tile = false;
+    if (warp == 0) {
+        // one warp: issue loads, wait, issue MMAs, wait for completion (jobs are short; CTAs overlap each other)
+        uint32_t njob = 0;
+        const uint32_t aAh = smem_u32(sAhi), aAl = smem_u32(sAlo), aBh = smem_u32(sBhi), aBl = smem_u32(sBlo);
+        for (int tile = grank; tile < num_tiles; tile += gsize) {
+            const bool first = !any_tile;
+            any_tile = true;
+            const uint8_t* xg = W::x_ptr(const_cast<uint8_t*>(ws), tile);
+            const uint8_t* gg = W::g_ptr(const_cast<uint8_t*>(ws), tile);
+            for (int layer = l0; layer <= l1; ++layer) {
+                // three jobs per layer: (0) dW hidden part, (1) dW embedding part, (2) dWc
+                for (int job = 0; job < 3; ++job) {
+                    if (job == 0 && layer == 0) continue;
+                    if (job == 1 && !(layer == 0 || layer == 3)) continue;
+                    const int nb = job == 0 ? HS : (job == 1 ? ES : 1);           // B slabs per precision
+                    const int N = job == 0 ? NH : (job == 1 ? NE : 64);
+                    const int tcol = job == 0 ? GW::col_w_h(layer) : (job == 1 ? GW::col_w_e(layer) : GW::col_wc(layer));
+                    if (njob > 0) mbar_wait(done, (njob - 1) & 1);               // previous job released the buffers
+                    if (elect_one()) {
+                        const uint32_t bytes = (uint32_t)(2 * HS + (job == 2 ? 1 : 2 * nb)) * SLAB;
+                        mbar_expect_tx(full, bytes);
+                        for (int s = 0; s < HS; ++s) {
+                            const int ih = job == 2 ? W::g_dy(layer, 0, s) : W::g_da(layer, 0, s);
+                            const int il = job == 2 ? W::g_dy(layer, 1, s) : W::g_da(layer, 1, s);
+                            bulk_g2s(sAhi + s * SLAB, gg + (size_t)ih * SLAB, SLAB, full);
+                            bulk_g2s(sAlo + s * SLAB, gg + (size_t)il * SLAB, SLAB, full);
+                        }
+                        if (job == 2) {
+                            bulk_g2s(sBhi, xg + (size_t)W::x_c() * SLAB, SLAB, full);
+                        } else {
+                            for (int s = 0; s < nb; ++s) {
+                                int ih, il;
+                                if (job == 1) { ih = W::x_e(0, s); il = W::x_e(1, s); }
+                                else { ih = W::x_y(layer - 1, 0, s); il = W::x_y(layer - 1, 1, s); }
+                                bulk_g2s(sBhi + s * SLAB, xg + (size_t)ih * SLAB, SLAB, full);
+                                bulk_g2s(sBlo + s * SLAB, xg + (size_t)il * SLAB, SLAB, full);
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    mbar_wait(full, njob & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t idesc = instr_desc_mn(TILE, N);
+#pragma unroll 1
+                        for (int k = 0; k < TILE / 16; ++k) {                     // contraction over the 128 points
+                            const uint64_t ah = smem_desc_mn(aAh + k * 2048, SLAB), al = smem_desc_mn(aAl + k * 2048, SLAB);
+                            const uint64_t bh = smem_desc_mn(aBh + k * 2048, SLAB), bl = smem_desc_mn(aBl + k * 2048, SLAB);
+                            tc_mma(tmem + tcol, ah, bh, idesc, (!first || k > 0) ? 1u : 0u);
+                            if (job != 2) tc_mma(tmem + tcol, ah, bl, idesc, 1u);   // job 2: B = [c_hi | c_lo] in one slab
+                            tc_mma(tmem + tcol, al, bh, idesc, 1u);
+                        }
+                        tc_commit(done);
+                    }
+                    __syncwarp();
+                    ++njob;
+                }
+            }
+        }
+        if (njob > 0) mbar_wait(done, (njob - 1) & 1);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // ---- flush: TMEM lane = output feature h, columns = input feature ----
+    {
+        bool mine = false;
+        for (int tile = grank; tile < num_tiles; tile += gsize) { mine = true; break; }
+        if (mine && warp >= 2) {
+            const int quad = warp & 3;
+            const int h = quad * 32 + lane;
+            const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+            for (int layer = l0; layer <= l1; ++layer) {
+                const int K = layer == 0 ? E : (layer == 3 ? E + H : H);
+                if (layer >= 1) {
+                    for (int cb = 0; cb < NH; cb += 32) {
+                        float v[32];
+                        tc_ld32(tmem + lane_addr + GW::col_w_h(layer) + cb, v);
+                        if (h < H) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int r = cb + j;
+                                if (r < H) red_add(grd.v[iW(layer)] + (int64_t)h * K + (layer == 3 ? E + r : r), v[j]);
+                            }
+                        }
+                    }
+                }
+                if (layer == 0 || layer == 3) {
+                    for (int cb = 0; cb < NE; cb += 32) {
+                        float v[32];
+                        tc_ld32(tmem + lane_addr + GW::col_w_e(layer) + cb, v);
+                        if (h < H) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (cb + j < E) red_add(grd.v[iW(layer)] + (int64_t)h * K + cb + j, v[j]);
+                        }
+                    }
+                }
+                {
+                    float v[32], v2[32];
+                    tc_ld32(tmem + lane_addr + GW::col_wc(layer), v);
+                    tc_ld32(tmem + lane_addr + GW::col_wc(layer) + 32, v2);
+                    if (h < H) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) red_add(grd.v[iWc(layer)] + (int64_t)h * kC + j, v[j] + v2[j]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)GW::TMEM_COLS));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- launch
+template <int KIND> int launch_pack_bwd(const float* const* params, void* img, cudaStream_t s) {
+    Ptrs prm;
+    for (int i = 0; i < HPS_MLP_NPARAM; ++i) prm.v[i] = params[i];
+    pack_bwd_kernel<KIND><<<148, 256, 0, s>>>(prm, reinterpret_cast<uint16_t*>(img));
+    return 0;
+}
+
+template <int KIND>
+int launch_bwd(const float* const* params, const void* img, void* ws, const float* p, const float* affine,
+               const float* dout, int64_t P, float* const* dparams, float* dc, float* dp, float* daffine,
+               cudaStream_t s) {
+    Ptrs prm;
+    GradPtrs grd;
+    for (int i = 0; i < HPS_MLP_NPARAM; ++i) {
+        prm.v[i] = params[i];
+        grd.v[i] = dparams ? dparams[i] : nullptr;
+    }
+    if (dparams)
+        for (int i = 1; i < HPS_MLP_NPARAM; ++i) HPS_REQUIRE(grd.v[i] != nullptr, "dparams: all Linear gradients or none");
+    static bool configured = false;
+    if (!configured) {
+        HPS_CUDA_OK(cudaFuncSetAttribute(mlp_dgrad_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GeoB<KIND>::SMEM_BYTES));
+        HPS_CUDA_OK(cudaFuncSetAttribute(mlp_wgrad_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         GeoW<KIND>::SMEM_BYTES));
+        configured = true;
+    }
+    const int num_tiles = (int)ceil_div(P, TILE);
+    int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+    mlp_dgrad_tc_kernel<KIND><<<grid, NTHR, GeoB<KIND>::SMEM_BYTES, s>>>(
+        prm, grd, reinterpret_cast<const uint8_t*>(img), reinterpret_cast<uint8_t*>(ws), p, affine, dout, P, num_tiles,
+        dc, dp, daffine);
+    if (dparams) {
+        int wgrid = 2 * num_tiles < kNumSMs ? 2 * num_tiles : kNumSMs;
+        if (wgrid < 2) wgrid = 2;
+        mlp_wgrad_tc_kernel<KIND><<<wgrid, 192, GeoW<KIND>::SMEM_BYTES, s>>>(grd, reinterpret_cast<const uint8_t*>(ws),
+                                                                            num_tiles);
+    }
+    return 0;
+}
+
+}  // namespace tc
+}  // namespace hps
+
+extern "C" int64_t hps_mlp_tc_bwd_packed_bytes(int kind) {
+    using namespace hps::tc;
+    return kind == HPS_MLP_GEO ? (int64_t)GeoB<HPS_MLP_GEO>::SLABS_PER_TILE * SLAB
+                               : (int64_t)GeoB<HPS_MLP_COL>::SLABS_PER_TILE * SLAB;
+}
+
+extern "C" int hps_mlp_tc_bwd_pack(int kind, const float* const* params, void* packed, void* stream) {
+    using namespace hps;
+    HPS_REQUIRE(kind == HPS_MLP_GEO || kind == HPS_MLP_COL, "bad decoder kind");
+    HPS_REQUIRE(params && packed, "null buffer");
+    for (int i = 0; i < HPS_MLP_NPARAM; ++i) HPS_REQUIRE(params[i] != nullptr, "null parameter pointer");
+    int rc = kind == HPS_MLP_GEO ? tc::launch_pack_bwd<HPS_MLP_GEO>(params, packed, (cudaStream_t)stream)
+                                 : tc::launch_pack_bwd<HPS_MLP_COL>(params, packed, (cudaStream_t)stream);
+    if (rc) return rc;
+    HPS_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int hps_mlp_tc_bwd(int kind, const float* const* params, const void* packed, void* ws, const float* p,
+                              const float* affine, const float* dout, int64_t P, float* const* dparams, float* dc,
+                              float* dp, float* daffine, void* stream) {
+    using namespace hps;
+    HPS_REQUIRE(kind == HPS_MLP_GEO || kind == HPS_MLP_COL, "bad decoder kind");
+    HPS_REQUIRE(P >= 0, "negative point count");
+    if (P == 0) return 0;
+    HPS_REQUIRE(params && packed && ws && p && dout && dc, "null buffer");
+    for (int i = 0; i < HPS_MLP_NPARAM; ++i) HPS_REQUIRE(params[i] != nullptr, "null parameter pointer");
+    int rc = kind == HPS_MLP_GEO ? tc::launch_bwd<HPS_MLP_GEO>(params, packed, ws, p, affine, dout, P, dparams, dc, dp,
+                                                               daffine, (cudaStream_t)stream)
+                                 : tc::launch_bwd<HPS_MLP_COL>(params, packed, ws, p, affine, dout, P, dparams, dc, dp,
+                                                               daffine, (cudaStream_t)stream);
+    if (rc) return rc;
+    HPS_LAUNCH_OK();
+    return 0;
+}

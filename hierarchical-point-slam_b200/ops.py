@@ -23,7 +23,8 @@ def _stream():
 # ---- instrumentation: kernel-launch counter and optional CUDA-event timers per C-ABI call -----------
 LAUNCHES = {"n": 0}
 _KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_interp_fwd": 1, "hps_interp_bwd": 1,
-                     "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_mlp_tc_pack": 1, "hps_mlp_tc_fwd": 1, "hps_composite_fwd": 1,
+                     "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_mlp_tc_pack": 1, "hps_mlp_tc_fwd": 1,
+                     "hps_mlp_tc_bwd_pack": 1, "hps_mlp_tc_bwd": 2, "hps_tc_selftest": 1, "hps_composite_fwd": 1,
                      "hps_composite_bwd": 1, "hps_sample_rays": 1, "hps_sample_rays_bwd": 1, "hps_mapper_loss": 1,
                      "hps_tracker_loss_stats": 1, "hps_tracker_loss": 1}
 TIMERS = None   # set to {} to record (start, end) CUDA events per call name on the current stream
@@ -40,7 +41,7 @@ def _call(name, *args):
     a.record()
     _lib.check(fn(*args))
     b.record()
-    key = "%s[%d]" % (name, args[0]) if name in ("hps_mlp_fwd", "hps_mlp_bwd", "hps_mlp_tc_fwd") else name
+    key = "%s[%d]" % (name, args[0]) if name in ("hps_mlp_fwd", "hps_mlp_bwd", "hps_mlp_tc_fwd", "hps_mlp_tc_bwd") else name
     TIMERS.setdefault(key, []).append((a, b))
 
 
@@ -229,18 +230,62 @@ def _packed_buffer(kind, device, tc=False):
     return buf
 
 
-def _mlp_forward(kind, arr, p_c, c_c, aff, P, out, act, dev):
-    """pack + forward of one decoder on the current stream (tensor-core or SIMT edition)."""
+# True: the backward also runs on tensor cores (dgrad chain + streaming wgrad kernels); False: fp32 SIMT backward.
+USE_TC_BWD = os.environ.get("HPS_USE_TC_BWD", "1") != "0"
+
+
+def _mlp_forward(kind, arr, p_c, c_c, aff, P, out, need_grad, dev):
+    """pack + forward of one decoder on the current stream.  Returns the saved workspace ("tc"|"simt", tensor)
+    that _mlp_backward consumes (None when no backward will follow)."""
+    lib = _lib.load()
+    saved = None
     if USE_TC:
         pk = _packed_buffer(kind, dev, tc=True)
+        act = ws = None
+        if need_grad and USE_TC_BWD:
+            ws = torch.empty(int(lib.hps_mlp_tc_ws_bytes(kind, P)), dtype=torch.uint8, device=dev)
+            saved = ("tc", ws)
+        elif need_grad:
+            act = torch.empty((P + 63) // 64 * 64 * int(lib.hps_mlp_act_floats(kind)), dtype=torch.float32, device=dev)
+            saved = ("simt", act)
         _call("hps_mlp_tc_pack", kind, arr, _lib.ptr(pk), _stream())
         _call("hps_mlp_tc_fwd", kind, arr, _lib.ptr(pk), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), P, _lib.ptr(out),
-              _lib.ptr(act), _stream())
+              _lib.ptr(act), _lib.ptr(ws), _stream())
     else:
         pk = _packed_buffer(kind, dev)
+        act = None
+        if need_grad:
+            act = torch.empty((P + 63) // 64 * 64 * int(lib.hps_mlp_act_floats(kind)), dtype=torch.float32, device=dev)
+            saved = ("simt", act)
         _call("hps_mlp_pack", kind, arr, _lib.ptr(pk), _stream())
         _call("hps_mlp_fwd", kind, arr, _lib.ptr(pk), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), P, _lib.ptr(out),
               _lib.ptr(act), _stream())
+    return saved
+
+
+_bwd_packed_cache = {}
+
+
+def _mlp_backward(kind, prm, saved_kind, saved, p_c, c_c, aff, dout, P, dprm, dc, need_dp, daff, dev):
+    """Backward of one decoder; returns dp (P,3) or None.  dprm: list of gradient buffers (or None)."""
+    f32 = dict(dtype=torch.float32, device=dev)
+    darr = _ptr_array(dprm) if dprm is not None else None
+    if saved_kind == "tc":
+        key = (kind, dev)
+        pk = _bwd_packed_cache.get(key)
+        if pk is None:
+            pk = torch.empty(int(_lib.load().hps_mlp_tc_bwd_packed_bytes(kind)), dtype=torch.uint8, device=dev)
+            _bwd_packed_cache[key] = pk
+        dp = torch.zeros(P, 3, **f32) if need_dp else None      # accumulated by the kernel
+        arr = _ptr_array(prm)
+        _call("hps_mlp_tc_bwd_pack", kind, arr, _lib.ptr(pk), _stream())
+        _call("hps_mlp_tc_bwd", kind, arr, _lib.ptr(pk), _lib.ptr(saved), _lib.ptr(p_c), _lib.ptr(aff), _lib.ptr(dout), P,
+              darr, _lib.ptr(dc), _lib.ptr(dp), _lib.ptr(daff), _stream())
+        return dp
+    dp = torch.empty(P, 3, **f32) if need_dp else None
+    _call("hps_mlp_bwd", kind, _ptr_array(prm), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), _lib.ptr(saved),
+          _lib.ptr(dout), P, darr, _lib.ptr(dc), _lib.ptr(dp), _lib.ptr(daff), _stream())
+    return dp
 
 
 class _Mlp(torch.autograd.Function):
@@ -256,16 +301,13 @@ class _Mlp(torch.autograd.Function):
         nout = 1 if kind == MLP_GEO else 3
         out = torch.empty((P,) if nout == 1 else (P, 3), dtype=torch.float32, device=dev)
         need_grad = any(ctx.needs_input_grad)
-        act = None
-        if need_grad:
-            tiles = (P + 63) // 64
-            act = torch.empty(tiles * 64 * int(lib.hps_mlp_act_floats(kind)), dtype=torch.float32, device=dev)
         arr = _ptr_array(prm)
         with torch.cuda.device(dev):
-            _mlp_forward(kind, arr, p_c, c_c, aff, P, out, act, dev)
+            saved = _mlp_forward(kind, arr, p_c, c_c, aff, P, out, need_grad, dev)
         ctx.kind = kind
         ctx.has_affine = aff is not None
-        ctx.save_for_backward(p_c, c_c, aff, act, *prm)
+        ctx.saved_kind = saved[0] if saved else None
+        ctx.save_for_backward(p_c, c_c, aff, saved[1] if saved else None, *prm)
         return out
 
     @staticmethod
@@ -282,13 +324,10 @@ class _Mlp(torch.autograd.Function):
         elif want_b:
             raise _lib.HpsError("gradient w.r.t. embedder._B alone is not supported")
         dc = torch.empty(P, C_DIM, dtype=torch.float32, device=dev)
-        dp = torch.empty(P, 3, dtype=torch.float32, device=dev) if need[1] else None
         daff = torch.zeros(12, dtype=torch.float32, device=dev) if (ctx.has_affine and need[3]) else None
-        darr = _ptr_array(dprm) if want_w else None
         with torch.cuda.device(dev):
-            _call("hps_mlp_bwd", kind, _ptr_array(prm), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff),
-                                               _lib.ptr(act), _lib.ptr(_f32c(dout)), P, darr, _lib.ptr(dc),
-                                               _lib.ptr(dp), _lib.ptr(daff), _stream())
+            dp = _mlp_backward(kind, prm, ctx.saved_kind, act, p_c, c_c, aff, _f32c(dout), P, dprm if want_w else None,
+                               dc, need[1], daff, dev)
         grads = [g if (g is not None and need[4 + i]) else None for i, g in enumerate(dprm)]
         return (None, dp, dc if need[2] else None, daff, *grads)
 
@@ -453,11 +492,6 @@ class _RenderRays(torch.autograd.Function):
         depth, var, color = torch.empty(R, **f32), torch.empty(R, **f32), torch.empty(R, 3, **f32)
         valid = torch.empty(R, dtype=torch.uint8, device=dev)
         need_grad = any(ctx.needs_input_grad)
-        lib = _lib.load()
-        tiles = (P + 63) // 64
-        act_g = torch.empty(tiles * 64 * int(lib.hps_mlp_act_floats(MLP_GEO)), **f32) if need_grad else None
-        act_c = torch.empty(tiles * 64 * int(lib.hps_mlp_act_floats(MLP_COL)), **f32) \
-            if (need_grad and spec.color_stage) else None
         pos = _f32c(spec.cloud_pos).reshape(-1, 3) if spec.tracker else None
         fill_g, fill_c = _f32c(spec.fill_geo), (_f32c(spec.fill_col) if spec.color_stage else None)
         zz = _f32c(spec.z_zero) if spec.z_zero is not None else None
@@ -472,9 +506,10 @@ class _RenderRays(torch.autograd.Function):
             _call("hps_interp_fwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(D), _lib.ptr(t_dn), _lib.ptr(cnt),
                   _lib.ptr(pos), _lib.ptr(fg), _lib.ptr(fc), _lib.ptr(fill_g), _lib.ptr(fill_c), P, int(spec.min_nn),
                   _lib.ptr(w), _lib.ptr(c_geo), _lib.ptr(c_col), _lib.ptr(has), st())
-            _mlp_forward(MLP_GEO, garr, pts, c_geo, None, P, occ, act_g, dev)
-            if spec.color_stage:
-                _mlp_forward(MLP_COL, carr, pts, c_col, aff, P, rgb, act_c, dev)
+            sv_g = _mlp_forward(MLP_GEO, garr, pts, c_geo, None, P, occ, need_grad, dev)
+            sv_c = _mlp_forward(MLP_COL, carr, pts, c_col, aff, P, rgb, need_grad, dev) if spec.color_stage else None
+            act_g, act_c = (sv_g[1] if sv_g else None), (sv_c[1] if sv_c else None)
+            ctx.saved_kinds = (sv_g[0] if sv_g else None, sv_c[0] if sv_c else None)
             _call("hps_composite_fwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
                   float(spec.coef), _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), None, int(spec.min_valid),
                   _lib.ptr(valid), st())
@@ -508,8 +543,6 @@ class _RenderRays(torch.autograd.Function):
         want_cw = spec.color_stage and any(need[7 + N_PARAM + i] for i in range(1, N_PARAM))
         dg = _zero_grads_like(gprm, skip_first=not need[7]) if want_gw else None
         dcw = _zero_grads_like(cprm, skip_first=True) if want_cw else None   # colour _B is not a parameter
-        dp_g = torch.empty(P, 3, **f32) if need_p else None
-        dp_c = torch.empty(P, 3, **f32) if (need_p and spec.color_stage) else None
         dp_i = torch.empty(P, 3, **f32) if need_p else None
         daff = torch.zeros(12, **f32) if (aff is not None and need[6]) else None
         if ctx.row_map is not None:
@@ -522,13 +555,12 @@ class _RenderRays(torch.autograd.Function):
         with torch.cuda.device(dev):
             _call("hps_composite_bwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
                   float(spec.coef), _lib.ptr(gd), _lib.ptr(gc), _lib.ptr(d_rgb), 3, _lib.ptr(d_occ), 1, st())
-            _call("hps_mlp_bwd", MLP_GEO, _ptr_array(gprm), _lib.ptr(pts), _lib.ptr(c_geo), None, _lib.ptr(act_g),
-                  _lib.ptr(d_occ), P, _ptr_array(dg) if dg is not None else None, _lib.ptr(dc_g), _lib.ptr(dp_g), None,
-                  st())
+            dp_g = _mlp_backward(MLP_GEO, gprm, ctx.saved_kinds[0], act_g, pts, c_geo, None, d_occ, P, dg, dc_g, need_p,
+                                 None, dev)
+            dp_c = None
             if spec.color_stage:
-                _call("hps_mlp_bwd", MLP_COL, _ptr_array(cprm), _lib.ptr(pts), _lib.ptr(c_col), _lib.ptr(aff),
-                      _lib.ptr(act_c), _lib.ptr(d_rgb), P, _ptr_array(dcw) if dcw is not None else None,
-                      _lib.ptr(dc_c), _lib.ptr(dp_c), _lib.ptr(daff), st())
+                dp_c = _mlp_backward(MLP_COL, cprm, ctx.saved_kinds[1], act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c,
+                                     need_p, daff, dev)
             if dfg is not None or dfc is not None or need_p:
                 _call("hps_interp_bwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(w), _lib.ptr(has), _lib.ptr(pos),
                       _lib.ptr(fg), _lib.ptr(fc), _lib.ptr(c_geo), _lib.ptr(c_col), _lib.ptr(dc_g), _lib.ptr(dc_c), P,

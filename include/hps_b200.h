@@ -101,8 +101,23 @@ int hps_mlp_fwd(int kind, const float* const* params, const float* packed, const
  * hps_mlp_tc_pack (hps_mlp_tc_packed_bytes(kind) bytes, 16-byte aligned).                             */
 int64_t hps_mlp_tc_packed_bytes(int kind);
 int hps_mlp_tc_pack(int kind, const float* const* params, void* packed, void* stream);
+/* `ws` (may be NULL): workspace of hps_mlp_tc_ws_bytes(kind, P) bytes for the tensor-core backward (fp16 hi/lo
+ * slab images of every layer input, the pre-activations and the raw output); `act` (may be NULL) is the SIMT
+ * workspace of hps_mlp_bwd.                                                                            */
+int64_t hps_mlp_tc_ws_bytes(int kind, int64_t P);
 int hps_mlp_tc_fwd(int kind, const float* const* params, const void* packed, const float* p, const float* c,
-                   const float* affine, int64_t P, float* out, float* act, void* stream);
+                   const float* affine, int64_t P, float* out, float* act, void* ws, void* stream);
+/* Tensor-core backward: dgrad chain kernel + streaming wgrad kernel (MN-major operands, accumulators in TMEM).
+ * Same outputs as hps_mlp_bwd except that dp (P,3) must be ZERO-initialised by the caller (it is accumulated).
+ * `packed` = hps_mlp_tc_bwd_pack image (transposed weight slabs, hps_mlp_tc_bwd_packed_bytes(kind) bytes).    */
+int64_t hps_mlp_tc_bwd_packed_bytes(int kind);
+int hps_mlp_tc_bwd_pack(int kind, const float* const* params, void* packed, void* stream);
+int hps_mlp_tc_bwd(int kind, const float* const* params, const void* packed, void* ws, const float* p,
+                   const float* affine, const float* dout, int64_t P, float* const* dparams, float* dc, float* dp,
+                   float* daffine, void* stream);
+/* Single-CTA tcgen05 self-test: D[128][N] = A . B^T with fp16 operands staged K-major (major = 0, source
+ * [rows][K]) or MN-major (major = 1, source [K][rows]) - pins the shared-memory descriptor encodings.        */
+int hps_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_major, int b_major, void* stream);
 /* dparams: HOST array of HPS_MLP_NPARAM device pointers (entries or the array may be NULL = skip);
  * parameter gradients are ACCUMULATED (atomic adds).  dc (P,32) written.  dp (P,3) written if not
  * NULL.  daffine (12) accumulated if not NULL.                                                     */

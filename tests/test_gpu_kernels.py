@@ -214,6 +214,23 @@ def test_mlp_fwd_bwd(hps, golden, kind, P, affine):
     assert torch.equal(out_i, out_d.detach())
 
 
+@pytest.mark.parametrize("N,K,a_major,b_major", [(128, 128, 0, 0), (32, 64, 0, 0), (128, 128, 1, 1), (192, 128, 1, 1),
+                                                 (32, 128, 1, 1), (128, 64, 0, 1), (64, 128, 1, 0), (176, 128, 1, 1)])
+def test_tcgen05_descriptor_selftest(hps, N, K, a_major, b_major):
+    """K-major and MN-major SWIZZLE_128B operand descriptors: exact integer GEMM through tcgen05.mma."""
+    g = torch.Generator().manual_seed(N * 1000 + K + a_major * 2 + b_major)
+    A = torch.randint(-4, 5, (128, K), generator=g).float()
+    B = torch.randint(-4, 5, (N, K), generator=g).float()
+    want = A @ B.T
+    Ad = (A if a_major == 0 else A.T).contiguous().to(DEV)
+    Bd = (B if b_major == 0 else B.T).contiguous().to(DEV)
+    D = torch.full((128, N), float("nan"), device=DEV)
+    L = hps._lib
+    hps.ops._call("hps_tc_selftest", L.ptr(Ad), L.ptr(Bd), L.ptr(D), N, K, a_major, b_major, hps.ops._stream())
+    torch.cuda.synchronize()
+    assert torch.equal(D.cpu(), want), "max err %g" % float((D.cpu() - want).abs().max())
+
+
 @pytest.mark.parametrize("kind,P,affine", [("col", 1000, False), ("col", 130, True), ("geo", 1000, False), ("geo", 77, False),
                                            ("col", 40000, False), ("geo", 40000, False)])
 def test_mlp_tensor_core_forward_matches_simt(hps, golden, kind, P, affine):
