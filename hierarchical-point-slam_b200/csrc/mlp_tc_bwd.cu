@@ -56,6 +56,7 @@ __global__ void pack_bwd_kernel(Ptrs prm, uint16_t* __restrict__ img) {
     using B = GeoB<KIND>;
     constexpr int H = C::H, E = C::E, HS = B::HS, NE = B::NE;
     const int total = B::SLABS_PER_TILE * (SLAB / 2);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<uint32_t*>(img + total) = 0u;   // gradient abs-max word
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
         const int slab = idx / (SLAB / 2);
         const int byte = (idx % (SLAB / 2)) * 2;
@@ -100,6 +101,30 @@ __global__ void pack_bwd_kernel(Ptrs prm, uint16_t* __restrict__ img) {
     }
 }
 
+// Gradient scaling.  Upstream gradients can be tiny (1e-7 .. 1e-3); fp16 hi/lo operands would lose their low half
+// to subnormals.  The whole backward therefore runs on S * gradient with S a power of two chosen so that
+// max|dout| lands in [128, 256) (exact, overflow-safe through the five layers), and un-scales on output.
+// The max is reduced on the device into the 4 bytes behind the packed weight image (zeroed by the pack kernel).
+__device__ __forceinline__ float grad_scale(const uint32_t* maxbits) {
+    const float m = __uint_as_float(*maxbits);
+    if (!(m > 0.f) || m > 3.0e38f) return 1.0f;
+    int e;
+    frexpf(m, &e);
+    e = 8 - e;
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    return ldexpf(1.0f, e);
+}
+
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restrict__ maxbits) {
+    float m = 0.f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float v = fabsf(x[i]);
+        if (v <= 3.0e38f) m = fmaxf(m, v);     // ignores NaN / inf
+    }
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(kFull, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(maxbits, __float_as_uint(m));
+}
+
 template <bool RELU> __device__ __forceinline__ float act_grad(float a) {
     if (RELU) return a > 0.f ? 1.f : 0.f;
     const float t = a * 100.0f;
@@ -139,6 +164,8 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTB + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool want_w = grd.v[iWo] != nullptr;
+    const float gS = grad_scale(reinterpret_cast<const uint32_t*>(wimg + (size_t)B::SLABS_PER_TILE * SLAB));
+    const float gInv = 1.0f / gS;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTB; ++s) {
@@ -297,8 +324,8 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 for (int j = 0; j < 32; ++j) da[j] = dy[j] * act_grad<C::RELU>(ag[(layer * H + c0 + j) * TILE + row]);
                 if (want_w) {
                     const float s1 = warp_colsum32(dy, lane), s2 = warp_colsum32(da, lane);
-                    red_add(grd.v[iBc(layer)] + c0 + lane, s1);
-                    red_add(grd.v[iB(layer)] + c0 + lane, s2);
+                    red_add(grd.v[iBc(layer)] + c0 + lane, s1 * gInv);
+                    red_add(grd.v[iB(layer)] + c0 + lane, s2 * gInv);
                 }
                 uint16_t yh[32], yl[32], ah[32], al[32];
 #pragma unroll
@@ -379,7 +406,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                             float s = 0.f;
 #pragma unroll
                             for (int o = 0; o < NOUT; ++o) s = fmaf(dr[o], __ldg(prm.v[iWo] + o * H + c0 + j), s);
-                            dy[j] = s;
+                            dy[j] = s * gS;      // the chain below runs on scaled gradients
                         }
                         if (want_w) {   // dWo[o][h] += sum_pt d raw[pt][o] * y_4[pt][h]
                             float y4[32];
@@ -449,7 +476,8 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 if (live) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q)
-                        *reinterpret_cast<float4*>(dc + pt * kC + q * 4) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+                        *reinterpret_cast<float4*>(dc + pt * kC + q * 4) =
+                            make_float4(v[q * 4] * gInv, v[q * 4 + 1] * gInv, v[q * 4 + 2] * gInv, v[q * 4 + 3] * gInv);
                 }
             }
             tc_fence_before();
@@ -479,7 +507,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                             const float arg = fmaf(x2, b2, fmaf(x1, b1, x0 * b0));
                             float s, co;
                             sincosf(arg, &s, &co);
-                            g = (C::CONCAT && e >= NF) ? -de[eb + j] * s : de[eb + j] * co;
+                            g = ((C::CONCAT && e >= NF) ? -de[eb + j] * s : de[eb + j] * co) * gInv;
                         }
                         g0 = fmaf(g * kTwoPi, b0, g0);
                         g1 = fmaf(g * kTwoPi, b1, g1);
@@ -546,7 +574,7 @@ template <int KIND> struct GeoW {
 
 template <int KIND>
 __global__ void __launch_bounds__(192, 1)
-mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles) {
+mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles, const uint32_t* __restrict__ maxbits) {
     using C = Cfg<KIND>;
     using GW = GeoW<KIND>;
     using W = Ws<KIND>;
@@ -659,6 +687,7 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles)
             const int quad = warp & 3;
             const int h = quad * 32 + lane;
             const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+            const float gInv = 1.0f / grad_scale(maxbits);
             for (int layer = l0; layer <= l1; ++layer) {
                 const int K = layer == 0 ? E : (layer == 3 ? E + H : H);
                 if (layer >= 1) {
@@ -669,7 +698,7 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles)
 #pragma unroll
                             for (int j = 0; j < 32; ++j) {
                                 const int r = cb + j;
-                                if (r < H) red_add(grd.v[iW(layer)] + (int64_t)h * K + (layer == 3 ? E + r : r), v[j]);
+                                if (r < H) red_add(grd.v[iW(layer)] + (int64_t)h * K + (layer == 3 ? E + r : r), v[j] * gInv);
                             }
                         }
                     }
@@ -681,7 +710,7 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles)
                         if (h < H) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (cb + j < E) red_add(grd.v[iW(layer)] + (int64_t)h * K + cb + j, v[j]);
+                                if (cb + j < E) red_add(grd.v[iW(layer)] + (int64_t)h * K + cb + j, v[j] * gInv);
                         }
                     }
                 }
@@ -691,7 +720,7 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles)
                     tc_ld32(tmem + lane_addr + GW::col_wc(layer) + 32, v2);
                     if (h < H) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) red_add(grd.v[iWc(layer)] + (int64_t)h * kC + j, v[j] + v2[j]);
+                        for (int j = 0; j < 32; ++j) red_add(grd.v[iWc(layer)] + (int64_t)h * kC + j, (v[j] + v2[j]) * gInv);
                     }
                 }
             }
@@ -734,6 +763,13 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
     }
     const int num_tiles = (int)ceil_div(P, TILE);
     int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+    uint32_t* maxbits = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(img)) +
+                                                    (size_t)GeoB<KIND>::SLABS_PER_TILE * SLAB);
+    {
+        const int64_t n = P * Cfg<KIND>::NOUT;
+        const int nb = (int)(ceil_div(n, 1024) < kNumSMs ? ceil_div(n, 1024) : kNumSMs);
+        absmax_kernel<<<nb, 1024, 0, s>>>(dout, n, maxbits);
+    }
     mlp_dgrad_tc_kernel<KIND><<<grid, NTHR, GeoB<KIND>::SMEM_BYTES, s>>>(
         prm, grd, reinterpret_cast<const uint8_t*>(img), reinterpret_cast<uint8_t*>(ws), p, affine, dout, P, num_tiles,
         dc, dp, daffine);
@@ -741,7 +777,7 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
         int wgrid = 2 * num_tiles < kNumSMs ? 2 * num_tiles : kNumSMs;
         if (wgrid < 2) wgrid = 2;
         mlp_wgrad_tc_kernel<KIND><<<wgrid, 192, GeoW<KIND>::SMEM_BYTES, s>>>(grd, reinterpret_cast<const uint8_t*>(ws),
-                                                                            num_tiles);
+                                                                            num_tiles, maxbits);
     }
     return 0;
 }
@@ -751,8 +787,8 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
 
 extern "C" int64_t hps_mlp_tc_bwd_packed_bytes(int kind) {
     using namespace hps::tc;
-    return kind == HPS_MLP_GEO ? (int64_t)GeoB<HPS_MLP_GEO>::SLABS_PER_TILE * SLAB
-                               : (int64_t)GeoB<HPS_MLP_COL>::SLABS_PER_TILE * SLAB;
+    return (kind == HPS_MLP_GEO ? (int64_t)GeoB<HPS_MLP_GEO>::SLABS_PER_TILE * SLAB
+                                : (int64_t)GeoB<HPS_MLP_COL>::SLABS_PER_TILE * SLAB) + 16;   // + gradient abs-max word
 }
 
 extern "C" int hps_mlp_tc_bwd_pack(int kind, const float* const* params, void* packed, void* stream) {

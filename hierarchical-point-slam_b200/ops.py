@@ -24,7 +24,7 @@ def _stream():
 LAUNCHES = {"n": 0}
 _KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_interp_fwd": 1, "hps_interp_bwd": 1,
                      "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_mlp_tc_pack": 1, "hps_mlp_tc_fwd": 1,
-                     "hps_mlp_tc_bwd_pack": 1, "hps_mlp_tc_bwd": 2, "hps_tc_selftest": 1, "hps_composite_fwd": 1,
+                     "hps_mlp_tc_bwd_pack": 1, "hps_mlp_tc_bwd": 3, "hps_tc_selftest": 1, "hps_composite_fwd": 1,
                      "hps_composite_bwd": 1, "hps_sample_rays": 1, "hps_sample_rays_bwd": 1, "hps_mapper_loss": 1,
                      "hps_tracker_loss_stats": 1, "hps_tracker_loss": 1}
 TIMERS = None   # set to {} to record (start, end) CUDA events per call name on the current stream
