@@ -378,6 +378,10 @@ def roofline(per, hps, npc, devb, sl):
     work = {"hps_mlp_fwd[1]": ("tensor", 193400.0 * P), "hps_mlp_bwd[1]": ("tensor", 2 * 193400.0 * P),
             "hps_mlp_fwd[0]": ("tensor", 30958.0 * P), "hps_mlp_bwd[0]": ("tensor", 2 * 30958.0 * P),
             "hps_interp_fwd": ("hbm", 2432.0 * P), "hps_interp_bwd": ("hbm", 2432.0 * P)}
+    # tensor-core entry points: same algorithmic (fp32-equivalent) FLOPs; the 3-product fp16 split is overhead
+    for k in (0, 1):
+        work["hps_mlp_tc_fwd[%d]" % k] = work["hps_mlp_fwd[%d]" % k]
+        work["hps_mlp_tc_bwd[%d]" % k] = work["hps_mlp_bwd[%d]" % k]
     # measured mean candidate count for the search figure
     z, _ = None, None
     q, cand = npc.query_neighbors((devb["rays_o"][sl][:, None, :] + devb["rays_d"][sl][:, None, :] *

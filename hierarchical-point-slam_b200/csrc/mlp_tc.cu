@@ -272,13 +272,13 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
         }
     } else {
         // ================= epilogue warps =================
-        const int ew = warp - EPI_WARP0;          // 0..7
+        const int ew = warp - EPI_WARP0;          // 0..EPI_WARPS-1
         const int quad = warp & 3;                // TMEM lane quadrant this warp may access
-        const int half = ew >> 2;                 // column half handled by this warp
+        const int cgp = ew >> 2;                  // column group handled by this warp
         const int row = quad * 32 + lane;         // tile row = TMEM lane
-        constexpr int CPT = (H >= 64) ? H / 2 : H;   // hidden columns per thread: colour 64, geometry 32 (half 0 only)
-        const bool col_owner = (H >= 64) || (half == 0);
-        const int col0 = (H >= 64) ? half * CPT : 0;
+        constexpr int CPT = (H >= 32 * CG) ? H / CG : 32;   // hidden columns per thread (colour 32; geometry 32, group 0 only)
+        const bool col_owner = (H >= 32 * CG) || (cgp == 0);
+        const int col0 = (H >= 32 * CG) ? cgp * CPT : 0;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         uint32_t nacc = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -295,7 +295,7 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
                     x2 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 2));
                 }
                 const float* B = prm.v[0];
-                for (int j = half; j < NF; j += 2) {
+                for (int j = cgp; j < NF; j += CG) {
                     const float arg = fmaf(x2, __ldg(B + 2 * NF + j), fmaf(x1, __ldg(B + NF + j), x0 * __ldg(B + j)));
                     float s, co;
                     if (C::CONCAT) sincosf(arg, &s, &co); else { s = sinf(arg); co = 0.f; }
@@ -326,26 +326,29 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
                         }
                     }
                 }
-                // c: this thread converts 16 of the 32 channels
-                float4 cv[4];
+                // c: this thread converts kC / CG of the 32 channels
+                constexpr int CPC = kC / CG;
+                float cf[CPC];
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    cv[q] = live ? ldg4(c + pt * kC + half * 16 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float* cf = reinterpret_cast<const float*>(cv);
-                uint16_t hi[16], lo[16];
+                for (int q = 0; q < CPC / 4; ++q) {
+                    const float4 v4 = live ? ldg4(c + pt * kC + cgp * CPC + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    cf[q * 4] = v4.x; cf[q * 4 + 1] = v4.y; cf[q * 4 + 2] = v4.z; cf[q * 4 + 3] = v4.w;
+                }
+                uint16_t hi[CPC], lo[CPC];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) split16(cf[q], hi[q], lo[q]);
+                for (int q = 0; q < CPC; ++q) split16(cf[q], hi[q], lo[q]);
 #pragma unroll
-                for (int q = 0; q < 2; ++q) {
+                for (int q = 0; q < CPC / 8; ++q) {
                     const uint4 vh = make_uint4(hi[q * 8 + 0] | (hi[q * 8 + 1] << 16), hi[q * 8 + 2] | (hi[q * 8 + 3] << 16),
                                                 hi[q * 8 + 4] | (hi[q * 8 + 5] << 16), hi[q * 8 + 6] | (hi[q * 8 + 7] << 16));
                     const uint4 vl = make_uint4(lo[q * 8 + 0] | (lo[q * 8 + 1] << 16), lo[q * 8 + 2] | (lo[q * 8 + 3] << 16),
                                                 lo[q * 8 + 4] | (lo[q * 8 + 5] << 16), lo[q * 8 + 6] | (lo[q * 8 + 7] << 16));
-                    *reinterpret_cast<uint4*>(sC + slab_off(row, half * 2 + q)) = vh;
-                    *reinterpret_cast<uint4*>(sC + slab_off(row, 4 + half * 2 + q)) = vl;
+                    const int ch = cgp * (CPC / 8) + q;
+                    *reinterpret_cast<uint4*>(sC + slab_off(row, ch)) = vh;
+                    *reinterpret_cast<uint4*>(sC + slab_off(row, 4 + ch)) = vl;
                     if (xg) {
-                        *reinterpret_cast<uint4*>(xg + W::x_c() * SLAB + slab_off(row, half * 2 + q)) = vh;
-                        *reinterpret_cast<uint4*>(xg + W::x_c() * SLAB + slab_off(row, 4 + half * 2 + q)) = vl;
+                        *reinterpret_cast<uint4*>(xg + W::x_c() * SLAB + slab_off(row, ch)) = vh;
+                        *reinterpret_cast<uint4*>(xg + W::x_c() * SLAB + slab_off(row, 4 + ch)) = vl;
                     }
                 }
             }
@@ -409,7 +412,7 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
             mbar_wait(acc_ready, nacc & 1);
             ++nacc;
             tc_fence_after();
-            if (half == 0) {
+            if (cgp == 0) {
                 float o[32];
                 tc_ld32(tmem + lane_addr + 2 * H, o);
                 if (ws) {

@@ -31,10 +31,12 @@ template <int KIND> struct GeoB {
     static constexpr int HS = G::HS, ES = G::ES, H = C::H;
     static constexpr int SLABS_PER_TILE = 9 + 8 * HS;           // see pack_bwd_kernel
     static constexpr int NE = 64 * ES;                           // padded embedding width
-    static constexpr int T_H = 0, T_E = H, T_DC = H + NE;        // TMEM columns of the dgrad kernel
-    static constexpr int TMEM_COLS = 256;
-    static constexpr int SMEM_BYTES = 1024 + (4 * HS + NSTB) * SLAB + 256;
-    static constexpr int ECPT = NE / 2;                          // embedding columns per epilogue thread
+    // TMEM columns of the dgrad kernel: dx hidden, dx embedding, dc, colsum(da_i), colsum(dy_i)
+    static constexpr int T_H = 0, T_E = H, T_DC = H + NE, T_SB = H + NE + 32, T_SBC = H + NE + 32 + H;
+    static constexpr int TMEM_COLS = (T_SBC + H) <= 256 ? 256 : 512;
+    static_assert(T_SBC + H <= 512, "TMEM budget");
+    static constexpr int SMEM_BYTES = 1024 + (4 * HS + 1 + NSTB) * SLAB + 256;   // + one slab of ones
+    static constexpr int ECPT = NE / CG;                         // embedding columns per epilogue thread
 };
 
 // ---------------------------------------------------------------------------------------------- pack
@@ -137,6 +139,16 @@ __device__ __forceinline__ uint4 pack8(const uint16_t* v) {
     return make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
 }
 
+// MN-major SWIZZLE_128B descriptor for an operand stored rows = contraction index (points), 64 columns per slab:
+// LBO = byte distance between consecutive 64-column slabs, SBO = 1024 (8-row groups along the contraction).
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr, uint32_t lbo) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | (64ull << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+__host__ __device__ constexpr uint32_t instr_desc_mn(int M, int N) {   // both operands MN-major, fp16, f32 accumulate
+    return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---------------------------------------------------------------------------------------------- dgrad
 template <int KIND>
 __global__ void __launch_bounds__(NTHR, 1)
@@ -155,7 +167,8 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
     uint8_t* sDYlo = sDYhi + HS * SLAB;
     uint8_t* sDAhi = sDYlo + HS * SLAB;
     uint8_t* sDAlo = sDAhi + HS * SLAB;
-    uint8_t* sW = sDAlo + HS * SLAB;
+    uint8_t* sOnes = sDAlo + HS * SLAB;            // fp16 1.0 everywhere: A operand of the bias-gradient column sums
+    uint8_t* sW = sOnes + SLAB;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sW + NSTB * SLAB);
     uint64_t* full = bars;
     uint64_t* empty = bars + NSTB;
@@ -182,6 +195,8 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     for (int i = threadIdx.x; i < 4 * HS * SLAB / 16; i += NTHR) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < SLAB / 16; i += NTHR)
+        reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -205,6 +220,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
         constexpr uint32_t ID_H = instr_desc(FMT_F16, FMT_F16, TILE, H);
         constexpr uint32_t ID_E = instr_desc(FMT_F16, FMT_F16, TILE, NE);
         constexpr uint32_t ID_C = instr_desc(FMT_F16, FMT_F16, TILE, 32);
+        constexpr uint32_t ID_SUM = instr_desc_mn(TILE, H);
         const uint32_t t_h = tmem + B::T_H, t_e = tmem + B::T_E, t_dc = tmem + B::T_DC;
         const uint32_t aDYh = smem_u32(sDYhi), aDYl = smem_u32(sDYlo), aDAh = smem_u32(sDAhi), aDAl = smem_u32(sDAlo);
         const uint32_t aW = smem_u32(sW);
@@ -216,6 +232,22 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 mbar_wait(a_ready, nready & 1);
                 ++nready;
                 tc_fence_after();
+                if (want_w) {
+                    // bias gradients on the tensor pipe: colsum(da_i), colsum(dy_i) = ones^T . da_i / dy_i, contracted
+                    // over the 128 points with MN-major operands (every TMEM lane ends up with the same sums)
+                    if (elect_one()) {
+                        const uint32_t aOnes = smem_u32(sOnes);
+#pragma unroll 1
+                        for (int k = 0; k < TILE / 16; ++k) {
+                            const uint64_t on = smem_desc_mn(aOnes + k * 2048, 0);       // both 64-wide M atoms = the ones slab
+                            tc_mma(tmem + B::T_SB, on, smem_desc_mn(aDAh + k * 2048, SLAB), ID_SUM, k > 0 ? 1u : 0u);
+                            tc_mma(tmem + B::T_SB, on, smem_desc_mn(aDAl + k * 2048, SLAB), ID_SUM, 1u);
+                            tc_mma(tmem + B::T_SBC, on, smem_desc_mn(aDYh + k * 2048, SLAB), ID_SUM, k > 0 ? 1u : 0u);
+                            tc_mma(tmem + B::T_SBC, on, smem_desc_mn(aDYl + k * 2048, SLAB), ID_SUM, 1u);
+                        }
+                    }
+                    __syncwarp();
+                }
                 {   // dc += dy_i . Wc_i
                     const int st = it % NSTB;
                     mbar_wait(&full[st], (it / NSTB) & 1);
@@ -298,13 +330,14 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
         // ================= epilogue warps =================
         const int ew = warp - EPI_WARP0;
         const int quad = warp & 3;
-        const int half = ew >> 2;
+        const int cgp = ew >> 2;
         const int row = quad * 32 + lane;
-        constexpr int CPT = (H >= 64) ? H / 2 : H;
-        const bool col_owner = (H >= 64) || (half == 0);
-        const int col0 = (H >= 64) ? half * CPT : 0;
+        constexpr int CPT = (H >= 32 * CG) ? H / CG : 32;
+        const bool col_owner = (H >= 32 * CG) || (cgp == 0);
+        const int col0 = (H >= 32 * CG) ? cgp * CPT : 0;
         constexpr int ECPT = B::ECPT;
-        const int ecol0 = half * ECPT;
+        constexpr int EB = ECPT < 32 ? ECPT : 32;       // embedding columns per TMEM load
+        const int ecol0 = cgp * ECPT;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         uint32_t nacc = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -317,27 +350,21 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
 #pragma unroll
             for (int j = 0; j < ECPT; ++j) de[j] = 0.f;
 
-            // dy (32 columns starting at hidden column c0) of layer `layer` -> da, bias gradients, operands, dumps
+            // dy (32 columns starting at hidden column c0) of layer `layer` -> da, next A operands, dumps for wgrad
             auto emit = [&](int layer, int c0, const float (&dy)[32]) {
-                float da[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) da[j] = dy[j] * act_grad<C::RELU>(ag[(layer * H + c0 + j) * TILE + row]);
-                if (want_w) {
-                    const float s1 = warp_colsum32(dy, lane), s2 = warp_colsum32(da, lane);
-                    red_add(grd.v[iBc(layer)] + c0 + lane, s1 * gInv);
-                    red_add(grd.v[iB(layer)] + c0 + lane, s2 * gInv);
-                }
-                uint16_t yh[32], yl[32], ah[32], al[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    split16(dy[j], yh[j], yl[j]);
-                    split16(da[j], ah[j], al[j]);
-                }
                 const int slab = c0 / 64, cc = c0 % 64;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
+                    uint16_t yh[8], yl[8], ah[8], al[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float a = ag[(layer * H + c0 + q * 8 + j) * TILE + row];
+                        const float d = dy[q * 8 + j];
+                        split16(d, yh[j], yl[j]);
+                        split16(d * act_grad<C::RELU>(a), ah[j], al[j]);
+                    }
                     const uint32_t so = slab_off(row, (cc >> 3) + q);
-                    const uint4 v0 = pack8(yh + q * 8), v1 = pack8(yl + q * 8), v2 = pack8(ah + q * 8), v3 = pack8(al + q * 8);
+                    const uint4 v0 = pack8(yh), v1 = pack8(yl), v2 = pack8(ah), v3 = pack8(al);
                     *reinterpret_cast<uint4*>(sDYhi + slab * SLAB + so) = v0;
                     *reinterpret_cast<uint4*>(sDYlo + slab * SLAB + so) = v1;
                     *reinterpret_cast<uint4*>(sDAhi + slab * SLAB + so) = v2;
@@ -369,7 +396,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                         const float s = 1.0f / (1.0f + expf(-lin));
                         dl[cc] = dr[cc] * s * (1.0f - s);
                     }
-                    if (daffine != nullptr && half == 0) {
+                    if (daffine != nullptr && cgp == 0) {
                         float v[12];
 #pragma unroll
                         for (int k = 0; k < 3; ++k)
@@ -388,7 +415,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                     for (int k = 0; k < 3; ++k)
                         dr[k] = dl[0] * __ldg(affine + 3 * k) + dl[1] * __ldg(affine + 3 * k + 1) + dl[2] * __ldg(affine + 3 * k + 2);
                 }
-                if (want_w && half == 0) {
+                if (want_w && cgp == 0) {
 #pragma unroll
                     for (int o = 0; o < NOUT; ++o) {
                         float s = dr[o];
@@ -446,13 +473,29 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 mbar_wait(acc_ready, nacc & 1);
                 ++nacc;
                 tc_fence_after();
+                if (want_w && quad == 0 && col_owner) {   // bias gradients of this layer: row 0 of the column sums
+#pragma unroll 1
+                    for (int cb = 0; cb < CPT; cb += 32) {
+                        float sb[32], sbc[32];
+                        tc_ld32(tmem + B::T_SB + col0 + cb, sb);
+                        tc_ld32(tmem + B::T_SBC + col0 + cb, sbc);
+                        if (lane == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                red_add(grd.v[iB(layer)] + col0 + cb + j, sb[j] * gInv);
+                                red_add(grd.v[iBc(layer)] + col0 + cb + j, sbc[j] * gInv);
+                            }
+                        }
+                    }
+                }
                 if (layer == 0 || layer == 3) {
 #pragma unroll 1
-                    for (int eb = 0; eb < ECPT; eb += 32) {
-                        float v[32];
-                        tc_ld32(tmem + lane_addr + B::T_E + ecol0 + eb, v);
+                    for (int eb = 0; eb < ECPT; eb += EB) {
+                        float v[EB];
+                        if constexpr (EB == 32) tc_ld32(tmem + lane_addr + B::T_E + ecol0 + eb, v);
+                        else tc_ld16(tmem + lane_addr + B::T_E + ecol0 + eb, v);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) de[eb + j] += v[j];
+                        for (int j = 0; j < EB; ++j) de[eb + j] += v[j];
                     }
                 }
                 if (layer >= 1) {
@@ -470,7 +513,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 }
             }
             // ---- dc ----
-            if (half == 0) {
+            if (cgp == 0) {
                 float v[32];
                 tc_ld32(tmem + lane_addr + B::T_DC, v);
                 if (live) {
@@ -492,10 +535,10 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 }
                 float g0 = 0.f, g1 = 0.f, g2 = 0.f;
 #pragma unroll 1
-                for (int eb = 0; eb < ECPT; eb += 32) {
-                    float gb0[32], gb1[32], gb2[32];
+                for (int eb = 0; eb < ECPT; eb += EB) {
+                    float gb0[EB], gb1[EB], gb2[EB];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
+                    for (int j = 0; j < EB; ++j) {
                         const int e = ecol0 + eb + j;
                         float g = 0.f;
                         float b0 = 0.f, b1 = 0.f, b2 = 0.f;
@@ -516,13 +559,15 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                         gb1[j] = g * x1;
                         gb2[j] = g * x2;
                     }
-                    if (want_b) {   // dB[d][f] += sum_pt g * x'_d   (geometry decoder: e == f)
-                        const float s0 = warp_colsum32(gb0, lane), s1 = warp_colsum32(gb1, lane), s2 = warp_colsum32(gb2, lane);
-                        const int e = ecol0 + eb + lane;
-                        if (e < E) {
-                            red_add(grd.v[0] + e, s0);
-                            red_add(grd.v[0] + NF + e, s1);
-                            red_add(grd.v[0] + 2 * NF + e, s2);
+                    if constexpr (EB == 32) {
+                        if (want_b) {   // dB[d][f] += sum_pt g * x'_d   (geometry decoder: e == f)
+                            const float s0 = warp_colsum32(gb0, lane), s1 = warp_colsum32(gb1, lane), s2 = warp_colsum32(gb2, lane);
+                            const int e = ecol0 + eb + lane;
+                            if (e < E) {
+                                red_add(grd.v[0] + e, s0);
+                                red_add(grd.v[0] + NF + e, s1);
+                                red_add(grd.v[0] + 2 * NF + e, s2);
+                            }
                         }
                     }
                 }
@@ -542,16 +587,6 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
 }
 
 // ---------------------------------------------------------------------------------------------- wgrad
-// MN-major SWIZZLE_128B descriptor for an operand stored rows = contraction index (points), 64 columns per slab:
-// LBO = byte distance between consecutive 64-column slabs, SBO = 1024 (8-row groups along the contraction).
-__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr, uint32_t lbo) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | (64ull << 32) | (1ull << 46) |
-           (2ull << 61);
-}
-__host__ __device__ constexpr uint32_t instr_desc_mn(int M, int N) {   // both operands MN-major, fp16, f32 accumulate
-    return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
 template <int KIND> struct GeoW {
     using C = Cfg<KIND>;
     using G = Geo<KIND>;

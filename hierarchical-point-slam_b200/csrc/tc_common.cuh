@@ -12,9 +12,11 @@ namespace tc {
 constexpr int TILE = 128;            // sample points per tile = UMMA M = TMEM lanes
 constexpr int SLAB = 16384;          // bytes: 128 rows x 128 B
 constexpr int NST = 6;               // weight ring stages
-constexpr int NTHR = 320;
-constexpr int EPI_WARP0 = 2;
-constexpr int NEPI = 256;
+constexpr int EPI_WARP0 = 2;         // warp 0 = producer, warp 1 = MMA issuer, then the epilogue warps
+constexpr int EPI_WARPS = 16;        // 4 TMEM lane quadrants x CG column groups
+constexpr int CG = EPI_WARPS / 4;    // column groups: an epilogue thread owns one point (row) x 1/CG of the columns
+constexpr int NEPI = EPI_WARPS * 32;
+constexpr int NTHR = (EPI_WARP0 + EPI_WARPS) * 32;
 constexpr float kTwoPi = 6.283185307179586f;
 
 template <int KIND> struct Cfg;
@@ -125,6 +127,19 @@ __device__ __forceinline__ bool elect_one() {
         "@px mov.s32 %0, 1;\n\t}"
         : "+r"(pred));
     return pred != 0;
+}
+
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100 version 1):
