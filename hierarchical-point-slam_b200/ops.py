@@ -16,8 +16,26 @@ MLP_GEO, MLP_COL = 0, 1
 N_PARAM = 23
 
 
-def _stream():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream(stream=None):
+    return ctypes.c_void_p((stream if stream is not None else torch.cuda.current_stream()).cuda_stream)
+
+
+# The two decoders of a colour stage are independent between the gather and the compositing kernel: the fused
+# render runs the geometry decoder (and all weight re-packing) on a side stream so that the hardware block
+# scheduler fills the tail of one persistent kernel with CTAs of the other.  Everything is allocated on the main
+# stream before the fork and the side stream joins before anything is released, so the caching allocator needs no
+# record_stream calls; the fork/join pattern is capturable in a CUDA graph.  HPS_STREAMS=0 serialises.
+MULTI_STREAM = os.environ.get("HPS_STREAMS", "1") != "0"
+_side_streams = {}
+
+
+def _side_stream(dev):
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    s = _side_streams.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=dev)
+        _side_streams[key] = s
+    return s
 
 
 # ---- instrumentation: kernel-launch counter and optional CUDA-event timers per C-ABI call -----------
@@ -234,23 +252,44 @@ def _packed_buffer(kind, device, tc=False):
 USE_TC_BWD = os.environ.get("HPS_USE_TC_BWD", "1") != "0"
 
 
-def _mlp_forward(kind, arr, p_c, c_c, aff, P, out, need_grad, dev):
-    """pack + forward of one decoder on the current stream.  Returns the saved workspace ("tc"|"simt", tensor)
-    that _mlp_backward consumes (None when no backward will follow)."""
+def _mlp_workspace(kind, P, need_grad, dev):
+    """Saved-for-backward workspace of one decoder forward: ("tc"|"simt", tensor) or None."""
     lib = _lib.load()
-    saved = None
+    if not need_grad:
+        return None
+    if USE_TC and USE_TC_BWD:
+        return ("tc", torch.empty(int(lib.hps_mlp_tc_ws_bytes(kind, P)), dtype=torch.uint8, device=dev))
+    return ("simt", torch.empty((P + 63) // 64 * 64 * int(lib.hps_mlp_act_floats(kind)), dtype=torch.float32,
+                                device=dev))
+
+
+def _mlp_pack(kind, arr, dev, stream=None, bwd=None):
+    """Re-pack the (possibly just updated) decoder weights into the tensor-core operand images.  bwd: a buffer
+    (_new_bwd_images) owned by the caller that receives the backward images too, so that a later backward of
+    this very forward finds the weights it was run with."""
+    _call("hps_mlp_tc_pack", kind, arr, _lib.ptr(_packed_buffer(kind, dev, tc=True)), _stream(stream))
+    if bwd is not None:
+        _call("hps_mlp_tc_bwd_pack", kind, arr, _lib.ptr(bwd), _stream(stream))
+
+
+def _new_bwd_images(kind, dev):
+    return torch.empty(int(_lib.load().hps_mlp_tc_bwd_packed_bytes(kind)), dtype=torch.uint8, device=dev)
+
+
+def _mlp_forward(kind, arr, p_c, c_c, aff, P, out, need_grad, dev, stream=None, saved=None, packed=False):
+    """pack + forward of one decoder on `stream` (default: current).  Returns the saved workspace ("tc"|"simt",
+    tensor) that _mlp_backward consumes (None when no backward will follow)."""
+    lib = _lib.load()
     if USE_TC:
+        if saved is None:
+            saved = _mlp_workspace(kind, P, need_grad, dev)
         pk = _packed_buffer(kind, dev, tc=True)
-        act = ws = None
-        if need_grad and USE_TC_BWD:
-            ws = torch.empty(int(lib.hps_mlp_tc_ws_bytes(kind, P)), dtype=torch.uint8, device=dev)
-            saved = ("tc", ws)
-        elif need_grad:
-            act = torch.empty((P + 63) // 64 * 64 * int(lib.hps_mlp_act_floats(kind)), dtype=torch.float32, device=dev)
-            saved = ("simt", act)
-        _call("hps_mlp_tc_pack", kind, arr, _lib.ptr(pk), _stream())
+        act = saved[1] if (saved and saved[0] == "simt") else None
+        ws = saved[1] if (saved and saved[0] == "tc") else None
+        if not packed:
+            _call("hps_mlp_tc_pack", kind, arr, _lib.ptr(pk), _stream(stream))
         _call("hps_mlp_tc_fwd", kind, arr, _lib.ptr(pk), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), P, _lib.ptr(out),
-              _lib.ptr(act), _lib.ptr(ws), _stream())
+              _lib.ptr(act), _lib.ptr(ws), _stream(stream))
     else:
         pk = _packed_buffer(kind, dev)
         act = None
@@ -266,25 +305,42 @@ def _mlp_forward(kind, arr, p_c, c_c, aff, P, out, need_grad, dev):
 _bwd_packed_cache = {}
 
 
-def _mlp_backward(kind, prm, saved_kind, saved, p_c, c_c, aff, dout, P, dprm, dc, need_dp, daff, dev):
-    """Backward of one decoder; returns dp (P,3) or None.  dprm: list of gradient buffers (or None)."""
-    f32 = dict(dtype=torch.float32, device=dev)
-    darr = _ptr_array(dprm) if dprm is not None else None
+def _bwd_packed_buffer(kind, dev):
+    key = (kind, dev)
+    pk = _bwd_packed_cache.get(key)
+    if pk is None:
+        pk = torch.empty(int(_lib.load().hps_mlp_tc_bwd_packed_bytes(kind)), dtype=torch.uint8, device=dev)
+        _bwd_packed_cache[key] = pk
+    return pk
+
+
+def _mlp_dp_buffer(saved_kind, P, need_dp, dev):
+    if not need_dp:
+        return None
     if saved_kind == "tc":
-        key = (kind, dev)
-        pk = _bwd_packed_cache.get(key)
-        if pk is None:
-            pk = torch.empty(int(_lib.load().hps_mlp_tc_bwd_packed_bytes(kind)), dtype=torch.uint8, device=dev)
-            _bwd_packed_cache[key] = pk
-        dp = torch.zeros(P, 3, **f32) if need_dp else None      # accumulated by the kernel
+        return torch.zeros(P, 3, dtype=torch.float32, device=dev)      # accumulated by the kernel
+    return torch.empty(P, 3, dtype=torch.float32, device=dev)
+
+
+def _mlp_backward(kind, prm, saved_kind, saved, p_c, c_c, aff, dout, P, dprm, dc, need_dp, daff, dev, stream=None,
+                  dp=None, packed=None):
+    """Backward of one decoder on `stream`; returns dp (P,3) or None.  dprm: list of gradient buffers (or None).
+    dp: preallocated _mlp_dp_buffer (required when `stream` is not the current stream); packed: backward weight
+    images built at forward time by _mlp_pack (None: build them now)."""
+    darr = _ptr_array(dprm) if dprm is not None else None
+    if dp is None:
+        dp = _mlp_dp_buffer(saved_kind, P, need_dp, dev)
+    if saved_kind == "tc":
         arr = _ptr_array(prm)
-        _call("hps_mlp_tc_bwd_pack", kind, arr, _lib.ptr(pk), _stream())
+        pk = packed
+        if pk is None:
+            pk = _bwd_packed_buffer(kind, dev)
+            _call("hps_mlp_tc_bwd_pack", kind, arr, _lib.ptr(pk), _stream(stream))
         _call("hps_mlp_tc_bwd", kind, arr, _lib.ptr(pk), _lib.ptr(saved), _lib.ptr(p_c), _lib.ptr(aff), _lib.ptr(dout), P,
-              darr, _lib.ptr(dc), _lib.ptr(dp), _lib.ptr(daff), _stream())
+              darr, _lib.ptr(dc), _lib.ptr(dp), _lib.ptr(daff), _stream(stream))
         return dp
-    dp = torch.empty(P, 3, **f32) if need_dp else None
     _call("hps_mlp_bwd", kind, _ptr_array(prm), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), _lib.ptr(saved),
-          _lib.ptr(dout), P, darr, _lib.ptr(dc), _lib.ptr(dp), _lib.ptr(daff), _stream())
+          _lib.ptr(dout), P, darr, _lib.ptr(dc), _lib.ptr(dp), _lib.ptr(daff), _stream(stream))
     return dp
 
 
@@ -497,7 +553,21 @@ class _RenderRays(torch.autograd.Function):
         zz = _f32c(spec.z_zero) if spec.z_zero is not None else None
         garr, carr = _ptr_array(gprm), (_ptr_array(cprm) if spec.color_stage else None)
         st = _stream
+        fork = MULTI_STREAM and TIMERS is None and USE_TC and spec.color_stage
         with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            bpk_g = bpk_c = None
+            if fork:
+                # side stream: weight images for forward (and backward) while the main stream samples and searches
+                side = _side_stream(dev)
+                ws_g = _mlp_workspace(MLP_GEO, P, need_grad, dev)
+                ws_c = _mlp_workspace(MLP_COL, P, need_grad, dev)
+                if need_grad and USE_TC_BWD:
+                    bpk_g, bpk_c = _new_bwd_images(MLP_GEO, dev), _new_bwd_images(MLP_COL, dev)
+                side.wait_stream(main)
+                _mlp_pack(MLP_COL, carr, dev, side, bwd=bpk_c)
+                packed_col = side.record_event()
+                _mlp_pack(MLP_GEO, garr, dev, side, bwd=bpk_g)
             _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t),
                   0.0 if rad_t is not None else float(rad), _lib.ptr(zz), R, S, float(spec.near), float(spec.far),
                   _lib.ptr(z), _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), st())
@@ -506,8 +576,16 @@ class _RenderRays(torch.autograd.Function):
             _call("hps_interp_fwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(D), _lib.ptr(t_dn), _lib.ptr(cnt),
                   _lib.ptr(pos), _lib.ptr(fg), _lib.ptr(fc), _lib.ptr(fill_g), _lib.ptr(fill_c), P, int(spec.min_nn),
                   _lib.ptr(w), _lib.ptr(c_geo), _lib.ptr(c_col), _lib.ptr(has), st())
-            sv_g = _mlp_forward(MLP_GEO, garr, pts, c_geo, None, P, occ, need_grad, dev)
-            sv_c = _mlp_forward(MLP_COL, carr, pts, c_col, aff, P, rgb, need_grad, dev) if spec.color_stage else None
+            if fork:
+                side.wait_stream(main)
+                main.wait_event(packed_col)
+                sv_c = _mlp_forward(MLP_COL, carr, pts, c_col, aff, P, rgb, need_grad, dev, main, ws_c, packed=True)
+                sv_g = _mlp_forward(MLP_GEO, garr, pts, c_geo, None, P, occ, need_grad, dev, side, ws_g, packed=True)
+                main.wait_stream(side)
+            else:
+                sv_g = _mlp_forward(MLP_GEO, garr, pts, c_geo, None, P, occ, need_grad, dev)
+                sv_c = _mlp_forward(MLP_COL, carr, pts, c_col, aff, P, rgb, need_grad, dev) if spec.color_stage else None
+            ctx.bwd_packed = (bpk_g, bpk_c)
             act_g, act_c = (sv_g[1] if sv_g else None), (sv_c[1] if sv_c else None)
             ctx.saved_kinds = (sv_g[0] if sv_g else None, sv_c[0] if sv_c else None)
             _call("hps_composite_fwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
@@ -555,12 +633,24 @@ class _RenderRays(torch.autograd.Function):
         with torch.cuda.device(dev):
             _call("hps_composite_bwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
                   float(spec.coef), _lib.ptr(gd), _lib.ptr(gc), _lib.ptr(d_rgb), 3, _lib.ptr(d_occ), 1, st())
-            dp_g = _mlp_backward(MLP_GEO, gprm, ctx.saved_kinds[0], act_g, pts, c_geo, None, d_occ, P, dg, dc_g, need_p,
-                                 None, dev)
+            fork = MULTI_STREAM and TIMERS is None and spec.color_stage and ctx.saved_kinds == ("tc", "tc")
             dp_c = None
-            if spec.color_stage:
-                dp_c = _mlp_backward(MLP_COL, cprm, ctx.saved_kinds[1], act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c,
-                                     need_p, daff, dev)
+            if fork:
+                main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+                dp_g = _mlp_dp_buffer("tc", P, need_p, dev)
+                dp_c = _mlp_dp_buffer("tc", P, need_p, dev)
+                side.wait_stream(main)
+                _mlp_backward(MLP_COL, cprm, "tc", act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c, need_p, daff, dev, main,
+                              dp_c, packed=ctx.bwd_packed[1])
+                _mlp_backward(MLP_GEO, gprm, "tc", act_g, pts, c_geo, None, d_occ, P, dg, dc_g, need_p, None, dev, side,
+                              dp_g, packed=ctx.bwd_packed[0])
+                main.wait_stream(side)
+            else:
+                dp_g = _mlp_backward(MLP_GEO, gprm, ctx.saved_kinds[0], act_g, pts, c_geo, None, d_occ, P, dg, dc_g,
+                                     need_p, None, dev)
+                if spec.color_stage:
+                    dp_c = _mlp_backward(MLP_COL, cprm, ctx.saved_kinds[1], act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c,
+                                         need_p, daff, dev)
             if dfg is not None or dfc is not None or need_p:
                 _call("hps_interp_bwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(w), _lib.ptr(has), _lib.ptr(pos),
                       _lib.ptr(fg), _lib.ptr(fc), _lib.ptr(c_geo), _lib.ptr(c_col), _lib.ptr(dc_g), _lib.ptr(dc_c), P,
