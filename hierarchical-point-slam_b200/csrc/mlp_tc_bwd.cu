@@ -312,7 +312,8 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                             for (int k = 0; k < NK; ++k) {
                                 const uint64_t ah = smem_desc(aDAh + s * SLAB + k * 32), al = smem_desc(aDAl + s * SLAB + k * 32);
                                 const uint64_t bh = smem_desc(wh + s * (NE * 128) + k * 32), bl = smem_desc(wl + s * (NE * 128) + k * 32);
-                                tc_mma(t_e, ah, bh, ID_E, (s > 0 || k > 0) ? 1u : 0u);
+                                // layer 3 starts the embedding gradient, layer 0 accumulates onto it in TMEM
+                                tc_mma(t_e, ah, bh, ID_E, (layer == 0 || s > 0 || k > 0) ? 1u : 0u);
                                 tc_mma(t_e, ah, bl, ID_E, 1u);
                                 tc_mma(t_e, al, bh, ID_E, 1u);
                             }
@@ -333,6 +334,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
         const int cgp = ew >> 2;
         const int row = quad * 32 + lane;
         constexpr int CPT = (H >= 32 * CG) ? H / CG : 32;
+        static_assert(CPT == 32, "one 32-column block per epilogue thread");
         const bool col_owner = (H >= 32 * CG) || (cgp == 0);
         const int col0 = (H >= 32 * CG) ? cgp * CPT : 0;
         constexpr int ECPT = B::ECPT;
@@ -346,22 +348,23 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
             uint8_t* xg = W::x_ptr(ws, tile);
             uint8_t* gg = W::g_ptr(ws, tile);
             const float* ag = W::a_ptr(ws, tile);
-            float de[ECPT];
+            // pre-activations a_layer (this thread's row, its 32 hidden columns): issued before the wait on the
+            // accumulator so that the HBM/L2 latency of the forward workspace hides behind the MMAs
+            auto load_a = [&](int layer, float (&av)[32]) {
 #pragma unroll
-            for (int j = 0; j < ECPT; ++j) de[j] = 0.f;
-
-            // dy (32 columns starting at hidden column c0) of layer `layer` -> da, next A operands, dumps for wgrad
-            auto emit = [&](int layer, int c0, const float (&dy)[32]) {
-                const int slab = c0 / 64, cc = c0 % 64;
+                for (int j = 0; j < 32; ++j) av[j] = __ldg(ag + (layer * H + col0 + j) * TILE + row);
+            };
+            // dy (this thread's 32 hidden columns) of layer `layer` -> da, next A operands, dumps for wgrad
+            auto emit = [&](int layer, const float (&av)[32], const float (&dy)[32]) {
+                const int slab = col0 / 64, cc = col0 % 64;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     uint16_t yh[8], yl[8], ah[8], al[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float a = ag[(layer * H + c0 + q * 8 + j) * TILE + row];
                         const float d = dy[q * 8 + j];
                         split16(d, yh[j], yl[j]);
-                        split16(d * act_grad<C::RELU>(a), ah[j], al[j]);
+                        split16(d * act_grad<C::RELU>(av[q * 8 + j]), ah[j], al[j]);
                     }
                     const uint32_t so = slab_off(row, (cc >> 3) + q);
                     const uint4 v0 = pack8(yh), v1 = pack8(yl), v2 = pack8(ah), v3 = pack8(al);
@@ -380,6 +383,8 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
 
             // ---- output layer (SIMT): d raw, dWo, dbo, daffine, dy_4 ----
             {
+                float a4[32];
+                if (col_owner) load_a(4, a4);
                 float dr[3] = {0.f, 0.f, 0.f};
                 if (live) {
 #pragma unroll
@@ -424,9 +429,8 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                     }
                 }
                 if (col_owner) {
-#pragma unroll 1
-                    for (int cb = 0; cb < CPT; cb += 32) {
-                        const int c0 = col0 + cb;
+                    {
+                        const int c0 = col0;
                         float dy[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -461,7 +465,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                                 red_add(grd.v[iWo] + o * H + c0 + lane, s);
                             }
                         }
-                        emit(4, c0, dy);
+                        emit(4, a4, dy);
                     }
                 }
             }
@@ -470,42 +474,28 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
 
 #pragma unroll 1
             for (int layer = 4; layer >= 0; --layer) {
+                float an[32];
+                if (layer >= 1 && col_owner) load_a(layer - 1, an);
                 mbar_wait(acc_ready, nacc & 1);
                 ++nacc;
                 tc_fence_after();
                 if (want_w && quad == 0 && col_owner) {   // bias gradients of this layer: row 0 of the column sums
 #pragma unroll 1
-                    for (int cb = 0; cb < CPT; cb += 32) {
-                        float sb[32], sbc[32];
-                        tc_ld32(tmem + B::T_SB + col0 + cb, sb);
-                        tc_ld32(tmem + B::T_SBC + col0 + cb, sbc);
+                    for (int which = 0; which < 2; ++which) {
+                        float sb[32];
+                        tc_ld32(tmem + (which ? B::T_SBC : B::T_SB) + col0, sb);
+                        float* dst = (which ? grd.v[iBc(layer)] : grd.v[iB(layer)]) + col0;
                         if (lane == 0) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                red_add(grd.v[iB(layer)] + col0 + cb + j, sb[j] * gInv);
-                                red_add(grd.v[iBc(layer)] + col0 + cb + j, sbc[j] * gInv);
-                            }
+                            for (int j = 0; j < 32; ++j) red_add(dst + j, sb[j] * gInv);
                         }
-                    }
-                }
-                if (layer == 0 || layer == 3) {
-#pragma unroll 1
-                    for (int eb = 0; eb < ECPT; eb += EB) {
-                        float v[EB];
-                        if constexpr (EB == 32) tc_ld32(tmem + lane_addr + B::T_E + ecol0 + eb, v);
-                        else tc_ld16(tmem + lane_addr + B::T_E + ecol0 + eb, v);
-#pragma unroll
-                        for (int j = 0; j < EB; ++j) de[eb + j] += v[j];
                     }
                 }
                 if (layer >= 1) {
                     if (col_owner) {
-#pragma unroll 1
-                        for (int cb = 0; cb < CPT; cb += 32) {
-                            float dy[32];
-                            tc_ld32(tmem + lane_addr + B::T_H + col0 + cb, dy);
-                            emit(layer - 1, col0 + cb, dy);
-                        }
+                        float dy[32];
+                        tc_ld32(tmem + lane_addr + B::T_H + col0, dy);
+                        emit(layer - 1, an, dy);
                     }
                     tc_fence_before();
                     fence_proxy_async();
@@ -536,6 +526,9 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 float g0 = 0.f, g1 = 0.f, g2 = 0.f;
 #pragma unroll 1
                 for (int eb = 0; eb < ECPT; eb += EB) {
+                    float de[EB];       // d loss / d embedding (layers 3 and 0 summed in TMEM)
+                    if constexpr (EB == 32) tc_ld32(tmem + lane_addr + B::T_E + ecol0 + eb, de);
+                    else tc_ld16(tmem + lane_addr + B::T_E + ecol0 + eb, de);
                     float gb0[EB], gb1[EB], gb2[EB];
 #pragma unroll
                     for (int j = 0; j < EB; ++j) {
@@ -550,7 +543,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                             const float arg = fmaf(x2, b2, fmaf(x1, b1, x0 * b0));
                             float s, co;
                             sincosf(arg, &s, &co);
-                            g = ((C::CONCAT && e >= NF) ? -de[eb + j] * s : de[eb + j] * co) * gInv;
+                            g = ((C::CONCAT && e >= NF) ? -de[j] * s : de[j] * co) * gInv;
                         }
                         g0 = fmaf(g * kTwoPi, b0, g0);
                         g1 = fmaf(g * kTwoPi, b1, g1);
@@ -577,6 +570,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                     red_add(dp + pt * 3 + 2, g2);
                 }
             }
+            tc_fence_before();     // the embedding-gradient reads above precede the next tile's MMAs
         }
     }
     tc_fence_before();
@@ -591,47 +585,54 @@ template <int KIND> struct GeoW {
     using C = Cfg<KIND>;
     using G = Geo<KIND>;
     static constexpr int HS = G::HS, ES = G::ES, H = C::H, NE = 64 * ES, NH = 64 * HS;
-    // shared memory: A region [hi: 2 slabs][lo: 2 slabs] (M = 128 = two 64-column atoms; the second atom of a
-    // 32-wide decoder is a zero slab), B region [hi: up to 2 slabs][lo: up to 2 slabs]
-    static constexpr int SMEM_BYTES = 1024 + 9 * SLAB + 256;
-    // TMEM columns per group: group 0 = layers {0,1,2}, group 1 = layers {3,4}
-    __host__ __device__ static constexpr int col_w_h(int layer) {   // dW_i hidden part
-        return layer == 1 ? 0 : layer == 2 ? NH : layer == 3 ? 0 : layer == 4 ? NH : -1;
-    }
-    __host__ __device__ static constexpr int col_w_e(int layer) { return layer == 0 ? 2 * NH : layer == 3 ? 2 * NH : -1; }
-    // dWc_i accumulates as 64 columns: [sum a*c_hi | sum a*c_lo] (the c slab holds hi in columns 0..31, lo in 32..63)
-    __host__ __device__ static constexpr int col_wc(int layer) {
-        return 2 * NH + NE + 64 * (layer < 3 ? layer : layer - 3);
-    }
-    static constexpr int TMEM_COLS = 512;
-    static_assert(2 * NH + NE + 192 <= 512, "TMEM budget");
+    // One pipeline stage = a quarter tile (32 points = two K=16 steps) of every operand of one layer, as 4 KB
+    // chunks (32 rows x 128 B of a swizzled slab; the swizzle period is 8 rows, so a chunk is itself a valid
+    // SWIZZLE_128B MN-major operand with atom stride CH):
+    //   A chunks: dy_hi[HS] dy_lo[HS] da_hi[HS] da_lo[HS]        (same order as the G region of the workspace)
+    //   B chunks: y_hi[HS] e_hi[ES] y_lo[HS] e_lo[ES] c[1]        (so [y | e] is one N = NH+NE operand)
+    static constexpr int CH = 4096;
+    static constexpr int A_CHUNKS = 4 * HS, B_CHUNKS = 2 * (HS + ES) + 1;
+    static constexpr int STAGE_BYTES = (A_CHUNKS + B_CHUNKS) * CH;
+    static constexpr int NSTW = 3;
+    static constexpr int SMEM_BYTES = 1024 + NSTW * STAGE_BYTES + CH + 256;   // + CH: M=128 reads one atom past da_lo
+    // TMEM columns: dW hidden [0,NH), dW embedding [NH,NH+NE), dWc as [sum dy*c_hi | sum dy*c_lo] [NH+NE, +64)
+    static constexpr int T_WH = 0, T_WE = NH, T_WC = NH + NE;
+    static constexpr int TMEM_COLS = 256;
+    static_assert(NH + NE + 64 <= 256, "TMEM budget");
+    static constexpr int NTHRW = 320;      // producer warp, MMA warp, 8 flush warps
 };
 
+// Weight gradients.  CTA b works on layer b % 5 for every (b / 5)-th tile: it streams that layer's dgrad dumps
+// (da_i, dy_i) and the forward's operand dumps (y_{i-1}, embedding, c) through a 3-stage quarter-tile ring and
+// accumulates  dW_i = da_i^T [y_{i-1} | e]  and  dWc_i = dy_i^T c  over all its tiles in TMEM (contraction over
+// the points: both operands MN-major), then adds its partial sums to the gradient buffers (red.global.add,
+// 16-byte vectors where the row pitch allows).
 template <int KIND>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GeoW<KIND>::NTHRW, 1)
 mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles, const uint32_t* __restrict__ maxbits) {
     using C = Cfg<KIND>;
     using GW = GeoW<KIND>;
     using W = Ws<KIND>;
-    constexpr int H = C::H, E = C::E, HS = GW::HS, ES = GW::ES, NH = GW::NH, NE = GW::NE;
+    constexpr int H = C::H, E = C::E, HS = GW::HS, ES = GW::ES, NH = GW::NH, NE = GW::NE, CH = GW::CH, NSTW = GW::NSTW;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sAhi = smem;                 // 2 slabs
-    uint8_t* sAlo = smem + 2 * SLAB;      // 2 slabs
-    uint8_t* sBhi = smem + 4 * SLAB;      // 2 slabs
-    uint8_t* sBlo = smem + 6 * SLAB;      // 2 slabs
-    uint8_t* sZero = smem + 8 * SLAB;     // (unused padding keeps descriptors inside the allocation)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 9 * SLAB);
-    uint64_t* full = bars;                // operands landed
-    uint64_t* done = bars + 1;            // MMAs of the job finished (smem reusable)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTW * GW::STAGE_BYTES + CH);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NSTW;
+    uint64_t* done = bars + 2 * NSTW;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTW + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int group = blockIdx.x & 1;                       // 0: layers {0,1,2}; 1: layers {3,4}
-    const int gsize = (gridDim.x + 1 - group) / 2;          // CTAs in this group
-    const int grank = blockIdx.x >> 1;
+    const int layer = blockIdx.x % 5;
+    const int rank = blockIdx.x / 5;
+    const int gsize = ((int)gridDim.x - layer + 4) / 5;     // CTAs working on this layer
+    const bool has_h = layer >= 1, has_e = (layer == 0 || layer == 3);
+    const bool mine = rank < num_tiles;
 
     if (threadIdx.x == 0) {
-        mbar_init(full, 1);
+        for (int s = 0; s < NSTW; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
         mbar_init(done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -640,125 +641,135 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
                      "r"((uint32_t)GW::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int i = threadIdx.x; i < 9 * SLAB / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    (void)sZero;
+    // operands that a layer does not load (and the over-read atom) must still be finite: zero everything once
+    for (int i = threadIdx.x; i < (NSTW * GW::STAGE_BYTES + CH) / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const int l0 = group == 0 ? 0 : 3, l1 = group == 0 ? 2 : 4;
-    bool any_tile = false;
     if (warp == 0) {
-        // one warp: issue loads, wait, issue MMAs, wait for completion (jobs are short; CTAs overlap each other)
-        uint32_t njob = 0;
-        const uint32_t aAh = smem_u32(sAhi), aAl = smem_u32(sAlo), aBh = smem_u32(sBhi), aBl = smem_u32(sBlo);
-        for (int tile = grank; tile < num_tiles; tile += gsize) {
-            const bool first = !any_tile;
-            any_tile = true;
+        // ---- producer ----
+        const uint32_t bytes = (uint32_t)CH * (4 * HS + (has_h ? 2 * HS : 0) + (has_e ? 2 * ES : 0) + 1);
+        uint32_t it = 0;
+        for (int tile = rank; tile < num_tiles; tile += gsize) {
             const uint8_t* xg = W::x_ptr(const_cast<uint8_t*>(ws), tile);
-            const uint8_t* gg = W::g_ptr(const_cast<uint8_t*>(ws), tile);
-            for (int layer = l0; layer <= l1; ++layer) {
-                // three jobs per layer: (0) dW hidden part, (1) dW embedding part, (2) dWc
-                for (int job = 0; job < 3; ++job) {
-                    if (job == 0 && layer == 0) continue;
-                    if (job == 1 && !(layer == 0 || layer == 3)) continue;
-                    const int nb = job == 0 ? HS : (job == 1 ? ES : 1);           // B slabs per precision
-                    const int N = job == 0 ? NH : (job == 1 ? NE : 64);
-                    const int tcol = job == 0 ? GW::col_w_h(layer) : (job == 1 ? GW::col_w_e(layer) : GW::col_wc(layer));
-                    if (njob > 0) mbar_wait(done, (njob - 1) & 1);               // previous job released the buffers
-                    if (elect_one()) {
-                        const uint32_t bytes = (uint32_t)(2 * HS + (job == 2 ? 1 : 2 * nb)) * SLAB;
-                        mbar_expect_tx(full, bytes);
-                        for (int s = 0; s < HS; ++s) {
-                            const int ih = job == 2 ? W::g_dy(layer, 0, s) : W::g_da(layer, 0, s);
-                            const int il = job == 2 ? W::g_dy(layer, 1, s) : W::g_da(layer, 1, s);
-                            bulk_g2s(sAhi + s * SLAB, gg + (size_t)ih * SLAB, SLAB, full);
-                            bulk_g2s(sAlo + s * SLAB, gg + (size_t)il * SLAB, SLAB, full);
-                        }
-                        if (job == 2) {
-                            bulk_g2s(sBhi, xg + (size_t)W::x_c() * SLAB, SLAB, full);
-                        } else {
-                            for (int s = 0; s < nb; ++s) {
-                                int ih, il;
-                                if (job == 1) { ih = W::x_e(0, s); il = W::x_e(1, s); }
-                                else { ih = W::x_y(layer - 1, 0, s); il = W::x_y(layer - 1, 1, s); }
-                                bulk_g2s(sBhi + s * SLAB, xg + (size_t)ih * SLAB, SLAB, full);
-                                bulk_g2s(sBlo + s * SLAB, xg + (size_t)il * SLAB, SLAB, full);
-                            }
+            const uint8_t* gg = W::g_ptr(const_cast<uint8_t*>(ws), tile) + (size_t)W::g_dy(layer, 0, 0) * SLAB;
+            for (int q = 0; q < 4; ++q, ++it) {
+                const int st = it % NSTW;
+                if (it >= NSTW) mbar_wait(&empty[st], ((it / NSTW) - 1) & 1);
+                if (elect_one()) {
+                    uint8_t* sa = smem + st * GW::STAGE_BYTES;
+                    uint8_t* sb = sa + GW::A_CHUNKS * CH;
+                    mbar_expect_tx(&full[st], bytes);
+                    for (int j = 0; j < 4 * HS; ++j) bulk_g2s(sa + j * CH, gg + (size_t)j * SLAB + q * CH, CH, &full[st]);
+                    if (has_h) {
+                        for (int s2 = 0; s2 < HS; ++s2) {
+                            bulk_g2s(sb + s2 * CH, xg + (size_t)W::x_y(layer - 1, 0, s2) * SLAB + q * CH, CH, &full[st]);
+                            bulk_g2s(sb + (HS + ES + s2) * CH, xg + (size_t)W::x_y(layer - 1, 1, s2) * SLAB + q * CH, CH,
+                                     &full[st]);
                         }
                     }
-                    __syncwarp();
-                    mbar_wait(full, njob & 1);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t idesc = instr_desc_mn(TILE, N);
-#pragma unroll 1
-                        for (int k = 0; k < TILE / 16; ++k) {                     // contraction over the 128 points
-                            const uint64_t ah = smem_desc_mn(aAh + k * 2048, SLAB), al = smem_desc_mn(aAl + k * 2048, SLAB);
-                            const uint64_t bh = smem_desc_mn(aBh + k * 2048, SLAB), bl = smem_desc_mn(aBl + k * 2048, SLAB);
-                            tc_mma(tmem + tcol, ah, bh, idesc, (!first || k > 0) ? 1u : 0u);
-                            if (job != 2) tc_mma(tmem + tcol, ah, bl, idesc, 1u);   // job 2: B = [c_hi | c_lo] in one slab
-                            tc_mma(tmem + tcol, al, bh, idesc, 1u);
+                    if (has_e) {
+                        for (int s2 = 0; s2 < ES; ++s2) {
+                            bulk_g2s(sb + (HS + s2) * CH, xg + (size_t)W::x_e(0, s2) * SLAB + q * CH, CH, &full[st]);
+                            bulk_g2s(sb + (2 * HS + ES + s2) * CH, xg + (size_t)W::x_e(1, s2) * SLAB + q * CH, CH,
+                                     &full[st]);
                         }
-                        tc_commit(done);
                     }
-                    __syncwarp();
-                    ++njob;
+                    bulk_g2s(sb + 2 * (HS + ES) * CH, xg + (size_t)W::x_c() * SLAB + q * CH, CH, &full[st]);
                 }
+                __syncwarp();
             }
         }
-        if (njob > 0) mbar_wait(done, (njob - 1) & 1);
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    // ---- flush: TMEM lane = output feature h, columns = input feature ----
-    {
-        bool mine = false;
-        for (int tile = grank; tile < num_tiles; tile += gsize) { mine = true; break; }
-        if (mine && warp >= 2) {
-            const int quad = warp & 3;
-            const int h = quad * 32 + lane;
-            const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-            const float gInv = 1.0f / grad_scale(maxbits);
-            for (int layer = l0; layer <= l1; ++layer) {
-                const int K = layer == 0 ? E : (layer == 3 ? E + H : H);
-                if (layer >= 1) {
-                    for (int cb = 0; cb < NH; cb += 32) {
-                        float v[32];
-                        tc_ld32(tmem + lane_addr + GW::col_w_h(layer) + cb, v);
-                        if (h < H) {
+    } else if (warp == 1) {
+        // ---- MMA issue ----
+        const int nW = (has_h ? NH : 0) + (has_e ? NE : 0);
+        const uint32_t id_w = instr_desc_mn(TILE, nW), id_c = instr_desc_mn(TILE, 64);
+        const uint32_t t_w = tmem + (has_h ? GW::T_WH : GW::T_WE), t_c = tmem + GW::T_WC;
+        const uint32_t b_off = (uint32_t)(has_h ? 0 : HS) * CH;       // layer 0: B starts at the embedding chunks
+        uint32_t it = 0;
+        for (int tile = rank; tile < num_tiles; tile += gsize) {
+            for (int q = 0; q < 4; ++q, ++it) {
+                const int st = it % NSTW;
+                mbar_wait(&full[st], (it / NSTW) & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t sa = smem_u32(smem + st * GW::STAGE_BYTES);
+                    const uint32_t sb = sa + GW::A_CHUNKS * CH;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const int r = cb + j;
-                                if (r < H) red_add(grd.v[iW(layer)] + (int64_t)h * K + (layer == 3 ? E + r : r), v[j] * gInv);
-                            }
-                        }
+                    for (int k = 0; k < 2; ++k) {
+                        const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+                        const uint64_t dyh = smem_desc_mn(sa + k * 2048, CH), dyl = smem_desc_mn(sa + HS * CH + k * 2048, CH);
+                        const uint64_t dah = smem_desc_mn(sa + 2 * HS * CH + k * 2048, CH);
+                        const uint64_t dal = smem_desc_mn(sa + 3 * HS * CH + k * 2048, CH);
+                        const uint64_t bh = smem_desc_mn(sb + b_off + k * 2048, CH);
+                        const uint64_t bl = smem_desc_mn(sb + (HS + ES) * CH + b_off + k * 2048, CH);
+                        const uint64_t bc = smem_desc_mn(sb + 2 * (HS + ES) * CH + k * 2048, CH);
+                        tc_mma(t_w, dah, bh, id_w, acc);
+                        tc_mma(t_w, dah, bl, id_w, 1u);
+                        tc_mma(t_w, dal, bh, id_w, 1u);
+                        tc_mma(t_c, dyh, bc, id_c, acc);      // c chunk = [c_hi | c_lo]: the halves are summed at flush
+                        tc_mma(t_c, dyl, bc, id_c, 1u);
                     }
+                    tc_commit(&empty[st]);
                 }
-                if (layer == 0 || layer == 3) {
-                    for (int cb = 0; cb < NE; cb += 32) {
-                        float v[32];
-                        tc_ld32(tmem + lane_addr + GW::col_w_e(layer) + cb, v);
-                        if (h < H) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (cb + j < E) red_add(grd.v[iW(layer)] + (int64_t)h * K + cb + j, v[j] * gInv);
-                        }
-                    }
-                }
-                {
-                    float v[32], v2[32];
-                    tc_ld32(tmem + lane_addr + GW::col_wc(layer), v);
-                    tc_ld32(tmem + lane_addr + GW::col_wc(layer) + 32, v2);
-                    if (h < H) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) red_add(grd.v[iWc(layer)] + (int64_t)h * kC + j, (v[j] + v2[j]) * gInv);
-                    }
-                }
+                __syncwarp();
             }
+        }
+        if (mine) {
+            if (elect_one()) tc_commit(done);
+            __syncwarp();
+        }
+    } else if (mine) {
+        // ---- flush: TMEM lane = output feature h, columns = input feature ----
+        mbar_wait(done, 0);
+        tc_fence_after();
+        const int quad = warp & 3, half = (warp - 2) >> 2;
+        const int h = quad * 32 + lane;
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        const float gInv = 1.0f / grad_scale(maxbits);
+        const int K = layer == 0 ? E : (layer == 3 ? E + H : H);
+        float* gw = grd.v[iW(layer)];
+        float* gwc = grd.v[iWc(layer)];
+        const bool vec_w = ((reinterpret_cast<uintptr_t>(gw) & 15) == 0) && (K % 4 == 0) && (E % 4 == 0);
+        const bool vec_c = (reinterpret_cast<uintptr_t>(gwc) & 15) == 0;
+        auto flush16 = [&](float* dst, const float (&v)[16], int n_valid, bool vec) {     // dst: this row, 16 columns
+            if (vec && n_valid == 16) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    red_add_v4(dst + j, make_float4(v[j] * gInv, v[j + 1] * gInv, v[j + 2] * gInv, v[j + 3] * gInv));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j < n_valid) red_add(dst + j, v[j] * gInv);
+            }
+        };
+        if (has_h) {
+            for (int cb = half * (NH / 2); cb < (half + 1) * (NH / 2); cb += 16) {
+                float v[16];
+                tc_ld16(tmem + lane_addr + GW::T_WH + cb, v);
+                const int nv = H - cb < 16 ? H - cb : 16;
+                if (h < H && nv > 0) flush16(gw + (int64_t)h * K + (layer == 3 ? E : 0) + cb, v, nv, vec_w);
+            }
+        }
+        if (has_e) {
+            for (int cb = half * (NE / 2); cb < (half + 1) * (NE / 2); cb += 16) {
+                float v[16];
+                tc_ld16(tmem + lane_addr + GW::T_WE + cb, v);
+                const int nv = E - cb < 16 ? E - cb : 16;
+                if (h < H && nv > 0) flush16(gw + (int64_t)h * K + cb, v, nv, vec_w);
+            }
+        }
+        {
+            float v[16], v2[16];
+            tc_ld16(tmem + lane_addr + GW::T_WC + half * 16, v);
+            tc_ld16(tmem + lane_addr + GW::T_WC + 32 + half * 16, v2);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += v2[j];
+            if (h < H) flush16(gwc + (int64_t)h * kC + half * 16, v, 16, vec_c);
         }
     }
     tc_fence_before();
@@ -809,9 +820,8 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
         prm, grd, reinterpret_cast<const uint8_t*>(img), reinterpret_cast<uint8_t*>(ws), p, affine, dout, P, num_tiles,
         dc, dp, daffine);
     if (dparams) {
-        int wgrid = 2 * num_tiles < kNumSMs ? 2 * num_tiles : kNumSMs;
-        if (wgrid < 2) wgrid = 2;
-        mlp_wgrad_tc_kernel<KIND><<<wgrid, 192, GeoW<KIND>::SMEM_BYTES, s>>>(grd, reinterpret_cast<const uint8_t*>(ws),
+        const int wgrid = 5 * num_tiles < kNumSMs ? 5 * num_tiles : kNumSMs;     // >= 5: every layer has a CTA
+        mlp_wgrad_tc_kernel<KIND><<<wgrid, GeoW<KIND>::NTHRW, GeoW<KIND>::SMEM_BYTES, s>>>(grd, reinterpret_cast<const uint8_t*>(ws),
                                                                             num_tiles, maxbits);
     }
     return 0;
