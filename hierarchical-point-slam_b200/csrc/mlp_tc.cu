@@ -25,6 +25,12 @@
 namespace hps {
 namespace tc {
 
+static __device__ unsigned long long* g_trace_fwd = nullptr;
+int set_trace_fwd(void* buf) {
+    HPS_CUDA_OK(cudaMemcpyToSymbol(g_trace_fwd, &buf, sizeof(buf)));
+    return 0;
+}
+
 // ---------------------------------------------------------------------------------------------- pack
 // Global image of the weight slabs in consumption order (see Geo::SLABS_PER_TILE):
 //   for layer i: [Wc_i: cols 0..31 fp16 hi, 32..63 fp16 lo]  then for every k-slab s: [W_i hi], [W_i lo]
@@ -108,7 +114,8 @@ template <bool RELU> __device__ __forceinline__ float act_fast(float a) {
     return fmaxf(a, 0.f) + __logf(1.0f + __expf(-fabsf(100.0f * a))) * 0.01f;
 }
 
-template <int KIND>
+// DUMP: 0 = inference, 1 = SIMT-layout activations for mlp_bwd_kernel (act), 2 = workspace for the tensor-core backward (ws)
+template <int KIND, int DUMP>
 __global__ void __launch_bounds__(NTHR, 1)
 mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __restrict__ p,
                   const float* __restrict__ c, const float* __restrict__ affine, int64_t P, int num_tiles,
@@ -124,7 +131,10 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
     uint8_t* sC = sAlo + AS * SLAB;                // cols 0..31 c hi, 32..63 c lo (fp16 both)
     uint8_t* sW = sC + SLAB;                       // NST ring stages
     float* sBias = reinterpret_cast<float*>(sW + NST * SLAB);      // [5][2][H]: b_i, bc_i
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sBias + 2 * 5 * H);
+    float* sB = sBias + 2 * 5 * H;                                  // [3][NF] Fourier projection
+    float* sBo = sB + 3 * NF;                                       // [4] output bias
+    float* sAff = sBo + 4;                                          // [12] exposure affine (colour)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sAff + 12 + ((3 * NF) & 1));   // 8-byte aligned
     uint64_t* full = bars;                         // [NST]
     uint64_t* empty = bars + NST;                  // [NST]
     uint64_t* a_ready = bars + 2 * NST;            // epilogue -> MMA: A operand in place, accumulators drained
@@ -153,6 +163,9 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
         sBias[(l * 2 + 0) * H + n] = prm.v[iB(l)][n];
         sBias[(l * 2 + 1) * H + n] = prm.v[iBc(l)][n];
     }
+    for (int i = threadIdx.x; i < 3 * NF; i += NTHR) sB[i] = prm.v[0][i];
+    if (threadIdx.x < NOUT) sBo[threadIdx.x] = prm.v[iBo][threadIdx.x];
+    if (threadIdx.x < 12 && affine != nullptr) sAff[threadIdx.x] = affine[threadIdx.x];
     // zero the A slabs and the c slab once (padding columns stay zero for the whole kernel)
     for (int i = threadIdx.x; i < (2 * AS + 1) * SLAB / 16; i += NTHR)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -183,12 +196,15 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
         const uint32_t t_a = tmem, t_u = tmem + H, t_o = tmem + 2 * H;
         const uint32_t aHi = smem_u32(sAhi), aLo = smem_u32(sAlo), aC = smem_u32(sC), aW = smem_u32(sW);
         uint32_t it = 0, nready = 0;
+        unsigned long long* tr = (blockIdx.x == 0 && lane == 0) ? g_trace_fwd : nullptr;
+        int ts = 64;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 #pragma unroll 1
             for (int layer = 0; layer < 6; ++layer) {
                 mbar_wait(a_ready, nready & 1);
                 ++nready;
                 tc_fence_after();
+                trace_stamp(tr, ts++);
                 if (layer < 5) {
                     // u = c . Wc^T   (K = 32: two k-steps; c slab / Wc slab hold hi in columns 0..31, lo in 32..63)
                     {
@@ -268,6 +284,7 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
                 }
                 if (elect_one()) tc_commit(acc_ready);
                 __syncwarp();
+                trace_stamp(tr, ts++);
             }
         }
     } else {
@@ -276,161 +293,153 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
         const int quad = warp & 3;                // TMEM lane quadrant this warp may access
         const int cgp = ew >> 2;                  // column group handled by this warp
         const int row = quad * 32 + lane;         // tile row = TMEM lane
-        constexpr int CPT = (H >= 32 * CG) ? H / CG : 32;   // hidden columns per thread (colour 32; geometry 32, group 0 only)
-        const bool col_owner = (H >= 32 * CG) || (cgp == 0);
-        const int col0 = (H >= 32 * CG) ? cgp * CPT : 0;
+        constexpr int CPT = H / CG;               // hidden columns per thread: colour 32, geometry 8
+        static_assert(CPT == 32 || CPT == 8, "epilogue column split");
+        constexpr int NCH = (E + 7) / 8;          // 16-byte chunks (8 columns) of the embedding
+        const int col0 = cgp * CPT;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         uint32_t nacc = 0;
+        unsigned long long* tr = (blockIdx.x == 0 && ew == 0 && lane == 0) ? g_trace_fwd : nullptr;
+        int ts = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            trace_stamp(tr, ts++);
             const int64_t pt = (int64_t)tile * TILE + row;
             const bool live = pt < P;
-            uint8_t* xg = ws ? W::x_ptr(ws, tile) : nullptr;          // X slab images of this tile (tensor-core backward)
-            float* ag = ws ? W::a_ptr(ws, tile) : nullptr;
-            // ---- tile prologue: Fourier features -> embedding slabs, c -> c slab ----
+            uint8_t* xg = DUMP == 2 ? W::x_ptr(ws, tile) : nullptr;   // X slab images of this tile (tensor-core backward)
+            float* ag = DUMP == 2 ? W::a_ptr(ws, tile) : nullptr;
+            // ---- tile prologue: c -> c slab, Fourier features -> embedding slabs ----
             {
+                // this thread converts kC / CG = 8 of the 32 channels; loaded first so the latency hides behind the sines
+                static_assert(kC / CG == 8, "c split");
+                float cf[8];
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const float4 v4 = live ? ldg4(c + pt * kC + cgp * 8 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    cf[q * 4] = v4.x; cf[q * 4 + 1] = v4.y; cf[q * 4 + 2] = v4.z; cf[q * 4 + 3] = v4.w;
+                }
                 float x0 = 0.f, x1 = 0.f, x2 = 0.f;
                 if (live) {
                     x0 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 0));
                     x1 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 1));
                     x2 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 2));
                 }
-                const float* B = prm.v[0];
-                for (int j = cgp; j < NF; j += CG) {
-                    const float arg = fmaf(x2, __ldg(B + 2 * NF + j), fmaf(x1, __ldg(B + NF + j), x0 * __ldg(B + j)));
-                    float s, co;
-                    if (C::CONCAT) sincosf(arg, &s, &co); else { s = sinf(arg); co = 0.f; }
-                    uint16_t hi, lo;
-                    {
-                        split16(s, hi, lo);
-                        const int slab = HS + j / 64, cc = j % 64;
-                        const uint32_t so = slab_off(row, cc >> 3) + (cc & 7) * 2;
-                        const uint32_t off = slab * SLAB + so;
-                        *reinterpret_cast<uint16_t*>(sAhi + off) = hi;
-                        *reinterpret_cast<uint16_t*>(sAlo + off) = lo;
-                        if (xg) {
-                            *reinterpret_cast<uint16_t*>(xg + W::x_e(0, j / 64) * SLAB + so) = hi;
-                            *reinterpret_cast<uint16_t*>(xg + W::x_e(1, j / 64) * SLAB + so) = lo;
+#pragma unroll 1
+                for (int ch = cgp; ch < NCH; ch += CG) {        // ch is warp-uniform
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int e = ch * 8 + j;
+                        float val = 0.f;                         // columns >= E stay zero
+                        if (e < E) {
+                            const bool is_cos = C::CONCAT && e >= NF;
+                            const int f = is_cos ? e - NF : e;
+                            const float arg = fmaf(x2, sB[2 * NF + f], fmaf(x1, sB[NF + f], x0 * sB[f]));
+                            val = is_cos ? cosf(arg) : sinf(arg);
                         }
+                        v[j] = val;
                     }
-                    if (C::CONCAT) {
-                        split16(co, hi, lo);
-                        const int e = NF + j;
-                        const int slab = HS + e / 64, cc = e % 64;
-                        const uint32_t so = slab_off(row, cc >> 3) + (cc & 7) * 2;
-                        const uint32_t off = slab * SLAB + so;
-                        *reinterpret_cast<uint16_t*>(sAhi + off) = hi;
-                        *reinterpret_cast<uint16_t*>(sAlo + off) = lo;
-                        if (xg) {
-                            *reinterpret_cast<uint16_t*>(xg + W::x_e(0, e / 64) * SLAB + so) = hi;
-                            *reinterpret_cast<uint16_t*>(xg + W::x_e(1, e / 64) * SLAB + so) = lo;
-                        }
+                    uint4 vh, vl;
+                    split8(v, vh, vl);
+                    const int slab = ch >> 3;
+                    const uint32_t so = slab_off(row, ch & 7);
+                    *reinterpret_cast<uint4*>(sAhi + (HS + slab) * SLAB + so) = vh;
+                    *reinterpret_cast<uint4*>(sAlo + (HS + slab) * SLAB + so) = vl;
+                    if (DUMP == 2) {
+                        *reinterpret_cast<uint4*>(xg + W::x_e(0, slab) * SLAB + so) = vh;
+                        *reinterpret_cast<uint4*>(xg + W::x_e(1, slab) * SLAB + so) = vl;
                     }
                 }
-                // c: this thread converts kC / CG of the 32 channels
-                constexpr int CPC = kC / CG;
-                float cf[CPC];
-#pragma unroll
-                for (int q = 0; q < CPC / 4; ++q) {
-                    const float4 v4 = live ? ldg4(c + pt * kC + cgp * CPC + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    cf[q * 4] = v4.x; cf[q * 4 + 1] = v4.y; cf[q * 4 + 2] = v4.z; cf[q * 4 + 3] = v4.w;
-                }
-                uint16_t hi[CPC], lo[CPC];
-#pragma unroll
-                for (int q = 0; q < CPC; ++q) split16(cf[q], hi[q], lo[q]);
-#pragma unroll
-                for (int q = 0; q < CPC / 8; ++q) {
-                    const uint4 vh = make_uint4(hi[q * 8 + 0] | (hi[q * 8 + 1] << 16), hi[q * 8 + 2] | (hi[q * 8 + 3] << 16),
-                                                hi[q * 8 + 4] | (hi[q * 8 + 5] << 16), hi[q * 8 + 6] | (hi[q * 8 + 7] << 16));
-                    const uint4 vl = make_uint4(lo[q * 8 + 0] | (lo[q * 8 + 1] << 16), lo[q * 8 + 2] | (lo[q * 8 + 3] << 16),
-                                                lo[q * 8 + 4] | (lo[q * 8 + 5] << 16), lo[q * 8 + 6] | (lo[q * 8 + 7] << 16));
-                    const int ch = cgp * (CPC / 8) + q;
-                    *reinterpret_cast<uint4*>(sC + slab_off(row, ch)) = vh;
-                    *reinterpret_cast<uint4*>(sC + slab_off(row, 4 + ch)) = vl;
-                    if (xg) {
-                        *reinterpret_cast<uint4*>(xg + W::x_c() * SLAB + slab_off(row, ch)) = vh;
-                        *reinterpret_cast<uint4*>(xg + W::x_c() * SLAB + slab_off(row, 4 + ch)) = vl;
-                    }
+                trace_stamp(tr, ts++);
+                uint4 vh, vl;
+                split8(cf, vh, vl);
+                *reinterpret_cast<uint4*>(sC + slab_off(row, cgp)) = vh;
+                *reinterpret_cast<uint4*>(sC + slab_off(row, 4 + cgp)) = vl;
+                if (DUMP == 2) {
+                    *reinterpret_cast<uint4*>(xg + W::x_c() * SLAB + slab_off(row, cgp)) = vh;
+                    *reinterpret_cast<uint4*>(xg + W::x_c() * SLAB + slab_off(row, 4 + cgp)) = vl;
                 }
             }
             fence_proxy_async();
             mbar_arrive(a_ready);
+            trace_stamp(tr, ts++);
 
-            // activation workspace: same layout as the SIMT edition ([64-point tile][slot][feature][point]); rows
-            // beyond P but inside the last 64-point tile are written too (finite values: the backward multiplies
-            // them by zero gradients)
-            float* act_tile0 = (act != nullptr && pt < ((P + 63) / 64) * 64)
+            // SIMT-backward activation workspace (DUMP == 1): [64-point tile][slot][feature][point]; rows beyond P
+            // but inside the last 64-point tile are written too (finite values: the backward multiplies them by
+            // zero gradients)
+            float* act_tile0 = (DUMP == 1 && pt < ((P + 63) / 64) * 64)
                                    ? act + (pt / 64) * (int64_t)(10 * H * 64) + (pt % 64) : nullptr;
             for (int layer = 0; layer < 5; ++layer) {
                 mbar_wait(acc_ready, nacc & 1);
                 ++nacc;
                 tc_fence_after();
-                if (col_owner) {
-#pragma unroll 1
-                    for (int cb = 0; cb < CPT; cb += 32) {
-                        float a[32], u[32];
-                        tc_ld32(tmem + lane_addr + (col0 + cb), a);
-                        tc_ld32(tmem + lane_addr + H + (col0 + cb), u);
-                        const float* bi = sBias + (layer * 2 + 0) * H + col0 + cb;
-                        const float* bc = sBias + (layer * 2 + 1) * H + col0 + cb;
-                        uint16_t hi[32], lo[32];
+                trace_stamp(tr, ts++);
+                float a[CPT], u[CPT];
+                if constexpr (CPT == 32) {
+                    tc_ld32(tmem + lane_addr + col0, a);
+                    tc_ld32(tmem + lane_addr + H + col0, u);
+                } else {
+                    tc_ld8(tmem + lane_addr + col0, a);
+                    tc_ld8(tmem + lane_addr + H + col0, u);
+                }
+                const float4* bi4 = reinterpret_cast<const float4*>(sBias + (layer * 2 + 0) * H + col0);
+                const float4* bc4 = reinterpret_cast<const float4*>(sBias + (layer * 2 + 1) * H + col0);
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float av = a[j] + bi[j];
-                            const float yv = act_fast<C::RELU>(av) + (u[j] + bc[j]);
-                            if (act_tile0 != nullptr) {
-                                const int n = col0 + cb + j;
-                                act_tile0[(int64_t)(2 * layer) * H * 64 + n * 64] = av;
-                                act_tile0[(int64_t)(2 * layer + 1) * H * 64 + n * 64] = yv;
-                            }
-                            if (ag != nullptr) ag[(layer * H + col0 + cb + j) * TILE + row] = av;
-                            split16(yv, hi[j], lo[j]);
-                        }
-                        const int colabs = col0 + cb;              // first hidden column of this block
-                        const int slab = colabs / 64, cc = colabs % 64;
+                for (int q = 0; q < CPT / 8; ++q) {
+                    const float4 b0 = bi4[2 * q], b1 = bi4[2 * q + 1], c0 = bc4[2 * q], c1 = bc4[2 * q + 1];
+                    const float bi[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    const float bc[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+                    float yv[8];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const uint4 vh = make_uint4(hi[q * 8 + 0] | (hi[q * 8 + 1] << 16), hi[q * 8 + 2] | (hi[q * 8 + 3] << 16),
-                                                        hi[q * 8 + 4] | (hi[q * 8 + 5] << 16), hi[q * 8 + 6] | (hi[q * 8 + 7] << 16));
-                            const uint4 vl = make_uint4(lo[q * 8 + 0] | (lo[q * 8 + 1] << 16), lo[q * 8 + 2] | (lo[q * 8 + 3] << 16),
-                                                        lo[q * 8 + 4] | (lo[q * 8 + 5] << 16), lo[q * 8 + 6] | (lo[q * 8 + 7] << 16));
-                            const uint32_t so = slab_off(row, (cc >> 3) + q);
-                            const uint32_t off = slab * SLAB + so;
-                            *reinterpret_cast<uint4*>(sAhi + off) = vh;
-                            *reinterpret_cast<uint4*>(sAlo + off) = vl;
-                            if (xg) {
-                                *reinterpret_cast<uint4*>(xg + W::x_y(layer, 0, slab) * SLAB + so) = vh;
-                                *reinterpret_cast<uint4*>(xg + W::x_y(layer, 1, slab) * SLAB + so) = vl;
-                            }
+                    for (int j = 0; j < 8; ++j) {
+                        const float av = a[q * 8 + j] + bi[j];
+                        yv[j] = act_fast<C::RELU>(av) + (u[q * 8 + j] + bc[j]);
+                        const int n = col0 + q * 8 + j;
+                        if (DUMP == 1 && act_tile0 != nullptr) {
+                            act_tile0[(int64_t)(2 * layer) * H * 64 + n * 64] = av;
+                            act_tile0[(int64_t)(2 * layer + 1) * H * 64 + n * 64] = yv[j];
                         }
+                        if (DUMP == 2) ag[(layer * H + n) * TILE + row] = av;
+                    }
+                    uint4 vh, vl;
+                    split8(yv, vh, vl);
+                    const int colabs = col0 + q * 8;
+                    const int slab = colabs >> 6;
+                    const uint32_t so = slab_off(row, (colabs & 63) >> 3);
+                    *reinterpret_cast<uint4*>(sAhi + slab * SLAB + so) = vh;
+                    *reinterpret_cast<uint4*>(sAlo + slab * SLAB + so) = vl;
+                    if (DUMP == 2) {
+                        *reinterpret_cast<uint4*>(xg + W::x_y(layer, 0, slab) * SLAB + so) = vh;
+                        *reinterpret_cast<uint4*>(xg + W::x_y(layer, 1, slab) * SLAB + so) = vl;
                     }
                 }
                 tc_fence_before();
                 fence_proxy_async();
                 mbar_arrive(a_ready);
+                trace_stamp(tr, ts++);
             }
             // ---- output layer result ----
             mbar_wait(acc_ready, nacc & 1);
             ++nacc;
             tc_fence_after();
+            trace_stamp(tr, ts++);
             if (cgp == 0) {
-                float o[32];
-                tc_ld32(tmem + lane_addr + 2 * H, o);
-                if (ws) {
+                float o[8];
+                tc_ld8(tmem + lane_addr + 2 * H, o);
+                if (DUMP == 2) {
                     float* rg = W::raw_ptr(ws, tile) + row * 4;
 #pragma unroll
-                    for (int q = 0; q < NOUT; ++q) rg[q] = o[q] + __ldg(prm.v[iBo] + q);
+                    for (int q = 0; q < NOUT; ++q) rg[q] = o[q] + sBo[q];
                 }
                 if (live) {
                     if (NOUT == 1) {
-                        out[pt] = o[0] + __ldg(prm.v[iBo]);
+                        out[pt] = o[0] + sBo[0];
                     } else {
-                        float r[3] = {o[0] + __ldg(prm.v[iBo] + 0), o[1] + __ldg(prm.v[iBo] + 1), o[2] + __ldg(prm.v[iBo] + 2)};
+                        float r[3] = {o[0] + sBo[0], o[1] + sBo[1], o[2] + sBo[2]};
                         if (affine != nullptr) {
                             float q[3];
 #pragma unroll
                             for (int cc = 0; cc < 3; ++cc) {
-                                const float lin = r[0] * __ldg(affine + cc) + r[1] * __ldg(affine + 3 + cc) +
-                                                  r[2] * __ldg(affine + 6 + cc) + __ldg(affine + 9 + cc);
+                                const float lin = r[0] * sAff[cc] + r[1] * sAff[3 + cc] + r[2] * sAff[6 + cc] + sAff[9 + cc];
                                 q[cc] = 1.0f / (1.0f + expf(-lin));
                             }
                             r[0] = q[0]; r[1] = q[1]; r[2] = q[2];
@@ -442,6 +451,7 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
                 }
             }
             tc_fence_before();
+            trace_stamp(tr, ts++);
         }
     }
     // ---- teardown ----
@@ -467,19 +477,28 @@ int launch_fwd(const float* const* params, const void* img, const float* p, cons
     const int smem = Geo<KIND>::SMEM_BYTES;
     static bool configured = false;
     if (!configured) {
-        HPS_CUDA_OK(cudaFuncSetAttribute(mlp_fwd_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        HPS_CUDA_OK(cudaFuncSetAttribute(mlp_fwd_tc_kernel<KIND, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        HPS_CUDA_OK(cudaFuncSetAttribute(mlp_fwd_tc_kernel<KIND, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        HPS_CUDA_OK(cudaFuncSetAttribute(mlp_fwd_tc_kernel<KIND, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
     const int num_tiles = (int)ceil_div(P, TILE);
-    int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
-    if (const char* e = getenv("HPS_TC_GRID")) grid = atoi(e) < grid ? atoi(e) : grid;   // debug aid
-    mlp_fwd_tc_kernel<KIND><<<grid, NTHR, smem, s>>>(prm, reinterpret_cast<const uint8_t*>(img), p, c, affine, P,
-                                                     num_tiles, out, act, reinterpret_cast<uint8_t*>(ws));
+    const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+    auto kern = ws ? mlp_fwd_tc_kernel<KIND, 2> : (act ? mlp_fwd_tc_kernel<KIND, 1> : mlp_fwd_tc_kernel<KIND, 0>);
+    kern<<<grid, NTHR, smem, s>>>(prm, reinterpret_cast<const uint8_t*>(img), p, c, affine, P, num_tiles, out, act,
+                                  reinterpret_cast<uint8_t*>(ws));
     return 0;
 }
 
 }  // namespace tc
 }  // namespace hps
+
+extern "C" int hps_tc_trace(void* buf) {
+    using namespace hps;
+    int rc = tc::set_trace_fwd(buf);
+    if (rc) return rc;
+    return tc::set_trace_bwd(buf);
+}
 
 extern "C" int64_t hps_mlp_tc_ws_bytes(int kind, int64_t P) {
     using namespace hps::tc;

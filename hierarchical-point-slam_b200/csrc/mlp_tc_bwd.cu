@@ -19,6 +19,12 @@
 namespace hps {
 namespace tc {
 
+static __device__ unsigned long long* g_trace_bwd = nullptr;
+int set_trace_bwd(void* buf) {
+    HPS_CUDA_OK(cudaMemcpyToSymbol(g_trace_bwd, &buf, sizeof(buf)));
+    return 0;
+}
+
 constexpr int NSTB = 5;   // ring stages of the dgrad kernel
 
 struct GradPtrs {
@@ -226,12 +232,15 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
         const uint32_t aW = smem_u32(sW);
         constexpr int NK = G::ksteps(G::HCOLS);
         uint32_t it = 0, nready = 0;
+        unsigned long long* tr = (blockIdx.x == 0 && lane == 0) ? g_trace_bwd : nullptr;
+        int ts = 192;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 #pragma unroll 1
             for (int layer = 4; layer >= 0; --layer) {
                 mbar_wait(a_ready, nready & 1);
                 ++nready;
                 tc_fence_after();
+                trace_stamp(tr, ts++);
                 if (want_w) {
                     // bias gradients on the tensor pipe: colsum(da_i), colsum(dy_i) = ones^T . da_i / dy_i, contracted
                     // over the 128 points with MN-major operands (every TMEM lane ends up with the same sums)
@@ -325,6 +334,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 }
                 if (elect_one()) tc_commit(acc_ready);
                 __syncwarp();
+                trace_stamp(tr, ts++);
             }
         }
     } else {
@@ -342,7 +352,10 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
         const int ecol0 = cgp * ECPT;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         uint32_t nacc = 0;
+        unsigned long long* tr = (blockIdx.x == 0 && ew == 0 && lane == 0) ? g_trace_bwd : nullptr;
+        int ts = 128;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            trace_stamp(tr, ts++);
             const int64_t pt = (int64_t)tile * TILE + row;
             const bool live = pt < P;
             uint8_t* xg = W::x_ptr(ws, tile);
@@ -420,6 +433,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                     for (int k = 0; k < 3; ++k)
                         dr[k] = dl[0] * __ldg(affine + 3 * k) + dl[1] * __ldg(affine + 3 * k + 1) + dl[2] * __ldg(affine + 3 * k + 2);
                 }
+                trace_stamp(tr, ts++);   // P1: d raw known
                 if (want_w && cgp == 0) {
 #pragma unroll
                     for (int o = 0; o < NOUT; ++o) {
@@ -428,6 +442,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                         if (lane == 0) red_add(grd.v[iBo] + o, s);
                     }
                 }
+                trace_stamp(tr, ts++);   // P2: dbo / daffine reduced
                 if (col_owner) {
                     {
                         const int c0 = col0;
@@ -439,6 +454,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                             for (int o = 0; o < NOUT; ++o) s = fmaf(dr[o], __ldg(prm.v[iWo] + o * H + c0 + j), s);
                             dy[j] = s * gS;      // the chain below runs on scaled gradients
                         }
+                        trace_stamp(tr, ts++);   // P3: dy_4
                         if (want_w) {   // dWo[o][h] += sum_pt d raw[pt][o] * y_4[pt][h]
                             float y4[32];
                             const int slab = c0 / 64, cc = c0 % 64;
@@ -465,12 +481,14 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                                 red_add(grd.v[iWo] + o * H + c0 + lane, s);
                             }
                         }
+                        trace_stamp(tr, ts++);   // P4: dWo
                         emit(4, a4, dy);
                     }
                 }
             }
             fence_proxy_async();
             mbar_arrive(a_ready);
+            trace_stamp(tr, ts++);
 
 #pragma unroll 1
             for (int layer = 4; layer >= 0; --layer) {
@@ -479,6 +497,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 mbar_wait(acc_ready, nacc & 1);
                 ++nacc;
                 tc_fence_after();
+                trace_stamp(tr, ts++);
                 if (want_w && quad == 0 && col_owner) {   // bias gradients of this layer: row 0 of the column sums
 #pragma unroll 1
                     for (int which = 0; which < 2; ++which) {
@@ -492,14 +511,17 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                     }
                 }
                 if (layer >= 1) {
+                    trace_stamp(tr, ts++);   // E1: bias sums flushed
                     if (col_owner) {
                         float dy[32];
                         tc_ld32(tmem + lane_addr + B::T_H + col0, dy);
+                        trace_stamp(tr, ts++);   // E2: dy loaded from TMEM
                         emit(layer - 1, an, dy);
                     }
                     tc_fence_before();
                     fence_proxy_async();
                     mbar_arrive(a_ready);
+                    trace_stamp(tr, ts++);
                 }
             }
             // ---- dc ----
@@ -571,6 +593,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 }
             }
             tc_fence_before();     // the embedding-gradient reads above precede the next tile's MMAs
+            trace_stamp(tr, ts++);
         }
     }
     tc_fence_before();

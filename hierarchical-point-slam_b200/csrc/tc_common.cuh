@@ -40,7 +40,9 @@ template <int KIND> struct Geo {
     static constexpr int SLABS_PER_TILE = 5 + 2 * (ES + HS + HS + (HS + ES) + HS) + 1;
     // TMEM columns: a [0,H), u [H,2H), out [2H, 2H+16)
     static constexpr int TMEM_COLS = (2 * C::H + 16) <= 128 ? 128 : ((2 * C::H + 16) <= 256 ? 256 : 512);
-    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + (2 * AS + 1 + NST) * SLAB + 2 * 5 * C::H * 4 + 256;
+    // slabs + biases [5][2][H] + Fourier matrix [3][NF] + output bias / exposure affine + barriers
+    static constexpr int SMEM_BYTES = 1024 /*align slack*/ + (2 * AS + 1 + NST) * SLAB + 2 * 5 * C::H * 4 +
+                                      (3 * C::NF + 4 + 12 + 2) * 4 + 256;
 };
 
 __host__ __device__ constexpr int iW(int i) { return 1 + 4 * i; }
@@ -129,6 +131,16 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile(
@@ -169,6 +181,21 @@ __device__ __forceinline__ void split16(float x, uint16_t& hi, uint16_t& lo) {
     lo = __half_as_ushort(l);
 }
 
+// Eight values at once: two packed-conversion instructions per pair instead of four scalar conversions; the
+// halves are bit-identical to split16's.  vh / vl are one 16-byte slab chunk each.
+__device__ __forceinline__ void split8(const float (&x)[8], uint4& vh, uint4& vl) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const __half2 hh = __floats2half2_rn(x[2 * q], x[2 * q + 1]);
+        const float2 back = __half22float2(hh);
+        const __half2 ll = __floats2half2_rn(x[2 * q] - back.x, x[2 * q + 1] - back.y);
+        h[q] = *reinterpret_cast<const uint32_t*>(&hh);
+        l[q] = *reinterpret_cast<const uint32_t*>(&ll);
+    }
+    vh = make_uint4(h[0], h[1], h[2], h[3]);
+    vl = make_uint4(l[0], l[1], l[2], l[3]);
+}
 
 // ---------------------------------------------------------------------------------------------- workspace
 // Per 128-point tile, written by the forward when a tensor-core backward will follow:
@@ -233,6 +260,17 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
     const float keep = up ? t2[1] : t2[0], send = up ? t2[0] : t2[1];
     return keep + __shfl_xor_sync(kFull, send, 1);
 }
+
+// Diagnostic timeline (hps_tc_trace): CTA 0 stamps %globaltimer (ns) at phase boundaries into a caller buffer.
+__device__ __forceinline__ void trace_stamp(unsigned long long* tr, int slot) {
+    if (tr != nullptr) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        tr[slot] = t;
+    }
+}
+int set_trace_fwd(void* buf);
+int set_trace_bwd(void* buf);
 
 }  // namespace tc
 }  // namespace hps

@@ -118,6 +118,11 @@ int hps_mlp_tc_bwd(int kind, const float* const* params, const void* packed, voi
 /* Single-CTA tcgen05 self-test: D[128][N] = A . B^T with fp16 operands staged K-major (major = 0, source
  * [rows][K]) or MN-major (major = 1, source [K][rows]) - pins the shared-memory descriptor encodings.        */
 int hps_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_major, int b_major, void* stream);
+/* Diagnostics: install (buf != NULL) or remove (NULL) a device buffer of 256 uint64 in which CTA 0 of the
+ * tensor-core decoder kernels stamps %globaltimer (ns) at its phase boundaries: [0,64) forward epilogue warp,
+ * [64,128) forward MMA warp, [128,192) dgrad epilogue warp, [192,256) dgrad MMA warp (scripts/tc_trace.py).
+ * No counterpart in the reference. */
+int hps_tc_trace(void* buf);
 /* dparams: HOST array of HPS_MLP_NPARAM device pointers (entries or the array may be NULL = skip);
  * parameter gradients are ACCUMULATED (atomic adds).  dc (P,32) written.  dp (P,3) written if not
  * NULL.  daffine (12) accumulated if not NULL.                                                     */
