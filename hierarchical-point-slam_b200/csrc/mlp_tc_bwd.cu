@@ -37,11 +37,14 @@ template <int KIND> struct GeoB {
     static constexpr int HS = G::HS, ES = G::ES, H = C::H;
     static constexpr int SLABS_PER_TILE = 9 + 8 * HS;           // see pack_bwd_kernel
     static constexpr int NE = 64 * ES;                           // padded embedding width
-    // TMEM columns of the dgrad kernel: dx hidden, dx embedding, dc, colsum(da_i), colsum(dy_i)
-    static constexpr int T_H = 0, T_E = H, T_DC = H + NE, T_SB = H + NE + 32, T_SBC = H + NE + 32 + H;
-    static constexpr int TMEM_COLS = (T_SBC + H) <= 256 ? 256 : 512;
-    static_assert(T_SBC + H <= 512, "TMEM budget");
-    static constexpr int SMEM_BYTES = 1024 + (4 * HS + 1 + NSTB) * SLAB + 256;   // + one slab of ones
+    // TMEM columns of the dgrad kernel: dx hidden, dx embedding (layers 3 and 0 accumulate), dc
+    static constexpr int T_H = 0, T_E = H, T_DC = H + NE;
+    static constexpr int TMEM_COLS = 256;
+    static_assert(H + NE + 32 <= 256, "TMEM budget");
+    // small fp32 tables in shared memory: Wo [NOUT][H], exposure affine [12], Fourier matrix [3][NF]
+    static constexpr int TAB_FLOATS = C::NOUT * H + 12 + 3 * C::NF + 1;
+    static constexpr int SMEM_BYTES = 1024 + (4 * HS + NSTB) * SLAB + TAB_FLOATS * 4 + 256;
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     static constexpr int ECPT = NE / CG;                         // embedding columns per epilogue thread
 };
 
@@ -156,6 +159,16 @@ __host__ __device__ constexpr uint32_t instr_desc_mn(int M, int N) {   // both o
 }
 
 // ---------------------------------------------------------------------------------------------- dgrad
+__device__ __forceinline__ float ldg_pinned(const float* p) {   // a load the compiler may neither sink nor re-issue
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+
+// Data gradients of one decoder: the chain dy_4 -> da_4 -> dy_3 ... runs layer by layer on the tensor cores
+// (dx_i = da_i W_i, dc += dy_i Wc_i), the epilogue warps turn each dx into the next layer's operands and dump
+// them (fp16 hi/lo slab images) for the weight-gradient kernel.  Everything that is a sum over points - dW, dWc,
+// db, dbc, dWo - is left to mlp_wgrad_tc_kernel.
 template <int KIND>
 __global__ void __launch_bounds__(NTHR, 1)
 mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, uint8_t* __restrict__ ws,
@@ -166,16 +179,18 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
     using G = Geo<KIND>;
     using B = GeoB<KIND>;
     using W = Ws<KIND>;
-    constexpr int H = C::H, E = C::E, NF = C::NF, NOUT = C::NOUT, HS = G::HS, ES = G::ES, NE = B::NE;
+    constexpr int H = C::H, E = C::E, NF = C::NF, NOUT = C::NOUT, HS = G::HS, NE = B::NE;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sDYhi = smem;
     uint8_t* sDYlo = sDYhi + HS * SLAB;
     uint8_t* sDAhi = sDYlo + HS * SLAB;
     uint8_t* sDAlo = sDAhi + HS * SLAB;
-    uint8_t* sOnes = sDAlo + HS * SLAB;            // fp16 1.0 everywhere: A operand of the bias-gradient column sums
-    uint8_t* sW = sOnes + SLAB;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sW + NSTB * SLAB);
+    uint8_t* sW = sDAlo + HS * SLAB;
+    float* sWo = reinterpret_cast<float*>(sW + NSTB * SLAB);        // [NOUT][H]
+    float* sAff = sWo + NOUT * H;                                   // [12]
+    float* sB = sAff + 12;                                          // [3][NF]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 3 * NF + ((NOUT * H + 3 * NF) & 1));
     uint64_t* full = bars;
     uint64_t* empty = bars + NSTB;
     uint64_t* a_ready = bars + 2 * NSTB;
@@ -200,9 +215,10 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                      "r"((uint32_t)B::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
+    for (int i = threadIdx.x; i < NOUT * H; i += NTHR) sWo[i] = prm.v[iWo][i];
+    for (int i = threadIdx.x; i < 3 * NF; i += NTHR) sB[i] = prm.v[0][i];
+    if (threadIdx.x < 12 && affine != nullptr) sAff[threadIdx.x] = affine[threadIdx.x];
     for (int i = threadIdx.x; i < 4 * HS * SLAB / 16; i += NTHR) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-    for (int i = threadIdx.x; i < SLAB / 16; i += NTHR)
-        reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -226,7 +242,6 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
         constexpr uint32_t ID_H = instr_desc(FMT_F16, FMT_F16, TILE, H);
         constexpr uint32_t ID_E = instr_desc(FMT_F16, FMT_F16, TILE, NE);
         constexpr uint32_t ID_C = instr_desc(FMT_F16, FMT_F16, TILE, 32);
-        constexpr uint32_t ID_SUM = instr_desc_mn(TILE, H);
         const uint32_t t_h = tmem + B::T_H, t_e = tmem + B::T_E, t_dc = tmem + B::T_DC;
         const uint32_t aDYh = smem_u32(sDYhi), aDYl = smem_u32(sDYlo), aDAh = smem_u32(sDAhi), aDAl = smem_u32(sDAlo);
         const uint32_t aW = smem_u32(sW);
@@ -241,22 +256,6 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 ++nready;
                 tc_fence_after();
                 trace_stamp(tr, ts++);
-                if (want_w) {
-                    // bias gradients on the tensor pipe: colsum(da_i), colsum(dy_i) = ones^T . da_i / dy_i, contracted
-                    // over the 128 points with MN-major operands (every TMEM lane ends up with the same sums)
-                    if (elect_one()) {
-                        const uint32_t aOnes = smem_u32(sOnes);
-#pragma unroll 1
-                        for (int k = 0; k < TILE / 16; ++k) {
-                            const uint64_t on = smem_desc_mn(aOnes + k * 2048, 0);       // both 64-wide M atoms = the ones slab
-                            tc_mma(tmem + B::T_SB, on, smem_desc_mn(aDAh + k * 2048, SLAB), ID_SUM, k > 0 ? 1u : 0u);
-                            tc_mma(tmem + B::T_SB, on, smem_desc_mn(aDAl + k * 2048, SLAB), ID_SUM, 1u);
-                            tc_mma(tmem + B::T_SBC, on, smem_desc_mn(aDYh + k * 2048, SLAB), ID_SUM, k > 0 ? 1u : 0u);
-                            tc_mma(tmem + B::T_SBC, on, smem_desc_mn(aDYl + k * 2048, SLAB), ID_SUM, 1u);
-                        }
-                    }
-                    __syncwarp();
-                }
                 {   // dc += dy_i . Wc_i
                     const int st = it % NSTB;
                     mbar_wait(&full[st], (it / NSTB) & 1);
@@ -305,7 +304,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                         __syncwarp();
                     }
                 }
-                if (layer == 0 || layer == 3) {   // dx (embedding columns) = da_i . W_i[:, embedding]
+                if (layer == 0 || layer == 3) {   // dx (embedding columns) += da_i . W_i[:, embedding]
                     const int st_hi = it % NSTB;
                     mbar_wait(&full[st_hi], (it / NSTB) & 1);
                     ++it;
@@ -332,6 +331,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                     }
                     __syncwarp();
                 }
+                // all MMAs that read this layer's operands are tracked: the epilogue may overwrite them afterwards
                 if (elect_one()) tc_commit(acc_ready);
                 __syncwarp();
                 trace_stamp(tr, ts++);
@@ -343,12 +343,10 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
         const int quad = warp & 3;
         const int cgp = ew >> 2;
         const int row = quad * 32 + lane;
-        constexpr int CPT = (H >= 32 * CG) ? H / CG : 32;
-        static_assert(CPT == 32, "one 32-column block per epilogue thread");
-        const bool col_owner = (H >= 32 * CG) || (cgp == 0);
-        const int col0 = (H >= 32 * CG) ? cgp * CPT : 0;
-        constexpr int ECPT = B::ECPT;
-        constexpr int EB = ECPT < 32 ? ECPT : 32;       // embedding columns per TMEM load
+        constexpr int CPT = H / CG;               // hidden columns per thread: colour 32, geometry 8
+        static_assert(CPT == 32 || CPT == 8, "epilogue column split");
+        const int col0 = cgp * CPT;
+        constexpr int ECPT = B::ECPT;             // embedding columns per thread: colour 16, geometry 32
         const int ecol0 = cgp * ECPT;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         uint32_t nacc = 0;
@@ -358,29 +356,31 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
             trace_stamp(tr, ts++);
             const int64_t pt = (int64_t)tile * TILE + row;
             const bool live = pt < P;
-            uint8_t* xg = W::x_ptr(ws, tile);
             uint8_t* gg = W::g_ptr(ws, tile);
             const float* ag = W::a_ptr(ws, tile);
-            // pre-activations a_layer (this thread's row, its 32 hidden columns): issued before the wait on the
+
+            // pre-activations a_layer (this thread's row, its CPT hidden columns): issued before the wait on the
             // accumulator so that the HBM/L2 latency of the forward workspace hides behind the MMAs
-            auto load_a = [&](int layer, float (&av)[32]) {
+            auto load_a = [&](int layer, float (&av)[CPT]) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) av[j] = __ldg(ag + (layer * H + col0 + j) * TILE + row);
+                for (int j = 0; j < CPT; ++j) av[j] = ldg_pinned(ag + (layer * H + col0 + j) * TILE + row);
             };
-            // dy (this thread's 32 hidden columns) of layer `layer` -> da, next A operands, dumps for wgrad
-            auto emit = [&](int layer, const float (&av)[32], const float (&dy)[32]) {
-                const int slab = col0 / 64, cc = col0 % 64;
+            // dy (this thread's hidden columns) of layer `layer` -> da, next A operands, dumps for wgrad
+            auto emit = [&](int layer, const float (&av)[CPT], const float (&dy)[CPT]) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint16_t yh[8], yl[8], ah[8], al[8];
+                for (int q = 0; q < CPT / 8; ++q) {
+                    float d8[8], a8[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const float d = dy[q * 8 + j];
-                        split16(d, yh[j], yl[j]);
-                        split16(d * act_grad<C::RELU>(av[q * 8 + j]), ah[j], al[j]);
+                        d8[j] = dy[q * 8 + j];
+                        a8[j] = d8[j] * act_grad<C::RELU>(av[q * 8 + j]);
                     }
-                    const uint32_t so = slab_off(row, (cc >> 3) + q);
-                    const uint4 v0 = pack8(yh), v1 = pack8(yl), v2 = pack8(ah), v3 = pack8(al);
+                    uint4 v0, v1, v2, v3;
+                    split8(d8, v0, v1);
+                    split8(a8, v2, v3);
+                    const int colabs = col0 + q * 8;
+                    const int slab = colabs >> 6;
+                    const uint32_t so = slab_off(row, (colabs & 63) >> 3);
                     *reinterpret_cast<uint4*>(sDYhi + slab * SLAB + so) = v0;
                     *reinterpret_cast<uint4*>(sDYlo + slab * SLAB + so) = v1;
                     *reinterpret_cast<uint4*>(sDAhi + slab * SLAB + so) = v2;
@@ -394,23 +394,22 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 }
             };
 
-            // ---- output layer (SIMT): d raw, dWo, dbo, daffine, dy_4 ----
+            // ---- output layer (SIMT): d raw, dbo, daffine, dy_4 ----
             {
-                float a4[32];
-                if (col_owner) load_a(4, a4);
+                float a4[CPT];
+                load_a(4, a4);
                 float dr[3] = {0.f, 0.f, 0.f};
                 if (live) {
 #pragma unroll
                     for (int o = 0; o < NOUT; ++o) dr[o] = __ldg(dout + pt * NOUT + o);
                 }
                 if (NOUT == 3 && affine != nullptr) {
-                    const float* rg = W::raw_ptr(ws, tile) + row * 4;
-                    const float r[3] = {rg[0], rg[1], rg[2]};
+                    const float4 r4 = *reinterpret_cast<const float4*>(W::raw_ptr(ws, tile) + row * 4);
+                    const float r[3] = {r4.x, r4.y, r4.z};
                     float dl[3];
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) {
-                        const float lin = r[0] * __ldg(affine + cc) + r[1] * __ldg(affine + 3 + cc) +
-                                          r[2] * __ldg(affine + 6 + cc) + __ldg(affine + 9 + cc);
+                        const float lin = r[0] * sAff[cc] + r[1] * sAff[3 + cc] + r[2] * sAff[6 + cc] + sAff[9 + cc];
                         const float s = 1.0f / (1.0f + expf(-lin));
                         dl[cc] = dr[cc] * s * (1.0f - s);
                     }
@@ -431,7 +430,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                     }
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
-                        dr[k] = dl[0] * __ldg(affine + 3 * k) + dl[1] * __ldg(affine + 3 * k + 1) + dl[2] * __ldg(affine + 3 * k + 2);
+                        dr[k] = dl[0] * sAff[3 * k] + dl[1] * sAff[3 * k + 1] + dl[2] * sAff[3 * k + 2];
                 }
                 trace_stamp(tr, ts++);   // P1: d raw known
                 if (want_w && cgp == 0) {
@@ -441,131 +440,88 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                         for (int q = 16; q; q >>= 1) s += __shfl_xor_sync(kFull, s, q);
                         if (lane == 0) red_add(grd.v[iBo] + o, s);
                     }
+                    // d raw (scaled) as an operand of the weight-gradient kernel: dWo = y_4^T d raw
+                    const float d8[8] = {dr[0] * gS, dr[1] * gS, dr[2] * gS, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    uint4 vh, vl;
+                    split8(d8, vh, vl);
+                    *reinterpret_cast<uint4*>(gg + W::g_dr(0) * SLAB + slab_off(row, 0)) = vh;
+                    *reinterpret_cast<uint4*>(gg + W::g_dr(1) * SLAB + slab_off(row, 0)) = vl;
                 }
-                trace_stamp(tr, ts++);   // P2: dbo / daffine reduced
-                if (col_owner) {
-                    {
-                        const int c0 = col0;
-                        float dy[32];
+                float dy[CPT];
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float s = 0.f;
+                for (int j = 0; j < CPT; ++j) {
+                    float s = 0.f;
 #pragma unroll
-                            for (int o = 0; o < NOUT; ++o) s = fmaf(dr[o], __ldg(prm.v[iWo] + o * H + c0 + j), s);
-                            dy[j] = s * gS;      // the chain below runs on scaled gradients
-                        }
-                        trace_stamp(tr, ts++);   // P3: dy_4
-                        if (want_w) {   // dWo[o][h] += sum_pt d raw[pt][o] * y_4[pt][h]
-                            float y4[32];
-                            const int slab = c0 / 64, cc = c0 % 64;
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const uint32_t so = slab_off(row, (cc >> 3) + q);
-                                const uint4 vh = *reinterpret_cast<const uint4*>(xg + W::x_y(4, 0, slab) * SLAB + so);
-                                const uint4 vl = *reinterpret_cast<const uint4*>(xg + W::x_y(4, 1, slab) * SLAB + so);
-                                const __half2* hh = reinterpret_cast<const __half2*>(&vh);
-                                const __half2* hl = reinterpret_cast<const __half2*>(&vl);
-#pragma unroll
-                                for (int e2 = 0; e2 < 4; ++e2) {
-                                    const float2 a2 = __half22float2(hh[e2]), b2 = __half22float2(hl[e2]);
-                                    y4[q * 8 + e2 * 2] = a2.x + b2.x;
-                                    y4[q * 8 + e2 * 2 + 1] = a2.y + b2.y;
-                                }
-                            }
-#pragma unroll
-                            for (int o = 0; o < NOUT; ++o) {
-                                float pr[32];
-#pragma unroll
-                                for (int j = 0; j < 32; ++j) pr[j] = dr[o] * y4[j];
-                                const float s = warp_colsum32(pr, lane);
-                                red_add(grd.v[iWo] + o * H + c0 + lane, s);
-                            }
-                        }
-                        trace_stamp(tr, ts++);   // P4: dWo
-                        emit(4, a4, dy);
-                    }
+                    for (int o = 0; o < NOUT; ++o) s = fmaf(dr[o], sWo[o * H + col0 + j], s);
+                    dy[j] = s * gS;      // the chain below runs on scaled gradients
                 }
+                trace_stamp(tr, ts++);   // P2: dy_4
+                emit(4, a4, dy);
             }
             fence_proxy_async();
             mbar_arrive(a_ready);
             trace_stamp(tr, ts++);
 
 #pragma unroll 1
-            for (int layer = 4; layer >= 0; --layer) {
-                float an[32];
-                if (layer >= 1 && col_owner) load_a(layer - 1, an);
+            for (int layer = 4; layer >= 1; --layer) {
+                float an[CPT];
+                load_a(layer - 1, an);
                 mbar_wait(acc_ready, nacc & 1);
                 ++nacc;
                 tc_fence_after();
                 trace_stamp(tr, ts++);
-                if (want_w && quad == 0 && col_owner) {   // bias gradients of this layer: row 0 of the column sums
-#pragma unroll 1
-                    for (int which = 0; which < 2; ++which) {
-                        float sb[32];
-                        tc_ld32(tmem + (which ? B::T_SBC : B::T_SB) + col0, sb);
-                        float* dst = (which ? grd.v[iBc(layer)] : grd.v[iB(layer)]) + col0;
-                        if (lane == 0) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) red_add(dst + j, sb[j] * gInv);
-                        }
-                    }
-                }
-                if (layer >= 1) {
-                    trace_stamp(tr, ts++);   // E1: bias sums flushed
-                    if (col_owner) {
-                        float dy[32];
-                        tc_ld32(tmem + lane_addr + B::T_H + col0, dy);
-                        trace_stamp(tr, ts++);   // E2: dy loaded from TMEM
-                        emit(layer - 1, an, dy);
-                    }
-                    tc_fence_before();
-                    fence_proxy_async();
-                    mbar_arrive(a_ready);
-                    trace_stamp(tr, ts++);
-                }
+                float dy[CPT];
+                if constexpr (CPT == 32) tc_ld32(tmem + lane_addr + B::T_H + col0, dy);
+                else tc_ld8(tmem + lane_addr + B::T_H + col0, dy);
+                emit(layer - 1, an, dy);
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive(a_ready);
+                trace_stamp(tr, ts++);
             }
-            // ---- dc ----
-            if (cgp == 0) {
-                float v[32];
-                tc_ld32(tmem + lane_addr + B::T_DC, v);
-                if (live) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        *reinterpret_cast<float4*>(dc + pt * kC + q * 4) =
-                            make_float4(v[q * 4] * gInv, v[q * 4 + 1] * gInv, v[q * 4 + 2] * gInv, v[q * 4 + 3] * gInv);
-                }
-            }
-            tc_fence_before();
-            // ---- dE -> dp, dB ----
+            // ---- end of the chain: dc and the embedding gradient ----
+            float x0 = 0.f, x1 = 0.f, x2 = 0.f;
             const bool want_b = (KIND == HPS_MLP_GEO) && grd.v[0] != nullptr;
-            if (dp != nullptr || want_b) {
-                float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+            if ((dp != nullptr || want_b) && live) {
+                x0 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 0));
+                x1 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 1));
+                x2 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 2));
+            }
+            mbar_wait(acc_ready, nacc & 1);
+            ++nacc;
+            tc_fence_after();
+            trace_stamp(tr, ts++);
+            {
+                float v[8];
+                tc_ld8(tmem + lane_addr + B::T_DC + cgp * 8, v);
                 if (live) {
-                    x0 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 0));
-                    x1 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 1));
-                    x2 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 2));
+                    *reinterpret_cast<float4*>(dc + pt * kC + cgp * 8) = make_float4(v[0] * gInv, v[1] * gInv, v[2] * gInv, v[3] * gInv);
+                    *reinterpret_cast<float4*>(dc + pt * kC + cgp * 8 + 4) = make_float4(v[4] * gInv, v[5] * gInv, v[6] * gInv, v[7] * gInv);
                 }
+            }
+            // ---- dE -> dp, dB ----
+            if (dp != nullptr || want_b) {
                 float g0 = 0.f, g1 = 0.f, g2 = 0.f;
 #pragma unroll 1
-                for (int eb = 0; eb < ECPT; eb += EB) {
-                    float de[EB];       // d loss / d embedding (layers 3 and 0 summed in TMEM)
-                    if constexpr (EB == 32) tc_ld32(tmem + lane_addr + B::T_E + ecol0 + eb, de);
-                    else tc_ld16(tmem + lane_addr + B::T_E + ecol0 + eb, de);
-                    float gb0[EB], gb1[EB], gb2[EB];
+                for (int eb = 0; eb < ECPT; eb += 8) {
+                    const int e0 = ecol0 + eb;               // warp-uniform
+                    if (e0 >= E) break;
+                    float de[8];       // d loss / d embedding (layers 3 and 0 summed in TMEM)
+                    tc_ld8(tmem + lane_addr + B::T_E + e0, de);
+                    float gb0[8], gb1[8], gb2[8];
 #pragma unroll
-                    for (int j = 0; j < EB; ++j) {
-                        const int e = ecol0 + eb + j;
-                        float g = 0.f;
-                        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-                        if (e < E && live) {
-                            const int f = C::CONCAT ? (e < NF ? e : e - NF) : e;
-                            b0 = __ldg(prm.v[0] + f);
-                            b1 = __ldg(prm.v[0] + NF + f);
-                            b2 = __ldg(prm.v[0] + 2 * NF + f);
+                    for (int j = 0; j < 8; ++j) {
+                        const int e = e0 + j;
+                        float g = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+                        if (e < E) {
+                            const bool is_cos = C::CONCAT && e >= NF;
+                            const int f = is_cos ? e - NF : e;
+                            b0 = sB[f];
+                            b1 = sB[NF + f];
+                            b2 = sB[2 * NF + f];
                             const float arg = fmaf(x2, b2, fmaf(x1, b1, x0 * b0));
-                            float s, co;
-                            sincosf(arg, &s, &co);
-                            g = ((C::CONCAT && e >= NF) ? -de[j] * s : de[j] * co) * gInv;
+                            // d sin = cos, d cos = -sin
+                            g = live ? (is_cos ? -de[j] * sinf(arg) : de[j] * cosf(arg)) * gInv : 0.f;
                         }
                         g0 = fmaf(g * kTwoPi, b0, g0);
                         g1 = fmaf(g * kTwoPi, b1, g1);
@@ -574,25 +530,23 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                         gb1[j] = g * x1;
                         gb2[j] = g * x2;
                     }
-                    if constexpr (EB == 32) {
-                        if (want_b) {   // dB[d][f] += sum_pt g * x'_d   (geometry decoder: e == f)
-                            const float s0 = warp_colsum32(gb0, lane), s1 = warp_colsum32(gb1, lane), s2 = warp_colsum32(gb2, lane);
-                            const int e = ecol0 + eb + lane;
-                            if (e < E) {
-                                red_add(grd.v[0] + e, s0);
-                                red_add(grd.v[0] + NF + e, s1);
-                                red_add(grd.v[0] + 2 * NF + e, s2);
-                            }
+                    if (want_b) {   // dB[d][f] += sum_pt g * x'_d   (geometry decoder: e == f)
+                        const float s0 = warp_colsum8(gb0, lane), s1 = warp_colsum8(gb1, lane), s2 = warp_colsum8(gb2, lane);
+                        const int e = e0 + colsum8_col(lane);
+                        if (lane < 8 && e < E) {
+                            red_add(grd.v[0] + e, s0);
+                            red_add(grd.v[0] + NF + e, s1);
+                            red_add(grd.v[0] + 2 * NF + e, s2);
                         }
                     }
                 }
-                if (dp != nullptr && live) {   // dp is zero-initialised by the caller; both column halves add
+                if (dp != nullptr && live) {   // dp is zero-initialised by the caller; the column groups add
                     red_add(dp + pt * 3 + 0, g0);
                     red_add(dp + pt * 3 + 1, g1);
                     red_add(dp + pt * 3 + 2, g2);
                 }
             }
-            tc_fence_before();     // the embedding-gradient reads above precede the next tile's MMAs
+            tc_fence_before();     // the TMEM reads above precede the next tile's MMAs
             trace_stamp(tr, ts++);
         }
     }
@@ -608,47 +562,56 @@ template <int KIND> struct GeoW {
     using C = Cfg<KIND>;
     using G = Geo<KIND>;
     static constexpr int HS = G::HS, ES = G::ES, H = C::H, NE = 64 * ES, NH = 64 * HS;
-    // One pipeline stage = a quarter tile (32 points = two K=16 steps) of every operand of one layer, as 4 KB
+    // One pipeline stage = a quarter tile (32 points = two K=16 steps) of every operand of one role, as 4 KB
     // chunks (32 rows x 128 B of a swizzled slab; the swizzle period is 8 rows, so a chunk is itself a valid
-    // SWIZZLE_128B MN-major operand with atom stride CH):
+    // SWIZZLE_128B MN-major operand with atom stride CH).  Roles 0..4 (layer i):
     //   A chunks: dy_hi[HS] dy_lo[HS] da_hi[HS] da_lo[HS]        (same order as the G region of the workspace)
     //   B chunks: y_hi[HS] e_hi[ES] y_lo[HS] e_lo[ES] c[1]        (so [y | e] is one N = NH+NE operand)
+    // Role 5 (output layer): A chunks y4_hi[HS] y4_lo[HS], B chunks draw_hi draw_lo.
     static constexpr int CH = 4096;
     static constexpr int A_CHUNKS = 4 * HS, B_CHUNKS = 2 * (HS + ES) + 1;
     static constexpr int STAGE_BYTES = (A_CHUNKS + B_CHUNKS) * CH;
     static constexpr int NSTW = 3;
-    static constexpr int SMEM_BYTES = 1024 + NSTW * STAGE_BYTES + CH + 256;   // + CH: M=128 reads one atom past da_lo
-    // TMEM columns: dW hidden [0,NH), dW embedding [NH,NH+NE), dWc as [sum dy*c_hi | sum dy*c_lo] [NH+NE, +64)
-    static constexpr int T_WH = 0, T_WE = NH, T_WC = NH + NE;
-    static constexpr int TMEM_COLS = 256;
-    static_assert(NH + NE + 64 <= 256, "TMEM budget");
+    static constexpr int NROLE = 6;
+    // + CH: M=128 reads one atom past the last A chunk; + CH: the chunk of ones (bias-gradient column sums)
+    static constexpr int SMEM_BYTES = 1024 + NSTW * STAGE_BYTES + 2 * CH + 256;
+    // TMEM columns: dW hidden [0,NH), dW embedding [NH,NH+NE), dWc as [sum dy*c_hi | sum dy*c_lo] [NH+NE, +64),
+    // db (16 equal columns), dbc (16 equal columns); role 5: dWo^T in columns [0,16)
+    static constexpr int T_WH = 0, T_WE = NH, T_WC = NH + NE, T_B = NH + NE + 64, T_BC = NH + NE + 80;
+    static constexpr int TMEM_COLS = 512;
+    static_assert(NH + NE + 96 <= 512, "TMEM budget");
     static constexpr int NTHRW = 320;      // producer warp, MMA warp, 8 flush warps
 };
 
-// Weight gradients.  CTA b works on layer b % 5 for every (b / 5)-th tile: it streams that layer's dgrad dumps
-// (da_i, dy_i) and the forward's operand dumps (y_{i-1}, embedding, c) through a 3-stage quarter-tile ring and
-// accumulates  dW_i = da_i^T [y_{i-1} | e]  and  dWc_i = dy_i^T c  over all its tiles in TMEM (contraction over
-// the points: both operands MN-major), then adds its partial sums to the gradient buffers (red.global.add,
-// 16-byte vectors where the row pitch allows).
+// Everything that is a sum over the points.  CTA b has role b % 6 and works on every (b / 6)-th tile: it streams
+// the dgrad dumps (da_i, dy_i, d raw) and the forward's operand dumps (y_i, embedding, c) through a 3-stage
+// quarter-tile ring and accumulates over all its tiles in TMEM (contraction over the points: both operands
+// MN-major)
+//     roles 0..4:  dW_i = da_i^T [y_{i-1} | e],  dWc_i = dy_i^T c,  db_i = da_i^T 1,  dbc_i = dy_i^T 1
+//     role 5:      dWo^T = y_4^T d raw
+// then adds its partial sums to the gradient buffers (red.global.add, 16-byte vectors where the pitch allows).
 template <int KIND>
 __global__ void __launch_bounds__(GeoW<KIND>::NTHRW, 1)
 mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles, const uint32_t* __restrict__ maxbits) {
     using C = Cfg<KIND>;
     using GW = GeoW<KIND>;
     using W = Ws<KIND>;
-    constexpr int H = C::H, E = C::E, HS = GW::HS, ES = GW::ES, NH = GW::NH, NE = GW::NE, CH = GW::CH, NSTW = GW::NSTW;
+    constexpr int H = C::H, E = C::E, NOUT = C::NOUT, HS = GW::HS, ES = GW::ES, NH = GW::NH, NE = GW::NE, CH = GW::CH,
+                  NSTW = GW::NSTW;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTW * GW::STAGE_BYTES + CH);
+    uint8_t* sOnes = smem + NSTW * GW::STAGE_BYTES + CH;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + CH);
     uint64_t* full = bars;
     uint64_t* empty = bars + NSTW;
     uint64_t* done = bars + 2 * NSTW;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTW + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int layer = blockIdx.x % 5;
-    const int rank = blockIdx.x / 5;
-    const int gsize = ((int)gridDim.x - layer + 4) / 5;     // CTAs working on this layer
-    const bool has_h = layer >= 1, has_e = (layer == 0 || layer == 3);
+    const int role = blockIdx.x % GW::NROLE;
+    const int layer = role;                                   // roles 0..4
+    const int rank = blockIdx.x / GW::NROLE;
+    const int gsize = ((int)gridDim.x - role + GW::NROLE - 1) / GW::NROLE;     // CTAs with this role
+    const bool has_h = role >= 1 && role < 5, has_e = (role == 0 || role == 3);
     const bool mine = rank < num_tiles;
 
     if (threadIdx.x == 0) {
@@ -664,9 +627,11 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
                      "r"((uint32_t)GW::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    // operands that a layer does not load (and the over-read atom) must still be finite: zero everything once
+    // operands that a role does not load (and the over-read atom) must still be finite: zero everything once
     for (int i = threadIdx.x; i < (NSTW * GW::STAGE_BYTES + CH) / 16; i += blockDim.x)
         reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < CH / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(sOnes)[i] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);   // fp16 1.0
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -675,11 +640,12 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
 
     if (warp == 0) {
         // ---- producer ----
-        const uint32_t bytes = (uint32_t)CH * (4 * HS + (has_h ? 2 * HS : 0) + (has_e ? 2 * ES : 0) + 1);
+        const uint32_t bytes = role == 5 ? (uint32_t)CH * (2 * HS + 2)
+                                         : (uint32_t)CH * (4 * HS + (has_h ? 2 * HS : 0) + (has_e ? 2 * ES : 0) + 1);
         uint32_t it = 0;
         for (int tile = rank; tile < num_tiles; tile += gsize) {
             const uint8_t* xg = W::x_ptr(const_cast<uint8_t*>(ws), tile);
-            const uint8_t* gg = W::g_ptr(const_cast<uint8_t*>(ws), tile) + (size_t)W::g_dy(layer, 0, 0) * SLAB;
+            const uint8_t* gt = W::g_ptr(const_cast<uint8_t*>(ws), tile);
             for (int q = 0; q < 4; ++q, ++it) {
                 const int st = it % NSTW;
                 if (it >= NSTW) mbar_wait(&empty[st], ((it / NSTW) - 1) & 1);
@@ -687,22 +653,30 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
                     uint8_t* sa = smem + st * GW::STAGE_BYTES;
                     uint8_t* sb = sa + GW::A_CHUNKS * CH;
                     mbar_expect_tx(&full[st], bytes);
-                    for (int j = 0; j < 4 * HS; ++j) bulk_g2s(sa + j * CH, gg + (size_t)j * SLAB + q * CH, CH, &full[st]);
-                    if (has_h) {
-                        for (int s2 = 0; s2 < HS; ++s2) {
-                            bulk_g2s(sb + s2 * CH, xg + (size_t)W::x_y(layer - 1, 0, s2) * SLAB + q * CH, CH, &full[st]);
-                            bulk_g2s(sb + (HS + ES + s2) * CH, xg + (size_t)W::x_y(layer - 1, 1, s2) * SLAB + q * CH, CH,
-                                     &full[st]);
+                    if (role == 5) {
+                        for (int j = 0; j < 2 * HS; ++j)      // y4 hi[HS], lo[HS] are consecutive X slabs
+                            bulk_g2s(sa + j * CH, xg + (size_t)(W::x_y(4, 0, 0) + j) * SLAB + q * CH, CH, &full[st]);
+                        bulk_g2s(sb, gt + (size_t)W::g_dr(0) * SLAB + q * CH, CH, &full[st]);
+                        bulk_g2s(sb + CH, gt + (size_t)W::g_dr(1) * SLAB + q * CH, CH, &full[st]);
+                    } else {
+                        const uint8_t* gg = gt + (size_t)W::g_dy(layer, 0, 0) * SLAB;
+                        for (int j = 0; j < 4 * HS; ++j) bulk_g2s(sa + j * CH, gg + (size_t)j * SLAB + q * CH, CH, &full[st]);
+                        if (has_h) {
+                            for (int s2 = 0; s2 < HS; ++s2) {
+                                bulk_g2s(sb + s2 * CH, xg + (size_t)W::x_y(layer - 1, 0, s2) * SLAB + q * CH, CH, &full[st]);
+                                bulk_g2s(sb + (HS + ES + s2) * CH, xg + (size_t)W::x_y(layer - 1, 1, s2) * SLAB + q * CH, CH,
+                                         &full[st]);
+                            }
                         }
-                    }
-                    if (has_e) {
-                        for (int s2 = 0; s2 < ES; ++s2) {
-                            bulk_g2s(sb + (HS + s2) * CH, xg + (size_t)W::x_e(0, s2) * SLAB + q * CH, CH, &full[st]);
-                            bulk_g2s(sb + (2 * HS + ES + s2) * CH, xg + (size_t)W::x_e(1, s2) * SLAB + q * CH, CH,
-                                     &full[st]);
+                        if (has_e) {
+                            for (int s2 = 0; s2 < ES; ++s2) {
+                                bulk_g2s(sb + (HS + s2) * CH, xg + (size_t)W::x_e(0, s2) * SLAB + q * CH, CH, &full[st]);
+                                bulk_g2s(sb + (2 * HS + ES + s2) * CH, xg + (size_t)W::x_e(1, s2) * SLAB + q * CH, CH,
+                                         &full[st]);
+                            }
                         }
+                        bulk_g2s(sb + 2 * (HS + ES) * CH, xg + (size_t)W::x_c() * SLAB + q * CH, CH, &full[st]);
                     }
-                    bulk_g2s(sb + 2 * (HS + ES) * CH, xg + (size_t)W::x_c() * SLAB + q * CH, CH, &full[st]);
                 }
                 __syncwarp();
             }
@@ -710,9 +684,12 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
     } else if (warp == 1) {
         // ---- MMA issue ----
         const int nW = (has_h ? NH : 0) + (has_e ? NE : 0);
-        const uint32_t id_w = instr_desc_mn(TILE, nW), id_c = instr_desc_mn(TILE, 64);
+        const uint32_t id_w = instr_desc_mn(TILE, nW > 0 ? nW : 16), id_c = instr_desc_mn(TILE, 64);
+        const uint32_t id_16 = instr_desc_mn(TILE, 16);
         const uint32_t t_w = tmem + (has_h ? GW::T_WH : GW::T_WE), t_c = tmem + GW::T_WC;
+        const uint32_t t_b = tmem + GW::T_B, t_bc = tmem + GW::T_BC;
         const uint32_t b_off = (uint32_t)(has_h ? 0 : HS) * CH;       // layer 0: B starts at the embedding chunks
+        const uint64_t ones = smem_desc_mn(smem_u32(sOnes), CH);
         uint32_t it = 0;
         for (int tile = rank; tile < num_tiles; tile += gsize) {
             for (int q = 0; q < 4; ++q, ++it) {
@@ -725,17 +702,29 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
-                        const uint64_t dyh = smem_desc_mn(sa + k * 2048, CH), dyl = smem_desc_mn(sa + HS * CH + k * 2048, CH);
-                        const uint64_t dah = smem_desc_mn(sa + 2 * HS * CH + k * 2048, CH);
-                        const uint64_t dal = smem_desc_mn(sa + 3 * HS * CH + k * 2048, CH);
-                        const uint64_t bh = smem_desc_mn(sb + b_off + k * 2048, CH);
-                        const uint64_t bl = smem_desc_mn(sb + (HS + ES) * CH + b_off + k * 2048, CH);
-                        const uint64_t bc = smem_desc_mn(sb + 2 * (HS + ES) * CH + k * 2048, CH);
-                        tc_mma(t_w, dah, bh, id_w, acc);
-                        tc_mma(t_w, dah, bl, id_w, 1u);
-                        tc_mma(t_w, dal, bh, id_w, 1u);
-                        tc_mma(t_c, dyh, bc, id_c, acc);      // c chunk = [c_hi | c_lo]: the halves are summed at flush
-                        tc_mma(t_c, dyl, bc, id_c, 1u);
+                        if (role == 5) {
+                            const uint64_t yh = smem_desc_mn(sa + k * 2048, CH), yl = smem_desc_mn(sa + HS * CH + k * 2048, CH);
+                            const uint64_t rh = smem_desc_mn(sb + k * 2048, CH), rl = smem_desc_mn(sb + CH + k * 2048, CH);
+                            tc_mma(tmem, yh, rh, id_16, acc);
+                            tc_mma(tmem, yh, rl, id_16, 1u);
+                            tc_mma(tmem, yl, rh, id_16, 1u);
+                        } else {
+                            const uint64_t dyh = smem_desc_mn(sa + k * 2048, CH), dyl = smem_desc_mn(sa + HS * CH + k * 2048, CH);
+                            const uint64_t dah = smem_desc_mn(sa + 2 * HS * CH + k * 2048, CH);
+                            const uint64_t dal = smem_desc_mn(sa + 3 * HS * CH + k * 2048, CH);
+                            const uint64_t bh = smem_desc_mn(sb + b_off + k * 2048, CH);
+                            const uint64_t bl = smem_desc_mn(sb + (HS + ES) * CH + b_off + k * 2048, CH);
+                            const uint64_t bc = smem_desc_mn(sb + 2 * (HS + ES) * CH + k * 2048, CH);
+                            tc_mma(t_w, dah, bh, id_w, acc);
+                            tc_mma(t_w, dah, bl, id_w, 1u);
+                            tc_mma(t_w, dal, bh, id_w, 1u);
+                            tc_mma(t_c, dyh, bc, id_c, acc);      // c chunk = [c_hi | c_lo]: the halves are summed at flush
+                            tc_mma(t_c, dyl, bc, id_c, 1u);
+                            tc_mma(t_b, dah, ones, id_16, acc);   // bias gradients: column sums over the points
+                            tc_mma(t_b, dal, ones, id_16, 1u);
+                            tc_mma(t_bc, dyh, ones, id_16, acc);
+                            tc_mma(t_bc, dyl, ones, id_16, 1u);
+                        }
                     }
                     tc_commit(&empty[st]);
                 }
@@ -754,45 +743,61 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
         const int h = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         const float gInv = 1.0f / grad_scale(maxbits);
-        const int K = layer == 0 ? E : (layer == 3 ? E + H : H);
-        float* gw = grd.v[iW(layer)];
-        float* gwc = grd.v[iWc(layer)];
-        const bool vec_w = ((reinterpret_cast<uintptr_t>(gw) & 15) == 0) && (K % 4 == 0) && (E % 4 == 0);
-        const bool vec_c = (reinterpret_cast<uintptr_t>(gwc) & 15) == 0;
-        auto flush16 = [&](float* dst, const float (&v)[16], int n_valid, bool vec) {     // dst: this row, 16 columns
-            if (vec && n_valid == 16) {
+        if (role == 5) {
+            if (half == 0) {
+                float v[8];
+                tc_ld8(tmem + lane_addr, v);
+                if (h < H) {
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    red_add_v4(dst + j, make_float4(v[j] * gInv, v[j + 1] * gInv, v[j + 2] * gInv, v[j + 3] * gInv));
-            } else {
+                    for (int o = 0; o < NOUT; ++o) red_add(grd.v[iWo] + o * H + h, v[o] * gInv);
+                }
+            }
+        } else {
+            const int K = layer == 0 ? E : (layer == 3 ? E + H : H);
+            float* gw = grd.v[iW(layer)];
+            float* gwc = grd.v[iWc(layer)];
+            const bool vec_w = ((reinterpret_cast<uintptr_t>(gw) & 15) == 0) && (K % 4 == 0) && (E % 4 == 0);
+            const bool vec_c = (reinterpret_cast<uintptr_t>(gwc) & 15) == 0;
+            auto flush16 = [&](float* dst, const float (&v)[16], int n_valid, bool vec) {     // dst: this row, 16 columns
+                if (vec && n_valid == 16) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if (j < n_valid) red_add(dst + j, v[j] * gInv);
-            }
-        };
-        if (has_h) {
-            for (int cb = half * (NH / 2); cb < (half + 1) * (NH / 2); cb += 16) {
-                float v[16];
-                tc_ld16(tmem + lane_addr + GW::T_WH + cb, v);
-                const int nv = H - cb < 16 ? H - cb : 16;
-                if (h < H && nv > 0) flush16(gw + (int64_t)h * K + (layer == 3 ? E : 0) + cb, v, nv, vec_w);
-            }
-        }
-        if (has_e) {
-            for (int cb = half * (NE / 2); cb < (half + 1) * (NE / 2); cb += 16) {
-                float v[16];
-                tc_ld16(tmem + lane_addr + GW::T_WE + cb, v);
-                const int nv = E - cb < 16 ? E - cb : 16;
-                if (h < H && nv > 0) flush16(gw + (int64_t)h * K + cb, v, nv, vec_w);
-            }
-        }
-        {
-            float v[16], v2[16];
-            tc_ld16(tmem + lane_addr + GW::T_WC + half * 16, v);
-            tc_ld16(tmem + lane_addr + GW::T_WC + 32 + half * 16, v2);
+                    for (int j = 0; j < 16; j += 4)
+                        red_add_v4(dst + j, make_float4(v[j] * gInv, v[j + 1] * gInv, v[j + 2] * gInv, v[j + 3] * gInv));
+                } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += v2[j];
-            if (h < H) flush16(gwc + (int64_t)h * kC + half * 16, v, 16, vec_c);
+                    for (int j = 0; j < 16; ++j)
+                        if (j < n_valid) red_add(dst + j, v[j] * gInv);
+                }
+            };
+            if (has_h) {
+                for (int cb = half * (NH / 2); cb < (half + 1) * (NH / 2); cb += 16) {
+                    float v[16];
+                    tc_ld16(tmem + lane_addr + GW::T_WH + cb, v);
+                    const int nv = H - cb < 16 ? H - cb : 16;
+                    if (h < H && nv > 0) flush16(gw + (int64_t)h * K + (layer == 3 ? E : 0) + cb, v, nv, vec_w);
+                }
+            }
+            if (has_e) {
+                for (int cb = half * (NE / 2); cb < (half + 1) * (NE / 2); cb += 16) {
+                    float v[16];
+                    tc_ld16(tmem + lane_addr + GW::T_WE + cb, v);
+                    const int nv = E - cb < 16 ? E - cb : 16;
+                    if (h < H && nv > 0) flush16(gw + (int64_t)h * K + cb, v, nv, vec_w);
+                }
+            }
+            {
+                float v[16], v2[16];
+                tc_ld16(tmem + lane_addr + GW::T_WC + half * 16, v);
+                tc_ld16(tmem + lane_addr + GW::T_WC + 32 + half * 16, v2);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += v2[j];
+                if (h < H) flush16(gwc + (int64_t)h * kC + half * 16, v, 16, vec_c);
+            }
+            {
+                float v[8];
+                tc_ld8(tmem + lane_addr + (half == 0 ? GW::T_B : GW::T_BC), v);
+                if (h < H) red_add((half == 0 ? grd.v[iB(layer)] : grd.v[iBc(layer)]) + h, v[0] * gInv);
+            }
         }
     }
     tc_fence_before();
@@ -843,7 +848,7 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
         prm, grd, reinterpret_cast<const uint8_t*>(img), reinterpret_cast<uint8_t*>(ws), p, affine, dout, P, num_tiles,
         dc, dp, daffine);
     if (dparams) {
-        const int wgrid = 5 * num_tiles < kNumSMs ? 5 * num_tiles : kNumSMs;     // >= 5: every layer has a CTA
+        const int wgrid = GeoW<KIND>::NROLE * num_tiles < kNumSMs ? GeoW<KIND>::NROLE * num_tiles : kNumSMs;   // every role has a CTA
         mlp_wgrad_tc_kernel<KIND><<<wgrid, GeoW<KIND>::NTHRW, GeoW<KIND>::SMEM_BYTES, s>>>(grd, reinterpret_cast<const uint8_t*>(ws),
                                                                             num_tiles, maxbits);
     }

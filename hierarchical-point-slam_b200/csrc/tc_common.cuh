@@ -209,7 +209,7 @@ template <int KIND> struct Ws {
     using G_ = Geo<KIND>;
     static constexpr int HS = G_::HS, ES = G_::ES, H = Cfg<KIND>::H;
     static constexpr int NX = 2 * ES + 1 + 10 * HS;
-    static constexpr int NG = 20 * HS;
+    static constexpr int NG = 20 * HS + 2;      // + d raw (hi, lo): columns 0..NOUT-1 of two slabs
     static constexpr size_t A_BYTES = (size_t)5 * H * TILE * 4;
     static constexpr size_t RAW_BYTES = (size_t)TILE * 4 * 4;
     static constexpr size_t X_BYTES = (size_t)NX * SLAB;
@@ -220,11 +220,37 @@ template <int KIND> struct Ws {
     __host__ __device__ static constexpr int x_y(int i, int lo, int s) { return 2 * ES + 1 + i * 2 * HS + lo * HS + s; }
     __host__ __device__ static constexpr int g_dy(int i, int lo, int s) { return i * 4 * HS + lo * HS + s; }
     __host__ __device__ static constexpr int g_da(int i, int lo, int s) { return i * 4 * HS + 2 * HS + lo * HS + s; }
+    __host__ __device__ static constexpr int g_dr(int lo) { return 20 * HS + lo; }
     __device__ static float* a_ptr(uint8_t* ws, int64_t tile) { return reinterpret_cast<float*>(ws + tile * TILE_BYTES); }
     __device__ static float* raw_ptr(uint8_t* ws, int64_t tile) { return reinterpret_cast<float*>(ws + tile * TILE_BYTES + A_BYTES); }
     __device__ static uint8_t* x_ptr(uint8_t* ws, int64_t tile) { return ws + tile * TILE_BYTES + A_BYTES + RAW_BYTES; }
     __device__ static uint8_t* g_ptr(uint8_t* ws, int64_t tile) { return ws + tile * TILE_BYTES + A_BYTES + RAW_BYTES + X_BYTES; }
 };
+
+// Sum over the 32 lanes of each of 8 per-lane values (9 shuffles).  Every lane returns the total of column
+// colsum8_col(lane).
+__device__ __forceinline__ int colsum8_col(int lane) { return ((lane >> 2) & 1) * 4 + ((lane >> 1) & 1) * 2 + (lane & 1); }
+__device__ __forceinline__ float warp_colsum8(const float (&v)[8], int lane) {
+    float t4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool up = lane & 4;
+        const float keep = up ? v[i + 4] : v[i], send = up ? v[i] : v[i + 4];
+        t4[i] = keep + __shfl_xor_sync(kFull, send, 4);
+    }
+    float t2[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool up = lane & 2;
+        const float keep = up ? t4[i + 2] : t4[i], send = up ? t4[i] : t4[i + 2];
+        t2[i] = keep + __shfl_xor_sync(kFull, send, 2);
+    }
+    const bool up = lane & 1;
+    float r = (up ? t2[1] : t2[0]) + __shfl_xor_sync(kFull, up ? t2[0] : t2[1], 1);
+    r += __shfl_xor_sync(kFull, r, 8);
+    r += __shfl_xor_sync(kFull, r, 16);
+    return r;
+}
 
 // lane j returns sum over the 32 lanes of v[j]  (31 shuffles: recursive halving)
 __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
