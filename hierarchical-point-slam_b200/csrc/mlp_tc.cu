@@ -139,7 +139,8 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
     uint64_t* empty = bars + NST;                  // [NST]
     uint64_t* a_ready = bars + 2 * NST;            // epilogue -> MMA: A operand in place, accumulators drained
     uint64_t* acc_ready = bars + 2 * NST + 1;      // MMA -> epilogue
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 2);
+    uint64_t* dump_done = bars + 2 * NST + 2;      // dump warp -> epilogue: operand slabs copied out, reusable
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NST + 3);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -151,6 +152,7 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
         }
         mbar_init(a_ready, NEPI);
         mbar_init(acc_ready, 1);
+        mbar_init(dump_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -287,9 +289,42 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
                 trace_stamp(tr, ts++);
             }
         }
+    } else if (warp == DUMP_WARP) {
+        // ================= dump warp (DUMP == 2): operand slabs -> workspace of the tensor-core backward ==============
+        if constexpr (DUMP == 2) {
+            uint32_t nready = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                uint8_t* xg = W::x_ptr(ws, tile);
+#pragma unroll 1
+                for (int step = 0; step < 6; ++step) {     // 0: embedding + c, 1..5: y_0 .. y_4
+                    mbar_wait(a_ready, nready & 1);
+                    ++nready;
+                    if (elect_one()) {
+                        if (step == 0) {
+                            for (int s2 = 0; s2 < ES; ++s2) {
+                                bulk_s2g(xg + (size_t)W::x_e(0, s2) * SLAB, sAhi + (HS + s2) * SLAB, SLAB);
+                                bulk_s2g(xg + (size_t)W::x_e(1, s2) * SLAB, sAlo + (HS + s2) * SLAB, SLAB);
+                            }
+                            bulk_s2g(xg + (size_t)W::x_c() * SLAB, sC, SLAB);
+                        } else {
+                            for (int s2 = 0; s2 < HS; ++s2) {
+                                bulk_s2g(xg + (size_t)W::x_y(step - 1, 0, s2) * SLAB, sAhi + s2 * SLAB, SLAB);
+                                bulk_s2g(xg + (size_t)W::x_y(step - 1, 1, s2) * SLAB, sAlo + s2 * SLAB, SLAB);
+                            }
+                        }
+                        bulk_commit();
+                        bulk_wait_read();
+                        mbar_arrive(dump_done);
+                    }
+                    __syncwarp();
+                }
+            }
+            bulk_wait_all();
+        }
     } else {
         // ================= epilogue warps =================
         const int ew = warp - EPI_WARP0;          // 0..EPI_WARPS-1
+        uint32_t ndump = 0;
         const int quad = warp & 3;                // TMEM lane quadrant this warp may access
         const int cgp = ew >> 2;                  // column group handled by this warp
         const int row = quad * 32 + lane;         // tile row = TMEM lane
@@ -305,7 +340,6 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
             trace_stamp(tr, ts++);
             const int64_t pt = (int64_t)tile * TILE + row;
             const bool live = pt < P;
-            uint8_t* xg = DUMP == 2 ? W::x_ptr(ws, tile) : nullptr;   // X slab images of this tile (tensor-core backward)
             float* ag = DUMP == 2 ? W::a_ptr(ws, tile) : nullptr;
             // ---- tile prologue: c -> c slab, Fourier features -> embedding slabs ----
             {
@@ -322,6 +356,10 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
                     x0 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 0));
                     x1 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 1));
                     x2 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 2));
+                }
+                if constexpr (DUMP == 2) {      // the previous tile's y_4 dump also covers its embedding / c slabs
+                    mbar_wait(dump_done, (ndump & 1) ^ 1);
+                    ++ndump;
                 }
 #pragma unroll 1
                 for (int ch = cgp; ch < NCH; ch += CG) {        // ch is warp-uniform
@@ -344,20 +382,12 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
                     const uint32_t so = slab_off(row, ch & 7);
                     *reinterpret_cast<uint4*>(sAhi + (HS + slab) * SLAB + so) = vh;
                     *reinterpret_cast<uint4*>(sAlo + (HS + slab) * SLAB + so) = vl;
-                    if (DUMP == 2) {
-                        *reinterpret_cast<uint4*>(xg + W::x_e(0, slab) * SLAB + so) = vh;
-                        *reinterpret_cast<uint4*>(xg + W::x_e(1, slab) * SLAB + so) = vl;
-                    }
                 }
                 trace_stamp(tr, ts++);
                 uint4 vh, vl;
                 split8(cf, vh, vl);
                 *reinterpret_cast<uint4*>(sC + slab_off(row, cgp)) = vh;
                 *reinterpret_cast<uint4*>(sC + slab_off(row, 4 + cgp)) = vl;
-                if (DUMP == 2) {
-                    *reinterpret_cast<uint4*>(xg + W::x_c() * SLAB + slab_off(row, cgp)) = vh;
-                    *reinterpret_cast<uint4*>(xg + W::x_c() * SLAB + slab_off(row, 4 + cgp)) = vl;
-                }
             }
             fence_proxy_async();
             mbar_arrive(a_ready);
@@ -380,6 +410,10 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
                 } else {
                     tc_ld8(tmem + lane_addr + col0, a);
                     tc_ld8(tmem + lane_addr + H + col0, u);
+                }
+                if constexpr (DUMP == 2) {
+                    mbar_wait(dump_done, (ndump & 1) ^ 1);
+                    ++ndump;
                 }
                 const float4* bi4 = reinterpret_cast<const float4*>(sBias + (layer * 2 + 0) * H + col0);
                 const float4* bc4 = reinterpret_cast<const float4*>(sBias + (layer * 2 + 1) * H + col0);
@@ -407,10 +441,6 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
                     const uint32_t so = slab_off(row, (colabs & 63) >> 3);
                     *reinterpret_cast<uint4*>(sAhi + slab * SLAB + so) = vh;
                     *reinterpret_cast<uint4*>(sAlo + slab * SLAB + so) = vl;
-                    if (DUMP == 2) {
-                        *reinterpret_cast<uint4*>(xg + W::x_y(layer, 0, slab) * SLAB + so) = vh;
-                        *reinterpret_cast<uint4*>(xg + W::x_y(layer, 1, slab) * SLAB + so) = vl;
-                    }
                 }
                 tc_fence_before();
                 fence_proxy_async();

@@ -195,7 +195,8 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
     uint64_t* empty = bars + NSTB;
     uint64_t* a_ready = bars + 2 * NSTB;
     uint64_t* acc_ready = bars + 2 * NSTB + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTB + 2);
+    uint64_t* dump_done = bars + 2 * NSTB + 2;     // dump warp -> epilogue: operand slabs copied out, reusable
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTB + 3);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool want_w = grd.v[iWo] != nullptr;
     const float gS = grad_scale(reinterpret_cast<const uint32_t*>(wimg + (size_t)B::SLABS_PER_TILE * SLAB));
@@ -208,6 +209,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
         }
         mbar_init(a_ready, NEPI);
         mbar_init(acc_ready, 1);
+        mbar_init(dump_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -337,12 +339,37 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 trace_stamp(tr, ts++);
             }
         }
+    } else if (warp == DUMP_WARP) {
+        // ================= dump warp: dy_i / da_i operand slabs -> workspace (for the weight-gradient kernel) =========
+        uint32_t nready = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            uint8_t* gg = W::g_ptr(ws, tile);
+#pragma unroll 1
+            for (int layer = 4; layer >= 0; --layer) {
+                mbar_wait(a_ready, nready & 1);       // the epilogue has written (and proxy-fenced) layer `layer`'s operands
+                ++nready;
+                if (want_w) {
+                    if (elect_one()) {
+                        // shared order dy_hi dy_lo da_hi da_lo == workspace order g_dy(.,0) g_dy(.,1) g_da(.,0) g_da(.,1)
+                        for (int j = 0; j < 4 * HS; ++j)
+                            bulk_s2g(gg + (size_t)(W::g_dy(layer, 0, 0) + j) * SLAB, sDYhi + j * SLAB, SLAB);
+                        bulk_commit();
+                        bulk_wait_read();
+                    }
+                    __syncwarp();
+                }
+                if (elect_one()) mbar_arrive(dump_done);
+                __syncwarp();
+            }
+        }
+        bulk_wait_all();
     } else {
         // ================= epilogue warps =================
         const int ew = warp - EPI_WARP0;
         const int quad = warp & 3;
         const int cgp = ew >> 2;
         const int row = quad * 32 + lane;
+        uint32_t ndump = 0;
         constexpr int CPT = H / CG;               // hidden columns per thread: colour 32, geometry 8
         static_assert(CPT == 32 || CPT == 8, "epilogue column split");
         const int col0 = cgp * CPT;
@@ -366,7 +393,9 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 for (int j = 0; j < CPT; ++j) av[j] = ldg_pinned(ag + (layer * H + col0 + j) * TILE + row);
             };
             // dy (this thread's hidden columns) of layer `layer` -> da, next A operands, dumps for wgrad
-            auto emit = [&](int layer, const float (&av)[CPT], const float (&dy)[CPT]) {
+            auto emit = [&](const float (&av)[CPT], const float (&dy)[CPT]) {
+                mbar_wait(dump_done, (ndump & 1) ^ 1);      // the previous operands have been copied out
+                ++ndump;
 #pragma unroll
                 for (int q = 0; q < CPT / 8; ++q) {
                     float d8[8], a8[8];
@@ -385,12 +414,6 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                     *reinterpret_cast<uint4*>(sDYlo + slab * SLAB + so) = v1;
                     *reinterpret_cast<uint4*>(sDAhi + slab * SLAB + so) = v2;
                     *reinterpret_cast<uint4*>(sDAlo + slab * SLAB + so) = v3;
-                    if (want_w) {
-                        *reinterpret_cast<uint4*>(gg + W::g_dy(layer, 0, slab) * SLAB + so) = v0;
-                        *reinterpret_cast<uint4*>(gg + W::g_dy(layer, 1, slab) * SLAB + so) = v1;
-                        *reinterpret_cast<uint4*>(gg + W::g_da(layer, 0, slab) * SLAB + so) = v2;
-                        *reinterpret_cast<uint4*>(gg + W::g_da(layer, 1, slab) * SLAB + so) = v3;
-                    }
                 }
             };
 
@@ -456,7 +479,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                     dy[j] = s * gS;      // the chain below runs on scaled gradients
                 }
                 trace_stamp(tr, ts++);   // P2: dy_4
-                emit(4, a4, dy);
+                emit(a4, dy);
             }
             fence_proxy_async();
             mbar_arrive(a_ready);
@@ -473,7 +496,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 float dy[CPT];
                 if constexpr (CPT == 32) tc_ld32(tmem + lane_addr + B::T_H + col0, dy);
                 else tc_ld8(tmem + lane_addr + B::T_H + col0, dy);
-                emit(layer - 1, an, dy);
+                emit(an, dy);
                 tc_fence_before();
                 fence_proxy_async();
                 mbar_arrive(a_ready);

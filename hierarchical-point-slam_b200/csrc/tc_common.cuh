@@ -16,7 +16,8 @@ constexpr int EPI_WARP0 = 2;         // warp 0 = producer, warp 1 = MMA issuer, 
 constexpr int EPI_WARPS = 16;        // 4 TMEM lane quadrants x CG column groups
 constexpr int CG = EPI_WARPS / 4;    // column groups: an epilogue thread owns one point (row) x 1/CG of the columns
 constexpr int NEPI = EPI_WARPS * 32;
-constexpr int NTHR = (EPI_WARP0 + EPI_WARPS) * 32;
+constexpr int DUMP_WARP = EPI_WARP0 + EPI_WARPS;   // last warp: bulk-stores the operand slabs to the backward workspace
+constexpr int NTHR = (DUMP_WARP + 1) * 32;
 constexpr float kTwoPi = 6.283185307179586f;
 
 template <int KIND> struct Cfg;
@@ -86,6 +87,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// shared -> global bulk copy (TMA store path) and its group bookkeeping
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
