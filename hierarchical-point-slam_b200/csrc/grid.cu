@@ -196,16 +196,56 @@ struct GridView {
     float inv_cell;
 };
 
-__device__ __forceinline__ bool better(float d, int i, float d2, int i2) {
-    return d < d2 || (d == d2 && i < i2);
+// A candidate is the 64-bit key (bits(D) << 32) | index: squared distances are non-negative, so unsigned key
+// order == the reference's (D, index) order and one compare replaces the two-level test.  ~0 = empty slot.
+constexpr unsigned long long kNoKey = ~0ull;
+
+__device__ __forceinline__ unsigned long long shfl_xor_u64(unsigned long long v, int m) {
+    return ((unsigned long long)__shfl_xor_sync(kFull, (unsigned)(v >> 32), m) << 32) | __shfl_xor_sync(kFull, (unsigned)v, m);
+}
+__device__ __forceinline__ unsigned long long shfl_u64(unsigned long long v, int src) {
+    return ((unsigned long long)__shfl_sync(kFull, (unsigned)(v >> 32), src) << 32) | __shfl_sync(kFull, (unsigned)v, src);
 }
 
+// ascending bitonic sort of one key per lane (15 compare-exchange steps)
+__device__ __forceinline__ unsigned long long warp_sort32(unsigned long long v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const unsigned long long o = shfl_xor_u64(v, j);
+            const bool keep_min = ((lane & j) == 0) == ((lane & k) == 0);
+            v = (keep_min == (v < o)) ? v : o;
+        }
+    }
+    return v;
+}
+
+// best: ascending top-8 in lanes 0..7 (other lanes kNoKey); blk: ascending in lanes 0..31.  Returns the merged top-8.
+__device__ __forceinline__ unsigned long long merge_top8(unsigned long long best, unsigned long long blk, int lane) {
+    const unsigned long long rev = shfl_u64(blk, 15 - (lane & 15));     // lanes 8..15 <- blk[7..0]
+    unsigned long long v = lane < 8 ? best : rev;                        // lanes 0..15: bitonic sequence
+#pragma unroll
+    for (int j = 8; j > 0; j >>= 1) {
+        const unsigned long long o = shfl_xor_u64(v, j);
+        v = (((lane & j) == 0) == (v < o)) ? v : o;
+    }
+    return lane < kK ? v : kNoKey;
+}
+
+// One warp per query.  (1) the voxels overlapping the search ball are looked up in the hash table, one per lane;
+// the non-empty ones are compacted into shared memory as (first point, exclusive prefix of the counts); (2) the
+// concatenation of their point ranges is swept 32 candidates at a time - the owner voxel of every candidate comes
+// from a start-bit mask (redux.or + popc), not from a search; (3) candidates inside the radius and better than the
+// current 8th are appended to a per-warp buffer, and every 32 of them are sorted by a bitonic network and merged
+// into the running top-8.
 __global__ void __launch_bounds__(kQueryWarps * 32)
 knn_query_kernel(GridView g, const float* __restrict__ q, const float* __restrict__ t_up,
                  const float* __restrict__ t_dn, int64_t nq, int32_t* __restrict__ I, float* __restrict__ D,
                  int32_t* __restrict__ count, int32_t* __restrict__ cand) {
     __shared__ int s_start[kQueryWarps][kStageCells];
-    __shared__ int s_excl[kQueryWarps][kStageCells];
+    __shared__ int s_excl[kQueryWarps][kStageCells + 32];
+    __shared__ unsigned long long s_buf[kQueryWarps][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t qi = (int64_t)blockIdx.x * kQueryWarps + warp;
     if (qi >= nq) return;
@@ -222,28 +262,44 @@ knn_query_kernel(GridView g, const float* __restrict__ q, const float* __restric
     const bool any = (nx > 0) && (ny > 0) && (nz > 0) && (tdn >= 0.f);
     const int64_t ncell = any ? (int64_t)nx * ny * nz : 0;
 
-    // running top-8 in lanes 0..7, ascending (D, index)
-    float bD = INFINITY;
-    int bI = 0x7fffffff;
-    float tauD = INFINITY;
-    int tauI = 0x7fffffff;
+    // D <= t_dn  <=>  key < radius_thr
+    const unsigned long long radius_thr = ((unsigned long long)__float_as_uint(fmaxf(tdn, 0.f)) + 1ull) << 32;
+    unsigned long long best = kNoKey;          // running top-8 in lanes 0..7, ascending
+    unsigned long long thr = radius_thr;       // a candidate is interesting iff key < thr
+    int nbuf = 0;                              // warp-uniform fill of s_buf
     int examined = 0;
 
     int* my_start = s_start[warp];
     int* my_excl = s_excl[warp];
+    unsigned long long* my_buf = s_buf[warp];
+
+    auto absorb = [&](unsigned long long k) {  // k: one key per lane (kNoKey padding)
+        best = merge_top8(best, warp_sort32(k, lane), lane);
+        const unsigned long long tau = shfl_u64(best, kK - 1);
+        thr = tau < radius_thr ? tau : radius_thr;
+    };
 
     for (int64_t pass0 = 0; pass0 < ncell; pass0 += kStageCells) {
         const int npass = (int)min((int64_t)kStageCells, ncell - pass0);
         const int nchunk = (npass + 31) >> 5;
-        int running = 0;
+        int running = 0, nne = 0;              // candidates / non-empty voxels staged so far
         for (int t = 0; t < nchunk; ++t) {
             const int64_t ci = pass0 + t * 32 + lane;
             int cnt = 0, st = 0;
             if (ci < pass0 + npass) {
-                const int ix = x0 + (int)(ci % nx);
-                const int64_t r2 = ci / nx;
-                const int iy = y0 + (int)(r2 % ny);
-                const int iz = z0 + (int)(r2 / ny);
+                int ix, iy, iz;
+                if (ncell <= 0x7fffffff) {     // the usual case: 32-bit index arithmetic
+                    const unsigned c32 = (unsigned)ci, r2 = c32 / (unsigned)nx;
+                    ix = x0 + (int)(c32 - r2 * (unsigned)nx);
+                    const unsigned r3 = r2 / (unsigned)ny;
+                    iy = y0 + (int)(r2 - r3 * (unsigned)ny);
+                    iz = z0 + (int)r3;
+                } else {
+                    ix = x0 + (int)(ci % nx);
+                    const int64_t r2 = ci / nx;
+                    iy = y0 + (int)(r2 % ny);
+                    iz = z0 + (int)(r2 / ny);
+                }
                 const unsigned long long key = cell_key(ix, iy, iz);
                 unsigned h = hash_key(key) & g.mask;
                 while (true) {
@@ -259,66 +315,64 @@ knn_query_kernel(GridView g, const float* __restrict__ q, const float* __restric
                 }
             }
             int incl = cnt;
+#pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 int v = __shfl_up_sync(kFull, incl, o);
                 if (lane >= o) incl += v;
             }
-            my_start[t * 32 + lane] = st;
-            my_excl[t * 32 + lane] = running + incl - cnt;
+            const unsigned ne = __ballot_sync(kFull, cnt > 0);
+            if (cnt > 0) {
+                const int r = nne + __popc(ne & ((1u << lane) - 1));
+                my_start[r] = st;
+                my_excl[r] = running + incl - cnt;
+            }
+            nne += __popc(ne);
             running += __shfl_sync(kFull, incl, 31);
         }
+        my_excl[nne + lane] = 0x7fffffff;      // sentinels for the start-mask look-ahead
         __syncwarp();
-        const int nstored = nchunk * 32;
         const int total = running;
         examined += total;
+        int R = 0;                             // non-empty voxels whose range starts before the window
         for (int t0 = 0; t0 < total; t0 += 32) {
             const int t = t0 + lane;
-            float d = INFINITY;
-            int pidx = 0x7fffffff;
+            // voxels starting inside [t0, t0+32): consecutive compact ranks R, R+1, ... (each holds >= 1 point)
+            const unsigned rel = (unsigned)(my_excl[R + lane] - t0);
+            const unsigned starts = __reduce_or_sync(kFull, rel < 32u ? (1u << rel) : 0u);
+            const int owner = R - 1 + __popc(starts & (0xffffffffu >> (31 - lane)));
+            R += __popc(starts);
+            unsigned long long key = kNoKey;
             if (t < total) {
-                int lo = 0;
-#pragma unroll
-                for (int step = kStageCells / 2; step > 0; step >>= 1) {
-                    const int m = lo + step;
-                    if (m < nstored && my_excl[m] <= t) lo = m;
-                }
-                const float4 p = __ldg(g.sorted + (my_start[lo] + (t - my_excl[lo])));
-                d = sqdist_rn(qx, qy, qz, p.x, p.y, p.z);
-                pidx = __float_as_int(p.w);
+                const float4 p = __ldg(g.sorted + (my_start[owner] + (t - my_excl[owner])));
+                const float d = sqdist_rn(qx, qy, qz, p.x, p.y, p.z);
+                key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
             }
-            const bool want = (d <= tdn) && better(d, pidx, tauD, tauI);
-            unsigned m = __ballot_sync(kFull, want);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const float cD = __shfl_sync(kFull, d, src);
-                const int cI = __shfl_sync(kFull, pidx, src);
-                if (better(cD, cI, tauD, tauI)) {   // warp-uniform
-                    const bool before = (lane < kK) && better(bD, bI, cD, cI);
-                    const int pos = __popc(__ballot_sync(kFull, before));
-                    const float upD = __shfl_up_sync(kFull, bD, 1);
-                    const int upI = __shfl_up_sync(kFull, bI, 1);
-                    if (lane < kK) {
-                        if (lane > pos) {
-                            bD = upD;
-                            bI = upI;
-                        } else if (lane == pos) {
-                            bD = cD;
-                            bI = cI;
-                        }
-                    }
-                    tauD = __shfl_sync(kFull, bD, kK - 1);
-                    tauI = __shfl_sync(kFull, bI, kK - 1);
+            const bool want = key < thr;
+            const unsigned m = __ballot_sync(kFull, want);
+            if (m) {
+                if (want) my_buf[nbuf + __popc(m & ((1u << lane) - 1))] = key;
+                nbuf += __popc(m);
+                __syncwarp();
+                if (nbuf >= 32) {
+                    const unsigned long long k = my_buf[lane];
+                    const unsigned long long rest = my_buf[32 + lane];
+                    __syncwarp();
+                    nbuf -= 32;
+                    if (lane < nbuf) my_buf[lane] = rest;
+                    __syncwarp();
+                    absorb(k);
                 }
             }
         }
         __syncwarp();
     }
+    if (nbuf > 0) absorb(lane < nbuf ? my_buf[lane] : kNoKey);
 
-    const unsigned inr = __ballot_sync(kFull, (lane < kK) && (bD < tup));
+    const bool used = best != kNoKey;
+    const float bD = __uint_as_float((unsigned)(best >> 32));
+    const unsigned inr = __ballot_sync(kFull, (lane < kK) && used && (bD < tup));
     if (lane < kK) {
-        const bool used = bI != 0x7fffffff;
-        I[qi * kK + lane] = used ? bI : -1;
+        I[qi * kK + lane] = used ? (int)(unsigned)best : -1;
         D[qi * kK + lane] = used ? bD : FLT_MAX;
     }
     if (lane == 0) {
