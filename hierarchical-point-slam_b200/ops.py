@@ -76,6 +76,37 @@ def _f32c(t):
     return t.to(torch.float32).contiguous()
 
 
+class _ZeroPool:
+    """Zero-initialised scratch tensors carved out of ONE allocation (one memset kernel for all of them); every
+    tensor starts on a 16-byte boundary.  want() before alloc(), get() after."""
+
+    def __init__(self, device):
+        self.device, self.total, self.reqs, self.flat = device, 0, [], None
+
+    def want(self, shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        self.reqs.append((self.total, n, tuple(shape)))
+        self.total += (n + 3) // 4 * 4
+        return len(self.reqs) - 1
+
+    def want_like(self, tensors, skip_first):
+        return [None if (skip_first and i == 0) else self.want(t.shape) for i, t in enumerate(tensors)]
+
+    def alloc(self):
+        self.flat = torch.zeros(max(self.total, 1), dtype=torch.float32, device=self.device)
+        return self
+
+    def get(self, h):
+        if h is None:
+            return None
+        if isinstance(h, list):
+            return [self.get(x) for x in h]
+        off, n, shape = self.reqs[h]
+        return self.flat[off:off + n].view(shape)
+
+
 def _zero_grads_like(tensors, skip_first):
     """Zero-initialised gradient buffers for a parameter list as views of ONE flat allocation (one memset instead
     of one per parameter); every view starts on a 16-byte boundary (the wgrad kernels use red.global.add.v4)."""
@@ -510,8 +541,10 @@ class _RenderRays(torch.autograd.Function):
         ro, rd, gd = _f32c(rays_o).reshape(-1, 3), _f32c(rays_d).reshape(-1, 3), _f32c(gt_depth).reshape(-1)
         # live-row mode: feats_* are the compact (M,32) leaves; the kernels gather from the refreshed full tables
         row_map = None
+        fork = MULTI_STREAM and TIMERS is None and USE_TC and spec.color_stage
         if spec.live_geo is not None:
-            spec.live_geo.refresh()
+            if not fork:
+                spec.live_geo.refresh()
             fg = spec.live_geo.table
             row_map = spec.live_geo.row_map
         else:
@@ -519,7 +552,8 @@ class _RenderRays(torch.autograd.Function):
         fc = None
         if spec.color_stage:
             if spec.live_col is not None:
-                spec.live_col.refresh()
+                if not fork:
+                    spec.live_col.refresh()
                 fc = spec.live_col.table
                 row_map = spec.live_col.row_map
             else:
@@ -553,7 +587,6 @@ class _RenderRays(torch.autograd.Function):
         zz = _f32c(spec.z_zero) if spec.z_zero is not None else None
         garr, carr = _ptr_array(gprm), (_ptr_array(cprm) if spec.color_stage else None)
         st = _stream
-        fork = MULTI_STREAM and TIMERS is None and USE_TC and spec.color_stage
         with torch.cuda.device(dev):
             main = torch.cuda.current_stream(dev)
             bpk_g = bpk_c = None
@@ -565,6 +598,14 @@ class _RenderRays(torch.autograd.Function):
                 if need_grad and USE_TC_BWD:
                     bpk_g, bpk_c = _new_bwd_images(MLP_GEO, dev), _new_bwd_images(MLP_COL, dev)
                 side.wait_stream(main)
+                refreshed = None
+                if spec.live_geo is not None or spec.live_col is not None:
+                    with torch.cuda.stream(side):     # table[live rows] = leaves, off the critical path
+                        if spec.live_geo is not None:
+                            spec.live_geo.refresh()
+                        if spec.live_col is not None:
+                            spec.live_col.refresh()
+                    refreshed = side.record_event()
                 _mlp_pack(MLP_COL, carr, dev, side, bwd=bpk_c)
                 packed_col = side.record_event()
                 _mlp_pack(MLP_GEO, garr, dev, side, bwd=bpk_g)
@@ -573,6 +614,8 @@ class _RenderRays(torch.autograd.Function):
                   _lib.ptr(z), _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), st())
             _call("hps_knn_query", spec.grid._h, _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), P, _lib.ptr(I),
                   _lib.ptr(D), _lib.ptr(cnt), None, st())
+            if fork and refreshed is not None:
+                main.wait_event(refreshed)
             _call("hps_interp_fwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(D), _lib.ptr(t_dn), _lib.ptr(cnt),
                   _lib.ptr(pos), _lib.ptr(fg), _lib.ptr(fc), _lib.ptr(fill_g), _lib.ptr(fill_c), P, int(spec.min_nn),
                   _lib.ptr(w), _lib.ptr(c_geo), _lib.ptr(c_col), _lib.ptr(has), st())
@@ -619,26 +662,30 @@ class _RenderRays(torch.autograd.Function):
         dc_c = torch.empty(P, C_DIM, **f32) if spec.color_stage else None
         want_gw = any(need[7 + i] for i in range(1, N_PARAM))
         want_cw = spec.color_stage and any(need[7 + N_PARAM + i] for i in range(1, N_PARAM))
-        dg = _zero_grads_like(gprm, skip_first=not need[7]) if want_gw else None
-        dcw = _zero_grads_like(cprm, skip_first=True) if want_cw else None   # colour _B is not a parameter
+        fork = MULTI_STREAM and TIMERS is None and spec.color_stage and ctx.saved_kinds == ("tc", "tc")
+        # every zero-initialised buffer of the backward comes out of one allocation = one memset kernel
+        zp = _ZeroPool(dev)
+        h_dg = zp.want_like(gprm, skip_first=not need[7]) if want_gw else None
+        h_dcw = zp.want_like(cprm, skip_first=True) if want_cw else None   # colour _B is not a parameter
+        h_daff = zp.want((12,)) if (aff is not None and need[6]) else None
+        n_rows = ctx.n_live if ctx.row_map is not None else fg.shape[0]
+        h_dfg = zp.want((n_rows, C_DIM)) if need[4] else None
+        h_dfc = zp.want((n_rows, C_DIM)) if (spec.color_stage and need[5]) else None
+        tc_dp = need_p and ctx.saved_kinds[0] == "tc"
+        h_dpg = zp.want((P, 3)) if tc_dp else None                          # accumulated by the dgrad kernels
+        h_dpc = zp.want((P, 3)) if (tc_dp and spec.color_stage) else None
+        zp.alloc()
+        dg, dcw, daff = zp.get(h_dg), zp.get(h_dcw), zp.get(h_daff)
+        dfg, dfc = zp.get(h_dfg), zp.get(h_dfc)
         dp_i = torch.empty(P, 3, **f32) if need_p else None
-        daff = torch.zeros(12, **f32) if (aff is not None and need[6]) else None
-        if ctx.row_map is not None:
-            dfg = torch.zeros(ctx.n_live, C_DIM, **f32) if need[4] else None
-            dfc = torch.zeros(ctx.n_live, C_DIM, **f32) if (spec.color_stage and need[5]) else None
-        else:
-            dfg = torch.zeros_like(fg) if need[4] else None
-            dfc = torch.zeros_like(fc) if (spec.color_stage and need[5]) else None
         st = _stream
         with torch.cuda.device(dev):
             _call("hps_composite_bwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
                   float(spec.coef), _lib.ptr(gd), _lib.ptr(gc), _lib.ptr(d_rgb), 3, _lib.ptr(d_occ), 1, st())
-            fork = MULTI_STREAM and TIMERS is None and spec.color_stage and ctx.saved_kinds == ("tc", "tc")
             dp_c = None
             if fork:
                 main, side = torch.cuda.current_stream(dev), _side_stream(dev)
-                dp_g = _mlp_dp_buffer("tc", P, need_p, dev)
-                dp_c = _mlp_dp_buffer("tc", P, need_p, dev)
+                dp_g, dp_c = zp.get(h_dpg), zp.get(h_dpc)
                 side.wait_stream(main)
                 _mlp_backward(MLP_COL, cprm, "tc", act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c, need_p, daff, dev, main,
                               dp_c, packed=ctx.bwd_packed[1])
@@ -647,10 +694,10 @@ class _RenderRays(torch.autograd.Function):
                 main.wait_stream(side)
             else:
                 dp_g = _mlp_backward(MLP_GEO, gprm, ctx.saved_kinds[0], act_g, pts, c_geo, None, d_occ, P, dg, dc_g,
-                                     need_p, None, dev)
+                                     need_p, None, dev, dp=zp.get(h_dpg))
                 if spec.color_stage:
                     dp_c = _mlp_backward(MLP_COL, cprm, ctx.saved_kinds[1], act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c,
-                                         need_p, daff, dev)
+                                         need_p, daff, dev, dp=zp.get(h_dpc))
             if dfg is not None or dfc is not None or need_p:
                 _call("hps_interp_bwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(w), _lib.ptr(has), _lib.ptr(pos),
                       _lib.ptr(fg), _lib.ptr(fc), _lib.ptr(c_geo), _lib.ptr(c_col), _lib.ptr(dc_g), _lib.ptr(dc_c), P,
@@ -698,21 +745,27 @@ class _MapperLoss(torch.autograd.Function):
         aff = _f32c(affine) if (affine is not None and color_stage) else None
         v = valid.detach().contiguous()
         v = v.view(torch.uint8) if v.dtype == torch.bool else v.to(torch.uint8)
-        loss = torch.zeros((), **f32)
-        g_depth = torch.empty(R, **f32)
-        g_color = torch.empty(R, 3, **f32) if color_stage else None
-        d_aff = torch.zeros(12, **f32) if aff is not None else None
+        # one buffer: [loss, pad x3 | d_affine (12) | g_depth (R) | g_color (3R)]; the head is zeroed (accumulators)
+        flat = torch.empty(16 + R * (4 if color_stage else 1), **f32)
+        flat[:16].zero_()
+        loss = flat[0]
+        d_aff = flat[4:16] if aff is not None else None
+        g_depth = flat[16:16 + R]
+        g_color = flat[16 + R:].view(R, 3) if color_stage else None
         with torch.cuda.device(dev):
             _call("hps_mapper_loss", _lib.ptr(d), _lib.ptr(col), _lib.ptr(v), _lib.ptr(gdp), _lib.ptr(gcl), _lib.ptr(aff),
                   float(w_color), R, _lib.ptr(loss), _lib.ptr(g_depth), _lib.ptr(g_color), _lib.ptr(d_aff), _stream())
-        ctx.save_for_backward(g_depth, g_color, d_aff)
+        ctx.save_for_backward(flat)
+        ctx.dims = (R, color_stage, aff is not None)
         return loss
 
     @staticmethod
     def backward(ctx, gout):
-        g_depth, g_color, d_aff = ctx.saved_tensors
-        return (g_depth * gout, g_color * gout if g_color is not None else None, None, None, None,
-                d_aff * gout if d_aff is not None else None, None, None)
+        (flat,) = ctx.saved_tensors
+        R, color_stage, has_aff = ctx.dims
+        g = flat[4:] * gout                      # one kernel scales d_affine, g_depth and g_color
+        return (g[12:12 + R], g[12 + R:].view(R, 3) if color_stage else None, None, None, None,
+                g[:12] if has_aff else None, None, None)
 
 
 def mapper_loss(depth, color, valid_ray_mask, gt_depth, gt_color, stage, w_color_loss=0.1, affine=None):
