@@ -34,14 +34,16 @@ SIGNATURES = {
     "hps_mlp_tc_ws_bytes": (_i64, [_i32, _i64]),
     "hps_mlp_tc_bwd_packed_bytes": (_i64, [_i32]),
     "hps_mlp_tc_bwd_pack": (_i32, [_i32, _vp, _vp, _vp]),
-    "hps_mlp_tc_bwd": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "hps_mlp_tc_bwd": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
     "hps_tc_selftest": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "hps_tc_trace": (_i32, [_vp]),
     "hps_mlp_bwd": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "hps_composite_fwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp,
                                  _vp]),
     "hps_composite_bwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _i32, _vp,
-                                 _i32, _vp]),
+                                 _i32, _vp, _vp, _vp]),
+    "hps_exposure_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "hps_exposure_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hps_sample_rays": (_i32, [_vp, _vp, _vp, _vp, ctypes.c_double, _vp, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _vp,
                                _vp]),
     "hps_sample_rays_bwd": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),

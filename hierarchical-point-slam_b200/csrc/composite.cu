@@ -121,7 +121,8 @@ composite_bwd_kernel(const float* __restrict__ rgb, int rgb_stride, const float*
                      int occ_stride, const uint8_t* __restrict__ point_mask, const float* __restrict__ z,
                      int64_t R, int S, float coef, const float* __restrict__ g_depth,
                      const float* __restrict__ g_color, float* __restrict__ d_rgb, int d_rgb_stride,
-                     float* __restrict__ d_occ, int d_occ_stride) {
+                     float* __restrict__ d_occ, int d_occ_stride, unsigned* __restrict__ amax_rgb,
+                     unsigned* __restrict__ amax_occ) {
     constexpr int RPW = 32 / G;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -151,16 +152,34 @@ composite_bwd_kernel(const float* __restrict__ rgb, int rgb_stride, const float*
         const float v = group_bcast<G>(gww, j, lane_base);
         if (j > s) suffix += v;
     }
-    if (!live || !active) return;
+    const bool store = live && active;
     const int64_t i = ray * S + s;
     const float t = __fadd_rn(__fsub_rn(1.0f, me.alpha), 1e-10f);
     const float dalpha = gw * me.trans - suffix / t;
-    d_occ[i * d_occ_stride] = dalpha * coef * me.alpha * (1.0f - me.alpha);
-    if (d_rgb != nullptr) {
-        const float k = me.w / wsum;
-        d_rgb[i * d_rgb_stride + 0] = gr * k;
-        d_rgb[i * d_rgb_stride + 1] = gg * k;
-        d_rgb[i * d_rgb_stride + 2] = gb * k;
+    const float v_occ = store ? dalpha * coef * me.alpha * (1.0f - me.alpha) : 0.f;
+    const float k = me.w / wsum;
+    const float v_r = store ? gr * k : 0.f, v_g = store ? gg * k : 0.f, v_b = store ? gb * k : 0.f;
+    if (store) {
+        d_occ[i * d_occ_stride] = v_occ;
+        if (d_rgb != nullptr) {
+            d_rgb[i * d_rgb_stride + 0] = v_r;
+            d_rgb[i * d_rgb_stride + 1] = v_g;
+            d_rgb[i * d_rgb_stride + 2] = v_b;
+        }
+    }
+    // optional: max |gradient| of the two outputs (the tensor-core decoder backward scales by it; NaN/inf ignored)
+    if (amax_occ != nullptr || amax_rgb != nullptr) {
+        float mo = fabsf(v_occ), mc = fmaxf(fabsf(v_r), fmaxf(fabsf(v_g), fabsf(v_b)));
+        mo = mo <= 3.0e38f ? mo : 0.f;
+        mc = mc <= 3.0e38f ? mc : 0.f;
+        for (int o = 16; o; o >>= 1) {
+            mo = fmaxf(mo, __shfl_xor_sync(0xffffffffu, mo, o));
+            mc = fmaxf(mc, __shfl_xor_sync(0xffffffffu, mc, o));
+        }
+        if (lane == 0) {
+            if (amax_occ != nullptr && mo > 0.f) atomicMax(amax_occ, __float_as_uint(mo));
+            if (amax_rgb != nullptr && d_rgb != nullptr && mc > 0.f) atomicMax(amax_rgb, __float_as_uint(mc));
+        }
     }
 }
 
@@ -192,7 +211,8 @@ extern "C" int hps_composite_fwd(const float* rgb, int rgb_stride, const float* 
 extern "C" int hps_composite_bwd(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
                                  const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
                                  const float* g_depth, const float* g_color, float* d_rgb, int d_rgb_stride,
-                                 float* d_occ, int d_occ_stride, void* stream) {
+                                 float* d_occ, int d_occ_stride, uint32_t* absmax_rgb, uint32_t* absmax_occ,
+                                 void* stream) {
     using namespace hps;
     HPS_REQUIRE(R >= 0 && S >= 1 && S <= 32, "need 1 <= S <= 32");
     if (R == 0) return 0;
@@ -203,11 +223,11 @@ extern "C" int hps_composite_bwd(const float* rgb, int rgb_stride, const float* 
         const int64_t warps = ceil_div(R, 4);
         composite_bwd_kernel<8><<<(unsigned)ceil_div(warps * 32, tb), tb, 0, (cudaStream_t)stream>>>(
             rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, g_depth, g_color, d_rgb, d_rgb_stride,
-            d_occ, d_occ_stride);
+            d_occ, d_occ_stride, absmax_rgb, absmax_occ);
     } else {
         composite_bwd_kernel<32><<<(unsigned)ceil_div(R * 32, tb), tb, 0, (cudaStream_t)stream>>>(
             rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, g_depth, g_color, d_rgb, d_rgb_stride,
-            d_occ, d_occ_stride);
+            d_occ, d_occ_stride, absmax_rgb, absmax_occ);
     }
     HPS_LAUNCH_OK();
     return 0;

@@ -180,3 +180,99 @@ extern "C" int hps_tracker_loss(const float* depth, const float* var, const floa
     HPS_LAUNCH_OK();
     return 0;
 }
+
+
+// ------------------------------------------------------------------------------------------------
+// Exposure MLP (reference src/conv_onet/models/decoder.py:380-396): one CTA, one thread per hidden unit.
+// ------------------------------------------------------------------------------------------------
+namespace hps {
+
+__global__ void exposure_fwd_kernel(const float* __restrict__ x, const float* __restrict__ W1,
+                                    const float* __restrict__ b1, const float* __restrict__ W2,
+                                    const float* __restrict__ b2, int n_in, int hidden, int n_out,
+                                    float* __restrict__ a1, float* __restrict__ out) {
+    extern __shared__ float sh[];       // h[hidden]
+    const int j = threadIdx.x;
+    if (j < hidden) {
+        float a = b1[j];
+        for (int k = 0; k < n_in; ++k) a = fmaf(W1[j * n_in + k], x[k], a);
+        a1[j] = a;
+        const float t = a * 100.0f;     // nn.Softplus(beta=100, threshold=20)
+        sh[j] = t > 20.0f ? a : log1pf(expf(t)) / 100.0f;
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int o = warp; o < n_out; o += nw) {
+        float s = 0.f;
+        for (int k = lane; k < hidden; k += 32) s = fmaf(W2[o * hidden + k], sh[k], s);
+        for (int m = 16; m; m >>= 1) s += __shfl_xor_sync(kFull, s, m);
+        if (lane == 0) out[o] = s + b2[o];
+    }
+}
+
+__global__ void exposure_bwd_kernel(const float* __restrict__ x, const float* __restrict__ W1,
+                                    const float* __restrict__ W2, const float* __restrict__ a1,
+                                    const float* __restrict__ dout, int n_in, int hidden, int n_out,
+                                    float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
+                                    float* __restrict__ db2, float* __restrict__ dx) {
+    extern __shared__ float sh[];       // da[hidden]
+    const int j = threadIdx.x;
+    if (j < hidden) {
+        const float a = a1[j];
+        const float t = a * 100.0f;
+        const float h = t > 20.0f ? a : log1pf(expf(t)) / 100.0f;
+        float dh = 0.f;
+        for (int o = 0; o < n_out; ++o) {
+            const float g = dout[o];
+            dW2[o * hidden + j] = g * h;
+            dh = fmaf(W2[o * hidden + j], g, dh);
+        }
+        float sg = 1.f;                 // d softplus = sigmoid(100 a) below the threshold
+        if (t <= 20.0f) {
+            const float z = expf(t);
+            sg = z / (z + 1.0f);
+        }
+        const float da = dh * sg;
+        db1[j] = da;
+        sh[j] = da;
+        for (int k = 0; k < n_in; ++k) dW1[j * n_in + k] = da * x[k];
+    }
+    if (j < n_out) db2[j] = dout[j];
+    __syncthreads();
+    if (dx != nullptr) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+        for (int k = warp; k < n_in; k += nw) {
+            float s = 0.f;
+            for (int i = lane; i < hidden; i += 32) s = fmaf(W1[i * n_in + k], sh[i], s);
+            for (int m = 16; m; m >>= 1) s += __shfl_xor_sync(kFull, s, m);
+            if (lane == 0) dx[k] = s;
+        }
+    }
+}
+
+}  // namespace hps
+
+extern "C" int hps_exposure_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2,
+                                int n_in, int hidden, int n_out, float* a1, float* out, void* stream) {
+    using namespace hps;
+    HPS_REQUIRE(n_in >= 1 && n_in <= 64 && hidden >= 1 && hidden <= 1024 && n_out >= 1 && n_out <= 32, "exposure MLP size");
+    HPS_REQUIRE(x && W1 && b1 && W2 && b2 && a1 && out, "null buffer");
+    const int tb = (max(hidden, 32) + 31) / 32 * 32;
+    exposure_fwd_kernel<<<1, tb, hidden * sizeof(float), (cudaStream_t)stream>>>(x, W1, b1, W2, b2, n_in, hidden, n_out, a1,
+                                                                              out);
+    HPS_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int hps_exposure_bwd(const float* x, const float* W1, const float* W2, const float* a1, const float* dout,
+                                int n_in, int hidden, int n_out, float* dW1, float* db1, float* dW2, float* db2,
+                                float* dx, void* stream) {
+    using namespace hps;
+    HPS_REQUIRE(n_in >= 1 && n_in <= 64 && hidden >= 1 && hidden <= 1024 && n_out >= 1 && n_out <= 32, "exposure MLP size");
+    HPS_REQUIRE(x && W1 && W2 && a1 && dout && dW1 && db1 && dW2 && db2, "null buffer");
+    const int tb = (max(hidden, 32) + 31) / 32 * 32;
+    exposure_bwd_kernel<<<1, tb, hidden * sizeof(float), (cudaStream_t)stream>>>(x, W1, W2, a1, dout, n_in, hidden, n_out,
+                                                                              dW1, db1, dW2, db2, dx);
+    HPS_LAUNCH_OK();
+    return 0;
+}

@@ -841,7 +841,7 @@ template <int KIND> int launch_pack_bwd(const float* const* params, void* img, c
 template <int KIND>
 int launch_bwd(const float* const* params, const void* img, void* ws, const float* p, const float* affine,
                const float* dout, int64_t P, float* const* dparams, float* dc, float* dp, float* daffine,
-               cudaStream_t s) {
+               int absmax_done, cudaStream_t s) {
     Ptrs prm;
     GradPtrs grd;
     for (int i = 0; i < HPS_MLP_NPARAM; ++i) {
@@ -862,7 +862,7 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
     int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
     uint32_t* maxbits = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(img)) +
                                                     (size_t)GeoB<KIND>::SLABS_PER_TILE * SLAB);
-    {
+    if (!absmax_done) {
         const int64_t n = P * Cfg<KIND>::NOUT;
         const int nb = (int)(ceil_div(n, 1024) < kNumSMs ? ceil_div(n, 1024) : kNumSMs);
         absmax_kernel<<<nb, 1024, 0, s>>>(dout, n, maxbits);
@@ -901,7 +901,7 @@ extern "C" int hps_mlp_tc_bwd_pack(int kind, const float* const* params, void* p
 
 extern "C" int hps_mlp_tc_bwd(int kind, const float* const* params, const void* packed, void* ws, const float* p,
                               const float* affine, const float* dout, int64_t P, float* const* dparams, float* dc,
-                              float* dp, float* daffine, void* stream) {
+                              float* dp, float* daffine, int absmax_done, void* stream) {
     using namespace hps;
     HPS_REQUIRE(kind == HPS_MLP_GEO || kind == HPS_MLP_COL, "bad decoder kind");
     HPS_REQUIRE(P >= 0, "negative point count");
@@ -909,9 +909,9 @@ extern "C" int hps_mlp_tc_bwd(int kind, const float* const* params, const void* 
     HPS_REQUIRE(params && packed && ws && p && dout && dc, "null buffer");
     for (int i = 0; i < HPS_MLP_NPARAM; ++i) HPS_REQUIRE(params[i] != nullptr, "null parameter pointer");
     int rc = kind == HPS_MLP_GEO ? tc::launch_bwd<HPS_MLP_GEO>(params, packed, ws, p, affine, dout, P, dparams, dc, dp,
-                                                               daffine, (cudaStream_t)stream)
+                                                               daffine, absmax_done, (cudaStream_t)stream)
                                  : tc::launch_bwd<HPS_MLP_COL>(params, packed, ws, p, affine, dout, P, dparams, dc, dp,
-                                                               daffine, (cudaStream_t)stream);
+                                                               daffine, absmax_done, (cudaStream_t)stream);
     if (rc) return rc;
     HPS_LAUNCH_OK();
     return 0;

@@ -70,6 +70,11 @@ class _TwoLayer(nn.Module):
             init(lin.weight)
 
     def forward(self, x):
+        if x.is_cuda and x.numel() == self.linear1.in_features and self.linear1.out_features <= 1024 \
+                and self.linear1.in_features <= 64 and self.linear2.out_features <= 32:
+            # one latent vector (the exposure feature of a frame): fused kernel pair instead of ~10 library launches
+            return ops.exposure_mlp(x, self.linear1.weight, self.linear1.bias, self.linear2.weight,
+                                    self.linear2.bias).view(*x.shape[:-1], -1)
         return self.linear2(self.act_fn(self.linear1(x)))
 
 

@@ -44,7 +44,7 @@ _KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_interp_fwd": 
                      "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_mlp_tc_pack": 1, "hps_mlp_tc_fwd": 1,
                      "hps_mlp_tc_bwd_pack": 1, "hps_mlp_tc_bwd": 3, "hps_tc_selftest": 1, "hps_composite_fwd": 1,
                      "hps_composite_bwd": 1, "hps_sample_rays": 1, "hps_sample_rays_bwd": 1, "hps_mapper_loss": 1,
-                     "hps_tracker_loss_stats": 1, "hps_tracker_loss": 1}
+                     "hps_tracker_loss_stats": 1, "hps_tracker_loss": 1, "hps_exposure_fwd": 1, "hps_exposure_bwd": 1}
 TIMERS = None   # set to {} to record (start, end) CUDA events per call name on the current stream
 
 
@@ -353,8 +353,13 @@ def _mlp_dp_buffer(saved_kind, P, need_dp, dev):
     return torch.empty(P, 3, dtype=torch.float32, device=dev)
 
 
+def _absmax_word(kind, packed):
+    """Address of the max|dout| word behind a backward weight image (see hps_mlp_tc_bwd in the header)."""
+    return ctypes.c_void_p(packed.data_ptr() + int(_lib.load().hps_mlp_tc_bwd_packed_bytes(kind)) - 16)
+
+
 def _mlp_backward(kind, prm, saved_kind, saved, p_c, c_c, aff, dout, P, dprm, dc, need_dp, daff, dev, stream=None,
-                  dp=None, packed=None):
+                  dp=None, packed=None, absmax_done=False):
     """Backward of one decoder on `stream`; returns dp (P,3) or None.  dprm: list of gradient buffers (or None).
     dp: preallocated _mlp_dp_buffer (required when `stream` is not the current stream); packed: backward weight
     images built at forward time by _mlp_pack (None: build them now)."""
@@ -368,7 +373,8 @@ def _mlp_backward(kind, prm, saved_kind, saved, p_c, c_c, aff, dout, P, dprm, dc
             pk = _bwd_packed_buffer(kind, dev)
             _call("hps_mlp_tc_bwd_pack", kind, arr, _lib.ptr(pk), _stream(stream))
         _call("hps_mlp_tc_bwd", kind, arr, _lib.ptr(pk), _lib.ptr(saved), _lib.ptr(p_c), _lib.ptr(aff), _lib.ptr(dout), P,
-              darr, _lib.ptr(dc), _lib.ptr(dp), _lib.ptr(daff), _stream(stream))
+              darr, _lib.ptr(dc), _lib.ptr(dp), _lib.ptr(daff), 1 if (absmax_done and packed is not None) else 0,
+              _stream(stream))
         return dp
     _call("hps_mlp_bwd", kind, _ptr_array(prm), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), _lib.ptr(saved),
           _lib.ptr(dout), P, darr, _lib.ptr(dc), _lib.ptr(dp), _lib.ptr(daff), _stream(stream))
@@ -466,7 +472,8 @@ class _CompositeRaw(torch.autograd.Function):
         with torch.cuda.device(raw_c.device):
             _call("hps_composite_bwd", 
                 ctypes.c_void_p(base), 4, ctypes.c_void_p(base + 12), 4, _lib.ptr(pm), _lib.ptr(z_c), R, S, ctx.coef,
-                _lib.ptr(gd), _lib.ptr(gc), ctypes.c_void_p(dbase), 4, ctypes.c_void_p(dbase + 12), 4, _stream())
+                _lib.ptr(gd), _lib.ptr(gc), ctypes.c_void_p(dbase), 4, ctypes.c_void_p(dbase + 12), 4, None, None,
+                _stream())
         return d_raw, None, None, None, None
 
 
@@ -680,17 +687,22 @@ class _RenderRays(torch.autograd.Function):
         dp_i = torch.empty(P, 3, **f32) if need_p else None
         st = _stream
         with torch.cuda.device(dev):
+            # forward-time backward images exist => their max|dout| words are zeroed: reduce into them right here
+            bpk_g, bpk_c = ctx.bwd_packed
+            folded = fork and bpk_g is not None and bpk_c is not None
             _call("hps_composite_bwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
-                  float(spec.coef), _lib.ptr(gd), _lib.ptr(gc), _lib.ptr(d_rgb), 3, _lib.ptr(d_occ), 1, st())
+                  float(spec.coef), _lib.ptr(gd), _lib.ptr(gc), _lib.ptr(d_rgb), 3, _lib.ptr(d_occ), 1,
+                  _absmax_word(MLP_COL, bpk_c) if folded else None, _absmax_word(MLP_GEO, bpk_g) if folded else None,
+                  st())
             dp_c = None
             if fork:
                 main, side = torch.cuda.current_stream(dev), _side_stream(dev)
                 dp_g, dp_c = zp.get(h_dpg), zp.get(h_dpc)
                 side.wait_stream(main)
                 _mlp_backward(MLP_COL, cprm, "tc", act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c, need_p, daff, dev, main,
-                              dp_c, packed=ctx.bwd_packed[1])
+                              dp_c, packed=ctx.bwd_packed[1], absmax_done=folded)
                 _mlp_backward(MLP_GEO, gprm, "tc", act_g, pts, c_geo, None, d_occ, P, dg, dc_g, need_p, None, dev, side,
-                              dp_g, packed=ctx.bwd_packed[0])
+                              dp_g, packed=ctx.bwd_packed[0], absmax_done=folded)
                 main.wait_stream(side)
             else:
                 dp_g = _mlp_backward(MLP_GEO, gprm, ctx.saved_kinds[0], act_g, pts, c_geo, None, d_occ, P, dg, dc_g,
@@ -728,6 +740,55 @@ def render_rays(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, ge
     params = list(geo_params) + (list(col_params) if spec.color_stage else [])
     return _RenderRays.apply(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col if spec.color_stage else None,
                              affine if spec.color_stage else None, *params)
+
+
+# --------------------------------------------------------------------------------------------------
+# exposure MLP (decoder.py:380-396)
+# --------------------------------------------------------------------------------------------------
+class _ExposureMlp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2):
+        _need_cuda(x, W1, b1, W2, b2)
+        dev = x.device
+        xs, w1, bb1, w2, bb2 = _f32c(x).reshape(-1), _f32c(W1), _f32c(b1), _f32c(W2), _f32c(b2)
+        hidden, n_in = w1.shape
+        n_out = w2.shape[0]
+        if xs.numel() != n_in:
+            raise ValueError("exposure feature has %d entries, the MLP takes %d" % (xs.numel(), n_in))
+        a1 = torch.empty(hidden, dtype=torch.float32, device=dev)
+        out = torch.empty(n_out, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _call("hps_exposure_fwd", _lib.ptr(xs), _lib.ptr(w1), _lib.ptr(bb1), _lib.ptr(w2), _lib.ptr(bb2), n_in, hidden,
+                  n_out, _lib.ptr(a1), _lib.ptr(out), _stream())
+        ctx.save_for_backward(xs, w1, w2, a1)
+        ctx.x_shape = x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        xs, w1, w2, a1 = ctx.saved_tensors
+        hidden, n_in = w1.shape
+        n_out = w2.shape[0]
+        dev = xs.device
+        # one allocation: dW1 | db1 | dW2 | db2 | dx (all fully written by the kernel)
+        sizes = [hidden * n_in, hidden, n_out * hidden, n_out, n_in]
+        flat = torch.empty(sum((n + 3) // 4 * 4 for n in sizes), dtype=torch.float32, device=dev)
+        parts, off = [], 0
+        for n in sizes:
+            parts.append(flat[off:off + n])
+            off += (n + 3) // 4 * 4
+        dW1, db1, dW2, db2, dx = parts
+        want_x = ctx.needs_input_grad[0]
+        with torch.cuda.device(dev):
+            _call("hps_exposure_bwd", _lib.ptr(xs), _lib.ptr(w1), _lib.ptr(w2), _lib.ptr(a1), _lib.ptr(_f32c(dout)), n_in,
+                  hidden, n_out, _lib.ptr(dW1), _lib.ptr(db1), _lib.ptr(dW2), _lib.ptr(db2),
+                  _lib.ptr(dx) if want_x else None, _stream())
+        return (dx.view(ctx.x_shape) if want_x else None, dW1.view(hidden, n_in), db1, dW2.view(n_out, hidden), db2)
+
+
+def exposure_mlp(x, W1, b1, W2, b2):
+    """MLP_exposure.forward on one latent vector: W2 softplus_100(W1 x + b1) + b2, one kernel each way."""
+    return _ExposureMlp.apply(x, W1, b1, W2, b2)
 
 
 # --------------------------------------------------------------------------------------------------

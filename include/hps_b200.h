@@ -112,9 +112,14 @@ int hps_mlp_tc_fwd(int kind, const float* const* params, const void* packed, con
  * `packed` = hps_mlp_tc_bwd_pack image (transposed weight slabs, hps_mlp_tc_bwd_packed_bytes(kind) bytes).    */
 int64_t hps_mlp_tc_bwd_packed_bytes(int kind);
 int hps_mlp_tc_bwd_pack(int kind, const float* const* params, void* packed, void* stream);
+/*
+ * The backward runs on gradients scaled by a power of two derived from max|dout|; that maximum is reduced into the
+ * uint32 word (float bits) at packed + hps_mlp_tc_bwd_packed_bytes(kind) - 16, zeroed by hps_mlp_tc_bwd_pack.
+ * absmax_done != 0: the caller has already reduced max|dout| into that word (hps_composite_bwd can do it while
+ * it writes dout), so the extra reduction kernel is skipped.                                                   */
 int hps_mlp_tc_bwd(int kind, const float* const* params, const void* packed, void* ws, const float* p,
                    const float* affine, const float* dout, int64_t P, float* const* dparams, float* dc, float* dp,
-                   float* daffine, void* stream);
+                   float* daffine, int absmax_done, void* stream);
 /* Single-CTA tcgen05 self-test: D[128][N] = A . B^T with fp16 operands staged K-major (major = 0, source
  * [rows][K]) or MN-major (major = 1, source [K][rows]) - pins the shared-memory descriptor encodings.        */
 int hps_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_major, int b_major, void* stream);
@@ -145,7 +150,21 @@ int hps_composite_fwd(const float* rgb, int rgb_stride, const float* occ, int oc
 int hps_composite_bwd(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
                       const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
                       const float* g_depth, const float* g_color,
-                      float* d_rgb, int d_rgb_stride, float* d_occ, int d_occ_stride, void* stream);
+                      float* d_rgb, int d_rgb_stride, float* d_occ, int d_occ_stride,
+                      uint32_t* absmax_rgb, uint32_t* absmax_occ /* may be NULL: atomicMax of |d_rgb| / |d_occ| float bits */,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Exposure MLP (decoder.py:380-396 MLP_exposure: linear1 -> Softplus(beta=100) -> linear2) on one latent
+ * vector: out (n_out = 12) = W2 softplus(W1 x + b1) + b2; W1 (hidden, n_in), W2 (n_out, hidden) row-major as in
+ * nn.Linear.  a1 (hidden) receives the pre-activations for the backward.  One launch each way instead of the
+ * ~10 library kernels of the op-by-op version.  hps_exposure_bwd WRITES dW1, db1, dW2, db2 (and dx if not NULL).
+ * Limits: n_in <= 64, hidden <= 1024, n_out <= 32.
+ * ---------------------------------------------------------------------------------------------- */
+int hps_exposure_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, int n_in,
+                     int hidden, int n_out, float* a1, float* out, void* stream);
+int hps_exposure_bwd(const float* x, const float* W1, const float* W2, const float* a1, const float* dout, int n_in,
+                     int hidden, int n_out, float* dW1, float* db1, float* dW2, float* db2, float* dx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Depth-guided sampling (Renderer.py:163-229, N_samples = 0) + per-point radius thresholds.

@@ -305,3 +305,49 @@ def test_raw2outputs_dropin(hps):
     assert parity.rel(rawd[..., 3], torch.sigmoid(0.1 * raw[..., 3])) < 1e-6      # in-place alpha, common.py:414
     with pytest.raises(NotImplementedError):
         hps.raw2outputs_nerf_color(rawd, z.to(DEV), None, occupancy=False)
+
+
+def test_exposure_mlp_matches_oracle(hps, golden):
+    """decoder.py:380-396 MLP_exposure: fused kernel pair vs the oracle restatement (fp64), forward and all gradients."""
+    torch.manual_seed(7)
+    prm = {"mlp_exposure.linear1.weight": torch.randn(128, 8) * 0.3, "mlp_exposure.linear1.bias": torch.randn(128) * 0.05,
+           "mlp_exposure.linear2.weight": torch.randn(12, 128) * 0.1, "mlp_exposure.linear2.bias": torch.randn(12) * 0.1}
+    x = torch.randn(8) * 0.5
+    ref_in = {k: v.double().requires_grad_(True) for k, v in prm.items()}
+    xr = x.double().requires_grad_(True)
+    ref = O.exposure_affine(ref_in, xr)
+    g = torch.randn(12, dtype=torch.float64)
+    (ref * g).sum().backward()
+    dev_in = [x.to(DEV).requires_grad_(True)] + [prm[k].to(DEV).requires_grad_(True) for k in (
+        "mlp_exposure.linear1.weight", "mlp_exposure.linear1.bias", "mlp_exposure.linear2.weight", "mlp_exposure.linear2.bias")]
+    out = hps.ops.exposure_mlp(*dev_in)
+    (out * g.float().to(DEV)).sum().backward()
+    # tolerance: 1e-4 relative to the largest reference entry (fp32 kernel vs fp64 oracle)
+    def close(a, b):
+        return float((a.detach().cpu().double() - b).abs().max()) <= TOL * max(float(b.abs().max()), 1e-12)
+    assert close(out, ref.detach())
+    assert close(dev_in[0].grad, xr.grad)
+    for t, k in zip(dev_in[1:], ("mlp_exposure.linear1.weight", "mlp_exposure.linear1.bias", "mlp_exposure.linear2.weight",
+                                 "mlp_exposure.linear2.bias")):
+        assert close(t.grad, ref_in[k].grad), k
+
+
+def test_composite_bwd_reports_gradient_maxima(hps):
+    """The optional abs-max words of hps_composite_bwd equal max|d_rgb| / max|d_occ| (consumed by hps_mlp_tc_bwd)."""
+    import ctypes
+    from hps_b200 import _lib
+    torch.manual_seed(3)
+    R, S = 301, 5
+    rgb, occ = torch.rand(R * S, 3, device=DEV), torch.randn(R * S, device=DEV) * 5
+    z = torch.sort(torch.rand(R, S, device=DEV) + 1, dim=1).values
+    gd, gc = torch.randn(R, device=DEV) * 1e-3, torch.randn(R, 3, device=DEV) * 1e-3
+    d_rgb, d_occ = torch.empty_like(rgb), torch.empty_like(occ)
+    words = torch.zeros(2, dtype=torch.int32, device=DEV)
+    lib = _lib.load()
+    rc = lib.hps_composite_bwd(_lib.ptr(rgb), 3, _lib.ptr(occ), 1, None, _lib.ptr(z), R, S, 0.1, _lib.ptr(gd), _lib.ptr(gc),
+                               _lib.ptr(d_rgb), 3, _lib.ptr(d_occ), 1, ctypes.c_void_p(words.data_ptr()),
+                               ctypes.c_void_p(words.data_ptr() + 4), None)
+    _lib.check(rc)
+    torch.cuda.synchronize()
+    got = words.view(torch.float32).cpu()
+    assert float(got[0]) == float(d_rgb.abs().max()) and float(got[1]) == float(d_occ.abs().max())
