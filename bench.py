@@ -164,7 +164,18 @@ def run_reference(args, rank):
             "config": workload_config(args.gpus),
             "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Print the result line on the process's original stdout."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
 
 
 def workload_config(n_gpus):
@@ -273,10 +284,13 @@ def run_ours(args, rank, world, local_rank):
         loss.backward()
         return loss
 
+    grad_exchange = hps.parallel.GradExchange(grad_targets)
+
     def exchange():
-        """Gradient all-reduce over NCCL (eager, right after the captured iteration on the same stream)."""
+        """Gradient all-reduce over NCCL (eager, right after the captured iteration on the same stream): the fused
+        backward's gradients are views of one buffer, so this is one collective plus one small bucket."""
         if world > 1:
-            allreduce_grads(grad_targets, dist)
+            grad_exchange(dist)
 
     def log(msg):
         if os.environ.get("HPS_BENCH_VERBOSE"):
@@ -385,7 +399,7 @@ def run_ours(args, rank, world, local_rank):
         line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": "%d-ray mapper iteration of the same workload, oracle port (torch CPU fp32 + scipy "
                                           "cKDTree for the neighbour search), 3 timed repeats" % CPU_SAMPLE_RAYS}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -431,6 +445,11 @@ def roofline(per, hps, npc, devb, sl):
 
 
 def main():
+    # fd 1 carries the JSON line only: libraries (NCCL prints its version banner there) go to stderr meanwhile
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -451,6 +470,7 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__), "--gpus", str(args.gpus),
                "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        os.dup2(_REAL_STDOUT, 1)                 # the ranks inherit the real stdout
         raise SystemExit(subprocess.call(cmd))
     run_ours(args, rank, world, local_rank)
 

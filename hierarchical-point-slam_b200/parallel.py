@@ -21,27 +21,67 @@ def shard_rays(rank, world, *tensors):
     return tuple(t[lo:hi] for t in tensors)
 
 
-def allreduce_grads(tensors, dist, small_numel=1 << 16, group=None):
-    """Sum `.grad` of every tensor across ranks (missing grads count as zero).
+class GradExchange:
+    """Gradient all-reduce plan for a fixed set of tensors whose `.grad` buffers keep their addresses (CUDA-graph
+    replays; the fused backward hands out all its gradients as views of ONE zero-initialised allocation).
 
-    Large gradients (feature tables) are reduced in place; small ones (decoder parameters, pose,
-    exposure) are flattened into one bucket so the collective count per iteration stays at O(#tables)."""
-    small = []
-    for t in tensors:
-        if t.grad is None:
-            t.grad = torch.zeros_like(t)
-        if t.grad.numel() >= small_numel:
-            dist.all_reduce(t.grad, op=dist.ReduceOp.SUM, group=group)
-        else:
-            small.append(t)
-    if small:
-        flat = torch.cat([t.grad.reshape(-1) for t in small])
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        off = 0
-        for t in small:
-            n = t.grad.numel()
-            t.grad.copy_(flat[off:off + n].view_as(t.grad))
-            off += n
+    Gradients that live in the same storage are reduced with a single collective over the span that covers them
+    (gaps - alignment padding, scratch - ride along); the stragglers (a few small tensors) share one flat bucket.
+    Typical mapper iteration: one all-reduce over the fused backward's buffer + one small bucket, no per-tensor
+    host work."""
+
+    MAX_WASTE = 4.0     # coalesce a storage only if span <= MAX_WASTE x the gradient bytes inside it
+
+    def __init__(self, tensors):
+        self.tensors = list(tensors)
+        self.key = None
+
+    def _plan(self):
+        for t in self.tensors:
+            if t.grad is None:
+                t.grad = torch.zeros_like(t)
+        grads = [t.grad for t in self.tensors]
+        self.key = tuple((g.data_ptr(), g.numel()) for g in grads)
+        by_storage = {}
+        for g in grads:
+            ok = g.is_contiguous() and g.dtype == torch.float32
+            by_storage.setdefault(g.untyped_storage().data_ptr() if ok else ("solo", id(g)), []).append(g)
+        self.spans, self.bucket = [], []
+        for k, gs in by_storage.items():
+            lo = min(g.storage_offset() for g in gs)
+            hi = max(g.storage_offset() + g.numel() for g in gs)
+            used = sum(g.numel() for g in gs)
+            if isinstance(k, tuple):                       # other dtype / layout: reduced on its own
+                self.spans.extend(gs)
+            elif (len(gs) == 1 and used < (1 << 16)) or (hi - lo) > self.MAX_WASTE * used:
+                for g in gs:
+                    (self.bucket if g.numel() < (1 << 16) else self.spans).append(g)
+            else:
+                self.spans.append(gs[0].as_strided((hi - lo,), (1,), lo))
+        self.flat = None
+        if self.bucket:
+            self.flat = torch.empty(sum(g.numel() for g in self.bucket), dtype=self.bucket[0].dtype,
+                                    device=self.bucket[0].device)
+            self.views, off = [], 0
+            for g in self.bucket:
+                self.views.append(self.flat[off:off + g.numel()].view(g.shape))
+                off += g.numel()
+
+    def __call__(self, dist, group=None):
+        if self.key is None or any(t.grad is None or t.grad.data_ptr() != k[0] for t, k in zip(self.tensors, self.key)):
+            self._plan()
+        for sp in self.spans:
+            dist.all_reduce(sp, op=dist.ReduceOp.SUM, group=group)
+        if self.bucket:
+            torch._foreach_copy_(self.views, self.bucket)
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            torch._foreach_copy_(self.bucket, self.views)
+
+
+def allreduce_grads(tensors, dist, small_numel=1 << 16, group=None):
+    """Sum `.grad` of every tensor across ranks (missing grads count as zero): GradExchange built on the fly.  Keep a
+    GradExchange object instead when the same tensors are exchanged every iteration."""
+    GradExchange(tensors)(dist, group)
 
 
 def allreduce_scalars(values, dist, group=None):

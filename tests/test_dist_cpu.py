@@ -69,3 +69,48 @@ def test_shard_bounds_cover_everything():
             b = [hps.parallel.shard_bounds(n, r, w) for r in range(w)]
             assert b[0][0] == 0 and b[-1][1] == n and all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def _exchange_worker(rank, world, port, out):
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    hps = importlib.import_module("hierarchical-point-slam_b200")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(100 + rank)
+    # gradients laid out the way the fused backward hands them out: views of one flat buffer (with padding and a
+    # scratch region in between), plus stragglers in their own storage, one of them float64, one missing
+    flat = torch.randn(4096)
+    shapes = [(0, (7, 5)), (36, (100,)), (200, (32, 32)), (2000, (3,))]        # (offset, shape); [1300, 2000) is scratch
+    params = [torch.zeros(s) for _, s in shapes]
+    for p, (off, s) in zip(params, shapes):
+        n = p.numel()
+        p.grad = flat[off:off + n].view(s)
+    solo = [torch.zeros(70000), torch.zeros(11), torch.zeros(5, dtype=torch.float64), torch.zeros(4)]
+    solo[0].grad, solo[1].grad, solo[2].grad = torch.randn(70000), torch.randn(11), torch.randn(5, dtype=torch.float64)
+    targets = params + solo
+    mine = [None if t.grad is None else t.grad.clone() for t in targets]
+    ex = hps.parallel.GradExchange(targets)
+    ex(dist)
+    n_coll = len(ex.spans) + (1 if ex.bucket else 0)
+    # second iteration on the same buffers (plan reused): refill with this rank's values and exchange again
+    for t, m in zip(targets, mine):
+        t.grad.copy_(m if m is not None else torch.zeros_like(t))
+    ex(dist)
+    torch.save(dict(mine=mine, got=[t.grad.clone() for t in targets], n_coll=n_coll), out % rank)
+    dist.destroy_process_group()
+
+
+def test_grad_exchange_coalesces_views_of_one_buffer(tmp_path):
+    out = str(tmp_path / "ex%d.pt")
+    mp.spawn(_exchange_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = [torch.load(out % k, weights_only=False) for k in range(2)]
+    for i in range(len(r[0]["got"])):
+        a = r[0]["mine"][i] if r[0]["mine"][i] is not None else torch.zeros_like(r[0]["got"][i])
+        b = r[1]["mine"][i] if r[1]["mine"][i] is not None else torch.zeros_like(r[1]["got"][i])
+        for k in range(2):
+            assert torch.allclose(r[k]["got"][i], a + b, rtol=0, atol=1e-6), i
+    # 4 views of one buffer -> 1 collective; the 70000-element gradient and the float64 one on their own; 2 small -> 1 bucket
+    assert r[0]["n_coll"] == 4
