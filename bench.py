@@ -284,7 +284,7 @@ def run_ours(args, rank, world, local_rank):
         loss.backward()
         return loss
 
-    grad_exchange = hps.parallel.GradExchange(grad_targets)
+    grad_exchange = hps.parallel.GradExchange(grad_targets, skip_missing=True)   # untouched (mid-level) decoders stay out
 
     def exchange():
         """Gradient all-reduce over NCCL (eager, right after the captured iteration on the same stream): the fused
@@ -438,8 +438,14 @@ def roofline(per, hps, npc, devb, sl):
             detail[k] = {"ms": per[k], "achieved": amt / (per[k] * 1e-3) / (1e12 if b == "tensor" else 1e9),
                          "unit": "TFLOP/s" if b == "tensor" else "GB/s",
                          "frac": amt / (per[k] * 1e-3) / (1e12 if b == "tensor" else 1e9) / (pk["tf"] if b == "tensor" else pk["hbm"])}
+    traffic = None      # DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/)
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            traffic = json.load(f).get(top)
+    except (OSError, ValueError):
+        pass
     return {"roofline": {"kernel": top, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                         "frac": achieved / peak, "traffic": None, "peak_source": pk["src"],
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": pk["src"],
                          "mean_candidates_per_query": mean_cand, "all": detail},
             "per_kernel": per}
 

@@ -32,11 +32,18 @@ class GradExchange:
 
     MAX_WASTE = 4.0     # coalesce a storage only if span <= MAX_WASTE x the gradient bytes inside it
 
-    def __init__(self, tensors):
-        self.tensors = list(tensors)
+    def __init__(self, tensors, skip_missing=False):
+        """skip_missing: tensors whose .grad is None when the plan is built are left out (parameters the current stage
+        does not touch - the set is the same on every rank because every rank runs the same code path); otherwise
+        they get a zero gradient and take part."""
+        self.all_tensors = list(tensors)
+        self.tensors = self.all_tensors
+        self.skip_missing = skip_missing
         self.key = None
 
     def _plan(self):
+        if self.skip_missing:
+            self.tensors = [t for t in self.all_tensors if t.grad is not None]
         for t in self.tensors:
             if t.grad is None:
                 t.grad = torch.zeros_like(t)
@@ -68,7 +75,8 @@ class GradExchange:
                 off += g.numel()
 
     def __call__(self, dist, group=None):
-        if self.key is None or any(t.grad is None or t.grad.data_ptr() != k[0] for t, k in zip(self.tensors, self.key)):
+        if self.key is None or len(self.key) != len(self.tensors) or \
+                any(t.grad is None or t.grad.data_ptr() != k[0] for t, k in zip(self.tensors, self.key)):
             self._plan()
         for sp in self.spans:
             dist.all_reduce(sp, op=dist.ReduceOp.SUM, group=group)

@@ -24,9 +24,9 @@ if os.path.exists(path):
         a[1] += v
         n += 1
     tot = sum(a[1] for a in agg.values())
-    mine = sum(a[1] for k, a in agg.items() if "hps::" in k)
+    mine = sum(a[1] for k, a in agg.items() if ("hps::" in k or "tc::" in k))
     out = ["# ncu launch list (%s): ncu --metrics gpu__time_duration.sum --clock-control none; per-launch times are cold-cache and serialised" % tag,
-           "# command: python bench.py --steps 2 --warmup 3",
+           "# command: python bench.py --steps 3 --warmup 3 (ncu -s skip -c count window; includes the untimed L2-flush fills)",
            "# launches %d, total %.1f us; hps:: kernels %.1f us = %.1f%% of the window (rest = PyTorch glue)" % (n, tot, mine, 100 * mine / max(tot, 1e-9)),
            "# count   total_us   share   kernel"]
     for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
