@@ -251,25 +251,29 @@ def run_ours(args, rank, world, local_rank):
         return slice(b * RAYS, (b + 1) * RAYS)
 
     renderer.assume_positive_depth = True      # mapper batches are depth-filtered (common.py:248-254)
-    # One ray batch travels as two packed buffers (fp32: rays_o | rays_d | gt_depth | gt_color, fp64: the two radius
-    # vectors) so that staging it costs two copies, not six; the iteration reads contiguous views of them.
+    renderer.write_back_radius = False         # nobody reads the repeated radii the reference writes into the dict
+    # One ray batch travels as ONE packed byte buffer (fp32: rays_o | rays_d | gt_depth | gt_color, then fp64: the
+    # two radius vectors) so that staging it costs one copy, not six; the iteration reads contiguous typed views.
     F32_KEYS = (("rays_o", 3), ("rays_d", 3), ("gt_depth", 1), ("gt_color", 3))
+    N32 = sum(w for _, w in F32_KEYS) * RAYS                       # floats; 4 * N32 is a multiple of 8
 
     def pack(src, b):
         sl = slice(b * RAYS, (b + 1) * RAYS)
-        return (torch.cat([src[k][sl].reshape(-1).float() for k, _ in F32_KEYS]),
-                torch.cat([src["radius"][sl].reshape(-1).double(), src["radius_mid"][sl].reshape(-1).double()]))
+        f32 = torch.cat([src[k][sl].reshape(-1).float() for k, _ in F32_KEYS])
+        f64 = torch.cat([src["radius"][sl].reshape(-1).double(), src["radius_mid"][sl].reshape(-1).double()])
+        return torch.cat([f32.view(torch.uint8), f64.view(torch.uint8)])
 
-    packed = [pack(host, b) for b in range(N_BATCHES)]
-    host_pk = {"f32": torch.stack([a for a, _ in packed]).pin_memory(), "f64": torch.stack([b for _, b in packed]).pin_memory()}
+    host_pk = {"bytes": torch.stack([pack(host, b) for b in range(N_BATCHES)]).pin_memory()}
     dev_pk = {k: v.to(dev) for k, v in host_pk.items()}
-    static_pk = {"f32": torch.empty_like(dev_pk["f32"][0]), "f64": torch.empty_like(dev_pk["f64"][0])}
+    static_pk = {"bytes": torch.empty_like(dev_pk["bytes"][0])}
+    s32 = static_pk["bytes"][:4 * N32].view(torch.float32)
+    s64 = static_pk["bytes"][4 * N32:].view(torch.float64)
     static, off = {}, 0
     for k, w in F32_KEYS:
-        static[k] = static_pk["f32"][off:off + w * RAYS].view(devb[k][:RAYS].shape)
+        static[k] = s32[off:off + w * RAYS].view(devb[k][:RAYS].shape)
         off += w * RAYS
-    static["radius"] = static_pk["f64"][:RAYS].view(devb["radius"][:RAYS].shape)
-    static["radius_mid"] = static_pk["f64"][RAYS:].view(devb["radius_mid"][:RAYS].shape)
+    static["radius"] = s64[:RAYS].view(devb["radius"][:RAYS].shape)
+    static["radius_mid"] = s64[RAYS:].view(devb["radius_mid"][:RAYS].shape)
 
     def step():
         """One mapper iteration on the rays held in `static` (reference Mapper.py:783-858)."""

@@ -110,8 +110,9 @@ __global__ void pack_tc_kernel(Ptrs prm, uint16_t* __restrict__ img) {
 // ---------------------------------------------------------------------------------------------- forward
 template <bool RELU> __device__ __forceinline__ float act_fast(float a) {
     if (RELU) return fmaxf(a, 0.f);
-    // softplus(beta=100): max(a,0) + log(1 + exp(-|100 a|)) / 100   (absolute error < 1e-9)
-    return fmaxf(a, 0.f) + __logf(1.0f + __expf(-fabsf(100.0f * a))) * 0.01f;
+    // softplus(beta=100): max(a,0) + log(1 + exp(-|100 a|)) / 100   (absolute error < 1e-9): 6 instructions
+    const float e = ex2_ftz(fabsf(a) * -144.26950408889634f);               // exp(-|100 a|), 100 * log2(e)
+    return fmaf(lg2_ftz(1.0f + e), 0.0069314718055994531f, fmaxf(a, 0.f));    // ln(2) / 100
 }
 
 // DUMP: 0 = inference, 1 = SIMT-layout activations for mlp_bwd_kernel (act), 2 = workspace for the tensor-core backward (ws)
@@ -501,7 +502,7 @@ template <int KIND> int launch_pack(const float* const* params, void* img, cudaS
 
 template <int KIND>
 int launch_fwd(const float* const* params, const void* img, const float* p, const float* c, const float* affine,
-               int64_t P, float* out, float* act, void* ws, cudaStream_t s) {
+               int64_t P, float* out, float* act, void* ws, int max_ctas, cudaStream_t s) {
     Ptrs prm;
     for (int i = 0; i < HPS_MLP_NPARAM; ++i) prm.v[i] = params[i];
     const int smem = Geo<KIND>::SMEM_BYTES;
@@ -513,7 +514,8 @@ int launch_fwd(const float* const* params, const void* img, const float* p, cons
         configured = true;
     }
     const int num_tiles = (int)ceil_div(P, TILE);
-    const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+    const int cap = (max_ctas > 0 && max_ctas < kNumSMs) ? max_ctas : kNumSMs;
+    const int grid = num_tiles < cap ? num_tiles : cap;
     auto kern = ws ? mlp_fwd_tc_kernel<KIND, 2> : (act ? mlp_fwd_tc_kernel<KIND, 1> : mlp_fwd_tc_kernel<KIND, 0>);
     kern<<<grid, NTHR, smem, s>>>(prm, reinterpret_cast<const uint8_t*>(img), p, c, affine, P, num_tiles, out, act,
                                   reinterpret_cast<uint8_t*>(ws));
@@ -557,7 +559,7 @@ extern "C" int hps_mlp_tc_pack(int kind, const float* const* params, void* packe
 
 extern "C" int hps_mlp_tc_fwd(int kind, const float* const* params, const void* packed, const float* p,
                               const float* c, const float* affine, int64_t P, float* out, float* act, void* ws,
-                              void* stream) {
+                              int max_ctas, void* stream) {
     using namespace hps;
     HPS_REQUIRE(kind == HPS_MLP_GEO || kind == HPS_MLP_COL, "bad decoder kind");
     HPS_REQUIRE(P >= 0 && P < (1ll << 31) * 64, "point count out of range");
@@ -566,8 +568,8 @@ extern "C" int hps_mlp_tc_fwd(int kind, const float* const* params, const void* 
     HPS_REQUIRE(kind == HPS_MLP_COL || affine == nullptr, "affine is colour-only");
     for (int i = 0; i < HPS_MLP_NPARAM; ++i) HPS_REQUIRE(params[i] != nullptr, "null parameter pointer");
     int rc = kind == HPS_MLP_GEO
-                 ? tc::launch_fwd<HPS_MLP_GEO>(params, packed, p, c, affine, P, out, act, ws, (cudaStream_t)stream)
-                 : tc::launch_fwd<HPS_MLP_COL>(params, packed, p, c, affine, P, out, act, ws, (cudaStream_t)stream);
+                 ? tc::launch_fwd<HPS_MLP_GEO>(params, packed, p, c, affine, P, out, act, ws, max_ctas, (cudaStream_t)stream)
+                 : tc::launch_fwd<HPS_MLP_COL>(params, packed, p, c, affine, P, out, act, ws, max_ctas, (cudaStream_t)stream);
     if (rc) return rc;
     HPS_LAUNCH_OK();
     return 0;

@@ -138,10 +138,9 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* 
 
 template <bool RELU> __device__ __forceinline__ float act_grad(float a) {
     if (RELU) return a > 0.f ? 1.f : 0.f;
-    const float t = a * 100.0f;
-    if (t > 20.0f) return 1.f;
-    const float z = __expf(t);
-    return __fdividef(z, z + 1.0f);
+    // sigmoid(100 a) = 1 / (1 + exp(-100 a)); nn.Softplus's threshold (100 a > 20 -> slope 1) differs by < 2.1e-9
+    const float z = ex2_ftz(fminf(a * -144.26950408889634f, 126.0f));         // exp(-100 a), clamped below overflow
+    return rcp_ftz(1.0f + z);
 }
 
 __device__ __forceinline__ uint4 pack8(const uint16_t* v) {
@@ -841,7 +840,7 @@ template <int KIND> int launch_pack_bwd(const float* const* params, void* img, c
 template <int KIND>
 int launch_bwd(const float* const* params, const void* img, void* ws, const float* p, const float* affine,
                const float* dout, int64_t P, float* const* dparams, float* dc, float* dp, float* daffine,
-               int absmax_done, cudaStream_t s) {
+               int absmax_done, int max_ctas, cudaStream_t s) {
     Ptrs prm;
     GradPtrs grd;
     for (int i = 0; i < HPS_MLP_NPARAM; ++i) {
@@ -859,7 +858,8 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
         configured = true;
     }
     const int num_tiles = (int)ceil_div(P, TILE);
-    int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+    const int cap = (max_ctas > 0 && max_ctas < kNumSMs) ? max_ctas : kNumSMs;     // dgrad only; wgrad is HBM-bound
+    int grid = num_tiles < cap ? num_tiles : cap;
     uint32_t* maxbits = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(img)) +
                                                     (size_t)GeoB<KIND>::SLABS_PER_TILE * SLAB);
     if (!absmax_done) {
@@ -901,7 +901,7 @@ extern "C" int hps_mlp_tc_bwd_pack(int kind, const float* const* params, void* p
 
 extern "C" int hps_mlp_tc_bwd(int kind, const float* const* params, const void* packed, void* ws, const float* p,
                               const float* affine, const float* dout, int64_t P, float* const* dparams, float* dc,
-                              float* dp, float* daffine, int absmax_done, void* stream) {
+                              float* dp, float* daffine, int absmax_done, int max_ctas, void* stream) {
     using namespace hps;
     HPS_REQUIRE(kind == HPS_MLP_GEO || kind == HPS_MLP_COL, "bad decoder kind");
     HPS_REQUIRE(P >= 0, "negative point count");
@@ -909,9 +909,9 @@ extern "C" int hps_mlp_tc_bwd(int kind, const float* const* params, const void* 
     HPS_REQUIRE(params && packed && ws && p && dout && dc, "null buffer");
     for (int i = 0; i < HPS_MLP_NPARAM; ++i) HPS_REQUIRE(params[i] != nullptr, "null parameter pointer");
     int rc = kind == HPS_MLP_GEO ? tc::launch_bwd<HPS_MLP_GEO>(params, packed, ws, p, affine, dout, P, dparams, dc, dp,
-                                                               daffine, absmax_done, (cudaStream_t)stream)
+                                                               daffine, absmax_done, max_ctas, (cudaStream_t)stream)
                                  : tc::launch_bwd<HPS_MLP_COL>(params, packed, ws, p, affine, dout, P, dparams, dc, dp,
-                                                               daffine, absmax_done, (cudaStream_t)stream);
+                                                               daffine, absmax_done, max_ctas, (cudaStream_t)stream);
     if (rc) return rc;
     HPS_LAUNCH_OK();
     return 0;

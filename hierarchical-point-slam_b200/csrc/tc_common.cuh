@@ -190,6 +190,24 @@ __device__ __forceinline__ void split16(float x, uint16_t& hi, uint16_t& lo) {
     lo = __half_as_ushort(l);
 }
 
+// MUFU wrappers without the denormal pre/post-scaling of __expf/__logf (inputs here are never denormal where it
+// matters: lg2 sees 1 + e in [1,2], a flushed ex2 result is a correct 0)
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // Eight values at once: two packed-conversion instructions per pair instead of four scalar conversions; the
 // halves are bit-identical to split16's.  vh / vl are one 16-byte slab chunk each.
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& vh, uint4& vl) {

@@ -307,7 +307,28 @@ def _new_bwd_images(kind, dev):
     return torch.empty(int(_lib.load().hps_mlp_tc_bwd_packed_bytes(kind)), dtype=torch.uint8, device=dev)
 
 
-def _mlp_forward(kind, arr, p_c, c_c, aff, P, out, need_grad, dev, stream=None, saved=None, packed=False):
+N_SM = 148
+# per-tile cost of the colour decoder relative to the geometry decoder (measured: 27/16 us forward, 40/21 us dgrad)
+_COST_RATIO = {"fwd": 1.7, "bwd": 1.9}
+
+
+def _sm_split(P, which):
+    """(colour CTAs, geometry CTAs) for two decoder kernels that run concurrently on two streams.  Each kernel owns
+    its SMs (shared memory does not fit twice), so the split that minimises max(ceil(T/nc)*cost_c, ceil(T/ng)*cost_g)
+    beats letting one kernel queue behind the other's first wave."""
+    tiles = (P + 127) // 128
+    if tiles * 2 <= N_SM:
+        return 0, 0                      # everything fits in one wave: no cap
+    best, r = None, _COST_RATIO[which]
+    for nc in range(1, N_SM):
+        ng = N_SM - nc
+        t = max(-(-tiles // nc) * r, -(-tiles // ng) * 1.0)
+        if best is None or t < best[0] - 1e-9:
+            best = (t, nc, ng)
+    return best[1], best[2]
+
+
+def _mlp_forward(kind, arr, p_c, c_c, aff, P, out, need_grad, dev, stream=None, saved=None, packed=False, max_ctas=0):
     """pack + forward of one decoder on `stream` (default: current).  Returns the saved workspace ("tc"|"simt",
     tensor) that _mlp_backward consumes (None when no backward will follow)."""
     lib = _lib.load()
@@ -320,7 +341,7 @@ def _mlp_forward(kind, arr, p_c, c_c, aff, P, out, need_grad, dev, stream=None, 
         if not packed:
             _call("hps_mlp_tc_pack", kind, arr, _lib.ptr(pk), _stream(stream))
         _call("hps_mlp_tc_fwd", kind, arr, _lib.ptr(pk), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), P, _lib.ptr(out),
-              _lib.ptr(act), _lib.ptr(ws), _stream(stream))
+              _lib.ptr(act), _lib.ptr(ws), int(max_ctas), _stream(stream))
     else:
         pk = _packed_buffer(kind, dev)
         act = None
@@ -359,7 +380,7 @@ def _absmax_word(kind, packed):
 
 
 def _mlp_backward(kind, prm, saved_kind, saved, p_c, c_c, aff, dout, P, dprm, dc, need_dp, daff, dev, stream=None,
-                  dp=None, packed=None, absmax_done=False):
+                  dp=None, packed=None, absmax_done=False, max_ctas=0):
     """Backward of one decoder on `stream`; returns dp (P,3) or None.  dprm: list of gradient buffers (or None).
     dp: preallocated _mlp_dp_buffer (required when `stream` is not the current stream); packed: backward weight
     images built at forward time by _mlp_pack (None: build them now)."""
@@ -374,7 +395,7 @@ def _mlp_backward(kind, prm, saved_kind, saved, p_c, c_c, aff, dout, P, dprm, dc
             _call("hps_mlp_tc_bwd_pack", kind, arr, _lib.ptr(pk), _stream(stream))
         _call("hps_mlp_tc_bwd", kind, arr, _lib.ptr(pk), _lib.ptr(saved), _lib.ptr(p_c), _lib.ptr(aff), _lib.ptr(dout), P,
               darr, _lib.ptr(dc), _lib.ptr(dp), _lib.ptr(daff), 1 if (absmax_done and packed is not None) else 0,
-              _stream(stream))
+              int(max_ctas), _stream(stream))
         return dp
     _call("hps_mlp_bwd", kind, _ptr_array(prm), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), _lib.ptr(saved),
           _lib.ptr(dout), P, darr, _lib.ptr(dc), _lib.ptr(dp), _lib.ptr(daff), _stream(stream))
@@ -629,8 +650,11 @@ class _RenderRays(torch.autograd.Function):
             if fork:
                 side.wait_stream(main)
                 main.wait_event(packed_col)
-                sv_c = _mlp_forward(MLP_COL, carr, pts, c_col, aff, P, rgb, need_grad, dev, main, ws_c, packed=True)
-                sv_g = _mlp_forward(MLP_GEO, garr, pts, c_geo, None, P, occ, need_grad, dev, side, ws_g, packed=True)
+                n_c, n_g = _sm_split(P, "fwd")
+                sv_c = _mlp_forward(MLP_COL, carr, pts, c_col, aff, P, rgb, need_grad, dev, main, ws_c, packed=True,
+                                    max_ctas=n_c)
+                sv_g = _mlp_forward(MLP_GEO, garr, pts, c_geo, None, P, occ, need_grad, dev, side, ws_g, packed=True,
+                                    max_ctas=n_g)
                 main.wait_stream(side)
             else:
                 sv_g = _mlp_forward(MLP_GEO, garr, pts, c_geo, None, P, occ, need_grad, dev)
@@ -699,10 +723,11 @@ class _RenderRays(torch.autograd.Function):
                 main, side = torch.cuda.current_stream(dev), _side_stream(dev)
                 dp_g, dp_c = zp.get(h_dpg), zp.get(h_dpc)
                 side.wait_stream(main)
+                n_c, n_g = _sm_split(P, "bwd")
                 _mlp_backward(MLP_COL, cprm, "tc", act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c, need_p, daff, dev, main,
-                              dp_c, packed=ctx.bwd_packed[1], absmax_done=folded)
+                              dp_c, packed=ctx.bwd_packed[1], absmax_done=folded, max_ctas=n_c)
                 _mlp_backward(MLP_GEO, gprm, "tc", act_g, pts, c_geo, None, d_occ, P, dg, dc_g, need_p, None, dev, side,
-                              dp_g, packed=ctx.bwd_packed[0], absmax_done=folded)
+                              dp_g, packed=ctx.bwd_packed[0], absmax_done=folded, max_ctas=n_g)
                 main.wait_stream(side)
             else:
                 dp_g = _mlp_backward(MLP_GEO, gprm, ctx.saved_kinds[0], act_g, pts, c_geo, None, d_occ, P, dg, dc_g,

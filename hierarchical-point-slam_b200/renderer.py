@@ -30,6 +30,7 @@ class Renderer(object):
         # Mapper / tracker batches are depth-filtered (common.py:248-254): owners may set this to skip the
         # zero-depth branch (a handful of tiny device ops per call).
         self.assume_positive_depth = False
+        self.write_back_radius = True        # see render_batch_ray
         if self.N_samples > 0 or self.use_bound or self.sample_near_pcl or self.fix_interval or not self.occupancy:
             raise NotImplementedError("only the reference's ScanNet rendering mode is built: N_samples=0, "
                                       "use_bound False, sample_near_pcl False, occupancy True")
@@ -97,8 +98,12 @@ class Renderer(object):
         gt_depth = gt_depth.reshape(-1)
         if self.use_dynamic_radius:
             radius = dynamic_r_query[level].reshape(-1)
-            for key in dynamic_r_query.keys():                           # Renderer.py:226-229 (dict mutated)
-                dynamic_r_query[key] = dynamic_r_query[key].reshape(-1, 1).repeat_interleave(S, dim=0)
+            if self.write_back_radius:
+                # Renderer.py:226-229 repeats every radius vector per sample and writes it back into the caller's
+                # dict.  The kernels do not need it (the sampling kernel repeats on the fly): two copy kernels kept
+                # only for that visible side effect; set renderer.write_back_radius = False to skip them.
+                for key in dynamic_r_query.keys():
+                    dynamic_r_query[key] = dynamic_r_query[key].reshape(-1, 1).repeat_interleave(S, dim=0)
         else:
             radius = npc.get_radius_query()
         index = npc.get_index(level)
@@ -117,11 +122,10 @@ class Renderer(object):
         depth, uncertainty, color, valid = ops.render_rays(
             spec, rays_o, rays_d, gt_depth, npc_geo_feats[level], npc_col_feats[level] if color_stage else None, affine,
             geo.kernel_params(rays_o.device), col.kernel_params(rays_o.device) if color_stage else None)
-        nz = gt_depth > 0
         if not self.sample_near_pcl and not self.assume_positive_depth:
-            depth = torch.where(nz, depth, torch.zeros_like(depth))     # Renderer.py:250-251
+            depth = torch.where(gt_depth > 0, depth, torch.zeros_like(depth))     # Renderer.py:250-251
         if self.skip_zero_depth_pixel:
-            color = torch.where(nz[:, None], color, torch.zeros_like(color))
+            color = torch.where((gt_depth > 0)[:, None], color, torch.zeros_like(color))
         return depth, uncertainty, color, valid.view(torch.bool)
 
     def render_batch_ray_modular(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None,

@@ -105,8 +105,11 @@ int hps_mlp_tc_pack(int kind, const float* const* params, void* packed, void* st
  * slab images of every layer input, the pre-activations and the raw output); `act` (may be NULL) is the SIMT
  * workspace of hps_mlp_bwd.                                                                            */
 int64_t hps_mlp_tc_ws_bytes(int kind, int64_t P);
+/* max_ctas (hps_mlp_tc_fwd / hps_mlp_tc_bwd): 0 = one persistent CTA per SM; n > 0 caps the grid at n CTAs so that
+ * two decoders launched on two streams share the 148 SMs in proportion to their per-tile cost instead of queueing
+ * behind each other (the kernels hold an SM exclusively: their shared memory does not fit twice).              */
 int hps_mlp_tc_fwd(int kind, const float* const* params, const void* packed, const float* p, const float* c,
-                   const float* affine, int64_t P, float* out, float* act, void* ws, void* stream);
+                   const float* affine, int64_t P, float* out, float* act, void* ws, int max_ctas, void* stream);
 /* Tensor-core backward: dgrad chain kernel + streaming wgrad kernel (MN-major operands, accumulators in TMEM).
  * Same outputs as hps_mlp_bwd except that dp (P,3) must be ZERO-initialised by the caller (it is accumulated).
  * `packed` = hps_mlp_tc_bwd_pack image (transposed weight slabs, hps_mlp_tc_bwd_packed_bytes(kind) bytes).    */
@@ -119,7 +122,7 @@ int hps_mlp_tc_bwd_pack(int kind, const float* const* params, void* packed, void
  * it writes dout), so the extra reduction kernel is skipped.                                                   */
 int hps_mlp_tc_bwd(int kind, const float* const* params, const void* packed, void* ws, const float* p,
                    const float* affine, const float* dout, int64_t P, float* const* dparams, float* dc, float* dp,
-                   float* daffine, int absmax_done, void* stream);
+                   float* daffine, int absmax_done, int max_ctas, void* stream);
 /* Single-CTA tcgen05 self-test: D[128][N] = A . B^T with fp16 operands staged K-major (major = 0, source
  * [rows][K]) or MN-major (major = 1, source [K][rows]) - pins the shared-memory descriptor encodings.        */
 int hps_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_major, int b_major, void* stream);

@@ -81,6 +81,18 @@ def test_render_batch_does_not_need_dict_copy(built):
                                   npc_geo_feats={l: npc.get_geo_feats(l) for l in cl},
                                   npc_col_feats={l: npc.get_col_feats(l) for l in cl}, dynamic_r_query=rq)
     assert rq["fine"].shape == (rays["rays_d"].shape[0] * 5, 1)
+    # opt-out (bench.py): the dict is left alone, results unchanged
+    rq2 = {l: cl[l]["radius"].to(DEV).clone() for l in cl}
+    renderer.write_back_radius = False
+    try:
+        with torch.no_grad():
+            renderer.render_batch_ray(npc, dec, rays["rays_d"].to(DEV), rays["rays_o"].to(DEV), DEV, "color_fine",
+                                      gt_depth=rays["gt_depth"].to(DEV),
+                                      npc_geo_feats={l: npc.get_geo_feats(l) for l in cl},
+                                      npc_col_feats={l: npc.get_col_feats(l) for l in cl}, dynamic_r_query=rq2)
+    finally:
+        renderer.write_back_radius = True
+    assert rq2["fine"].shape == cl["fine"]["radius"].shape
 
 
 def test_sampling_kernel_is_bit_identical_to_torch_ops(built):
