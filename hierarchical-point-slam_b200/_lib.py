@@ -21,7 +21,7 @@ SIGNATURES = {
     "hps_grid_build": (_i32, [_vp, _vp, _i64, _f32, _vp]),
     "hps_grid_info": (_i32, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(_i64),
                              ctypes.POINTER(_f32), ctypes.POINTER(_i32), _vp]),
-    "hps_knn_query": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "hps_knn_query": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
     "hps_interp_fwd": (_i32, [_vp] * 10 + [_i64, _i32] + [_vp] * 5),
     "hps_interp_bwd": (_i32, [_vp] * 11 + [_i64] + [_vp] * 5),
     "hps_mlp_act_floats": (_i64, [_i32]),
@@ -34,7 +34,7 @@ SIGNATURES = {
     "hps_mlp_tc_ws_bytes": (_i64, [_i32, _i64]),
     "hps_mlp_tc_bwd_packed_bytes": (_i64, [_i32]),
     "hps_mlp_tc_bwd_pack": (_i32, [_i32, _vp, _vp, _vp]),
-    "hps_mlp_tc_bwd": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "hps_mlp_tc_bwd": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "hps_tc_selftest": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "hps_tc_trace": (_i32, [_vp]),
     "hps_mlp_bwd": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),

@@ -233,51 +233,68 @@ __device__ __forceinline__ unsigned long long merge_top8(unsigned long long best
     return lane < kK ? v : kNoKey;
 }
 
-// One warp per query.  (1) the voxels overlapping the search ball are looked up in the hash table, one per lane;
-// the non-empty ones are compacted into shared memory as (first point, exclusive prefix of the counts); (2) the
-// concatenation of their point ranges is swept 32 candidates at a time - the owner voxel of every candidate comes
-// from a start-bit mask (redux.or + popc), not from a search; (3) candidates inside the radius and better than the
-// current 8th are appended to a per-warp buffer, and every 32 of them are sorted by a bitonic network and merged
-// into the running top-8.
-__global__ void __launch_bounds__(kQueryWarps * 32)
+// One warp per GROUP of G consecutive queries (G = 1: a single query; G = 5: the samples of one ray, whose search
+// balls overlap heavily, so the voxel probes, the candidate loads and the owner look-ups are shared by the group).
+// (1) the voxels overlapping the bounding box of the group's search balls are looked up in the hash table, one per
+// lane; the non-empty ones are compacted into shared memory as (first point, exclusive prefix of the counts);
+// (2) the concatenation of their point ranges is swept 32 candidates at a time - the owner voxel of every candidate
+// comes from a start-bit mask (redux.or + popc), not from a search; (3) per query, candidates inside the radius and
+// better than the current 8th are appended to a per-warp buffer, and every 32 of them are sorted by a bitonic
+// network and merged into the running top-8.  Results do not depend on G (exact search).
+template <int G>
+__global__ void __launch_bounds__(kQueryWarps * 32, 4)      // 4 CTAs = 32 warps per SM (G = 5 would take 80 registers otherwise)
 knn_query_kernel(GridView g, const float* __restrict__ q, const float* __restrict__ t_up,
                  const float* __restrict__ t_dn, int64_t nq, int32_t* __restrict__ I, float* __restrict__ D,
                  int32_t* __restrict__ count, int32_t* __restrict__ cand) {
     __shared__ int s_start[kQueryWarps][kStageCells];
     __shared__ int s_excl[kQueryWarps][kStageCells + 32];
-    __shared__ unsigned long long s_buf[kQueryWarps][64];
+    __shared__ unsigned long long s_buf[kQueryWarps][G][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t qi = (int64_t)blockIdx.x * kQueryWarps + warp;
-    if (qi >= nq) return;
+    const int64_t q0 = ((int64_t)blockIdx.x * kQueryWarps + warp) * G;
+    if (q0 >= nq) return;
 
-    const float qx = __ldg(q + qi * 3 + 0), qy = __ldg(q + qi * 3 + 1), qz = __ldg(q + qi * 3 + 2);
-    const float tdn = __ldg(t_dn + qi), tup = __ldg(t_up + qi);
     const float ox = g.meta->origin[0], oy = g.meta->origin[1], oz = g.meta->origin[2];
-    // conservative search radius: sqrt(t_dn) plus slack that dominates every fp32 rounding involved
-    const float rr = sqrtf(fmaxf(tdn, 0.f)) * 1.00001f + 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 1.0f);
-    const int x0 = max(cell_coord(qx - rr, ox, g.inv_cell), 0), x1 = min(cell_coord(qx + rr, ox, g.inv_cell), g.meta->maxc[0]);
-    const int y0 = max(cell_coord(qy - rr, oy, g.inv_cell), 0), y1 = min(cell_coord(qy + rr, oy, g.inv_cell), g.meta->maxc[1]);
-    const int z0 = max(cell_coord(qz - rr, oz, g.inv_cell), 0), z1 = min(cell_coord(qz + rr, oz, g.inv_cell), g.meta->maxc[2]);
+    float qx[G], qy[G], qz[G], tdn[G];
+    int x0 = 0x7fffffff, y0 = 0x7fffffff, z0 = 0x7fffffff, x1 = -1, y1 = -1, z1 = -1;
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        const bool live = q0 + k < nq;
+        const int64_t qi = live ? q0 + k : q0;
+        qx[k] = __ldg(q + qi * 3 + 0);
+        qy[k] = __ldg(q + qi * 3 + 1);
+        qz[k] = __ldg(q + qi * 3 + 2);
+        tdn[k] = live ? __ldg(t_dn + qi) : -1.0f;
+        if (tdn[k] >= 0.f) {
+            // conservative search radius: sqrt(t_dn) plus slack that dominates every fp32 rounding involved
+            const float rr = sqrtf(tdn[k]) * 1.00001f + 1e-6f * (fabsf(qx[k]) + fabsf(qy[k]) + fabsf(qz[k]) + 1.0f);
+            x0 = min(x0, cell_coord(qx[k] - rr, ox, g.inv_cell));
+            x1 = max(x1, cell_coord(qx[k] + rr, ox, g.inv_cell));
+            y0 = min(y0, cell_coord(qy[k] - rr, oy, g.inv_cell));
+            y1 = max(y1, cell_coord(qy[k] + rr, oy, g.inv_cell));
+            z0 = min(z0, cell_coord(qz[k] - rr, oz, g.inv_cell));
+            z1 = max(z1, cell_coord(qz[k] + rr, oz, g.inv_cell));
+        }
+    }
+    x0 = max(x0, 0); y0 = max(y0, 0); z0 = max(z0, 0);
+    x1 = min(x1, g.meta->maxc[0]); y1 = min(y1, g.meta->maxc[1]); z1 = min(z1, g.meta->maxc[2]);
     const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
-    const bool any = (nx > 0) && (ny > 0) && (nz > 0) && (tdn >= 0.f);
+    const bool any = (nx > 0) && (ny > 0) && (nz > 0);
     const int64_t ncell = any ? (int64_t)nx * ny * nz : 0;
 
-    // D <= t_dn  <=>  key < radius_thr
-    const unsigned long long radius_thr = ((unsigned long long)__float_as_uint(fmaxf(tdn, 0.f)) + 1ull) << 32;
-    unsigned long long best = kNoKey;          // running top-8 in lanes 0..7, ascending
-    unsigned long long thr = radius_thr;       // a candidate is interesting iff key < thr
-    int nbuf = 0;                              // warp-uniform fill of s_buf
+    unsigned long long best[G];   // running top-8 of query k in lanes 0..7, ascending
+    unsigned long long thr[G];    // a candidate is interesting for query k iff key < thr[k]
+    int nbuf[G];                  // warp-uniform fill of s_buf[warp][k]
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        best[k] = kNoKey;
+        // D <= t_dn  <=>  key < (bits(t_dn) + 1) << 32 ; dead queries accept nothing
+        thr[k] = tdn[k] >= 0.f ? ((unsigned long long)__float_as_uint(tdn[k]) + 1ull) << 32 : 0ull;
+        nbuf[k] = 0;
+    }
     int examined = 0;
 
     int* my_start = s_start[warp];
     int* my_excl = s_excl[warp];
-    unsigned long long* my_buf = s_buf[warp];
-
-    auto absorb = [&](unsigned long long k) {  // k: one key per lane (kNoKey padding)
-        best = merge_top8(best, warp_sort32(k, lane), lane);
-        const unsigned long long tau = shfl_u64(best, kK - 1);
-        thr = tau < radius_thr ? tau : radius_thr;
-    };
 
     for (int64_t pass0 = 0; pass0 < ncell; pass0 += kStageCells) {
         const int npass = (int)min((int64_t)kStageCells, ncell - pass0);
@@ -341,43 +358,55 @@ knn_query_kernel(GridView g, const float* __restrict__ q, const float* __restric
             const unsigned starts = __reduce_or_sync(kFull, rel < 32u ? (1u << rel) : 0u);
             const int owner = R - 1 + __popc(starts & (0xffffffffu >> (31 - lane)));
             R += __popc(starts);
-            unsigned long long key = kNoKey;
-            if (t < total) {
-                const float4 p = __ldg(g.sorted + (my_start[owner] + (t - my_excl[owner])));
-                const float d = sqdist_rn(qx, qy, qz, p.x, p.y, p.z);
-                key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
-            }
-            const bool want = key < thr;
-            const unsigned m = __ballot_sync(kFull, want);
-            if (m) {
-                if (want) my_buf[nbuf + __popc(m & ((1u << lane) - 1))] = key;
-                nbuf += __popc(m);
-                __syncwarp();
-                if (nbuf >= 32) {
-                    const unsigned long long k = my_buf[lane];
-                    const unsigned long long rest = my_buf[32 + lane];
+            float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool have = t < total;
+            if (have) p = __ldg(g.sorted + (my_start[owner] + (t - my_excl[owner])));
+#pragma unroll
+            for (int k = 0; k < G; ++k) {
+                unsigned long long key = kNoKey;
+                if (have) {
+                    const float d = sqdist_rn(qx[k], qy[k], qz[k], p.x, p.y, p.z);
+                    key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
+                }
+                const bool want = key < thr[k];
+                const unsigned m = __ballot_sync(kFull, want);
+                if (m) {
+                    unsigned long long* buf = s_buf[warp][k];
+                    if (want) buf[nbuf[k] + __popc(m & ((1u << lane) - 1))] = key;
+                    nbuf[k] += __popc(m);
                     __syncwarp();
-                    nbuf -= 32;
-                    if (lane < nbuf) my_buf[lane] = rest;
-                    __syncwarp();
-                    absorb(k);
+                    if (nbuf[k] >= 32) {
+                        const unsigned long long blk = buf[lane];
+                        const unsigned long long rest = buf[32 + lane];
+                        __syncwarp();
+                        nbuf[k] -= 32;
+                        if (lane < nbuf[k]) buf[lane] = rest;
+                        __syncwarp();
+                        best[k] = merge_top8(best[k], warp_sort32(blk, lane), lane);
+                        const unsigned long long tau = shfl_u64(best[k], kK - 1);
+                        thr[k] = tau < thr[k] ? tau : thr[k];
+                    }
                 }
             }
         }
         __syncwarp();
     }
-    if (nbuf > 0) absorb(lane < nbuf ? my_buf[lane] : kNoKey);
-
-    const bool used = best != kNoKey;
-    const float bD = __uint_as_float((unsigned)(best >> 32));
-    const unsigned inr = __ballot_sync(kFull, (lane < kK) && used && (bD < tup));
-    if (lane < kK) {
-        I[qi * kK + lane] = used ? (int)(unsigned)best : -1;
-        D[qi * kK + lane] = used ? bD : FLT_MAX;
-    }
-    if (lane == 0) {
-        count[qi] = __popc(inr);
-        if (cand) cand[qi] = examined;
+#pragma unroll
+    for (int k = 0; k < G; ++k) {
+        if (q0 + k >= nq) break;
+        if (nbuf[k] > 0) best[k] = merge_top8(best[k], warp_sort32(lane < nbuf[k] ? s_buf[warp][k][lane] : kNoKey, lane), lane);
+        const int64_t qi = q0 + k;
+        const bool used = best[k] != kNoKey;
+        const float bD = __uint_as_float((unsigned)(best[k] >> 32));
+        const unsigned inr = __ballot_sync(kFull, (lane < kK) && used && (bD < __ldg(t_up + qi)));
+        if (lane < kK) {
+            I[qi * kK + lane] = used ? (int)(unsigned)best[k] : -1;
+            D[qi * kK + lane] = used ? bD : FLT_MAX;
+        }
+        if (lane == 0) {
+            count[qi] = __popc(inr);
+            if (cand) cand[qi] = examined;
+        }
     }
 }
 
@@ -491,7 +520,7 @@ extern "C" int hps_grid_info(const hps_grid_t* g, int64_t* n_points, int64_t* ta
 }
 
 extern "C" int hps_knn_query(const hps_grid_t* g, const float* q, const float* t_up, const float* t_dn, int64_t nq,
-                             int32_t* I, float* D, int32_t* count, int32_t* cand, void* stream_) {
+                             int32_t* I, float* D, int32_t* count, int32_t* cand, int group, void* stream_) {
     using namespace hps;
     HPS_REQUIRE(g != nullptr && g->T > 0, "grid not built");
     HPS_REQUIRE(nq >= 0, "negative query count");
@@ -503,8 +532,13 @@ extern "C" int hps_knn_query(const hps_grid_t* g, const float* q, const float* t
     v.meta = g->meta;
     v.mask = (unsigned)(g->T - 1);
     v.inv_cell = 1.0f / g->cell;
-    knn_query_kernel<<<(unsigned)ceil_div(nq, kQueryWarps), kQueryWarps * 32, 0, (cudaStream_t)stream_>>>(
-        v, q, t_up, t_dn, nq, I, D, count, cand);
+    if (group == 5) {     // the samples of one ray share a sweep
+        knn_query_kernel<5><<<(unsigned)ceil_div(ceil_div(nq, 5), kQueryWarps), kQueryWarps * 32, 0, (cudaStream_t)stream_>>>(
+            v, q, t_up, t_dn, nq, I, D, count, cand);
+    } else {
+        knn_query_kernel<1><<<(unsigned)ceil_div(nq, kQueryWarps), kQueryWarps * 32, 0, (cudaStream_t)stream_>>>(
+            v, q, t_up, t_dn, nq, I, D, count, cand);
+    }
     HPS_LAUNCH_OK();
     return 0;
 }

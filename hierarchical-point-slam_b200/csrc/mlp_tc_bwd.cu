@@ -840,7 +840,7 @@ template <int KIND> int launch_pack_bwd(const float* const* params, void* img, c
 template <int KIND>
 int launch_bwd(const float* const* params, const void* img, void* ws, const float* p, const float* affine,
                const float* dout, int64_t P, float* const* dparams, float* dc, float* dp, float* daffine,
-               int absmax_done, int max_ctas, cudaStream_t s) {
+               int absmax_done, int max_ctas, cudaStream_t wstream, cudaStream_t s) {
     Ptrs prm;
     GradPtrs grd;
     for (int i = 0; i < HPS_MLP_NPARAM; ++i) {
@@ -871,8 +871,18 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
         prm, grd, reinterpret_cast<const uint8_t*>(img), reinterpret_cast<uint8_t*>(ws), p, affine, dout, P, num_tiles,
         dc, dp, daffine);
     if (dparams) {
+        // The weight-gradient kernel may run on its own stream (ordered after the dgrad kernel by an event), so that
+        // whatever the caller enqueues next on `s` - the feature scatter needs only dc - overlaps with it.
+        cudaStream_t w = s;
+        if (wstream != nullptr && wstream != s) {
+            static cudaEvent_t dgrad_done = nullptr;          // one per decoder kind (template instantiation)
+            if (dgrad_done == nullptr) HPS_CUDA_OK(cudaEventCreateWithFlags(&dgrad_done, cudaEventDisableTiming));
+            HPS_CUDA_OK(cudaEventRecord(dgrad_done, s));
+            HPS_CUDA_OK(cudaStreamWaitEvent(wstream, dgrad_done, 0));
+            w = wstream;
+        }
         const int wgrid = GeoW<KIND>::NROLE * num_tiles < kNumSMs ? GeoW<KIND>::NROLE * num_tiles : kNumSMs;   // every role has a CTA
-        mlp_wgrad_tc_kernel<KIND><<<wgrid, GeoW<KIND>::NTHRW, GeoW<KIND>::SMEM_BYTES, s>>>(grd, reinterpret_cast<const uint8_t*>(ws),
+        mlp_wgrad_tc_kernel<KIND><<<wgrid, GeoW<KIND>::NTHRW, GeoW<KIND>::SMEM_BYTES, w>>>(grd, reinterpret_cast<const uint8_t*>(ws),
                                                                             num_tiles, maxbits);
     }
     return 0;
@@ -901,7 +911,8 @@ extern "C" int hps_mlp_tc_bwd_pack(int kind, const float* const* params, void* p
 
 extern "C" int hps_mlp_tc_bwd(int kind, const float* const* params, const void* packed, void* ws, const float* p,
                               const float* affine, const float* dout, int64_t P, float* const* dparams, float* dc,
-                              float* dp, float* daffine, int absmax_done, int max_ctas, void* stream) {
+                              float* dp, float* daffine, int absmax_done, int max_ctas, void* wgrad_stream,
+                              void* stream) {
     using namespace hps;
     HPS_REQUIRE(kind == HPS_MLP_GEO || kind == HPS_MLP_COL, "bad decoder kind");
     HPS_REQUIRE(P >= 0, "negative point count");
@@ -909,9 +920,11 @@ extern "C" int hps_mlp_tc_bwd(int kind, const float* const* params, const void* 
     HPS_REQUIRE(params && packed && ws && p && dout && dc, "null buffer");
     for (int i = 0; i < HPS_MLP_NPARAM; ++i) HPS_REQUIRE(params[i] != nullptr, "null parameter pointer");
     int rc = kind == HPS_MLP_GEO ? tc::launch_bwd<HPS_MLP_GEO>(params, packed, ws, p, affine, dout, P, dparams, dc, dp,
-                                                               daffine, absmax_done, max_ctas, (cudaStream_t)stream)
+                                                               daffine, absmax_done, max_ctas, (cudaStream_t)wgrad_stream,
+                                                               (cudaStream_t)stream)
                                  : tc::launch_bwd<HPS_MLP_COL>(params, packed, ws, p, affine, dout, P, dparams, dc, dp,
-                                                               daffine, absmax_done, max_ctas, (cudaStream_t)stream);
+                                                               daffine, absmax_done, max_ctas, (cudaStream_t)wgrad_stream,
+                                                               (cudaStream_t)stream);
     if (rc) return rc;
     HPS_LAUNCH_OK();
     return 0;

@@ -29,8 +29,8 @@ MULTI_STREAM = os.environ.get("HPS_STREAMS", "1") != "0"
 _side_streams = {}
 
 
-def _side_stream(dev):
-    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+def _side_stream(dev, which=0):
+    key = (torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device(), which)
     s = _side_streams.get(key)
     if s is None:
         s = torch.cuda.Stream(device=dev)
@@ -176,8 +176,9 @@ class VoxelHashGrid:
                                              ctypes.byref(cell), ctypes.byref(st), _stream()))
         return dict(n_points=n.value, table_size=T.value, n_cells=nc.value, cell_size=cell.value, status=st.value)
 
-    def query(self, q, t_up, t_dn, want_cand=False):
-        """q (Q,3) -> I (Q,8) int32, D (Q,8) f32, count (Q,) int32 [, cand (Q,) int32]."""
+    def query(self, q, t_up, t_dn, want_cand=False, group=1):
+        """q (Q,3) -> I (Q,8) int32, D (Q,8) f32, count (Q,) int32 [, cand (Q,) int32].  group=5: consecutive
+        queries in fives (the samples of a ray) share one sweep; the result is the same."""
         _need_cuda(q, t_up, t_dn)
         q = _f32c(q).reshape(-1, 3)
         Q = q.shape[0]
@@ -187,7 +188,7 @@ class VoxelHashGrid:
         cand = torch.empty(Q, dtype=torch.int32, device=q.device) if want_cand else None
         with torch.cuda.device(q.device):
             _call("hps_knn_query", self._h, _lib.ptr(q), _lib.ptr(t_up), _lib.ptr(t_dn), Q,
-                                                 _lib.ptr(I), _lib.ptr(D), _lib.ptr(cnt), _lib.ptr(cand), _stream())
+                  _lib.ptr(I), _lib.ptr(D), _lib.ptr(cnt), _lib.ptr(cand), int(group), _stream())
         return (I, D, cnt, cand) if want_cand else (I, D, cnt)
 
 
@@ -308,6 +309,10 @@ def _new_bwd_images(kind, dev):
 
 
 N_SM = 148
+# Ray-grouped neighbour search (one warp answers the 5 samples of a ray) trades parallelism for shared probes and
+# loads: measured on the bench cloud (scripts/knn_group_bench.py) 55 vs 47 us at 25,000 queries (too few warps to
+# hide latency), 143 vs 152 us at 100,000, 269 vs 292 us at 200,000.
+KNN_GROUP_MIN_QUERIES = 100000
 # per-tile cost of the colour decoder relative to the geometry decoder (measured: 27/16 us forward, 40/21 us dgrad)
 _COST_RATIO = {"fwd": 1.7, "bwd": 1.9}
 
@@ -380,7 +385,7 @@ def _absmax_word(kind, packed):
 
 
 def _mlp_backward(kind, prm, saved_kind, saved, p_c, c_c, aff, dout, P, dprm, dc, need_dp, daff, dev, stream=None,
-                  dp=None, packed=None, absmax_done=False, max_ctas=0):
+                  dp=None, packed=None, absmax_done=False, max_ctas=0, wgrad_stream=None):
     """Backward of one decoder on `stream`; returns dp (P,3) or None.  dprm: list of gradient buffers (or None).
     dp: preallocated _mlp_dp_buffer (required when `stream` is not the current stream); packed: backward weight
     images built at forward time by _mlp_pack (None: build them now)."""
@@ -395,7 +400,7 @@ def _mlp_backward(kind, prm, saved_kind, saved, p_c, c_c, aff, dout, P, dprm, dc
             _call("hps_mlp_tc_bwd_pack", kind, arr, _lib.ptr(pk), _stream(stream))
         _call("hps_mlp_tc_bwd", kind, arr, _lib.ptr(pk), _lib.ptr(saved), _lib.ptr(p_c), _lib.ptr(aff), _lib.ptr(dout), P,
               darr, _lib.ptr(dc), _lib.ptr(dp), _lib.ptr(daff), 1 if (absmax_done and packed is not None) else 0,
-              int(max_ctas), _stream(stream))
+              int(max_ctas), _stream(wgrad_stream) if wgrad_stream is not None else None, _stream(stream))
         return dp
     _call("hps_mlp_bwd", kind, _ptr_array(prm), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), _lib.ptr(saved),
           _lib.ptr(dout), P, darr, _lib.ptr(dc), _lib.ptr(dp), _lib.ptr(daff), _stream(stream))
@@ -641,7 +646,7 @@ class _RenderRays(torch.autograd.Function):
                   0.0 if rad_t is not None else float(rad), _lib.ptr(zz), R, S, float(spec.near), float(spec.far),
                   _lib.ptr(z), _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), st())
             _call("hps_knn_query", spec.grid._h, _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), P, _lib.ptr(I),
-                  _lib.ptr(D), _lib.ptr(cnt), None, st())
+                  _lib.ptr(D), _lib.ptr(cnt), None, 5 if (S == 5 and P >= KNN_GROUP_MIN_QUERIES) else 1, st())
             if fork and refreshed is not None:
                 main.wait_event(refreshed)
             _call("hps_interp_fwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(D), _lib.ptr(t_dn), _lib.ptr(cnt),
@@ -719,16 +724,21 @@ class _RenderRays(torch.autograd.Function):
                   _absmax_word(MLP_COL, bpk_c) if folded else None, _absmax_word(MLP_GEO, bpk_g) if folded else None,
                   st())
             dp_c = None
+            wgrad_streams = ()
             if fork:
                 main, side = torch.cuda.current_stream(dev), _side_stream(dev)
                 dp_g, dp_c = zp.get(h_dpg), zp.get(h_dpc)
                 side.wait_stream(main)
                 n_c, n_g = _sm_split(P, "bwd")
+                # the HBM-bound weight-gradient kernels go to streams of their own: the feature scatter below needs
+                # only dc of both decoders and overlaps with them
+                w_c, w_g = _side_stream(dev, 1), _side_stream(dev, 2)
                 _mlp_backward(MLP_COL, cprm, "tc", act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c, need_p, daff, dev, main,
-                              dp_c, packed=ctx.bwd_packed[1], absmax_done=folded, max_ctas=n_c)
+                              dp_c, packed=ctx.bwd_packed[1], absmax_done=folded, max_ctas=n_c, wgrad_stream=w_c)
                 _mlp_backward(MLP_GEO, gprm, "tc", act_g, pts, c_geo, None, d_occ, P, dg, dc_g, need_p, None, dev, side,
-                              dp_g, packed=ctx.bwd_packed[0], absmax_done=folded, max_ctas=n_g)
+                              dp_g, packed=ctx.bwd_packed[0], absmax_done=folded, max_ctas=n_g, wgrad_stream=w_g)
                 main.wait_stream(side)
+                wgrad_streams = (w_c, w_g)
             else:
                 dp_g = _mlp_backward(MLP_GEO, gprm, ctx.saved_kinds[0], act_g, pts, c_geo, None, d_occ, P, dg, dc_g,
                                      need_p, None, dev, dp=zp.get(h_dpg))
@@ -746,6 +756,8 @@ class _RenderRays(torch.autograd.Function):
                     dp += dp_c
                 g_ro, g_rd = torch.empty(R, 3, **f32), torch.empty(R, 3, **f32)
                 _call("hps_sample_rays_bwd", _lib.ptr(dp), _lib.ptr(z), R, S, _lib.ptr(g_ro), _lib.ptr(g_rd), st())
+            for w_s in wgrad_streams:
+                main.wait_stream(w_s)
         gg = [(g if (g is not None and need[7 + i]) else None) for i, g in enumerate(dg)] if dg else [None] * N_PARAM
         if spec.color_stage:
             gcw = [(g if (g is not None and need[7 + N_PARAM + i]) else None) for i, g in enumerate(dcw)] \

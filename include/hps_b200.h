@@ -53,10 +53,12 @@ int hps_grid_info(const hps_grid_t* g, int64_t* n_points, int64_t* table_size, i
  *   I[nq][8]   original point indices, ascending (D, index); unused slots -1
  *   D[nq][8]   fl(fl(dx*dx+dy*dy)+dz*dz) fp32 without FMA; unused slots FLT_MAX
  *   count[nq]  number of slots with D < t_up   (== reference neighbor_num)
- *   cand[nq]   optional (may be NULL): candidates examined per query (for the roofline figure)
+ *   cand[nq]   optional (may be NULL): candidates examined for the query's group (for the roofline figure)
+ *   group      1, or 5: consecutive queries [5g, 5g+5) - the samples of one ray - are answered by one warp that
+ *              shares the voxel probes and candidate loads among them (results are independent of `group`)
  * Slots j < count are bit-identical to the reference's exhaustive search.                           */
 int hps_knn_query(const hps_grid_t* g, const float* q, const float* t_up, const float* t_dn,
-                  int64_t nq, int32_t* I, float* D, int32_t* count, int32_t* cand, void* stream);
+                  int64_t nq, int32_t* I, float* D, int32_t* count, int32_t* cand, int group, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Inverse-distance interpolation (decoder.py:195-272 and :491-559; K2 in SURVEY 2.2).
@@ -119,10 +121,13 @@ int hps_mlp_tc_bwd_pack(int kind, const float* const* params, void* packed, void
  * The backward runs on gradients scaled by a power of two derived from max|dout|; that maximum is reduced into the
  * uint32 word (float bits) at packed + hps_mlp_tc_bwd_packed_bytes(kind) - 16, zeroed by hps_mlp_tc_bwd_pack.
  * absmax_done != 0: the caller has already reduced max|dout| into that word (hps_composite_bwd can do it while
- * it writes dout), so the extra reduction kernel is skipped.                                                   */
+ * it writes dout), so the extra reduction kernel is skipped.  wgrad_stream: stream for the weight-gradient kernel
+ * (ordered after the dgrad kernel through an event); dc / dp / daffine are complete on `stream`, the parameter
+ * gradients on `wgrad_stream`.                                                                                */
 int hps_mlp_tc_bwd(int kind, const float* const* params, const void* packed, void* ws, const float* p,
                    const float* affine, const float* dout, int64_t P, float* const* dparams, float* dc, float* dp,
-                   float* daffine, int absmax_done, int max_ctas, void* stream);
+                   float* daffine, int absmax_done, int max_ctas, void* wgrad_stream /* may be NULL = stream */,
+                   void* stream);
 /* Single-CTA tcgen05 self-test: D[128][N] = A . B^T with fp16 operands staged K-major (major = 0, source
  * [rows][K]) or MN-major (major = 1, source [K][rows]) - pins the shared-memory descriptor encodings.        */
 int hps_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_major, int b_major, void* stream);

@@ -351,3 +351,28 @@ def test_composite_bwd_reports_gradient_maxima(hps):
     torch.cuda.synchronize()
     got = words.view(torch.float32).cpu()
     assert float(got[0]) == float(d_rgb.abs().max()) and float(got[1]) == float(d_occ.abs().max())
+
+
+@pytest.mark.parametrize("Q", [5, 23, 5000])
+def test_knn_ray_grouped_sweep_equals_per_query(hps, Q):
+    """hps_knn_query(group=5) (the samples of a ray share voxel probes and candidate loads) returns bit-identical
+    neighbour lists, distances and counts to group=1, including a ragged last group, dead queries (t_dn < 0 cannot
+    occur through the host API, so: far-away queries) and mixed radii inside a group."""
+    g = torch.Generator().manual_seed(11 + Q)
+    pts = torch.rand(40000, 3, generator=g) * 2 - 1
+    # rays: 5 samples close to each other, like Renderer.py:163-229
+    o = torch.rand((Q + 4) // 5, 1, 3, generator=g) * 2 - 1
+    d = torch.nn.functional.normalize(torch.randn((Q + 4) // 5, 1, 3, generator=g), dim=-1)
+    z = torch.linspace(0.0, 0.12, 5).view(1, 5, 1)
+    q = (o + d * z).reshape(-1, 3)[:Q].contiguous()
+    q[::37] += 50.0                                            # queries with no voxel at all
+    radius = 0.04 + 0.12 * torch.rand(Q, generator=g, dtype=torch.float64)
+    idx = hps.GridIndex(DEV)
+    idx.reset(pts.to(DEV))
+    t_up, t_dn = hps.ops.radius_thresholds(radius.to(DEV), Q, DEV)
+    grid = idx._ensure_grid(t_dn)
+    a = grid.query(q.to(DEV), t_up, t_dn, group=1)
+    b = grid.query(q.to(DEV), t_up, t_dn, group=5)
+    for x, y, name in zip(a, b, ("I", "D", "count")):
+        assert torch.equal(x, y), name
+    assert int(a[2].max()) > 0
