@@ -78,11 +78,20 @@ class GradExchange:
         if self.key is None or len(self.key) != len(self.tensors) or \
                 any(t.grad is None or t.grad.data_ptr() != k[0] for t, k in zip(self.tensors, self.key)):
             self._plan()
-        for sp in self.spans:
-            dist.all_reduce(sp, op=dist.ReduceOp.SUM, group=group)
+        items = list(self.spans)
         if self.bucket:
             torch._foreach_copy_(self.views, self.bucket)
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            items.append(self.flat)
+        # NCCL: all buffers go out as ONE grouped launch (ncclGroupStart/End through the coalescing manager)
+        cm = getattr(dist, "_coalescing_manager", None)
+        if len(items) > 1 and cm is not None and items[0].is_cuda and dist.get_backend(group) == "nccl":
+            with cm(group=group, device=items[0].device, async_ops=False):
+                for t in items:
+                    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        else:
+            for t in items:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        if self.bucket:
             torch._foreach_copy_(self.bucket, self.views)
 
 
