@@ -33,6 +33,7 @@ SIGNATURES = {
     "hps_mlp_tc_fwd": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
     "hps_mlp_tc_ws_bytes": (_i64, [_i32, _i64]),
     "hps_mlp_tc_bwd_packed_bytes": (_i64, [_i32]),
+    "hps_mlp_tc_bwd_absmax_offset": (_i64, [_i32]),
     "hps_mlp_tc_bwd_pack": (_i32, [_i32, _vp, _vp, _vp]),
     "hps_mlp_tc_bwd": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "hps_tc_selftest": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),

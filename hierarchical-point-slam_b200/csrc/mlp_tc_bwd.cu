@@ -1,19 +1,25 @@
-// Decoder MLP backward on tcgen05 tensor cores: a dgrad chain kernel and a streaming wgrad kernel.
+// Decoder MLP backward on tcgen05 tensor cores: a dgrad chain kernel, a streaming wgrad kernel and a small
+// finalisation kernel.
 //
 // Backward of the 5-block decoders (reference: autograd through src/conv_onet/models/decoder.py:316-341 and
-// :583-605).  With y_i = act(a_i) + Wc_i c + bc_i, a_i = W_i x_i + b_i and dy_i the gradient w.r.t. y_i:
-//     da_i = dy_i * act'(a_i)
-//     dgrad :  dx_i = da_i W_i   (-> dy_{i-1} for the hidden columns, -> dE for the embedding columns),
-//              dc  += dy_i Wc_i
-//     wgrad :  dW_i += da_i^T x_i,  db_i += colsum(da_i),  dWc_i += dy_i^T c,  dbc_i += colsum(dy_i)
+// :583-605).  With y_i = act(a_i) + Wc_i c + bc_i, a_i = W_i x_i + b_i, raw = Wo y_4 + bo and dy_i the gradient
+// w.r.t. y_i:
+//     da_i = dy_i * act'(a_i),   dy_{i-1} = da_i W_i[:, hidden],   dE += da_i W_i[:, embedding],   dy_4 = d raw Wo
+//     dW_i = da_i^T x_i,  db_i = colsum(da_i),  dWo = d raw^T y_4,  dbo = colsum(d raw)
+//     dc   = sum_i dy_i Wc_i,   dWc_i = dy_i^T c,   dbc_i = colsum(dy_i)
+// The last line is evaluated WITHOUT ever materialising dy_i as an operand: dy_i = da_{i+1} W_{i+1} (i < 4), so
+//     dc    = sum_{j=1..4} da_j Q_{j-1} + d raw Q_4          Q_{j-1} = W_j[:, hidden] Wc_{j-1},  Q_4 = Wo Wc_4
+//     dWc_i = W_{i+1}[:, hidden]^T (da_{i+1}^T c),           dWc_4 = Wo^T (d raw^T c)
+//     dbc_i = db_{i+1} W_{i+1}[:, hidden],                   dbc_4 = dbo Wo
+// Q is folded into the packed weight image (the dc term rides along the dx MMAs as 32 extra B rows), the small
+// products on the second and third line are done by mlp_wfinal_kernel from (H x 32) sums the wgrad kernel leaves in
+// a scratch area.  Only da_i is kept in shared memory and dumped: half the operand traffic and half the MMAs of
+// the first edition, one conversion instead of two in the epilogue.
+//
 // mlp_dgrad_tc_kernel walks the chain 4..0 per 128-point tile with the same warp-specialised structure as the
-// forward (producer / one MMA lane / 8 epilogue warps): dx and dc accumulate in TMEM, the epilogue turns
-// dx into dy_{i-1}, da_{i-1} (act' from the saved pre-activations), writes them as the next A operands into
-// shared memory and dumps them as fp16 hi/lo slab images for the wgrad kernel; bias gradients are warp column
-// sums.  mlp_wgrad_tc_kernel streams the slab images (da_i, dy_i from dgrad; x_i, c from the forward) with
-// cp.async.bulk and contracts over the points with MN-major operands (the images are stored rows = points, so
-// the contraction dimension is the strided one), accumulating dW_i / dWc_i in TMEM across all tiles of a CTA
-// and flushing once with red.global.add.  Same split-fp16 arithmetic as the forward (three MMAs per product).
+// forward (producer / one MMA lane / 16 epilogue warps / dump warp).  mlp_wgrad_tc_kernel streams the slab images
+// (da_i from dgrad; x_i, c from the forward) with cp.async.bulk and contracts over the points with MN-major
+// operands, accumulating in TMEM across all tiles of a CTA.  Same split-fp16 arithmetic as the forward.
 #include "tc_common.cuh"
 
 namespace hps {
@@ -25,7 +31,7 @@ int set_trace_bwd(void* buf) {
     return 0;
 }
 
-constexpr int NSTB = 5;   // ring stages of the dgrad kernel
+constexpr int NSTB = 6;   // ring stages of the dgrad kernel
 
 struct GradPtrs {
     float* v[HPS_MLP_NPARAM];
@@ -34,81 +40,125 @@ struct GradPtrs {
 template <int KIND> struct GeoB {
     using C = Cfg<KIND>;
     using G = Geo<KIND>;
-    static constexpr int HS = G::HS, ES = G::ES, H = C::H;
-    static constexpr int SLABS_PER_TILE = 9 + 8 * HS;           // see pack_bwd_kernel
+    static constexpr int HS = G::HS, ES = G::ES, H = C::H, NOUT = C::NOUT;
     static constexpr int NE = 64 * ES;                           // padded embedding width
-    // TMEM columns of the dgrad kernel: dx hidden, dx embedding (layers 3 and 0 accumulate), dc
-    static constexpr int T_H = 0, T_E = H, T_DC = H + NE;
+    static constexpr int NB = H + 32;                            // B rows of a hidden stage: W_j^T (dx) + Q_{j-1}^T (dc)
+    // one ring stage holds either a hidden entry (NB rows x 64 h_out columns) or an embedding entry (HS mini-slabs of
+    // NE rows x 64 columns)
+    static constexpr int STAGE_BYTES = (NB * 128 > NE * 128 * HS) ? NB * 128 : NE * 128 * HS;
+    static_assert(STAGE_BYTES % 1024 == 0, "stage alignment");
+    static constexpr int ENTRIES = 8 * HS + 4;                   // layers 4..1: 2 HS each; layers 3 and 0: + 2
+    static constexpr int64_t IMG_BYTES = (int64_t)ENTRIES * STAGE_BYTES;
+    __host__ __device__ static constexpr int first_entry(int layer) {
+        return layer == 4 ? 0 : layer == 3 ? 2 * HS : layer == 2 ? 4 * HS + 2 : layer == 1 ? 6 * HS + 2 : 8 * HS + 2;
+    }
+    // tail of the image: [max|dout| word, 16 B] then fp32 scratch
+    //   Q4 [NOUT][32] | T [4][H][32] (da_{j}^T c, j = 1..4) | V [NOUT][32] (d raw^T c) | Sdb [4][H] | Sdbo [4]
+    static constexpr int OFF_Q4 = 0, OFF_T = OFF_Q4 + NOUT * 32, OFF_V = OFF_T + 4 * H * 32, OFF_SDB = OFF_V + NOUT * 32,
+                         OFF_SDBO = OFF_SDB + 4 * H, SCRATCH_FLOATS = OFF_SDBO + 4;
+    static constexpr int64_t TOTAL_BYTES = IMG_BYTES + 16 + (int64_t)SCRATCH_FLOATS * 4;
+    // TMEM columns of the dgrad kernel: dx hidden, this layer's dc part, dx embedding (layers 3 and 0 accumulate)
+    static constexpr int T_H = 0, T_DCP = H, T_E = H + 32;
     static constexpr int TMEM_COLS = 256;
-    static_assert(H + NE + 32 <= 256, "TMEM budget");
-    // small fp32 tables in shared memory: Wo [NOUT][H], exposure affine [12], Fourier matrix [3][NF]
-    static constexpr int TAB_FLOATS = C::NOUT * H + 12 + 3 * C::NF + 1;
-    static constexpr int SMEM_BYTES = 1024 + (4 * HS + NSTB) * SLAB + TAB_FLOATS * 4 + 256;
+    static_assert(H + 32 + NE <= 256, "TMEM budget");
+    // small fp32 tables in shared memory: Wo [NOUT][H], exposure affine [12], Fourier matrix [3][NF], Q4 [NOUT][32]
+    static constexpr int TAB_FLOATS = NOUT * H + 12 + 3 * C::NF + NOUT * 32 + 2;
+    static constexpr int SMEM_BYTES = 1024 + 2 * HS * SLAB + NSTB * STAGE_BYTES + TAB_FLOATS * 4 + 256;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     static constexpr int ECPT = NE / CG;                         // embedding columns per epilogue thread
+    __host__ __device__ static const uint32_t* maxbits(const void* img) {
+        return reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(img) + IMG_BYTES);
+    }
+    __host__ __device__ static float* scratch(void* img) {
+        return reinterpret_cast<float*>(static_cast<uint8_t*>(img) + IMG_BYTES + 16);
+    }
 };
 
 // ---------------------------------------------------------------------------------------------- pack
-// Image consumed by the dgrad kernel, per tile, in order i = 4..0:
-//   [Wc_i^T : (lo,s) mini-slabs of 32 rows (c channel) x 64 cols (h), 4 KB each]
-//   i >= 1     : for every h-slab s: [W_i^T hidden hi: rows = hidden input r, cols = h], [.. lo]
-//   i in {0,3} : [W_i^T embedding hi: per h-slab s a mini-slab of NE rows (e index) x 64 cols (h)], [.. lo]
+// Image consumed by the dgrad kernel, per tile, as ENTRIES stage-sized entries in processing order:
+//   layer j = 4..1: for every 64-wide h_out slab s: [hi], [lo] with rows 0..H-1   = W_j[h_out][hidden r]  (B rows = r)
+//                                                           rows H..H+31  = Q_{j-1}[h_out][k]      (B rows = k)
+//                   columns = h_out (the contraction index), K-major SWIZZLE_128B
+//   layers 3 and 0: [embedding hi], [embedding lo]: per h_out slab s a mini-slab of NE rows (e index) x 64 columns
+// Q_{j-1} = W_j[:, hidden] Wc_{j-1} (j = 1..4), fp32, staged in the T area of the scratch (same shape; the backward
+// zeroes that area before it uses it).  One thread per element, 32 consecutive threads share a W row.
 template <int KIND>
-__device__ __forceinline__ int bwd_layer_first_slab(int i) {   // i = 4..0 processing order
-    using B = GeoB<KIND>;
-    int n = 0;
-    for (int j = 4; j > i; --j) n += 1 + (j >= 1 ? 2 * B::HS : 0) + ((j == 0 || j == 3) ? 2 : 0);
-    return n;
+__global__ void pack_q_kernel(Ptrs prm, float* __restrict__ q) {
+    using C = Cfg<KIND>;
+    constexpr int H = C::H, E = C::E;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 4 * H * 32) return;
+    const int j = idx / (H * 32) + 1, ho = (idx / 32) % H, k = idx % 32;
+    const int K = j == 3 ? E + H : H, hoff = j == 3 ? E : 0;
+    const float* w = prm.v[iW(j)] + (int64_t)ho * K + hoff;
+    const float* wc = prm.v[iWc(j - 1)] + k;
+    float acc = 0.f;
+    for (int r = 0; r < H; ++r) acc = fmaf(__ldg(w + r), __ldg(wc + r * kC), acc);
+    q[idx] = acc;
 }
 
 template <int KIND>
 __global__ void pack_bwd_kernel(Ptrs prm, uint16_t* __restrict__ img) {
     using C = Cfg<KIND>;
     using B = GeoB<KIND>;
-    constexpr int H = C::H, E = C::E, HS = B::HS, NE = B::NE;
-    const int total = B::SLABS_PER_TILE * (SLAB / 2);
-    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<uint32_t*>(img + total) = 0u;   // gradient abs-max word
+    constexpr int H = C::H, E = C::E, HS = B::HS, NE = B::NE, NOUT = C::NOUT, STG = B::STAGE_BYTES;
+    const int total = B::ENTRIES * (STG / 2);
+    const float* q = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(img) + B::IMG_BYTES + 16) + B::OFF_T;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-        const int slab = idx / (SLAB / 2);
-        const int byte = (idx % (SLAB / 2)) * 2;
-        int layer = 4;
-        while (layer > 0 && slab >= bwd_layer_first_slab<KIND>(layer - 1)) --layer;
-        const int rel = slab - bwd_layer_first_slab<KIND>(layer);
+        const int entry = idx / (STG / 2);
+        const int byte = (idx % (STG / 2)) * 2;
+        int layer = 0;
+        for (int l = 4; l >= 1; --l)
+            if (entry < B::first_entry(l - 1)) { layer = l; break; }
+        const int rel = entry - B::first_entry(layer);
         const int K = layer == 0 ? E : (layer == 3 ? E + H : H);
+        const int hoff = layer == 3 ? E : 0;                 // first hidden input column of W_layer
         float val = 0.f;
         bool want_lo = false;
-        if (rel == 0) {
-            // Wc^T mini-slabs (4 KB = 32 rows x 128 B)
-            const int mini = byte / 4096, b = byte % 4096;
-            const int row = ((b >> 10) << 3) | ((b >> 7) & 7);
-            const int col = ((((b >> 4) & 7) ^ (row & 7)) << 3) + ((b >> 1) & 7);
-            if (mini < 2 * HS) {
-                want_lo = mini >= HS;
-                const int h = (mini % HS) * 64 + col;
-                if (h < H) val = prm.v[iWc(layer)][h * kC + row];
+        if (layer >= 1 && rel < 2 * HS) {
+            const int s = rel >> 1;
+            want_lo = (rel & 1) != 0;
+            const int row = ((byte >> 10) << 3) | ((byte >> 7) & 7);
+            const int col = ((((byte >> 4) & 7) ^ (row & 7)) << 3) + ((byte >> 1) & 7);
+            const int ho = s * 64 + col;
+            if (ho < H) {
+                const float* w = prm.v[iW(layer)] + (int64_t)ho * K + hoff;
+                if (row < H) {
+                    val = w[row];
+                } else if (row < H + 32) {
+                    val = q[((layer - 1) * H + ho) * 32 + (row - H)];      // Q_{layer-1}[ho][k] from pack_q_kernel
+                }
             }
         } else {
-            const int nh = layer >= 1 ? 2 * HS : 0;
-            if (rel - 1 < nh) {
-                const int s = (rel - 1) / 2;
-                want_lo = ((rel - 1) & 1) != 0;
-                const int row = ((byte >> 10) << 3) | ((byte >> 7) & 7);        // hidden input index r
-                const int col = ((((byte >> 4) & 7) ^ (row & 7)) << 3) + ((byte >> 1) & 7);
-                const int h = s * 64 + col;
-                if (row < H && h < H) val = prm.v[iW(layer)][h * K + (layer == 3 ? E + row : row)];
-            } else {
-                want_lo = (rel - 1 - nh) == 1;
-                const int msz = NE * 128;                                         // bytes per mini-slab
-                const int s = byte / msz, b = byte % msz;
-                const int row = ((b >> 10) << 3) | ((b >> 7) & 7);                // embedding index e
-                const int col = ((((b >> 4) & 7) ^ (row & 7)) << 3) + ((b >> 1) & 7);
-                const int h = s * 64 + col;
-                if (s < HS && row < E && h < H) val = prm.v[iW(layer)][h * K + row];
-            }
+            want_lo = (rel - (layer >= 1 ? 2 * HS : 0)) == 1;
+            const int msz = NE * 128;                                         // bytes per mini-slab
+            const int s = byte / msz, b = byte % msz;
+            const int row = ((b >> 10) << 3) | ((b >> 7) & 7);                // embedding index e
+            const int col = ((((b >> 4) & 7) ^ (row & 7)) << 3) + ((b >> 1) & 7);
+            const int h = s * 64 + col;
+            if (s < HS && row < E && h < H) val = prm.v[iW(layer)][h * K + row];
         }
         uint16_t hi, lo;
         split16(val, hi, lo);
         img[idx] = want_lo ? lo : hi;
+    }
+    // tail: max|dout| word = 0, Q4 = Wo Wc_4, remaining scratch = 0 (the backward re-zeroes it before every use)
+    uint8_t* tail = reinterpret_cast<uint8_t*>(img) + B::IMG_BYTES;
+    float* scr = reinterpret_cast<float*>(tail + 16);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 + B::SCRATCH_FLOATS; i += gridDim.x * blockDim.x) {
+        if (i < 4) {
+            reinterpret_cast<uint32_t*>(tail)[i] = 0u;
+        } else {
+            const int j = i - 4;
+            if (j < NOUT * 32) {
+                const int o = j / 32, k = j % 32;
+                float v = 0.f;
+                for (int h = 0; h < H; ++h) v = fmaf(prm.v[iWo][o * H + h], prm.v[iWc(4)][h * kC + k], v);
+                scr[j] = v;
+            } else if (j >= B::OFF_V) {
+                scr[j] = 0.f;          // [OFF_T, OFF_V) holds the staged Q (read above by other threads)
+            }
+        }
     }
 }
 
@@ -143,10 +193,6 @@ template <bool RELU> __device__ __forceinline__ float act_grad(float a) {
     return rcp_ftz(1.0f + z);
 }
 
-__device__ __forceinline__ uint4 pack8(const uint16_t* v) {
-    return make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
-}
-
 // MN-major SWIZZLE_128B descriptor for an operand stored rows = contraction index (points), 64 columns per slab:
 // LBO = byte distance between consecutive 64-column slabs, SBO = 1024 (8-row groups along the contraction).
 __device__ __forceinline__ uint64_t smem_desc_mn(uint32_t saddr, uint32_t lbo) {
@@ -157,6 +203,7 @@ __host__ __device__ constexpr uint32_t instr_desc_mn(int M, int N) {   // both o
     return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+
 // ---------------------------------------------------------------------------------------------- dgrad
 __device__ __forceinline__ float ldg_pinned(const float* p) {   // a load the compiler may neither sink nor re-issue
     float v;
@@ -164,32 +211,27 @@ __device__ __forceinline__ float ldg_pinned(const float* p) {   // a load the co
     return v;
 }
 
-// Data gradients of one decoder: the chain dy_4 -> da_4 -> dy_3 ... runs layer by layer on the tensor cores
-// (dx_i = da_i W_i, dc += dy_i Wc_i), the epilogue warps turn each dx into the next layer's operands and dump
-// them (fp16 hi/lo slab images) for the weight-gradient kernel.  Everything that is a sum over points - dW, dWc,
-// db, dbc, dWo - is left to mlp_wgrad_tc_kernel.
 template <int KIND>
 __global__ void __launch_bounds__(NTHR, 1)
-mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, uint8_t* __restrict__ ws,
+mlp_dgrad_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, uint8_t* __restrict__ ws,
                     const float* __restrict__ p, const float* __restrict__ affine,
                     const float* __restrict__ dout, int64_t P, int num_tiles, float* __restrict__ dc,
-                    float* __restrict__ dp, float* __restrict__ daffine) {
+                    float* __restrict__ dp, float* __restrict__ daffine, float* __restrict__ dB, int want_w) {
     using C = Cfg<KIND>;
     using G = Geo<KIND>;
     using B = GeoB<KIND>;
     using W = Ws<KIND>;
-    constexpr int H = C::H, E = C::E, NF = C::NF, NOUT = C::NOUT, HS = G::HS, NE = B::NE;
+    constexpr int H = C::H, E = C::E, NF = C::NF, NOUT = C::NOUT, HS = G::HS, NE = B::NE, STG = B::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sDYhi = smem;
-    uint8_t* sDYlo = sDYhi + HS * SLAB;
-    uint8_t* sDAhi = sDYlo + HS * SLAB;
+    uint8_t* sDAhi = smem;
     uint8_t* sDAlo = sDAhi + HS * SLAB;
     uint8_t* sW = sDAlo + HS * SLAB;
-    float* sWo = reinterpret_cast<float*>(sW + NSTB * SLAB);        // [NOUT][H]
+    float* sWo = reinterpret_cast<float*>(sW + NSTB * STG);         // [NOUT][H]
     float* sAff = sWo + NOUT * H;                                   // [12]
     float* sB = sAff + 12;                                          // [3][NF]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + 3 * NF + ((NOUT * H + 3 * NF) & 1));
+    float* sQ4 = sB + 3 * NF;                                       // [NOUT][32]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sQ4 + NOUT * 32 + ((NOUT * H + 3 * NF + NOUT * 32) & 1));
     uint64_t* full = bars;
     uint64_t* empty = bars + NSTB;
     uint64_t* a_ready = bars + 2 * NSTB;
@@ -197,8 +239,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
     uint64_t* dump_done = bars + 2 * NSTB + 2;     // dump warp -> epilogue: operand slabs copied out, reusable
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTB + 3);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const bool want_w = grd.v[iWo] != nullptr;
-    const float gS = grad_scale(reinterpret_cast<const uint32_t*>(wimg + (size_t)B::SLABS_PER_TILE * SLAB));
+    const float gS = grad_scale(B::maxbits(wimg));
     const float gInv = 1.0f / gS;
 
     if (threadIdx.x == 0) {
@@ -216,10 +257,14 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                      "r"((uint32_t)B::TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
-    for (int i = threadIdx.x; i < NOUT * H; i += NTHR) sWo[i] = prm.v[iWo][i];
-    for (int i = threadIdx.x; i < 3 * NF; i += NTHR) sB[i] = prm.v[0][i];
-    if (threadIdx.x < 12 && affine != nullptr) sAff[threadIdx.x] = affine[threadIdx.x];
-    for (int i = threadIdx.x; i < 4 * HS * SLAB / 16; i += NTHR) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    {
+        const float* q4 = reinterpret_cast<const float*>(wimg + B::IMG_BYTES + 16) + B::OFF_Q4;
+        for (int i = threadIdx.x; i < NOUT * H; i += NTHR) sWo[i] = prm.v[iWo][i];
+        for (int i = threadIdx.x; i < 3 * NF; i += NTHR) sB[i] = prm.v[0][i];
+        for (int i = threadIdx.x; i < NOUT * 32; i += NTHR) sQ4[i] = q4[i];
+        if (threadIdx.x < 12 && affine != nullptr) sAff[threadIdx.x] = affine[threadIdx.x];
+    }
+    for (int i = threadIdx.x; i < 2 * HS * SLAB / 16; i += NTHR) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -229,22 +274,21 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
     if (warp == 0) {
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            for (int j = 0; j < B::SLABS_PER_TILE; ++j, ++it) {
+            for (int j = 0; j < B::ENTRIES; ++j, ++it) {
                 const int st = it % NSTB;
                 mbar_wait(&empty[st], ((it / NSTB) & 1) ^ 1);
                 if (elect_one()) {
-                    mbar_expect_tx(&full[st], SLAB);
-                    bulk_g2s(sW + st * SLAB, wimg + (size_t)j * SLAB, SLAB, &full[st]);
+                    mbar_expect_tx(&full[st], STG);
+                    bulk_g2s(sW + st * STG, wimg + (size_t)j * STG, STG, &full[st]);
                 }
                 __syncwarp();
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t ID_H = instr_desc(FMT_F16, FMT_F16, TILE, H);
+        constexpr uint32_t ID_H = instr_desc(FMT_F16, FMT_F16, TILE, B::NB);      // dx (H columns) + dc part (32)
         constexpr uint32_t ID_E = instr_desc(FMT_F16, FMT_F16, TILE, NE);
-        constexpr uint32_t ID_C = instr_desc(FMT_F16, FMT_F16, TILE, 32);
-        const uint32_t t_h = tmem + B::T_H, t_e = tmem + B::T_E, t_dc = tmem + B::T_DC;
-        const uint32_t aDYh = smem_u32(sDYhi), aDYl = smem_u32(sDYlo), aDAh = smem_u32(sDAhi), aDAl = smem_u32(sDAlo);
+        const uint32_t t_h = tmem + B::T_H, t_e = tmem + B::T_E;
+        const uint32_t aDAh = smem_u32(sDAhi), aDAl = smem_u32(sDAlo);
         const uint32_t aW = smem_u32(sW);
         constexpr int NK = G::ksteps(G::HCOLS);
         uint32_t it = 0, nready = 0;
@@ -257,29 +301,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 ++nready;
                 tc_fence_after();
                 trace_stamp(tr, ts++);
-                {   // dc += dy_i . Wc_i
-                    const int st = it % NSTB;
-                    mbar_wait(&full[st], (it / NSTB) & 1);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t w = aW + st * SLAB;
-#pragma unroll 1
-                        for (int s = 0; s < HS; ++s) {
-#pragma unroll 1
-                            for (int k = 0; k < NK; ++k) {
-                                const uint64_t ah = smem_desc(aDYh + s * SLAB + k * 32), al = smem_desc(aDYl + s * SLAB + k * 32);
-                                const uint64_t bh = smem_desc(w + s * 4096 + k * 32), bl = smem_desc(w + (HS + s) * 4096 + k * 32);
-                                tc_mma(t_dc, ah, bh, ID_C, (layer < 4 || s > 0 || k > 0) ? 1u : 0u);
-                                tc_mma(t_dc, ah, bl, ID_C, 1u);
-                                tc_mma(t_dc, al, bh, ID_C, 1u);
-                            }
-                        }
-                        tc_commit(&empty[st]);
-                    }
-                    __syncwarp();
-                    ++it;
-                }
-                if (layer >= 1) {   // dx (hidden columns) = da_i . W_i[:, hidden]
+                if (layer >= 1) {   // [dx | dc part] = da_j . [W_j[:, hidden] | Q_{j-1}]
 #pragma unroll 1
                     for (int s = 0; s < HS; ++s) {
                         const int st_hi = it % NSTB;
@@ -290,7 +312,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                         ++it;
                         tc_fence_after();
                         if (elect_one()) {
-                            const uint32_t wh = aW + st_hi * SLAB, wl = aW + st_lo * SLAB;
+                            const uint32_t wh = aW + st_hi * STG, wl = aW + st_lo * STG;
 #pragma unroll 1
                             for (int k = 0; k < NK; ++k) {
                                 const uint64_t ah = smem_desc(aDAh + s * SLAB + k * 32), al = smem_desc(aDAl + s * SLAB + k * 32);
@@ -314,7 +336,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                     ++it;
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t wh = aW + st_hi * SLAB, wl = aW + st_lo * SLAB;
+                        const uint32_t wh = aW + st_hi * STG, wl = aW + st_lo * STG;
 #pragma unroll 1
                         for (int s = 0; s < HS; ++s) {
 #pragma unroll 1
@@ -339,7 +361,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
             }
         }
     } else if (warp == DUMP_WARP) {
-        // ================= dump warp: dy_i / da_i operand slabs -> workspace (for the weight-gradient kernel) =========
+        // ================= dump warp: da_i operand slabs -> workspace (for the weight-gradient kernel) =========
         uint32_t nready = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             uint8_t* gg = W::g_ptr(ws, tile);
@@ -349,9 +371,9 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 ++nready;
                 if (want_w) {
                     if (elect_one()) {
-                        // shared order dy_hi dy_lo da_hi da_lo == workspace order g_dy(.,0) g_dy(.,1) g_da(.,0) g_da(.,1)
-                        for (int j = 0; j < 4 * HS; ++j)
-                            bulk_s2g(gg + (size_t)(W::g_dy(layer, 0, 0) + j) * SLAB, sDYhi + j * SLAB, SLAB);
+                        // shared order da_hi[HS] da_lo[HS] == workspace order g_da(layer, 0, .) g_da(layer, 1, .)
+                        for (int j = 0; j < 2 * HS; ++j)
+                            bulk_s2g(gg + (size_t)(W::g_da(layer, 0, 0) + j) * SLAB, sDAhi + j * SLAB, SLAB);
                         bulk_commit();
                         bulk_wait_read();
                     }
@@ -391,36 +413,30 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
 #pragma unroll
                 for (int j = 0; j < CPT; ++j) av[j] = ldg_pinned(ag + (layer * H + col0 + j) * TILE + row);
             };
-            // dy (this thread's hidden columns) of layer `layer` -> da, next A operands, dumps for wgrad
+            // dy (this thread's hidden columns) -> da = dy * act'(a): the next A operand (and the wgrad dump)
             auto emit = [&](const float (&av)[CPT], const float (&dy)[CPT]) {
                 mbar_wait(dump_done, (ndump & 1) ^ 1);      // the previous operands have been copied out
                 ++ndump;
 #pragma unroll
                 for (int q = 0; q < CPT / 8; ++q) {
-                    float d8[8], a8[8];
+                    float a8[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        d8[j] = dy[q * 8 + j];
-                        a8[j] = d8[j] * act_grad<C::RELU>(av[q * 8 + j]);
-                    }
-                    uint4 v0, v1, v2, v3;
-                    split8(d8, v0, v1);
+                    for (int j = 0; j < 8; ++j) a8[j] = dy[q * 8 + j] * act_grad<C::RELU>(av[q * 8 + j]);
+                    uint4 v2, v3;
                     split8(a8, v2, v3);
                     const int colabs = col0 + q * 8;
                     const int slab = colabs >> 6;
                     const uint32_t so = slab_off(row, (colabs & 63) >> 3);
-                    *reinterpret_cast<uint4*>(sDYhi + slab * SLAB + so) = v0;
-                    *reinterpret_cast<uint4*>(sDYlo + slab * SLAB + so) = v1;
                     *reinterpret_cast<uint4*>(sDAhi + slab * SLAB + so) = v2;
                     *reinterpret_cast<uint4*>(sDAlo + slab * SLAB + so) = v3;
                 }
             };
 
-            // ---- output layer (SIMT): d raw, dbo, daffine, dy_4 ----
+            // ---- output layer (SIMT): d raw, daffine, dy_4 ----
+            float dr[3] = {0.f, 0.f, 0.f};
             {
                 float a4[CPT];
                 load_a(4, a4);
-                float dr[3] = {0.f, 0.f, 0.f};
                 if (live) {
 #pragma unroll
                     for (int o = 0; o < NOUT; ++o) dr[o] = __ldg(dout + pt * NOUT + o);
@@ -456,13 +472,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 }
                 trace_stamp(tr, ts++);   // P1: d raw known
                 if (want_w && cgp == 0) {
-#pragma unroll
-                    for (int o = 0; o < NOUT; ++o) {
-                        float s = dr[o];
-                        for (int q = 16; q; q >>= 1) s += __shfl_xor_sync(kFull, s, q);
-                        if (lane == 0) red_add(grd.v[iBo] + o, s);
-                    }
-                    // d raw (scaled) as an operand of the weight-gradient kernel: dWo = y_4^T d raw
+                    // d raw (scaled) as an operand of the weight-gradient kernel: dWo = y_4^T d raw, dbo = 1^T d raw, ...
                     const float d8[8] = {dr[0] * gS, dr[1] * gS, dr[2] * gS, 0.f, 0.f, 0.f, 0.f, 0.f};
                     uint4 vh, vl;
                     split8(d8, vh, vl);
@@ -484,6 +494,10 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
             mbar_arrive(a_ready);
             trace_stamp(tr, ts++);
 
+            // dc: the output-layer term d raw Q_4 (unscaled) + the per-layer parts read from TMEM (scaled)
+            float dcacc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dcacc[j] = 0.f;
 #pragma unroll 1
             for (int layer = 4; layer >= 1; --layer) {
                 float an[CPT];
@@ -495,15 +509,35 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                 float dy[CPT];
                 if constexpr (CPT == 32) tc_ld32(tmem + lane_addr + B::T_H + col0, dy);
                 else tc_ld8(tmem + lane_addr + B::T_H + col0, dy);
+                {
+                    float v[8];
+                    tc_ld8(tmem + lane_addr + B::T_DCP + cgp * 8, v);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dcacc[j] += v[j];
+                }
                 emit(an, dy);
                 tc_fence_before();
                 fence_proxy_async();
                 mbar_arrive(a_ready);
                 trace_stamp(tr, ts++);
             }
-            // ---- end of the chain: dc and the embedding gradient ----
+            {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float s = dcacc[j] * gInv;
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o) s = fmaf(dr[o], sQ4[o * 32 + cgp * 8 + j], s);
+                    v[j] = s;
+                }
+                if (live) {
+                    *reinterpret_cast<float4*>(dc + pt * kC + cgp * 8) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(dc + pt * kC + cgp * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+            // ---- end of the chain: the embedding gradient ----
             float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-            const bool want_b = (KIND == HPS_MLP_GEO) && grd.v[0] != nullptr;
+            const bool want_b = (KIND == HPS_MLP_GEO) && dB != nullptr;
             if ((dp != nullptr || want_b) && live) {
                 x0 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 0));
                 x1 = __fmul_rn(kTwoPi, __ldg(p + pt * 3 + 1));
@@ -513,14 +547,6 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
             ++nacc;
             tc_fence_after();
             trace_stamp(tr, ts++);
-            {
-                float v[8];
-                tc_ld8(tmem + lane_addr + B::T_DC + cgp * 8, v);
-                if (live) {
-                    *reinterpret_cast<float4*>(dc + pt * kC + cgp * 8) = make_float4(v[0] * gInv, v[1] * gInv, v[2] * gInv, v[3] * gInv);
-                    *reinterpret_cast<float4*>(dc + pt * kC + cgp * 8 + 4) = make_float4(v[4] * gInv, v[5] * gInv, v[6] * gInv, v[7] * gInv);
-                }
-            }
             // ---- dE -> dp, dB ----
             if (dp != nullptr || want_b) {
                 float g0 = 0.f, g1 = 0.f, g2 = 0.f;
@@ -556,9 +582,9 @@ mlp_dgrad_tc_kernel(Ptrs prm, GradPtrs grd, const uint8_t* __restrict__ wimg, ui
                         const float s0 = warp_colsum8(gb0, lane), s1 = warp_colsum8(gb1, lane), s2 = warp_colsum8(gb2, lane);
                         const int e = e0 + colsum8_col(lane);
                         if (lane < 8 && e < E) {
-                            red_add(grd.v[0] + e, s0);
-                            red_add(grd.v[0] + NF + e, s1);
-                            red_add(grd.v[0] + 2 * NF + e, s2);
+                            red_add(dB + e, s0);
+                            red_add(dB + NF + e, s1);
+                            red_add(dB + 2 * NF + e, s2);
                         }
                     }
                 }
@@ -587,36 +613,40 @@ template <int KIND> struct GeoW {
     // One pipeline stage = a quarter tile (32 points = two K=16 steps) of every operand of one role, as 4 KB
     // chunks (32 rows x 128 B of a swizzled slab; the swizzle period is 8 rows, so a chunk is itself a valid
     // SWIZZLE_128B MN-major operand with atom stride CH).  Roles 0..4 (layer i):
-    //   A chunks: dy_hi[HS] dy_lo[HS] da_hi[HS] da_lo[HS]        (same order as the G region of the workspace)
+    //   A chunks: da_hi[HS] da_lo[HS]                             (same order as the G region of the workspace)
     //   B chunks: y_hi[HS] e_hi[ES] y_lo[HS] e_lo[ES] c[1]        (so [y | e] is one N = NH+NE operand)
-    // Role 5 (output layer): A chunks y4_hi[HS] y4_lo[HS], B chunks draw_hi draw_lo.
+    // Role 5 (output layer): chunks y4_hi[HS] y4_lo[HS] c draw_hi draw_lo.
     static constexpr int CH = 4096;
-    static constexpr int A_CHUNKS = 4 * HS, B_CHUNKS = 2 * (HS + ES) + 1;
+    static constexpr int A_CHUNKS = 2 * HS, B_CHUNKS = 2 * (HS + ES) + 1;
     static constexpr int STAGE_BYTES = (A_CHUNKS + B_CHUNKS) * CH;
-    static constexpr int NSTW = 3;
+    static constexpr int NSTW = 4;
     static constexpr int NROLE = 6;
-    // + CH: M=128 reads one atom past the last A chunk; + CH: the chunk of ones (bias-gradient column sums)
+    // + CH: M=128 may read one atom past the last chunk; + CH: the chunk of ones (column sums)
     static constexpr int SMEM_BYTES = 1024 + NSTW * STAGE_BYTES + 2 * CH + 256;
-    // TMEM columns: dW hidden [0,NH), dW embedding [NH,NH+NE), dWc as [sum dy*c_hi | sum dy*c_lo] [NH+NE, +64),
-    // db (16 equal columns), dbc (16 equal columns); role 5: dWo^T in columns [0,16)
-    static constexpr int T_WH = 0, T_WE = NH, T_WC = NH + NE, T_B = NH + NE + 64, T_BC = NH + NE + 80;
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+    // TMEM columns: dW hidden [0,NH), dW embedding [NH,NH+NE), T = da^T [c_hi | c_lo] [NH+NE, +64), db (16 equal
+    // columns); role 5: dWo^T [0,16), V^T = c^T d raw [16,32), dbo [32,48)
+    static constexpr int T_WH = 0, T_WE = NH, T_T = NH + NE, T_B = NH + NE + 64;
     static constexpr int TMEM_COLS = 512;
-    static_assert(NH + NE + 96 <= 512, "TMEM budget");
+    static_assert(NH + NE + 80 <= 512, "TMEM budget");
     static constexpr int NTHRW = 320;      // producer warp, MMA warp, 8 flush warps
 };
 
 // Everything that is a sum over the points.  CTA b has role b % 6 and works on every (b / 6)-th tile: it streams
-// the dgrad dumps (da_i, dy_i, d raw) and the forward's operand dumps (y_i, embedding, c) through a 3-stage
+// the dgrad dumps (da_i, d raw) and the forward's operand dumps (y_i, embedding, c) through a 4-stage
 // quarter-tile ring and accumulates over all its tiles in TMEM (contraction over the points: both operands
 // MN-major)
-//     roles 0..4:  dW_i = da_i^T [y_{i-1} | e],  dWc_i = dy_i^T c,  db_i = da_i^T 1,  dbc_i = dy_i^T 1
-//     role 5:      dWo^T = y_4^T d raw
-// then adds its partial sums to the gradient buffers (red.global.add, 16-byte vectors where the pitch allows).
+//     roles 0..4:  dW_i = da_i^T [y_{i-1} | e],  db_i = da_i^T 1,  T_i = da_i^T c  (i >= 1, for dWc_{i-1})
+//     role 5:      dWo^T = y_4^T d raw,  V^T = c^T d raw (for dWc_4),  dbo = d raw^T 1
+// then adds its partial sums to the gradient buffers / the scratch area (red.global.add, 16-byte vectors where the
+// pitch allows).
 template <int KIND>
 __global__ void __launch_bounds__(GeoW<KIND>::NTHRW, 1)
-mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles, const uint32_t* __restrict__ maxbits) {
+mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles, const uint32_t* __restrict__ maxbits,
+                    float* __restrict__ scratch) {
     using C = Cfg<KIND>;
     using GW = GeoW<KIND>;
+    using GB = GeoB<KIND>;
     using W = Ws<KIND>;
     constexpr int H = C::H, E = C::E, NOUT = C::NOUT, HS = GW::HS, ES = GW::ES, NH = GW::NH, NE = GW::NE, CH = GW::CH,
                   NSTW = GW::NSTW;
@@ -633,7 +663,7 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
     const int layer = role;                                   // roles 0..4
     const int rank = blockIdx.x / GW::NROLE;
     const int gsize = ((int)gridDim.x - role + GW::NROLE - 1) / GW::NROLE;     // CTAs with this role
-    const bool has_h = role >= 1 && role < 5, has_e = (role == 0 || role == 3);
+    const bool has_h = role >= 1 && role < 5, has_e = (role == 0 || role == 3), has_c = role >= 1;
     const bool mine = rank < num_tiles;
 
     if (threadIdx.x == 0) {
@@ -662,8 +692,8 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
 
     if (warp == 0) {
         // ---- producer ----
-        const uint32_t bytes = role == 5 ? (uint32_t)CH * (2 * HS + 2)
-                                         : (uint32_t)CH * (4 * HS + (has_h ? 2 * HS : 0) + (has_e ? 2 * ES : 0) + 1);
+        const uint32_t bytes = role == 5 ? (uint32_t)CH * (2 * HS + 3)
+                                         : (uint32_t)CH * (2 * HS + (has_h ? 2 * HS : 0) + (has_e ? 2 * ES : 0) + (has_c ? 1 : 0));
         uint32_t it = 0;
         for (int tile = rank; tile < num_tiles; tile += gsize) {
             const uint8_t* xg = W::x_ptr(const_cast<uint8_t*>(ws), tile);
@@ -678,11 +708,12 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
                     if (role == 5) {
                         for (int j = 0; j < 2 * HS; ++j)      // y4 hi[HS], lo[HS] are consecutive X slabs
                             bulk_g2s(sa + j * CH, xg + (size_t)(W::x_y(4, 0, 0) + j) * SLAB + q * CH, CH, &full[st]);
-                        bulk_g2s(sb, gt + (size_t)W::g_dr(0) * SLAB + q * CH, CH, &full[st]);
-                        bulk_g2s(sb + CH, gt + (size_t)W::g_dr(1) * SLAB + q * CH, CH, &full[st]);
+                        bulk_g2s(sb, xg + (size_t)W::x_c() * SLAB + q * CH, CH, &full[st]);
+                        bulk_g2s(sb + CH, gt + (size_t)W::g_dr(0) * SLAB + q * CH, CH, &full[st]);
+                        bulk_g2s(sb + 2 * CH, gt + (size_t)W::g_dr(1) * SLAB + q * CH, CH, &full[st]);
                     } else {
-                        const uint8_t* gg = gt + (size_t)W::g_dy(layer, 0, 0) * SLAB;
-                        for (int j = 0; j < 4 * HS; ++j) bulk_g2s(sa + j * CH, gg + (size_t)j * SLAB + q * CH, CH, &full[st]);
+                        const uint8_t* gg = gt + (size_t)W::g_da(layer, 0, 0) * SLAB;
+                        for (int j = 0; j < 2 * HS; ++j) bulk_g2s(sa + j * CH, gg + (size_t)j * SLAB + q * CH, CH, &full[st]);
                         if (has_h) {
                             for (int s2 = 0; s2 < HS; ++s2) {
                                 bulk_g2s(sb + s2 * CH, xg + (size_t)W::x_y(layer - 1, 0, s2) * SLAB + q * CH, CH, &full[st]);
@@ -697,7 +728,7 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
                                          &full[st]);
                             }
                         }
-                        bulk_g2s(sb + 2 * (HS + ES) * CH, xg + (size_t)W::x_c() * SLAB + q * CH, CH, &full[st]);
+                        if (has_c) bulk_g2s(sb + 2 * (HS + ES) * CH, xg + (size_t)W::x_c() * SLAB + q * CH, CH, &full[st]);
                     }
                 }
                 __syncwarp();
@@ -708,8 +739,7 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
         const int nW = (has_h ? NH : 0) + (has_e ? NE : 0);
         const uint32_t id_w = instr_desc_mn(TILE, nW > 0 ? nW : 16), id_c = instr_desc_mn(TILE, 64);
         const uint32_t id_16 = instr_desc_mn(TILE, 16);
-        const uint32_t t_w = tmem + (has_h ? GW::T_WH : GW::T_WE), t_c = tmem + GW::T_WC;
-        const uint32_t t_b = tmem + GW::T_B, t_bc = tmem + GW::T_BC;
+        const uint32_t t_w = tmem + (has_h ? GW::T_WH : GW::T_WE), t_t = tmem + GW::T_T, t_b = tmem + GW::T_B;
         const uint32_t b_off = (uint32_t)(has_h ? 0 : HS) * CH;       // layer 0: B starts at the embedding chunks
         const uint64_t ones = smem_desc_mn(smem_u32(sOnes), CH);
         uint32_t it = 0;
@@ -726,26 +756,29 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
                         const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
                         if (role == 5) {
                             const uint64_t yh = smem_desc_mn(sa + k * 2048, CH), yl = smem_desc_mn(sa + HS * CH + k * 2048, CH);
-                            const uint64_t rh = smem_desc_mn(sb + k * 2048, CH), rl = smem_desc_mn(sb + CH + k * 2048, CH);
-                            tc_mma(tmem, yh, rh, id_16, acc);
+                            const uint64_t cc = smem_desc_mn(sb + k * 2048, CH);
+                            const uint64_t rh = smem_desc_mn(sb + CH + k * 2048, CH), rl = smem_desc_mn(sb + 2 * CH + k * 2048, CH);
+                            tc_mma(tmem, yh, rh, id_16, acc);           // dWo^T
                             tc_mma(tmem, yh, rl, id_16, 1u);
                             tc_mma(tmem, yl, rh, id_16, 1u);
+                            tc_mma(tmem + 16, cc, rh, id_16, acc);      // V^T: lanes = [c_hi | c_lo] columns
+                            tc_mma(tmem + 16, cc, rl, id_16, 1u);
+                            tc_mma(tmem + 32, rh, ones, id_16, acc);    // dbo: lanes = output channel
+                            tc_mma(tmem + 32, rl, ones, id_16, 1u);
                         } else {
-                            const uint64_t dyh = smem_desc_mn(sa + k * 2048, CH), dyl = smem_desc_mn(sa + HS * CH + k * 2048, CH);
-                            const uint64_t dah = smem_desc_mn(sa + 2 * HS * CH + k * 2048, CH);
-                            const uint64_t dal = smem_desc_mn(sa + 3 * HS * CH + k * 2048, CH);
+                            const uint64_t dah = smem_desc_mn(sa + k * 2048, CH), dal = smem_desc_mn(sa + HS * CH + k * 2048, CH);
                             const uint64_t bh = smem_desc_mn(sb + b_off + k * 2048, CH);
                             const uint64_t bl = smem_desc_mn(sb + (HS + ES) * CH + b_off + k * 2048, CH);
-                            const uint64_t bc = smem_desc_mn(sb + 2 * (HS + ES) * CH + k * 2048, CH);
                             tc_mma(t_w, dah, bh, id_w, acc);
                             tc_mma(t_w, dah, bl, id_w, 1u);
                             tc_mma(t_w, dal, bh, id_w, 1u);
-                            tc_mma(t_c, dyh, bc, id_c, acc);      // c chunk = [c_hi | c_lo]: the halves are summed at flush
-                            tc_mma(t_c, dyl, bc, id_c, 1u);
-                            tc_mma(t_b, dah, ones, id_16, acc);   // bias gradients: column sums over the points
+                            if (has_c) {
+                                const uint64_t bc = smem_desc_mn(sb + 2 * (HS + ES) * CH + k * 2048, CH);
+                                tc_mma(t_t, dah, bc, id_c, acc);      // c chunk = [c_hi | c_lo]: the halves are summed at flush
+                                tc_mma(t_t, dal, bc, id_c, 1u);
+                            }
+                            tc_mma(t_b, dah, ones, id_16, acc);       // bias gradient: column sums over the points
                             tc_mma(t_b, dal, ones, id_16, 1u);
-                            tc_mma(t_bc, dyh, ones, id_16, acc);
-                            tc_mma(t_bc, dyl, ones, id_16, 1u);
                         }
                     }
                     tc_commit(&empty[st]);
@@ -767,19 +800,29 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
         const float gInv = 1.0f / grad_scale(maxbits);
         if (role == 5) {
             if (half == 0) {
-                float v[8];
+                float v[8], b[8];
                 tc_ld8(tmem + lane_addr, v);
+                tc_ld8(tmem + lane_addr + 32, b);
                 if (h < H) {
 #pragma unroll
                     for (int o = 0; o < NOUT; ++o) red_add(grd.v[iWo] + o * H + h, v[o] * gInv);
+                }
+                if (h < NOUT) {
+                    red_add(grd.v[iBo] + h, b[0] * gInv);
+                    red_add(scratch + GB::OFF_SDBO + h, b[0] * gInv);
+                }
+            } else {
+                float v[8];
+                tc_ld8(tmem + lane_addr + 16, v);
+                if (h < 64) {       // lane = column of the c slab: hi part 0..31, lo part 32..63
+#pragma unroll
+                    for (int o = 0; o < NOUT; ++o) red_add(scratch + GB::OFF_V + o * 32 + (h & 31), v[o] * gInv);
                 }
             }
         } else {
             const int K = layer == 0 ? E : (layer == 3 ? E + H : H);
             float* gw = grd.v[iW(layer)];
-            float* gwc = grd.v[iWc(layer)];
             const bool vec_w = ((reinterpret_cast<uintptr_t>(gw) & 15) == 0) && (K % 4 == 0) && (E % 4 == 0);
-            const bool vec_c = (reinterpret_cast<uintptr_t>(gwc) & 15) == 0;
             auto flush16 = [&](float* dst, const float (&v)[16], int n_valid, bool vec) {     // dst: this row, 16 columns
                 if (vec && n_valid == 16) {
 #pragma unroll
@@ -807,18 +850,21 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
                     if (h < H && nv > 0) flush16(gw + (int64_t)h * K + cb, v, nv, vec_w);
                 }
             }
-            {
+            if (has_c) {   // T_layer[h][k] = sum_pt da[pt][h] c[pt][k]  ->  scratch (dWc_{layer-1} = W_layer^T T_layer)
                 float v[16], v2[16];
-                tc_ld16(tmem + lane_addr + GW::T_WC + half * 16, v);
-                tc_ld16(tmem + lane_addr + GW::T_WC + 32 + half * 16, v2);
+                tc_ld16(tmem + lane_addr + GW::T_T + half * 16, v);
+                tc_ld16(tmem + lane_addr + GW::T_T + 32 + half * 16, v2);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] += v2[j];
-                if (h < H) flush16(gwc + (int64_t)h * kC + half * 16, v, 16, vec_c);
+                if (h < H) flush16(scratch + GB::OFF_T + ((layer - 1) * H + h) * 32 + half * 16, v, 16, true);
             }
-            {
+            if (half == 0) {
                 float v[8];
-                tc_ld8(tmem + lane_addr + (half == 0 ? GW::T_B : GW::T_BC), v);
-                if (h < H) red_add((half == 0 ? grd.v[iB(layer)] : grd.v[iBc(layer)]) + h, v[0] * gInv);
+                tc_ld8(tmem + lane_addr + GW::T_B, v);
+                if (h < H) {
+                    red_add(grd.v[iB(layer)] + h, v[0] * gInv);
+                    if (layer >= 1) red_add(scratch + GB::OFF_SDB + (layer - 1) * H + h, v[0] * gInv);
+                }
             }
         }
     }
@@ -829,10 +875,48 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
     }
 }
 
+// dWc_i = W_{i+1}[:, hidden]^T T_{i+1},  dbc_i = db_{i+1} W_{i+1}[:, hidden]  (i = 0..3);  dWc_4 = Wo^T V,  dbc_4 = dbo Wo.
+// One thread per output element; 128-term dot products over L2-resident weights.
+template <int KIND>
+__global__ void mlp_wfinal_kernel(Ptrs prm, GradPtrs grd, const float* __restrict__ scratch) {
+    using C = Cfg<KIND>;
+    using GB = GeoB<KIND>;
+    constexpr int H = C::H, E = C::E, NOUT = C::NOUT;
+    const int per = H * 32 + H;                               // outputs per layer: dWc (H x 32) + dbc (H)
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 5 * per; idx += gridDim.x * blockDim.x) {
+        const int i = idx / per, r = idx % per;
+        const bool bias = r >= H * 32;
+        const int hin = bias ? r - H * 32 : r / 32, k = r % 32;
+        float acc = 0.f;
+        if (i < 4) {
+            const int Kn = (i + 1) == 3 ? E + H : H, off = (i + 1) == 3 ? E : 0;
+            const float* w = prm.v[iW(i + 1)] + off + hin;                    // W_{i+1}[ho][off + hin], pitch Kn
+            if (bias) {
+                const float* sdb = scratch + GB::OFF_SDB + i * H;
+                for (int ho = 0; ho < H; ++ho) acc = fmaf(sdb[ho], w[(int64_t)ho * Kn], acc);
+            } else {
+                const float* t = scratch + GB::OFF_T + i * H * 32 + k;
+                for (int ho = 0; ho < H; ++ho) acc = fmaf(w[(int64_t)ho * Kn], t[ho * 32], acc);
+            }
+        } else {
+            const float* wo = prm.v[iWo] + hin;
+            if (bias) {
+                for (int o = 0; o < NOUT; ++o) acc = fmaf(scratch[GB::OFF_SDBO + o], wo[o * H], acc);
+            } else {
+                for (int o = 0; o < NOUT; ++o) acc = fmaf(wo[o * H], scratch[GB::OFF_V + o * 32 + k], acc);
+            }
+        }
+        if (bias) red_add(grd.v[iBc(i)] + hin, acc);
+        else red_add(grd.v[iWc(i)] + hin * kC + k, acc);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- launch
 template <int KIND> int launch_pack_bwd(const float* const* params, void* img, cudaStream_t s) {
     Ptrs prm;
     for (int i = 0; i < HPS_MLP_NPARAM; ++i) prm.v[i] = params[i];
+    float* q = GeoB<KIND>::scratch(img) + GeoB<KIND>::OFF_T;
+    pack_q_kernel<KIND><<<(4 * Cfg<KIND>::H * 32 + 255) / 256, 256, 0, s>>>(prm, q);
     pack_bwd_kernel<KIND><<<148, 256, 0, s>>>(prm, reinterpret_cast<uint16_t*>(img));
     return 0;
 }
@@ -841,6 +925,7 @@ template <int KIND>
 int launch_bwd(const float* const* params, const void* img, void* ws, const float* p, const float* affine,
                const float* dout, int64_t P, float* const* dparams, float* dc, float* dp, float* daffine,
                int absmax_done, int max_ctas, cudaStream_t wstream, cudaStream_t s) {
+    using GB = GeoB<KIND>;
     Ptrs prm;
     GradPtrs grd;
     for (int i = 0; i < HPS_MLP_NPARAM; ++i) {
@@ -852,7 +937,7 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
     static bool configured = false;
     if (!configured) {
         HPS_CUDA_OK(cudaFuncSetAttribute(mlp_dgrad_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         GeoB<KIND>::SMEM_BYTES));
+                                         GB::SMEM_BYTES));
         HPS_CUDA_OK(cudaFuncSetAttribute(mlp_wgrad_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GeoW<KIND>::SMEM_BYTES));
         configured = true;
@@ -860,19 +945,20 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
     const int num_tiles = (int)ceil_div(P, TILE);
     const int cap = (max_ctas > 0 && max_ctas < kNumSMs) ? max_ctas : kNumSMs;     // dgrad only; wgrad is HBM-bound
     int grid = num_tiles < cap ? num_tiles : cap;
-    uint32_t* maxbits = reinterpret_cast<uint32_t*>(const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(img)) +
-                                                    (size_t)GeoB<KIND>::SLABS_PER_TILE * SLAB);
+    void* img_rw = const_cast<void*>(img);
+    uint32_t* maxbits = const_cast<uint32_t*>(GB::maxbits(img));
+    float* scratch = GB::scratch(img_rw);
     if (!absmax_done) {
         const int64_t n = P * Cfg<KIND>::NOUT;
         const int nb = (int)(ceil_div(n, 1024) < kNumSMs ? ceil_div(n, 1024) : kNumSMs);
         absmax_kernel<<<nb, 1024, 0, s>>>(dout, n, maxbits);
     }
-    mlp_dgrad_tc_kernel<KIND><<<grid, NTHR, GeoB<KIND>::SMEM_BYTES, s>>>(
-        prm, grd, reinterpret_cast<const uint8_t*>(img), reinterpret_cast<uint8_t*>(ws), p, affine, dout, P, num_tiles,
-        dc, dp, daffine);
+    mlp_dgrad_tc_kernel<KIND><<<grid, NTHR, GB::SMEM_BYTES, s>>>(
+        prm, reinterpret_cast<const uint8_t*>(img), reinterpret_cast<uint8_t*>(ws), p, affine, dout, P, num_tiles, dc, dp,
+        daffine, grd.v[0], dparams ? 1 : 0);
     if (dparams) {
-        // The weight-gradient kernel may run on its own stream (ordered after the dgrad kernel by an event), so that
-        // whatever the caller enqueues next on `s` - the feature scatter needs only dc - overlaps with it.
+        // The weight-gradient kernels may run on their own stream (ordered after the dgrad kernel by an event), so
+        // that whatever the caller enqueues next on `s` - the feature scatter needs only dc - overlaps with them.
         cudaStream_t w = s;
         if (wstream != nullptr && wstream != s) {
             static cudaEvent_t dgrad_done = nullptr;          // one per decoder kind (template instantiation)
@@ -881,9 +967,13 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
             HPS_CUDA_OK(cudaStreamWaitEvent(wstream, dgrad_done, 0));
             w = wstream;
         }
+        // the sums of this call only (T, V, Sdb, Sdbo; Q4 stays)
+        HPS_CUDA_OK(cudaMemsetAsync(scratch + GB::OFF_T, 0, (size_t)(GB::SCRATCH_FLOATS - GB::OFF_T) * 4, w));
         const int wgrid = GeoW<KIND>::NROLE * num_tiles < kNumSMs ? GeoW<KIND>::NROLE * num_tiles : kNumSMs;   // every role has a CTA
-        mlp_wgrad_tc_kernel<KIND><<<wgrid, GeoW<KIND>::NTHRW, GeoW<KIND>::SMEM_BYTES, w>>>(grd, reinterpret_cast<const uint8_t*>(ws),
-                                                                            num_tiles, maxbits);
+        mlp_wgrad_tc_kernel<KIND><<<wgrid, GeoW<KIND>::NTHRW, GeoW<KIND>::SMEM_BYTES, w>>>(
+            grd, reinterpret_cast<const uint8_t*>(ws), num_tiles, maxbits, scratch);
+        const int nout = 5 * (Cfg<KIND>::H * 32 + Cfg<KIND>::H);
+        mlp_wfinal_kernel<KIND><<<(nout + 127) / 128, 128, 0, w>>>(prm, grd, scratch);
     }
     return 0;
 }
@@ -893,8 +983,12 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
 
 extern "C" int64_t hps_mlp_tc_bwd_packed_bytes(int kind) {
     using namespace hps::tc;
-    return (kind == HPS_MLP_GEO ? (int64_t)GeoB<HPS_MLP_GEO>::SLABS_PER_TILE * SLAB
-                                : (int64_t)GeoB<HPS_MLP_COL>::SLABS_PER_TILE * SLAB) + 16;   // + gradient abs-max word
+    return kind == HPS_MLP_GEO ? GeoB<HPS_MLP_GEO>::TOTAL_BYTES : GeoB<HPS_MLP_COL>::TOTAL_BYTES;
+}
+
+extern "C" int64_t hps_mlp_tc_bwd_absmax_offset(int kind) {
+    using namespace hps::tc;
+    return kind == HPS_MLP_GEO ? GeoB<HPS_MLP_GEO>::IMG_BYTES : GeoB<HPS_MLP_COL>::IMG_BYTES;
 }
 
 extern "C" int hps_mlp_tc_bwd_pack(int kind, const float* const* params, void* packed, void* stream) {

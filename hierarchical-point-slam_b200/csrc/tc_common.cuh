@@ -231,12 +231,12 @@ __device__ __forceinline__ void split8(const float (&x)[8], uint4& vh, uint4& vl
 //   X   : NX 16-KB slab images (fp16, K-major SWIZZLE_128B, rows = points):
 //           e hi [ES], e lo [ES], c (cols 0..31 hi | 32..63 lo), then for i = 0..4: y_i hi [HS], y_i lo [HS]
 // written by the dgrad kernel, read by the wgrad kernel:
-//   G   : NG slab images: for i = 0..4: dy_i hi [HS], dy_i lo [HS], da_i hi [HS], da_i lo [HS]
+//   G   : NG slab images: for i = 0..4: da_i hi [HS], da_i lo [HS]; then d raw hi, d raw lo
 template <int KIND> struct Ws {
     using G_ = Geo<KIND>;
     static constexpr int HS = G_::HS, ES = G_::ES, H = Cfg<KIND>::H;
     static constexpr int NX = 2 * ES + 1 + 10 * HS;
-    static constexpr int NG = 20 * HS + 2;      // + d raw (hi, lo): columns 0..NOUT-1 of two slabs
+    static constexpr int NG = 10 * HS + 2;      // da_i hi/lo per layer + d raw (hi, lo): columns 0..NOUT-1 of two slabs
     static constexpr size_t A_BYTES = (size_t)5 * H * TILE * 4;
     static constexpr size_t RAW_BYTES = (size_t)TILE * 4 * 4;
     static constexpr size_t X_BYTES = (size_t)NX * SLAB;
@@ -245,9 +245,8 @@ template <int KIND> struct Ws {
     __host__ __device__ static constexpr int x_e(int lo, int s) { return lo * ES + s; }
     __host__ __device__ static constexpr int x_c() { return 2 * ES; }
     __host__ __device__ static constexpr int x_y(int i, int lo, int s) { return 2 * ES + 1 + i * 2 * HS + lo * HS + s; }
-    __host__ __device__ static constexpr int g_dy(int i, int lo, int s) { return i * 4 * HS + lo * HS + s; }
-    __host__ __device__ static constexpr int g_da(int i, int lo, int s) { return i * 4 * HS + 2 * HS + lo * HS + s; }
-    __host__ __device__ static constexpr int g_dr(int lo) { return 20 * HS + lo; }
+    __host__ __device__ static constexpr int g_da(int i, int lo, int s) { return i * 2 * HS + lo * HS + s; }
+    __host__ __device__ static constexpr int g_dr(int lo) { return 10 * HS + lo; }
     __device__ static float* a_ptr(uint8_t* ws, int64_t tile) { return reinterpret_cast<float*>(ws + tile * TILE_BYTES); }
     __device__ static float* raw_ptr(uint8_t* ws, int64_t tile) { return reinterpret_cast<float*>(ws + tile * TILE_BYTES + A_BYTES); }
     __device__ static uint8_t* x_ptr(uint8_t* ws, int64_t tile) { return ws + tile * TILE_BYTES + A_BYTES + RAW_BYTES; }

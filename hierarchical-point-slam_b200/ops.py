@@ -42,7 +42,7 @@ def _side_stream(dev, which=0):
 LAUNCHES = {"n": 0}
 _KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_interp_fwd": 1, "hps_interp_bwd": 1,
                      "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_mlp_tc_pack": 1, "hps_mlp_tc_fwd": 1,
-                     "hps_mlp_tc_bwd_pack": 1, "hps_mlp_tc_bwd": 3, "hps_tc_selftest": 1, "hps_composite_fwd": 1,
+                     "hps_mlp_tc_bwd_pack": 2, "hps_mlp_tc_bwd": 3, "hps_tc_selftest": 1, "hps_composite_fwd": 1,
                      "hps_composite_bwd": 1, "hps_sample_rays": 1, "hps_sample_rays_bwd": 1, "hps_mapper_loss": 1,
                      "hps_tracker_loss_stats": 1, "hps_tracker_loss": 1, "hps_exposure_fwd": 1, "hps_exposure_bwd": 1}
 TIMERS = None   # set to {} to record (start, end) CUDA events per call name on the current stream
@@ -381,7 +381,7 @@ def _mlp_dp_buffer(saved_kind, P, need_dp, dev):
 
 def _absmax_word(kind, packed):
     """Address of the max|dout| word behind a backward weight image (see hps_mlp_tc_bwd in the header)."""
-    return ctypes.c_void_p(packed.data_ptr() + int(_lib.load().hps_mlp_tc_bwd_packed_bytes(kind)) - 16)
+    return ctypes.c_void_p(packed.data_ptr() + int(_lib.load().hps_mlp_tc_bwd_absmax_offset(kind)))
 
 
 def _mlp_backward(kind, prm, saved_kind, saved, p_c, c_c, aff, dout, P, dprm, dc, need_dp, daff, dev, stream=None,
@@ -639,9 +639,16 @@ class _RenderRays(torch.autograd.Function):
                         if spec.live_col is not None:
                             spec.live_col.refresh()
                     refreshed = side.record_event()
-                _mlp_pack(MLP_COL, carr, dev, side, bwd=bpk_c)
+                # forward images first (the decoders wait for them), the backward images afterwards
+                _mlp_pack(MLP_COL, carr, dev, side)
                 packed_col = side.record_event()
-                _mlp_pack(MLP_GEO, garr, dev, side, bwd=bpk_g)
+                _mlp_pack(MLP_GEO, garr, dev, side)
+                aux = None
+                if bpk_c is not None:      # backward images on a third stream: nothing in the forward waits for them
+                    aux = _side_stream(dev, 1)
+                    aux.wait_stream(main)
+                    _call("hps_mlp_tc_bwd_pack", MLP_COL, carr, _lib.ptr(bpk_c), _stream(aux))
+                    _call("hps_mlp_tc_bwd_pack", MLP_GEO, garr, _lib.ptr(bpk_g), _stream(aux))
             _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t),
                   0.0 if rad_t is not None else float(rad), _lib.ptr(zz), R, S, float(spec.near), float(spec.far),
                   _lib.ptr(z), _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), st())
@@ -661,6 +668,8 @@ class _RenderRays(torch.autograd.Function):
                 sv_g = _mlp_forward(MLP_GEO, garr, pts, c_geo, None, P, occ, need_grad, dev, side, ws_g, packed=True,
                                     max_ctas=n_g)
                 main.wait_stream(side)
+                if aux is not None:
+                    main.wait_stream(aux)
             else:
                 sv_g = _mlp_forward(MLP_GEO, garr, pts, c_geo, None, P, occ, need_grad, dev)
                 sv_c = _mlp_forward(MLP_COL, carr, pts, c_col, aff, P, rgb, need_grad, dev) if spec.color_stage else None

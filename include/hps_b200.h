@@ -112,14 +112,17 @@ int64_t hps_mlp_tc_ws_bytes(int kind, int64_t P);
  * behind each other (the kernels hold an SM exclusively: their shared memory does not fit twice).              */
 int hps_mlp_tc_fwd(int kind, const float* const* params, const void* packed, const float* p, const float* c,
                    const float* affine, int64_t P, float* out, float* act, void* ws, int max_ctas, void* stream);
-/* Tensor-core backward: dgrad chain kernel + streaming wgrad kernel (MN-major operands, accumulators in TMEM).
+/* Tensor-core backward: dgrad chain kernel + streaming wgrad kernel (MN-major operands, accumulators in TMEM)
+ * + a small finalisation kernel for dWc / dbc.
  * Same outputs as hps_mlp_bwd except that dp (P,3) must be ZERO-initialised by the caller (it is accumulated).
  * `packed` = hps_mlp_tc_bwd_pack image (transposed weight slabs, hps_mlp_tc_bwd_packed_bytes(kind) bytes).    */
 int64_t hps_mlp_tc_bwd_packed_bytes(int kind);
+int64_t hps_mlp_tc_bwd_absmax_offset(int kind);   /* byte offset of the max|dout| word inside `packed` */
 int hps_mlp_tc_bwd_pack(int kind, const float* const* params, void* packed, void* stream);
 /*
  * The backward runs on gradients scaled by a power of two derived from max|dout|; that maximum is reduced into the
- * uint32 word (float bits) at packed + hps_mlp_tc_bwd_packed_bytes(kind) - 16, zeroed by hps_mlp_tc_bwd_pack.
+ * uint32 word (float bits) at packed + hps_mlp_tc_bwd_absmax_offset(kind), zeroed by hps_mlp_tc_bwd_pack (the
+ * image also carries Wo Wc_4 and a scratch area for the (H x 32) sums behind dWc / dbc, see csrc/mlp_tc_bwd.cu).
  * absmax_done != 0: the caller has already reduced max|dout| into that word (hps_composite_bwd can do it while
  * it writes dout), so the extra reduction kernel is skipped.  wgrad_stream: stream for the weight-gradient kernel
  * (ordered after the dgrad kernel through an event); dc / dp / daffine are complete on `stream`, the parameter
