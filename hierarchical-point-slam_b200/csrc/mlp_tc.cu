@@ -373,7 +373,7 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
                             const bool is_cos = C::CONCAT && e >= NF;
                             const int f = is_cos ? e - NF : e;
                             const float arg = fmaf(x2, sB[2 * NF + f], fmaf(x1, sB[NF + f], x0 * sB[f]));
-                            val = is_cos ? cosf(arg) : sinf(arg);
+                            val = is_cos ? cos_2pi(arg) : sin_2pi(arg);
                         }
                         v[j] = val;
                     }

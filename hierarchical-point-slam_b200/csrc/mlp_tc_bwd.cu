@@ -569,7 +569,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, uint8_t* __restr
                             b2 = sB[2 * NF + f];
                             const float arg = fmaf(x2, b2, fmaf(x1, b1, x0 * b0));
                             // d sin = cos, d cos = -sin
-                            g = live ? (is_cos ? -de[j] * sinf(arg) : de[j] * cosf(arg)) * gInv : 0.f;
+                            g = live ? (is_cos ? -de[j] * sin_2pi(arg) : de[j] * cos_2pi(arg)) * gInv : 0.f;
                         }
                         g0 = fmaf(g * kTwoPi, b0, g0);
                         g1 = fmaf(g * kTwoPi, b1, g1);
@@ -893,10 +893,12 @@ __global__ void mlp_wfinal_kernel(Ptrs prm, GradPtrs grd, const float* __restric
             const float* w = prm.v[iW(i + 1)] + off + hin;                    // W_{i+1}[ho][off + hin], pitch Kn
             if (bias) {
                 const float* sdb = scratch + GB::OFF_SDB + i * H;
-                for (int ho = 0; ho < H; ++ho) acc = fmaf(sdb[ho], w[(int64_t)ho * Kn], acc);
+#pragma unroll 8
+                for (int ho = 0; ho < H; ++ho) acc = fmaf(__ldg(sdb + ho), __ldg(w + (int64_t)ho * Kn), acc);
             } else {
                 const float* t = scratch + GB::OFF_T + i * H * 32 + k;
-                for (int ho = 0; ho < H; ++ho) acc = fmaf(w[(int64_t)ho * Kn], t[ho * 32], acc);
+#pragma unroll 8
+                for (int ho = 0; ho < H; ++ho) acc = fmaf(__ldg(w + (int64_t)ho * Kn), __ldg(t + ho * 32), acc);
             }
         } else {
             const float* wo = prm.v[iWo] + hin;

@@ -208,6 +208,17 @@ __device__ __forceinline__ float rcp_ftz(float x) {
     return y;
 }
 
+// sin / cos of Fourier arguments (|x| up to ~1e4 rad): exact-product reduction by 2*pi in two FMAs (error of the
+// reduced argument ~1e-7), then the MUFU approximations on |r| <= pi (absolute error 2^-20.9).  The fp32 argument
+// itself carries ~6e-5 rad of rounding at |x| ~ 1e3, in the reference as well, so nothing is lost against sinf/cosf,
+// at a quarter of the instructions.
+__device__ __forceinline__ float reduce_2pi(float x) {
+    const float k = rintf(x * 0.15915494309189535f);
+    return fmaf(-k, -1.7484555314695172e-07f, fmaf(-k, 6.2831854820251465f, x));
+}
+__device__ __forceinline__ float sin_2pi(float x) { return __sinf(reduce_2pi(x)); }
+__device__ __forceinline__ float cos_2pi(float x) { return __cosf(reduce_2pi(x)); }
+
 // Eight values at once: two packed-conversion instructions per pair instead of four scalar conversions; the
 // halves are bit-identical to split16's.  vh / vl are one 16-byte slab chunk each.
 __device__ __forceinline__ void split8(const float (&x)[8], uint4& vh, uint4& vl) {
