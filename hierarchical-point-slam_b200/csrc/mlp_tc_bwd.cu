@@ -893,11 +893,11 @@ __global__ void mlp_wfinal_kernel(Ptrs prm, GradPtrs grd, const float* __restric
             const float* w = prm.v[iW(i + 1)] + off + hin;                    // W_{i+1}[ho][off + hin], pitch Kn
             if (bias) {
                 const float* sdb = scratch + GB::OFF_SDB + i * H;
-#pragma unroll 8
+#pragma unroll 32
                 for (int ho = 0; ho < H; ++ho) acc = fmaf(__ldg(sdb + ho), __ldg(w + (int64_t)ho * Kn), acc);
             } else {
                 const float* t = scratch + GB::OFF_T + i * H * 32 + k;
-#pragma unroll 8
+#pragma unroll 32
                 for (int ho = 0; ho < H; ++ho) acc = fmaf(__ldg(w + (int64_t)ho * Kn), __ldg(t + ho * 32), acc);
             }
         } else {
