@@ -549,10 +549,48 @@ class LiveRows:
 # --------------------------------------------------------------------------------------------------
 # fused ray rendering: sampling -> neighbour search -> interpolation -> decoders -> compositing
 # --------------------------------------------------------------------------------------------------
+class RayPrep:
+    """The parameter-free head of a render call, computed ahead of time: depth-guided samples, their radius
+    thresholds and the exact neighbour lists (Renderer.py:163-229 + neural_point.py:366-417).  Nothing in it depends
+    on features or decoder weights, so a multi-GPU mapper can run it for iteration i+1 while the gradients of
+    iteration i are still being exchanged (bench.py does).  Build with prepare_rays(); pass as RenderSpec.prep."""
+    __slots__ = ("z", "pts", "t_up", "t_dn", "I", "D", "cnt", "R", "S")
+
+
+def prepare_rays(grid, rays_o, rays_d, gt_depth, radius, S, near, far, z_zero=None, out=None):
+    """Sampling + neighbour search for R rays (two kernel launches).  `out`: a RayPrep to refill in place."""
+    _need_cuda(rays_o, rays_d, gt_depth)
+    dev = rays_o.device
+    R = rays_o.shape[0]
+    P = R * S
+    f32 = dict(dtype=torch.float32, device=dev)
+    ro, rd, gd = _f32c(rays_o).reshape(-1, 3), _f32c(rays_d).reshape(-1, 3), _f32c(gt_depth).reshape(-1)
+    rad_t = radius.detach().to(device=dev, dtype=torch.float64).reshape(-1).contiguous() if torch.is_tensor(radius) else None
+    if rad_t is not None and rad_t.numel() != R:
+        raise ValueError("shape mis-match for rays and dynamic radius")
+    zz = _f32c(z_zero) if z_zero is not None else None
+    pr = out
+    if pr is None or pr.R != R or pr.S != S:
+        pr = RayPrep()
+        pr.R, pr.S = R, S
+        pr.z, pr.pts = torch.empty(R, S, **f32), torch.empty(P, 3, **f32)
+        pr.t_up, pr.t_dn = torch.empty(P, **f32), torch.empty(P, **f32)
+        pr.I = torch.empty(P, K_NN, dtype=torch.int32, device=dev)
+        pr.D = torch.empty(P, K_NN, **f32)
+        pr.cnt = torch.empty(P, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t),
+              0.0 if rad_t is not None else float(radius), _lib.ptr(zz), R, S, float(near), float(far),
+              _lib.ptr(pr.z), _lib.ptr(pr.pts), _lib.ptr(pr.t_up), _lib.ptr(pr.t_dn), _stream())
+        _call("hps_knn_query", grid._h, _lib.ptr(pr.pts), _lib.ptr(pr.t_up), _lib.ptr(pr.t_dn), P, _lib.ptr(pr.I),
+              _lib.ptr(pr.D), _lib.ptr(pr.cnt), None, 5 if (S == 5 and P >= KNN_GROUP_MIN_QUERIES) else 1, _stream())
+    return pr
+
+
 class RenderSpec:
     """Non-tensor arguments of render_rays (one per call)."""
     __slots__ = ("grid", "radius", "z_zero", "S", "near", "far", "coef", "min_nn", "min_valid", "color_stage",
-                 "tracker", "cloud_pos", "fill_geo", "fill_col", "live_geo", "live_col")
+                 "tracker", "cloud_pos", "fill_geo", "fill_col", "live_geo", "live_col", "prep")
 
     def __init__(self, **kw):
         for k in self.__slots__:
@@ -600,12 +638,18 @@ class _RenderRays(torch.autograd.Function):
         rad_t = rad.detach().to(device=dev, dtype=torch.float64).reshape(-1).contiguous() if torch.is_tensor(rad) else None
         if rad_t is not None and rad_t.numel() != R:
             raise ValueError("shape mis-match for rays and dynamic radius")
-        z = torch.empty(R, S, **f32)
-        pts = torch.empty(P, 3, **f32)
-        t_up, t_dn = torch.empty(P, **f32), torch.empty(P, **f32)
-        I = torch.empty(P, K_NN, dtype=torch.int32, device=dev)
-        D = torch.empty(P, K_NN, **f32)
-        cnt = torch.empty(P, dtype=torch.int32, device=dev)
+        prep = spec.prep
+        if prep is not None:
+            if prep.R != R or prep.S != S:
+                raise _lib.HpsError("RayPrep was built for %d rays x %d samples, the call has %d x %d" % (prep.R, prep.S, R, S))
+            z, pts, t_up, t_dn, I, D, cnt = prep.z, prep.pts, prep.t_up, prep.t_dn, prep.I, prep.D, prep.cnt
+        else:
+            z = torch.empty(R, S, **f32)
+            pts = torch.empty(P, 3, **f32)
+            t_up, t_dn = torch.empty(P, **f32), torch.empty(P, **f32)
+            I = torch.empty(P, K_NN, dtype=torch.int32, device=dev)
+            D = torch.empty(P, K_NN, **f32)
+            cnt = torch.empty(P, dtype=torch.int32, device=dev)
         w = torch.empty(P, K_NN, **f32)
         c_geo = torch.empty(P, C_DIM, **f32)
         c_col = torch.empty(P, C_DIM, **f32) if spec.color_stage else None
@@ -649,11 +693,12 @@ class _RenderRays(torch.autograd.Function):
                     aux.wait_stream(main)
                     _call("hps_mlp_tc_bwd_pack", MLP_COL, carr, _lib.ptr(bpk_c), _stream(aux))
                     _call("hps_mlp_tc_bwd_pack", MLP_GEO, garr, _lib.ptr(bpk_g), _stream(aux))
-            _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t),
-                  0.0 if rad_t is not None else float(rad), _lib.ptr(zz), R, S, float(spec.near), float(spec.far),
-                  _lib.ptr(z), _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), st())
-            _call("hps_knn_query", spec.grid._h, _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), P, _lib.ptr(I),
-                  _lib.ptr(D), _lib.ptr(cnt), None, 5 if (S == 5 and P >= KNN_GROUP_MIN_QUERIES) else 1, st())
+            if prep is None:
+                _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t),
+                      0.0 if rad_t is not None else float(rad), _lib.ptr(zz), R, S, float(spec.near), float(spec.far),
+                      _lib.ptr(z), _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), st())
+                _call("hps_knn_query", spec.grid._h, _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), P, _lib.ptr(I),
+                      _lib.ptr(D), _lib.ptr(cnt), None, 5 if (S == 5 and P >= KNN_GROUP_MIN_QUERIES) else 1, st())
             if fork and refreshed is not None:
                 main.wait_event(refreshed)
             _call("hps_interp_fwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(D), _lib.ptr(t_dn), _lib.ptr(cnt),

@@ -82,11 +82,25 @@ class Renderer(object):
         return torch.where(idx < S // 2, self.near_end + step * idx, far - step * (S - 1 - idx))
 
     # Renderer.py:84-254
+    def prepare_batch(self, npc, rays_d, rays_o, stage, gt_depth, dynamic_r_query=None, out=None):
+        """The parameter-free head of render_batch_ray for the same arguments (sampling + neighbour search) as an
+        ops.RayPrep; pass it back as render_batch_ray(..., prepared=prep).  Lets a caller issue it early - e.g. for the
+        next iteration while this iteration's gradients are still on the wire."""
+        level = "mid" if stage.endswith("mid") else "fine"
+        gt_depth = gt_depth.reshape(-1)
+        radius = dynamic_r_query[level].reshape(-1) if self.use_dynamic_radius else npc.get_radius_query()
+        index = npc.get_index(level)
+        return ops.prepare_rays(index.grid_for(radius), rays_o, rays_d, gt_depth, radius, self.N_surface,
+                                self.near_end_surface, self.far_end_surface,
+                                None if self.assume_positive_depth else self._z_for_zero_depth(gt_depth, rays_o.device),
+                                out=out)
+
     def render_batch_ray(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None,
                          npc_geo_feats=None, npc_col_feats=None, is_tracker=False, cloud_pos=None,
-                         normals=None, dynamic_r_query=None, exposure_feat=None):
+                         normals=None, dynamic_r_query=None, exposure_feat=None, prepared=None):
         """One fused kernel sequence (ops.render_rays): sampling, exact neighbour search, interpolation of both
-        feature tables from one neighbour list, both decoders, compositing with the -100 overwrite."""
+        feature tables from one neighbour list, both decoders, compositing with the -100 overwrite.
+        `prepared` (not in the reference): the ops.RayPrep of prepare_batch() for these very rays."""
         S = self.N_surface
         N_rays = rays_o.shape[0]
         if stage not in ("geometry_mid", "color_mid", "geometry_fine", "color_fine"):
@@ -118,7 +132,7 @@ class Renderer(object):
             near=self.near_end_surface, far=self.far_end_surface, coef=self.sigmoid_coefficient,
             min_nn=geo.min_nn_num, min_valid=int(S / 2 + 1), color_stage=color_stage, tracker=bool(is_tracker),
             cloud_pos=cloud_pos[level] if is_tracker else None, fill_geo=decoders._fill("geo", rays_o.device),
-            fill_col=decoders._fill("col", rays_o.device) if color_stage else None)
+            fill_col=decoders._fill("col", rays_o.device) if color_stage else None, prep=prepared)
         depth, uncertainty, color, valid = ops.render_rays(
             spec, rays_o, rays_d, gt_depth, npc_geo_feats[level], npc_col_feats[level] if color_stage else None, affine,
             geo.kernel_params(rays_o.device), col.kernel_params(rays_o.device) if color_stage else None)
