@@ -206,3 +206,47 @@ def test_add_neural_points_density_test(built):
     assert npc.index_ntotal("fine") == 897 + 3 * want
     import numpy as np
     assert np.array(npc.cloud_pos("fine")).shape == (897 + 3 * want, 3)
+
+
+@pytest.mark.parametrize("tracker", [False, True])
+def test_prepared_head_gives_identical_iteration(built, tracker):
+    """Renderer.prepare_batch (sampling + neighbour search issued ahead of time) + render_batch_ray(prepared=...) is
+    bit-identical to the one-call path in the forward and equal up to summation order in the gradients (mapper and
+    tracker pose path), and the RayPrep can be refilled in place."""
+    scene, hps, npc, dec, renderer = built
+    cl, rays = scene["clouds"], scene["rays"]
+    stage = "color_fine"
+
+    def run(prepared_box):
+        gf = {l: npc.get_geo_feats(l).detach().clone().requires_grad_(True) for l in cl}
+        cf = {l: npc.get_col_feats(l).detach().clone().requires_grad_(True) for l in cl}
+        ro = rays["rays_o"].to(DEV).clone().requires_grad_(tracker)
+        rd = rays["rays_d"].to(DEV).clone().requires_grad_(tracker)
+        gd = rays["gt_depth"].to(DEV)
+        rq = {l: cl[l]["radius"].to(DEV).clone() for l in cl}
+        prep = None
+        if prepared_box is not None:
+            prepared_box[0] = renderer.prepare_batch(npc, rd.detach(), ro.detach(), stage, gd, rq, out=prepared_box[0])
+            prep = prepared_box[0]
+        pos = {l: npc.cloud_pos_tensor(l) for l in cl}
+        d, u, c, v = renderer.render_batch_ray(npc, dec, rd, ro, DEV, stage, gt_depth=gd, npc_geo_feats=gf,
+                                               npc_col_feats=cf, is_tracker=tracker, cloud_pos=pos, dynamic_r_query=rq,
+                                               prepared=prep)
+        (d.sum() + c.sum()).backward()
+        out = [d.detach(), u.detach(), c.detach(), v, gf["fine"].grad, cf["fine"].grad]
+        if tracker:
+            out += [ro.grad, rd.grad]
+        return out
+
+    for p in dec.parameters():
+        p.grad = None
+    ref = run(None)
+    box = [None]
+    for _ in range(2):          # second round refills the same RayPrep
+        for p in dec.parameters():
+            p.grad = None
+        got = run(box)
+        for a, b in zip(ref[:4], got[:4]):                    # forward: bit-identical
+            assert torch.equal(a, b)
+        for a, b in zip(ref[4:], got[4:]):                    # gradients: atomics reorder the sums (fp32, 1e-5 of the max)
+            assert float((a - b).abs().max()) <= 1e-5 * max(float(a.abs().max()), 1e-30)
