@@ -39,6 +39,8 @@ def quad2rotation(quad):
 def get_camera_from_tensor(inputs):
     """(7,) or (B,7) [quat, T] -> (3,4) or (B,3,4); common.py:330-346."""
     single = inputs.dim() == 1
+    if single and inputs.is_cuda and inputs.numel() == 7 and inputs.dtype == torch.float32:
+        return ops.camera_from_tensor(inputs)              # one kernel each way (the tracker's per-iteration call)
     if single:
         inputs = inputs.unsqueeze(0)
     RT = torch.cat([quad2rotation(inputs[:, :4]), inputs[:, 4:, None]], 2)
@@ -49,6 +51,9 @@ def get_rays_from_uv(i, j, c2w, H, W, fx, fy, cx, cy, device):
     """common.py:103-119."""
     if isinstance(c2w, np.ndarray):
         c2w = torch.from_numpy(c2w).to(device)
+    if (torch.is_tensor(i) and i.is_cuda and i.dim() == 1 and i.is_floating_point() and c2w.is_cuda
+            and c2w.dtype == torch.float32 and c2w.dim() == 2 and c2w.shape[1] == 4):
+        return ops.rays_from_uv(i, j, c2w, fx, fy, cx, cy)  # one kernel each way, bit-identical to the expressions below
     dirs = torch.stack([(i - cx) / fx, -(j - cy) / fy, -torch.ones_like(i)], -1).to(device).reshape(-1, 1, 3)
     rays_d = torch.sum(dirs * c2w[:3, :3], -1)
     rays_o = c2w[:3, -1].expand(rays_d.shape)

@@ -44,7 +44,8 @@ _KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_interp_fwd": 
                      "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_mlp_tc_pack": 1, "hps_mlp_tc_fwd": 1,
                      "hps_mlp_tc_bwd_pack": 2, "hps_mlp_tc_bwd": 3, "hps_tc_selftest": 1, "hps_composite_fwd": 1,
                      "hps_composite_bwd": 1, "hps_sample_rays": 1, "hps_sample_rays_bwd": 1, "hps_mapper_loss": 1,
-                     "hps_tracker_loss_stats": 1, "hps_tracker_loss": 1, "hps_exposure_fwd": 1, "hps_exposure_bwd": 1}
+                     "hps_tracker_loss_stats": 1, "hps_tracker_loss": 1, "hps_exposure_fwd": 1, "hps_exposure_bwd": 1, "hps_camera_from_tensor": 1,
+                     "hps_camera_from_tensor_bwd": 1, "hps_rays_from_uv": 1, "hps_rays_from_uv_bwd": 1}
 TIMERS = None   # set to {} to record (start, end) CUDA events per call name on the current stream
 
 
@@ -786,13 +787,14 @@ class _RenderRays(torch.autograd.Function):
                 n_c, n_g = _sm_split(P, "bwd")
                 # the HBM-bound weight-gradient kernels go to streams of their own: the feature scatter below needs
                 # only dc of both decoders and overlaps with them
-                w_c, w_g = _side_stream(dev, 1), _side_stream(dev, 2)
+                w_c = _side_stream(dev, 1) if dcw is not None else None     # (no weight gradients: nothing to fork)
+                w_g = _side_stream(dev, 2) if dg is not None else None
                 _mlp_backward(MLP_COL, cprm, "tc", act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c, need_p, daff, dev, main,
                               dp_c, packed=ctx.bwd_packed[1], absmax_done=folded, max_ctas=n_c, wgrad_stream=w_c)
                 _mlp_backward(MLP_GEO, gprm, "tc", act_g, pts, c_geo, None, d_occ, P, dg, dc_g, need_p, None, dev, side,
                               dp_g, packed=ctx.bwd_packed[0], absmax_done=folded, max_ctas=n_g, wgrad_stream=w_g)
                 main.wait_stream(side)
-                wgrad_streams = (w_c, w_g)
+                wgrad_streams = tuple(w for w in (w_c, w_g) if w is not None)
             else:
                 dp_g = _mlp_backward(MLP_GEO, gprm, ctx.saved_kinds[0], act_g, pts, c_geo, None, d_occ, P, dg, dc_g,
                                      need_p, None, dev, dp=zp.get(h_dpg))
@@ -831,6 +833,68 @@ def render_rays(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, ge
     params = list(geo_params) + (list(col_params) if spec.color_stage else [])
     return _RenderRays.apply(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col if spec.color_stage else None,
                              affine if spec.color_stage else None, *params)
+
+
+# --------------------------------------------------------------------------------------------------
+# tracker pose helpers (common.py:304-346, 103-119)
+# --------------------------------------------------------------------------------------------------
+class _CameraFromTensor(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, cam):
+        _need_cuda(cam)
+        c = _f32c(cam).reshape(7)
+        RT = torch.empty(3, 4, dtype=torch.float32, device=c.device)
+        with torch.cuda.device(c.device):
+            _call("hps_camera_from_tensor", _lib.ptr(c), _lib.ptr(RT), _stream())
+        ctx.save_for_backward(c)
+        return RT
+
+    @staticmethod
+    def backward(ctx, g):
+        (c,) = ctx.saved_tensors
+        out = torch.empty(7, dtype=torch.float32, device=c.device)
+        with torch.cuda.device(c.device):
+            _call("hps_camera_from_tensor_bwd", _lib.ptr(c), _lib.ptr(_f32c(g)), _lib.ptr(out), _stream())
+        return out
+
+
+def camera_from_tensor(cam):
+    """(7,) [quaternion, translation] CUDA tensor -> (3,4); one kernel each way."""
+    return _CameraFromTensor.apply(cam)
+
+
+class _RaysFromUv(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, i, j, c2w, fx, fy, cx, cy):
+        _need_cuda(i, j, c2w)
+        dev = c2w.device
+        pi, pj, m = _f32c(i).reshape(-1), _f32c(j).reshape(-1), _f32c(c2w)
+        if m.dim() != 2 or m.shape[1] != 4 or m.shape[0] < 3:
+            raise ValueError("c2w must be (3,4) or (4,4)")
+        R = pi.numel()
+        ro = torch.empty(R, 3, dtype=torch.float32, device=dev)
+        rd = torch.empty(R, 3, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _call("hps_rays_from_uv", _lib.ptr(pi), _lib.ptr(pj), _lib.ptr(m), 4, R, float(fx), float(fy), float(cx),
+                  float(cy), _lib.ptr(ro), _lib.ptr(rd), _stream())
+        ctx.save_for_backward(pi, pj)
+        ctx.k = (float(fx), float(fy), float(cx), float(cy), tuple(c2w.shape))
+        return ro, rd
+
+    @staticmethod
+    def backward(ctx, g_o, g_d):
+        pi, pj = ctx.saved_tensors
+        fx, fy, cx, cy, shape = ctx.k
+        g = torch.zeros(shape, dtype=torch.float32, device=pi.device)
+        with torch.cuda.device(pi.device):
+            _call("hps_rays_from_uv_bwd", _lib.ptr(pi), _lib.ptr(pj), _lib.ptr(_f32c(g_o) if g_o is not None else None),
+                  _lib.ptr(_f32c(g_d) if g_d is not None else None), pi.numel(), fx, fy, cx, cy, _lib.ptr(g), _stream())
+        return None, None, g, None, None, None, None
+
+
+def rays_from_uv(i, j, c2w, fx, fy, cx, cy):
+    """Rays through pixels (i, j) of camera c2w ((3,4) or (4,4) CUDA tensor): rays_o (R,3), rays_d (R,3)."""
+    return _RaysFromUv.apply(i, j, c2w, fx, fy, cx, cy)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -936,8 +1000,9 @@ class _TrackerLoss(torch.autograd.Function):
         d, u, gdp = _f32c(depth), _f32c(uncertainty), _f32c(gt_depth).reshape(-1)
         col = _f32c(color) if color is not None else None
         gcl = _f32c(gt_color) if color is not None else None
-        stats = torch.zeros(2, **f32)
-        stats[1] = R
+        stats = torch.full((2,), float(R), **f32)      # [sum of tmp (accumulated by the kernel), number of rays]
+        stats[:1].zero_()                              # (no scalar assignment: that is a host-to-device copy, which a
+                                                       #  CUDA-graph capture of the tracker iteration would refuse)
         loss = torch.zeros((), **f32)
         g_depth = torch.empty(R, **f32)
         g_color = torch.empty(R, 3, **f32) if col is not None else None

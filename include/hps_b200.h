@@ -190,6 +190,20 @@ int hps_sample_rays(const float* rays_o, const float* rays_d, const float* gt_de
 int hps_sample_rays_bwd(const float* dp, const float* z, int64_t R, int S, float* g_rays_o, float* g_rays_d,
                         void* stream);
 
+/* Tracker pose helpers (common.py:304-346 get_camera_from_tensor / quad2rotation, :103-119 get_rays_from_uv) as
+ * single kernels with analytic backward; arithmetic is rounded like the reference's torch expressions.
+ *   hps_camera_from_tensor:      cam7 = [quaternion (w,x,y,z), translation] -> RT (3,4) row-major (q is not normalised)
+ *   hps_camera_from_tensor_bwd:  g_RT (3,4) -> g_cam7 (7), written
+ *   hps_rays_from_uv:            pixels (pi, pj) (R each, float) -> rays_d = sum(dirs * c2w[:3,:3], -1), rays_o = c2w[:3,3];
+ *                                c2w rows have `pitch` floats (4 for (3,4) and (4,4) matrices)
+ *   hps_rays_from_uv_bwd:        g_c2w (3,4) += [sum_r g_rays_d (x) dirs | sum_r g_rays_o]  (caller zero-initialises)  */
+int hps_camera_from_tensor(const float* cam7, float* RT, void* stream);
+int hps_camera_from_tensor_bwd(const float* cam7, const float* g_RT, float* g_cam7, void* stream);
+int hps_rays_from_uv(const float* pi, const float* pj, const float* c2w, int pitch, int64_t R, float fx, float fy,
+                     float cx, float cy, float* rays_o, float* rays_d, void* stream);
+int hps_rays_from_uv_bwd(const float* pi, const float* pj, const float* g_rays_o, const float* g_rays_d, int64_t R,
+                         float fx, float fy, float cx, float cy, float* g_c2w, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Losses fused with their gradients (Mapper.py:791-856; Tracker.py:213-231).  `loss` (1 float) and
  * `d_affine` (12 floats) are ACCUMULATED into; g_depth (R) / g_color (R,3) are written.

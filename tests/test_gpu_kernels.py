@@ -376,3 +376,31 @@ def test_knn_ray_grouped_sweep_equals_per_query(hps, Q):
     for x, y, name in zip(a, b, ("I", "D", "count")):
         assert torch.equal(x, y), name
     assert int(a[2].max()) > 0
+
+
+def test_pose_helpers_match_torch_expressions(hps):
+    """get_camera_from_tensor / get_rays_from_uv (common.py:304-346, 103-119) as single kernels: forward bit-identical
+    to the reference's torch expressions evaluated on the same device, backward (analytic) within 1e-6 of autograd."""
+    K = O.SCANNET_INTRINSICS
+    g = torch.Generator().manual_seed(21)
+    for trial in range(4):
+        cam = torch.randn(7, generator=g)
+        cam[:4] = torch.nn.functional.normalize(cam[:4], dim=0) * (1.0 + 0.05 * trial)     # also off the unit sphere
+        R = 777
+        pi = torch.randint(0, K["W"], (R,), generator=g).float().to(DEV)
+        pj = torch.randint(0, K["H"], (R,), generator=g).float().to(DEV)
+        w_o, w_d = torch.randn(R, 3, generator=g).to(DEV), torch.randn(R, 3, generator=g).to(DEV)
+        # reference expressions (oracle restatement, run on the GPU so that rounding is torch-CUDA's)
+        cr = cam.to(DEV).clone().requires_grad_(True)
+        c2w_r = O.camera_from_tensor(cr)
+        ro_r, rd_r = O.rays_from_uv(pi, pj, c2w_r, K["fx"], K["fy"], K["cx"], K["cy"])
+        ((ro_r * w_o).sum() + (rd_r * w_d).sum()).backward()
+        # product
+        cp = cam.to(DEV).clone().requires_grad_(True)
+        c2w_p = hps.get_camera_from_tensor(cp)
+        ro_p, rd_p = hps.get_rays_from_uv(pi, pj, c2w_p, K["H"], K["W"], K["fx"], K["fy"], K["cx"], K["cy"], DEV)
+        ((ro_p * w_o).sum() + (rd_p * w_d).sum()).backward()
+        assert torch.equal(c2w_p, c2w_r.detach()), "camera matrix differs"
+        assert torch.equal(rd_p, rd_r.detach()) and torch.equal(ro_p, ro_r.detach()), "rays differ"
+        err = float((cp.grad - cr.grad).abs().max()) / float(cr.grad.abs().max())
+        assert err < 1e-5, err            # sums over 777 rays in a different order
