@@ -1,0 +1,73 @@
+// Adam over the selected (live) feature rows, fused with the write-back into the full table.
+//
+// Reference: the mapper clones the frustum-selected rows of every feature table into leaf tensors, runs
+// torch.optim.Adam on them and writes them back into the tables each iteration (src/Mapper.py:512-536, 592-603,
+// 615-630, 859, 862-874).  Here one kernel per table does the Adam update of the compact (M,C) leaves AND stores the
+// new rows into the (N,C) table the gather kernels read, so neither the optimiser's foreach kernels nor the
+// per-iteration index copy remain.  The step counter lives on the device (CUDA-graph replayable): the kernel
+// reads t = step + 1 and the last block to finish stores it.
+//
+// Update rule = torch.optim.Adam (no amsgrad, no weight decay, maximize=False):
+//     m <- m + (g - m)(1 - b1);  v <- b2 v + (1 - b2) g g
+//     p <- p - (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+#include "hps_common.cuh"
+
+namespace hps {
+
+__global__ void __launch_bounds__(256)
+adam_rows_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 int64_t n4, int c4, float lr, float b1, float b2, float eps, int* __restrict__ step,
+                 float* __restrict__ table, const int64_t* __restrict__ rows) {
+    const int t = step[0] + 1;
+    const float bc1 = 1.0f - powf(b1, (float)t), bc2 = 1.0f - powf(b2, (float)t);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = 1.0f / sqrtf(bc2);
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n4) {
+        const float4 gg = reinterpret_cast<const float4*>(g)[i];
+        float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i], pp = reinterpret_cast<float4*>(p)[i];
+        float* gp = const_cast<float*>(reinterpret_cast<const float*>(&gg));
+        float *mp = reinterpret_cast<float*>(&mm), *vp = reinterpret_cast<float*>(&vv), *ppp = reinterpret_cast<float*>(&pp);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float gr = gp[k];
+            mp[k] = mp[k] + (gr - mp[k]) * (1.0f - b1);
+            vp[k] = vp[k] * b2 + (1.0f - b2) * gr * gr;
+            const float denom = sqrtf(vp[k]) * inv_sqrt_bc2 + eps;
+            ppp[k] = ppp[k] - step_size * (mp[k] / denom);
+        }
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+        reinterpret_cast<float4*>(p)[i] = pp;
+        if (table != nullptr) {
+            const int64_t row = i / c4, q = i - row * c4;
+            reinterpret_cast<float4*>(table)[rows[row] * c4 + q] = pp;
+        }
+    }
+    // the last block to finish publishes the new step count (every block has read the old one by then)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int done = atomicAdd(step + 1, 1) + 1;
+        if (done == (int)gridDim.x) {
+            step[1] = 0;
+            step[0] = t;
+        }
+    }
+}
+
+}  // namespace hps
+
+extern "C" int hps_adam_rows(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t M, int C,
+                             float lr, float beta1, float beta2, float eps, int32_t* step, float* table,
+                             const int64_t* rows, void* stream) {
+    using namespace hps;
+    HPS_REQUIRE(M >= 0 && C > 0 && C % 4 == 0, "need M >= 0 and C a multiple of 4");
+    if (M == 0) return 0;
+    HPS_REQUIRE(param && grad && exp_avg && exp_avg_sq && step, "null buffer");
+    HPS_REQUIRE(table == nullptr || rows != nullptr, "table write-back needs the row indices");
+    const int64_t n4 = M * (C / 4);
+    adam_rows_kernel<<<(unsigned)ceil_div(n4, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n4,
+                                                                                C / 4, lr, beta1, beta2, eps, step, table, rows);
+    HPS_LAUNCH_OK();
+    return 0;
+}

@@ -44,7 +44,7 @@ _KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_interp_fwd": 
                      "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_mlp_tc_pack": 1, "hps_mlp_tc_fwd": 1,
                      "hps_mlp_tc_bwd_pack": 2, "hps_mlp_tc_bwd": 3, "hps_tc_selftest": 1, "hps_composite_fwd": 1,
                      "hps_composite_bwd": 1, "hps_sample_rays": 1, "hps_sample_rays_bwd": 1, "hps_mapper_loss": 1,
-                     "hps_tracker_loss_stats": 1, "hps_tracker_loss": 1, "hps_exposure_fwd": 1, "hps_exposure_bwd": 1, "hps_camera_from_tensor": 1,
+                     "hps_tracker_loss_stats": 1, "hps_tracker_loss": 1, "hps_exposure_fwd": 1, "hps_exposure_bwd": 1, "hps_camera_from_tensor": 1, "hps_adam_rows": 1,
                      "hps_camera_from_tensor_bwd": 1, "hps_rays_from_uv": 1, "hps_rays_from_uv_bwd": 1}
 TIMERS = None   # set to {} to record (start, end) CUDA events per call name on the current stream
 
@@ -531,6 +531,7 @@ class LiveRows:
             row_map[self.indices] = torch.arange(self.indices.numel(), dtype=torch.int32, device=table.device)
         self.row_map = row_map
         self.param = self.table[self.indices].clone().requires_grad_(True)
+        self.fresh = False       # True: table[indices] == param is guaranteed (RowAdam.step writes both at once)
 
     @classmethod
     def pair(cls, geo_table, col_table, indices):
@@ -538,7 +539,10 @@ class LiveRows:
         return a, cls(col_table, indices, a.row_map)
 
     def refresh(self):
-        """table[indices] = param (no autograd)."""
+        """table[indices] = param (no autograd).  Skipped while RowAdam owns the update (it stores the new rows into the
+        table itself); with any other optimiser on `param` the copy runs before every render."""
+        if self.fresh:
+            return
         with torch.no_grad():
             self.table.index_copy_(0, self.indices, self.param)
 
@@ -833,6 +837,46 @@ def render_rays(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, ge
     params = list(geo_params) + (list(col_params) if spec.color_stage else [])
     return _RenderRays.apply(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col if spec.color_stage else None,
                              affine if spec.color_stage else None, *params)
+
+
+# --------------------------------------------------------------------------------------------------
+# optimiser over live rows (Mapper.py:592-603, 859)
+# --------------------------------------------------------------------------------------------------
+class RowAdam:
+    """torch.optim.Adam semantics (no amsgrad, no weight decay) for LiveRows leaves, one kernel per table and step,
+    fused with the write-back of the new rows into the full tables - the mapper's `optimizer.step()` plus its
+    per-iteration `table[indices] = rows` (Mapper.py:615-630, 859, 862-874).  `groups`: list of (LiveRows, lr).
+    The step counter is a device tensor, so step() can be captured in a CUDA graph with the iteration."""
+
+    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8):
+        self.groups = [[lr_rows, float(lr)] for lr_rows, lr in groups]
+        self.betas, self.eps = betas, float(eps)
+        self.state = []
+        for rows, _ in self.groups:
+            p = rows.param
+            self.state.append(dict(m=torch.zeros_like(p), v=torch.zeros_like(p),
+                                   step=torch.zeros(2, dtype=torch.int32, device=p.device)))
+
+    def set_lr(self, index, lr):
+        self.groups[index][1] = float(lr)
+
+    def zero_grad(self):
+        for rows, _ in self.groups:
+            rows.param.grad = None
+
+    @torch.no_grad()
+    def step(self):
+        for (rows, lr), st in zip(self.groups, self.state):
+            p = rows.param
+            if p.grad is None:
+                continue
+            _need_cuda(p, p.grad)
+            g = _f32c(p.grad)
+            with torch.cuda.device(p.device):
+                _call("hps_adam_rows", _lib.ptr(p), _lib.ptr(g), _lib.ptr(st["m"]), _lib.ptr(st["v"]), p.shape[0], p.shape[1],
+                      lr, float(self.betas[0]), float(self.betas[1]), self.eps, _lib.ptr(st["step"]), _lib.ptr(rows.table),
+                      _lib.ptr(rows.indices), _stream())
+            rows.fresh = True
 
 
 # --------------------------------------------------------------------------------------------------

@@ -166,6 +166,16 @@ int hps_composite_bwd(const float* rgb, int rgb_stride, const float* occ, int oc
                       void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Adam over the live (frustum-selected) rows of a feature table, fused with the write-back into the table
+ * (Mapper.py:512-536, 592-603, 615-630, 859, 862-874: clone rows -> torch.optim.Adam -> copy rows back).
+ *   param, grad, exp_avg, exp_avg_sq: (M,C) compact, C % 4 == 0;  step: 2 device ints {step count, scratch = 0}
+ *   (the kernel uses t = step[0] + 1 and stores it; replayable from a CUDA graph);  table (N,C) + rows (M) int64:
+ *   optional, table[rows[r]] = new param[r].  Update rule = torch.optim.Adam without amsgrad / weight decay.
+ * ---------------------------------------------------------------------------------------------- */
+int hps_adam_rows(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t M, int C, float lr,
+                  float beta1, float beta2, float eps, int32_t* step, float* table, const int64_t* rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Exposure MLP (decoder.py:380-396 MLP_exposure: linear1 -> Softplus(beta=100) -> linear2) on one latent
  * vector: out (n_out = 12) = W2 softplus(W1 x + b1) + b2; W1 (hidden, n_in), W2 (n_out, hidden) row-major as in
  * nn.Linear.  a1 (hidden) receives the pre-activations for the backward.  One launch each way instead of the

@@ -404,3 +404,34 @@ def test_pose_helpers_match_torch_expressions(hps):
         assert torch.equal(rd_p, rd_r.detach()) and torch.equal(ro_p, ro_r.detach()), "rays differ"
         err = float((cp.grad - cr.grad).abs().max()) / float(cr.grad.abs().max())
         assert err < 1e-5, err            # sums over 777 rays in a different order
+
+
+def test_row_adam_matches_torch_adam_and_writes_table(hps):
+    """RowAdam (Mapper.py:592-603, 859 + the row write-back :862-874) vs torch.optim.Adam on the same compact rows over
+    several steps with changing gradients and a learning-rate change; the full table must carry the new rows."""
+    torch.manual_seed(5)
+    N, M, C = 5000, 777, 32
+    table = torch.randn(N, C, device=DEV) * 0.1
+    idx = torch.randperm(N, device=DEV)[:M]
+    rows = hps.LiveRows(table.clone(), idx)
+    ref_p = rows.param.detach().clone().requires_grad_(True)
+    ref = torch.optim.Adam([ref_p], lr=5e-3, betas=(0.9, 0.999), eps=1e-8)
+    opt = hps.RowAdam([(rows, 5e-3)])
+    for it in range(7):
+        g = torch.randn(M, C, device=DEV) * (10.0 ** (-it % 4))
+        if it == 4:
+            for grp in ref.param_groups:
+                grp["lr"] = 1e-3
+            opt.set_lr(0, 1e-3)
+        ref_p.grad = g.clone()
+        rows.param.grad = g.clone()
+        ref.step()
+        opt.step()
+        # fp32, same formula: differences are a few ulp of the update (tolerance 1e-6 of the parameter scale)
+        assert float((rows.param.detach() - ref_p.detach()).abs().max()) <= 1e-6 * float(ref_p.detach().abs().max())
+        assert torch.equal(rows.table[idx], rows.param.detach())
+        assert rows.fresh
+    untouched = torch.ones(N, dtype=torch.bool, device=DEV)
+    untouched[idx] = False
+    assert torch.equal(rows.table[untouched], table[untouched])
+    assert int(opt.state[0]["step"][0]) == 7 and int(opt.state[0]["step"][1]) == 0
