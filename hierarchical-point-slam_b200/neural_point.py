@@ -161,6 +161,42 @@ class NeuralPointCloud(object):
         pos = self.index[level].positions.as_subclass(CloudPositions)
         return pos if index is None else pos[index]
 
+    def frustum_rows(self, level, c2w, depth, H, W, fx, fy, cx, cy, edge):
+        """Frustum feature selection on the device (Mapper.get_mask_from_c2w, Mapper.py:194-250): indices (int64, ascending)
+        of the level's points that project inside the frame cropped by `edge` pixels, in front of the camera and not
+        further than the (bilinearly sampled) depth + 0.5 m.  The reference does this on the host in numpy + cv2.remap for
+        every mapped frame and level; here it is a handful of tensor ops over the resident positions (float64 projection
+        like numpy's, exact bilinear weights instead of cv2's 5-bit fixed point: points within ~1e-3 of a threshold can
+        differ).  Feed the result to ops.LiveRows / LiveRows.pair."""
+        pos = self.index[level].positions
+        dev = pos.device
+        c2w = torch.as_tensor(c2w, dtype=torch.float64, device=dev)
+        if c2w.shape[0] == 3:
+            c2w = torch.cat([c2w, torch.tensor([[0.0, 0.0, 0.0, 1.0]], dtype=torch.float64, device=dev)], 0)
+        depth = torch.as_tensor(depth, device=dev).to(torch.float64)
+        w2c = torch.linalg.inv(c2w)
+        cam = pos.to(torch.float64) @ w2c[:3, :3].T + w2c[:3, 3]
+        cam = cam * torch.tensor([-1.0, 1.0, 1.0], dtype=torch.float64, device=dev)        # Mapper.py:225 axis flip
+        z = cam[:, 2] + 1e-5
+        u = ((fx * cam[:, 0] + cx * cam[:, 2]) / z).to(torch.float32)
+        v = ((fy * cam[:, 1] + cy * cam[:, 2]) / z).to(torch.float32)
+        x, y = u.to(torch.float64), v.to(torch.float64)
+        ok = torch.isfinite(x) & torch.isfinite(y)
+        x, y = torch.where(ok, x, torch.zeros_like(x)), torch.where(ok, y, torch.zeros_like(y))
+        x0, y0 = torch.floor(x), torch.floor(y)
+        ax, ay = x - x0, y - y0
+
+        def at(yy, xx):                                    # constant-0 border (cv2.remap default)
+            inside = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+            flat = (yy.clamp(0, H - 1) * W + xx.clamp(0, W - 1)).long()
+            return torch.where(inside, depth.reshape(-1)[flat], torch.zeros_like(xx))
+        dep = ((1 - ay) * ((1 - ax) * at(y0, x0) + ax * at(y0, x0 + 1)) + ay * ((1 - ax) * at(y0 + 1, x0) + ax * at(y0 + 1, x0 + 1)))
+        dep = dep.to(torch.float32).to(torch.float64)
+        dep = torch.where(dep == 0, dep.max(), dep)
+        mz = -z
+        mask = (u < W - edge) & (u > edge) & (v < H - edge) & (v > edge) & (mz >= 0) & (mz <= dep + 0.5)
+        return mask.nonzero().flatten()
+
     def cloud_pos_tensor(self, level):
         """The (N,3) device tensor itself (what Mapper.py:779 / Tracker.py:257 rebuild every time)."""
         return self.index[level].positions

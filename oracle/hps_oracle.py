@@ -335,6 +335,47 @@ def rays_from_uv(i, j, c2w, fx, fy, cx, cy):
 
 
 # ----------------------------------------------------------------------------------------------
+# frustum feature selection.  PARITY UNPINNED: the reference samples the depth image with
+# cv2.remap (INTER_LINEAR, fixed-point weights, constant-0 border); cv2 is not importable here, so this
+# restatement uses exact bilinear weights and has not been run against the reference function.
+# ----------------------------------------------------------------------------------------------
+def frustum_mask(points, c2w, depth, fx, fy, cx, cy, edge):
+    """Mapper.get_mask_from_c2w (Mapper.py:194-250): indices of the cloud points that project inside the frame
+    (cropped by `edge` pixels) and lie in front of the camera, not further than depth + 0.5 m.  numpy, float64."""
+    import numpy as np
+    H, W = depth.shape
+    pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)
+    w2c = np.linalg.inv(np.asarray(c2w, dtype=np.float64))
+    cam = (w2c @ np.concatenate([pts, np.ones_like(pts[:, :1])], 1).T).T[:, :3]
+    cam[:, 0] *= -1                                         # Mapper.py:225 axis flip
+    Kmat = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    uvz = (Kmat @ cam.T).T
+    z = uvz[:, 2:] + 1e-5
+    uv = (uvz[:, :2] / z).astype(np.float32)
+    x, y = uv[:, 0].astype(np.float64), uv[:, 1].astype(np.float64)
+    x0, y0 = np.floor(x), np.floor(y)
+    d = np.asarray(depth, dtype=np.float64)
+
+    def at(yy, xx):                                         # constant-0 border like cv2.remap's default
+        ok = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+        out = np.zeros_like(xx)
+        out[ok] = d[yy[ok].astype(np.int64), xx[ok].astype(np.int64)]
+        return out
+    ax, ay = x - x0, y - y0
+    ok = np.isfinite(x) & np.isfinite(y)
+    x0, y0, ax, ay = [np.where(ok, t, 0.0) for t in (x0, y0, ax, ay)]
+    dep = ((1 - ay) * ((1 - ax) * at(y0, x0) + ax * at(y0, x0 + 1)) + ay * ((1 - ax) * at(y0 + 1, x0) + ax * at(y0 + 1, x0 + 1)))
+    dep = dep.astype(np.float32).astype(np.float64)
+    mask = (uv[:, 0] < W - edge) & (uv[:, 0] > edge) & (uv[:, 1] < H - edge) & (uv[:, 1] > edge)
+    dep[dep == 0] = dep.max()
+    mz = -z[:, 0]
+    mask = mask & (0 <= mz) & (mz <= dep + 0.5)
+    margin = np.minimum.reduce([np.abs(uv[:, 0] - (W - edge)), np.abs(uv[:, 0] - edge), np.abs(uv[:, 1] - (H - edge)),
+                                np.abs(uv[:, 1] - edge), np.abs(mz), np.abs(mz - dep - 0.5)])
+    return np.where(mask)[0], margin
+
+
+# ----------------------------------------------------------------------------------------------
 # synthetic ScanNet-shaped inputs shared by tests / bench (SURVEY 8d)
 # ----------------------------------------------------------------------------------------------
 SCANNET_INTRINSICS = dict(H=480, W=640, fx=577.590698, fy=578.729797, cx=318.905426, cy=242.683609)

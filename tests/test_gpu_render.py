@@ -250,3 +250,24 @@ def test_prepared_head_gives_identical_iteration(built, tracker):
             assert torch.equal(a, b)
         for a, b in zip(ref[4:], got[4:]):                    # gradients: atomics reorder the sums (fp32, 1e-5 of the max)
             assert float((a - b).abs().max()) <= 1e-5 * max(float(a.abs().max()), 1e-30)
+
+
+def test_frustum_rows_matches_oracle(built):
+    """NeuralPointCloud.frustum_rows (Mapper.py:194-250 on the device) vs the numpy restatement: identical row sets
+    except for points that sit within 1e-3 of one of the selection thresholds (fp summation order / nothing else)."""
+    import numpy as np
+    scene, hps, npc, dec, renderer = built
+    K = O.SCANNET_INTRINSICS
+    depth = O.synthetic_depth()
+    depth[::7, ::5] = 0.0                                   # zero-depth pixels take the maximum (Mapper.py:243-244)
+    cam = torch.tensor([0.999, 0.02, -0.03, 0.01, 0.05, -0.02, 0.03])
+    c2w = torch.cat([O.camera_from_tensor(cam), torch.tensor([[0.0, 0.0, 0.0, 1.0]])], 0)
+    for level in ("mid", "fine"):
+        pts = npc.cloud_pos_tensor(level).cpu()
+        ref, margin = O.frustum_mask(pts.numpy(), c2w.numpy(), depth.numpy(), K["fx"], K["fy"], K["cx"], K["cy"], 20)
+        got = npc.frustum_rows(level, c2w.to(DEV), depth.to(DEV), K["H"], K["W"], K["fx"], K["fy"], K["cx"], K["cy"], 20)
+        got = got.cpu().numpy()
+        assert 0 < len(ref) < len(pts)
+        diff = np.setxor1d(ref, got)
+        assert (margin[diff] < 1e-3).all(), "rows differ away from the thresholds"
+        assert len(diff) <= 1e-3 * len(ref)
