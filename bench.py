@@ -133,7 +133,7 @@ def cpu_step_fn(scene, n_rays):
         aff = O.exposure_affine(dec["color_decoder_fine"], scene["exposure_feat"])
         loss = O.mapper_loss(d, c, m, fine["gt_depth"][sl], fine["gt_color"][sl], STAGE, 0.1, aff)
         loss.backward()
-        return float(loss)
+        return float(loss.detach())
     return step
 
 
