@@ -48,7 +48,8 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if pr.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
-    subprocess.check_call([nvcc(), "--shared", "-o", LIB] + objs + ["-lcudart"])
+    # same -gencode at link time: without it nvcc adds a default-arch (sm_52) stub and warns about it
+    subprocess.check_call([nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", LIB] + objs + ["-lcudart"])
     return LIB
 
 
