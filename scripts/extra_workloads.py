@@ -100,6 +100,48 @@ for stage in ("color_mid", "color_fine"):
     except Exception as e:   # noqa: BLE001
         print("  %-10s graph capture failed: %s" % (stage, str(e).splitlines()[0][:150]))
 
+# ------------------------------------------------------------------ (a2) mapper iteration including the optimiser
+print("== (a2) mapper iteration INCLUDING the optimiser step (RowAdam on the live rows, fused torch Adam on the decoders)")
+for prm in dec.parameters():
+    prm.requires_grad_(True)
+Kc = cfg["cam"]
+pf = npc.cloud_pos_tensor("fine")
+live_idx = npc.frustum_rows("fine", torch.eye(4, device=dev), O.synthetic_depth().to(dev), Kc["H"], Kc["W"], Kc["fx"],
+                            Kc["fy"], Kc["cx"], Kc["cy"], -20)
+lg, lc = hps.LiveRows.pair(npc.get_geo_feats("fine"), npc.get_col_feats("fine"), live_idx)
+gfm = {"fine": lg, "mid": npc.get_geo_feats("mid")}
+cfm = {"fine": lc, "mid": npc.get_col_feats("mid")}
+used = list(dec.geo_decoder_fine.parameters()) + list(dec.color_decoder_fine.parameters())
+opt_rows = hps.RowAdam([(lg, 5e-3), (lc, 5e-3)])
+opt_dec = torch.optim.Adam(used, lr=1e-3, fused=True, capturable=True)
+ro_m, rd_m = fine["rays_o"][:R].to(dev), fine["rays_d"][:R].to(dev)
+ef_m = scene["exposure_feat"].to(dev)
+
+
+def mapper_it():
+    opt_rows.zero_grad()
+    opt_dec.zero_grad(set_to_none=True)
+    d, v, c, m = renderer.render_batch_ray(npc, dec, rd_m, ro_m, dev, "color_fine", gt_depth=gt_d, npc_geo_feats=gfm,
+                                           npc_col_feats=cfm, dynamic_r_query=dict(rq_t), cloud_pos=pos)
+    aff = dec.color_decoder_fine.mlp_exposure(ef_m)
+    loss = hps.mapper_loss(d, c, m, gt_d, gt_c, "color_fine", 0.1, aff)
+    loss.backward()
+    opt_rows.step()
+    opt_dec.step()
+    return loss
+
+
+try:
+    gm = hps.graphs.GraphedStep(mapper_it, {}, warmup=3)
+    g_ms, w_ms = timed(lambda: gm(), 100)
+    l0 = float(gm.outputs)
+    for _ in range(50):
+        gm()
+    print("  graph : %.3f ms / iteration -> %.0f iterations/s = %.1f M rays/s; %d live rows; loss %.1f -> %.1f after 150 more steps"
+          % (g_ms, 1e3 / w_ms, R / w_ms / 1e3, live_idx.numel(), l0, float(gm.outputs)))
+except Exception as e:   # noqa: BLE001
+    print("  graph capture failed: %s" % str(e).splitlines()[0][:200])
+
 # ------------------------------------------------------------------ (b) full-frame render
 print("== (b) full-frame render_img, 640x480 = 307,200 rays x 5 samples, no_grad")
 depth_map = O.synthetic_depth().to(dev)
