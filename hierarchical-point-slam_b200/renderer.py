@@ -31,6 +31,7 @@ class Renderer(object):
         # zero-depth branch (a handful of tiny device ops per call).
         self.assume_positive_depth = False
         self.write_back_radius = True        # see render_batch_ray
+        self.min_render_chunk = 65536        # see render_img
         if self.N_samples > 0 or self.use_bound or self.sample_near_pcl or self.fix_interval or not self.occupancy:
             raise NotImplementedError("only the reference's ScanNet rendering mode is built: N_samples=0, "
                                       "use_bound False, sample_near_pcl False, occupancy True")
@@ -184,7 +185,9 @@ class Renderer(object):
                     dynamic_r_query[key] = dynamic_r_query[key].reshape(-1, 1)
             gt_depth = gt_depth.reshape(-1) if gt_depth is not None else None
             depths, uncs, colors = [], [], []
-            B = self.ray_batch_size
+            # Rays are independent and the reference only chunks to bound memory (ray_batch_size = 3000 -> 103 chunks
+            # per frame, host-bound here): chunks are widened to min_render_chunk rays; the outputs are the same.
+            B = max(self.ray_batch_size, self.min_render_chunk)
             for i in range(0, rays_d.shape[0], B):
                 rq = {k: v[i:i + B] for k, v in dynamic_r_query.items()} if self.use_dynamic_radius else None
                 d, u, c, _ = self.render_batch_ray(

@@ -152,6 +152,7 @@ c2w = torch.eye(4, device=dev)
 ef0 = scene["exposure_feat"].to(dev)
 for B in (3000, 65536):
     renderer.ray_batch_size = B
+    renderer.min_render_chunk = B        # (the default widens chunks to 65536 rays; 3000 = the reference's chunking)
     for stage in ("color_mid", "color_fine"):
         def frame():
             return renderer.render_img(npc, dec, c2w, dev, stage, gt_depth=depth_map, npc_geo_feats=gf, npc_col_feats=cf,

@@ -169,6 +169,7 @@ def test_render_img_matches_batch_path(built):
                                                                          cx=K["cx"] / 20, cy=K["cy"] / 20),
                          ray_batch_size=100)
     small.sigmoid_coefficient = 0.1
+    small.min_render_chunk = 1            # first pass: the reference's chunking (8 chunks of 100 rays)
     depth_img = O.synthetic_depth()[::20, ::20].contiguous().to(DEV)
     rq = {l: torch.full((24, 32), 0.16 if l == "fine" else 0.96, dtype=torch.float64, device=DEV) for l in cl}
     c2w = torch.eye(4, device=DEV)[:3]
@@ -176,7 +177,7 @@ def test_render_img_matches_batch_path(built):
                                npc_geo_feats={l: npc.get_geo_feats(l) for l in cl},
                                npc_col_feats={l: npc.get_col_feats(l) for l in cl}, dynamic_r_query=rq)
     assert d.shape == (24, 32) and c.shape == (24, 32, 3) and d.dtype == torch.float64
-    small.ray_batch_size = 768
+    small.min_render_chunk = 65536        # second pass: the default widening -> one chunk
     rq = {l: torch.full((24, 32), 0.16 if l == "fine" else 0.96, dtype=torch.float64, device=DEV) for l in cl}
     d2, u2, c2 = small.render_img(npc, dec, c2w, DEV, "color_fine", gt_depth=depth_img,
                                   npc_geo_feats={l: npc.get_geo_feats(l) for l in cl},
