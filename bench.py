@@ -8,7 +8,9 @@ features of the level, the colour decoder and (as in the reference) the geometry
 Workload at every N = BASELINE.json configs[1]: 5,000 rays (25,000 sample points) per GPU against a
 1M-point fine cloud (+250k mid), ScanNet intrinsics, synthetic data, random-init decoders (seed 1219).
 Weak scaling: every rank renders its own 5,000-ray shard of the global batch against the replicated cloud
-and the gradients are all-reduced (NCCL) - SURVEY 8e.
+and the gradients are all-reduced (NCCL) - SURVEY 8e.  At N > 1 the iteration is issued as two CUDA graphs (the
+parameter-free head = sampling + neighbour search | the rest) so that the all-reduce of step i overlaps the head of
+step i+1; it is started after the untimed L2 flush (it overlaps nothing untimed) and the last one is timed on its own.
 
 JSON line: see the driver's contract; `value` = rays/s with inputs resident in HBM (CUDA-event timed per
 step, L2 flushed between steps), `e2e` = same through the public API from pinned host buffers with the
