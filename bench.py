@@ -446,6 +446,9 @@ def run_ours(args, rank, world, local_rank):
         if world > 1:
             dist.destroy_process_group()
         return
+    tracking = None
+    if world == 1:
+        tracking = time_tracker(hps, npc, dec, renderer, scene, cfg, dev, gf, cf, pos)
     h2d = sum(v[0].numel() * v.element_size() for v in host_pk.values())
     line = {"metric": "mapping rays/sec (fwd+bwd)", "value": RAYS * world * args.steps / (dev_ms * 1e-3), "unit": "rays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -454,6 +457,8 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": RAYS * world * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "roofline": roof["roofline"], "kernels_ms_per_step": roof["per_kernel"]}
+    if tracking is not None:
+        line["tracking"] = tracking
     if world == 1:
         rps, sps = time_cpu(scene, CPU_SAMPLE_RAYS, 3, 1)
         line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": os.cpu_count() or 1, "kind": "port",
@@ -462,6 +467,62 @@ def run_ours(args, rank, world, local_rank):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_tracker(hps, npc, dec, renderer, scene, cfg, dev, gf, cf, pos, iters=100):
+    """The second half of BASELINE.json's metric: tracking iterations / s (Tracker.py:190-235) on the same scene - R = 5000
+    rays, stage color_fine, pose 7-vector + exposure latent under Adam, decoders frozen; the whole iteration (pose -> rays
+    -> render -> loss -> backward -> Adam) replayed from one CUDA graph, timed with CUDA events.  Extra key of the JSON
+    line, not part of `value`."""
+    K = cfg["cam"]
+    fine = scene["fine"]
+    rd0 = fine["rays_d"][:RAYS]
+    pi = (rd0[:, 0] * K["fx"] + K["cx"]).to(dev)
+    pj = (K["cy"] - rd0[:, 1] * K["fy"]).to(dev)
+    gt_d, gt_c = fine["gt_depth"][:RAYS].to(dev), fine["gt_color"][:RAYS].to(dev)
+    rq = {"fine": fine["radius"][:RAYS].to(dev), "mid": scene["radius_mid"][:RAYS].to(dev)}
+    feats_g = {l: (v.table if isinstance(v, hps.LiveRows) else v) for l, v in gf.items()}
+    feats_c = {l: (v.table if isinstance(v, hps.LiveRows) else v) for l, v in cf.items()}
+    req = [p.requires_grad for p in dec.parameters()]
+    for p in dec.parameters():
+        p.requires_grad_(False)
+    try:
+        cam = torch.tensor([1.0, 0.0, 0.0, 0.0, 0.005, -0.004, 0.003], device=dev).requires_grad_(True)
+        ef = scene["exposure_feat"].to(dev).clone().requires_grad_(True)
+        opt = torch.optim.Adam([cam, ef], lr=5e-4, capturable=True)
+        cam.grad, ef.grad = torch.zeros_like(cam), torch.zeros_like(ef)
+
+        def it():
+            opt.zero_grad(set_to_none=False)
+            c2w = hps.get_camera_from_tensor(cam)
+            ro, rd = hps.get_rays_from_uv(pi, pj, c2w, K["H"], K["W"], K["fx"], K["fy"], K["cx"], K["cy"], dev)
+            d, v, c, _ = renderer.render_batch_ray(npc, dec, rd, ro, dev, STAGE, gt_depth=gt_d, npc_geo_feats=feats_g,
+                                                   npc_col_feats=feats_c, is_tracker=True, cloud_pos=pos,
+                                                   dynamic_r_query=dict(rq), exposure_feat=ef)
+            loss = hps.tracker_loss(d, v, c, gt_d, gt_c, 0.5)
+            loss.backward()
+            opt.step()
+            return loss
+
+        g = hps.graphs.GraphedStep(it, {}, warmup=3)
+        for _ in range(5):
+            g()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(iters):
+            g()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / iters
+        return {"value": 1e3 / ms, "unit": "iters/s", "ms_per_iter": ms, "rays": RAYS, "stage": STAGE,
+                "note": "pose (7) + exposure latent (8) under Adam, decoders frozen, whole iteration replayed from one "
+                        "CUDA graph, back to back (no L2 flush), 1 GPU"}
+    except Exception as e:                                    # pragma: no cover - reported, never fatal
+        return {"value": None, "unit": "iters/s", "error": str(e).splitlines()[0][:160]}
+    finally:
+        for p, r in zip(dec.parameters(), req):
+            p.requires_grad_(r)
 
 
 def roofline(per, hps, npc, devb, sl):
