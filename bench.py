@@ -539,10 +539,10 @@ def roofline(per, hps, npc, devb, sl):
         work["hps_mlp_tc_fwd[%d]" % k] = work["hps_mlp_fwd[%d]" % k]
         work["hps_mlp_tc_bwd[%d]" % k] = work["hps_mlp_bwd[%d]" % k]
     # measured mean candidate count for the search figure
-    z, _ = None, None
-    q, cand = npc.query_neighbors((devb["rays_o"][sl][:, None, :] + devb["rays_d"][sl][:, None, :] *
-                                   (devb["gt_depth"][sl][:, None, None] * torch.linspace(0.96, 1.04, 5, device=devb["rays_o"].device)[None, :, None])).reshape(-1, 3),
-                                  step="query", dynamic_radius=devb["radius"][sl].repeat_interleave(5), level="fine",
+    dev = devb["rays_o"].device
+    z5 = devb["gt_depth"][sl][:, None, None] * torch.linspace(0.96, 1.04, 5, device=dev)[None, :, None]
+    pts = (devb["rays_o"][sl][:, None, :] + devb["rays_d"][sl][:, None, :] * z5).reshape(-1, 3)
+    _, cand = npc.query_neighbors(pts, step="query", dynamic_radius=devb["radius"][sl].repeat_interleave(5), level="fine",
                                   want_cand=True)
     mean_cand = float(cand.float().mean())
     work["hps_knn_query"] = ("hbm", (84.0 + 12.0 * mean_cand) * P)
