@@ -4,7 +4,7 @@ Host-side mirror of the reference's Python interface for this path (same class /
 argument meaning) over hand-written sm_100a kernels behind the C ABI in include/hps_b200.h.
 Importable as `hps_b200` (repo-root alias module) or importlib.import_module("hierarchical-point-slam_b200").
 """
-from . import _lib, graphs, ops, parallel  # noqa: F401
+from . import _lib, frame, graphs, ops, parallel  # noqa: F401
 from .config import scannet_cfg  # noqa: F401
 from .common import (get_camera_from_tensor, get_rays, get_rays_from_uv, quad2rotation,  # noqa: F401
                      raw2outputs_nerf_color)

@@ -68,3 +68,26 @@ def test_ops_refuse_cpu_tensors():
         ops.exposure_mlp(torch.zeros(8), torch.zeros(128, 8), torch.zeros(128), torch.zeros(12, 128), torch.zeros(12))
     with pytest.raises(Exception):
         ops.camera_from_tensor(torch.zeros(7))
+
+
+def test_dynamic_radius_maps_match_the_scipy_restatement():
+    """frame.dynamic_radius (Tracker.py:297-325, Mapper.py:1026-1050 as tensor ops) vs the numpy/scipy oracle restatement
+    of skimage 0.19.3's rgb2gray + sobel_h/sobel_v + interp1d: radii within 1e-9 m (float64 throughout, like the reference's numpy frames)."""
+    from oracle import hps_oracle as O
+    g = torch.Generator().manual_seed(9)
+    H, W = 60, 80
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.float32), torch.arange(W, dtype=torch.float32), indexing="ij")
+    img = torch.stack([0.5 + 0.5 * torch.sin(xx / 7), 0.5 + 0.5 * torch.cos(yy / 5), torch.rand(H, W, generator=g) * 0.3], -1)
+    img[20:30, 30:50] = 0.9                      # hard edges -> the clip at the threshold is exercised
+    cfg = hps.scannet_cfg("cpu")
+    rh, ratio, thr = cfg["pointcloud"]["radius_hierarchy"], cfg["pointcloud"]["radius_query_ratio"], cfg["pointcloud"]["color_grad_threshold"]
+    r_add, r_query = hps.frame.dynamic_radius(img, rh, ratio, thr)
+    ref = O.dynamic_radius_maps(img.numpy(), rh, ratio, thr)
+    for level in rh:
+        a, q = ref[level]
+        assert r_add[level].dtype == torch.float64 and r_add[level].shape == (H, W)
+        assert float((r_add[level] - torch.from_numpy(a)).abs().max()) < 1e-9
+        assert float((r_query[level] - torch.from_numpy(q)).abs().max()) < 1e-9
+        vals = list(rh[level].values())
+        assert float(r_add[level].max()) <= vals[0] + 1e-12 and float(r_add[level].min()) >= vals[1] - 1e-12
+        assert float(r_add[level].min()) < vals[0] - 1e-4        # the map is not constant on this image
