@@ -233,10 +233,11 @@ def test_tcgen05_descriptor_selftest(hps, N, K, a_major, b_major):
 
 @pytest.mark.parametrize("kind,P,affine", [("col", 1000, False), ("col", 130, True), ("geo", 1000, False), ("geo", 77, False),
                                            ("col", 40000, False), ("geo", 40000, False)])
-def test_mlp_tensor_core_forward_matches_simt(hps, golden, kind, P, affine):
-    """tcgen05 edition vs fp32 SIMT edition of the decoder forward: outputs and the activation workspace
-    (consumed by the backward) agree to 1e-5 (split-precision MMA, measured ~1e-6); gradients through the
-    SIMT backward fed by either forward agree to 1e-4."""
+def test_mlp_tensor_core_edition_matches_simt(hps, golden, kind, P, affine):
+    """tcgen05 edition (forward + dgrad / wgrad / wfinal backward) vs the fp32 SIMT edition of the decoders, up to the
+    bench's point count: outputs agree to 1e-5 (split-precision MMA, measured ~1e-6), input, feature and every
+    parameter gradient to 1e-4 - this is where the backward's dy-free algebra (dc through Q = W Wc, dWc / dbc through the
+    (H x 32) sums) is checked against a plain chain-rule implementation at scale."""
     scene = golden("scene_small.pt")
     name = "geo_decoder_fine" if kind == "geo" else "color_decoder_fine"
     g = torch.Generator().manual_seed(P)
