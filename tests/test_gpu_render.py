@@ -26,6 +26,29 @@ def test_mapper_iteration_matches_reference(built, stage, path):
     print(stage, errs)
 
 
+@pytest.mark.parametrize("switch", ["simt", "simt_bwd", "single_stream"])
+def test_mapper_iteration_other_kernel_editions(built, switch):
+    """The fused mapper iteration through the code paths the defaults do not take: fp32 SIMT decoders
+    (HPS_USE_TC=0), tensor-core forward with SIMT backward (HPS_USE_TC_BWD=0), and everything on one stream
+    (HPS_STREAMS=0) - same fixtures, same bar."""
+    scene, hps, npc, dec, renderer = built
+    ops = hps.ops
+    saved = (ops.USE_TC, ops.USE_TC_BWD, ops.MULTI_STREAM)
+    try:
+        if switch == "simt":
+            ops.USE_TC = False
+        elif switch == "simt_bwd":
+            ops.USE_TC_BWD = False
+        else:
+            ops.MULTI_STREAM = False
+        for stage in ("color_fine", "geometry_mid"):
+            ref = parity.load("render_mapper_small.pt")[stage]
+            out = parity.mapper_step(hps, npc, dec, renderer, scene, stage, DEV)
+            parity.check_mapper(stage, out, ref, dec)
+    finally:
+        ops.USE_TC, ops.USE_TC_BWD, ops.MULTI_STREAM = saved
+
+
 @pytest.mark.parametrize("path", ["fused", "modular"])
 @pytest.mark.parametrize("stage", ["color_mid", "color_fine"])
 def test_tracker_iteration_matches_reference(built, stage, path):
