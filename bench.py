@@ -50,9 +50,9 @@ def peaks():
 
 
 def make_scene(seed=1219):
-    from oracle import hps_oracle as O
-    fine = O.synthetic_scene(N_FINE, RAYS * N_BATCHES, (0.04, 0.16), seed=seed, extent_scale=EXTENT)
-    mid = O.synthetic_scene(N_MID, 8, (0.24, 0.96), seed=seed + 1, extent_scale=EXTENT)
+    import synthetic as S          # data generator only (the oracle is used by the CPU arm / cpu_baseline alone)
+    fine = S.synthetic_scene(N_FINE, RAYS * N_BATCHES, (0.04, 0.16), seed=seed, extent_scale=EXTENT)
+    mid = S.synthetic_scene(N_MID, 8, (0.24, 0.96), seed=seed + 1, extent_scale=EXTENT)
     g = torch.Generator().manual_seed(seed + 2)
     radius_mid = 0.24 + 0.72 * torch.rand(RAYS * N_BATCHES, generator=g, dtype=torch.float64)
     return dict(fine=fine, mid=mid, radius_mid=radius_mid,

@@ -14,7 +14,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-from oracle import hps_oracle as O  # noqa: E402  (scene generator only)
+import synthetic as O  # noqa: E402  (scene generator; the oracle is not used here)
 
 hps = importlib.import_module("hierarchical-point-slam_b200")
 dev = "cuda:0"
