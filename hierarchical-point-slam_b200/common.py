@@ -8,7 +8,7 @@ d/d rays_o, d/d rays_d into the quaternion - they are written 
 import numpy as np
 import torch
 
-from . import ops
+from . import frame, ops
 
 
 def raw2outputs_nerf_color(raw, z_vals, rays_d=None, occupancy=False, device="cuda:0", coef=0.1):
@@ -74,3 +74,153 @@ def get_rays(H, W, fx, fy, cx, cy, c2w, device, crop_edge=0):
     rays_d = torch.sum(dirs * c2w[:3, :3], -1)
     rays_o = c2w[:3, -1].expand(rays_d.shape)
     return rays_o, rays_d
+
+
+# ---- pixel / ray sampling that feeds the path.  Everything stays on the frame's device; the reference
+# ---- builds a dense (u,v) meshgrid per call and, for the gradient-guided variants, goes through skimage on the host.
+
+def random_select(l, k):
+    """k distinct values from range(l), numpy RNG like the reference (common.py:95-100)."""
+    return list(np.random.permutation(l)[:min(l, k)])
+
+
+def select_uv(i, j, n, depth, color, device="cuda:0"):
+    """n pixels drawn with replacement from dense (u,v) maps; common.py:122-137 (same torch.randint call, so the
+    same pixels for the same seed)."""
+    i, j = i.reshape(-1), j.reshape(-1)
+    pick = torch.randint(i.shape[0], (n,), device=device)
+    return i[pick], j[pick], depth.reshape(-1)[pick], color.reshape(-1, 3)[pick]
+
+
+def get_sample_uv(H0, H1, W0, W1, n, depth, color, device="cuda:0"):
+    """n (u,v) from the window rows H0..H1-1, columns W0..W1-1; common.py:159-171.  The reference materialises the
+    window's meshgrid (two (H1-H0, W1-W0) float maps per call) and gathers from it; the maps hold the integers
+    u = W0 + column, v = H0 + row exactly, so the draw is decoded arithmetically instead."""
+    rows, cols = H1 - H0, W1 - W0
+    pick = torch.randint(rows * cols, (n,), device=device)
+    r = torch.div(pick, cols, rounding_mode="floor")
+    c = pick - r * cols
+    return (c + W0).float(), (r + H0).float(), depth[r + H0, c + W0], color[r + H0, c + W0]
+
+
+def _depth_filter(sample_depth, depth_limit):
+    mask = sample_depth > 0
+    if depth_limit is not None:
+        mask = mask & (sample_depth < depth_limit)
+    return mask
+
+
+def get_samples(H0, H1, W0, W1, n, H, W, fx, fy, cx, cy, c2w, depth, color, device,
+                depth_filter=False, return_index=False, depth_limit=None):
+    """n rays from the window with their depth / colour (and pixel indices); common.py:236-258."""
+    i, j, sample_depth, sample_color = get_sample_uv(H0, H1, W0, W1, n, depth, color, device=device)
+    if depth_filter:
+        keep = _depth_filter(sample_depth, depth_limit)        # filtering before the ray kernel: same rays, less work
+        i, j, sample_depth, sample_color = i[keep], j[keep], sample_depth[keep], sample_color[keep]
+    rays_o, rays_d = get_rays_from_uv(i, j, c2w, H, W, fx, fy, cx, cy, device)
+    if return_index:
+        return rays_o, rays_d, sample_depth, sample_color, i.to(torch.int64), j.to(torch.int64)
+    return rays_o, rays_d, sample_depth, sample_color
+
+
+def _top_gradient_pixels(image, count, H0, H1, W0, W1):
+    """flat indices (int64, on image.device) of the `count` pixels with the largest Sobel colour-gradient magnitude
+    that also lie in the window, and the (H,W) float64 magnitude map; the host part of common.py:174-233."""
+    mag = frame.color_gradient_magnitude(image, float("inf"))
+    Himg, Wimg = mag.shape
+    top = torch.topk(mag.reshape(-1), min(count, mag.numel()), sorted=False).indices     # np.argpartition's set
+    h = torch.div(top, Wimg, rounding_mode="floor")
+    w = top - h * Wimg
+    inside = (h >= H0) & (h < H1) & (w >= W0) & (w < W1)
+    return top, h, w, inside, mag
+
+
+def get_sample_uv_with_grad(H0, H1, W0, W1, n, image):
+    """n distinct flat pixel indices among the top 5n colour-gradient pixels inside the window; common.py:174-196
+    (np.random.choice without replacement -> a device permutation)."""
+    top, _, _, inside, _ = _top_gradient_pixels(image, 5 * n, H0, H1, W0, W1)
+    cand = top[inside]
+    if cand.numel() < n:
+        raise ValueError("Cannot take a larger sample than population when 'replace=False'")
+    return cand[torch.randperm(cand.numel(), device=cand.device)[:n]]
+
+
+def get_selected_index_with_grad(H0, H1, W0, W1, n, image, ratio=15, gt_depth=None, depth_limit=False,
+                                 as_numpy=True):
+    """Flat indices of the top ratio*n colour-gradient pixels inside the window (with a depth reading, <= 5 m when
+    depth_limit) and the gradient-magnitude map; common.py:199-233.  as_numpy=True returns ndarrays like the
+    reference (one device->host read per frame); False keeps both on the device."""
+    top, h, w, keep, mag = _top_gradient_pixels(image, ratio * n, H0, H1, W0, W1)
+    if gt_depth is not None:
+        d = gt_depth[h, w]
+        keep = keep & (d > 0.0)
+        if depth_limit:
+            keep = keep & (d <= 5.0)
+    sel = top[keep]
+    if as_numpy:
+        return sel.cpu().numpy(), mag.cpu().numpy()
+    return sel, mag
+
+
+def get_samples_with_pixel_grad(H0, H1, W0, W1, num_tuple, H, W, fx, fy, cx, cy, c2w, depth, color, device, est_normal,
+                                depth_filter=True, return_index=True, depth_limit=None):
+    """Rays through the union of colour-gradient and normal-gradient guided pixels; common.py:261-301."""
+    n_color, n_normal = num_tuple
+    assert n_color > 0 or n_normal > 0, "invalid number of rays to sample."
+    picks = []
+    if n_color > 0:
+        picks.append(get_sample_uv_with_grad(H0, H1, W0, W1, n_color, color))
+    if n_normal > 0:
+        picks.append(get_sample_uv_with_grad(H0 + 10, H1 - 10, W0 + 10, W1 - 10, n_normal, est_normal))
+    merged = torch.unique(torch.cat(picks))                      # np.union1d: sorted, duplicates dropped
+    j = torch.div(merged, W, rounding_mode="floor")
+    i = merged - j * W
+    sample_depth, sample_color = depth[j, i], color[j, i]
+    if depth_filter:
+        keep = _depth_filter(sample_depth, depth_limit)
+        i, j, sample_depth, sample_color = i[keep], j[keep], sample_depth[keep], sample_color[keep]
+    rays_o, rays_d = get_rays_from_uv(i.float(), j.float(), c2w, H, W, fx, fy, cx, cy, device)
+    if return_index:
+        return rays_o, rays_d, sample_depth, sample_color, i, j
+    return rays_o, rays_d, sample_depth, sample_color
+
+
+def get_rotation_from_tensor(quad):
+    """(4,) or (B,4) quaternion -> (3,3) or (B,3,3); common.py:349-354."""
+    if quad.dim() == 1:
+        quad = quad.unsqueeze(0)
+    return quad2rotation(quad).squeeze(0)
+
+
+def get_tensor_from_camera(RT, Tquad=False):
+    """(3|4,4) camera matrix -> float32 [quat(w,x,y,z), T] (or [T, quat]); common.py:357-382.  The reference goes
+    through scipy on the host (Rotation.from_matrix(R).as_quat(), float64: nearest rotation by SVD, then the
+    largest-of-(diagonal, trace) branch, normalised); the same arithmetic runs here on RT's device and the result
+    stays there (the reference always hands back a CPU tensor, which its callers move to the device again)."""
+    if isinstance(RT, np.ndarray):
+        RT = torch.from_numpy(RT)
+    RT = RT.detach()
+    m = RT[:3, :3].to(torch.float64)
+    if torch.linalg.det(m) <= 0:
+        raise ValueError("Non-positive determinant (left-handed or null coordinate frame) in rotation matrix")
+    if not torch.allclose(m @ m.T, torch.eye(3, dtype=m.dtype, device=m.device), rtol=1e-5, atol=1e-12):
+        U, _, Vt = torch.linalg.svd(m)
+        m = U @ Vt
+    tr = m[0, 0] + m[1, 1] + m[2, 2]
+    choice = int(torch.argmax(torch.stack([m[0, 0], m[1, 1], m[2, 2], tr])))
+    q = torch.empty(4, dtype=m.dtype, device=m.device)             # (x, y, z, w)
+    if choice < 3:
+        a, b, c = choice, (choice + 1) % 3, (choice + 2) % 3
+        q[a] = 1 - tr + 2 * m[a, a]
+        q[b] = m[b, a] + m[a, b]
+        q[c] = m[c, a] + m[a, c]
+        q[3] = m[c, b] - m[b, c]
+    else:
+        q[0] = m[2, 1] - m[1, 2]
+        q[1] = m[0, 2] - m[2, 0]
+        q[2] = m[1, 0] - m[0, 1]
+        q[3] = 1 + tr
+    q = q / torch.linalg.norm(q)
+    quad = torch.roll(q, 1)                                          # (w, x, y, z)
+    T = RT[:3, 3].to(torch.float64)
+    return (torch.cat([T, quad]) if Tquad else torch.cat([quad, T])).float()

@@ -338,11 +338,11 @@ def rays_from_uv(i, j, c2w, fx, fy, cx, cy):
 # dynamic radius maps.  PARITY UNPINNED: skimage (rgb2gray, filters.sobel_h / sobel_v) is not
 # importable here; this restates scikit-image 0.19.3 (the reference's env.yaml pin) with scipy.ndimage.
 # ----------------------------------------------------------------------------------------------
-def dynamic_radius_maps(gt_color, radius_hierarchy, ratio, threshold):
-    """Tracker.py:297-325 / Mapper.py:1026-1050 in numpy + scipy: level -> (r_add, r_query) float64 (H,W) arrays."""
+def sobel_magnitude(gt_color):
+    """skimage rgb2gray -> filters.sobel_h / sobel_v -> magnitude (common.py:174-233, Tracker.py:297-325) restated with
+    scipy.ndimage; float64 (H,W).  PARITY UNPINNED (skimage is not installed here)."""
     import numpy as np
     from scipy import ndimage as ndi
-    from scipy.interpolate import interp1d
     img = np.asarray(gt_color, dtype=np.float64)          # frames are float64 here (datasets.py: uint8 / 255.)
     gray = img @ np.array([0.2125, 0.7154, 0.0721])
 
@@ -350,7 +350,14 @@ def dynamic_radius_maps(gt_color, radius_hierarchy, ratio, threshold):
         out = ndi.correlate1d(gray, [1, 0, -1], axis=axis, mode="reflect")
         return ndi.correlate1d(out, np.array([1, 2, 1]) / 4.0, axis=1 - axis, mode="reflect")
     gy, gx = sobel(0), sobel(1)
-    mag = np.clip(np.sqrt(gx ** 2 + gy ** 2), 0.0, threshold)
+    return np.sqrt(gx ** 2 + gy ** 2)
+
+
+def dynamic_radius_maps(gt_color, radius_hierarchy, ratio, threshold):
+    """Tracker.py:297-325 / Mapper.py:1026-1050 in numpy + scipy: level -> (r_add, r_query) float64 (H,W) arrays."""
+    import numpy as np
+    from scipy.interpolate import interp1d
+    mag = np.clip(sobel_magnitude(gt_color), 0.0, threshold)
     out = {}
     for level, d in radius_hierarchy.items():
         vals = list(d.values())

@@ -452,3 +452,38 @@ def test_tracker_loop_pose_trajectory_tracks_the_oracle(hps):
     # can be asserted: the first steps coincide (no systematic error) and the run stays within one Adam step (lr).
     assert max(dev_ours[:3]) <= 1e-5, (dev_ours, dev_ref)
     assert max(dev_ours) <= 2 * lr, (dev_ours, dev_ref)
+
+
+def test_pixel_sampling_on_device(hps, golden):
+    """get_samples / get_selected_index_with_grad / get_tensor_from_camera with CUDA inputs: nothing leaves the device,
+    the rays are bit-identical to the reference expressions evaluated on the same pixels, and the fixture values of
+    oracle/make_golden_sampling.py are reproduced where no RNG is involved."""
+    g = golden("sampling_small.pt")
+    fx, fy, cx, cy = g["intr"]
+    H, W = g["H"], g["W"]
+    depth, color, c2w = g["depth"].to(DEV), g["color"].to(DEV), g["c2w"].to(DEV)
+    torch.manual_seed(0)
+    ro, rd, sd, sc, i, j = hps.common.get_samples(4, H - 4, 6, W - 6, 500, H, W, fx, fy, cx, cy, c2w, depth, color, DEV,
+                                                  depth_filter=True, return_index=True, depth_limit=5.0)
+    for t in (ro, rd, sd, sc, i, j):
+        assert t.is_cuda
+    assert 0 < sd.shape[0] < 500 and bool(((sd > 0) & (sd < 5.0)).all())
+    assert int(i.min()) >= 6 and int(i.max()) < W - 6 and int(j.min()) >= 4 and int(j.max()) < H - 4
+    assert torch.equal(sd, depth[j, i]) and torch.equal(sc, color[j, i])
+    fi, fj = i.float(), j.float()
+    dirs = torch.stack([(fi - cx) / fx, -(fj - cy) / fy, -torch.ones_like(fi)], -1).reshape(-1, 1, 3)
+    assert torch.equal(rd, torch.sum(dirs * c2w[:3, :3], -1))                    # common.py:112-117
+    assert torch.equal(ro, c2w[:3, -1].expand(rd.shape))
+
+    sel, mag = hps.common.get_selected_index_with_grad(4, H - 4, 6, W - 6, 20, color, gt_depth=depth, depth_limit=True,
+                                                       as_numpy=False)
+    assert sel.is_cuda and mag.is_cuda
+    sel_c, mag_c = hps.common.get_selected_index_with_grad(4, H - 4, 6, W - 6, 20, color.cpu(), gt_depth=depth.cpu(),
+                                                           depth_limit=True, as_numpy=False)
+    assert torch.allclose(mag.cpu(), mag_c, rtol=0, atol=1e-14)
+    assert set(sel.tolist()) == set(sel_c.tolist())
+
+    for RT, (q, tq, _) in zip(g["mats"], g["quats"]):
+        mine = hps.common.get_tensor_from_camera(RT.to(DEV))
+        assert mine.is_cuda and torch.allclose(mine.cpu(), q, rtol=0, atol=2e-7)
+        assert torch.allclose(hps.common.get_tensor_from_camera(RT.to(DEV), Tquad=True).cpu(), tq, rtol=0, atol=2e-7)

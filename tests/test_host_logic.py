@@ -91,3 +91,113 @@ def test_dynamic_radius_maps_match_the_scipy_restatement():
         vals = list(rh[level].values())
         assert float(r_add[level].max()) <= vals[0] + 1e-12 and float(r_add[level].min()) >= vals[1] - 1e-12
         assert float(r_add[level].min()) < vals[0] - 1e-4        # the map is not constant on this image
+
+
+# ---- pixel / ray sampling and pose conversion against the reference's own outputs -------------------
+
+def test_get_samples_matches_reference_fixture(golden):
+    """Same torch seed -> same torch.randint draw -> the very same rays, depths, colours and pixel indices as the
+    reference's get_samples (common.py:236-258), bit for bit (fixture: oracle/make_golden_sampling.py)."""
+    g = golden("sampling_small.pt")
+    fx, fy, cx, cy = g["intr"]
+    for case in g["cases"]:
+        H0, H1, W0, W1 = case["window"]
+        torch.manual_seed(case["seed"])
+        out = hps.common.get_samples(H0, H1, W0, W1, case["n"], g["H"], g["W"], fx, fy, cx, cy, g["c2w"], g["depth"],
+                                     g["color"], "cpu", depth_filter=case["depth_filter"], return_index=True,
+                                     depth_limit=case["depth_limit"])
+        assert len(out) == 6
+        for name, a, b in zip(("rays_o", "rays_d", "depth", "color", "i", "j"), out, case["out"]):
+            assert a.dtype == b.dtype and a.shape == b.shape, (case["seed"], name)
+            assert torch.equal(a, b), (case["seed"], name)
+        four = None
+        torch.manual_seed(case["seed"])
+        four = hps.common.get_samples(H0, H1, W0, W1, case["n"], g["H"], g["W"], fx, fy, cx, cy, g["c2w"], g["depth"],
+                                      g["color"], "cpu", depth_filter=case["depth_filter"],
+                                      depth_limit=case["depth_limit"])
+        assert len(four) == 4 and torch.equal(four[1], case["out"][1])
+    torch.manual_seed(9)
+    uv = hps.common.get_sample_uv(3, 40, 2, 60, 100, g["depth"], g["color"], device="cpu")
+    for a, b in zip(uv, g["uv"]):
+        assert a.dtype == b.dtype and torch.equal(a, b)
+
+
+def test_select_uv_draws_like_a_dense_gather():
+    H, W = 12, 9
+    i, j = torch.meshgrid(torch.arange(W).float(), torch.arange(H).float(), indexing="ij")
+    i, j = i.t(), j.t()
+    depth, color = torch.rand(H, W), torch.rand(H, W, 3)
+    torch.manual_seed(3)
+    si, sj, sd, sc = hps.common.select_uv(i, j, 40, depth, color, device="cpu")
+    torch.manual_seed(3)
+    pick = torch.randint(H * W, (40,))
+    assert torch.equal(si, (pick % W).float()) and torch.equal(sj, (pick // W).float())
+    assert torch.equal(sd, depth.reshape(-1)[pick]) and torch.equal(sc, color.reshape(-1, 3)[pick])
+
+
+def test_get_tensor_from_camera_matches_reference_fixture(golden):
+    """All four branches of the matrix -> quaternion conversion (largest of m00, m11, m22, trace) against the
+    reference's scipy route (common.py:357-382); float64 arithmetic on both sides, so float32 results agree to the
+    last bit or one ulp."""
+    g = golden("sampling_small.pt")
+    for RT, (q, tq, q_np) in zip(g["mats"], g["quats"]):
+        mine = hps.common.get_tensor_from_camera(RT)
+        assert mine.dtype == torch.float32 and mine.shape == (7,)
+        assert torch.allclose(mine, q, rtol=0, atol=2e-7), (mine, q)
+        assert torch.allclose(hps.common.get_tensor_from_camera(RT, Tquad=True), tq, rtol=0, atol=2e-7)
+        assert torch.allclose(hps.common.get_tensor_from_camera(RT[:3].numpy()), q_np, rtol=0, atol=2e-7)
+        back = hps.common.get_camera_from_tensor(mine)            # and round trip through the path's own helper
+        assert torch.allclose(back, RT[:3], atol=2e-6)
+    with pytest.raises(ValueError):
+        hps.common.get_tensor_from_camera(torch.diag(torch.tensor([1.0, 1.0, -1.0, 1.0])))
+
+
+def test_rotation_from_tensor_shapes():
+    q = torch.randn(4, 4)
+    R = hps.common.get_rotation_from_tensor(q)
+    assert R.shape == (4, 3, 3)
+    assert torch.allclose(R @ R.transpose(1, 2), torch.eye(3).expand(4, 3, 3), atol=1e-5)
+    assert torch.equal(hps.common.get_rotation_from_tensor(q[2]), R[2])
+
+
+def test_gradient_guided_pixel_selection():
+    """get_selected_index_with_grad / get_sample_uv_with_grad (common.py:174-233; PARITY UNPINNED - skimage is not
+    installed) against the Sobel restatement the dynamic-radius oracle uses: the selected set is the top ratio*n
+    gradient pixels, restricted to the window and to pixels with a (limited) depth reading."""
+    from oracle import hps_oracle as O
+    import numpy as np
+    g = torch.Generator().manual_seed(5)
+    H, W, n, ratio = 40, 56, 20, 15
+    img = torch.rand(H, W, 3, generator=g, dtype=torch.float64)
+    depth = 1 + 5 * torch.rand(H, W, generator=g)
+    depth[torch.rand(H, W, generator=g) < 0.2] = 0
+    sel, mag = hps.common.get_selected_index_with_grad(4, H - 4, 6, W - 6, n, img, ratio=ratio, gt_depth=depth,
+                                                       depth_limit=True)
+    assert isinstance(sel, np.ndarray) and isinstance(mag, np.ndarray) and mag.shape == (H, W)
+    want_mag = O.sobel_magnitude(img.numpy())
+    assert np.allclose(mag, want_mag, rtol=0, atol=1e-14)
+    top = np.argpartition(want_mag, -ratio * n, axis=None)[-ratio * n:]
+    hh, ww = np.unravel_index(top, (H, W))
+    keep = (hh >= 4) & (hh < H - 4) & (ww >= 6) & (ww < W - 6)
+    d = depth.numpy()[hh, ww]
+    keep &= (d > 0) & (d <= 5.0)
+    assert set(sel.tolist()) == set(top[keep].tolist())
+    sel_t, mag_t = hps.common.get_selected_index_with_grad(4, H - 4, 6, W - 6, n, img, ratio=ratio, as_numpy=False)
+    assert torch.is_tensor(sel_t) and sel_t.dtype == torch.int64 and torch.is_tensor(mag_t)
+    keep0 = (hh >= 4) & (hh < H - 4) & (ww >= 6) & (ww < W - 6)
+    assert set(sel_t.tolist()) == set(top[keep0].tolist())
+
+    torch.manual_seed(0)
+    picks = hps.common.get_sample_uv_with_grad(0, H, 0, W, n, img)
+    assert picks.shape == (n,) and len(set(picks.tolist())) == n
+    top5 = set(np.argpartition(want_mag, -5 * n, axis=None)[-5 * n:].tolist())
+    assert set(picks.tolist()) <= top5
+
+    c2w = torch.eye(4)
+    out = hps.common.get_samples_with_pixel_grad(0, H, 0, W, (n, n), H, W, 50.0, 50.0, W / 2, H / 2, c2w,
+                                                 depth, img.float(), "cpu", est_normal=img.flip(0))
+    ro, rd, sd, sc, i, j = out
+    assert i.dtype == torch.int64 and torch.equal(sd, depth[j, i]) and torch.equal(sc, img.float()[j, i])
+    assert bool((sd > 0).all()) and torch.equal(torch.unique(j * W + i), j * W + i)      # sorted, distinct (union1d)
+    want_o, want_d = hps.common.get_rays_from_uv(i.float(), j.float(), c2w, H, W, 50.0, 50.0, W / 2, H / 2, "cpu")
+    assert torch.equal(rd, want_d) and torch.equal(ro, want_o)
