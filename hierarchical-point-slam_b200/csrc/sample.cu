@@ -20,7 +20,7 @@ __device__ __forceinline__ float linspace01(int i, int S) {
 
 __global__ void sample_rays_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
                                    const float* __restrict__ gt_depth, const double* __restrict__ radius,
-                                   double radius_scalar, const float* __restrict__ z_zero, int64_t R, int S,
+                                   double radius_scalar, const float* __restrict__ z_zero, int64_t zstride, int64_t R, int S,
                                    float near, float far, float* __restrict__ z, float* __restrict__ pts,
                                    float* __restrict__ t_up, float* __restrict__ t_dn) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -33,7 +33,7 @@ __global__ void sample_rays_kernel(const float* __restrict__ rays_o, const float
         const float t = linspace01(s, S);
         zz = __fadd_rn(__fmul_rn(__fmul_rn(near, d), __fsub_rn(1.0f, t)), __fmul_rn(__fmul_rn(far, d), t));
     } else {
-        zz = z_zero ? __ldg(z_zero + s) : 0.f;
+        zz = z_zero ? __ldg(z_zero + r * zstride + s) : 0.f;
     }
     z[i] = zz;
 #pragma unroll
@@ -68,14 +68,15 @@ __global__ void sample_rays_bwd_kernel(const float* __restrict__ dp, const float
 }  // namespace hps
 
 extern "C" int hps_sample_rays(const float* rays_o, const float* rays_d, const float* gt_depth, const double* radius,
-                               double radius_scalar, const float* z_zero, int64_t R, int S, float near, float far,
-                               float* z, float* pts, float* t_up, float* t_dn, void* stream) {
+                               double radius_scalar, const float* z_zero, int64_t z_zero_stride, int64_t R, int S,
+                               float near, float far, float* z, float* pts, float* t_up, float* t_dn, void* stream) {
     using namespace hps;
     HPS_REQUIRE(R >= 0 && S >= 1 && S <= 32, "need R >= 0, 1 <= S <= 32");
+    HPS_REQUIRE(z_zero_stride == 0 || z_zero_stride >= S, "z_zero_stride must be 0 (shared row) or >= S");
     if (R == 0) return 0;
     HPS_REQUIRE(rays_o && rays_d && gt_depth && z && pts && t_up && t_dn, "null buffer");
     sample_rays_kernel<<<(unsigned)ceil_div(R * S, 256), 256, 0, (cudaStream_t)stream>>>(
-        rays_o, rays_d, gt_depth, radius, radius_scalar, z_zero, R, S, near, far, z, pts, t_up, t_dn);
+        rays_o, rays_d, gt_depth, radius, radius_scalar, z_zero, z_zero_stride, R, S, near, far, z, pts, t_up, t_dn);
     HPS_LAUNCH_OK();
     return 0;
 }

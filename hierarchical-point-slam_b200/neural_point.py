@@ -355,5 +355,46 @@ class NeuralPointCloud(object):
         q = self.query_neighbors(pos, step, is_pts_grad, dynamic_radius, level)
         return q.D, q.I.long(), q.count
 
-    def sample_near_pcl(self, *a, **k):
-        raise NotImplementedError("rendering.sample_near_pcl is False in the ScanNet configuration (SURVEY 8f-4)")
+    def sample_near_pcl(self, rays_o, rays_d, near, far, num, dynamic_r_query=None, level=None):
+        """For rays without a depth reading: probe 25 positions between near and far, and sample `num` depths between
+        the FIRST TWO probes that have a neighbour within the query radius (neural_point.py:443-495; the reference
+        takes entries [0] and [1] of the hit list, not the first and the last).  Rays with fewer than two hits keep
+        linspace(near, far, num) and are flagged.  -> (z_vals (n_rays, num) float32, invalid (n_rays,) bool).
+
+        One neighbour-count query on the device replaces the reference's 65,000-point faiss batches, numpy
+        round trip and per-ray Python list; the float64 np.linspace arithmetic (start + i*step, last = stop) is kept.
+        dynamic_r_query: None (the fixed query radius - the only form the reference accepts, its dict form trips the
+        shape assert at neural_point.py:411), or a radius per ray / per probe."""
+        rays_o, rays_d = rays_o.reshape(-1, 3).float(), rays_d.reshape(-1, 3).float()
+        n_rays, probes, dev = rays_d.shape[0], 25, rays_o.device
+        far32 = torch.as_tensor(far, dtype=torch.float32, device=dev).reshape(())
+        idx = torch.arange(probes, device=dev, dtype=torch.float32)
+        step = (far32 - near) / (probes - 1)                            # torch.linspace's float32 arithmetic
+        z_probe = torch.where(idx < probes // 2, near + step * idx, far32 - step * (probes - 1 - idx))
+        pts = (rays_o[:, None, :] + rays_d[:, None, :] * z_probe[:, None]).reshape(-1, 3)
+        radius = dynamic_r_query[level] if isinstance(dynamic_r_query, dict) else dynamic_r_query
+        if radius is None:
+            radius = self.radius_query
+        else:
+            radius = radius.reshape(-1)
+            if radius.numel() == n_rays:
+                radius = radius.repeat_interleave(probes)
+            assert radius.numel() == pts.shape[0], "shape mis-match for input points and dynamic radius"
+        hit = (self.index[level].radius_search(pts, radius).count > 0).reshape(n_rays, probes)
+        invalid = hit.sum(-1) < 2
+        rank = hit.cumsum(-1)
+        first = ((rank == 1) & hit).int().argmax(-1)
+        second = ((rank == 2) & hit).int().argmax(-1)
+
+        def linspace64(start, stop, count):                               # np.linspace, float64, endpoint=True
+            i = torch.arange(count, device=dev, dtype=torch.float64)
+            out = i * ((stop - start) / (count - 1))[..., None] + start[..., None]
+            out[..., -1] = stop
+            return out
+
+        near64 = torch.full((), float(near), dtype=torch.float64, device=dev)
+        far64 = far32.double()
+        section = linspace64(near64, far64, probes)
+        z = linspace64(section[first], section[second], num)
+        z = torch.where(invalid[:, None], linspace64(near64, far64, num)[None, :], z)
+        return z.float(), invalid

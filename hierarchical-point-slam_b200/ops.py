@@ -562,6 +562,17 @@ class RayPrep:
     __slots__ = ("z", "pts", "t_up", "t_dn", "I", "D", "cnt", "R", "S")
 
 
+def _z_zero_stride(zz, R, S):
+    """z for rays without a depth reading: one shared row (S,) -> stride 0, or one row per ray (R,S) -> stride S."""
+    if zz is None or zz.dim() == 1:
+        if zz is not None and zz.numel() != S:
+            raise ValueError("z_zero must hold S values (shared) or R x S (per ray)")
+        return 0
+    if tuple(zz.shape) != (R, S):
+        raise ValueError("z_zero must hold S values (shared) or R x S (per ray)")
+    return S
+
+
 def prepare_rays(grid, rays_o, rays_d, gt_depth, radius, S, near, far, z_zero=None, out=None):
     """Sampling + neighbour search for R rays (two kernel launches).  `out`: a RayPrep to refill in place."""
     _need_cuda(rays_o, rays_d, gt_depth)
@@ -585,7 +596,8 @@ def prepare_rays(grid, rays_o, rays_d, gt_depth, radius, S, near, far, z_zero=No
         pr.cnt = torch.empty(P, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
         _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t),
-              0.0 if rad_t is not None else float(radius), _lib.ptr(zz), R, S, float(near), float(far),
+              0.0 if rad_t is not None else float(radius), _lib.ptr(zz), _z_zero_stride(zz, R, S), R, S, float(near),
+              float(far),
               _lib.ptr(pr.z), _lib.ptr(pr.pts), _lib.ptr(pr.t_up), _lib.ptr(pr.t_dn), _stream())
         _call("hps_knn_query", grid._h, _lib.ptr(pr.pts), _lib.ptr(pr.t_up), _lib.ptr(pr.t_dn), P, _lib.ptr(pr.I),
               _lib.ptr(pr.D), _lib.ptr(pr.cnt), None, 5 if (S == 5 and P >= KNN_GROUP_MIN_QUERIES) else 1, _stream())
@@ -700,7 +712,8 @@ class _RenderRays(torch.autograd.Function):
                     _call("hps_mlp_tc_bwd_pack", MLP_GEO, garr, _lib.ptr(bpk_g), _stream(aux))
             if prep is None:
                 _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t),
-                      0.0 if rad_t is not None else float(rad), _lib.ptr(zz), R, S, float(spec.near), float(spec.far),
+                      0.0 if rad_t is not None else float(rad), _lib.ptr(zz), _z_zero_stride(zz, R, S), R, S,
+                      float(spec.near), float(spec.far),
                       _lib.ptr(z), _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), st())
                 _call("hps_knn_query", spec.grid._h, _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), P, _lib.ptr(I),
                       _lib.ptr(D), _lib.ptr(cnt), None, 5 if (S == 5 and P >= KNN_GROUP_MIN_QUERIES) else 1, st())

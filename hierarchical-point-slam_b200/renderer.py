@@ -11,6 +11,14 @@ from . import ops
 from .common import get_rays
 
 
+def _linspace32(start, end, steps, device):
+    """torch.linspace(start, end, steps) in float32 for a 0-d tensor `end`, with the CUDA kernel's arithmetic
+    (step = (end - start) / (steps - 1); first half start + step*i, second half end - step*(steps-1-i))."""
+    idx = torch.arange(steps, device=device, dtype=torch.float32)
+    step = (end - start) / (steps - 1)
+    return torch.where(idx < steps // 2, start + step * idx, end - step * (steps - 1 - idx))
+
+
 class Renderer(object):
     def __init__(self, cfg, args=None, slam=None, points_batch_size=500000, ray_batch_size=3000):
         self.ray_batch_size = ray_batch_size
@@ -32,9 +40,9 @@ class Renderer(object):
         self.assume_positive_depth = False
         self.write_back_radius = True        # see render_batch_ray
         self.min_render_chunk = 65536        # see render_img
-        if self.N_samples > 0 or self.use_bound or self.sample_near_pcl or self.fix_interval or not self.occupancy:
-            raise NotImplementedError("only the reference's ScanNet rendering mode is built: N_samples=0, "
-                                      "use_bound False, sample_near_pcl False, occupancy True")
+        if self.N_samples > 0 or self.use_bound or self.fix_interval or not self.occupancy:
+            raise NotImplementedError("only the reference's live rendering modes are built: N_samples=0, "
+                                      "use_bound False, occupancy True (sample_near_pcl either way)")
         if slam is not None:
             self.H, self.W, self.fx, self.fy, self.cx, self.cy = slam.H, slam.W, slam.fx, slam.fy, slam.cx, slam.cy
 
@@ -70,17 +78,33 @@ class Renderer(object):
         z[nz, :] = self.near_end_surface * d * (1. - t) + self.far_end_surface * d * t
         return z, nz
 
-    def _z_for_zero_depth(self, gt_depth, device):
-        """linspace(near_end, max(far)) for rays without a depth reading (Renderer.py:133-134,148-153,207-208),
-        evaluated with device ops only (no host synchronisation)."""
-        S = self.N_surface
+    def _far_end(self, gt_depth):
+        """0-d tensor max(far): clamp(min(5 mean(d), max(1.2 d)), 0, max(1.2 d)) when any depth is positive, else the
+        unclamped bound (Renderer.py:133-134,148-153); device ops only (no host synchronisation)."""
         gt = gt_depth.reshape(-1).float()
         hi = torch.max(gt * 1.2)
         far_bb = torch.minimum(5 * gt.mean(), hi)
-        far = torch.where(hi > 0, torch.clamp(far_bb, min=0.0).minimum(hi), far_bb)   # clamp(far_bb, 0, max(1.2 d))
-        idx = torch.arange(S, device=device, dtype=torch.float32)
-        step = (far - self.near_end) / (S - 1)
-        return torch.where(idx < S // 2, self.near_end + step * idx, far - step * (S - 1 - idx))
+        return torch.where(hi > 0, torch.clamp(far_bb, min=0.0).minimum(hi), far_bb)
+
+    def _z_for_zero_depth(self, gt_depth, device):
+        """linspace(near_end, max(far)) for rays without a depth reading (Renderer.py:207-208)."""
+        return _linspace32(self.near_end, self._far_end(gt_depth), self.N_surface, device)
+
+    def _z_near_pcl(self, npc, rays_o, rays_d, gt_depth, radius, level):
+        """sample_near_pcl mode (Renderer.py:196-206): rays without a depth reading are sampled between the first two
+        of 25 probe positions that have neighbours in the cloud.  -> (z rows (R,S) - only the zero-depth rows are
+        read by the sampling kernel -, mask_rays_near_pcl (R,) bool)."""
+        R, S, dev = rays_o.shape[0], self.N_surface, rays_o.device
+        none = torch.nonzero(~(gt_depth > 0)).squeeze(1)              # the mode's one host synchronisation
+        z_rows = torch.zeros(R, S, device=dev)
+        near_mask = torch.ones(R, dtype=torch.bool, device=dev)
+        if none.numel():
+            rad = radius[none] if torch.is_tensor(radius) else None
+            z0, not_near = npc.sample_near_pcl(rays_o[none].detach(), rays_d[none].detach(), self.near_end,
+                                               self._far_end(gt_depth), S, rad, level)
+            z_rows[none] = z0
+            near_mask[none[not_near]] = False
+        return z_rows, near_mask
 
     # Renderer.py:84-254
     def prepare_batch(self, npc, rays_d, rays_o, stage, gt_depth, dynamic_r_query=None, out=None):
@@ -91,6 +115,9 @@ class Renderer(object):
         gt_depth = gt_depth.reshape(-1)
         radius = dynamic_r_query[level].reshape(-1) if self.use_dynamic_radius else npc.get_radius_query()
         index = npc.get_index(level)
+        if self.sample_near_pcl and not self.assume_positive_depth:
+            raise NotImplementedError("prepare_batch serves depth-filtered batches; sample_near_pcl needs the "
+                                      "near-cloud mask of render_batch_ray")
         return ops.prepare_rays(index.grid_for(radius), rays_o, rays_d, gt_depth, radius, self.N_surface,
                                 self.near_end_surface, self.far_end_surface,
                                 None if self.assume_positive_depth else self._z_for_zero_depth(gt_depth, rays_o.device),
@@ -122,6 +149,13 @@ class Renderer(object):
         else:
             radius = npc.get_radius_query()
         index = npc.get_index(level)
+        near_mask = None
+        if self.assume_positive_depth:
+            z_zero = None
+        elif self.sample_near_pcl:
+            z_zero, near_mask = self._z_near_pcl(npc, rays_o, rays_d, gt_depth, radius, level)
+        else:
+            z_zero = self._z_for_zero_depth(gt_depth, device)
         geo = getattr(decoders, "geo_decoder_" + level)
         col = getattr(decoders, "color_decoder_" + level)
         affine = None
@@ -129,7 +163,7 @@ class Renderer(object):
             affine = col.mlp_exposure(exposure_feat)                     # decoder.py:608
         spec = ops.RenderSpec(
             grid=index.grid_for(radius), radius=radius,
-            z_zero=None if self.assume_positive_depth else self._z_for_zero_depth(gt_depth, device), S=S,
+            z_zero=z_zero, S=S,
             near=self.near_end_surface, far=self.far_end_surface, coef=self.sigmoid_coefficient,
             min_nn=geo.min_nn_num, min_valid=int(S / 2 + 1), color_stage=color_stage, tracker=bool(is_tracker),
             cloud_pos=cloud_pos[level] if is_tracker else None, fill_geo=decoders._fill("geo", rays_o.device),
@@ -141,7 +175,10 @@ class Renderer(object):
             depth = torch.where(gt_depth > 0, depth, torch.zeros_like(depth))     # Renderer.py:250-251
         if self.skip_zero_depth_pixel:
             color = torch.where((gt_depth > 0)[:, None], color, torch.zeros_like(color))
-        return depth, uncertainty, color, valid.view(torch.bool)
+        valid = valid.view(torch.bool)
+        if near_mask is not None:
+            valid = valid & near_mask                                              # Renderer.py:247-248
+        return depth, uncertainty, color, valid
 
     def render_batch_ray_modular(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None,
                                  npc_geo_feats=None, npc_col_feats=None, is_tracker=False, cloud_pos=None,
@@ -153,7 +190,15 @@ class Renderer(object):
         if gt_depth is None or torch.numel(gt_depth) == 0:
             gt_depth = torch.zeros(N_rays, device=device)
         z_vals, nz = self.surface_samples(gt_depth, device)
-        z_vals = torch.where(nz[:, None], z_vals, self._z_for_zero_depth(gt_depth, device)[None, :].expand_as(z_vals))
+        near_mask = None
+        if self.sample_near_pcl:
+            level = "mid" if stage.endswith("mid") else "fine"
+            radius = dynamic_r_query[level].reshape(-1) if self.use_dynamic_radius else None
+            z_rows, near_mask = self._z_near_pcl(npc, rays_o, rays_d, gt_depth.reshape(-1), radius, level)
+            z_vals = torch.where(nz[:, None], z_vals, z_rows)
+        else:
+            z_vals = torch.where(nz[:, None], z_vals,
+                                 self._z_for_zero_depth(gt_depth, device)[None, :].expand_as(z_vals))
         pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]      # Renderer.py:218-219
         pointsf = pts.reshape(-1, 3)
         rq = None
@@ -171,6 +216,8 @@ class Renderer(object):
             depth = torch.where(nz, depth, torch.zeros_like(depth))
         if self.skip_zero_depth_pixel:
             color = torch.where(nz[:, None], color, torch.zeros_like(color))
+        if near_mask is not None:
+            valid_ray_mask = valid_ray_mask & near_mask
         return depth, uncertainty, color, valid_ray_mask
 
     # Renderer.py:256-337

@@ -190,13 +190,14 @@ int hps_exposure_bwd(const float* x, const float* W1, const float* W2, const flo
 /* ------------------------------------------------------------------------------------------------
  * Depth-guided sampling (Renderer.py:163-229, N_samples = 0) + per-point radius thresholds.
  *   z[r][s] = near*d*(1-t_s) + far*d*t_s, t = linspace(0,1,S); pts = rays_o + rays_d*z (no FMA);
- *   rays with gt_depth == 0 take z_zero[s] (S floats on the device, may be NULL -> 0).
+ *   rays with gt_depth == 0 take z_zero[r*z_zero_stride + s]: z_zero_stride 0 = one shared row of S floats
+ *   (Renderer.py:207-208), S = one row per ray (the sample_near_pcl mode, Renderer.py:197-206); NULL -> 0.
  *   radius: per-RAY float64 radii (may be NULL -> radius_scalar), repeated per sample into t_up/t_dn.
  * hps_sample_rays_bwd: g_rays_o = sum_s dp, g_rays_d = sum_s dp * z (tracker pose path).
  * ---------------------------------------------------------------------------------------------- */
 int hps_sample_rays(const float* rays_o, const float* rays_d, const float* gt_depth, const double* radius,
-                    double radius_scalar, const float* z_zero, int64_t R, int S, float near, float far,
-                    float* z, float* pts, float* t_up, float* t_dn, void* stream);
+                    double radius_scalar, const float* z_zero, int64_t z_zero_stride, int64_t R, int S, float near,
+                    float far, float* z, float* pts, float* t_up, float* t_dn, void* stream);
 int hps_sample_rays_bwd(const float* dp, const float* z, int64_t R, int S, float* g_rays_o, float* g_rays_d,
                         void* stream);
 

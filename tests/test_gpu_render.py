@@ -134,7 +134,7 @@ def test_sampling_kernel_is_bit_identical_to_torch_ops(built):
     z = torch.empty(R, S, device=DEV); pts = torch.empty(R * S, 3, device=DEV)
     t_up = torch.empty(R * S, device=DEV); t_dn = torch.empty(R * S, device=DEV)
     L = hps._lib
-    hps.ops._call("hps_sample_rays", L.ptr(ro), L.ptr(rd), L.ptr(gd), L.ptr(rad), 0.0, L.ptr(zz), R, S, 0.96, 1.04,
+    hps.ops._call("hps_sample_rays", L.ptr(ro), L.ptr(rd), L.ptr(gd), L.ptr(rad), 0.0, L.ptr(zz), 0, R, S, 0.96, 1.04,
                   L.ptr(z), L.ptr(pts), L.ptr(t_up), L.ptr(t_dn), hps.ops._stream())
     z_ref, nz = renderer.surface_samples(gd, DEV)
     z_ref = torch.where(nz[:, None], z_ref, zz[None, :].expand_as(z_ref))
@@ -487,3 +487,79 @@ def test_pixel_sampling_on_device(hps, golden):
         mine = hps.common.get_tensor_from_camera(RT.to(DEV))
         assert mine.is_cuda and torch.allclose(mine.cpu(), q, rtol=0, atol=2e-7)
         assert torch.allclose(hps.common.get_tensor_from_camera(RT.to(DEV), Tquad=True).cpu(), tq, rtol=0, atol=2e-7)
+
+
+def test_sample_near_pcl_matches_reference(built, golden):
+    """NeuralPointCloud.sample_near_pcl against the reference's own function (neural_point.py:443-495; fixture:
+    oracle/make_golden_near_pcl.py): the not-near-the-cloud mask and the float32 sample depths, bit for bit, for the
+    fixed query radius and for a radius per probe."""
+    scene, hps, npc, dec, renderer = built
+    g = golden("near_pcl_small.pt")
+    none = ~(g["gt_depth"] > 0)
+    ro, rd = scene["rays"]["rays_o"][none].to(DEV), g["rays_d"][none].to(DEV)
+    keep = npc.radius_query
+    try:
+        for stage, s in g["stages"].items():
+            level = "mid" if stage.endswith("mid") else "fine"
+            npc.radius_query = g["radius_query"][level]
+            z, invalid = npc.sample_near_pcl(ro, rd, s["near"], s["far"].to(DEV), 5, None, level)
+            assert z.dtype == torch.float32 and z.shape == (int(none.sum()), 5)
+            assert torch.equal(invalid.cpu(), s["invalid"]), stage
+            assert torch.equal(z.cpu(), s["z"]), (stage, float((z.cpu() - s["z"]).abs().max()))
+            z, invalid = npc.sample_near_pcl(ro, rd, s["near"], s["far"].to(DEV), 5, s["r_probe"].to(DEV), level)
+            assert torch.equal(invalid.cpu(), s["invalid_dyn"]) and torch.equal(z.cpu(), s["z_dyn"]), stage
+    finally:
+        npc.radius_query = keep
+    assert 0 < int(g["stages"]["color_fine"]["invalid"].sum()) < int(none.sum())      # the fixture has both kinds
+
+
+@pytest.mark.parametrize("dynamic", [False, True])
+def test_sample_near_pcl_render_mode(built, golden, dynamic):
+    """rendering.sample_near_pcl = True (Renderer.py:196-206,247-251): depth-less rays are sampled near the cloud (one
+    z row per ray through hps_sample_rays' z_zero_stride), keep their rendered depth, and are masked out when the
+    cloud is not near.  The reference's call site cannot run (oracle/make_golden_near_pcl.py); the fused path is
+    checked against the modular path and against sample_near_pcl's own output."""
+    import types
+    scene, hps, npc, dec, _ = built
+    g = golden("near_pcl_small.pt")
+    cfg = hps.scannet_cfg(DEV)
+    cfg["rendering"]["sample_near_pcl"] = True
+    cfg["use_dynamic_radius"] = dynamic
+    rend = hps.Renderer(cfg, None, types.SimpleNamespace(**O.SCANNET_INTRINSICS))
+    rend.sigmoid_coefficient = scene["cfg"]["coef"]
+    gt = g["gt_depth"].to(DEV)
+    ro, rd = scene["rays"]["rays_o"].to(DEV), g["rays_d"].to(DEV)
+    cl = scene["clouds"]
+    gf = {l: cl[l]["geo_feats"].to(DEV) for l in cl}
+    cf = {l: cl[l]["col_feats"].to(DEV) for l in cl}
+    keep = npc.radius_query
+    try:
+        for stage in ("geometry_mid", "color_fine"):
+            level = "mid" if stage.endswith("mid") else "fine"
+            npc.radius_query = g["radius_query"][level]
+            rq = lambda: {l: cl[l]["radius"].to(DEV).clone() for l in cl} if dynamic else None
+            with torch.no_grad():
+                d1, u1, c1, v1 = rend.render_batch_ray(npc, dec, rd, ro, DEV, stage, gt_depth=gt, npc_geo_feats=gf,
+                                                       npc_col_feats=cf, dynamic_r_query=rq())
+                d2, u2, c2, v2 = rend.render_batch_ray_modular(npc, dec, rd, ro, DEV, stage, gt_depth=gt,
+                                                               npc_geo_feats=gf, npc_col_feats=cf,
+                                                               dynamic_r_query=rq())
+            assert torch.equal(v1, v2)
+            for a, b in ((d1, d2), (u1, u2), (c1, c2)):
+                assert parity.rel(a, b) <= 1e-5
+            none = ~(gt > 0)
+            radius = cl[level]["radius"].to(DEV).reshape(-1)[none] if dynamic else None
+            z0, not_near = npc.sample_near_pcl(ro[none], rd[none], rend.near_end, rend._far_end(gt), 5, radius, level)
+            idx = torch.nonzero(none).squeeze(1)
+            assert not bool(v1[idx[not_near]].any())                              # not near the cloud: never valid
+            near_valid = v1[idx[~not_near]]
+            if not dynamic:
+                assert torch.equal(not_near.cpu(), g["stages"][stage]["invalid"])
+                assert torch.equal(z0.cpu(), g["stages"][stage]["z"])
+            if bool(near_valid.any()):
+                dd = d1[idx[~not_near]][near_valid]
+                zz = z0[~not_near][near_valid]
+                assert bool((dd > 0).all())                                       # depth kept (Renderer.py:250)
+                assert bool((dd <= zz[:, -1] + 1e-4).all())                       # sum of w*z with sum(w) <= 1
+    finally:
+        npc.radius_query = keep
