@@ -36,6 +36,7 @@ N_FINE = 1_000_000
 N_MID = 250_000
 N_BATCHES = 8            # distinct ray batches cycled through
 STAGE = "color_fine"
+FUSED_LOSS = os.environ.get("HPS_BENCH_FUSED_LOSS", "1") != "0"   # renderer.render_batch_ray_loss vs render + mapper_loss
 EXTENT = 10.0            # cloud spread (in image-plane widths): ~2,700 pts/m^2, ScanNet-like
 CPU_SAMPLE_RAYS = 2500
 
@@ -292,12 +293,18 @@ def run_ours(args, rank, world, local_rank):
         for t in grad_targets:
             t.grad = None
         rq = {"fine": static["radius"], "mid": static["radius_mid"]}
-        depth, unc, color, valid = renderer.render_batch_ray(
-            npc, dec, static["rays_d"], static["rays_o"], dev, STAGE, gt_depth=static["gt_depth"],
-            npc_geo_feats=gf, npc_col_feats=cf, is_tracker=False, cloud_pos=pos, dynamic_r_query=rq, exposure_feat=None,
-            prepared=prepared)
-        affine = dec.color_decoder_fine.mlp_exposure(exposure_feat)
-        loss = hps.mapper_loss(depth, color, valid, static["gt_depth"], static["gt_color"], STAGE, 0.1, affine)
+        if FUSED_LOSS:      # render + loss as one autograd node (compositing and loss in one kernel)
+            loss = renderer.render_batch_ray_loss(
+                npc, dec, static["rays_d"], static["rays_o"], dev, STAGE, static["gt_depth"], static["gt_color"], 0.1,
+                npc_geo_feats=gf, npc_col_feats=cf, cloud_pos=pos, dynamic_r_query=rq, exposure_feat=exposure_feat,
+                prepared=prepared)[0]
+        else:               # the reference's seams: render_batch_ray, then the loss (HPS_BENCH_FUSED_LOSS=0)
+            depth, unc, color, valid = renderer.render_batch_ray(
+                npc, dec, static["rays_d"], static["rays_o"], dev, STAGE, gt_depth=static["gt_depth"],
+                npc_geo_feats=gf, npc_col_feats=cf, is_tracker=False, cloud_pos=pos, dynamic_r_query=rq,
+                exposure_feat=None, prepared=prepared)
+            affine = dec.color_decoder_fine.mlp_exposure(exposure_feat)
+            loss = hps.mapper_loss(depth, color, valid, static["gt_depth"], static["gt_color"], STAGE, 0.1, affine)
         loss.backward()
         return loss
 
@@ -453,7 +460,9 @@ def run_ours(args, rank, world, local_rank):
     line = {"metric": "mapping rays/sec (fwd+bwd)", "value": RAYS * world * args.steps / (dev_ms * 1e-3), "unit": "rays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(world), issue=mode, n_live_rows=int(live_idx.numel())), "clocks": clocks,
+            "config": dict(workload_config(world), issue=mode, n_live_rows=int(live_idx.numel()),
+                           api="renderer.render_batch_ray_loss + backward" if FUSED_LOSS else
+                           "renderer.render_batch_ray + mapper_loss + backward"), "clocks": clocks,
             "e2e": {"value": RAYS * world * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "roofline": roof["roofline"], "kernels_ms_per_step": roof["per_kernel"]}

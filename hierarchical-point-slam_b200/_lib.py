@@ -41,15 +41,17 @@ SIGNATURES = {
     "hps_mlp_bwd": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "hps_composite_fwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp,
                                  _vp]),
-    "hps_composite_bwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _i32, _vp,
+    "hps_composite_bwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp,
                                  _i32, _vp, _vp, _vp]),
+    "hps_composite_mapper_loss": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _f32]
+                                  + [_vp] * 9),
     "hps_camera_from_tensor": (_i32, [_vp, _vp, _vp]),
     "hps_camera_from_tensor_bwd": (_i32, [_vp, _vp, _vp, _vp]),
     "hps_rays_from_uv": (_i32, [_vp, _vp, _vp, _i32, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
     "hps_rays_from_uv_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _vp, _vp]),
     "hps_adam_rows": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp]),
     "hps_exposure_fwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp]),
-    "hps_exposure_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "hps_exposure_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hps_sample_rays": (_i32, [_vp, _vp, _vp, _vp, ctypes.c_double, _vp, _i64, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _vp,
                                _vp]),
     "hps_sample_rays_bwd": (_i32, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),

@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(256)
 composite_bwd_kernel(const float* __restrict__ rgb, int rgb_stride, const float* __restrict__ occ,
                      int occ_stride, const uint8_t* __restrict__ point_mask, const float* __restrict__ z,
                      int64_t R, int S, float coef, const float* __restrict__ g_depth,
-                     const float* __restrict__ g_color, float* __restrict__ d_rgb, int d_rgb_stride,
+                     const float* __restrict__ g_color, const float* __restrict__ gscale,
+                     float* __restrict__ d_rgb, int d_rgb_stride,
                      float* __restrict__ d_occ, int d_occ_stride, unsigned* __restrict__ amax_rgb,
                      unsigned* __restrict__ amax_occ) {
     constexpr int RPW = 32 / G;
@@ -137,12 +138,13 @@ composite_bwd_kernel(const float* __restrict__ rgb, int rgb_stride, const float*
     float wsum, depth, cr, cg, cb, var;
     composite_core<G>(rgb, rgb_stride, occ, occ_stride, point_mask, z, ray, S, s, active, coef, lane_base, me,
                       wsum, depth, cr, cg, cb, var);
-    const float gd = g_depth != nullptr ? __ldg(g_depth + ray) : 0.f;
+    const float gs = gscale != nullptr ? __ldg(gscale) : 1.0f;      // upstream gradient of a scalar loss
+    const float gd = g_depth != nullptr ? __ldg(g_depth + ray) * gs : 0.f;
     float gr = 0.f, gg = 0.f, gb = 0.f;
     if (g_color != nullptr) {
-        gr = __ldg(g_color + ray * 3 + 0);
-        gg = __ldg(g_color + ray * 3 + 1);
-        gb = __ldg(g_color + ray * 3 + 2);
+        gr = __ldg(g_color + ray * 3 + 0) * gs;
+        gg = __ldg(g_color + ray * 3 + 1) * gs;
+        gb = __ldg(g_color + ray * 3 + 2) * gs;
     }
     const float gw = active ? (gd * (me.z - depth) + gr * (me.r - cr) + gg * (me.g - cg) + gb * (me.b - cb)) / wsum
                             : 0.f;
@@ -183,7 +185,134 @@ composite_bwd_kernel(const float* __restrict__ rgb, int rgb_stride, const float*
     }
 }
 
+// Compositing forward fused with the mapper loss (reference src/Mapper.py:791-856): the ray's lane 0 holds depth and
+// colour right after the sums, so the masked L1 depth term, the sigmoid(colour x affine) L1 colour term and their
+// gradients wrt depth / colour / the exposure affine are evaluated in place; one block reduction and 13 atomics
+// per block replace the separate loss kernel (same expressions as mapper_loss_kernel in loss.cu).
+template <int G>
+__global__ void __launch_bounds__(256)
+composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, const float* __restrict__ occ,
+                             int occ_stride, const uint8_t* __restrict__ point_mask, const float* __restrict__ z,
+                             int64_t R, int S, float coef, int min_valid, const float* __restrict__ gt_depth,
+                             const float* __restrict__ gt_color, const float* __restrict__ affine, float w_color,
+                             float* __restrict__ depth_out, float* __restrict__ var_out,
+                             float* __restrict__ color_out, uint8_t* __restrict__ valid_ray,
+                             float* __restrict__ loss, float* __restrict__ g_depth, float* __restrict__ g_color,
+                             float* __restrict__ d_affine) {
+    constexpr int RPW = 32 / G, NACC = 13;
+    __shared__ float red[NACC][8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int sub = lane / G, s = lane % G;
+    const int64_t ray_raw = warp * RPW + sub;
+    float acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+    if (warp * RPW < R) {                                  // warp-uniform: the shuffles below stay converged
+        const int64_t ray = ray_raw < R ? ray_raw : R - 1;
+        const bool live = ray_raw < R;
+        const bool active = s < S;
+        RaySample me;
+        float wsum, depth, cr, cg, cb, var;
+        composite_core<G>(rgb, rgb_stride, occ, occ_stride, point_mask, z, ray, S, s, active, coef, sub * G, me,
+                          wsum, depth, cr, cg, cb, var);
+        const bool pm = active && (point_mask == nullptr || point_mask[ray * S + s] != 0);
+        const unsigned grp = (G == 32) ? kFull : (((1u << G) - 1u) << (sub * G));
+        const int n_has = __popc(__ballot_sync(kFull, pm) & grp);
+        if (live && s == 0) {
+            const bool ok = n_has >= min_valid;            // decoder.py:310-311
+            valid_ray[ray] = ok ? 1 : 0;
+            depth_out[ray] = depth;
+            var_out[ray] = var;
+            color_out[ray * 3 + 0] = cr;
+            color_out[ray * 3 + 1] = cg;
+            color_out[ray * 3 + 2] = cb;
+            const float gd = __ldg(gt_depth + ray);
+            const bool m = (gd > 0.f) && ok && !isnan(depth);
+            float gdep = 0.f;
+            if (m) {
+                acc[0] = fabsf(gd - depth);
+                gdep = depth > gd ? 1.f : (depth < gd ? -1.f : 0.f);
+            }
+            g_depth[ray] = gdep;
+            if (gt_color != nullptr) {
+                float gc[3] = {0.f, 0.f, 0.f};
+                if (m) {
+                    const float c[3] = {cr, cg, cb};
+                    float dl[3];
+#pragma unroll
+                    for (int cc = 0; cc < 3; ++cc) {
+                        float lin = c[cc];
+                        if (affine != nullptr)
+                            lin = c[0] * __ldg(affine + cc) + c[1] * __ldg(affine + 3 + cc) + c[2] * __ldg(affine + 6 + cc) +
+                                  __ldg(affine + 9 + cc);
+                        const float sg = 1.0f / (1.0f + expf(-lin));
+                        const float g = __ldg(gt_color + ray * 3 + cc);
+                        acc[0] += w_color * fabsf(g - sg);
+                        dl[cc] = w_color * (sg > g ? 1.f : (sg < g ? -1.f : 0.f)) * sg * (1.0f - sg);
+                    }
+                    if (affine != nullptr) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            gc[k] = dl[0] * __ldg(affine + 3 * k) + dl[1] * __ldg(affine + 3 * k + 1) +
+                                    dl[2] * __ldg(affine + 3 * k + 2);
+#pragma unroll
+                            for (int cc = 0; cc < 3; ++cc) acc[1 + k * 3 + cc] = c[k] * dl[cc];
+                        }
+#pragma unroll
+                        for (int cc = 0; cc < 3; ++cc) acc[10 + cc] = dl[cc];
+                    } else {
+                        gc[0] = dl[0]; gc[1] = dl[1]; gc[2] = dl[2];
+                    }
+                }
+                g_color[ray * 3 + 0] = gc[0];
+                g_color[ray * 3 + 1] = gc[1];
+                g_color[ray * 3 + 2] = gc[2];
+            }
+        }
+    }
+    const int n_acc = (gt_color != nullptr && affine != nullptr && d_affine != nullptr) ? NACC : 1;
+    for (int k = 0; k < n_acc; ++k) {
+        float v = acc[k];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+        if (lane == 0) red[k][wib] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < n_acc) {
+        float t = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
+        red_add(threadIdx.x == 0 ? loss : d_affine + (threadIdx.x - 1), t);
+    }
+}
+
 }  // namespace hps
+
+extern "C" int hps_composite_mapper_loss(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
+                                         const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
+                                         int min_valid, const float* gt_depth, const float* gt_color,
+                                         const float* affine, float w_color, float* depth, float* var, float* color,
+                                         uint8_t* valid_ray, float* loss, float* g_depth, float* g_color,
+                                         float* d_affine, void* stream) {
+    using namespace hps;
+    HPS_REQUIRE(R >= 0 && S >= 1 && S <= 32, "need 1 <= S <= 32");
+    if (R == 0) return 0;
+    HPS_REQUIRE(occ && z && depth && var && color && valid_ray && gt_depth && loss && g_depth, "null buffer");
+    HPS_REQUIRE(gt_color == nullptr || (rgb != nullptr && g_color != nullptr), "colour term needs rgb and g_color");
+    HPS_REQUIRE(affine == nullptr || d_affine != nullptr, "affine needs d_affine");
+    const int tb = 256;
+    if (S <= 8) {
+        const int64_t warps = ceil_div(R, 4);
+        composite_mapper_loss_kernel<8><<<(unsigned)ceil_div(warps * 32, tb), tb, 0, (cudaStream_t)stream>>>(
+            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, min_valid, gt_depth, gt_color, affine, w_color,
+            depth, var, color, valid_ray, loss, g_depth, g_color, d_affine);
+    } else {
+        composite_mapper_loss_kernel<32><<<(unsigned)ceil_div(R * 32, tb), tb, 0, (cudaStream_t)stream>>>(
+            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, min_valid, gt_depth, gt_color, affine, w_color,
+            depth, var, color, valid_ray, loss, g_depth, g_color, d_affine);
+    }
+    HPS_LAUNCH_OK();
+    return 0;
+}
 
 extern "C" int hps_composite_fwd(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
                                  const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
@@ -210,9 +339,9 @@ extern "C" int hps_composite_fwd(const float* rgb, int rgb_stride, const float* 
 
 extern "C" int hps_composite_bwd(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
                                  const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
-                                 const float* g_depth, const float* g_color, float* d_rgb, int d_rgb_stride,
-                                 float* d_occ, int d_occ_stride, uint32_t* absmax_rgb, uint32_t* absmax_occ,
-                                 void* stream) {
+                                 const float* g_depth, const float* g_color, const float* gscale, float* d_rgb,
+                                 int d_rgb_stride, float* d_occ, int d_occ_stride, uint32_t* absmax_rgb,
+                                 uint32_t* absmax_occ, void* stream) {
     using namespace hps;
     HPS_REQUIRE(R >= 0 && S >= 1 && S <= 32, "need 1 <= S <= 32");
     if (R == 0) return 0;
@@ -222,12 +351,12 @@ extern "C" int hps_composite_bwd(const float* rgb, int rgb_stride, const float* 
     if (S <= 8) {
         const int64_t warps = ceil_div(R, 4);
         composite_bwd_kernel<8><<<(unsigned)ceil_div(warps * 32, tb), tb, 0, (cudaStream_t)stream>>>(
-            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, g_depth, g_color, d_rgb, d_rgb_stride,
-            d_occ, d_occ_stride, absmax_rgb, absmax_occ);
+            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, g_depth, g_color, gscale, d_rgb,
+            d_rgb_stride, d_occ, d_occ_stride, absmax_rgb, absmax_occ);
     } else {
         composite_bwd_kernel<32><<<(unsigned)ceil_div(R * 32, tb), tb, 0, (cudaStream_t)stream>>>(
-            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, g_depth, g_color, d_rgb, d_rgb_stride,
-            d_occ, d_occ_stride, absmax_rgb, absmax_occ);
+            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, g_depth, g_color, gscale, d_rgb,
+            d_rgb_stride, d_occ, d_occ_stride, absmax_rgb, absmax_occ);
     }
     HPS_LAUNCH_OK();
     return 0;

@@ -212,18 +212,19 @@ __global__ void exposure_fwd_kernel(const float* __restrict__ x, const float* __
 
 __global__ void exposure_bwd_kernel(const float* __restrict__ x, const float* __restrict__ W1,
                                     const float* __restrict__ W2, const float* __restrict__ a1,
-                                    const float* __restrict__ dout, int n_in, int hidden, int n_out,
-                                    float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
+                                    const float* __restrict__ dout, const float* __restrict__ gscale, int n_in,
+                                    int hidden, int n_out, float* __restrict__ dW1, float* __restrict__ db1, float* __restrict__ dW2,
                                     float* __restrict__ db2, float* __restrict__ dx) {
     extern __shared__ float sh[];       // da[hidden]
     const int j = threadIdx.x;
+    const float gs = gscale != nullptr ? __ldg(gscale) : 1.0f;      // upstream gradient of a scalar loss
     if (j < hidden) {
         const float a = a1[j];
         const float t = a * 100.0f;
         const float h = t > 20.0f ? a : log1pf(expf(t)) / 100.0f;
         float dh = 0.f;
         for (int o = 0; o < n_out; ++o) {
-            const float g = dout[o];
+            const float g = dout[o] * gs;
             dW2[o * hidden + j] = g * h;
             dh = fmaf(W2[o * hidden + j], g, dh);
         }
@@ -237,7 +238,7 @@ __global__ void exposure_bwd_kernel(const float* __restrict__ x, const float* __
         sh[j] = da;
         for (int k = 0; k < n_in; ++k) dW1[j * n_in + k] = da * x[k];
     }
-    if (j < n_out) db2[j] = dout[j];
+    if (j < n_out) db2[j] = dout[j] * gs;
     __syncthreads();
     if (dx != nullptr) {
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
@@ -265,14 +266,14 @@ extern "C" int hps_exposure_fwd(const float* x, const float* W1, const float* b1
 }
 
 extern "C" int hps_exposure_bwd(const float* x, const float* W1, const float* W2, const float* a1, const float* dout,
-                                int n_in, int hidden, int n_out, float* dW1, float* db1, float* dW2, float* db2,
+                                const float* gscale, int n_in, int hidden, int n_out, float* dW1, float* db1, float* dW2, float* db2,
                                 float* dx, void* stream) {
     using namespace hps;
     HPS_REQUIRE(n_in >= 1 && n_in <= 64 && hidden >= 1 && hidden <= 1024 && n_out >= 1 && n_out <= 32, "exposure MLP size");
     HPS_REQUIRE(x && W1 && W2 && a1 && dout && dW1 && db1 && dW2 && db2, "null buffer");
     const int tb = (max(hidden, 32) + 31) / 32 * 32;
-    exposure_bwd_kernel<<<1, tb, hidden * sizeof(float), (cudaStream_t)stream>>>(x, W1, W2, a1, dout, n_in, hidden, n_out,
-                                                                              dW1, db1, dW2, db2, dx);
+    exposure_bwd_kernel<<<1, tb, hidden * sizeof(float), (cudaStream_t)stream>>>(x, W1, W2, a1, dout, gscale, n_in, hidden,
+                                                                              n_out, dW1, db1, dW2, db2, dx);
     HPS_LAUNCH_OK();
     return 0;
 }

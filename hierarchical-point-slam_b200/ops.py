@@ -43,7 +43,7 @@ LAUNCHES = {"n": 0}
 _KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_interp_fwd": 1, "hps_interp_bwd": 1,
                      "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_mlp_tc_pack": 1, "hps_mlp_tc_fwd": 1,
                      "hps_mlp_tc_bwd_pack": 2, "hps_mlp_tc_bwd": 3, "hps_tc_selftest": 1, "hps_composite_fwd": 1,
-                     "hps_composite_bwd": 1, "hps_sample_rays": 1, "hps_sample_rays_bwd": 1, "hps_mapper_loss": 1,
+                     "hps_composite_bwd": 1, "hps_composite_mapper_loss": 1, "hps_sample_rays": 1, "hps_sample_rays_bwd": 1, "hps_mapper_loss": 1,
                      "hps_tracker_loss_stats": 1, "hps_tracker_loss": 1, "hps_exposure_fwd": 1, "hps_exposure_bwd": 1, "hps_camera_from_tensor": 1, "hps_adam_rows": 1,
                      "hps_camera_from_tensor_bwd": 1, "hps_rays_from_uv": 1, "hps_rays_from_uv_bwd": 1}
 TIMERS = None   # set to {} to record (start, end) CUDA events per call name on the current stream
@@ -499,7 +499,7 @@ class _CompositeRaw(torch.autograd.Function):
         with torch.cuda.device(raw_c.device):
             _call("hps_composite_bwd", 
                 ctypes.c_void_p(base), 4, ctypes.c_void_p(base + 12), 4, _lib.ptr(pm), _lib.ptr(z_c), R, S, ctx.coef,
-                _lib.ptr(gd), _lib.ptr(gc), ctypes.c_void_p(dbase), 4, ctypes.c_void_p(dbase + 12), 4, None, None,
+                _lib.ptr(gd), _lib.ptr(gc), None, ctypes.c_void_p(dbase), 4, ctypes.c_void_p(dbase + 12), 4, None, None,
                 _stream())
         return d_raw, None, None, None, None
 
@@ -607,11 +607,21 @@ def prepare_rays(grid, rays_o, rays_d, gt_depth, radius, S, near, far, z_zero=No
 class RenderSpec:
     """Non-tensor arguments of render_rays (one per call)."""
     __slots__ = ("grid", "radius", "z_zero", "S", "near", "far", "coef", "min_nn", "min_valid", "color_stage",
-                 "tracker", "cloud_pos", "fill_geo", "fill_col", "live_geo", "live_col", "prep")
+                 "tracker", "cloud_pos", "fill_geo", "fill_col", "live_geo", "live_col", "prep", "loss")
 
     def __init__(self, **kw):
         for k in self.__slots__:
             setattr(self, k, kw.get(k))
+
+
+class MapperLossSpec:
+    """Fuses the mapper's loss (Mapper.py:791-856) into render_rays: `gt_color` (R,3) or None (geometry stages),
+    `w_color`, and `exposure` = True when the five tensors of the exposure MLP (latent, W1, b1, W2, b2) follow the
+    decoder parameters - the colour term then is |gt - sigmoid(colour x affine)| with affine = MLP(latent)."""
+    __slots__ = ("gt_color", "w_color", "exposure")
+
+    def __init__(self, gt_color, w_color, exposure):
+        self.gt_color, self.w_color, self.exposure = gt_color, float(w_color), bool(exposure)
 
 
 class _RenderRays(torch.autograd.Function):
@@ -650,7 +660,34 @@ class _RenderRays(torch.autograd.Function):
             raise _lib.HpsError("pass LiveRows for both feature tables of a level or for neither")
         aff = _f32c(affine) if (affine is not None and spec.color_stage) else None
         gprm = [_f32c(t) for t in params[:N_PARAM]]
-        cprm = [_f32c(t) for t in params[N_PARAM:]] if spec.color_stage else []
+        cprm = [_f32c(t) for t in params[N_PARAM:2 * N_PARAM]] if spec.color_stage else []
+        # loss mode: [loss, pad x3 | d_affine (12) | g_depth (R) | g_color (3R)] in one buffer, head zeroed (accumulators)
+        lm = spec.loss
+        eprm, flat, a1_l, aff_l = [], None, None, None
+        if lm is not None:
+            if spec.tracker:
+                raise _lib.HpsError("the fused loss is the mapper's; the tracker's needs a batch statistic (tracker_loss)")
+            color_loss = spec.color_stage and lm.gt_color is not None
+            gtc = _f32c(lm.gt_color).reshape(-1, 3) if color_loss else None
+            flat = torch.empty(16 + R * (4 if color_loss else 1), **f32)
+            if lm.exposure and color_loss:
+                eprm = [_f32c(t) for t in params[len(gprm) + len(cprm):]]
+                if len(eprm) != 5:
+                    raise _lib.HpsError("exposure MLP: expected latent, W1, b1, W2, b2")
+                ctx.exp_x_shape = params[len(gprm) + len(cprm)].shape
+                eprm[0] = eprm[0].reshape(-1)
+                e_hidden, e_in = eprm[1].shape
+                if eprm[0].numel() != e_in or eprm[3].shape[0] != 12:
+                    raise _lib.HpsError("exposure MLP: latent / output size mismatch")
+                a1_l, aff_l = torch.empty(e_hidden, **f32), torch.empty(12, **f32)
+
+        def loss_head(s):
+            """zero the accumulators and evaluate the exposure MLP (independent of the rays): off the critical path"""
+            with torch.cuda.stream(s):
+                flat[:16].zero_()
+            if eprm:
+                _call("hps_exposure_fwd", _lib.ptr(eprm[0]), _lib.ptr(eprm[1]), _lib.ptr(eprm[2]), _lib.ptr(eprm[3]),
+                      _lib.ptr(eprm[4]), e_in, e_hidden, 12, _lib.ptr(a1_l), _lib.ptr(aff_l), _stream(s))
         rad = spec.radius
         rad_t = rad.detach().to(device=dev, dtype=torch.float64).reshape(-1).contiguous() if torch.is_tensor(rad) else None
         if rad_t is not None and rad_t.numel() != R:
@@ -704,12 +741,16 @@ class _RenderRays(torch.autograd.Function):
                 _mlp_pack(MLP_COL, carr, dev, side)
                 packed_col = side.record_event()
                 _mlp_pack(MLP_GEO, garr, dev, side)
+                if lm is not None:
+                    loss_head(side)
                 aux = None
                 if bpk_c is not None:      # backward images on a third stream: nothing in the forward waits for them
                     aux = _side_stream(dev, 1)
                     aux.wait_stream(main)
                     _call("hps_mlp_tc_bwd_pack", MLP_COL, carr, _lib.ptr(bpk_c), _stream(aux))
                     _call("hps_mlp_tc_bwd_pack", MLP_GEO, garr, _lib.ptr(bpk_g), _stream(aux))
+            if lm is not None and not fork:
+                loss_head(main)
             if prep is None:
                 _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t),
                       0.0 if rad_t is not None else float(rad), _lib.ptr(zz), _z_zero_stride(zz, R, S), R, S,
@@ -739,20 +780,40 @@ class _RenderRays(torch.autograd.Function):
             ctx.bwd_packed = (bpk_g, bpk_c)
             act_g, act_c = (sv_g[1] if sv_g else None), (sv_c[1] if sv_c else None)
             ctx.saved_kinds = (sv_g[0] if sv_g else None, sv_c[0] if sv_c else None)
-            _call("hps_composite_fwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
-                  float(spec.coef), _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), None, int(spec.min_valid),
-                  _lib.ptr(valid), st())
+            if lm is None:
+                _call("hps_composite_fwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
+                      float(spec.coef), _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), None, int(spec.min_valid),
+                      _lib.ptr(valid), st())
+            else:
+                _call("hps_composite_mapper_loss", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
+                      float(spec.coef), int(spec.min_valid), _lib.ptr(gd), _lib.ptr(gtc), _lib.ptr(aff_l), lm.w_color,
+                      _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), _lib.ptr(valid), _lib.ptr(flat),
+                      _lib.ptr(flat[16:]), _lib.ptr(flat[16 + R:]) if color_loss else None,
+                      _lib.ptr(flat[4:]) if aff_l is not None else None, st())
+        ctx.loss_state = None if lm is None else (flat, a1_l, eprm, color_loss)
         ctx.spec = spec
         ctx.n_g = len(gprm)
         ctx.row_map = row_map
         ctx.n_live = feats_geo.shape[0] if row_map is not None else None
         ctx.save_for_backward(z, pts, I, w, has, c_geo, c_col, occ, rgb, act_g, act_c, fg, fc, aff, pos, *gprm, *cprm)
+        if lm is not None:
+            ctx.mark_non_differentiable(depth, var, color, valid)
+            return flat[0], depth, var, color, valid
         ctx.mark_non_differentiable(var, valid)
         return depth, var, color, valid
 
     @staticmethod
-    def backward(ctx, g_depth, _g_var, g_color, _g_valid):
+    def backward(ctx, *gouts):
         spec = ctx.spec
+        gscale = None
+        if ctx.loss_state is not None:          # gradients of the fused loss, scaled by the upstream gradient in-kernel
+            l_flat, l_a1, l_eprm, l_color = ctx.loss_state
+            l_R = ctx.saved_tensors[0].shape[0]
+            gscale = _f32c(gouts[0]).reshape(1)
+            g_depth = l_flat[16:16 + l_R]
+            g_color = l_flat[16 + l_R:].view(l_R, 3) if l_color else None
+        else:
+            g_depth, _g_var, g_color, _g_valid = gouts
         (z, pts, I, w, has, c_geo, c_col, occ, rgb, act_g, act_c, fg, fc, aff, pos) = ctx.saved_tensors[:15]
         gprm = list(ctx.saved_tensors[15:15 + N_PARAM])
         cprm = list(ctx.saved_tensors[15 + N_PARAM:])
@@ -792,7 +853,7 @@ class _RenderRays(torch.autograd.Function):
             bpk_g, bpk_c = ctx.bwd_packed
             folded = fork and bpk_g is not None and bpk_c is not None
             _call("hps_composite_bwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
-                  float(spec.coef), _lib.ptr(gd), _lib.ptr(gc), _lib.ptr(d_rgb), 3, _lib.ptr(d_occ), 1,
+                  float(spec.coef), _lib.ptr(gd), _lib.ptr(gc), _lib.ptr(gscale), _lib.ptr(d_rgb), 3, _lib.ptr(d_occ), 1,
                   _absmax_word(MLP_COL, bpk_c) if folded else None, _absmax_word(MLP_GEO, bpk_g) if folded else None,
                   st())
             dp_c = None
@@ -829,6 +890,27 @@ class _RenderRays(torch.autograd.Function):
                     dp += dp_c
                 g_ro, g_rd = torch.empty(R, 3, **f32), torch.empty(R, 3, **f32)
                 _call("hps_sample_rays_bwd", _lib.ptr(dp), _lib.ptr(z), R, S, _lib.ptr(g_ro), _lib.ptr(g_rd), st())
+            g_exp = ()
+            if ctx.loss_state is not None and l_eprm:
+                # exposure MLP backward from d loss / d affine (accumulated by the fused loss kernel); the main stream
+                # has slack here - the weight-gradient kernels on their own streams finish later
+                e_need = need[7 + len(gprm) + len(cprm):]
+                g_exp = (None,) * 5
+                if any(e_need):
+                    e_hidden, e_in = l_eprm[1].shape
+                    sizes = [e_hidden * e_in, e_hidden, 12 * e_hidden, 12, e_in]
+                    ebuf = torch.empty(sum((n + 3) // 4 * 4 for n in sizes), **f32)
+                    parts, off = [], 0
+                    for n in sizes:
+                        parts.append(ebuf[off:off + n])
+                        off += (n + 3) // 4 * 4
+                    _call("hps_exposure_bwd", _lib.ptr(l_eprm[0]), _lib.ptr(l_eprm[1]), _lib.ptr(l_eprm[3]), _lib.ptr(l_a1),
+                          _lib.ptr(l_flat[4:]), _lib.ptr(gscale), e_in, e_hidden, 12, _lib.ptr(parts[0]),
+                          _lib.ptr(parts[1]), _lib.ptr(parts[2]), _lib.ptr(parts[3]),
+                          _lib.ptr(parts[4]) if e_need[0] else None, st())
+                    shaped = (parts[4].view(ctx.exp_x_shape), parts[0].view(e_hidden, e_in), parts[1],
+                              parts[2].view(12, e_hidden), parts[3])
+                    g_exp = tuple(g if e_need[i] else None for i, g in enumerate(shaped))
             for w_s in wgrad_streams:
                 main.wait_stream(w_s)
         gg = [(g if (g is not None and need[7 + i]) else None) for i, g in enumerate(dg)] if dg else [None] * N_PARAM
@@ -837,10 +919,13 @@ class _RenderRays(torch.autograd.Function):
                 if dcw else [None] * N_PARAM
         else:
             gcw = []
-        return (None, g_ro if need[1] else None, g_rd if need[2] else None, None, dfg, dfc, daff, *gg, *gcw)
+        return (None, g_ro if need[1] else None, g_rd if need[2] else None, None, dfg, dfc, daff, *gg, *gcw, *g_exp)
 
 
-def render_rays(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, geo_params, col_params):
+def render_rays(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, geo_params, col_params,
+                exposure_params=None):
+    """exposure_params (with spec.loss.exposure): (latent, W1, b1, W2, b2) of the exposure MLP; the call then returns
+    (loss, depth, var, color, valid) with only the loss differentiable."""
     spec.live_geo = feats_geo if isinstance(feats_geo, LiveRows) else None
     spec.live_col = feats_col if (isinstance(feats_col, LiveRows) and spec.color_stage) else None
     if spec.live_geo is not None:
@@ -848,6 +933,8 @@ def render_rays(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, ge
     if isinstance(feats_col, LiveRows):
         feats_col = feats_col.param
     params = list(geo_params) + (list(col_params) if spec.color_stage else [])
+    if spec.loss is not None and spec.loss.exposure and spec.color_stage and spec.loss.gt_color is not None:
+        params += list(exposure_params)
     return _RenderRays.apply(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col if spec.color_stage else None,
                              affine if spec.color_stage else None, *params)
 
@@ -992,8 +1079,8 @@ class _ExposureMlp(torch.autograd.Function):
         dW1, db1, dW2, db2, dx = parts
         want_x = ctx.needs_input_grad[0]
         with torch.cuda.device(dev):
-            _call("hps_exposure_bwd", _lib.ptr(xs), _lib.ptr(w1), _lib.ptr(w2), _lib.ptr(a1), _lib.ptr(_f32c(dout)), n_in,
-                  hidden, n_out, _lib.ptr(dW1), _lib.ptr(db1), _lib.ptr(dW2), _lib.ptr(db2),
+            _call("hps_exposure_bwd", _lib.ptr(xs), _lib.ptr(w1), _lib.ptr(w2), _lib.ptr(a1), _lib.ptr(_f32c(dout)), None,
+                  n_in, hidden, n_out, _lib.ptr(dW1), _lib.ptr(db1), _lib.ptr(dW2), _lib.ptr(db2),
                   _lib.ptr(dx) if want_x else None, _stream())
         return (dx.view(ctx.x_shape) if want_x else None, dW1.view(hidden, n_in), db1, dW2.view(n_out, hidden), db2)
 

@@ -125,7 +125,7 @@ class Renderer(object):
 
     def render_batch_ray(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None,
                          npc_geo_feats=None, npc_col_feats=None, is_tracker=False, cloud_pos=None,
-                         normals=None, dynamic_r_query=None, exposure_feat=None, prepared=None):
+                         normals=None, dynamic_r_query=None, exposure_feat=None, prepared=None, _loss=None):
         """One fused kernel sequence (ops.render_rays): sampling, exact neighbour search, interpolation of both
         feature tables from one neighbour list, both decoders, compositing with the -100 overwrite.
         `prepared` (not in the reference): the ops.RayPrep of prepare_batch() for these very rays."""
@@ -168,9 +168,22 @@ class Renderer(object):
             min_nn=geo.min_nn_num, min_valid=int(S / 2 + 1), color_stage=color_stage, tracker=bool(is_tracker),
             cloud_pos=cloud_pos[level] if is_tracker else None, fill_geo=decoders._fill("geo", rays_o.device),
             fill_col=decoders._fill("col", rays_o.device) if color_stage else None, prep=prepared)
-        depth, uncertainty, color, valid = ops.render_rays(
-            spec, rays_o, rays_d, gt_depth, npc_geo_feats[level], npc_col_feats[level] if color_stage else None, affine,
-            geo.kernel_params(rays_o.device), col.kernel_params(rays_o.device) if color_stage else None)
+        loss = None
+        if _loss is not None:
+            gt_color, w_color, loss_exposure_feat = _loss
+            mlp = col.mlp_exposure if (color_stage and loss_exposure_feat is not None) else None
+            spec.loss = ops.MapperLossSpec(gt_color if color_stage else None, w_color, mlp is not None)
+            eprm = None
+            if mlp is not None:
+                eprm = (loss_exposure_feat, mlp.linear1.weight, mlp.linear1.bias, mlp.linear2.weight, mlp.linear2.bias)
+            loss, depth, uncertainty, color, valid = ops.render_rays(
+                spec, rays_o, rays_d, gt_depth, npc_geo_feats[level], npc_col_feats[level] if color_stage else None,
+                affine, geo.kernel_params(rays_o.device), col.kernel_params(rays_o.device) if color_stage else None,
+                eprm)
+        else:
+            depth, uncertainty, color, valid = ops.render_rays(
+                spec, rays_o, rays_d, gt_depth, npc_geo_feats[level], npc_col_feats[level] if color_stage else None,
+                affine, geo.kernel_params(rays_o.device), col.kernel_params(rays_o.device) if color_stage else None)
         if not self.sample_near_pcl and not self.assume_positive_depth:
             depth = torch.where(gt_depth > 0, depth, torch.zeros_like(depth))     # Renderer.py:250-251
         if self.skip_zero_depth_pixel:
@@ -178,7 +191,27 @@ class Renderer(object):
         valid = valid.view(torch.bool)
         if near_mask is not None:
             valid = valid & near_mask                                              # Renderer.py:247-248
+        if _loss is not None:
+            return loss, depth, uncertainty, color, valid
         return depth, uncertainty, color, valid
+
+    def render_batch_ray_loss(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth, gt_color, w_color_loss,
+                              npc_geo_feats=None, npc_col_feats=None, cloud_pos=None, dynamic_r_query=None,
+                              exposure_feat=None, prepared=None):
+        """One mapper iteration's forward as ONE autograd node (not in the reference, which spells it out in
+        Mapper.py:783-856): render_batch_ray(..., exposure_feat=None) followed by
+            mask = (gt_depth > 0) & valid & ~isnan(depth)
+            loss = |gt_depth - depth|[mask].sum()
+                   + w_color_loss * |gt_color - sigmoid(color @ A + t)|[mask].sum()        (colour stages)
+        with [A | t] = color_decoder_<level>.mlp_exposure(exposure_feat) (no exposure_feat: the colour as rendered).
+        -> (loss, depth, uncertainty, color, valid_ray_mask); only `loss` carries gradient (to the feature tables, the
+        decoders, the exposure MLP and exposure_feat).  The compositing and loss kernels are one, the exposure MLP
+        runs beside the neighbour search, and loss.backward() feeds the upstream gradient to the kernels as a device
+        scalar - ten launches fewer on the critical path than render_batch_ray + mapper_loss."""
+        return self.render_batch_ray(npc, decoders, rays_d, rays_o, device, stage, gt_depth=gt_depth,
+                                     npc_geo_feats=npc_geo_feats, npc_col_feats=npc_col_feats, is_tracker=False,
+                                     cloud_pos=cloud_pos, dynamic_r_query=dynamic_r_query, exposure_feat=None,
+                                     prepared=prepared, _loss=(gt_color, w_color_loss, exposure_feat))
 
     def render_batch_ray_modular(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None,
                                  npc_geo_feats=None, npc_col_feats=None, is_tracker=False, cloud_pos=None,

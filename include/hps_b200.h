@@ -161,9 +161,22 @@ int hps_composite_fwd(const float* rgb, int rgb_stride, const float* occ, int oc
 int hps_composite_bwd(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
                       const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
                       const float* g_depth, const float* g_color,
+                      const float* gscale /* device scalar multiplied into g_depth / g_color; may be NULL = 1 */,
                       float* d_rgb, int d_rgb_stride, float* d_occ, int d_occ_stride,
                       uint32_t* absmax_rgb, uint32_t* absmax_occ /* may be NULL: atomicMax of |d_rgb| / |d_occ| float bits */,
                       void* stream);
+/* hps_composite_fwd fused with hps_mapper_loss (Mapper.py:791-856): same depth / var / color / valid_ray, plus
+ * loss += sum over rays with gt_depth > 0, valid and a finite depth of |gt_depth - depth|
+ *         (+ w_color * |gt_color - sigmoid(color x affine[0:9] + affine[9:12])| when gt_color is given; affine may
+ *         be NULL = identity without the sigmoid's affine, see hps_mapper_loss),
+ * g_depth (R), g_color (R,3) = d loss / d depth, d color, and d_affine (12) += d loss / d affine.
+ * loss and d_affine are ACCUMULATED: zero them first.                                                            */
+int hps_composite_mapper_loss(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
+                              const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
+                              int min_valid, const float* gt_depth, const float* gt_color /* may be NULL */,
+                              const float* affine /* may be NULL */, float w_color, float* depth, float* var,
+                              float* color, uint8_t* valid_ray, float* loss, float* g_depth, float* g_color,
+                              float* d_affine, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Adam over the live (frustum-selected) rows of a feature table, fused with the write-back into the table
@@ -184,7 +197,8 @@ int hps_adam_rows(float* param, const float* grad, float* exp_avg, float* exp_av
  * ---------------------------------------------------------------------------------------------- */
 int hps_exposure_fwd(const float* x, const float* W1, const float* b1, const float* W2, const float* b2, int n_in,
                      int hidden, int n_out, float* a1, float* out, void* stream);
-int hps_exposure_bwd(const float* x, const float* W1, const float* W2, const float* a1, const float* dout, int n_in,
+int hps_exposure_bwd(const float* x, const float* W1, const float* W2, const float* a1, const float* dout,
+                     const float* gscale /* device scalar multiplied into dout; may be NULL = 1 */, int n_in,
                      int hidden, int n_out, float* dW1, float* db1, float* dW2, float* db2, float* dx, void* stream);
 
 /* ------------------------------------------------------------------------------------------------

@@ -48,7 +48,9 @@ def product(scene, device):
     return hps, npc, dec, renderer
 
 
-def mapper_step(hps, npc, dec, renderer, scene, stage, device, modular=False):
+def mapper_step(hps, npc, dec, renderer, scene, stage, device, modular=False, fused_loss=False, upstream=None):
+    """fused_loss: the iteration through renderer.render_batch_ray_loss (render + loss as one autograd node);
+    upstream: backpropagate upstream * loss instead of loss."""
     cl, rays, cfg = scene["clouds"], scene["rays"], scene["cfg"]
     level = "mid" if stage.endswith("mid") else "fine"
     gf = {l: cl[l]["geo_feats"].to(device).clone().requires_grad_(True) for l in cl}
@@ -57,6 +59,15 @@ def mapper_step(hps, npc, dec, renderer, scene, stage, device, modular=False):
     dec.zero_grad()
     rq = {l: cl[l]["radius"].to(device).clone() for l in cl}
     gt_d, gt_c = rays["gt_depth"].to(device), rays["gt_color"].to(device)
+    ef = scene["exposure_feat"].to(device).clone().requires_grad_(True)
+    if fused_loss:
+        loss, depth, var, color, valid = renderer.render_batch_ray_loss(
+            npc, dec, rays["rays_d"].to(device), rays["rays_o"].to(device), device, stage, gt_d, gt_c,
+            cfg["w_color_mapper"], npc_geo_feats=gf, npc_col_feats=cf, cloud_pos=pos, dynamic_r_query=rq,
+            exposure_feat=ef if stage.startswith("color") else None)
+        (loss if upstream is None else loss * upstream).backward()
+        return dict(depth=depth, var=var, color=color, valid=valid, loss=loss, g_geo=gf[level].grad,
+                    g_col=cf[level].grad, g_ef=ef.grad)
     render = renderer.render_batch_ray_modular if modular else renderer.render_batch_ray
     depth, var, color, valid = render(
         npc, dec, rays["rays_d"].to(device), rays["rays_o"].to(device), device, stage, gt_depth=gt_d,
@@ -64,12 +75,12 @@ def mapper_step(hps, npc, dec, renderer, scene, stage, device, modular=False):
         exposure_feat=None)
     affine = None
     if stage.startswith("color"):
-        affine = getattr(dec, "color_decoder_" + level).mlp_exposure(scene["exposure_feat"].to(device))
+        affine = getattr(dec, "color_decoder_" + level).mlp_exposure(ef)
     loss_fn = hps.mapper_loss_torch if modular else hps.mapper_loss
     loss = loss_fn(depth, color, valid, gt_d, gt_c, stage, cfg["w_color_mapper"], affine)
-    loss.backward()
+    (loss if upstream is None else loss * upstream).backward()
     return dict(depth=depth, var=var, color=color, valid=valid, loss=loss, g_geo=gf[level].grad,
-                g_col=cf[level].grad)
+                g_col=cf[level].grad, g_ef=ef.grad)
 
 
 def check_mapper(stage, out, ref, dec, tol=TOL):

@@ -346,7 +346,7 @@ def test_composite_bwd_reports_gradient_maxima(hps):
     words = torch.zeros(2, dtype=torch.int32, device=DEV)
     lib = _lib.load()
     rc = lib.hps_composite_bwd(_lib.ptr(rgb), 3, _lib.ptr(occ), 1, None, _lib.ptr(z), R, S, 0.1, _lib.ptr(gd), _lib.ptr(gc),
-                               _lib.ptr(d_rgb), 3, _lib.ptr(d_occ), 1, ctypes.c_void_p(words.data_ptr()),
+                               None, _lib.ptr(d_rgb), 3, _lib.ptr(d_occ), 1, ctypes.c_void_p(words.data_ptr()),
                                ctypes.c_void_p(words.data_ptr() + 4), None)
     _lib.check(rc)
     torch.cuda.synchronize()

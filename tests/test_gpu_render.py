@@ -16,14 +16,51 @@ def built(hps):
     return (scene,) + parity.product(scene, DEV)
 
 
-@pytest.mark.parametrize("path", ["fused", "modular"])
+@pytest.mark.parametrize("path", ["fused", "modular", "fused_loss"])
 @pytest.mark.parametrize("stage", ["geometry_mid", "color_mid", "geometry_fine", "color_fine"])
 def test_mapper_iteration_matches_reference(built, stage, path):
     scene, hps, npc, dec, renderer = built
     ref = parity.load("render_mapper_small.pt")[stage]
-    out = parity.mapper_step(hps, npc, dec, renderer, scene, stage, DEV, modular=(path == "modular"))
+    out = parity.mapper_step(hps, npc, dec, renderer, scene, stage, DEV, modular=(path == "modular"),
+                             fused_loss=(path == "fused_loss"))
     errs = parity.check_mapper(stage, out, ref, dec)
     print(stage, errs)
+
+
+@pytest.mark.parametrize("streams", [True, False])
+def test_render_batch_ray_loss_equals_render_plus_loss(built, streams):
+    """renderer.render_batch_ray_loss (compositing + loss in one kernel, exposure MLP beside the search, upstream
+    gradient as a device scalar) against render_batch_ray + mapper_loss: every gradient, including the exposure MLP's
+    and the exposure latent's, with an upstream gradient different from 1."""
+    scene, hps, npc, dec, renderer = built
+    saved = hps.ops.MULTI_STREAM
+    hps.ops.MULTI_STREAM = streams
+    try:
+        for stage in ("color_fine", "color_mid", "geometry_fine"):
+            level = "mid" if stage.endswith("mid") else "fine"
+            mods = [getattr(dec, "color_decoder_" + level), getattr(dec, "geo_decoder_" + level)]
+            grads = []
+            for fused in (False, True):
+                out = parity.mapper_step(hps, npc, dec, renderer, scene, stage, DEV, fused_loss=fused, upstream=-2.5)
+                g = {n + "/" + k: v.grad.clone() for n, m in zip("cg", mods) for k, v in m.named_parameters()
+                     if v.grad is not None}
+                grads.append((out, g))
+            (a, ga), (b, gb) = grads
+            assert torch.equal(a["valid"], b["valid"]) and torch.equal(a["depth"], b["depth"])
+            assert torch.equal(a["color"], b["color"]) and torch.equal(a["var"], b["var"])
+            assert parity.rel(b["loss"], a["loss"]) <= 1e-6
+            assert set(ga) == set(gb), set(ga) ^ set(gb)
+            if stage.startswith("color"):
+                assert any("mlp_exposure" in k for k in gb), "the exposure MLP must receive gradients"
+                assert parity.rel(b["g_ef"], a["g_ef"]) <= 1e-5
+                assert parity.rel(b["g_col"], a["g_col"]) <= 1e-5
+            else:
+                assert b["g_ef"] is None
+            assert parity.rel(b["g_geo"], a["g_geo"]) <= 1e-5
+            worst = max(parity.rel(gb[k], ga[k]) for k in ga)
+            assert worst <= 2e-5, (stage, worst)
+    finally:
+        hps.ops.MULTI_STREAM = saved
 
 
 @pytest.mark.parametrize("switch", ["simt", "simt_bwd", "single_stream"])
