@@ -212,6 +212,24 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
         const int64_t ray = ray_raw < R ? ray_raw : R - 1;
         const bool live = ray_raw < R;
         const bool active = s < S;
+        // the loss operands of the ray's leading lane are requested before the compositing loads, not after the sums
+        const bool lead = live && s == 0;
+        const bool use_aff = gt_color != nullptr && affine != nullptr;
+        float gd = 0.f, gtc[3] = {0.f, 0.f, 0.f}, af[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) af[k] = 0.f;
+        if (lead) {
+            gd = __ldg(gt_depth + ray);
+            if (gt_color != nullptr) {
+                gtc[0] = __ldg(gt_color + ray * 3 + 0);
+                gtc[1] = __ldg(gt_color + ray * 3 + 1);
+                gtc[2] = __ldg(gt_color + ray * 3 + 2);
+            }
+            if (use_aff) {
+#pragma unroll
+                for (int k = 0; k < 12; ++k) af[k] = __ldg(affine + k);
+            }
+        }
         RaySample me;
         float wsum, depth, cr, cg, cb, var;
         composite_core<G>(rgb, rgb_stride, occ, occ_stride, point_mask, z, ray, S, s, active, coef, sub * G, me,
@@ -219,7 +237,7 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
         const bool pm = active && (point_mask == nullptr || point_mask[ray * S + s] != 0);
         const unsigned grp = (G == 32) ? kFull : (((1u << G) - 1u) << (sub * G));
         const int n_has = __popc(__ballot_sync(kFull, pm) & grp);
-        if (live && s == 0) {
+        if (lead) {
             const bool ok = n_has >= min_valid;            // decoder.py:310-311
             valid_ray[ray] = ok ? 1 : 0;
             depth_out[ray] = depth;
@@ -227,7 +245,6 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
             color_out[ray * 3 + 0] = cr;
             color_out[ray * 3 + 1] = cg;
             color_out[ray * 3 + 2] = cb;
-            const float gd = __ldg(gt_depth + ray);
             const bool m = (gd > 0.f) && ok && !isnan(depth);
             float gdep = 0.f;
             if (m) {
@@ -243,19 +260,16 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
 #pragma unroll
                     for (int cc = 0; cc < 3; ++cc) {
                         float lin = c[cc];
-                        if (affine != nullptr)
-                            lin = c[0] * __ldg(affine + cc) + c[1] * __ldg(affine + 3 + cc) + c[2] * __ldg(affine + 6 + cc) +
-                                  __ldg(affine + 9 + cc);
+                        if (use_aff) lin = c[0] * af[cc] + c[1] * af[3 + cc] + c[2] * af[6 + cc] + af[9 + cc];
                         const float sg = 1.0f / (1.0f + expf(-lin));
-                        const float g = __ldg(gt_color + ray * 3 + cc);
+                        const float g = gtc[cc];
                         acc[0] += w_color * fabsf(g - sg);
                         dl[cc] = w_color * (sg > g ? 1.f : (sg < g ? -1.f : 0.f)) * sg * (1.0f - sg);
                     }
-                    if (affine != nullptr) {
+                    if (use_aff) {
 #pragma unroll
                         for (int k = 0; k < 3; ++k) {
-                            gc[k] = dl[0] * __ldg(affine + 3 * k) + dl[1] * __ldg(affine + 3 * k + 1) +
-                                    dl[2] * __ldg(affine + 3 * k + 2);
+                            gc[k] = dl[0] * af[3 * k] + dl[1] * af[3 * k + 1] + dl[2] * af[3 * k + 2];
 #pragma unroll
                             for (int cc = 0; cc < 3; ++cc) acc[1 + k * 3 + cc] = c[k] * dl[cc];
                         }

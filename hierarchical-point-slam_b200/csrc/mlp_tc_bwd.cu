@@ -630,9 +630,40 @@ template <int KIND> struct GeoW {
     static constexpr int TMEM_COLS = 512;
     static_assert(NH + NE + 80 <= 512, "TMEM budget");
     static constexpr int NTHRW = 320;      // producer warp, MMA warp, 8 flush warps
+    // 4 KB chunks a role streams per quarter tile: the roles are not equally heavy (layer 3 also reads the embedding,
+    // layer 0 reads no hidden slab and no c), so the CTAs are dealt out in proportion to this
+    __host__ __device__ static constexpr int role_chunks(int role) {
+        return role == 0 ? 2 * HS + 2 * ES
+             : role == 3 ? 2 * HS + 2 * (HS + ES) + 1
+             : role == 5 ? 2 * HS + 1 + 2
+                         : 2 * HS + 2 * HS + 1;
+    }
 };
 
-// Everything that is a sum over the points.  CTA b has role b % 6 and works on every (b / 6)-th tile: it streams
+// first CTA of every role (begin[NROLE] = grid size): CTA b has the role r with begin[r] <= b < begin[r + 1]
+struct RoleSplit {
+    int begin[7];
+};
+
+// Deal `grid` (>= NROLE) CTAs out to the roles so that the heaviest per-CTA share is as small as possible: one
+// each, then one at a time to the role with the most chunks per CTA.
+template <int KIND> RoleSplit split_roles(int grid) {
+    using GW = GeoW<KIND>;
+    int n[GW::NROLE];
+    for (int r = 0; r < GW::NROLE; ++r) n[r] = 1;
+    for (int used = GW::NROLE; used < grid; ++used) {
+        int best = 0;
+        for (int r = 1; r < GW::NROLE; ++r)
+            if ((int64_t)GW::role_chunks(r) * n[best] > (int64_t)GW::role_chunks(best) * n[r]) best = r;
+        ++n[best];
+    }
+    RoleSplit s;
+    s.begin[0] = 0;
+    for (int r = 0; r < GW::NROLE; ++r) s.begin[r + 1] = s.begin[r] + n[r];
+    return s;
+}
+
+// Everything that is a sum over the points.  The CTAs of a role (RoleSplit) share its tiles round robin: each streams
 // the dgrad dumps (da_i, d raw) and the forward's operand dumps (y_i, embedding, c) through a 4-stage
 // quarter-tile ring and accumulates over all its tiles in TMEM (contraction over the points: both operands
 // MN-major)
@@ -643,7 +674,7 @@ template <int KIND> struct GeoW {
 template <int KIND>
 __global__ void __launch_bounds__(GeoW<KIND>::NTHRW, 1)
 mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles, const uint32_t* __restrict__ maxbits,
-                    float* __restrict__ scratch) {
+                    float* __restrict__ scratch, const RoleSplit split) {
     using C = Cfg<KIND>;
     using GW = GeoW<KIND>;
     using GB = GeoB<KIND>;
@@ -659,10 +690,12 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
     uint64_t* done = bars + 2 * NSTW;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTW + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int role = blockIdx.x % GW::NROLE;
+    int role = 0;
+#pragma unroll
+    for (int r = 1; r < GW::NROLE; ++r) role += (int)blockIdx.x >= split.begin[r] ? 1 : 0;
     const int layer = role;                                   // roles 0..4
-    const int rank = blockIdx.x / GW::NROLE;
-    const int gsize = ((int)gridDim.x - role + GW::NROLE - 1) / GW::NROLE;     // CTAs with this role
+    const int rank = (int)blockIdx.x - split.begin[role];
+    const int gsize = split.begin[role + 1] - split.begin[role];               // CTAs with this role
     const bool has_h = role >= 1 && role < 5, has_e = (role == 0 || role == 3), has_c = role >= 1;
     const bool mine = rank < num_tiles;
 
@@ -973,7 +1006,7 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
         HPS_CUDA_OK(cudaMemsetAsync(scratch + GB::OFF_T, 0, (size_t)(GB::SCRATCH_FLOATS - GB::OFF_T) * 4, w));
         const int wgrid = GeoW<KIND>::NROLE * num_tiles < kNumSMs ? GeoW<KIND>::NROLE * num_tiles : kNumSMs;   // every role has a CTA
         mlp_wgrad_tc_kernel<KIND><<<wgrid, GeoW<KIND>::NTHRW, GeoW<KIND>::SMEM_BYTES, w>>>(
-            grd, reinterpret_cast<const uint8_t*>(ws), num_tiles, maxbits, scratch);
+            grd, reinterpret_cast<const uint8_t*>(ws), num_tiles, maxbits, scratch, split_roles<KIND>(wgrid));
         const int nout = 5 * (Cfg<KIND>::H * 32 + Cfg<KIND>::H);
         mlp_wfinal_kernel<KIND><<<(nout + 127) / 128, 128, 0, w>>>(prm, grd, scratch);
     }

@@ -95,8 +95,15 @@ class _ZeroPool:
     def want_like(self, tensors, skip_first):
         return [None if (skip_first and i == 0) else self.want(t.shape) for i, t in enumerate(tensors)]
 
-    def alloc(self):
-        self.flat = torch.zeros(max(self.total, 1), dtype=torch.float32, device=self.device)
+    def alloc(self, stream=None):
+        """stream: issue the memset there (the caller orders it: that stream must already wait for the work that last
+        touched the allocator's block, and the consumers must wait for that stream)."""
+        if stream is None:
+            self.flat = torch.zeros(max(self.total, 1), dtype=torch.float32, device=self.device)
+        else:
+            self.flat = torch.empty(max(self.total, 1), dtype=torch.float32, device=self.device)
+            with torch.cuda.stream(stream):
+                self.flat.zero_()
         return self
 
     def get(self, h):
@@ -796,6 +803,7 @@ class _RenderRays(torch.autograd.Function):
         ctx.row_map = row_map
         ctx.n_live = feats_geo.shape[0] if row_map is not None else None
         ctx.save_for_backward(z, pts, I, w, has, c_geo, c_col, occ, rgb, act_g, act_c, fg, fc, aff, pos, *gprm, *cprm)
+        ctx.set_materialize_grads(False)        # no zero tensors for the outputs nobody differentiates
         if lm is not None:
             ctx.mark_non_differentiable(depth, var, color, valid)
             return flat[0], depth, var, color, valid
@@ -843,7 +851,13 @@ class _RenderRays(torch.autograd.Function):
         tc_dp = need_p and ctx.saved_kinds[0] == "tc"
         h_dpg = zp.want((P, 3)) if tc_dp else None                          # accumulated by the dgrad kernels
         h_dpc = zp.want((P, 3)) if (tc_dp and spec.color_stage) else None
-        zp.alloc()
+        with torch.cuda.device(dev):
+            if fork:        # the memset runs beside the compositing backward instead of in front of it
+                main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+                side.wait_stream(main)
+                zp.alloc(side)
+            else:
+                zp.alloc()
         dg, dcw, daff = zp.get(h_dg), zp.get(h_dcw), zp.get(h_daff)
         dfg, dfc = zp.get(h_dfg), zp.get(h_dfc)
         dp_i = torch.empty(P, 3, **f32) if need_p else None
@@ -859,8 +873,8 @@ class _RenderRays(torch.autograd.Function):
             dp_c = None
             wgrad_streams = ()
             if fork:
-                main, side = torch.cuda.current_stream(dev), _side_stream(dev)
                 dp_g, dp_c = zp.get(h_dpg), zp.get(h_dpc)
+                main.wait_stream(side)          # the zeroed buffers
                 side.wait_stream(main)
                 n_c, n_g = _sm_split(P, "bwd")
                 # the HBM-bound weight-gradient kernels go to streams of their own: the feature scatter below needs

@@ -48,12 +48,17 @@ targets = [lg.param, lc.param] + list(dec.parameters())
 def step():
     for t in targets:
         t.grad = None
-    depth, unc, color, valid = renderer.render_batch_ray(
-        npc, dec, st["rays_d"], st["rays_o"], dev, bench.STAGE, gt_depth=st["gt_depth"], npc_geo_feats=gf,
-        npc_col_feats=cf, is_tracker=False, cloud_pos=pos, dynamic_r_query={"fine": st["radius"], "mid": st["radius_mid"]},
-        exposure_feat=None)
-    affine = dec.color_decoder_fine.mlp_exposure(exposure_feat)
-    loss = hps.mapper_loss(depth, color, valid, st["gt_depth"], st["gt_color"], bench.STAGE, 0.1, affine)
+    rq = {"fine": st["radius"], "mid": st["radius_mid"]}
+    if bench.FUSED_LOSS:
+        loss = renderer.render_batch_ray_loss(
+            npc, dec, st["rays_d"], st["rays_o"], dev, bench.STAGE, st["gt_depth"], st["gt_color"], 0.1,
+            npc_geo_feats=gf, npc_col_feats=cf, cloud_pos=pos, dynamic_r_query=rq, exposure_feat=exposure_feat)[0]
+    else:
+        depth, unc, color, valid = renderer.render_batch_ray(
+            npc, dec, st["rays_d"], st["rays_o"], dev, bench.STAGE, gt_depth=st["gt_depth"], npc_geo_feats=gf,
+            npc_col_feats=cf, is_tracker=False, cloud_pos=pos, dynamic_r_query=rq, exposure_feat=None)
+        affine = dec.color_decoder_fine.mlp_exposure(exposure_feat)
+        loss = hps.mapper_loss(depth, color, valid, st["gt_depth"], st["gt_color"], bench.STAGE, 0.1, affine)
     loss.backward()
     return loss
 
