@@ -498,11 +498,9 @@ def time_tracker(hps, npc, dec, renderer, scene, cfg, dev, gf, cf, pos, iters=10
     try:
         cam = torch.tensor([1.0, 0.0, 0.0, 0.0, 0.005, -0.004, 0.003], device=dev).requires_grad_(True)
         ef = scene["exposure_feat"].to(dev).clone().requires_grad_(True)
-        opt = torch.optim.Adam([cam, ef], lr=5e-4, capturable=True)
-        cam.grad, ef.grad = torch.zeros_like(cam), torch.zeros_like(ef)
+        opt = hps.FusedAdam([([cam, ef], 5e-4)])      # torch.optim.Adam semantics, one kernel (gradients cleared by it)
 
         def it():
-            opt.zero_grad(set_to_none=False)
             c2w = hps.get_camera_from_tensor(cam)
             ro, rd = hps.get_rays_from_uv(pi, pj, c2w, K["H"], K["W"], K["fx"], K["fy"], K["cx"], K["cy"], dev)
             d, v, c, _ = renderer.render_batch_ray(npc, dec, rd, ro, dev, STAGE, gt_depth=gt_d, npc_geo_feats=feats_g,

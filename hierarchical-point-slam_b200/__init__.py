@@ -11,7 +11,7 @@ from .common import (get_camera_from_tensor, get_rays, get_rays_from_uv, quad2ro
 from .decoder import NICER, PointDecoder  # noqa: F401
 from .losses import mapper_loss, mapper_loss_torch, tracker_loss, tracker_loss_torch  # noqa: F401
 from .neural_point import GridIndex, NeuralPointCloud  # noqa: F401
-from .ops import LiveRows, RowAdam  # noqa: F401
+from .ops import FusedAdam, LiveRows, RowAdam  # noqa: F401
 from .renderer import Renderer  # noqa: F401
 
 

@@ -55,7 +55,81 @@ adam_rows_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
     }
 }
 
+// The same update for a handful of small dense tensors (tracker: pose quaternion / translation, exposure latent and
+// exposure MLP, reference src/Tracker.py:383-416) in ONE launch: torch.optim.Adam's capturable foreach path is ~20
+// launches of 1-2 us each, more than a tenth of a tracker iteration.  Tensor descriptors travel by value in the
+// kernel arguments.  zero_grad != 0: the gradient is cleared after use (the next backward accumulates into it), so
+// the caller's optimizer.zero_grad() disappears as well.
+constexpr int kAdamMaxTensors = 24;
+struct AdamPack {
+    float* p[kAdamMaxTensors];
+    float* g[kAdamMaxTensors];
+    float* m[kAdamMaxTensors];
+    float* v[kAdamMaxTensors];
+    float lr[kAdamMaxTensors];
+    int n[kAdamMaxTensors];
+    int block_begin[kAdamMaxTensors + 1];
+    int count;
+};
+
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const AdamPack pk, float b1, float b2, float eps, int* __restrict__ step, int zero_grad) {
+    const int t = step[0] + 1;
+    const float bc1 = 1.0f - powf(b1, (float)t), bc2 = 1.0f - powf(b2, (float)t);
+    const float inv_sqrt_bc2 = 1.0f / sqrtf(bc2);
+    int ti = 0;
+    while (ti + 1 < pk.count && (int)blockIdx.x >= pk.block_begin[ti + 1]) ++ti;
+    const int i = ((int)blockIdx.x - pk.block_begin[ti]) * blockDim.x + threadIdx.x;
+    if (i < pk.n[ti]) {
+        const float gr = pk.g[ti][i];
+        const float mm = pk.m[ti][i] + (gr - pk.m[ti][i]) * (1.0f - b1);
+        const float vv = pk.v[ti][i] * b2 + (1.0f - b2) * gr * gr;
+        const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+        pk.m[ti][i] = mm;
+        pk.v[ti][i] = vv;
+        pk.p[ti][i] = pk.p[ti][i] - (pk.lr[ti] / bc1) * (mm / denom);
+        if (zero_grad) pk.g[ti][i] = 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const int done = atomicAdd(step + 1, 1) + 1;
+        if (done == (int)gridDim.x) {
+            step[1] = 0;
+            step[0] = t;
+        }
+    }
+}
+
 }  // namespace hps
+
+extern "C" int hps_adam_multi(int n_tensors, float* const* params, float* const* grads, float* const* exp_avg,
+                              float* const* exp_avg_sq, const int64_t* numel, const float* lr, float beta1,
+                              float beta2, float eps, int32_t* step, int zero_grad, void* stream) {
+    using namespace hps;
+    HPS_REQUIRE(n_tensors >= 0 && n_tensors <= kAdamMaxTensors, "at most 24 tensors per call");
+    if (n_tensors == 0) return 0;
+    HPS_REQUIRE(params && grads && exp_avg && exp_avg_sq && numel && lr && step, "null buffer");
+    AdamPack pk;
+    pk.count = n_tensors;
+    int blocks = 0;
+    for (int i = 0; i < n_tensors; ++i) {
+        HPS_REQUIRE(params[i] && grads[i] && exp_avg[i] && exp_avg_sq[i], "null tensor pointer");
+        HPS_REQUIRE(numel[i] > 0 && numel[i] < (1ll << 24), "tensor size out of range for the small-tensor Adam");
+        pk.p[i] = params[i];
+        pk.g[i] = grads[i];
+        pk.m[i] = exp_avg[i];
+        pk.v[i] = exp_avg_sq[i];
+        pk.lr[i] = lr[i];
+        pk.n[i] = (int)numel[i];
+        pk.block_begin[i] = blocks;
+        blocks += (int)ceil_div(numel[i], 256);
+    }
+    pk.block_begin[n_tensors] = blocks;
+    adam_multi_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pk, beta1, beta2, eps, step, zero_grad);
+    HPS_LAUNCH_OK();
+    return 0;
+}
 
 extern "C" int hps_adam_rows(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t M, int C,
                              float lr, float beta1, float beta2, float eps, int32_t* step, float* table,

@@ -49,7 +49,9 @@ __global__ void sample_rays_kernel(const float* __restrict__ rays_o, const float
 }
 
 // g_rays_o[r] = sum_s dp[r,s],  g_rays_d[r] = sum_s dp[r,s] * z[r,s]
-__global__ void sample_rays_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ z, int64_t R, int S,
+// (dp = dp + dp2 + dp3 where given: the two decoders' and the gather's contributions, summed on the fly)
+__global__ void sample_rays_bwd_kernel(const float* __restrict__ dp, const float* __restrict__ dp2,
+                                       const float* __restrict__ dp3, const float* __restrict__ z, int64_t R, int S,
                                        float* __restrict__ g_o, float* __restrict__ g_d) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= R * 3) return;
@@ -57,7 +59,10 @@ __global__ void sample_rays_bwd_kernel(const float* __restrict__ dp, const float
     const int a = (int)(i - r * 3);
     float so = 0.f, sd = 0.f;
     for (int s = 0; s < S; ++s) {
-        const float g = __ldg(dp + (r * S + s) * 3 + a);
+        const int64_t e = (r * S + s) * 3 + a;
+        float g = __ldg(dp + e);
+        if (dp2 != nullptr) g += __ldg(dp2 + e);
+        if (dp3 != nullptr) g += __ldg(dp3 + e);
         so += g;
         sd += g * __ldg(z + r * S + s);
     }
@@ -81,14 +86,14 @@ extern "C" int hps_sample_rays(const float* rays_o, const float* rays_d, const f
     return 0;
 }
 
-extern "C" int hps_sample_rays_bwd(const float* dp, const float* z, int64_t R, int S, float* g_rays_o, float* g_rays_d,
-                                   void* stream) {
+extern "C" int hps_sample_rays_bwd(const float* dp, const float* dp2, const float* dp3, const float* z, int64_t R, int S,
+                                   float* g_rays_o, float* g_rays_d, void* stream) {
     using namespace hps;
     HPS_REQUIRE(R >= 0 && S >= 1, "bad sizes");
     if (R == 0) return 0;
     HPS_REQUIRE(dp && z && g_rays_o && g_rays_d, "null buffer");
-    sample_rays_bwd_kernel<<<(unsigned)ceil_div(R * 3, 256), 256, 0, (cudaStream_t)stream>>>(dp, z, R, S, g_rays_o,
-                                                                                             g_rays_d);
+    sample_rays_bwd_kernel<<<(unsigned)ceil_div(R * 3, 256), 256, 0, (cudaStream_t)stream>>>(dp, dp2, dp3, z, R, S,
+                                                                                             g_rays_o, g_rays_d);
     HPS_LAUNCH_OK();
     return 0;
 }

@@ -44,7 +44,7 @@ _KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_interp_fwd": 
                      "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_mlp_tc_pack": 1, "hps_mlp_tc_fwd": 1,
                      "hps_mlp_tc_bwd_pack": 2, "hps_mlp_tc_bwd": 3, "hps_tc_selftest": 1, "hps_composite_fwd": 1,
                      "hps_composite_bwd": 1, "hps_composite_mapper_loss": 1, "hps_sample_rays": 1, "hps_sample_rays_bwd": 1, "hps_mapper_loss": 1,
-                     "hps_tracker_loss_stats": 1, "hps_tracker_loss": 1, "hps_exposure_fwd": 1, "hps_exposure_bwd": 1, "hps_camera_from_tensor": 1, "hps_adam_rows": 1,
+                     "hps_tracker_loss_stats": 1, "hps_tracker_loss": 1, "hps_exposure_fwd": 1, "hps_exposure_bwd": 1, "hps_camera_from_tensor": 1, "hps_adam_rows": 1, "hps_adam_multi": 1,
                      "hps_camera_from_tensor_bwd": 1, "hps_rays_from_uv": 1, "hps_rays_from_uv_bwd": 1}
 TIMERS = None   # set to {} to record (start, end) CUDA events per call name on the current stream
 
@@ -899,11 +899,9 @@ class _RenderRays(torch.autograd.Function):
                       _lib.ptr(dfg), _lib.ptr(dfc), _lib.ptr(dp_i), _lib.ptr(ctx.row_map), st())
             g_ro = g_rd = None
             if need_p:
-                dp = dp_g + dp_i
-                if dp_c is not None:
-                    dp += dp_c
                 g_ro, g_rd = torch.empty(R, 3, **f32), torch.empty(R, 3, **f32)
-                _call("hps_sample_rays_bwd", _lib.ptr(dp), _lib.ptr(z), R, S, _lib.ptr(g_ro), _lib.ptr(g_rd), st())
+                _call("hps_sample_rays_bwd", _lib.ptr(dp_g), _lib.ptr(dp_i), _lib.ptr(dp_c), _lib.ptr(z), R, S,
+                      _lib.ptr(g_ro), _lib.ptr(g_rd), st())
             g_exp = ()
             if ctx.loss_state is not None and l_eprm:
                 # exposure MLP backward from d loss / d affine (accumulated by the fused loss kernel); the main stream
@@ -991,6 +989,66 @@ class RowAdam:
                       lr, float(self.betas[0]), float(self.betas[1]), self.eps, _lib.ptr(st["step"]), _lib.ptr(rows.table),
                       _lib.ptr(rows.indices), _stream())
             rows.fresh = True
+
+
+class FusedAdam:
+    """torch.optim.Adam semantics (no amsgrad, no weight decay) for a few small dense tensors - the tracker's pose,
+    exposure latent and exposure MLPs (Tracker.py:383-416) - as ONE kernel per step instead of the ~20 launches of
+    torch's capturable foreach path.  `groups`: list of (tensor or list of tensors, lr) = parameter groups.
+    Every gradient lives in one flat buffer (p.grad are views of it, created here and kept: backward accumulates into
+    them) and is cleared by the step kernel itself, so zero_grad() costs nothing.  Device step counter: capturable."""
+
+    MAX = 24
+
+    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8):
+        self.params, self.lrs = [], []
+        for tensors, lr in groups:
+            for t in ([tensors] if torch.is_tensor(tensors) else list(tensors)):
+                _need_cuda(t)
+                if t.dtype != torch.float32 or not t.is_contiguous():
+                    raise _lib.HpsError("FusedAdam takes contiguous fp32 tensors")
+                self.params.append(t)
+                self.lrs.append(float(lr))
+        if not self.params:
+            raise ValueError("no parameters")
+        dev = self.params[0].device
+        self.betas, self.eps = betas, float(eps)
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]
+        self._flat = torch.zeros(3, sum(sizes), dtype=torch.float32, device=dev)        # grad | exp_avg | exp_avg_sq
+        self._views, off = [], 0
+        for p, n in zip(self.params, sizes):
+            g, m, v = (self._flat[k, off:off + p.numel()].view(p.shape) for k in range(3))
+            p.grad = g
+            self._views.append((g, m, v))
+            off += n
+        n_chunks = (len(self.params) + self.MAX - 1) // self.MAX
+        self.step_count = torch.zeros(n_chunks, 2, dtype=torch.int32, device=dev)     # one counter per launch
+
+    def set_lr(self, index, lr):
+        self.lrs[index] = float(lr)
+
+    def zero_grad(self, set_to_none=False):
+        """Nothing to do after a step() (the kernel cleared the gradients); kept for optimiser-shaped call sites."""
+        if set_to_none:
+            raise _lib.HpsError("FusedAdam keeps its gradient buffers (views of one allocation)")
+
+    @torch.no_grad()
+    def step(self):
+        ps, gs, ms, vs = [], [], [], []
+        for p, (g, m, v) in zip(self.params, self._views):
+            if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+                raise _lib.HpsError("FusedAdam: a .grad was replaced; keep the buffers (zero_grad(set_to_none=False))")
+            ps.append(p); gs.append(g); ms.append(m); vs.append(v)
+        dev = self.params[0].device
+        with torch.cuda.device(dev):
+            for s in range(0, len(ps), self.MAX):
+                e = min(s + self.MAX, len(ps))
+                n = e - s
+                numel = (ctypes.c_int64 * n)(*[p.numel() for p in ps[s:e]])
+                lrs = (ctypes.c_float * n)(*self.lrs[s:e])
+                arrs = [(ctypes.c_void_p * n)(*[t.data_ptr() for t in ts[s:e]]) for ts in (ps, gs, ms, vs)]
+                _call("hps_adam_multi", n, arrs[0], arrs[1], arrs[2], arrs[3], numel, lrs, float(self.betas[0]),
+                      float(self.betas[1]), self.eps, _lib.ptr(self.step_count[s // self.MAX]), 1, _stream())
 
 
 # --------------------------------------------------------------------------------------------------

@@ -187,6 +187,13 @@ int hps_composite_mapper_loss(const float* rgb, int rgb_stride, const float* occ
  * ---------------------------------------------------------------------------------------------- */
 int hps_adam_rows(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t M, int C, float lr,
                   float beta1, float beta2, float eps, int32_t* step, float* table, const int64_t* rows, void* stream);
+/* The same update for up to 24 small dense fp32 tensors in one launch (tracker: pose, exposure latent, exposure MLPs -
+ * Tracker.py:383-416 builds a torch.optim.Adam over exactly these).  params / grads / exp_avg / exp_avg_sq: HOST arrays
+ * of n_tensors device pointers; numel, lr: HOST arrays (per-tensor size and learning rate = parameter groups);
+ * step as above (one counter for the call).  zero_grad != 0: every gradient is cleared after it has been used.   */
+int hps_adam_multi(int n_tensors, float* const* params, float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const int64_t* numel, const float* lr, float beta1, float beta2,
+                   float eps, int32_t* step, int zero_grad, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Exposure MLP (decoder.py:380-396 MLP_exposure: linear1 -> Softplus(beta=100) -> linear2) on one latent
@@ -207,13 +214,13 @@ int hps_exposure_bwd(const float* x, const float* W1, const float* W2, const flo
  *   rays with gt_depth == 0 take z_zero[r*z_zero_stride + s]: z_zero_stride 0 = one shared row of S floats
  *   (Renderer.py:207-208), S = one row per ray (the sample_near_pcl mode, Renderer.py:197-206); NULL -> 0.
  *   radius: per-RAY float64 radii (may be NULL -> radius_scalar), repeated per sample into t_up/t_dn.
- * hps_sample_rays_bwd: g_rays_o = sum_s dp, g_rays_d = sum_s dp * z (tracker pose path).
+ * hps_sample_rays_bwd: g_rays_o = sum_s dp, g_rays_d = sum_s dp * z with dp = dp + dp2 + dp3 (tracker pose path).
  * ---------------------------------------------------------------------------------------------- */
 int hps_sample_rays(const float* rays_o, const float* rays_d, const float* gt_depth, const double* radius,
                     double radius_scalar, const float* z_zero, int64_t z_zero_stride, int64_t R, int S, float near,
                     float far, float* z, float* pts, float* t_up, float* t_dn, void* stream);
-int hps_sample_rays_bwd(const float* dp, const float* z, int64_t R, int S, float* g_rays_o, float* g_rays_d,
-                        void* stream);
+int hps_sample_rays_bwd(const float* dp, const float* dp2 /* may be NULL */, const float* dp3 /* may be NULL */,
+                        const float* z, int64_t R, int S, float* g_rays_o, float* g_rays_d, void* stream);
 
 /* Tracker pose helpers (common.py:304-346 get_camera_from_tensor / quad2rotation, :103-119 get_rays_from_uv) as
  * single kernels with analytic backward; arithmetic is rounded like the reference's torch expressions.

@@ -436,3 +436,73 @@ def test_row_adam_matches_torch_adam_and_writes_table(hps):
     untouched[idx] = False
     assert torch.equal(rows.table[untouched], table[untouched])
     assert int(opt.state[0]["step"][0]) == 7 and int(opt.state[0]["step"][1]) == 0
+
+
+def test_fused_adam_matches_torch_adam(hps):
+    """FusedAdam (the tracker's optimiser, Tracker.py:383-416: pose / exposure latent / exposure MLP groups with their
+    own learning rates) vs torch.optim.Adam over several steps; gradients accumulate into the optimiser's buffers and
+    are cleared by the step kernel; the whole loss.backward(); step() pair replays from a CUDA graph."""
+    torch.manual_seed(11)
+    shapes = [(7,), (8,), (128, 8), (128,), (12, 128), (12,), (3,), (4,)]
+    lrs = [5e-4, 1e-3, 1e-3, 1e-3, 1e-3, 1e-3, 2e-3, 4e-4]
+    mine = [torch.randn(s, device=DEV).requires_grad_(True) for s in shapes]
+    ref = [p.detach().clone().requires_grad_(True) for p in mine]
+    groups = [([mine[0]], lrs[0]), (mine[1:6], lrs[1]), (mine[6], lrs[6]), ([mine[7]], lrs[7])]
+    opt = hps.FusedAdam(groups)
+    topt = torch.optim.Adam([{"params": [ref[0]], "lr": lrs[0]}, {"params": ref[1:6], "lr": lrs[1]},
+                             {"params": [ref[6]], "lr": lrs[6]}, {"params": [ref[7]], "lr": lrs[7]}])
+    coef = [torch.randn(s, device=DEV) for s in shapes]
+
+    def loss_of(ps, k):
+        return sum(((p * c).sum() * (k + 1.0)) ** 2 + (p ** 3).sum() * 0.1 for p, c in zip(ps, coef))
+
+    for k in range(6):
+        if k == 3:
+            opt.set_lr(0, 1e-4)
+            topt.param_groups[0]["lr"] = 1e-4
+        opt.zero_grad()
+        topt.zero_grad()
+        loss_of(mine, k).backward()
+        loss_of(ref, k).backward()
+        opt.step()
+        topt.step()
+        for a, b in zip(mine, ref):
+            assert float((a.detach() - b.detach()).abs().max()) <= 2e-6 * max(1.0, float(b.detach().abs().max()))
+            assert float(a.grad.abs().max()) == 0.0             # cleared by the step kernel
+    assert int(opt.step_count[0, 0]) == 6 and int(opt.step_count[0, 1]) == 0
+
+    # graph replay: the device step counter advances, results keep following torch.optim.Adam
+    def it():
+        loss_of(mine, 1).backward()
+        opt.step()
+    g = hps.graphs.GraphedStep(it, {}, warmup=1)                  # one executed warm-up step, then the recording
+    topt.zero_grad()
+    loss_of(ref, 1).backward()
+    topt.step()
+    for _ in range(3):
+        g()
+        topt.zero_grad()
+        loss_of(ref, 1).backward()
+        topt.step()
+    torch.cuda.synchronize()
+    assert int(opt.step_count[0, 0]) == 10
+    for a, b in zip(mine, ref):
+        assert float((a.detach() - b.detach()).abs().max()) <= 5e-6 * max(1.0, float(b.detach().abs().max()))
+    with pytest.raises(hps._lib.HpsError):
+        mine[0].grad = torch.zeros_like(mine[0])
+        opt.step()
+
+
+def test_sample_rays_bwd_sums_its_three_terms(hps):
+    R, S = 333, 5
+    g = torch.Generator(device=DEV).manual_seed(2)
+    dps = [torch.randn(R * S, 3, device=DEV, generator=g) for _ in range(3)]
+    z = torch.rand(R, S, device=DEV, generator=g) + 1
+    L = hps._lib
+    for n in (1, 2, 3):
+        go, gd = torch.empty(R, 3, device=DEV), torch.empty(R, 3, device=DEV)
+        hps.ops._call("hps_sample_rays_bwd", L.ptr(dps[0]), L.ptr(dps[1]) if n > 1 else None, L.ptr(dps[2]) if n > 2 else None,
+                      L.ptr(z), R, S, L.ptr(go), L.ptr(gd), hps.ops._stream())
+        dp = sum(dps[:n]).view(R, S, 3)
+        assert torch.allclose(go, dp.sum(1), rtol=1e-5, atol=1e-5)
+        assert torch.allclose(gd, (dp * z[..., None]).sum(1), rtol=1e-5, atol=1e-5)
