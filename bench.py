@@ -503,10 +503,15 @@ def time_tracker(hps, npc, dec, renderer, scene, cfg, dev, gf, cf, pos, iters=10
         def it():
             c2w = hps.get_camera_from_tensor(cam)
             ro, rd = hps.get_rays_from_uv(pi, pj, c2w, K["H"], K["W"], K["fx"], K["fy"], K["cx"], K["cy"], dev)
-            d, v, c, _ = renderer.render_batch_ray(npc, dec, rd, ro, dev, STAGE, gt_depth=gt_d, npc_geo_feats=feats_g,
-                                                   npc_col_feats=feats_c, is_tracker=True, cloud_pos=pos,
-                                                   dynamic_r_query=dict(rq), exposure_feat=ef)
-            loss = hps.tracker_loss(d, v, c, gt_d, gt_c, 0.5)
+            if FUSED_LOSS:
+                loss = renderer.render_batch_ray_tracker_loss(
+                    npc, dec, rd, ro, dev, STAGE, gt_d, gt_c, 0.5, npc_geo_feats=feats_g, npc_col_feats=feats_c,
+                    cloud_pos=pos, dynamic_r_query=dict(rq), exposure_feat=ef)[0]
+            else:
+                d, v, c, _ = renderer.render_batch_ray(npc, dec, rd, ro, dev, STAGE, gt_depth=gt_d, npc_geo_feats=feats_g,
+                                                       npc_col_feats=feats_c, is_tracker=True, cloud_pos=pos,
+                                                       dynamic_r_query=dict(rq), exposure_feat=ef)
+                loss = hps.tracker_loss(d, v, c, gt_d, gt_c, 0.5)
             loss.backward()
             opt.step()
             return loss

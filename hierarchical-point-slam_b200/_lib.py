@@ -40,7 +40,7 @@ SIGNATURES = {
     "hps_tc_trace": (_i32, [_vp]),
     "hps_mlp_bwd": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "hps_composite_fwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp,
-                                 _vp]),
+                                 _vp, _vp, _i32, _vp]),
     "hps_composite_bwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp,
                                  _i32, _vp, _vp, _vp]),
     "hps_composite_mapper_loss": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _f32]

@@ -83,7 +83,8 @@ composite_fwd_kernel(const float* __restrict__ rgb, int rgb_stride, const float*
                      int occ_stride, const uint8_t* __restrict__ point_mask, const float* __restrict__ z,
                      int64_t R, int S, float coef, float* __restrict__ depth_out, float* __restrict__ var_out,
                      float* __restrict__ color_out, float* __restrict__ weights_out, int min_valid,
-                     uint8_t* __restrict__ valid_ray) {
+                     uint8_t* __restrict__ valid_ray, const float* __restrict__ gt_depth,
+                     float* __restrict__ tracker_sum, int zero_missing) {
     constexpr int RPW = 32 / G;
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -102,6 +103,16 @@ composite_fwd_kernel(const float* __restrict__ rgb, int rgb_stride, const float*
         const bool pm = active && (point_mask == nullptr || point_mask[ray * S + s] != 0);
         const unsigned grp = (G == 32) ? kFull : (((1u << G) - 1u) << (sub * G));
         n_has = __popc(__ballot_sync(kFull, pm) & grp);
+    }
+    if (tracker_sum != nullptr) {   // Tracker.py:217: sum over the batch of |gt - depth| / sqrt(var + 1e-10)
+        float t = 0.f;
+        if (live && s == 0) {
+            const float gd = __ldg(gt_depth + ray);
+            // rays without a depth reading: the renderer reports depth 0 for them (Renderer.py:250-251)
+            t = fabsf(gd - ((zero_missing && !(gd > 0.f)) ? 0.f : depth)) / sqrtf(var + 1e-10f);
+        }
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(kFull, t, o);
+        if (lane == 0) red_add(tracker_sum, t);
     }
     if (!live) return;
     if (s == 0 && valid_ray != nullptr) valid_ray[ray] = n_has >= min_valid ? 1 : 0;
@@ -331,21 +342,23 @@ extern "C" int hps_composite_mapper_loss(const float* rgb, int rgb_stride, const
 extern "C" int hps_composite_fwd(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
                                  const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
                                  float* depth, float* var, float* color, float* weights, int min_valid,
-                                 uint8_t* valid_ray, void* stream) {
+                                 uint8_t* valid_ray, const float* gt_depth, float* tracker_sum, int zero_missing,
+                                 void* stream) {
     using namespace hps;
     HPS_REQUIRE(R >= 0 && S >= 1 && S <= 32, "need 1 <= S <= 32");
     if (R == 0) return 0;
     HPS_REQUIRE(occ && z && depth && var && color, "null buffer");
+    HPS_REQUIRE(tracker_sum == nullptr || gt_depth != nullptr, "tracker_sum needs gt_depth");
     const int tb = 256;
     if (S <= 8) {
         const int64_t warps = ceil_div(R, 4);
         composite_fwd_kernel<8><<<(unsigned)ceil_div(warps * 32, tb), tb, 0, (cudaStream_t)stream>>>(
             rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, depth, var, color, weights, min_valid,
-            valid_ray);
+            valid_ray, gt_depth, tracker_sum, zero_missing);
     } else {
         composite_fwd_kernel<32><<<(unsigned)ceil_div(R * 32, tb), tb, 0, (cudaStream_t)stream>>>(
             rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, depth, var, color, weights, min_valid,
-            valid_ray);
+            valid_ray, gt_depth, tracker_sum, zero_missing);
     }
     HPS_LAUNCH_OK();
     return 0;

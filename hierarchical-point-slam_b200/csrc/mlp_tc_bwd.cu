@@ -909,14 +909,19 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
 }
 
 // dWc_i = W_{i+1}[:, hidden]^T T_{i+1},  dbc_i = db_{i+1} W_{i+1}[:, hidden]  (i = 0..3);  dWc_4 = Wo^T V,  dbc_4 = dbo Wo.
-// One thread per output element; 128-term dot products over L2-resident weights.
+// WFINAL_PARTS threads per output element, each with a quarter of the H-term dot product over L2-resident weights
+// (fully unrolled: all its loads are in flight at once - the kernel is pure latency), combined by the red.add that
+// writes the gradient anyway.
+constexpr int WFINAL_PARTS = 4;
 template <int KIND>
-__global__ void mlp_wfinal_kernel(Ptrs prm, GradPtrs grd, const float* __restrict__ scratch) {
+__global__ void __launch_bounds__(128) mlp_wfinal_kernel(Ptrs prm, GradPtrs grd, const float* __restrict__ scratch) {
     using C = Cfg<KIND>;
     using GB = GeoB<KIND>;
-    constexpr int H = C::H, E = C::E, NOUT = C::NOUT;
+    constexpr int H = C::H, E = C::E, NOUT = C::NOUT, HQ = H / WFINAL_PARTS;
+    static_assert(H % WFINAL_PARTS == 0, "hidden width must split evenly");
     const int per = H * 32 + H;                               // outputs per layer: dWc (H x 32) + dbc (H)
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 5 * per; idx += gridDim.x * blockDim.x) {
+    for (int tid = blockIdx.x * blockDim.x + threadIdx.x; tid < WFINAL_PARTS * 5 * per; tid += gridDim.x * blockDim.x) {
+        const int part = tid / (5 * per), idx = tid - part * (5 * per);
         const int i = idx / per, r = idx % per;
         const bool bias = r >= H * 32;
         const int hin = bias ? r - H * 32 : r / 32, k = r % 32;
@@ -926,14 +931,28 @@ __global__ void mlp_wfinal_kernel(Ptrs prm, GradPtrs grd, const float* __restric
             const float* w = prm.v[iW(i + 1)] + off + hin;                    // W_{i+1}[ho][off + hin], pitch Kn
             if (bias) {
                 const float* sdb = scratch + GB::OFF_SDB + i * H;
-#pragma unroll 32
-                for (int ho = 0; ho < H; ++ho) acc = fmaf(__ldg(sdb + ho), __ldg(w + (int64_t)ho * Kn), acc);
+                float a[HQ], b[HQ];
+#pragma unroll
+                for (int j = 0; j < HQ; ++j) {               // every load issued before the first use
+                    const int ho = part * HQ + j;
+                    a[j] = __ldg(sdb + ho);
+                    b[j] = __ldg(w + (int64_t)ho * Kn);
+                }
+#pragma unroll
+                for (int j = 0; j < HQ; ++j) acc = fmaf(a[j], b[j], acc);
             } else {
                 const float* t = scratch + GB::OFF_T + i * H * 32 + k;
-#pragma unroll 32
-                for (int ho = 0; ho < H; ++ho) acc = fmaf(__ldg(w + (int64_t)ho * Kn), __ldg(t + ho * 32), acc);
+                float a[HQ], b[HQ];
+#pragma unroll
+                for (int j = 0; j < HQ; ++j) {
+                    const int ho = part * HQ + j;
+                    a[j] = __ldg(w + (int64_t)ho * Kn);
+                    b[j] = __ldg(t + ho * 32);
+                }
+#pragma unroll
+                for (int j = 0; j < HQ; ++j) acc = fmaf(a[j], b[j], acc);
             }
-        } else {
+        } else if (part == 0) {
             const float* wo = prm.v[iWo] + hin;
             if (bias) {
                 for (int o = 0; o < NOUT; ++o) acc = fmaf(scratch[GB::OFF_SDBO + o], wo[o * H], acc);
@@ -941,6 +960,7 @@ __global__ void mlp_wfinal_kernel(Ptrs prm, GradPtrs grd, const float* __restric
                 for (int o = 0; o < NOUT; ++o) acc = fmaf(wo[o * H], scratch[GB::OFF_V + o * 32 + k], acc);
             }
         }
+        if (i == 4 && part != 0) continue;                    // the output-layer terms are three products: one thread
         if (bias) red_add(grd.v[iBc(i)] + hin, acc);
         else red_add(grd.v[iWc(i)] + hin * kC + k, acc);
     }
@@ -1008,7 +1028,7 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
         mlp_wgrad_tc_kernel<KIND><<<wgrid, GeoW<KIND>::NTHRW, GeoW<KIND>::SMEM_BYTES, w>>>(
             grd, reinterpret_cast<const uint8_t*>(ws), num_tiles, maxbits, scratch, split_roles<KIND>(wgrid));
         const int nout = 5 * (Cfg<KIND>::H * 32 + Cfg<KIND>::H);
-        mlp_wfinal_kernel<KIND><<<(nout + 127) / 128, 128, 0, w>>>(prm, grd, scratch);
+        mlp_wfinal_kernel<KIND><<<(WFINAL_PARTS * nout + 127) / 128, 128, 0, w>>>(prm, grd, scratch);
     }
     return 0;
 }

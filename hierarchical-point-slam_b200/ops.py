@@ -486,7 +486,8 @@ class _CompositeRaw(torch.autograd.Function):
         with torch.cuda.device(dev):
             _call("hps_composite_fwd", 
                 ctypes.c_void_p(base), 4, ctypes.c_void_p(base + 12), 4, _lib.ptr(pm), _lib.ptr(z_c), R, S,
-                float(coef), _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), _lib.ptr(weights), 0, None, _stream())
+                float(coef), _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), _lib.ptr(weights), 0, None, None, None, 0,
+                _stream())
         ctx.save_for_backward(raw_c, z_c, pm)
         ctx.coef = float(coef)
         ctx.mark_non_differentiable(var)
@@ -631,6 +632,17 @@ class MapperLossSpec:
         self.gt_color, self.w_color, self.exposure = gt_color, float(w_color), bool(exposure)
 
 
+class TrackerLossSpec:
+    """Fuses the tracker's loss (Tracker.py:213-231) into render_rays: the batch statistic sum |gt - depth| / sqrt(var)
+    is accumulated by the compositing kernel, the loss kernel applies the 10 x mean outlier mask.  `gt_color` (R,3) or
+    None (depth only), `w_color`, `reduce_fn` as in tracker_loss (rays sharded over ranks), `zero_missing`: the
+    renderer reports depth 0 for rays without a depth reading (Renderer.py:250-251)."""
+    __slots__ = ("gt_color", "w_color", "reduce_fn", "zero_missing")
+
+    def __init__(self, gt_color, w_color, reduce_fn=None, zero_missing=False):
+        self.gt_color, self.w_color, self.reduce_fn, self.zero_missing = gt_color, float(w_color), reduce_fn, zero_missing
+
+
 class _RenderRays(torch.autograd.Function):
     """depth (R,), var (R,), color (R,3), valid (R,) uint8  =  f(rays_o, rays_d, gt_depth, feats_geo, feats_col,
     affine, 23 geometry-decoder tensors, 23 colour-decoder tensors).  Ten kernel launches forward, five or
@@ -671,13 +683,12 @@ class _RenderRays(torch.autograd.Function):
         # loss mode: [loss, pad x3 | d_affine (12) | g_depth (R) | g_color (3R)] in one buffer, head zeroed (accumulators)
         lm = spec.loss
         eprm, flat, a1_l, aff_l = [], None, None, None
+        trk_loss = isinstance(lm, TrackerLossSpec)
         if lm is not None:
-            if spec.tracker:
-                raise _lib.HpsError("the fused loss is the mapper's; the tracker's needs a batch statistic (tracker_loss)")
             color_loss = spec.color_stage and lm.gt_color is not None
             gtc = _f32c(lm.gt_color).reshape(-1, 3) if color_loss else None
-            flat = torch.empty(16 + R * (4 if color_loss else 1), **f32)
-            if lm.exposure and color_loss:
+            flat = torch.empty(16 + R * (4 if color_loss else 1), **f32)   # tracker: [4] = the batch statistic
+            if not trk_loss and lm.exposure and color_loss:
                 eprm = [_f32c(t) for t in params[len(gprm) + len(cprm):]]
                 if len(eprm) != 5:
                     raise _lib.HpsError("exposure MLP: expected latent, W1, b1, W2, b2")
@@ -790,7 +801,19 @@ class _RenderRays(torch.autograd.Function):
             if lm is None:
                 _call("hps_composite_fwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
                       float(spec.coef), _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), None, int(spec.min_valid),
-                      _lib.ptr(valid), st())
+                      _lib.ptr(valid), None, None, 0, st())
+            elif trk_loss:
+                _call("hps_composite_fwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
+                      float(spec.coef), _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), None, int(spec.min_valid),
+                      _lib.ptr(valid), _lib.ptr(gd), _lib.ptr(flat[4:]), 1 if lm.zero_missing else 0, st())
+                count = float(R)
+                if lm.reduce_fn is not None:       # rays sharded over ranks: global sum and count
+                    flat[5:6].fill_(float(R))
+                    count = float(lm.reduce_fn(flat[4:6]))
+                # (rays without a depth reading are masked out of the loss by gt_depth > 0, whatever their depth)
+                _call("hps_tracker_loss", _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color) if color_loss else None,
+                      _lib.ptr(gd), _lib.ptr(gtc), _lib.ptr(flat[4:]), count, lm.w_color, R, _lib.ptr(flat),
+                      _lib.ptr(flat[16:]), _lib.ptr(flat[16 + R:]) if color_loss else None, st())
             else:
                 _call("hps_composite_mapper_loss", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
                       float(spec.coef), int(spec.min_valid), _lib.ptr(gd), _lib.ptr(gtc), _lib.ptr(aff_l), lm.w_color,
@@ -945,7 +968,8 @@ def render_rays(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, ge
     if isinstance(feats_col, LiveRows):
         feats_col = feats_col.param
     params = list(geo_params) + (list(col_params) if spec.color_stage else [])
-    if spec.loss is not None and spec.loss.exposure and spec.color_stage and spec.loss.gt_color is not None:
+    if isinstance(spec.loss, MapperLossSpec) and spec.loss.exposure and spec.color_stage \
+            and spec.loss.gt_color is not None:
         params += list(exposure_params)
     return _RenderRays.apply(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col if spec.color_stage else None,
                              affine if spec.color_stage else None, *params)

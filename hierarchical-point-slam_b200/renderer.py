@@ -169,8 +169,15 @@ class Renderer(object):
             cloud_pos=cloud_pos[level] if is_tracker else None, fill_geo=decoders._fill("geo", rays_o.device),
             fill_col=decoders._fill("col", rays_o.device) if color_stage else None, prep=prepared)
         loss = None
-        if _loss is not None:
-            gt_color, w_color, loss_exposure_feat = _loss
+        if _loss is not None and _loss[0] == "tracker":
+            _, gt_color, w_color, reduce_fn = _loss
+            spec.loss = ops.TrackerLossSpec(gt_color if color_stage else None, w_color, reduce_fn,
+                                            zero_missing=not self.sample_near_pcl and not self.assume_positive_depth)
+            loss, depth, uncertainty, color, valid = ops.render_rays(
+                spec, rays_o, rays_d, gt_depth, npc_geo_feats[level], npc_col_feats[level] if color_stage else None,
+                affine, geo.kernel_params(rays_o.device), col.kernel_params(rays_o.device) if color_stage else None)
+        elif _loss is not None:
+            _, gt_color, w_color, loss_exposure_feat = _loss
             mlp = col.mlp_exposure if (color_stage and loss_exposure_feat is not None) else None
             spec.loss = ops.MapperLossSpec(gt_color if color_stage else None, w_color, mlp is not None)
             eprm = None
@@ -211,7 +218,22 @@ class Renderer(object):
         return self.render_batch_ray(npc, decoders, rays_d, rays_o, device, stage, gt_depth=gt_depth,
                                      npc_geo_feats=npc_geo_feats, npc_col_feats=npc_col_feats, is_tracker=False,
                                      cloud_pos=cloud_pos, dynamic_r_query=dynamic_r_query, exposure_feat=None,
-                                     prepared=prepared, _loss=(gt_color, w_color_loss, exposure_feat))
+                                     prepared=prepared, _loss=("mapper", gt_color, w_color_loss, exposure_feat))
+
+    def render_batch_ray_tracker_loss(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth, gt_color,
+                                      w_color_loss, npc_geo_feats=None, npc_col_feats=None, cloud_pos=None,
+                                      dynamic_r_query=None, exposure_feat=None, use_color=True, reduce_fn=None):
+        """One tracker iteration's forward as ONE autograd node (the reference spells it out in Tracker.py:199-231):
+        render_batch_ray(..., is_tracker=True, exposure_feat=exposure_feat) followed by
+            tmp  = |gt_depth - depth| / sqrt(uncertainty + 1e-10)          (uncertainty detached)
+            mask = (tmp < 10 * tmp.mean()) & (gt_depth > 0) & finite
+            loss = clamp(tmp, 0, 1e3)[mask].sum() + w_color_loss * |gt_color - color|[mask].sum()   (use_color)
+        -> (loss, depth, uncertainty, color, valid_ray_mask); only `loss` carries gradient (pose through rays_o / rays_d,
+        exposure_feat, and whatever else requires it).  reduce_fn: see ops.tracker_loss (rays sharded over ranks)."""
+        return self.render_batch_ray(npc, decoders, rays_d, rays_o, device, stage, gt_depth=gt_depth,
+                                     npc_geo_feats=npc_geo_feats, npc_col_feats=npc_col_feats, is_tracker=True,
+                                     cloud_pos=cloud_pos, dynamic_r_query=dynamic_r_query, exposure_feat=exposure_feat,
+                                     _loss=("tracker", gt_color if use_color else None, w_color_loss, reduce_fn))
 
     def render_batch_ray_modular(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None,
                                  npc_geo_feats=None, npc_col_feats=None, is_tracker=False, cloud_pos=None,

@@ -157,6 +157,9 @@ int hps_composite_fwd(const float* rgb, int rgb_stride, const float* occ, int oc
                       const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
                       float* depth, float* var, float* color, float* weights,
                       int min_valid, uint8_t* valid_ray /* may be NULL: #samples with neighbours >= min_valid */,
+                      const float* gt_depth, float* tracker_sum /* may be NULL; else += sum_r |gt - depth| /
+                      sqrt(var + 1e-10), the first pass of the tracker loss (hps_tracker_loss_stats) */,
+                      int zero_missing /* depth counts as 0 where gt_depth <= 0 (Renderer.py:250-251) */,
                       void* stream);
 int hps_composite_bwd(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
                       const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,

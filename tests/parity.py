@@ -106,7 +106,7 @@ def check_mapper(stage, out, ref, dec, tol=TOL):
     return errs
 
 
-def tracker_step(hps, npc, dec, renderer, scene, ref_inputs, stage, device, modular=False):
+def tracker_step(hps, npc, dec, renderer, scene, ref_inputs, stage, device, modular=False, fused_loss=False):
     cl, cfg = scene["clouds"], scene["cfg"]
     K = O.SCANNET_INTRINSICS
     cam = ref_inputs["cam"].to(device).clone().requires_grad_(True)
@@ -119,13 +119,19 @@ def tracker_step(hps, npc, dec, renderer, scene, ref_inputs, stage, device, modu
     rq = {l: cl[l]["radius"].to(device).clone() for l in cl}
     ro.retain_grad()
     rd.retain_grad()
-    render = renderer.render_batch_ray_modular if modular else renderer.render_batch_ray
-    depth, var, color, _ = render(
-        npc, dec, rd, ro, device, stage, gt_depth=gt_d,
-        npc_geo_feats={l: npc.get_geo_feats(l) for l in cl}, npc_col_feats={l: npc.get_col_feats(l) for l in cl},
-        is_tracker=True, cloud_pos={l: npc.cloud_pos_tensor(l) for l in cl}, dynamic_r_query=rq, exposure_feat=ef)
-    loss_fn = hps.tracker_loss_torch if modular else hps.tracker_loss
-    loss = loss_fn(depth, var, color, gt_d, gt_c, cfg["w_color_tracker"])
+    if fused_loss:
+        loss, depth, var, color, _ = renderer.render_batch_ray_tracker_loss(
+            npc, dec, rd, ro, device, stage, gt_d, gt_c, cfg["w_color_tracker"],
+            npc_geo_feats={l: npc.get_geo_feats(l) for l in cl}, npc_col_feats={l: npc.get_col_feats(l) for l in cl},
+            cloud_pos={l: npc.cloud_pos_tensor(l) for l in cl}, dynamic_r_query=rq, exposure_feat=ef)
+    else:
+        render = renderer.render_batch_ray_modular if modular else renderer.render_batch_ray
+        depth, var, color, _ = render(
+            npc, dec, rd, ro, device, stage, gt_depth=gt_d,
+            npc_geo_feats={l: npc.get_geo_feats(l) for l in cl}, npc_col_feats={l: npc.get_col_feats(l) for l in cl},
+            is_tracker=True, cloud_pos={l: npc.cloud_pos_tensor(l) for l in cl}, dynamic_r_query=rq, exposure_feat=ef)
+        loss_fn = hps.tracker_loss_torch if modular else hps.tracker_loss
+        loss = loss_fn(depth, var, color, gt_d, gt_c, cfg["w_color_tracker"])
     loss.backward()
     level = "mid" if stage.endswith("mid") else "fine"
     mexp = getattr(dec, "color_decoder_" + level).mlp_exposure

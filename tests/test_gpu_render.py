@@ -86,12 +86,13 @@ def test_mapper_iteration_other_kernel_editions(built, switch):
         ops.USE_TC, ops.USE_TC_BWD, ops.MULTI_STREAM = saved
 
 
-@pytest.mark.parametrize("path", ["fused", "modular"])
+@pytest.mark.parametrize("path", ["fused", "modular", "fused_loss"])
 @pytest.mark.parametrize("stage", ["color_mid", "color_fine"])
 def test_tracker_iteration_matches_reference(built, stage, path):
     scene, hps, npc, dec, renderer = built
     ref = parity.load("render_tracker_small.pt")
-    out = parity.tracker_step(hps, npc, dec, renderer, scene, ref["inputs"], stage, DEV, modular=(path == "modular"))
+    out = parity.tracker_step(hps, npc, dec, renderer, scene, ref["inputs"], stage, DEV, modular=(path == "modular"),
+                              fused_loss=(path == "fused_loss"))
     errs = parity.check_tracker(stage, out, ref[stage], scene, ref["inputs"])
     print(stage, errs)
 
@@ -600,3 +601,42 @@ def test_sample_near_pcl_render_mode(built, golden, dynamic):
                 assert bool((dd <= zz[:, -1] + 1e-4).all())                       # sum of w*z with sum(w) <= 1
     finally:
         npc.radius_query = keep
+
+
+def test_render_batch_ray_tracker_loss_equals_render_plus_loss(built):
+    """renderer.render_batch_ray_tracker_loss (batch statistic accumulated by the compositing kernel, loss kernel,
+    upstream gradient as a device scalar) against render_batch_ray + tracker_loss, with some rays stripped of their
+    depth reading (they count with depth 0 in the statistic, Renderer.py:250-251) and an upstream gradient of 0.5."""
+    scene, hps, npc, dec, renderer = built
+    ref = parity.load("render_tracker_small.pt")
+    inp = dict(ref["inputs"])
+    inp["gt_depth"] = inp["gt_depth"].clone()
+    inp["gt_depth"][::7] = 0.0
+    K = O.SCANNET_INTRINSICS
+    cl = scene["clouds"]
+    outs = []
+    for fused in (False, True):
+        cam = inp["cam"].to(DEV).clone().requires_grad_(True)
+        ef = scene["exposure_feat"].to(DEV).clone().requires_grad_(True)
+        dec.zero_grad()
+        c2w = hps.get_camera_from_tensor(cam)
+        ro, rd = hps.get_rays_from_uv(inp["i"].to(DEV), inp["j"].to(DEV), c2w, K["H"], K["W"], K["fx"], K["fy"],
+                                      K["cx"], K["cy"], DEV)
+        gt_d, gt_c = inp["gt_depth"].to(DEV), inp["gt_color"].to(DEV)
+        kw = dict(npc_geo_feats={l: npc.get_geo_feats(l) for l in cl}, npc_col_feats={l: npc.get_col_feats(l) for l in cl},
+                  cloud_pos={l: npc.cloud_pos_tensor(l) for l in cl},
+                  dynamic_r_query={l: cl[l]["radius"].to(DEV).clone() for l in cl}, exposure_feat=ef)
+        if fused:
+            loss, d, v, c, m = renderer.render_batch_ray_tracker_loss(npc, dec, rd, ro, DEV, "color_fine", gt_d, gt_c,
+                                                                      0.5, **kw)
+        else:
+            d, v, c, m = renderer.render_batch_ray(npc, dec, rd, ro, DEV, "color_fine", gt_depth=gt_d, is_tracker=True,
+                                                   **kw)
+            loss = hps.tracker_loss(d, v, c, gt_d, gt_c, 0.5)
+        (0.5 * loss).backward()
+        outs.append(dict(loss=loss.detach(), d=d.detach(), v=v, c=c.detach(), m=m, g_cam=cam.grad, g_ef=ef.grad))
+    a, b = outs
+    assert torch.equal(a["d"], b["d"]) and torch.equal(a["v"], b["v"]) and torch.equal(a["c"], b["c"])
+    assert torch.equal(a["m"], b["m"])
+    assert parity.rel(b["loss"], a["loss"]) <= 1e-6
+    assert parity.rel(b["g_cam"], a["g_cam"]) <= 1e-4 and parity.rel(b["g_ef"], a["g_ef"]) <= 1e-4
