@@ -43,8 +43,8 @@ SIGNATURES = {
                                  _vp, _vp, _i32, _vp]),
     "hps_composite_bwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp,
                                  _i32, _vp, _vp, _vp]),
-    "hps_composite_mapper_loss": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _f32]
-                                  + [_vp] * 9),
+    "hps_composite_mapper_loss": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp,
+                                         _f32] + [_vp] * 9),
     "hps_camera_from_tensor": (_i32, [_vp, _vp, _vp]),
     "hps_camera_from_tensor_bwd": (_i32, [_vp, _vp, _vp, _vp]),
     "hps_rays_from_uv": (_i32, [_vp, _vp, _vp, _i32, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),
@@ -56,7 +56,7 @@ SIGNATURES = {
                                _vp]),
     "hps_sample_rays_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "hps_adam_multi": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _vp, _i32, _vp]),
-    "hps_mapper_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "hps_mapper_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "hps_tracker_loss_stats": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "hps_tracker_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _f32, _i64, _vp, _vp, _vp, _vp]),
 }

@@ -205,8 +205,8 @@ __global__ void __launch_bounds__(256)
 composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, const float* __restrict__ occ,
                              int occ_stride, const uint8_t* __restrict__ point_mask, const float* __restrict__ z,
                              int64_t R, int S, float coef, int min_valid, const float* __restrict__ gt_depth,
-                             const float* __restrict__ gt_color, const float* __restrict__ affine, float w_color,
-                             float* __restrict__ depth_out, float* __restrict__ var_out,
+                             const float* __restrict__ gt_color, const float* __restrict__ affine,
+                             const int32_t* __restrict__ frame, float w_color, float* __restrict__ depth_out, float* __restrict__ var_out,
                              float* __restrict__ color_out, uint8_t* __restrict__ valid_ray,
                              float* __restrict__ loss, float* __restrict__ g_depth, float* __restrict__ g_color,
                              float* __restrict__ d_affine) {
@@ -219,13 +219,19 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
     float acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+    const bool use_aff = gt_color != nullptr && affine != nullptr;
+    // rays of several keyframes in one batch (Mapper.py:805-822): frame[ray] selects the ray's exposure affine
+    int f = 0, f_block = 0;
+    if (frame != nullptr && use_aff) {
+        f_block = __ldg(frame + min(((int64_t)blockIdx.x * blockDim.x >> 5) * RPW, R - 1));
+        f = f_block;
+    }
     if (warp * RPW < R) {                                  // warp-uniform: the shuffles below stay converged
         const int64_t ray = ray_raw < R ? ray_raw : R - 1;
         const bool live = ray_raw < R;
         const bool active = s < S;
         // the loss operands of the ray's leading lane are requested before the compositing loads, not after the sums
         const bool lead = live && s == 0;
-        const bool use_aff = gt_color != nullptr && affine != nullptr;
         float gd = 0.f, gtc[3] = {0.f, 0.f, 0.f}, af[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) af[k] = 0.f;
@@ -237,8 +243,9 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
                 gtc[2] = __ldg(gt_color + ray * 3 + 2);
             }
             if (use_aff) {
+                if (frame != nullptr) f = __ldg(frame + ray);
 #pragma unroll
-                for (int k = 0; k < 12; ++k) af[k] = __ldg(affine + k);
+                for (int k = 0; k < 12; ++k) af[k] = __ldg(affine + 12 * (int64_t)f + k);
             }
         }
         RaySample me;
@@ -296,7 +303,14 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
             }
         }
     }
-    const int n_acc = (gt_color != nullptr && affine != nullptr && d_affine != nullptr) ? NACC : 1;
+    int n_acc = (use_aff && d_affine != nullptr) ? NACC : 1;
+    if (n_acc == NACC && !__syncthreads_and(f == f_block)) {
+        // the block straddles a frame boundary: per-ray atomics for the affine gradient, block sum for the loss only
+#pragma unroll
+        for (int k = 1; k < NACC; ++k)
+            if (acc[k] != 0.f) red_add(d_affine + 12 * (int64_t)f + (k - 1), acc[k]);
+        n_acc = 1;
+    }
     for (int k = 0; k < n_acc; ++k) {
         float v = acc[k];
         for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
@@ -306,7 +320,7 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
     if (threadIdx.x < n_acc) {
         float t = 0.f;
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
-        red_add(threadIdx.x == 0 ? loss : d_affine + (threadIdx.x - 1), t);
+        red_add(threadIdx.x == 0 ? loss : d_affine + 12 * (int64_t)f_block + (threadIdx.x - 1), t);
     }
 }
 
@@ -315,7 +329,8 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
 extern "C" int hps_composite_mapper_loss(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
                                          const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
                                          int min_valid, const float* gt_depth, const float* gt_color,
-                                         const float* affine, float w_color, float* depth, float* var, float* color,
+                                         const float* affine, const int32_t* frame, float w_color, float* depth,
+                                         float* var, float* color,
                                          uint8_t* valid_ray, float* loss, float* g_depth, float* g_color,
                                          float* d_affine, void* stream) {
     using namespace hps;
@@ -328,12 +343,12 @@ extern "C" int hps_composite_mapper_loss(const float* rgb, int rgb_stride, const
     if (S <= 8) {
         const int64_t warps = ceil_div(R, 4);
         composite_mapper_loss_kernel<8><<<(unsigned)ceil_div(warps * 32, tb), tb, 0, (cudaStream_t)stream>>>(
-            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, min_valid, gt_depth, gt_color, affine, w_color,
-            depth, var, color, valid_ray, loss, g_depth, g_color, d_affine);
+            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, min_valid, gt_depth, gt_color, affine, frame,
+            w_color, depth, var, color, valid_ray, loss, g_depth, g_color, d_affine);
     } else {
         composite_mapper_loss_kernel<32><<<(unsigned)ceil_div(R * 32, tb), tb, 0, (cudaStream_t)stream>>>(
-            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, min_valid, gt_depth, gt_color, affine, w_color,
-            depth, var, color, valid_ray, loss, g_depth, g_color, d_affine);
+            rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, min_valid, gt_depth, gt_color, affine, frame,
+            w_color, depth, var, color, valid_ray, loss, g_depth, g_color, d_affine);
     }
     HPS_LAUNCH_OK();
     return 0;

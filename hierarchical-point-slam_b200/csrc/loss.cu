@@ -28,7 +28,8 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
 __global__ void __launch_bounds__(256)
 mapper_loss_kernel(const float* __restrict__ depth, const float* __restrict__ color,
                    const uint8_t* __restrict__ valid, const float* __restrict__ gt_depth,
-                   const float* __restrict__ gt_color, const float* __restrict__ affine, float w_color, int64_t R,
+                   const float* __restrict__ gt_color, const float* __restrict__ affine,
+                   const int32_t* __restrict__ frame, float w_color, int64_t R,
                    float* __restrict__ loss, float* __restrict__ g_depth, float* __restrict__ g_color,
                    float* __restrict__ d_affine) {
     __shared__ float scratch[32];
@@ -37,6 +38,13 @@ mapper_loss_kernel(const float* __restrict__ depth, const float* __restrict__ co
     float da[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) da[k] = 0.f;
+    // rays of several keyframes in one batch (Mapper.py:805-822): frame[r] selects the ray's exposure affine
+    int f = 0, f_block = 0;
+    if (frame != nullptr && affine != nullptr) {
+        f_block = __ldg(frame + min((int64_t)blockIdx.x * blockDim.x, R - 1));
+        f = r < R ? __ldg(frame + r) : f_block;
+        affine += 12 * (int64_t)f;
+    }
     if (r < R) {
         const float d = depth[r], gd = gt_depth[r];
         const bool m = (gd > 0.f) && (valid[r] != 0) && !isnan(d);
@@ -83,10 +91,17 @@ mapper_loss_kernel(const float* __restrict__ depth, const float* __restrict__ co
     const float bl = block_sum(l, scratch);
     if (threadIdx.x == 0) red_add(loss, bl);
     if (color != nullptr && affine != nullptr && d_affine != nullptr) {
+        // one frame per block (the usual case: frames are contiguous runs of rays): block sums; else per-ray atomics
+        if (__syncthreads_and(f == f_block)) {
 #pragma unroll
-        for (int k = 0; k < 12; ++k) {
-            const float s = block_sum(da[k], scratch);
-            if (threadIdx.x == 0) red_add(d_affine + k, s);
+            for (int k = 0; k < 12; ++k) {
+                const float s = block_sum(da[k], scratch);
+                if (threadIdx.x == 0) red_add(d_affine + 12 * (int64_t)f_block + k, s);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 12; ++k)
+                if (da[k] != 0.f) red_add(d_affine + 12 * (int64_t)f + k, da[k]);
         }
     }
 }
@@ -143,15 +158,15 @@ tracker_loss_kernel(const float* __restrict__ depth, const float* __restrict__ v
 }  // namespace hps
 
 extern "C" int hps_mapper_loss(const float* depth, const float* color, const uint8_t* valid, const float* gt_depth,
-                               const float* gt_color, const float* affine, float w_color, int64_t R, float* loss,
-                               float* g_depth, float* g_color, float* d_affine, void* stream) {
+                               const float* gt_color, const float* affine, const int32_t* frame, float w_color,
+                               int64_t R, float* loss, float* g_depth, float* g_color, float* d_affine, void* stream) {
     using namespace hps;
     HPS_REQUIRE(R >= 0, "negative ray count");
     if (R == 0) return 0;
     HPS_REQUIRE(depth && valid && gt_depth && loss && g_depth, "null buffer");
     HPS_REQUIRE(color == nullptr || (gt_color && g_color), "colour term needs gt_color and g_color");
     mapper_loss_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, (cudaStream_t)stream>>>(
-        depth, color, valid, gt_depth, gt_color, affine, w_color, R, loss, g_depth, g_color, d_affine);
+        depth, color, valid, gt_depth, gt_color, affine, frame, w_color, R, loss, g_depth, g_color, d_affine);
     HPS_LAUNCH_OK();
     return 0;
 }

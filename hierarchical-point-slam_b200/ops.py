@@ -624,12 +624,16 @@ class RenderSpec:
 
 class MapperLossSpec:
     """Fuses the mapper's loss (Mapper.py:791-856) into render_rays: `gt_color` (R,3) or None (geometry stages),
-    `w_color`, and `exposure` = True when the five tensors of the exposure MLP (latent, W1, b1, W2, b2) follow the
-    decoder parameters - the colour term then is |gt - sigmoid(colour x affine)| with affine = MLP(latent)."""
-    __slots__ = ("gt_color", "w_color", "exposure")
+    `w_color`, and what follows the decoder parameters in the argument list: `exposure` = "mlp": the five tensors of
+    the exposure MLP (latent, W1, b1, W2, b2) - the colour term then is |gt - sigmoid(colour x affine)| with affine =
+    MLP(latent), evaluated inside the call; "affine": the affine itself, (12,) or (F,12) with `frame_index` (R,) for a
+    batch that mixes rays of F keyframes (Mapper.py:805-822); None: the colour as rendered."""
+    __slots__ = ("gt_color", "w_color", "exposure", "frame_index")
 
-    def __init__(self, gt_color, w_color, exposure):
-        self.gt_color, self.w_color, self.exposure = gt_color, float(w_color), bool(exposure)
+    def __init__(self, gt_color, w_color, exposure=None, frame_index=None):
+        if exposure not in (None, "mlp", "affine"):
+            raise ValueError("exposure: None, 'mlp' or 'affine'")
+        self.gt_color, self.w_color, self.exposure, self.frame_index = gt_color, float(w_color), exposure, frame_index
 
 
 class TrackerLossSpec:
@@ -682,13 +686,19 @@ class _RenderRays(torch.autograd.Function):
         cprm = [_f32c(t) for t in params[N_PARAM:2 * N_PARAM]] if spec.color_stage else []
         # loss mode: [loss, pad x3 | d_affine (12) | g_depth (R) | g_color (3R)] in one buffer, head zeroed (accumulators)
         lm = spec.loss
-        eprm, flat, a1_l, aff_l = [], None, None, None
+        eprm, flat, a1_l, aff_l, frm_l, head, n_aff, aff_in_shape = [], None, None, None, None, 16, 12, None
         trk_loss = isinstance(lm, TrackerLossSpec)
         if lm is not None:
             color_loss = spec.color_stage and lm.gt_color is not None
             gtc = _f32c(lm.gt_color).reshape(-1, 3) if color_loss else None
-            flat = torch.empty(16 + R * (4 if color_loss else 1), **f32)   # tracker: [4] = the batch statistic
-            if not trk_loss and lm.exposure and color_loss:
+            if not trk_loss and lm.exposure == "affine" and color_loss:
+                aff_in = params[len(gprm) + len(cprm)]
+                aff_in_shape = aff_in.shape
+                aff_l = _f32c(aff_in)
+                frm_l, n_aff = _loss_frames(aff_l, lm.frame_index, R)
+                head = _loss_head_floats(n_aff)
+            flat = torch.empty(head + R * (4 if color_loss else 1), **f32)   # tracker: [4] = the batch statistic
+            if not trk_loss and lm.exposure == "mlp" and color_loss:
                 eprm = [_f32c(t) for t in params[len(gprm) + len(cprm):]]
                 if len(eprm) != 5:
                     raise _lib.HpsError("exposure MLP: expected latent, W1, b1, W2, b2")
@@ -702,7 +712,7 @@ class _RenderRays(torch.autograd.Function):
         def loss_head(s):
             """zero the accumulators and evaluate the exposure MLP (independent of the rays): off the critical path"""
             with torch.cuda.stream(s):
-                flat[:16].zero_()
+                flat[:head].zero_()
             if eprm:
                 _call("hps_exposure_fwd", _lib.ptr(eprm[0]), _lib.ptr(eprm[1]), _lib.ptr(eprm[2]), _lib.ptr(eprm[3]),
                       _lib.ptr(eprm[4]), e_in, e_hidden, 12, _lib.ptr(a1_l), _lib.ptr(aff_l), _stream(s))
@@ -816,11 +826,11 @@ class _RenderRays(torch.autograd.Function):
                       _lib.ptr(flat[16:]), _lib.ptr(flat[16 + R:]) if color_loss else None, st())
             else:
                 _call("hps_composite_mapper_loss", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
-                      float(spec.coef), int(spec.min_valid), _lib.ptr(gd), _lib.ptr(gtc), _lib.ptr(aff_l), lm.w_color,
-                      _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), _lib.ptr(valid), _lib.ptr(flat),
-                      _lib.ptr(flat[16:]), _lib.ptr(flat[16 + R:]) if color_loss else None,
+                      float(spec.coef), int(spec.min_valid), _lib.ptr(gd), _lib.ptr(gtc), _lib.ptr(aff_l),
+                      _lib.ptr(frm_l), lm.w_color, _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), _lib.ptr(valid),
+                      _lib.ptr(flat), _lib.ptr(flat[head:]), _lib.ptr(flat[head + R:]) if color_loss else None,
                       _lib.ptr(flat[4:]) if aff_l is not None else None, st())
-        ctx.loss_state = None if lm is None else (flat, a1_l, eprm, color_loss)
+        ctx.loss_state = None if lm is None else (flat, a1_l, eprm, color_loss, head, n_aff, aff_in_shape)
         ctx.spec = spec
         ctx.n_g = len(gprm)
         ctx.row_map = row_map
@@ -838,11 +848,11 @@ class _RenderRays(torch.autograd.Function):
         spec = ctx.spec
         gscale = None
         if ctx.loss_state is not None:          # gradients of the fused loss, scaled by the upstream gradient in-kernel
-            l_flat, l_a1, l_eprm, l_color = ctx.loss_state
+            l_flat, l_a1, l_eprm, l_color, l_head, l_naff, l_aff_shape = ctx.loss_state
             l_R = ctx.saved_tensors[0].shape[0]
             gscale = _f32c(gouts[0]).reshape(1)
-            g_depth = l_flat[16:16 + l_R]
-            g_color = l_flat[16 + l_R:].view(l_R, 3) if l_color else None
+            g_depth = l_flat[l_head:l_head + l_R]
+            g_color = l_flat[l_head + l_R:].view(l_R, 3) if l_color else None
         else:
             g_depth, _g_var, g_color, _g_valid = gouts
         (z, pts, I, w, has, c_geo, c_col, occ, rgb, act_g, act_c, fg, fc, aff, pos) = ctx.saved_tensors[:15]
@@ -926,6 +936,9 @@ class _RenderRays(torch.autograd.Function):
                 _call("hps_sample_rays_bwd", _lib.ptr(dp_g), _lib.ptr(dp_i), _lib.ptr(dp_c), _lib.ptr(z), R, S,
                       _lib.ptr(g_ro), _lib.ptr(g_rd), st())
             g_exp = ()
+            if ctx.loss_state is not None and l_aff_shape is not None:
+                # the loss-side affine was an input: its gradient, scaled by the upstream gradient (main stream has slack)
+                g_exp = ((l_flat[4:4 + l_naff] * gscale).view(l_aff_shape) if need[7 + len(gprm) + len(cprm)] else None,)
             if ctx.loss_state is not None and l_eprm:
                 # exposure MLP backward from d loss / d affine (accumulated by the fused loss kernel); the main stream
                 # has slack here - the weight-gradient kernels on their own streams finish later
@@ -970,7 +983,7 @@ def render_rays(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, ge
     params = list(geo_params) + (list(col_params) if spec.color_stage else [])
     if isinstance(spec.loss, MapperLossSpec) and spec.loss.exposure and spec.color_stage \
             and spec.loss.gt_color is not None:
-        params += list(exposure_params)
+        params += list(exposure_params)      # "mlp": (latent, W1, b1, W2, b2); "affine": (affine,)
     return _RenderRays.apply(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col if spec.color_stage else None,
                              affine if spec.color_stage else None, *params)
 
@@ -1191,7 +1204,7 @@ def exposure_mlp(x, W1, b1, W2, b2):
 # --------------------------------------------------------------------------------------------------
 class _MapperLoss(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, depth, color, valid, gt_depth, gt_color, affine, w_color, color_stage):
+    def forward(ctx, depth, color, valid, gt_depth, gt_color, affine, w_color, color_stage, frame):
         _need_cuda(depth, valid, gt_depth)
         dev, R = depth.device, depth.shape[0]
         f32 = dict(dtype=torch.float32, device=dev)
@@ -1199,36 +1212,65 @@ class _MapperLoss(torch.autograd.Function):
         col = _f32c(color) if color_stage else None
         gcl = _f32c(gt_color) if color_stage else None
         aff = _f32c(affine) if (affine is not None and color_stage) else None
+        frm, n_aff = _loss_frames(aff, frame, R)
         v = valid.detach().contiguous()
         v = v.view(torch.uint8) if v.dtype == torch.bool else v.to(torch.uint8)
-        # one buffer: [loss, pad x3 | d_affine (12) | g_depth (R) | g_color (3R)]; the head is zeroed (accumulators)
-        flat = torch.empty(16 + R * (4 if color_stage else 1), **f32)
-        flat[:16].zero_()
+        # one buffer: [loss, pad x3 | d_affine (12 per frame) | g_depth (R) | g_color (3R)]; the head is zeroed
+        # (accumulators)
+        head = _loss_head_floats(n_aff)
+        flat = torch.empty(head + R * (4 if color_stage else 1), **f32)
+        flat[:head].zero_()
         loss = flat[0]
-        d_aff = flat[4:16] if aff is not None else None
-        g_depth = flat[16:16 + R]
-        g_color = flat[16 + R:].view(R, 3) if color_stage else None
+        d_aff = flat[4:4 + n_aff] if aff is not None else None
+        g_depth = flat[head:head + R]
+        g_color = flat[head + R:].view(R, 3) if color_stage else None
         with torch.cuda.device(dev):
             _call("hps_mapper_loss", _lib.ptr(d), _lib.ptr(col), _lib.ptr(v), _lib.ptr(gdp), _lib.ptr(gcl), _lib.ptr(aff),
-                  float(w_color), R, _lib.ptr(loss), _lib.ptr(g_depth), _lib.ptr(g_color), _lib.ptr(d_aff), _stream())
+                  _lib.ptr(frm), float(w_color), R, _lib.ptr(loss), _lib.ptr(g_depth), _lib.ptr(g_color), _lib.ptr(d_aff),
+                  _stream())
         ctx.save_for_backward(flat)
-        ctx.dims = (R, color_stage, aff is not None)
+        ctx.dims = (R, color_stage, affine.shape if aff is not None else None, head, n_aff)
         return loss
 
     @staticmethod
     def backward(ctx, gout):
         (flat,) = ctx.saved_tensors
-        R, color_stage, has_aff = ctx.dims
+        R, color_stage, aff_shape, head, n_aff = ctx.dims
         g = flat[4:] * gout                      # one kernel scales d_affine, g_depth and g_color
-        return (g[12:12 + R], g[12 + R:].view(R, 3) if color_stage else None, None, None, None,
-                g[:12] if has_aff else None, None, None)
+        return (g[head - 4:head - 4 + R], g[head - 4 + R:].view(R, 3) if color_stage else None, None, None, None,
+                g[:n_aff].view(aff_shape) if aff_shape is not None else None, None, None, None)
 
 
-def mapper_loss(depth, color, valid_ray_mask, gt_depth, gt_color, stage, w_color_loss=0.1, affine=None):
-    """Mapper.py:791-856 in one kernel (loss + gradients)."""
+def _loss_head_floats(n_aff):
+    """[loss, pad x3 | d_affine (n_aff)] rounded up to 16 floats."""
+    return max(16, (4 + n_aff + 15) // 16 * 16)
+
+
+def _loss_frames(aff, frame, R):
+    """Checks the (affine, frame index) pair of a multi-keyframe batch -> (int32 frame tensor or None, #affine floats)."""
+    if aff is None:
+        return None, 0
+    if aff.numel() % 12 != 0:
+        raise ValueError("exposure affine: 12 values per frame")
+    n_frames = aff.numel() // 12
+    if frame is None:
+        if n_frames != 1:
+            raise ValueError("%d exposure affines but no frame index per ray" % n_frames)
+        return None, 12
+    frm = frame.detach().reshape(-1).to(device=aff.device, dtype=torch.int32).contiguous()
+    if frm.numel() != R:
+        raise ValueError("frame index: one entry per ray")
+    return frm, 12 * n_frames
+
+
+def mapper_loss(depth, color, valid_ray_mask, gt_depth, gt_color, stage, w_color_loss=0.1, affine=None,
+                frame_index=None):
+    """Mapper.py:791-856 in one kernel (loss + gradients).  affine: (12,) = one frame's exposure correction, or (F,12)
+    with frame_index (R,) in [0,F) for a batch that mixes rays of F keyframes (Mapper.py:805-822; the kernel does not
+    range-check the indices)."""
     cs = stage.startswith("color")
     return _MapperLoss.apply(depth, color if cs else None, valid_ray_mask, gt_depth, gt_color if cs else None,
-                             affine if cs else None, w_color_loss, cs)
+                             affine if cs else None, w_color_loss, cs, frame_index if cs else None)
 
 
 class _TrackerLoss(torch.autograd.Function):

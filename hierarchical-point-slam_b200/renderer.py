@@ -177,12 +177,17 @@ class Renderer(object):
                 spec, rays_o, rays_d, gt_depth, npc_geo_feats[level], npc_col_feats[level] if color_stage else None,
                 affine, geo.kernel_params(rays_o.device), col.kernel_params(rays_o.device) if color_stage else None)
         elif _loss is not None:
-            _, gt_color, w_color, loss_exposure_feat = _loss
+            _, gt_color, w_color, loss_exposure_feat, loss_affine, frame_index = _loss
+            if loss_exposure_feat is not None and loss_affine is not None:
+                raise ValueError("pass exposure_feat (one frame, MLP evaluated inside) or affine, not both")
             mlp = col.mlp_exposure if (color_stage and loss_exposure_feat is not None) else None
-            spec.loss = ops.MapperLossSpec(gt_color if color_stage else None, w_color, mlp is not None)
-            eprm = None
+            eprm, mode = None, None
             if mlp is not None:
+                mode = "mlp"
                 eprm = (loss_exposure_feat, mlp.linear1.weight, mlp.linear1.bias, mlp.linear2.weight, mlp.linear2.bias)
+            elif color_stage and loss_affine is not None:
+                mode, eprm = "affine", (loss_affine,)
+            spec.loss = ops.MapperLossSpec(gt_color if color_stage else None, w_color, mode, frame_index)
             loss, depth, uncertainty, color, valid = ops.render_rays(
                 spec, rays_o, rays_d, gt_depth, npc_geo_feats[level], npc_col_feats[level] if color_stage else None,
                 affine, geo.kernel_params(rays_o.device), col.kernel_params(rays_o.device) if color_stage else None,
@@ -204,13 +209,15 @@ class Renderer(object):
 
     def render_batch_ray_loss(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth, gt_color, w_color_loss,
                               npc_geo_feats=None, npc_col_feats=None, cloud_pos=None, dynamic_r_query=None,
-                              exposure_feat=None, prepared=None):
+                              exposure_feat=None, prepared=None, affine=None, frame_index=None):
         """One mapper iteration's forward as ONE autograd node (not in the reference, which spells it out in
         Mapper.py:783-856): render_batch_ray(..., exposure_feat=None) followed by
             mask = (gt_depth > 0) & valid & ~isnan(depth)
             loss = |gt_depth - depth|[mask].sum()
                    + w_color_loss * |gt_color - sigmoid(color @ A + t)|[mask].sum()        (colour stages)
         with [A | t] = color_decoder_<level>.mlp_exposure(exposure_feat) (no exposure_feat: the colour as rendered).
+        A batch that mixes rays of F keyframes (Mapper.py:805-822) passes the affines instead: affine (F,12) =
+        stack of mlp_exposure(exposure_feat_f), frame_index (R,) = the keyframe slot of every ray.
         -> (loss, depth, uncertainty, color, valid_ray_mask); only `loss` carries gradient (to the feature tables, the
         decoders, the exposure MLP and exposure_feat).  The compositing and loss kernels are one, the exposure MLP
         runs beside the neighbour search, and loss.backward() feeds the upstream gradient to the kernels as a device
@@ -218,7 +225,8 @@ class Renderer(object):
         return self.render_batch_ray(npc, decoders, rays_d, rays_o, device, stage, gt_depth=gt_depth,
                                      npc_geo_feats=npc_geo_feats, npc_col_feats=npc_col_feats, is_tracker=False,
                                      cloud_pos=cloud_pos, dynamic_r_query=dynamic_r_query, exposure_feat=None,
-                                     prepared=prepared, _loss=("mapper", gt_color, w_color_loss, exposure_feat))
+                                     prepared=prepared,
+                                     _loss=("mapper", gt_color, w_color_loss, exposure_feat, affine, frame_index))
 
     def render_batch_ray_tracker_loss(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth, gt_color,
                                       w_color_loss, npc_geo_feats=None, npc_col_feats=None, cloud_pos=None,

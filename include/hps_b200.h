@@ -177,7 +177,8 @@ int hps_composite_bwd(const float* rgb, int rgb_stride, const float* occ, int oc
 int hps_composite_mapper_loss(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
                               const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
                               int min_valid, const float* gt_depth, const float* gt_color /* may be NULL */,
-                              const float* affine /* may be NULL */, float w_color, float* depth, float* var,
+                              const float* affine /* may be NULL */, const int32_t* frame /* may be NULL */,
+                              float w_color, float* depth, float* var,
                               float* color, uint8_t* valid_ray, float* loss, float* g_depth, float* g_color,
                               float* d_affine, void* stream);
 
@@ -242,14 +243,16 @@ int hps_rays_from_uv_bwd(const float* pi, const float* pj, const float* g_rays_o
 /* ------------------------------------------------------------------------------------------------
  * Losses fused with their gradients (Mapper.py:791-856; Tracker.py:213-231).  `loss` (1 float) and
  * `d_affine` (12 floats) are ACCUMULATED into; g_depth (R) / g_color (R,3) are written.
- *   mapper: color may be NULL (geometry stages); affine may be NULL (no exposure correction).
+ *   mapper: color may be NULL (geometry stages); affine may be NULL (no exposure correction); frame (R int32, may be
+ *   NULL = one frame): rays of several keyframes in one batch (Mapper.py:805-822) - ray r uses affine[12*frame[r]..]
+ *   and accumulates into d_affine[12*frame[r]..] (F x 12 floats each).
  *   tracker: two passes - hps_tracker_loss_stats accumulates sum_r |gt-d|/sqrt(var+1e-10) into sum_tmp
  *   (all-reduce it across ranks when rays are sharded), hps_tracker_loss applies the 10*mean outlier mask
  *   with mean = sum_tmp / count.
  * ---------------------------------------------------------------------------------------------- */
 int hps_mapper_loss(const float* depth, const float* color, const uint8_t* valid, const float* gt_depth,
-                    const float* gt_color, const float* affine, float w_color, int64_t R, float* loss,
-                    float* g_depth, float* g_color, float* d_affine, void* stream);
+                    const float* gt_color, const float* affine, const int32_t* frame, float w_color, int64_t R,
+                    float* loss, float* g_depth, float* g_color, float* d_affine, void* stream);
 int hps_tracker_loss_stats(const float* depth, const float* var, const float* gt_depth, int64_t R,
                            float* sum_tmp, void* stream);
 int hps_tracker_loss(const float* depth, const float* var, const float* color, const float* gt_depth,

@@ -506,3 +506,42 @@ def test_sample_rays_bwd_sums_its_three_terms(hps):
         dp = sum(dps[:n]).view(R, S, 3)
         assert torch.allclose(go, dp.sum(1), rtol=1e-5, atol=1e-5)
         assert torch.allclose(gd, (dp * z[..., None]).sum(1), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("layout", ["segments", "interleaved"])
+def test_mapper_loss_with_several_keyframes(hps, layout):
+    """A mapper batch mixes rays of several keyframes, each with its own exposure affine (Mapper.py:805-822): the loss
+    kernel against the reference's expressions written out in torch (slice-wise colour @ rot + trans, sigmoid, masked
+    L1 sums) under autograd.  'segments' = contiguous runs per frame (block sums), 'interleaved' = frames change from
+    ray to ray (per-ray atomics)."""
+    torch.manual_seed(8)
+    R, F, w = 1500, 4, 0.1
+    depth = (1 + torch.rand(R, device=DEV)).requires_grad_(True)
+    color = torch.rand(R, 3, device=DEV).requires_grad_(True)
+    gt_d = 1 + torch.rand(R, device=DEV)
+    gt_d[::9] = 0
+    gt_c = torch.rand(R, 3, device=DEV)
+    valid = torch.rand(R, device=DEV) > 0.1
+    affine = (torch.eye(3, device=DEV).reshape(1, 9).repeat(F, 1) + 0.2 * torch.randn(F, 9, device=DEV))
+    affine = torch.cat([affine, 0.1 * torch.randn(F, 3, device=DEV)], 1).requires_grad_(True)
+    if layout == "segments":
+        bounds = [0, 300, 777, 778, R]
+        frame = torch.cat([torch.full((bounds[i + 1] - bounds[i],), i, device=DEV) for i in range(F)])
+    else:
+        frame = torch.arange(R, device=DEV) % F
+    loss = hps.mapper_loss(depth, color, valid, gt_d, gt_c, "color_fine", w, affine, frame_index=frame)
+    (loss * 3.0).backward()
+    got = [loss.detach(), depth.grad.clone(), color.grad.clone(), affine.grad.clone()]
+    for t in (depth, color, affine):
+        t.grad = None
+    mask = (gt_d > 0) & valid & ~torch.isnan(depth)
+    rot, trans = affine[:, :9].reshape(F, 3, 3), affine[:, 9:]
+    c2 = torch.sigmoid(torch.einsum("rk,rkc->rc", color, rot[frame]) + trans[frame])
+    ref = (gt_d[mask] - depth[mask]).abs().sum() + w * (gt_c[mask] - c2[mask]).abs().sum()
+    (ref * 3.0).backward()
+    want = [ref.detach(), depth.grad, color.grad, affine.grad]
+    for name, a, b in zip(("loss", "g_depth", "g_color", "d_affine"), got, want):
+        err = float((a - b).abs().max() / (b.abs().max() + 1e-30))
+        assert err < 1e-5, (name, err)
+    with pytest.raises(ValueError):
+        hps.mapper_loss(depth, color, valid, gt_d, gt_c, "color_fine", w, affine)          # (F,12) needs frame_index

@@ -640,3 +640,43 @@ def test_render_batch_ray_tracker_loss_equals_render_plus_loss(built):
     assert torch.equal(a["m"], b["m"])
     assert parity.rel(b["loss"], a["loss"]) <= 1e-6
     assert parity.rel(b["g_cam"], a["g_cam"]) <= 1e-4 and parity.rel(b["g_ef"], a["g_ef"]) <= 1e-4
+
+
+def test_render_batch_ray_loss_with_several_keyframes(built):
+    """render_batch_ray_loss(affine=(F,12), frame_index=...) - a batch mixing rays of F keyframes, Mapper.py:805-822 -
+    against render_batch_ray + mapper_loss with the same arguments; the affines come from the exposure MLP, so its
+    parameters and the F latents receive their gradients through autograd."""
+    scene, hps, npc, dec, renderer = built
+    dev, stage, level, F = DEV, "color_fine", "fine", 3
+    cl, rays = scene["clouds"], scene["rays"]
+    R = rays["rays_o"].shape[0]
+    frame = (torch.arange(R, device=dev) * F) // R
+    gt_d, gt_c = rays["gt_depth"].to(dev), rays["gt_color"].to(dev)
+    mlp = dec.color_decoder_fine.mlp_exposure
+    outs = []
+    for fused in (False, True):
+        dec.zero_grad()
+        gf = {l: cl[l]["geo_feats"].to(dev).clone().requires_grad_(True) for l in cl}
+        cf = {l: cl[l]["col_feats"].to(dev).clone().requires_grad_(True) for l in cl}
+        efs = [(scene["exposure_feat"].to(dev) * (1 + 0.3 * k)).clone().requires_grad_(True) for k in range(F)]
+        affine = torch.stack([mlp(e) for e in efs])
+        kw = dict(npc_geo_feats=gf, npc_col_feats=cf, cloud_pos={l: npc.cloud_pos_tensor(l) for l in cl},
+                  dynamic_r_query={l: cl[l]["radius"].to(dev).clone() for l in cl})
+        if fused:
+            loss = renderer.render_batch_ray_loss(npc, dec, rays["rays_d"].to(dev), rays["rays_o"].to(dev), dev, stage,
+                                                  gt_d, gt_c, 0.1, affine=affine, frame_index=frame, **kw)[0]
+        else:
+            d, v, c, m = renderer.render_batch_ray(npc, dec, rays["rays_d"].to(dev), rays["rays_o"].to(dev), dev, stage,
+                                                   gt_depth=gt_d, is_tracker=False, exposure_feat=None, **kw)
+            loss = hps.mapper_loss(d, c, m, gt_d, gt_c, stage, 0.1, affine, frame_index=frame)
+        loss.backward()
+        outs.append(dict(loss=loss.detach(), g_geo=gf[level].grad, g_col=cf[level].grad, g_ef=torch.stack([e.grad for e in efs]),
+                         g_mlp={k: p.grad.clone() for k, p in mlp.named_parameters()},
+                         g_dec={k: p.grad.clone() for k, p in dec.color_decoder_fine.named_parameters() if p.grad is not None}))
+    a, b = outs
+    assert parity.rel(b["loss"], a["loss"]) <= 1e-6
+    assert float(a["g_ef"].abs().min(1).values.max()) > 0            # every frame's latent is reached
+    for k in ("g_geo", "g_col", "g_ef"):
+        assert parity.rel(b[k], a[k]) <= 2e-5, k
+    assert max(parity.rel(b["g_mlp"][k], a["g_mlp"][k]) for k in a["g_mlp"]) <= 2e-5
+    assert max(parity.rel(b["g_dec"][k], a["g_dec"][k]) for k in a["g_dec"]) <= 2e-5
