@@ -11,12 +11,17 @@ mapper_loss = ops.mapper_loss
 tracker_loss = ops.tracker_loss
 
 
-def mapper_loss_torch(depth, color, valid_ray_mask, gt_depth, gt_color, stage, w_color_loss=0.1, affine=None):
-    """affine: (12,) exposure tensor of the (single) frame the batch comes from, or None."""
+def mapper_loss_torch(depth, color, valid_ray_mask, gt_depth, gt_color, stage, w_color_loss=0.1, affine=None,
+                      frame_index=None):
+    """affine: (12,) exposure tensor of the (single) frame the batch comes from, (F,12) with frame_index (R,) for a
+    batch that mixes rays of F keyframes (Mapper.py:805-822), or None."""
     mask = (gt_depth > 0) & valid_ray_mask & (~torch.isnan(depth))
     loss = torch.abs(gt_depth[mask] - depth[mask]).sum()
     if stage.startswith("color"):
-        if affine is not None:
+        if affine is not None and frame_index is not None:
+            a = affine.reshape(-1, 12)[frame_index.long()]
+            color = torch.einsum("rk,rkc->rc", color, a[:, :9].reshape(-1, 3, 3)) + a[:, 9:]
+        elif affine is not None:
             color = torch.matmul(color, affine[:9].reshape(3, 3)) + affine[-3:]
         color = torch.sigmoid(color)
         loss = loss + w_color_loss * torch.abs(gt_color[mask] - color[mask]).sum()
