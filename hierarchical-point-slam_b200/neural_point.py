@@ -18,7 +18,12 @@ from collections import namedtuple
 import numpy as np
 import torch
 
+import os
+
 from . import ops
+
+# voxel edge as a fraction of the level's largest query radius (see NeuralPointCloud._cell_for)
+CELL_PER_RADIUS = float(os.environ.get("HPS_CELL_PER_RADIUS", "0.5"))
 
 NeighborQuery = namedtuple("NeighborQuery", "I D count t_up t_dn")
 
@@ -275,7 +280,7 @@ class NeuralPointCloud(object):
             r_max = self.cfg["pointcloud"]["radius_query_ratio"] * max(self.radius_hierarchy[level].values())
         else:
             r_max = self.radius_query
-        return 0.5 * float(r_max)
+        return CELL_PER_RADIUS * float(r_max)
 
     def set_cloud(self, level, pos, geo_feats=None, col_feats=None):
         """Install a whole level at once (tests / benchmarks / checkpoint restore)."""
