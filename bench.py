@@ -498,9 +498,10 @@ def time_tracker(hps, npc, dec, renderer, scene, cfg, dev, gf, cf, pos, iters=10
     try:
         cam = torch.tensor([1.0, 0.0, 0.0, 0.0, 0.005, -0.004, 0.003], device=dev).requires_grad_(True)
         ef = scene["exposure_feat"].to(dev).clone().requires_grad_(True)
-        opt = hps.FusedAdam([([cam, ef], 5e-4)])      # torch.optim.Adam semantics, one kernel (gradients cleared by it)
+        opt = hps.FusedAdam([([cam, ef], 5e-4)], own_grads=False)      # torch.optim.Adam semantics, one kernel
 
         def it():
+            opt.zero_grad()
             c2w = hps.get_camera_from_tensor(cam)
             ro, rd = hps.get_rays_from_uv(pi, pj, c2w, K["H"], K["W"], K["fx"], K["fy"], K["cx"], K["cy"], dev)
             if FUSED_LOSS:

@@ -69,9 +69,13 @@ class _TwoLayer(nn.Module):
         for lin in (self.linear1, self.linear2):
             init(lin.weight)
 
+    def kernel_fits(self, x):
+        """One latent vector within the fused kernels' size limits (hps_exposure_fwd/bwd)."""
+        return x.is_cuda and x.numel() == self.linear1.in_features and self.linear1.out_features <= 1024 \
+            and self.linear1.in_features <= 64 and self.linear2.out_features <= 32
+
     def forward(self, x):
-        if x.is_cuda and x.numel() == self.linear1.in_features and self.linear1.out_features <= 1024 \
-                and self.linear1.in_features <= 64 and self.linear2.out_features <= 32:
+        if self.kernel_fits(x):
             # one latent vector (the exposure feature of a frame): fused kernel pair instead of ~10 library launches
             return ops.exposure_mlp(x, self.linear1.weight, self.linear1.bias, self.linear2.weight,
                                     self.linear2.bias).view(*x.shape[:-1], -1)

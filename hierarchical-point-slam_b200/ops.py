@@ -615,11 +615,42 @@ def prepare_rays(grid, rays_o, rays_d, gt_depth, radius, S, near, far, z_zero=No
 class RenderSpec:
     """Non-tensor arguments of render_rays (one per call)."""
     __slots__ = ("grid", "radius", "z_zero", "S", "near", "far", "coef", "min_nn", "min_valid", "color_stage",
-                 "tracker", "cloud_pos", "fill_geo", "fill_col", "live_geo", "live_col", "prep", "loss")
+                 "tracker", "cloud_pos", "fill_geo", "fill_col", "live_geo", "live_col", "prep", "loss", "aff_mlp")
 
     def __init__(self, **kw):
         for k in self.__slots__:
             setattr(self, k, kw.get(k))
+
+
+def _exposure_backward(eprm, a1, dout, gscale, e_need, x_shape, stream):
+    """d/d(latent, W1, b1, W2, b2) of the exposure MLP from d/d affine (12 floats, times the device scalar `gscale`
+    when given): one kernel on `stream`, one allocation.  e_need: which of the five gradients are wanted."""
+    if not any(e_need):
+        return (None,) * 5
+    hidden, n_in = eprm[1].shape
+    sizes = [hidden * n_in, hidden, 12 * hidden, 12, n_in]
+    buf = torch.empty(sum((n + 3) // 4 * 4 for n in sizes), dtype=torch.float32, device=a1.device)
+    parts, off = [], 0
+    for n in sizes:
+        parts.append(buf[off:off + n])
+        off += (n + 3) // 4 * 4
+    _call("hps_exposure_bwd", _lib.ptr(eprm[0]), _lib.ptr(eprm[1]), _lib.ptr(eprm[3]), _lib.ptr(a1), _lib.ptr(dout),
+          _lib.ptr(gscale), n_in, hidden, 12, _lib.ptr(parts[0]), _lib.ptr(parts[1]), _lib.ptr(parts[2]),
+          _lib.ptr(parts[3]), _lib.ptr(parts[4]) if e_need[0] else None, _stream(stream))
+    shaped = (parts[4].view(x_shape), parts[0].view(hidden, n_in), parts[1], parts[2].view(12, hidden), parts[3])
+    return tuple(g if e_need[i] else None for i, g in enumerate(shaped))
+
+
+def _exposure_params(tensors):
+    """(latent, W1, b1, W2, b2) as contiguous fp32 with the sizes checked -> (list, hidden, n_in)."""
+    ep = [_f32c(t) for t in tensors]
+    if len(ep) != 5:
+        raise _lib.HpsError("exposure MLP: expected latent, W1, b1, W2, b2")
+    ep[0] = ep[0].reshape(-1)
+    hidden, n_in = ep[1].shape
+    if ep[0].numel() != n_in or ep[3].shape[0] != 12:
+        raise _lib.HpsError("exposure MLP: latent / output size mismatch")
+    return ep, hidden, n_in
 
 
 class MapperLossSpec:
@@ -699,15 +730,22 @@ class _RenderRays(torch.autograd.Function):
                 head = _loss_head_floats(n_aff)
             flat = torch.empty(head + R * (4 if color_loss else 1), **f32)   # tracker: [4] = the batch statistic
             if not trk_loss and lm.exposure == "mlp" and color_loss:
-                eprm = [_f32c(t) for t in params[len(gprm) + len(cprm):]]
-                if len(eprm) != 5:
-                    raise _lib.HpsError("exposure MLP: expected latent, W1, b1, W2, b2")
                 ctx.exp_x_shape = params[len(gprm) + len(cprm)].shape
-                eprm[0] = eprm[0].reshape(-1)
-                e_hidden, e_in = eprm[1].shape
-                if eprm[0].numel() != e_in or eprm[3].shape[0] != 12:
-                    raise _lib.HpsError("exposure MLP: latent / output size mismatch")
+                eprm, e_hidden, e_in = _exposure_params(params[len(gprm) + len(cprm):])
                 a1_l, aff_l = torch.empty(e_hidden, **f32), torch.empty(12, **f32)
+        # decoder-side exposure affine (tracker, decoder.py:606-612) from the MLP's own tensors: evaluated beside the
+        # neighbour search instead of in front of the call, its backward beside the feature scatter
+        mprm, a1_d = [], None
+        if spec.aff_mlp and spec.color_stage:
+            if eprm or aff_l is not None or aff is not None:
+                raise _lib.HpsError("exposure: either the decoder-side MLP or a loss-side correction, not both")
+            ctx.aff_x_shape = params[len(gprm) + len(cprm)].shape
+            mprm, m_hidden, m_in = _exposure_params(params[len(gprm) + len(cprm):])
+            a1_d, aff = torch.empty(m_hidden, **f32), torch.empty(12, **f32)
+
+        def aff_head(s):
+            _call("hps_exposure_fwd", _lib.ptr(mprm[0]), _lib.ptr(mprm[1]), _lib.ptr(mprm[2]), _lib.ptr(mprm[3]),
+                  _lib.ptr(mprm[4]), m_in, m_hidden, 12, _lib.ptr(a1_d), _lib.ptr(aff), _stream(s))
 
         def loss_head(s):
             """zero the accumulators and evaluate the exposure MLP (independent of the rays): off the critical path"""
@@ -767,6 +805,8 @@ class _RenderRays(torch.autograd.Function):
                     refreshed = side.record_event()
                 # forward images first (the decoders wait for them), the backward images afterwards
                 _mlp_pack(MLP_COL, carr, dev, side)
+                if mprm:
+                    aff_head(side)
                 packed_col = side.record_event()
                 _mlp_pack(MLP_GEO, garr, dev, side)
                 if lm is not None:
@@ -779,6 +819,8 @@ class _RenderRays(torch.autograd.Function):
                     _call("hps_mlp_tc_bwd_pack", MLP_GEO, garr, _lib.ptr(bpk_g), _stream(aux))
             if lm is not None and not fork:
                 loss_head(main)
+            if mprm and not fork:
+                aff_head(main)
             if prep is None:
                 _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t),
                       0.0 if rad_t is not None else float(rad), _lib.ptr(zz), _z_zero_stride(zz, R, S), R, S,
@@ -831,6 +873,7 @@ class _RenderRays(torch.autograd.Function):
                       _lib.ptr(flat), _lib.ptr(flat[head:]), _lib.ptr(flat[head + R:]) if color_loss else None,
                       _lib.ptr(flat[4:]) if aff_l is not None else None, st())
         ctx.loss_state = None if lm is None else (flat, a1_l, eprm, color_loss, head, n_aff, aff_in_shape)
+        ctx.aff_mlp_state = (mprm, a1_d) if mprm else None
         ctx.spec = spec
         ctx.n_g = len(gprm)
         ctx.row_map = row_map
@@ -877,7 +920,8 @@ class _RenderRays(torch.autograd.Function):
         zp = _ZeroPool(dev)
         h_dg = zp.want_like(gprm, skip_first=not need[7]) if want_gw else None
         h_dcw = zp.want_like(cprm, skip_first=True) if want_cw else None   # colour _B is not a parameter
-        h_daff = zp.want((12,)) if (aff is not None and need[6]) else None
+        m_need = need[7 + len(gprm) + len(cprm):] if ctx.aff_mlp_state is not None else ()
+        h_daff = zp.want((12,)) if (aff is not None and (need[6] or any(m_need))) else None
         n_rows = ctx.n_live if ctx.row_map is not None else fg.shape[0]
         h_dfg = zp.want((n_rows, C_DIM)) if need[4] else None
         h_dfc = zp.want((n_rows, C_DIM)) if (spec.color_stage and need[5]) else None
@@ -916,6 +960,12 @@ class _RenderRays(torch.autograd.Function):
                 w_g = _side_stream(dev, 2) if dg is not None else None
                 _mlp_backward(MLP_COL, cprm, "tc", act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c, need_p, daff, dev, main,
                               dp_c, packed=ctx.bwd_packed[1], absmax_done=folded, max_ctas=n_c, wgrad_stream=w_c)
+                e_s = None
+                if any(m_need):            # d affine is complete with the colour dgrad: the MLP's backward runs beside
+                    e_s = _side_stream(dev, 3)                                      # the feature scatter
+                    e_s.wait_stream(main)
+                    g_aff_mlp = _exposure_backward(ctx.aff_mlp_state[0], ctx.aff_mlp_state[1], daff, None, m_need,
+                                                   ctx.aff_x_shape, e_s)
                 _mlp_backward(MLP_GEO, gprm, "tc", act_g, pts, c_geo, None, d_occ, P, dg, dc_g, need_p, None, dev, side,
                               dp_g, packed=ctx.bwd_packed[0], absmax_done=folded, max_ctas=n_g, wgrad_stream=w_g)
                 main.wait_stream(side)
@@ -926,6 +976,10 @@ class _RenderRays(torch.autograd.Function):
                 if spec.color_stage:
                     dp_c = _mlp_backward(MLP_COL, cprm, ctx.saved_kinds[1], act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c,
                                          need_p, daff, dev, dp=zp.get(h_dpc))
+                e_s = None
+                if any(m_need):
+                    g_aff_mlp = _exposure_backward(ctx.aff_mlp_state[0], ctx.aff_mlp_state[1], daff, None, m_need,
+                                                   ctx.aff_x_shape, None)
             if dfg is not None or dfc is not None or need_p:
                 _call("hps_interp_bwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(w), _lib.ptr(has), _lib.ptr(pos),
                       _lib.ptr(fg), _lib.ptr(fc), _lib.ptr(c_geo), _lib.ptr(c_col), _lib.ptr(dc_g), _lib.ptr(dc_c), P,
@@ -942,23 +996,12 @@ class _RenderRays(torch.autograd.Function):
             if ctx.loss_state is not None and l_eprm:
                 # exposure MLP backward from d loss / d affine (accumulated by the fused loss kernel); the main stream
                 # has slack here - the weight-gradient kernels on their own streams finish later
-                e_need = need[7 + len(gprm) + len(cprm):]
-                g_exp = (None,) * 5
-                if any(e_need):
-                    e_hidden, e_in = l_eprm[1].shape
-                    sizes = [e_hidden * e_in, e_hidden, 12 * e_hidden, 12, e_in]
-                    ebuf = torch.empty(sum((n + 3) // 4 * 4 for n in sizes), **f32)
-                    parts, off = [], 0
-                    for n in sizes:
-                        parts.append(ebuf[off:off + n])
-                        off += (n + 3) // 4 * 4
-                    _call("hps_exposure_bwd", _lib.ptr(l_eprm[0]), _lib.ptr(l_eprm[1]), _lib.ptr(l_eprm[3]), _lib.ptr(l_a1),
-                          _lib.ptr(l_flat[4:]), _lib.ptr(gscale), e_in, e_hidden, 12, _lib.ptr(parts[0]),
-                          _lib.ptr(parts[1]), _lib.ptr(parts[2]), _lib.ptr(parts[3]),
-                          _lib.ptr(parts[4]) if e_need[0] else None, st())
-                    shaped = (parts[4].view(ctx.exp_x_shape), parts[0].view(e_hidden, e_in), parts[1],
-                              parts[2].view(12, e_hidden), parts[3])
-                    g_exp = tuple(g if e_need[i] else None for i, g in enumerate(shaped))
+                g_exp = _exposure_backward(l_eprm, l_a1, l_flat[4:], gscale, need[7 + len(gprm) + len(cprm):],
+                                           ctx.exp_x_shape, None)
+            if ctx.aff_mlp_state is not None:
+                g_exp = g_aff_mlp if any(m_need) else (None,) * 5
+                if e_s is not None:
+                    main.wait_stream(e_s)
             for w_s in wgrad_streams:
                 main.wait_stream(w_s)
         gg = [(g if (g is not None and need[7 + i]) else None) for i, g in enumerate(dg)] if dg else [None] * N_PARAM
@@ -967,7 +1010,8 @@ class _RenderRays(torch.autograd.Function):
                 if dcw else [None] * N_PARAM
         else:
             gcw = []
-        return (None, g_ro if need[1] else None, g_rd if need[2] else None, None, dfg, dfc, daff, *gg, *gcw, *g_exp)
+        return (None, g_ro if need[1] else None, g_rd if need[2] else None, None, dfg, dfc,
+                daff if need[6] else None, *gg, *gcw, *g_exp)
 
 
 def render_rays(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, geo_params, col_params,
@@ -981,7 +1025,9 @@ def render_rays(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, ge
     if isinstance(feats_col, LiveRows):
         feats_col = feats_col.param
     params = list(geo_params) + (list(col_params) if spec.color_stage else [])
-    if isinstance(spec.loss, MapperLossSpec) and spec.loss.exposure and spec.color_stage \
+    if spec.aff_mlp and spec.color_stage:
+        params += list(exposure_params)      # decoder-side exposure MLP: (latent, W1, b1, W2, b2)
+    elif isinstance(spec.loss, MapperLossSpec) and spec.loss.exposure and spec.color_stage \
             and spec.loss.gt_color is not None:
         params += list(exposure_params)      # "mlp": (latent, W1, b1, W2, b2); "affine": (affine,)
     return _RenderRays.apply(spec, rays_o, rays_d, gt_depth, feats_geo, feats_col if spec.color_stage else None,
@@ -1032,12 +1078,18 @@ class FusedAdam:
     """torch.optim.Adam semantics (no amsgrad, no weight decay) for a few small dense tensors - the tracker's pose,
     exposure latent and exposure MLPs (Tracker.py:383-416) - as ONE kernel per step instead of the ~20 launches of
     torch's capturable foreach path.  `groups`: list of (tensor or list of tensors, lr) = parameter groups.
-    Every gradient lives in one flat buffer (p.grad are views of it, created here and kept: backward accumulates into
-    them) and is cleared by the step kernel itself, so zero_grad() costs nothing.  Device step counter: capturable."""
+    own_grads=True: every gradient lives in one flat buffer (p.grad are views of it, created here and kept: backward
+    accumulates into them) and is cleared by the step kernel itself, so zero_grad() costs nothing.
+    own_grads=False: step() reads whatever p.grad holds (parameters without a gradient are skipped) and
+    zero_grad() sets the gradients to None, so that backward hands its buffers over instead of adding into ours -
+    one small kernel less per parameter; inside a CUDA graph the buffers keep their addresses.
+    Device step counter (one per launch of up to 24 tensors, so a parameter that sits out an iteration shares the
+    bias correction of the others): capturable."""
 
     MAX = 24
 
-    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8, own_grads=True):
+        self.own_grads = bool(own_grads)
         self.params, self.lrs = [], []
         for tensors, lr in groups:
             for t in ([tensors] if torch.is_tensor(tensors) else list(tensors)):
@@ -1055,7 +1107,8 @@ class FusedAdam:
         self._views, off = [], 0
         for p, n in zip(self.params, sizes):
             g, m, v = (self._flat[k, off:off + p.numel()].view(p.shape) for k in range(3))
-            p.grad = g
+            if self.own_grads:
+                p.grad = g
             self._views.append((g, m, v))
             off += n
         n_chunks = (len(self.params) + self.MAX - 1) // self.MAX
@@ -1064,28 +1117,42 @@ class FusedAdam:
     def set_lr(self, index, lr):
         self.lrs[index] = float(lr)
 
-    def zero_grad(self, set_to_none=False):
-        """Nothing to do after a step() (the kernel cleared the gradients); kept for optimiser-shaped call sites."""
-        if set_to_none:
-            raise _lib.HpsError("FusedAdam keeps its gradient buffers (views of one allocation)")
+    def zero_grad(self, set_to_none=None):
+        """own_grads: nothing to do after a step() (the kernel cleared the gradients).  Otherwise: gradients -> None."""
+        if self.own_grads:
+            if set_to_none:
+                raise _lib.HpsError("FusedAdam(own_grads=True) keeps its gradient buffers (views of one allocation)")
+            return
+        for p in self.params:
+            p.grad = None
 
     @torch.no_grad()
     def step(self):
-        ps, gs, ms, vs = [], [], [], []
-        for p, (g, m, v) in zip(self.params, self._views):
-            if p.grad is None or p.grad.data_ptr() != g.data_ptr():
-                raise _lib.HpsError("FusedAdam: a .grad was replaced; keep the buffers (zero_grad(set_to_none=False))")
-            ps.append(p); gs.append(g); ms.append(m); vs.append(v)
+        ps, gs, ms, vs, lr_of = [], [], [], [], []
+        for p, (g, m, v), lr in zip(self.params, self._views, self.lrs):
+            if self.own_grads:
+                if p.grad is None or p.grad.data_ptr() != g.data_ptr():
+                    raise _lib.HpsError("FusedAdam: a .grad was replaced; keep the buffers (or use own_grads=False)")
+            else:
+                if p.grad is None:
+                    continue
+                g = p.grad
+                if g.dtype != torch.float32 or not g.is_contiguous():
+                    g = p.grad = g.float().contiguous()
+            ps.append(p); gs.append(g); ms.append(m); vs.append(v); lr_of.append(lr)
+        if not ps:
+            return
         dev = self.params[0].device
         with torch.cuda.device(dev):
             for s in range(0, len(ps), self.MAX):
                 e = min(s + self.MAX, len(ps))
                 n = e - s
                 numel = (ctypes.c_int64 * n)(*[p.numel() for p in ps[s:e]])
-                lrs = (ctypes.c_float * n)(*self.lrs[s:e])
+                lrs = (ctypes.c_float * n)(*lr_of[s:e])
                 arrs = [(ctypes.c_void_p * n)(*[t.data_ptr() for t in ts[s:e]]) for ts in (ps, gs, ms, vs)]
                 _call("hps_adam_multi", n, arrs[0], arrs[1], arrs[2], arrs[3], numel, lrs, float(self.betas[0]),
-                      float(self.betas[1]), self.eps, _lib.ptr(self.step_count[s // self.MAX]), 1, _stream())
+                      float(self.betas[1]), self.eps, _lib.ptr(self.step_count[s // self.MAX]),
+                      1 if self.own_grads else 0, _stream())
 
 
 # --------------------------------------------------------------------------------------------------

@@ -158,16 +158,23 @@ class Renderer(object):
             z_zero = self._z_for_zero_depth(gt_depth, device)
         geo = getattr(decoders, "geo_decoder_" + level)
         col = getattr(decoders, "color_decoder_" + level)
-        affine = None
-        if color_stage and exposure_feat is not None and col.encode_exposure:
-            affine = col.mlp_exposure(exposure_feat)                     # decoder.py:608
+        affine, aff_prm = None, None
+        if color_stage and exposure_feat is not None and col.encode_exposure:        # decoder.py:606-612
+            mlp = col.mlp_exposure
+            if mlp.kernel_fits(exposure_feat):
+                # the MLP's own tensors go into the fused call: evaluated beside the neighbour search, its backward
+                # beside the feature scatter
+                aff_prm = (exposure_feat, mlp.linear1.weight, mlp.linear1.bias, mlp.linear2.weight, mlp.linear2.bias)
+            else:
+                affine = mlp(exposure_feat)
         spec = ops.RenderSpec(
             grid=index.grid_for(radius), radius=radius,
             z_zero=z_zero, S=S,
             near=self.near_end_surface, far=self.far_end_surface, coef=self.sigmoid_coefficient,
             min_nn=geo.min_nn_num, min_valid=int(S / 2 + 1), color_stage=color_stage, tracker=bool(is_tracker),
             cloud_pos=cloud_pos[level] if is_tracker else None, fill_geo=decoders._fill("geo", rays_o.device),
-            fill_col=decoders._fill("col", rays_o.device) if color_stage else None, prep=prepared)
+            fill_col=decoders._fill("col", rays_o.device) if color_stage else None, prep=prepared,
+            aff_mlp=aff_prm is not None)
         loss = None
         if _loss is not None and _loss[0] == "tracker":
             _, gt_color, w_color, reduce_fn = _loss
@@ -175,7 +182,8 @@ class Renderer(object):
                                             zero_missing=not self.sample_near_pcl and not self.assume_positive_depth)
             loss, depth, uncertainty, color, valid = ops.render_rays(
                 spec, rays_o, rays_d, gt_depth, npc_geo_feats[level], npc_col_feats[level] if color_stage else None,
-                affine, geo.kernel_params(rays_o.device), col.kernel_params(rays_o.device) if color_stage else None)
+                affine, geo.kernel_params(rays_o.device), col.kernel_params(rays_o.device) if color_stage else None,
+                aff_prm)
         elif _loss is not None:
             _, gt_color, w_color, loss_exposure_feat, loss_affine, frame_index = _loss
             if loss_exposure_feat is not None and loss_affine is not None:
@@ -195,7 +203,8 @@ class Renderer(object):
         else:
             depth, uncertainty, color, valid = ops.render_rays(
                 spec, rays_o, rays_d, gt_depth, npc_geo_feats[level], npc_col_feats[level] if color_stage else None,
-                affine, geo.kernel_params(rays_o.device), col.kernel_params(rays_o.device) if color_stage else None)
+                affine, geo.kernel_params(rays_o.device), col.kernel_params(rays_o.device) if color_stage else None,
+                aff_prm)
         if not self.sample_near_pcl and not self.assume_positive_depth:
             depth = torch.where(gt_depth > 0, depth, torch.zeros_like(depth))     # Renderer.py:250-251
         if self.skip_zero_depth_pixel:

@@ -223,17 +223,17 @@ def check_tracker(stage, out, ref, scene, inputs, tol=TOL):
 
 
 def run_small_scene(device="cuda:0", stages=("geometry_mid", "color_mid", "geometry_fine", "color_fine"),
-                    tracker=True):
+                    tracker=True, fused_loss=False):
     scene = load("scene_small.pt")
     hps, npc, dec, renderer = product(scene, device)
     report = {}
     ref = load("render_mapper_small.pt")
     for stage in stages:
-        out = mapper_step(hps, npc, dec, renderer, scene, stage, device)
+        out = mapper_step(hps, npc, dec, renderer, scene, stage, device, fused_loss=fused_loss)
         report["mapper/" + stage] = check_mapper(stage, out, ref[stage], dec)
     if tracker:
         tref = load("render_tracker_small.pt")
         for stage in ("color_mid", "color_fine"):
-            out = tracker_step(hps, npc, dec, renderer, scene, tref["inputs"], stage, device)
+            out = tracker_step(hps, npc, dec, renderer, scene, tref["inputs"], stage, device, fused_loss=fused_loss)
             report["tracker/" + stage] = check_tracker(stage, out, tref[stage], scene, tref["inputs"])
     return report

@@ -545,3 +545,29 @@ def test_mapper_loss_with_several_keyframes(hps, layout):
         assert err < 1e-5, (name, err)
     with pytest.raises(ValueError):
         hps.mapper_loss(depth, color, valid, gt_d, gt_c, "color_fine", w, affine)          # (F,12) needs frame_index
+
+
+def test_fused_adam_on_handed_over_gradients(hps):
+    """FusedAdam(own_grads=False): backward hands its gradient buffers over (zero_grad sets them to None), the step
+    kernel reads them where they are; parameters without a gradient are skipped."""
+    torch.manual_seed(12)
+    mine = [torch.randn(s, device=DEV).requires_grad_(True) for s in ((7,), (8,), (5, 3))]
+    ref = [p.detach().clone().requires_grad_(True) for p in mine]
+    opt = hps.FusedAdam([(mine[:2], 5e-4), ([mine[2]], 1e-3)], own_grads=False)
+    topt = torch.optim.Adam([{"params": ref[:2], "lr": 5e-4}, {"params": [ref[2]], "lr": 1e-3}])
+    assert all(p.grad is None for p in mine)
+    for k in range(5):
+        opt.zero_grad()
+        topt.zero_grad()
+        for ps in (mine, ref):
+            (sum((p * (k + 1.0)).sin().sum() for p in ps)).backward()
+        held = [p.grad.data_ptr() for p in mine]
+        opt.step()
+        topt.step()
+        assert [p.grad.data_ptr() for p in mine] == held and float(mine[0].grad.abs().max()) > 0    # left as they were
+        for a, b in zip(mine, ref):
+            assert float((a.detach() - b.detach()).abs().max()) <= 2e-6 * max(1.0, float(b.detach().abs().max()))
+    opt.zero_grad()
+    assert all(p.grad is None for p in mine)
+    opt.step()                                                       # nothing to do, no launch
+    assert int(opt.step_count[0, 0]) == 5
