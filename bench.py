@@ -13,7 +13,7 @@ parameter-free head = sampling + neighbour search | the rest) so that the all-re
 step i+1; it is started after the untimed L2 flush (it overlaps nothing untimed) and the last one is timed on its own.
 
 JSON line: see the driver's contract; `value` = rays/s with inputs resident in HBM (CUDA-event timed per
-step, L2 flushed between steps), `e2e` = same through the public API from pinned host buffers with the
+step, L2 flushed between steps), `e2e` = same through the public API from pinned host buffers (double-buffered H2D on a copy stream) with the
 loss read back every step, `roofline` = dominant kernel vs MEASURED_PEAKS.json, `cpu_baseline` = the
 oracle port timed on the host cores on a bounded sample.
 """
@@ -359,11 +359,21 @@ def run_ours(args, rank, world, local_rank):
                 g_head(**{k: src[k][batch_index(i)] for k in static_pk})
                 drain()
                 return g_tail()
+
+            def replay():                      # inputs already in static_pk
+                g_head.graph.replay()
+                drain()
+                g_tail.graph.replay()
+                return g_tail.outputs
         else:
             graphed = hps.graphs.GraphedStep(step, static_pk, warmup=3)
 
             def run(i, src):
                 return graphed(**{k: src[k][batch_index(i)] for k in static_pk})
+
+            def replay():
+                graphed.graph.replay()
+                return graphed.outputs
         launches_per_step = hps.ops.LAUNCHES["n"] // 4          # 3 warm-up passes + the captured one
     except Exception as e:                                        # pragma: no cover - reported in the JSON line
         mode = "eager (graph capture failed: %s)" % str(e).splitlines()[0][:120]
@@ -374,6 +384,10 @@ def run_ours(args, rank, world, local_rank):
         def run(i, src):
             for k in static_pk:
                 static_pk[k].copy_(src[k][batch_index(i)], non_blocking=True)
+            drain()
+            return step()
+
+        def replay():
             drain()
             return step()
 
@@ -411,21 +425,54 @@ def run_ours(args, rank, world, local_rank):
     log("timed region done")
     launches = launches_per_step * args.steps
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    # ---- e2e: pinned host buffers in, loss read back every step, wall clock around the synchronised region ----
-    for i in range(3):
-        loss = run(i, host_pk)
-        post()
-        loss.item()
+    # ---- e2e: every step's inputs come from pinned host memory and every step's loss is read back on the host, wall
+    # clock around the synchronised region.  The loop is pipelined like a real mapper loop would be: step i+1's H2D
+    # copy runs on a copy stream into the other of two staging buffers while step i computes, and the host reads the
+    # loss of step i-1 (pinned, event-ordered) after it has issued step i - the GPU never waits for the host. ----
+    copy_s = torch.cuda.Stream()
+    main_s = torch.cuda.current_stream()
+    stage = [torch.empty_like(static_pk["bytes"]) for _ in range(2)]
+    loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+    ev_in, ev_used, ev_out = [None, None], [None, None], [None, None]
+    seen = []
+
+    def feed(i):
+        """H2D copy of step i's ray batch (copy stream; waits until the staging buffer's previous reader is done)."""
+        with torch.cuda.stream(copy_s):
+            if ev_used[i % 2] is not None:
+                copy_s.wait_event(ev_used[i % 2])
+            stage[i % 2].copy_(host_pk["bytes"][batch_index(i)], non_blocking=True)
+            ev_in[i % 2] = copy_s.record_event()
+
+    def e2e_loop(n, first):
+        feed(first)
+        for k in range(n):
+            i = first + k
+            if k + 1 < n:
+                feed(i + 1)
+            main_s.wait_event(ev_in[i % 2])
+            static_pk["bytes"].copy_(stage[i % 2], non_blocking=True)
+            ev_used[i % 2] = main_s.record_event()
+            loss = replay()
+            post()                                                  # (ranks > 1) start the exchange
+            loss_host[i % 2].copy_(loss.detach().reshape(()), non_blocking=True)      # D2H read of the loss
+            ev_out[i % 2] = main_s.record_event()
+            if k > 0:
+                ev_out[(i - 1) % 2].synchronize()
+                seen.append(float(loss_host[(i - 1) % 2]))
+        ev_out[(first + n - 1) % 2].synchronize()
+        seen.append(float(loss_host[(first + n - 1) % 2]))
+
+    e2e_loop(3, 0)
     drain()
     sync_all()
+    seen.clear()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        loss = run(args.warmup + i, host_pk)   # H2D copy + iteration
-        post()                                  # (ranks > 1) start the exchange, then ...
-        loss.item()                             # ... D2H read of the loss
+    e2e_loop(args.steps, args.warmup)
     drain()
     sync_all()
     e2e_s = time.perf_counter() - t0
+    assert len(seen) == args.steps and all(v == v for v in seen), "e2e: every step's loss must have been read back"
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -464,7 +511,9 @@ def run_ours(args, rank, world, local_rank):
                            api="renderer.render_batch_ray_loss + backward" if FUSED_LOSS else
                            "renderer.render_batch_ray + mapper_loss + backward"), "clocks": clocks,
             "e2e": {"value": RAYS * world * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 4},
+                    "d2h_bytes_per_step": 4,
+                    "note": "every step: H2D of its ray batch from pinned memory (copy stream, two staging buffers) and "
+                            "D2H of its loss (read by the host one step behind); no L2 flush"},
             "gpu_launches": launches, "roofline": roof["roofline"], "kernels_ms_per_step": roof["per_kernel"]}
     if tracking is not None:
         line["tracking"] = tracking
