@@ -608,6 +608,7 @@ def roofline(per, hps, npc, devb, sl):
                                   want_cand=True)
     mean_cand = float(cand.float().mean())
     work["hps_knn_query"] = ("hbm", (84.0 + 12.0 * mean_cand) * P)
+    work["hps_sample_knn"] = ("hbm", (84.0 + 12.0 * mean_cand + 60.0) * P)     # + the sampling kernel's 36 B in, 24 B out
     top = max(per, key=per.get)
     bound, amount = work.get(top, ("hbm", 0.0))
     ms = per[top]

@@ -54,6 +54,7 @@ SIGNATURES = {
     "hps_exposure_bwd": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp]),
     "hps_sample_rays": (_i32, [_vp, _vp, _vp, _vp, ctypes.c_double, _vp, _i64, _i64, _i32, _f32, _f32, _vp, _vp, _vp, _vp,
                                _vp]),
+    "hps_sample_knn": (_i32, [_vp, _vp, _vp, _vp, _vp, ctypes.c_double, _vp, _i64, _i64, _i32, _f32, _f32] + [_vp] * 9),
     "hps_sample_rays_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "hps_adam_multi": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _vp, _i32, _vp]),
     "hps_mapper_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _vp, _vp, _vp, _vp, _vp]),

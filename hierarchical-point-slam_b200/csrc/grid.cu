@@ -16,6 +16,7 @@
 // candidate list with coalesced float4 loads and keeps the running top-8 in lanes 0..7
 // (insertion by ballot + shfl_up, ordered by (D, original index)).
 #include "hps_common.cuh"
+#include "sample_point.cuh"
 
 namespace hps {
 
@@ -241,11 +242,15 @@ __device__ __forceinline__ unsigned long long merge_top8(unsigned long long best
 // comes from a start-bit mask (redux.or + popc), not from a search; (3) per query, candidates inside the radius and
 // better than the current 8th are appended to a per-warp buffer, and every 32 of them are sorted by a bitonic
 // network and merged into the running top-8.  Results do not depend on G (exact search).
-template <int G>
+// RAYS: the queries are the sample points of rays and are computed here (sample_point.cuh) instead of being read -
+// the warp also writes z / point / thresholds for the kernels downstream, which saves the sampling launch.
+template <int G, bool RAYS>
 __global__ void __launch_bounds__(kQueryWarps * 32, 4)      // 4 CTAs = 32 warps per SM (G = 5 would take 80 registers otherwise)
 knn_query_kernel(GridView g, const float* __restrict__ q, const float* __restrict__ t_up,
                  const float* __restrict__ t_dn, int64_t nq, int32_t* __restrict__ I, float* __restrict__ D,
-                 int32_t* __restrict__ count, int32_t* __restrict__ cand) {
+                 int32_t* __restrict__ count, int32_t* __restrict__ cand, const RaySource src,
+                 float* __restrict__ z_out, float* __restrict__ pts_out, float* __restrict__ tup_out,
+                 float* __restrict__ tdn_out) {
     __shared__ int s_start[kQueryWarps][kStageCells];
     __shared__ int s_excl[kQueryWarps][kStageCells + 32];
     __shared__ unsigned long long s_buf[kQueryWarps][G][64];
@@ -255,15 +260,34 @@ knn_query_kernel(GridView g, const float* __restrict__ q, const float* __restric
 
     const float ox = g.meta->origin[0], oy = g.meta->origin[1], oz = g.meta->origin[2];
     float qx[G], qy[G], qz[G], tdn[G];
+    float tup[RAYS ? G : 1];
     int x0 = 0x7fffffff, y0 = 0x7fffffff, z0 = 0x7fffffff, x1 = -1, y1 = -1, z1 = -1;
 #pragma unroll
     for (int k = 0; k < G; ++k) {
         const bool live = q0 + k < nq;
         const int64_t qi = live ? q0 + k : q0;
-        qx[k] = __ldg(q + qi * 3 + 0);
-        qy[k] = __ldg(q + qi * 3 + 1);
-        qz[k] = __ldg(q + qi * 3 + 2);
-        tdn[k] = live ? __ldg(t_dn + qi) : -1.0f;
+        if constexpr (RAYS) {
+            const int64_t r = qi / src.S;
+            const SamplePoint sp = sample_point(src, r, (int)(qi - r * src.S));
+            qx[k] = sp.x;
+            qy[k] = sp.y;
+            qz[k] = sp.zc;
+            tdn[k] = live ? sp.t_dn : -1.0f;
+            tup[k] = sp.t_up;
+            if (live && lane == 0) {
+                z_out[qi] = sp.z;
+                pts_out[qi * 3 + 0] = sp.x;
+                pts_out[qi * 3 + 1] = sp.y;
+                pts_out[qi * 3 + 2] = sp.zc;
+                tup_out[qi] = sp.t_up;
+                tdn_out[qi] = sp.t_dn;
+            }
+        } else {
+            qx[k] = __ldg(q + qi * 3 + 0);
+            qy[k] = __ldg(q + qi * 3 + 1);
+            qz[k] = __ldg(q + qi * 3 + 2);
+            tdn[k] = live ? __ldg(t_dn + qi) : -1.0f;
+        }
         if (tdn[k] >= 0.f) {
             // conservative search radius: sqrt(t_dn) plus slack that dominates every fp32 rounding involved
             const float rr = sqrtf(tdn[k]) * 1.00001f + 1e-6f * (fabsf(qx[k]) + fabsf(qy[k]) + fabsf(qz[k]) + 1.0f);
@@ -398,7 +422,10 @@ knn_query_kernel(GridView g, const float* __restrict__ q, const float* __restric
         const int64_t qi = q0 + k;
         const bool used = best[k] != kNoKey;
         const float bD = __uint_as_float((unsigned)(best[k] >> 32));
-        const unsigned inr = __ballot_sync(kFull, (lane < kK) && used && (bD < __ldg(t_up + qi)));
+        float up;
+        if constexpr (RAYS) up = tup[k];
+        else up = __ldg(t_up + qi);
+        const unsigned inr = __ballot_sync(kFull, (lane < kK) && used && (bD < up));
         if (lane < kK) {
             I[qi * kK + lane] = used ? (int)(unsigned)best[k] : -1;
             D[qi * kK + lane] = used ? bD : FLT_MAX;
@@ -532,13 +559,38 @@ extern "C" int hps_knn_query(const hps_grid_t* g, const float* q, const float* t
     v.meta = g->meta;
     v.mask = (unsigned)(g->T - 1);
     v.inv_cell = 1.0f / g->cell;
+    const RaySource none{};
     if (group == 5) {     // the samples of one ray share a sweep
-        knn_query_kernel<5><<<(unsigned)ceil_div(ceil_div(nq, 5), kQueryWarps), kQueryWarps * 32, 0, (cudaStream_t)stream_>>>(
-            v, q, t_up, t_dn, nq, I, D, count, cand);
+        knn_query_kernel<5, false><<<(unsigned)ceil_div(ceil_div(nq, 5), kQueryWarps), kQueryWarps * 32, 0, (cudaStream_t)stream_>>>(
+            v, q, t_up, t_dn, nq, I, D, count, cand, none, nullptr, nullptr, nullptr, nullptr);
     } else {
-        knn_query_kernel<1><<<(unsigned)ceil_div(nq, kQueryWarps), kQueryWarps * 32, 0, (cudaStream_t)stream_>>>(
-            v, q, t_up, t_dn, nq, I, D, count, cand);
+        knn_query_kernel<1, false><<<(unsigned)ceil_div(nq, kQueryWarps), kQueryWarps * 32, 0, (cudaStream_t)stream_>>>(
+            v, q, t_up, t_dn, nq, I, D, count, cand, none, nullptr, nullptr, nullptr, nullptr);
     }
+    HPS_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int hps_sample_knn(const hps_grid_t* g, const float* rays_o, const float* rays_d, const float* gt_depth,
+                              const double* radius, double radius_scalar, const float* z_zero, int64_t z_zero_stride,
+                              int64_t R, int S, float near, float far, float* z, float* pts, float* t_up, float* t_dn,
+                              int32_t* I, float* D, int32_t* count, int32_t* cand, void* stream_) {
+    using namespace hps;
+    HPS_REQUIRE(g != nullptr && g->T > 0, "grid not built");
+    HPS_REQUIRE(R >= 0 && S >= 1 && S <= 32, "need R >= 0, 1 <= S <= 32");
+    HPS_REQUIRE(z_zero_stride == 0 || z_zero_stride >= S, "z_zero_stride must be 0 (shared row) or >= S");
+    if (R == 0) return 0;
+    HPS_REQUIRE(rays_o && rays_d && gt_depth && z && pts && t_up && t_dn && I && D && count, "null buffer");
+    GridView v;
+    v.sorted = g->sorted;
+    v.table = g->table;
+    v.meta = g->meta;
+    v.mask = (unsigned)(g->T - 1);
+    v.inv_cell = 1.0f / g->cell;
+    const RaySource src{rays_o, rays_d, gt_depth, radius, radius_scalar, z_zero, z_zero_stride, S, near, far};
+    const int64_t nq = R * S;
+    knn_query_kernel<1, true><<<(unsigned)ceil_div(nq, kQueryWarps), kQueryWarps * 32, 0, (cudaStream_t)stream_>>>(
+        v, nullptr, nullptr, nullptr, nq, I, D, count, cand, src, z, pts, t_up, t_dn);
     HPS_LAUNCH_OK();
     return 0;
 }

@@ -8,44 +8,22 @@
 //     D >  r^2 (f64)  <=>  D >  t_dn      (decoder.py:236, weight zeroing)
 // Every product and sum is rounded separately (no FMA contraction) in the reference's operation order, so
 // sample points - and therefore neighbour sets - are bit-identical to the reference's.
-#include "hps_common.cuh"
+#include "sample_point.cuh"
 
 namespace hps {
 
-__device__ __forceinline__ float linspace01(int i, int S) {
-    if (S == 1) return 0.f;
-    const float step = 1.0f / (float)(S - 1);
-    return i < S / 2 ? __fmul_rn(step, (float)i) : __fsub_rn(1.0f, __fmul_rn(step, (float)(S - 1 - i)));
-}
-
-__global__ void sample_rays_kernel(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
-                                   const float* __restrict__ gt_depth, const double* __restrict__ radius,
-                                   double radius_scalar, const float* __restrict__ z_zero, int64_t zstride, int64_t R, int S,
-                                   float near, float far, float* __restrict__ z, float* __restrict__ pts,
+__global__ void sample_rays_kernel(const RaySource src, int64_t R, float* __restrict__ z, float* __restrict__ pts,
                                    float* __restrict__ t_up, float* __restrict__ t_dn) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R * S) return;
-    const int64_t r = i / S;
-    const int s = (int)(i - r * S);
-    const float d = __ldg(gt_depth + r);
-    float zz;
-    if (d > 0.f) {
-        const float t = linspace01(s, S);
-        zz = __fadd_rn(__fmul_rn(__fmul_rn(near, d), __fsub_rn(1.0f, t)), __fmul_rn(__fmul_rn(far, d), t));
-    } else {
-        zz = z_zero ? __ldg(z_zero + r * zstride + s) : 0.f;
-    }
-    z[i] = zz;
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-        pts[i * 3 + a] = __fadd_rn(__ldg(rays_o + r * 3 + a), __fmul_rn(__ldg(rays_d + r * 3 + a), zz));
-    const double rad = radius ? radius[r] : radius_scalar;
-    const double r2 = rad * rad;
-    const float t = __double2float_rn(r2);
-    const float dn = ((double)t > r2) ? nextafterf(t, -INFINITY) : t;
-    const float up = ((double)t < r2) ? nextafterf(t, INFINITY) : t;
-    t_dn[i] = dn;
-    t_up[i] = up;
+    if (i >= R * src.S) return;
+    const int64_t r = i / src.S;
+    const SamplePoint sp = sample_point(src, r, (int)(i - r * src.S));
+    z[i] = sp.z;
+    pts[i * 3 + 0] = sp.x;
+    pts[i * 3 + 1] = sp.y;
+    pts[i * 3 + 2] = sp.zc;
+    t_dn[i] = sp.t_dn;
+    t_up[i] = sp.t_up;
 }
 
 // g_rays_o[r] = sum_s dp[r,s],  g_rays_d[r] = sum_s dp[r,s] * z[r,s]
@@ -80,8 +58,8 @@ extern "C" int hps_sample_rays(const float* rays_o, const float* rays_d, const f
     HPS_REQUIRE(z_zero_stride == 0 || z_zero_stride >= S, "z_zero_stride must be 0 (shared row) or >= S");
     if (R == 0) return 0;
     HPS_REQUIRE(rays_o && rays_d && gt_depth && z && pts && t_up && t_dn, "null buffer");
-    sample_rays_kernel<<<(unsigned)ceil_div(R * S, 256), 256, 0, (cudaStream_t)stream>>>(
-        rays_o, rays_d, gt_depth, radius, radius_scalar, z_zero, z_zero_stride, R, S, near, far, z, pts, t_up, t_dn);
+    const RaySource src{rays_o, rays_d, gt_depth, radius, radius_scalar, z_zero, z_zero_stride, S, near, far};
+    sample_rays_kernel<<<(unsigned)ceil_div(R * S, 256), 256, 0, (cudaStream_t)stream>>>(src, R, z, pts, t_up, t_dn);
     HPS_LAUNCH_OK();
     return 0;
 }

@@ -40,7 +40,7 @@ def _side_stream(dev, which=0):
 
 # ---- instrumentation: kernel-launch counter and optional CUDA-event timers per C-ABI call -----------
 LAUNCHES = {"n": 0}
-_KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_interp_fwd": 1, "hps_interp_bwd": 1,
+_KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_sample_knn": 1, "hps_interp_fwd": 1, "hps_interp_bwd": 1,
                      "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_mlp_tc_pack": 1, "hps_mlp_tc_fwd": 1,
                      "hps_mlp_tc_bwd_pack": 2, "hps_mlp_tc_bwd": 3, "hps_tc_selftest": 1, "hps_composite_fwd": 1,
                      "hps_composite_bwd": 1, "hps_composite_mapper_loss": 1, "hps_sample_rays": 1, "hps_sample_rays_bwd": 1, "hps_mapper_loss": 1,
@@ -603,13 +603,31 @@ def prepare_rays(grid, rays_o, rays_d, gt_depth, radius, S, near, far, z_zero=No
         pr.D = torch.empty(P, K_NN, **f32)
         pr.cnt = torch.empty(P, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
-        _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t),
-              0.0 if rad_t is not None else float(radius), _lib.ptr(zz), _z_zero_stride(zz, R, S), R, S, float(near),
-              float(far),
-              _lib.ptr(pr.z), _lib.ptr(pr.pts), _lib.ptr(pr.t_up), _lib.ptr(pr.t_dn), _stream())
-        _call("hps_knn_query", grid._h, _lib.ptr(pr.pts), _lib.ptr(pr.t_up), _lib.ptr(pr.t_dn), P, _lib.ptr(pr.I),
-              _lib.ptr(pr.D), _lib.ptr(pr.cnt), None, 5 if (S == 5 and P >= KNN_GROUP_MIN_QUERIES) else 1, _stream())
+        _sample_and_search(grid, ro, rd, gd, rad_t, radius, zz, R, S, near, far, pr.z, pr.pts, pr.t_up, pr.t_dn, pr.I,
+                           pr.D, pr.cnt, _stream())
     return pr
+
+
+# hps_sample_knn (one launch) instead of hps_sample_rays + hps_knn_query: bit-identical, measured 1 % slower on the
+# bench workload (the merged kernel repeats the sampling arithmetic in every lane), so off unless asked for
+SAMPLE_IN_SEARCH = os.environ.get("HPS_SAMPLE_IN_SEARCH", "0") != "0"
+
+
+def _sample_and_search(grid, ro, rd, gd, rad_t, rad, zz, R, S, near, far, z, pts, t_up, t_dn, I, D, cnt, stream):
+    """Sample points + thresholds + exact neighbour search: the sampling kernel, then the search (ray-grouped from
+    KNN_GROUP_MIN_QUERIES queries on); with SAMPLE_IN_SEARCH one launch (the search computes its query points itself)."""
+    P = R * S
+    scalar = 0.0 if rad_t is not None else float(rad)
+    if (S == 5 and P >= KNN_GROUP_MIN_QUERIES) or not SAMPLE_IN_SEARCH:
+        _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t), scalar, _lib.ptr(zz),
+              _z_zero_stride(zz, R, S), R, S, float(near), float(far), _lib.ptr(z), _lib.ptr(pts), _lib.ptr(t_up),
+              _lib.ptr(t_dn), stream)
+        _call("hps_knn_query", grid._h, _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), P, _lib.ptr(I), _lib.ptr(D),
+              _lib.ptr(cnt), None, 5 if (S == 5 and P >= KNN_GROUP_MIN_QUERIES) else 1, stream)
+    else:
+        _call("hps_sample_knn", grid._h, _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t), scalar, _lib.ptr(zz),
+              _z_zero_stride(zz, R, S), R, S, float(near), float(far), _lib.ptr(z), _lib.ptr(pts), _lib.ptr(t_up),
+              _lib.ptr(t_dn), _lib.ptr(I), _lib.ptr(D), _lib.ptr(cnt), None, stream)
 
 
 class RenderSpec:
@@ -822,12 +840,8 @@ class _RenderRays(torch.autograd.Function):
             if mprm and not fork:
                 aff_head(main)
             if prep is None:
-                _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t),
-                      0.0 if rad_t is not None else float(rad), _lib.ptr(zz), _z_zero_stride(zz, R, S), R, S,
-                      float(spec.near), float(spec.far),
-                      _lib.ptr(z), _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), st())
-                _call("hps_knn_query", spec.grid._h, _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), P, _lib.ptr(I),
-                      _lib.ptr(D), _lib.ptr(cnt), None, 5 if (S == 5 and P >= KNN_GROUP_MIN_QUERIES) else 1, st())
+                _sample_and_search(spec.grid, ro, rd, gd, rad_t, rad, zz, R, S, spec.near, spec.far, z, pts, t_up, t_dn,
+                                   I, D, cnt, st())
             if fork and refreshed is not None:
                 main.wait_event(refreshed)
             _call("hps_interp_fwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(D), _lib.ptr(t_dn), _lib.ptr(cnt),

@@ -223,6 +223,12 @@ int hps_exposure_bwd(const float* x, const float* W1, const float* W2, const flo
 int hps_sample_rays(const float* rays_o, const float* rays_d, const float* gt_depth, const double* radius,
                     double radius_scalar, const float* z_zero, int64_t z_zero_stride, int64_t R, int S, float near,
                     float far, float* z, float* pts, float* t_up, float* t_dn, void* stream);
+/* hps_sample_rays + hps_knn_query (group 1) in one launch: the search computes its query points itself and writes
+ * z / pts / t_up / t_dn for the kernels downstream.  Same outputs, bit for bit.                                    */
+int hps_sample_knn(const hps_grid_t* g, const float* rays_o, const float* rays_d, const float* gt_depth,
+                   const double* radius, double radius_scalar, const float* z_zero, int64_t z_zero_stride, int64_t R,
+                   int S, float near, float far, float* z, float* pts, float* t_up, float* t_dn, int32_t* I, float* D,
+                   int32_t* count, int32_t* cand /* may be NULL */, void* stream);
 int hps_sample_rays_bwd(const float* dp, const float* dp2 /* may be NULL */, const float* dp3 /* may be NULL */,
                         const float* z, int64_t R, int S, float* g_rays_o, float* g_rays_d, void* stream);
 

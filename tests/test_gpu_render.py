@@ -680,3 +680,47 @@ def test_render_batch_ray_loss_with_several_keyframes(built):
         assert parity.rel(b[k], a[k]) <= 2e-5, k
     assert max(parity.rel(b["g_mlp"][k], a["g_mlp"][k]) for k in a["g_mlp"]) <= 2e-5
     assert max(parity.rel(b["g_dec"][k], a["g_dec"][k]) for k in a["g_dec"]) <= 2e-5
+
+
+@pytest.mark.parametrize("per_ray_z", [False, True])
+def test_search_that_samples_on_the_fly_is_bit_identical(built, per_ray_z):
+    """hps_sample_knn (the neighbour search computes its query points itself) against hps_sample_rays followed by
+    hps_knn_query: sample depths, points, both thresholds, neighbour indices, distances and counts, bit for bit -
+    with depth-less rays taking a shared z row or one row per ray."""
+    scene, hps, npc, dec, renderer = built
+    L, ops = hps._lib, hps.ops
+    rays, cl = scene["rays"], scene["clouds"]["fine"]
+    ro, rd = rays["rays_o"].to(DEV).contiguous(), rays["rays_d"].to(DEV).contiguous()
+    gd = rays["gt_depth"].to(DEV).clone()
+    gd[::4] = 0.0
+    R, S = ro.shape[0], 5
+    rad = cl["radius"].to(DEV).double().reshape(-1).contiguous()
+    zz = (torch.rand(R, S, device=DEV) * 3 + 0.3).sort(1).values if per_ray_z else torch.linspace(0.3, 4.0, S, device=DEV)
+    grid = npc.get_index("fine").grid_for(rad)
+    f = lambda *s: torch.empty(*s, device=DEV)
+    i32 = lambda *s: torch.empty(*s, device=DEV, dtype=torch.int32)
+    a = dict(z=f(R, S), pts=f(R * S, 3), up=f(R * S), dn=f(R * S), I=i32(R * S, 8), D=f(R * S, 8), n=i32(R * S))
+    b = {k: torch.empty_like(v) for k, v in a.items()}
+    st = ops._stream()
+    ops._call("hps_sample_rays", L.ptr(ro), L.ptr(rd), L.ptr(gd), L.ptr(rad), 0.0, L.ptr(zz), S if per_ray_z else 0, R, S,
+              0.96, 1.04, L.ptr(a["z"]), L.ptr(a["pts"]), L.ptr(a["up"]), L.ptr(a["dn"]), st)
+    ops._call("hps_knn_query", grid._h, L.ptr(a["pts"]), L.ptr(a["up"]), L.ptr(a["dn"]), R * S, L.ptr(a["I"]), L.ptr(a["D"]),
+              L.ptr(a["n"]), None, 1, st)
+    ops._call("hps_sample_knn", grid._h, L.ptr(ro), L.ptr(rd), L.ptr(gd), L.ptr(rad), 0.0, L.ptr(zz), S if per_ray_z else 0,
+              R, S, 0.96, 1.04, L.ptr(b["z"]), L.ptr(b["pts"]), L.ptr(b["up"]), L.ptr(b["dn"]), L.ptr(b["I"]), L.ptr(b["D"]),
+              L.ptr(b["n"]), None, st)
+    torch.cuda.synchronize()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    assert int(a["n"].sum()) > 0
+    # scalar radius form
+    ops._call("hps_sample_rays", L.ptr(ro), L.ptr(rd), L.ptr(gd), None, 0.08, None, 0, R, S, 0.96, 1.04, L.ptr(a["z"]),
+              L.ptr(a["pts"]), L.ptr(a["up"]), L.ptr(a["dn"]), st)
+    ops._call("hps_knn_query", grid._h, L.ptr(a["pts"]), L.ptr(a["up"]), L.ptr(a["dn"]), R * S, L.ptr(a["I"]), L.ptr(a["D"]),
+              L.ptr(a["n"]), None, 1, st)
+    ops._call("hps_sample_knn", grid._h, L.ptr(ro), L.ptr(rd), L.ptr(gd), None, 0.08, None, 0, R, S, 0.96, 1.04,
+              L.ptr(b["z"]), L.ptr(b["pts"]), L.ptr(b["up"]), L.ptr(b["dn"]), L.ptr(b["I"]), L.ptr(b["D"]), L.ptr(b["n"]),
+              None, st)
+    torch.cuda.synchronize()
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
