@@ -201,3 +201,38 @@ def test_gradient_guided_pixel_selection():
     assert bool((sd > 0).all()) and torch.equal(torch.unique(j * W + i), j * W + i)      # sorted, distinct (union1d)
     want_o, want_d = hps.common.get_rays_from_uv(i.float(), j.float(), c2w, H, W, 50.0, 50.0, W / 2, H / 2, "cpu")
     assert torch.equal(rd, want_d) and torch.equal(ro, want_o)
+
+
+def test_loss_buffer_layout_and_frame_checks():
+    """Host-side bookkeeping of the fused losses: accumulator head sizes and the (affine, frame index) validation."""
+    assert ops._loss_head_floats(0) == 16 and ops._loss_head_floats(12) == 16
+    assert ops._loss_head_floats(13) == 32 and ops._loss_head_floats(12 * 5) == 64
+    aff1, aff3 = torch.zeros(12), torch.zeros(3, 12)
+    assert ops._loss_frames(None, None, 10) == (None, 0)
+    assert ops._loss_frames(aff1, None, 10) == (None, 12)
+    frm, n = ops._loss_frames(aff3, torch.tensor([0, 1, 2, 2]), 4)
+    assert frm.dtype == torch.int32 and n == 36
+    with pytest.raises(ValueError):
+        ops._loss_frames(aff3, None, 4)                       # several affines need a frame index
+    with pytest.raises(ValueError):
+        ops._loss_frames(aff3, torch.tensor([0, 1]), 4)       # one entry per ray
+    with pytest.raises(ValueError):
+        ops._loss_frames(torch.zeros(13), None, 4)
+
+
+def test_z_rows_for_depthless_rays_are_validated():
+    assert ops._z_zero_stride(None, 7, 5) == 0
+    assert ops._z_zero_stride(torch.zeros(5), 7, 5) == 0
+    assert ops._z_zero_stride(torch.zeros(7, 5), 7, 5) == 5
+    with pytest.raises(ValueError):
+        ops._z_zero_stride(torch.zeros(4), 7, 5)
+    with pytest.raises(ValueError):
+        ops._z_zero_stride(torch.zeros(6, 5), 7, 5)
+
+
+def test_mapper_loss_spec_modes():
+    with pytest.raises(ValueError):
+        ops.MapperLossSpec(None, 0.1, exposure="latent")
+    s = ops.MapperLossSpec(None, 0.1, "affine", torch.zeros(3, dtype=torch.int64))
+    assert s.exposure == "affine" and s.w_color == pytest.approx(0.1)
+    assert ops.TrackerLossSpec(None, 0.5).zero_missing is False
