@@ -57,6 +57,7 @@ SIGNATURES = {
     "hps_sample_knn": (_i32, [_vp, _vp, _vp, _vp, _vp, ctypes.c_double, _vp, _i64, _i64, _i32, _f32, _f32] + [_vp] * 9),
     "hps_sample_rays_bwd": (_i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "hps_adam_multi": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _vp, _i32, _vp]),
+    "hps_adam_multi_own_steps": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _vp, _i32, _vp]),
     "hps_mapper_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "hps_tracker_loss_stats": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
     "hps_tracker_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _f32, _i64, _vp, _vp, _vp, _vp]),

@@ -7,6 +7,14 @@ a full reference cfg dict can be passed to every class instead.
 """
 import copy
 
+# configs/point_slam.yaml:105-146 (the `init` and `stage` tables hold the same numbers)
+_STAGE_LRS = {
+    "geometry_mid": {"decoders_lr": 0.001, "geometry_mid_lr": 0.03, "geometry_fine_lr": 0.03, "color_lr": 0.0},
+    "geometry_fine": {"decoders_lr": 0.001, "geometry_mid_lr": 0.03, "geometry_fine_lr": 0.03, "color_lr": 0.0},
+    "color_mid": {"decoders_lr": 0.005, "geometry_mid_lr": 0.005, "geometry_fine_lr": 0.005, "color_lr": 0.005},
+    "color_fine": {"decoders_lr": 0.005, "geometry_mid_lr": 0.005, "geometry_fine_lr": 0.005, "color_lr": 0.005},
+}
+
 _SCANNET = {
     "occupancy": True,
     "use_normals": False,
@@ -31,7 +39,11 @@ _SCANNET = {
                   "skip_zero_depth_pixel": False},
     "cam": {"H": 480, "W": 640, "fx": 577.590698, "fy": 578.729797, "cx": 318.905426, "cy": 242.683609,
             "crop_edge": 10},
-    "mapping": {"device": "cuda:0", "w_color_loss": 0.1, "pixels": 10000, "iters": 600, "BA": False},
+    "mapping": {"device": "cuda:0", "w_color_loss": 0.1, "pixels": 10000, "iters": 600, "iters_first": 500, "BA": False,
+                "BA_cam_lr": 0.0002, "geo_iter_ratio": 0.3, "mid_iter_ratio": 0.5, "geo_iter_first": 200,
+                "min_iter_ratio": 0.95, "fix_geo_decoder_mid": True, "fix_geo_decoder_fine": True,
+                "fix_color_decoder": False, "frustum_feature_selection": True, "color_refine": False,
+                "init": _STAGE_LRS, "stage": _STAGE_LRS},
     "tracking": {"device": "cuda:0", "w_color_loss": 0.5, "pixels": 5000, "iters": 100, "lr": 0.0005,
                  "handle_dynamic": True, "use_color_in_tracking": True},
 }

@@ -101,6 +101,47 @@ adam_multi_kernel(const AdamPack pk, float b1, float b2, float eps, int* __restr
     }
 }
 
+// adam_multi with ONE STEP COUNTER PER TENSOR - torch.optim.Adam keeps `state[p]['step']` per parameter and skips
+// parameters whose gradient is None, so in the mapper (src/Mapper.py:592-603, 637-660: one optimiser over all four
+// decoders, four feature tables, poses and the exposure latent, of which a stage touches only some) every tensor has its
+// own bias correction.  steps[i] points at that tensor's counter; `done` is a scratch word (0 between launches).
+struct AdamStepPack {
+    int* step[kAdamMaxTensors];
+};
+
+__global__ void __launch_bounds__(256)
+adam_multi_own_steps_kernel(const AdamPack pk, const AdamStepPack sp, float b1, float b2, float eps,
+                            int* __restrict__ done_word, int zero_grad) {
+    int ti = 0;
+    while (ti + 1 < pk.count && (int)blockIdx.x >= pk.block_begin[ti + 1]) ++ti;
+    const int t = *sp.step[ti] + 1;
+    const float bc1 = 1.0f - powf(b1, (float)t), bc2 = 1.0f - powf(b2, (float)t);
+    const float inv_sqrt_bc2 = 1.0f / sqrtf(bc2);
+    const int i = ((int)blockIdx.x - pk.block_begin[ti]) * blockDim.x + threadIdx.x;
+    if (i < pk.n[ti]) {
+        const float gr = pk.g[ti][i];
+        const float mm = pk.m[ti][i] + (gr - pk.m[ti][i]) * (1.0f - b1);
+        const float vv = pk.v[ti][i] * b2 + (1.0f - b2) * gr * gr;
+        const float denom = sqrtf(vv) * inv_sqrt_bc2 + eps;
+        pk.m[ti][i] = mm;
+        pk.v[ti][i] = vv;
+        pk.p[ti][i] = pk.p[ti][i] - (pk.lr[ti] / bc1) * (mm / denom);
+        if (zero_grad) pk.g[ti][i] = 0.f;
+    }
+    // the last block to finish advances every counter of the launch (all blocks have read theirs by then)
+    __shared__ int last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = (atomicAdd(done_word, 1) + 1 == (int)gridDim.x);
+    }
+    __syncthreads();
+    if (last) {
+        if ((int)threadIdx.x < pk.count) *sp.step[threadIdx.x] += 1;
+        if (threadIdx.x == 0) *done_word = 0;
+    }
+}
+
 }  // namespace hps
 
 extern "C" int hps_adam_multi(int n_tensors, float* const* params, float* const* grads, float* const* exp_avg,
@@ -142,6 +183,38 @@ extern "C" int hps_adam_rows(float* param, const float* grad, float* exp_avg, fl
     const int64_t n4 = M * (C / 4);
     adam_rows_kernel<<<(unsigned)ceil_div(n4, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n4,
                                                                                 C / 4, lr, beta1, beta2, eps, step, table, rows);
+    HPS_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int hps_adam_multi_own_steps(int n_tensors, float* const* params, float* const* grads, float* const* exp_avg,
+                                        float* const* exp_avg_sq, const int64_t* numel, const float* lr,
+                                        int32_t* const* steps, float beta1, float beta2, float eps, int32_t* done_word,
+                                        int zero_grad, void* stream) {
+    using namespace hps;
+    HPS_REQUIRE(n_tensors >= 0 && n_tensors <= kAdamMaxTensors, "at most 24 tensors per call");
+    if (n_tensors == 0) return 0;
+    HPS_REQUIRE(params && grads && exp_avg && exp_avg_sq && numel && lr && steps && done_word, "null buffer");
+    AdamPack pk;
+    AdamStepPack sp;
+    pk.count = n_tensors;
+    int blocks = 0;
+    for (int i = 0; i < n_tensors; ++i) {
+        HPS_REQUIRE(params[i] && grads[i] && exp_avg[i] && exp_avg_sq[i] && steps[i], "null tensor pointer");
+        HPS_REQUIRE(numel[i] > 0 && numel[i] < (1ll << 24), "tensor size out of range for the small-tensor Adam");
+        for (int j = 0; j < i; ++j) HPS_REQUIRE(steps[j] != steps[i], "two tensors share a step counter");
+        pk.p[i] = params[i];
+        pk.g[i] = grads[i];
+        pk.m[i] = exp_avg[i];
+        pk.v[i] = exp_avg_sq[i];
+        pk.lr[i] = lr[i];
+        pk.n[i] = (int)numel[i];
+        pk.block_begin[i] = blocks;
+        sp.step[i] = steps[i];
+        blocks += (int)ceil_div(numel[i], 256);
+    }
+    pk.block_begin[n_tensors] = blocks;
+    adam_multi_own_steps_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(pk, sp, beta1, beta2, eps, done_word, zero_grad);
     HPS_LAUNCH_OK();
     return 0;
 }

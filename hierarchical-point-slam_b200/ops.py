@@ -1057,8 +1057,19 @@ class RowAdam:
     per-iteration `table[indices] = rows` (Mapper.py:615-630, 859, 862-874).  `groups`: list of (LiveRows, lr).
     The step counter is a device tensor, so step() can be captured in a CUDA graph with the iteration."""
 
+    class _Dense:
+        """A whole (N,C) table as the leaf (first mapped frame / frustum_feature_selection off, Mapper.py:538-556):
+        no separate table to write back into."""
+        table = indices = None
+
+        def __init__(self, param):
+            _need_cuda(param)
+            if param.dim() != 2 or param.shape[1] % 4 or param.dtype != torch.float32 or not param.is_contiguous():
+                raise _lib.HpsError("RowAdam takes LiveRows or a contiguous fp32 (N,C) leaf with C % 4 == 0")
+            self.param, self.fresh = param, False
+
     def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8):
-        self.groups = [[lr_rows, float(lr)] for lr_rows, lr in groups]
+        self.groups = [[self._Dense(r) if torch.is_tensor(r) else r, float(lr)] for r, lr in groups]
         self.betas, self.eps = betas, float(eps)
         self.state = []
         for rows, _ in self.groups:
@@ -1085,7 +1096,7 @@ class RowAdam:
                 _call("hps_adam_rows", _lib.ptr(p), _lib.ptr(g), _lib.ptr(st["m"]), _lib.ptr(st["v"]), p.shape[0], p.shape[1],
                       lr, float(self.betas[0]), float(self.betas[1]), self.eps, _lib.ptr(st["step"]), _lib.ptr(rows.table),
                       _lib.ptr(rows.indices), _stream())
-            rows.fresh = True
+            rows.fresh = rows.table is not None
 
 
 class FusedAdam:
@@ -1098,12 +1109,16 @@ class FusedAdam:
     zero_grad() sets the gradients to None, so that backward hands its buffers over instead of adding into ours -
     one small kernel less per parameter; inside a CUDA graph the buffers keep their addresses.
     Device step counter (one per launch of up to 24 tensors, so a parameter that sits out an iteration shares the
-    bias correction of the others): capturable."""
+    bias correction of the others): capturable.
+    per_tensor_steps=True: one device counter per tensor instead, exactly torch.optim.Adam's `state[p]['step']` - what
+    the mapper's optimiser needs, whose parameter list holds all four decoders although a stage gives gradients to
+    one or two of them (Mapper.py:555-569, 592-603); use it with own_grads=False (tensors without .grad sit out)."""
 
     MAX = 24
 
-    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8, own_grads=True):
+    def __init__(self, groups, betas=(0.9, 0.999), eps=1e-8, own_grads=True, per_tensor_steps=False):
         self.own_grads = bool(own_grads)
+        self.per_tensor_steps = bool(per_tensor_steps)
         self.params, self.lrs = [], []
         for tensors, lr in groups:
             for t in ([tensors] if torch.is_tensor(tensors) else list(tensors)):
@@ -1127,6 +1142,8 @@ class FusedAdam:
             off += n
         n_chunks = (len(self.params) + self.MAX - 1) // self.MAX
         self.step_count = torch.zeros(n_chunks, 2, dtype=torch.int32, device=dev)     # one counter per launch
+        # per_tensor_steps: one counter per tensor; column 1 of step_count row c is launch c's scratch word
+        self.tensor_steps = torch.zeros(len(self.params), dtype=torch.int32, device=dev) if self.per_tensor_steps else None
 
     def set_lr(self, index, lr):
         self.lrs[index] = float(lr)
@@ -1142,8 +1159,8 @@ class FusedAdam:
 
     @torch.no_grad()
     def step(self):
-        ps, gs, ms, vs, lr_of = [], [], [], [], []
-        for p, (g, m, v), lr in zip(self.params, self._views, self.lrs):
+        ps, gs, ms, vs, lr_of, which = [], [], [], [], [], []
+        for k, (p, (g, m, v), lr) in enumerate(zip(self.params, self._views, self.lrs)):
             if self.own_grads:
                 if p.grad is None or p.grad.data_ptr() != g.data_ptr():
                     raise _lib.HpsError("FusedAdam: a .grad was replaced; keep the buffers (or use own_grads=False)")
@@ -1153,7 +1170,7 @@ class FusedAdam:
                 g = p.grad
                 if g.dtype != torch.float32 or not g.is_contiguous():
                     g = p.grad = g.float().contiguous()
-            ps.append(p); gs.append(g); ms.append(m); vs.append(v); lr_of.append(lr)
+            ps.append(p); gs.append(g); ms.append(m); vs.append(v); lr_of.append(lr); which.append(k)
         if not ps:
             return
         dev = self.params[0].device
@@ -1164,6 +1181,14 @@ class FusedAdam:
                 numel = (ctypes.c_int64 * n)(*[p.numel() for p in ps[s:e]])
                 lrs = (ctypes.c_float * n)(*lr_of[s:e])
                 arrs = [(ctypes.c_void_p * n)(*[t.data_ptr() for t in ts[s:e]]) for ts in (ps, gs, ms, vs)]
+                if self.per_tensor_steps:
+                    base = self.tensor_steps.data_ptr()
+                    steps = (ctypes.c_void_p * n)(*[base + 4 * k for k in which[s:e]])
+                    _call("hps_adam_multi_own_steps", n, arrs[0], arrs[1], arrs[2], arrs[3], numel, lrs, steps,
+                          float(self.betas[0]), float(self.betas[1]), self.eps,
+                          ctypes.c_void_p(self.step_count.data_ptr() + 4 * (2 * (s // self.MAX) + 1)),
+                          1 if self.own_grads else 0, _stream())
+                    continue
                 _call("hps_adam_multi", n, arrs[0], arrs[1], arrs[2], arrs[3], numel, lrs, float(self.betas[0]),
                       float(self.betas[1]), self.eps, _lib.ptr(self.step_count[s // self.MAX]),
                       1 if self.own_grads else 0, _stream())

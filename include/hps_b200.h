@@ -198,6 +198,14 @@ int hps_adam_rows(float* param, const float* grad, float* exp_avg, float* exp_av
 int hps_adam_multi(int n_tensors, float* const* params, float* const* grads, float* const* exp_avg,
                    float* const* exp_avg_sq, const int64_t* numel, const float* lr, float beta1, float beta2,
                    float eps, int32_t* step, int zero_grad, void* stream);
+/* hps_adam_multi with one step counter PER TENSOR: torch.optim.Adam keeps state[p]['step'] per parameter and skips
+ * parameters whose .grad is None, which matters for the mapper's single optimiser over all decoders, feature tables,
+ * poses and the exposure latent (Mapper.py:592-603; a stage gives gradients to only some of them, :637-660).
+ * steps: HOST array of n_tensors device pointers, each to one int32 counter (distinct);  done_word: one device int32
+ * of scratch that is 0 between launches.  Replayable from a CUDA graph.                                           */
+int hps_adam_multi_own_steps(int n_tensors, float* const* params, float* const* grads, float* const* exp_avg,
+                             float* const* exp_avg_sq, const int64_t* numel, const float* lr, int32_t* const* steps,
+                             float beta1, float beta2, float eps, int32_t* done_word, int zero_grad, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Exposure MLP (decoder.py:380-396 MLP_exposure: linear1 -> Softplus(beta=100) -> linear2) on one latent

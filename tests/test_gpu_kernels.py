@@ -571,3 +571,83 @@ def test_fused_adam_on_handed_over_gradients(hps):
     assert all(p.grad is None for p in mine)
     opt.step()                                                       # nothing to do, no launch
     assert int(opt.step_count[0, 0]) == 5
+
+
+def test_mapper_optimizer_follows_torch_adam_through_the_stages(hps):
+    """MapperOptimizer (RowAdam per feature table + FusedAdam with per-tensor step counters for decoders / poses /
+    exposure latent) vs the reference's construction: ONE torch.optim.Adam over the seven groups of Mapper.py:592-603
+    whose learning rates are rewritten per iteration (:637-667).  A stage gives gradients to some tensors only; torch
+    skips the others and keeps their own step counts - so must we (51 small tensors; a colour stage touches 27 of them = two launches, whose
+    make-up changes with the stage)."""
+    torch.manual_seed(21)
+    mo = hps.mapper_optim
+    cfg = hps.scannet_cfg()["mapping"]
+    N, M, C = 900, 130, 32
+    shapes = [(32, 96), (32,), (32, 32), (32,), (4, 32), (4,), (128, 40), (128,), (128, 168), (128,), (3, 128), (3,),
+              (40, 3), (5, 7), (9,), (32, 32), (32,), (128, 128), (128,), (128, 128), (128,), (1, 300), (2,), (257,)]
+    dec_mid = [torch.randn(s, device=DEV).requires_grad_(True) for s in shapes]
+    dec_fine = [torch.randn(s, device=DEV).requires_grad_(True) for s in shapes]
+    cams = [torch.randn(7, device=DEV).requires_grad_(True) for _ in range(2)]
+    expo = torch.randn(8, device=DEV).requires_grad_(True)
+    tab = {k: torch.randn(N, C, device=DEV) * 0.1 for k in mo.MapperOptimizer.ROW_KEYS}
+    idx = torch.randperm(N, device=DEV)[:M]
+    g_mid, c_mid = hps.LiveRows.pair(tab["geometry_mid"].clone(), tab["color_mid"].clone(), idx)   # selected rows
+    g_fine = tab["geometry_fine"].clone().requires_grad_(True)                                    # whole tables
+    c_fine = tab["color_fine"].clone().requires_grad_(True)
+    rows = {"geometry_mid": g_mid, "color_mid": c_mid, "geometry_fine": g_fine, "color_fine": c_fine}
+    opt = mo.MapperOptimizer(cfg, decoder_params=dec_mid + dec_fine, rows=rows, cameras=cams, exposure_feat=expo)
+    assert len(opt.small_opt.params) == 51 and opt.small_opt.step_count.shape[0] == 3
+
+    leaf = {"geometry_mid": g_mid.param, "color_mid": c_mid.param, "geometry_fine": g_fine, "color_fine": c_fine}
+    mine = dec_mid + dec_fine + [leaf[k] for k in mo.MapperOptimizer.ROW_KEYS] + cams + [expo]
+    ref = [p.detach().clone().requires_grad_(True) for p in mine]
+    nd = 2 * len(shapes)
+    topt = torch.optim.Adam([{"params": ref[:nd], "lr": 0}, {"params": [ref[nd]], "lr": 0},
+                             {"params": [ref[nd + 1]], "lr": 0}, {"params": [ref[nd + 2]], "lr": 0},
+                             {"params": [ref[nd + 3]], "lr": 0}, {"params": ref[nd + 4:nd + 6], "lr": 0},
+                             {"params": [ref[nd + 6]], "lr": 0.001}])
+    # which tensors a stage gives gradients to (positions in `mine`)
+    ns = len(shapes)
+    touched = {"geometry_mid": list(range(0, 6)) + [nd],
+               "color_mid": list(range(0, ns)) + [nd, nd + 2, nd + 4, nd + 5, nd + 6],
+               "geometry_fine": list(range(ns, ns + 6)) + [nd + 1],
+               "color_fine": list(range(ns, 2 * ns)) + [nd + 1, nd + 3, nd + 4, nd + 5, nd + 6]}
+    n_iters, seen = 24, set()
+    expect_steps = [0] * len(mine)
+    for j in range(n_iters):
+        stage = opt.set_iteration(j, n_iters, BA=True)
+        seen.add(stage)
+        lr = mo.stage_learning_rates(cfg, stage)
+        cam_lr = mo.ba_camera_lr(j, n_iters, cfg["mid_iter_ratio"], cfg["geo_iter_ratio"], cfg["BA_cam_lr"])
+        for grp, v in zip(topt.param_groups[:6], [lr["decoders"], lr["geometry_mid"], lr["geometry_fine"],
+                                                  lr["color_mid"], lr["color_fine"], cam_lr]):
+            grp["lr"] = v
+        opt.zero_grad()
+        topt.zero_grad()
+        assert all(p.grad is None for p in mine)
+        for k in touched[stage]:
+            g = torch.randn(mine[k].shape, device=DEV) * (10.0 ** (-(j + k) % 3))
+            mine[k].grad = g.clone()
+            ref[k].grad = g.clone()
+            expect_steps[k] += 1
+        opt.step()
+        topt.step()
+        for k, (a, b) in enumerate(zip(mine, ref)):
+            err = float((a.detach() - b.detach()).abs().max())
+            assert err <= 1e-5 * max(1.0, float(b.detach().abs().max())), (j, stage, k, err)
+    assert seen == set(mo.STAGES)
+    torch.cuda.synchronize()
+    # per-tensor step counters = torch's state[p]['step'];  scratch words back to zero
+    small = opt.small_opt
+    pos = {id(p): k for k, p in enumerate(mine)}
+    for p, st in zip(small.params, small.tensor_steps.tolist()):
+        assert st == expect_steps[pos[id(p)]] == int(topt.state[ref[pos[id(p)]]]["step"]), (pos[id(p)], st)
+    assert small.step_count.abs().sum().item() == 0
+    # live rows were written back into their tables, the other rows left alone
+    for r, key in ((g_mid, "geometry_mid"), (c_mid, "color_mid")):
+        assert torch.equal(r.table[idx], r.param.detach())
+        other = torch.ones(N, dtype=torch.bool, device=DEV)
+        other[idx] = False
+        assert torch.equal(r.table[other], tab[key][other])
+    with pytest.raises(ValueError):
+        mo.MapperOptimizer(cfg, rows={"geometry_coarse": g_fine})

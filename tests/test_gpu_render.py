@@ -335,7 +335,8 @@ def test_frustum_rows_matches_oracle(built):
         assert len(diff) <= 1e-3 * len(ref)
 
 
-def test_mapper_loop_five_iterations_tracks_the_oracle(hps):
+@pytest.mark.parametrize("optimiser", ["rows+torch", "mapper"])
+def test_mapper_loop_five_iterations_tracks_the_oracle(hps, optimiser):
     """Five mapper iterations end to end (Mapper.py:783-874): frustum-selected live rows + RowAdam on the rows, Adam on
     the two fine decoders, vs the CPU oracle driven by torch.optim.Adam on dense tables.  The loss trajectory and the
     final feature rows must agree (fp32 rounding compounds over the steps: 2e-3 on the rows, 1e-3 on the losses)."""
@@ -355,8 +356,16 @@ def test_mapper_loop_five_iterations_tracks_the_oracle(hps):
     gf = {l: (lg if l == level else npc.get_geo_feats(l)) for l in cl}
     cf = {l: (lc if l == level else npc.get_col_feats(l)) for l in cl}
     dparams = list(dec.geo_decoder_fine.parameters()) + list(dec.color_decoder_fine.parameters())
-    opt_rows = hpsm.RowAdam([(lg, lr_rows), (lc, lr_rows)])
-    opt_dec = torch.optim.Adam(dparams, lr=lr_dec)
+    if optimiser == "mapper":      # the whole optimiser on this package's kernels (decoders through FusedAdam)
+        opt_rows = hpsm.MapperOptimizer(hpsm.scannet_cfg(DEV)["mapping"], decoder_params=dparams,
+                                        rows={"geometry_fine": lg, "color_fine": lc})
+        opt_rows.set_learning_rates({"decoders": lr_dec, "geometry_mid": 0.0, "geometry_fine": lr_rows,
+                                     "color_mid": 0.0, "color_fine": lr_rows})
+        import types
+        opt_dec = types.SimpleNamespace(zero_grad=lambda: None, step=lambda: None)     # opt_rows does both
+    else:
+        opt_rows = hpsm.RowAdam([(lg, lr_rows), (lc, lr_rows)])
+        opt_dec = torch.optim.Adam(dparams, lr=lr_dec)
     ef = scene["exposure_feat"].to(DEV)
     gt_d, gt_c = rays["gt_depth"].to(DEV), rays["gt_color"].to(DEV)
     losses = []

@@ -236,3 +236,38 @@ def test_mapper_loss_spec_modes():
     s = ops.MapperLossSpec(None, 0.1, "affine", torch.zeros(3, dtype=torch.int64))
     assert s.exposure == "affine" and s.w_color == pytest.approx(0.1)
     assert ops.TrackerLossSpec(None, 0.5).zero_missing is False
+
+
+def test_mapper_schedule_matches_the_reference_statements():
+    """mapper_optim's stage selection, learning rates, BA pose learning rate and iteration counts against the fixture
+    made by EXECUTING Mapper.py:605-612 and :633-666 of the reference (oracle/make_golden_schedule.py)."""
+    import json
+    import os
+    GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    mo = hps.mapper_optim
+    with open(os.path.join(GOLDEN, "mapper_schedule.json")) as f:
+        gold = json.load(f)
+    ref_cfg = gold["mapping_cfg"]
+    mine = hps.scannet_cfg()["mapping"]
+    for k, v in ref_cfg.items():                    # config.py carries the reference's merged yaml numbers
+        assert mine[k] == v, k
+    for case in gold["cases"]:
+        n = case["num_joint_iters_in"]
+        if case["more_iters_when_adding"] and case["idx"] > 0 and not case["color_refine"]:
+            n = mo.joint_iters_when_adding(n, case["frame_pts_add"], ref_cfg["min_iter_ratio"])
+        assert n == case["num_joint_iters"]
+        assert mo.split_iters(n, case["mid_iter_ratio"]) == (case["num_mid_iters"], case["num_fine_iters"])
+        last = case["idx"] == case["n_img"] - 1 and case["color_refine"]
+        covered = 0
+        for first, count, stage, *lrs in case["rows"]:
+            for j in range(first, first + count):
+                st = mo.mapper_stage(j, n, case["mid_iter_ratio"], case["geo_iter_ratio"], case["init"],
+                                     ref_cfg["geo_iter_first"])
+                assert st == stage, (j, st, stage)
+                lr = mo.stage_learning_rates(ref_cfg, st, case["init"], last)
+                got = [lr["decoders"], lr["geometry_mid"], lr["geometry_fine"], lr["color_mid"], lr["color_fine"]]
+                cam = mo.ba_camera_lr(j, n, case["mid_iter_ratio"], case["geo_iter_ratio"], ref_cfg["BA_cam_lr"]) \
+                    if case["BA"] else 0.0
+                assert got + [cam] == lrs, (j, got, cam, lrs)
+            covered += count
+        assert covered == n
