@@ -18,6 +18,7 @@ import synthetic as O  # noqa: E402  (scene generator; the oracle is not used he
 
 hps = importlib.import_module("hierarchical-point-slam_b200")
 dev = "cuda:0"
+SECTIONS = set(sys.argv[1:]) or {"a", "a2", "b", "c"}      # e.g. `python scripts/extra_workloads.py a2`
 K = O.SCANNET_INTRINSICS
 
 
@@ -63,7 +64,7 @@ gt_d, gt_c = fine["gt_depth"][:R].to(dev), fine["gt_color"][:R].to(dev)
 rq_t = {"fine": fine["radius"][:R].to(dev), "mid": scene["radius_mid"][:R].to(dev)}
 for prm in dec.parameters():          # the tracker optimises the pose and the exposure latent only (Tracker.py:190-235)
     prm.requires_grad_(False)
-for stage in ("color_mid", "color_fine"):
+for stage in (("color_mid", "color_fine") if "a" in SECTIONS else ()):
     cam = torch.tensor([1.0, 0.0, 0.0, 0.0, 0.005, -0.004, 0.003], device=dev).requires_grad_(True)   # ~1 cm off
     ef = scene["exposure_feat"].to(dev).clone().requires_grad_(True)
     opt = torch.optim.Adam([cam, ef], lr=5e-4, capturable=True)
@@ -101,46 +102,73 @@ for stage in ("color_mid", "color_fine"):
         print("  %-10s graph capture failed: %s" % (stage, str(e).splitlines()[0][:150]))
 
 # ------------------------------------------------------------------ (a2) mapper iteration including the optimiser
-print("== (a2) mapper iteration INCLUDING the optimiser step (RowAdam on the live rows, fused torch Adam on the decoders)")
+print("== (a2) mapper iteration INCLUDING the optimiser step, stage color_fine, fused render+loss call")
 for prm in dec.parameters():
     prm.requires_grad_(True)
 Kc = cfg["cam"]
-pf = npc.cloud_pos_tensor("fine")
+used = list(dec.geo_decoder_fine.parameters()) + list(dec.color_decoder_fine.parameters())
+ro_m, rd_m = fine["rays_o"][:R].to(dev), fine["rays_d"][:R].to(dev)
 live_idx = npc.frustum_rows("fine", torch.eye(4, device=dev), O.synthetic_depth().to(dev), Kc["H"], Kc["W"], Kc["fx"],
                             Kc["fy"], Kc["cx"], Kc["cy"], -20)
-lg, lc = hps.LiveRows.pair(npc.get_geo_feats("fine"), npc.get_col_feats("fine"), live_idx)
-gfm = {"fine": lg, "mid": npc.get_geo_feats("mid")}
-cfm = {"fine": lc, "mid": npc.get_col_feats("mid")}
-used = list(dec.geo_decoder_fine.parameters()) + list(dec.color_decoder_fine.parameters())
-opt_rows = hps.RowAdam([(lg, 5e-3), (lc, 5e-3)])
-opt_dec = torch.optim.Adam(used, lr=1e-3, fused=True, capturable=True)
-ro_m, rd_m = fine["rays_o"][:R].to(dev), fine["rays_d"][:R].to(dev)
-ef_m = scene["exposure_feat"].to(dev)
+table0 = (npc.get_geo_feats("fine").clone(), npc.get_col_feats("fine").clone())
+dec0 = [p.detach().clone() for p in used]
 
 
-def mapper_it():
-    opt_rows.zero_grad()
-    opt_dec.zero_grad(set_to_none=True)
-    d, v, c, m = renderer.render_batch_ray(npc, dec, rd_m, ro_m, dev, "color_fine", gt_depth=gt_d, npc_geo_feats=gfm,
-                                           npc_col_feats=cfm, dynamic_r_query=dict(rq_t), cloud_pos=pos)
-    aff = dec.color_decoder_fine.mlp_exposure(ef_m)
-    loss = hps.mapper_loss(d, c, m, gt_d, gt_c, "color_fine", 0.1, aff)
-    loss.backward()
-    opt_rows.step()
-    opt_dec.step()
-    return loss
+def mapper_variant(which):
+    with torch.no_grad():                         # every variant starts from the same tables and decoders
+        npc.get_geo_feats("fine").copy_(table0[0])
+        npc.get_col_feats("fine").copy_(table0[1])
+        for p, q in zip(used, dec0):
+            p.copy_(q)
+            p.grad = None
+    lg, lc = hps.LiveRows.pair(npc.get_geo_feats("fine"), npc.get_col_feats("fine"), live_idx)
+    gfm = {"fine": lg, "mid": npc.get_geo_feats("mid")}
+    cfm = {"fine": lc, "mid": npc.get_col_feats("mid")}
+    ef_m = scene["exposure_feat"].to(dev).clone().requires_grad_(True)
+    if which == "none":
+        opts = []
+    elif which == "RowAdam + torch fused Adam":
+        opts = [hps.RowAdam([(lg, 5e-3), (lc, 5e-3)]),
+                torch.optim.Adam([{"params": used, "lr": 5e-3}, {"params": [ef_m], "lr": 1e-3}], fused=True,
+                                 capturable=True)]
+    else:                                         # everything on this package's kernels (Mapper.py:592-603, 646-660)
+        mo = hps.MapperOptimizer(cfg["mapping"], decoder_params=used, rows={"geometry_fine": lg, "color_fine": lc},
+                                 exposure_feat=ef_m)
+        mo.set_learning_rates(hps.mapper_optim.stage_learning_rates(cfg["mapping"], "color_fine"))
+        opts = [mo]
+
+    def mapper_it():
+        for o in opts:
+            o.zero_grad()
+        if not opts:
+            for t in used + [lg.param, lc.param, ef_m]:
+                t.grad = None
+        loss = renderer.render_batch_ray_loss(npc, dec, rd_m, ro_m, dev, "color_fine", gt_d, gt_c, 0.1, npc_geo_feats=gfm,
+                                              npc_col_feats=cfm, cloud_pos=pos, dynamic_r_query=dict(rq_t),
+                                              exposure_feat=ef_m)[0]
+        loss.backward()
+        for o in opts:
+            o.step()
+        return loss
+
+    try:
+        gm = hps.graphs.GraphedStep(mapper_it, {}, warmup=3)
+        traj = []                                  # loss after replay 1, 2, 5, 10, 20, 50 (iterations 4 .. 53)
+        for k in range(1, 51):
+            gm()
+            if k in (1, 2, 5, 10, 20, 50):
+                traj.append(float(gm.outputs.detach()))
+        g_ms, w_ms = timed(lambda: gm(), 200)
+        print("  %-28s: %.4f ms / iteration (GPU events) -> %.0f iterations/s = %.2f M rays/s; %d live rows; loss at "
+              "iteration 4/5/8/13/23/53: %s" % (which, g_ms, 1e3 / w_ms, R / w_ms / 1e3, live_idx.numel(),
+                                                " ".join("%.3f" % t for t in traj)))
+    except Exception as e:   # noqa: BLE001
+        print("  %s: graph capture failed: %s" % (which, str(e).splitlines()[0][:200]))
 
 
-try:
-    gm = hps.graphs.GraphedStep(mapper_it, {}, warmup=3)
-    g_ms, w_ms = timed(lambda: gm(), 100)
-    l0 = float(gm.outputs)
-    for _ in range(50):
-        gm()
-    print("  graph : %.3f ms / iteration -> %.0f iterations/s = %.1f M rays/s; %d live rows; loss %.1f -> %.1f after 150 more steps"
-          % (g_ms, 1e3 / w_ms, R / w_ms / 1e3, live_idx.numel(), l0, float(gm.outputs)))
-except Exception as e:   # noqa: BLE001
-    print("  graph capture failed: %s" % str(e).splitlines()[0][:200])
+if "a2" in SECTIONS:
+    for which in ("none", "RowAdam + torch fused Adam", "MapperOptimizer"):
+        mapper_variant(which)
 
 # ------------------------------------------------------------------ (b) full-frame render
 print("== (b) full-frame render_img, 640x480 = 307,200 rays x 5 samples, no_grad")
@@ -150,7 +178,7 @@ rad_maps = {"fine": (0.04 + 0.12 * torch.rand(K["H"], K["W"], generator=g, dtype
             "mid": (0.24 + 0.72 * torch.rand(K["H"], K["W"], generator=g, dtype=torch.float64)).to(dev)}
 c2w = torch.eye(4, device=dev)
 ef0 = scene["exposure_feat"].to(dev)
-for B in (3000, 65536):
+for B in ((3000, 65536) if "b" in SECTIONS else ()):
     renderer.ray_batch_size = B
     renderer.min_render_chunk = B        # (the default widens chunks to 65536 rays; 3000 = the reference's chunking)
     for stage in ("color_mid", "color_fine"):
@@ -172,7 +200,7 @@ rad = rad_maps["fine"].reshape(-1).repeat_interleave(5)
 t_up, t_dn = hps.ops.radius_thresholds(rad, q.shape[0], dev)
 del npc, gf, cf, pos
 torch.cuda.empty_cache()
-for n_m in (1, 2, 4, 8):
+for n_m in ((1, 2, 4, 8) if "c" in SECTIONS else ()):
     sc = O.synthetic_scene(n_m * 1_000_000, 8, (0.04, 0.16), seed=7, extent_scale=bench.EXTENT * n_m ** 0.5)
     idx = hps.GridIndex(dev)
     pts = sc["points"].to(dev)
