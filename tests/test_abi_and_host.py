@@ -80,3 +80,56 @@ def test_unsupported_modes_fail_loudly(hps):
     cfg["pointcloud"]["nn_weighting"] = "expo"
     with pytest.raises(NotImplementedError):
         hps.get_model(cfg)
+
+
+def test_c_abi_empty_inputs_and_argument_checks_without_a_gpu(hps):
+    """The C ABI's contract for empty and malformed calls, exercised here because it needs no device: a call over zero
+    rays / points / queries / tensors returns 0 before it touches CUDA (the host mirror relies on it for empty ray
+    batches, e.g. a frame whose pixels were all depth-filtered, common.py:248-254), and a malformed call returns a
+    negative code with hps_last_error() naming the violated condition instead of launching anything."""
+    lib = hps._lib.load()
+    N = None
+
+    def err():
+        return lib.hps_last_error().decode()
+
+    # ---- empty inputs: rc 0, no buffers needed
+    assert lib.hps_interp_fwd(N, N, N, N, N, N, N, N, N, N, 0, 2, N, N, N, N, N) == 0
+    assert lib.hps_interp_bwd(N, N, N, N, N, N, N, N, N, N, N, 0, N, N, N, N, N) == 0
+    assert lib.hps_composite_fwd(N, 4, N, 4, N, N, 0, 5, 0.1, N, N, N, N, 2, N, N, N, 0, N) == 0
+    assert lib.hps_composite_bwd(N, 4, N, 4, N, N, 0, 5, 0.1, N, N, N, N, 4, N, 4, N, N, N) == 0
+    assert lib.hps_mapper_loss(N, N, N, N, N, N, N, 0.1, 0, N, N, N, N, N) == 0
+    assert lib.hps_tracker_loss_stats(N, N, N, 0, N, N) == 0
+    assert lib.hps_tracker_loss(N, N, N, N, N, N, 1.0, 0.5, 0, N, N, N, N) == 0
+    assert lib.hps_sample_rays(N, N, N, N, 0.08, N, 0, 0, 5, 0.0, 1.0, N, N, N, N, N) == 0
+    assert lib.hps_adam_rows(N, N, N, N, 0, 32, 1e-3, 0.9, 0.999, 1e-8, N, N, N, N) == 0
+    assert lib.hps_adam_multi(0, N, N, N, N, N, N, 0.9, 0.999, 1e-8, N, 0, N) == 0
+    assert lib.hps_adam_multi_own_steps(0, N, N, N, N, N, N, N, 0.9, 0.999, 1e-8, N, 0, N) == 0
+    for kind in (0, 1):
+        assert lib.hps_mlp_fwd(kind, N, N, N, N, N, 0, N, N, N) == 0
+        assert lib.hps_mlp_tc_fwd(kind, N, N, N, N, N, 0, N, N, N, 0, N) == 0
+
+    # ---- malformed calls: negative code + a message that names the condition
+    cases = [
+        (lambda: lib.hps_interp_fwd(N, N, N, N, N, N, N, N, N, N, -1, 2, N, N, N, N, N), "P >= 0"),
+        (lambda: lib.hps_interp_fwd(N, N, N, N, N, N, N, N, N, N, 8, 2, N, N, N, N, N), "null buffer"),
+        (lambda: lib.hps_composite_fwd(N, 4, N, 4, N, N, 3, 33, 0.1, N, N, N, N, 2, N, N, N, 0, N), "S <= 32"),
+        (lambda: lib.hps_composite_fwd(N, 4, N, 4, N, N, 3, 5, 0.1, N, N, N, N, 2, N, N, N, 0, N), "null buffer"),
+        (lambda: lib.hps_mapper_loss(N, N, N, N, N, N, N, 0.1, -5, N, N, N, N, N), "R >= 0"),
+        (lambda: lib.hps_tracker_loss(N, N, N, N, N, N, 0.0, 0.5, 4, N, N, N, N), "count > 0"),
+        (lambda: lib.hps_sample_rays(N, N, N, N, 0.08, N, 3, 10, 5, 0.0, 1.0, N, N, N, N, N), "z_zero_stride"),
+        (lambda: lib.hps_adam_rows(N, N, N, N, 4, 30, 1e-3, 0.9, 0.999, 1e-8, N, N, N, N), "C % 4 == 0"),
+        (lambda: lib.hps_adam_multi(25, N, N, N, N, N, N, 0.9, 0.999, 1e-8, N, 0, N), "at most 24"),
+        (lambda: lib.hps_adam_multi_own_steps(3, N, N, N, N, N, N, N, 0.9, 0.999, 1e-8, N, 0, N), "null buffer"),
+        (lambda: lib.hps_mlp_fwd(7, N, N, N, N, N, 0, N, N, N), "bad decoder kind"),
+        (lambda: lib.hps_mlp_tc_fwd(1, N, N, N, N, N, 16, N, N, N, 0, N), "null buffer"),
+        (lambda: lib.hps_knn_query(N, N, N, N, 0, N, N, N, N, 1, N), "grid not built"),
+        (lambda: lib.hps_exposure_fwd(N, N, N, N, N, 8, 4096, 12, N, N, N), "exposure MLP size"),
+    ]
+    for call, needle in cases:
+        rc = call()
+        assert rc < 0, needle
+        assert needle in err(), (needle, err())
+    # the Python wrapper turns the code into an exception carrying that message
+    with pytest.raises(hps._lib.HpsError, match="bad decoder kind"):
+        hps._lib.check(lib.hps_mlp_fwd(7, N, N, N, N, N, 0, N, N, N))

@@ -271,3 +271,65 @@ def test_mapper_schedule_matches_the_reference_statements():
                 assert got + [cam] == lrs, (j, got, cam, lrs)
             covered += count
         assert covered == n
+
+
+def test_mapper_optimizer_bookkeeping_with_emulated_kernels(monkeypatch):
+    """MapperOptimizer's host side without a GPU: which tensors go into which launch, the per-tensor step-counter
+    pointers, the scratch words, the learning rates handed to the kernels, the row write-back arguments.  The two
+    Adam entry points are replaced by a numpy emulation of their documented semantics (include/hps_b200.h) acting on
+    the raw pointers the host code passes, and the GPU parity test's own body runs against it on CPU tensors - so
+    the comparison with the reference's single torch.optim.Adam (Mapper.py:592-603, 633-667) covers everything except
+    the kernels' arithmetic, which `-m gpu` checks."""
+    import contextlib
+    import ctypes
+    import numpy as np
+
+    def arr(ptr, n, dt=np.float32):
+        if isinstance(ptr, ctypes.c_void_p):
+            ptr = ptr.value
+        return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,))
+
+    def adam(p, g, m, v, lr, b1, b2, eps, t):
+        b1, b2 = np.float32(b1), np.float32(b2)
+        bc1, bc2 = np.float32(1 - float(b1) ** t), np.float32(1 - float(b2) ** t)
+        m[:] = m + (g - m) * (np.float32(1) - b1)
+        v[:] = v * b2 + (np.float32(1) - b2) * g * g
+        p[:] = p - (np.float32(lr) / bc1) * (m / (np.sqrt(v) / np.sqrt(bc2) + np.float32(eps)))
+
+    launches = []
+
+    def fake_call(name, *a):
+        if name == "hps_adam_rows":
+            p, g, m, v, M, C, lr, b1, b2, eps, step, table, rows, _stream = a
+            st = arr(step, 2, np.int32)
+            P = arr(p, M * C)
+            adam(P, arr(g, M * C), arr(m, M * C), arr(v, M * C), lr, b1, b2, eps, int(st[0]) + 1)
+            st[0] += 1
+            if table is not None:
+                R = arr(rows, M, np.int64)
+                arr(table, (int(R.max()) + 1) * C).reshape(-1, C)[R] = P.reshape(M, C)
+        elif name == "hps_adam_multi_own_steps":
+            n, ps, gs, ms, vs, numel, lrs, steps, b1, b2, eps, done, zero_grad, _stream = a
+            launches.append(n)
+            assert 0 < n <= 24 and arr(done, 1, np.int32)[0] == 0
+            assert len({steps[i] for i in range(n)}) == n               # distinct counters
+            for i in range(n):
+                st = arr(steps[i], 1, np.int32)
+                G = arr(gs[i], numel[i])
+                adam(arr(ps[i], numel[i]), G, arr(ms[i], numel[i]), arr(vs[i], numel[i]), lrs[i], b1, b2, eps, int(st[0]) + 1)
+                st[0] += 1
+                if zero_grad:
+                    G[:] = 0
+        else:
+            raise AssertionError("unexpected kernel call " + name)
+
+    monkeypatch.setattr(ops, "_call", fake_call)
+    monkeypatch.setattr(ops, "_need_cuda", lambda *t: None)
+    monkeypatch.setattr(ops, "_stream", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    from tests import test_gpu_kernels as T
+    monkeypatch.setattr(T, "DEV", "cpu")
+    T.test_mapper_optimizer_follows_torch_adam_through_the_stages(hps)
+    # geometry stages: 6 decoder tensors; colour stages: 24 decoder tensors + 2 poses + the latent = 24 + 3
+    assert sorted(set(launches)) == [3, 6, 24]
