@@ -651,3 +651,43 @@ def test_mapper_optimizer_follows_torch_adam_through_the_stages(hps):
         assert torch.equal(r.table[other], tab[key][other])
     with pytest.raises(ValueError):
         mo.MapperOptimizer(cfg, rows={"geometry_coarse": g_fine})
+
+
+def test_knn_largest_cloud_properties(hps):
+    """BASELINE configs[4] size (8M fine points, 8x the area of configs[1] at the same ScanNet-like density): the
+    size-independent properties of test_knn_full_size_properties + an exhaustive check of 16 queries against the
+    oracle's distance formula over all 8M points (in-radius slots ordered by (D, index))."""
+    g = torch.Generator().manual_seed(79)
+    K, depth = O.SCANNET_INTRINSICS, O.synthetic_depth()
+    n, ext, Q = 8_000_000, 28.0, 20_000
+    u = torch.rand(n, generator=g) * (K["W"] - 1) * ext - (ext - 1) * K["W"] / 2
+    v = torch.rand(n, generator=g) * (K["H"] - 1) * ext - (ext - 1) * K["H"] / 2
+    d = depth[v.clamp(0, K["H"] - 1).long(), u.clamp(0, K["W"] - 1).long()]
+    d = d * (0.96 + 0.04 * torch.randint(0, 3, (n,), generator=g).float())
+    pts = torch.stack([(u - K["cx"]) / K["fx"] * d, -(v - K["cy"]) / K["fy"] * d, -d], -1).float().contiguous()
+    q = pts[torch.randint(0, n, (Q,), generator=g)] + (torch.rand(Q, 3, generator=g) - 0.5) * 0.05
+    r = 0.04 + 0.12 * torch.rand(Q, generator=g, dtype=torch.float64)
+    idx = hps.GridIndex(DEV)
+    idx.reset(pts.to(DEV))
+    idx.cell_hint = 0.08
+    res = idx.radius_search(q.to(DEV), r.to(DEV))
+    I, D, cnt = res.I.cpu(), res.D.cpu(), res.count.cpu()
+    info = idx._grid.info()
+    assert info["status"] == 0 and info["n_points"] == n
+    used = I >= 0
+    assert int(used.sum()) > 4 * Q                                                    # the queries do find neighbours
+    assert bool((D[:, 1:] >= D[:, :-1]).all()) and bool((used[:, 1:] <= used[:, :-1]).all())
+    t_up, t_dn = O.radius_thresholds(r)
+    assert bool((D[used] <= t_dn[:, None].expand_as(D)[used]).all())
+    assert torch.equal(cnt, (D < t_up[:, None]).sum(1).int())
+    dd = q[:, None, :] - pts[I.clamp(min=0).long()]
+    assert torch.equal(((dd[..., 0] * dd[..., 0] + dd[..., 1] * dd[..., 1]) + dd[..., 2] * dd[..., 2])[used], D[used])
+    assert bool((I[used].long() < n).all())
+    for j in range(16):
+        Dall = O.sqdist_direct(q[j:j + 1], pts)[0]
+        inr = torch.nonzero(Dall <= t_dn[j]).flatten()                                # ascending index order
+        order = torch.sort(Dall[inr], stable=True).indices[:8]                        # (D, index) order
+        want_i, want_d = inr[order], Dall[inr][order]
+        m = want_i.numel()
+        assert int(used[j].sum()) == m, (j, m)
+        assert torch.equal(I[j, :m].long(), want_i) and torch.equal(D[j, :m], want_d)
