@@ -132,6 +132,65 @@ class GridIndex:
         return D, I
 
 
+def remap_bilinear(depth, x, y):
+    """cv2.remap(depth, x, y, interpolation=cv2.INTER_LINEAR) with the default constant-0 border, for a float32 image and
+    float32 positions, as tensor ops on the positions' device (Mapper.py:231-236).  OpenCV samples on a 1/32-pixel
+    lattice: sx = cvRound(32 x), pixel sx >> 5 (saturated to int16), fraction (sx & 31) / 32, four float weights
+    (1-fy)(1-fx), (1-fy)fx, fy(1-fx), fy fx, summed left to right in float32; taps outside the image count as 0.  Next to
+    missing-depth (zero) pixels this differs from exact bilinear weights by centimetres, so it is restated, not
+    approximated; bit-exact against cv2 4.13 on the fixture of oracle/make_golden_frustum.py."""
+    H, W = depth.shape
+    flat = depth.to(torch.float32).reshape(-1)
+
+    def fixed(t):
+        t32 = t.to(torch.float32) * 32.0
+        bad = ~torch.isfinite(t32) | (t32.abs() >= 2.0 ** 31)
+        r = torch.round(torch.where(bad, torch.zeros_like(t32), t32)).to(torch.int64)      # half to even, like cvRound
+        r = torch.where(bad, torch.full_like(r, -2 ** 31), r)
+        return (r >> 5).clamp(-32768, 32767), (r & 31).to(torch.float32) * (1.0 / 32.0)
+    ix, ax = fixed(x)
+    iy, ay = fixed(y)
+
+    def tap(yy, xx):
+        inside = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+        return torch.where(inside, flat[yy.clamp(0, H - 1) * W + xx.clamp(0, W - 1)], torch.zeros_like(ax))
+    acc = tap(iy, ix) * ((1.0 - ay) * (1.0 - ax))
+    acc = acc + tap(iy, ix + 1) * ((1.0 - ay) * ax)
+    acc = acc + tap(iy + 1, ix) * (ay * (1.0 - ax))
+    return acc + tap(iy + 1, ix + 1) * (ay * ax)
+
+
+def frustum_select(pos, c2w, depth, H, W, fx, fy, cx, cy, edge):
+    """Mapper.get_mask_from_c2w (Mapper.py:194-250) over a (N,3) position tensor, on its device: -> ascending int64
+    indices.  The number types follow the reference so that the selection is the same set, not a similar one: w2c is
+    the float32 inverse of the float32 pose (:208-209, computed on the host by the same numpy call), the projection runs in float64 (:213-227), the pixel position is
+    cast to float32 (:228), the depth image is sampled like cv2.remap does (`remap_bilinear`), zero samples take the
+    maximum (:243-244) and `depths + 0.5` is a float32 sum (:246).  Pinned against the reference's own method run with
+    the real cv2 (tests/golden/frustum_small.pt; the same ops run here on CPU tensors and on the GPU)."""
+    dev = pos.device
+    if pos.shape[0] == 0:
+        return torch.zeros(0, dtype=torch.long, device=dev)
+    # the pose inverse is the reference's own statement, on the host like there (`np.linalg.inv(c2w.cpu().numpy())`, float32
+    # LAPACK): 64 bytes each way per call; a device-side inverse differs from it in the last bit, which moves points
+    # across cv2's 1/32-pixel lattice
+    c2w = np.asarray(torch.as_tensor(c2w).detach().cpu().numpy(), dtype=np.float32)
+    if c2w.shape[0] == 3:
+        c2w = np.concatenate([c2w, np.array([[0.0, 0.0, 0.0, 1.0]], dtype=np.float32)], 0)
+    w2c = torch.from_numpy(np.linalg.inv(c2w).astype(np.float64)).to(dev)
+    depth = torch.as_tensor(depth, device=dev)
+    cam = pos.to(torch.float64) @ w2c[:3, :3].T + w2c[:3, 3]
+    cam = cam * torch.tensor([-1.0, 1.0, 1.0], dtype=torch.float64, device=dev)        # Mapper.py:225 axis flip
+    z = cam[:, 2] + 1e-5
+    u = ((fx * cam[:, 0] + cx * cam[:, 2]) / z).to(torch.float32)
+    v = ((fy * cam[:, 1] + cy * cam[:, 2]) / z).to(torch.float32)
+    dep = remap_bilinear(depth, u, v)
+    dep = torch.where(dep == 0, dep.max(), dep)
+    far = (dep + 0.5).to(torch.float64)                                                # float32 sum, then widened
+    mz = -z
+    mask = (u < W - edge) & (u > edge) & (v < H - edge) & (v > edge) & (mz >= 0) & (mz <= far)
+    return mask.nonzero().flatten()
+
+
 class NeuralPointCloud(object):
     def __init__(self, cfg):
         self.cfg = cfg
@@ -169,38 +228,10 @@ class NeuralPointCloud(object):
     def frustum_rows(self, level, c2w, depth, H, W, fx, fy, cx, cy, edge):
         """Frustum feature selection on the device (Mapper.get_mask_from_c2w, Mapper.py:194-250): indices (int64, ascending)
         of the level's points that project inside the frame cropped by `edge` pixels, in front of the camera and not
-        further than the (bilinearly sampled) depth + 0.5 m.  The reference does this on the host in numpy + cv2.remap for
-        every mapped frame and level; here it is a handful of tensor ops over the resident positions (float64 projection
-        like numpy's, exact bilinear weights instead of cv2's 5-bit fixed point: points within ~1e-3 of a threshold can
-        differ).  Feed the result to ops.LiveRows / LiveRows.pair."""
-        pos = self.index[level].positions
-        dev = pos.device
-        c2w = torch.as_tensor(c2w, dtype=torch.float64, device=dev)
-        if c2w.shape[0] == 3:
-            c2w = torch.cat([c2w, torch.tensor([[0.0, 0.0, 0.0, 1.0]], dtype=torch.float64, device=dev)], 0)
-        depth = torch.as_tensor(depth, device=dev).to(torch.float64)
-        w2c = torch.linalg.inv(c2w)
-        cam = pos.to(torch.float64) @ w2c[:3, :3].T + w2c[:3, 3]
-        cam = cam * torch.tensor([-1.0, 1.0, 1.0], dtype=torch.float64, device=dev)        # Mapper.py:225 axis flip
-        z = cam[:, 2] + 1e-5
-        u = ((fx * cam[:, 0] + cx * cam[:, 2]) / z).to(torch.float32)
-        v = ((fy * cam[:, 1] + cy * cam[:, 2]) / z).to(torch.float32)
-        x, y = u.to(torch.float64), v.to(torch.float64)
-        ok = torch.isfinite(x) & torch.isfinite(y)
-        x, y = torch.where(ok, x, torch.zeros_like(x)), torch.where(ok, y, torch.zeros_like(y))
-        x0, y0 = torch.floor(x), torch.floor(y)
-        ax, ay = x - x0, y - y0
-
-        def at(yy, xx):                                    # constant-0 border (cv2.remap default)
-            inside = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
-            flat = (yy.clamp(0, H - 1) * W + xx.clamp(0, W - 1)).long()
-            return torch.where(inside, depth.reshape(-1)[flat], torch.zeros_like(xx))
-        dep = ((1 - ay) * ((1 - ax) * at(y0, x0) + ax * at(y0, x0 + 1)) + ay * ((1 - ax) * at(y0 + 1, x0) + ax * at(y0 + 1, x0 + 1)))
-        dep = dep.to(torch.float32).to(torch.float64)
-        dep = torch.where(dep == 0, dep.max(), dep)
-        mz = -z
-        mask = (u < W - edge) & (u > edge) & (v < H - edge) & (v > edge) & (mz >= 0) & (mz <= dep + 0.5)
-        return mask.nonzero().flatten()
+        further than the sampled depth + 0.5 m.  The reference does this on the host in numpy + cv2.remap for every mapped
+        frame and level (four times per frame, :506-509); here it is `frustum_select` over the resident positions.
+        Feed the result to ops.LiveRows / LiveRows.pair."""
+        return frustum_select(self.index[level].positions, c2w, depth, H, W, fx, fy, cx, cy, edge)
 
     def cloud_pos_tensor(self, level):
         """The (N,3) device tensor itself (what Mapper.py:779 / Tracker.py:257 rebuild every time)."""

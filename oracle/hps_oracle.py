@@ -368,43 +368,73 @@ def dynamic_radius_maps(gt_color, radius_hierarchy, ratio, threshold):
 
 
 # ----------------------------------------------------------------------------------------------
-# frustum feature selection.  PARITY UNPINNED: the reference samples the depth image with
-# cv2.remap (INTER_LINEAR, fixed-point weights, constant-0 border); cv2 is not importable here, so this
-# restatement uses exact bilinear weights and has not been run against the reference function.
+# frustum feature selection.  PINNED: oracle/make_golden_frustum.py executes the reference's
+# Mapper.get_mask_from_c2w with the real cv2 (4.13, installed in the build image) and commits the selected indices;
+# tests/test_oracle_golden.py requires this restatement to return the same sets and its sampler to equal cv2.remap.
 # ----------------------------------------------------------------------------------------------
+def remap_bilinear_cv2(depth, x, y):
+    """cv2.remap(depth, x, y, interpolation=cv2.INTER_LINEAR) for a float32 image and float32 maps, default constant-0
+    border, as called at Mapper.py:231-236.  OpenCV (imgproc/remap: INTER_BITS = 5) rounds the sampling position to
+    1/32 pixel - sx = cvRound(x * 32), pixel sx >> 5, fraction (sx & 31) / 32 - takes the four weights from its float
+    table ((1 - fy)(1 - fx), (1 - fy) fx, fy (1 - fx), fy fx; exact products of multiples of 1/32) and sums
+    S00 w0 + S01 w1 + S10 w2 + S11 w3 left to right in float32; taps outside the image contribute 0; the integer pixel
+    coordinate saturates to int16.  Pinned bit-exact against cv2 4.13 by tests/golden/frustum_small.pt."""
+    import numpy as np
+    d = np.asarray(depth, dtype=np.float32)
+    H, W = d.shape
+    x = np.asarray(x, dtype=np.float32)
+    y = np.asarray(y, dtype=np.float32)
+
+    def fixed(t):                                          # cvRound = round half to even; NaN / overflow -> INT_MIN
+        t32 = t * np.float32(32.0)
+        bad = ~np.isfinite(t32) | (np.abs(t32) >= 2.0 ** 31)
+        r = np.rint(np.where(bad, 0.0, t32).astype(np.float64)).astype(np.int64)
+        r = np.where(bad, -2 ** 31, r)
+        return np.clip(r >> 5, -32768, 32767), (r & 31)
+    ix, fx5 = fixed(x)
+    iy, fy5 = fixed(y)
+    ax = fx5.astype(np.float32) * np.float32(1.0 / 32.0)
+    ay = fy5.astype(np.float32) * np.float32(1.0 / 32.0)
+    w = [(np.float32(1) - ay) * (np.float32(1) - ax), (np.float32(1) - ay) * ax, ay * (np.float32(1) - ax), ay * ax]
+
+    def at(yy, xx):
+        ok = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+        out = np.zeros(xx.shape, dtype=np.float32)
+        out[ok] = d[yy[ok], xx[ok]]
+        return out
+    acc = at(iy, ix) * w[0]
+    acc = acc + at(iy, ix + 1) * w[1]
+    acc = acc + at(iy + 1, ix) * w[2]
+    acc = acc + at(iy + 1, ix + 1) * w[3]
+    return acc.astype(np.float32)
+
+
 def frustum_mask(points, c2w, depth, fx, fy, cx, cy, edge):
     """Mapper.get_mask_from_c2w (Mapper.py:194-250): indices of the cloud points that project inside the frame
-    (cropped by `edge` pixels) and lie in front of the camera, not further than depth + 0.5 m.  numpy, float64."""
+    (cropped by `edge` pixels) and lie in front of the camera, not further than depth + 0.5 m.  numpy; the types follow
+    the reference: w2c is the float32 inverse of the float32 pose (:208-209), the projection runs in float64 on the
+    float64 point list (:213-227), uv is cast to float32 (:228), the depth is sampled by cv2.remap's fixed-point
+    bilinear (:231-236), `depths + 0.5` is a float32 sum (:246).  Pinned against the reference's own method executed
+    with the real cv2 (oracle/make_golden_frustum.py).  Also returns each point's distance to the nearest threshold."""
     import numpy as np
     H, W = depth.shape
     pts = np.asarray(points, dtype=np.float64).reshape(-1, 3)
-    w2c = np.linalg.inv(np.asarray(c2w, dtype=np.float64))
+    w2c = np.linalg.inv(np.asarray(c2w, dtype=np.float32)).astype(np.float64)
     cam = (w2c @ np.concatenate([pts, np.ones_like(pts[:, :1])], 1).T).T[:, :3]
     cam[:, 0] *= -1                                         # Mapper.py:225 axis flip
     Kmat = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
     uvz = (Kmat @ cam.T).T
     z = uvz[:, 2:] + 1e-5
-    uv = (uvz[:, :2] / z).astype(np.float32)
-    x, y = uv[:, 0].astype(np.float64), uv[:, 1].astype(np.float64)
-    x0, y0 = np.floor(x), np.floor(y)
-    d = np.asarray(depth, dtype=np.float64)
-
-    def at(yy, xx):                                         # constant-0 border like cv2.remap's default
-        ok = (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
-        out = np.zeros_like(xx)
-        out[ok] = d[yy[ok].astype(np.int64), xx[ok].astype(np.int64)]
-        return out
-    ax, ay = x - x0, y - y0
-    ok = np.isfinite(x) & np.isfinite(y)
-    x0, y0, ax, ay = [np.where(ok, t, 0.0) for t in (x0, y0, ax, ay)]
-    dep = ((1 - ay) * ((1 - ax) * at(y0, x0) + ax * at(y0, x0 + 1)) + ay * ((1 - ax) * at(y0 + 1, x0) + ax * at(y0 + 1, x0 + 1)))
-    dep = dep.astype(np.float32).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        uv = (uvz[:, :2] / z).astype(np.float32)
+    dep = remap_bilinear_cv2(depth, uv[:, 0], uv[:, 1])
     mask = (uv[:, 0] < W - edge) & (uv[:, 0] > edge) & (uv[:, 1] < H - edge) & (uv[:, 1] > edge)
     dep[dep == 0] = dep.max()
     mz = -z[:, 0]
-    mask = mask & (0 <= mz) & (mz <= dep + 0.5)
+    far = (dep + np.float32(0.5)).astype(np.float64)        # float32 sum, compared against the float64 -z
+    mask = mask & (0 <= mz) & (mz <= far)
     margin = np.minimum.reduce([np.abs(uv[:, 0] - (W - edge)), np.abs(uv[:, 0] - edge), np.abs(uv[:, 1] - (H - edge)),
-                                np.abs(uv[:, 1] - edge), np.abs(mz), np.abs(mz - dep - 0.5)])
+                                np.abs(uv[:, 1] - edge), np.abs(mz), np.abs(mz - far)])
     return np.where(mask)[0], margin
 
 

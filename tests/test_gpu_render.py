@@ -315,8 +315,9 @@ def test_prepared_head_gives_identical_iteration(built, tracker):
 
 
 def test_frustum_rows_matches_oracle(built):
-    """NeuralPointCloud.frustum_rows (Mapper.py:194-250 on the device) vs the numpy restatement: identical row sets
-    except for points that sit within 1e-3 of one of the selection thresholds (fp summation order / nothing else)."""
+    """NeuralPointCloud.frustum_rows (Mapper.py:194-250 on the device) vs the numpy restatement, which is itself pinned
+    against the reference's method run with the real cv2 (tests/test_oracle_golden.py): identical row sets except for
+    points that sit within 1e-3 of one of the selection thresholds (float64 summation order / nothing else)."""
     import numpy as np
     scene, hps, npc, dec, renderer = built
     K = O.SCANNET_INTRINSICS

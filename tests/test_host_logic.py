@@ -333,3 +333,27 @@ def test_mapper_optimizer_bookkeeping_with_emulated_kernels(monkeypatch):
     T.test_mapper_optimizer_follows_torch_adam_through_the_stages(hps)
     # geometry stages: 6 decoder tensors; colour stages: 24 decoder tensors + 2 poses + the latent = 24 + 3
     assert sorted(set(launches)) == [3, 6, 24]
+
+
+def test_frustum_selection_arithmetic_matches_the_reference_method(golden):
+    """The product's frustum feature selection (neural_point.frustum_select - the tensor ops NeuralPointCloud.frustum_rows
+    runs on the device, here on CPU tensors) vs the reference's Mapper.get_mask_from_c2w executed with the real cv2
+    (tests/golden/frustum_small.pt): identical index sets; 3x4 poses; empty cloud; and its depth sampler vs the
+    oracle's cv2.remap restatement bit for bit."""
+    import numpy as np
+    from oracle import hps_oracle as O
+    npm = hps.neural_point
+    fx = golden("frustum_small.pt")
+    K = fx["intrinsics"]
+    args = (fx["depth"], K["H"], K["W"], K["fx"], K["fy"], K["cx"], K["cy"])
+    for case in fx["cases"]:
+        got = npm.frustum_select(case["points"], case["c2w"], *args, case["edge"])
+        assert got.dtype == torch.long and torch.equal(got, case["indices"])
+        assert torch.equal(npm.frustum_select(case["points"], case["c2w"][:3], *args, case["edge"]), got)
+    assert npm.frustum_select(torch.zeros(0, 3), fx["cases"][0]["c2w"], *args, 0).numel() == 0
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(50_000, generator=g) * 700 - 30
+    y = torch.rand(50_000, generator=g) * 540 - 30
+    x[:4] = torch.tensor([float("nan"), float("inf"), -1e12, 639.0])
+    mine = npm.remap_bilinear(fx["depth"], x, y)
+    assert np.array_equal(mine.numpy(), O.remap_bilinear_cv2(fx["depth"].numpy(), x.numpy(), y.numpy()))
