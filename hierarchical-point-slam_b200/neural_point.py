@@ -218,6 +218,8 @@ class NeuralPointCloud(object):
         self._cloud_normal = {}
         self._input_pos = []
         self._input_rgb = []
+        self._input_normal = []
+        self._input_normal_cartesian = []
         self.keyframe_dict = []
 
     # ---- reference accessors ----------------------------------------------------------------
@@ -246,8 +248,50 @@ class NeuralPointCloud(object):
     def input_rgb(self):
         return torch.cat(self._input_rgb).tolist() if self._input_rgb else []
 
+    def input_normal(self):
+        """neural_point.py:93 (checkpoint logger, Logger.py:33).  Stays empty: normals are not built (use_normals False)."""
+        return self._input_normal
+
+    def input_normal_cartesian(self):
+        return self._input_normal_cartesian
+
     def pts_num(self):
         return self._pts_num
+
+    def set_pts_num(self, value):
+        self._pts_num = value
+
+    def index_is_trained(self, level=None):
+        """neural_point.py:124-138 address `self.index` as one faiss index although it is a per-level dict (they would
+        raise there); here they take the level, or answer for all levels when it is omitted."""
+        levels = [level] if level is not None else list(self.index)
+        return bool(levels) and all(self.index[l].is_trained for l in levels)
+
+    def index_train(self, xb, level=None):
+        assert torch.is_tensor(xb), "use tensor to train FAISS index"
+        for l in ([level] if level is not None else list(self.index)):
+            self.index[l].train(xb)
+        return self.index_is_trained(level)
+
+    def index_set_nprobe(self, value, level=None):
+        """Kept for callers that tune faiss; the grid search is exact whatever nprobe says."""
+        self.nprobe = value
+        for l in ([level] if level is not None else list(self.index)):
+            self.index[l].nprobe = value
+
+    def index_get_nprobe(self, level=None):
+        return self.index[level].nprobe if level is not None else self.nprobe
+
+    @staticmethod
+    def cart2sph(xyz):
+        """neural_point.py:181-189: unit normals (N,3) -> (N,2) polar / azimuth angles."""
+        out = torch.zeros(xyz.shape[0], 2, device=xyz.device)
+        out[:, 0] = torch.atan2(torch.sqrt(xyz[:, 0] ** 2 + xyz[:, 1] ** 2), xyz[:, 2])
+        out[:, 1] = torch.atan2(xyz[:, 1], xyz[:, 0])
+        return out
+
+    def merge_points(self, keyframe_list):
+        """neural_point.py:419-420: a no-op in the reference as well."""
 
     def set_keyframe_dict(self, value):
         self.keyframe_dict = value

@@ -357,3 +357,30 @@ def test_frustum_selection_arithmetic_matches_the_reference_method(golden):
     x[:4] = torch.tensor([float("nan"), float("inf"), -1e12, 639.0])
     mine = npm.remap_bilinear(fx["depth"], x, y)
     assert np.array_equal(mine.numpy(), O.remap_bilinear_cv2(fx["depth"].numpy(), x.numpy(), y.numpy()))
+
+
+def test_neural_point_cloud_reference_accessors():
+    """The small accessors of the reference class that callers outside the render path use (checkpoint logger
+    Logger.py:25-40, tools): present, with the reference's return conventions; no device needed."""
+    import math
+    npc = hps.NeuralPointCloud(hps.scannet_cfg("cpu"))
+    for level in ("mid", "fine"):
+        npc._init_level(level)
+    assert npc.input_pos() == [] and npc.input_rgb() == [] and npc.input_normal() == [] and npc.input_normal_cartesian() == []
+    assert npc.pts_num() == {"mid": 0, "fine": 0} and npc.index_ntotal("fine") == 0
+    assert not npc.index_is_trained() and not npc.index_is_trained("mid")
+    assert npc.index_train(torch.zeros(4, 3), level="mid") and npc.index_is_trained("mid") and not npc.index_is_trained()
+    assert npc.index_train(torch.zeros(4, 3)) and npc.index_is_trained()
+    with pytest.raises(AssertionError):
+        npc.index_train([[0.0, 0.0, 0.0]])                      # 'use tensor to train FAISS index'
+    assert npc.index_get_nprobe() == 4 and npc.index_get_nprobe("fine") == 4
+    npc.index_set_nprobe(400)
+    assert npc.index_get_nprobe("mid") == 400 and npc.get_index("fine").nprobe == 400
+    npc.set_pts_num({"mid": 3, "fine": 5})
+    assert npc.pts_num()["fine"] == 5
+    assert npc.get_c_dim() == 32 and npc.get_radius_query() == 0.08 and npc.get_radius_add() == 0.04
+    assert npc.merge_points([]) is None
+    n = torch.tensor([[0.0, 0.0, 1.0], [1.0, 0.0, 0.0], [0.0, -1.0, 0.0], [0.6, 0.0, 0.8]])
+    sph = npc.cart2sph(n)
+    want = torch.tensor([[0.0, 0.0], [math.pi / 2, 0.0], [math.pi / 2, -math.pi / 2], [math.atan2(0.6, 0.8), 0.0]])
+    assert torch.allclose(sph, want, atol=1e-7)
