@@ -11,6 +11,26 @@ import torch
 from . import frame, ops
 
 
+def setup_seed(seed):
+    """common.py:31-37: the reference seeds torch, numpy and `random` (1219 everywhere) before building the decoders
+    and the cloud; NICER's seeded init equals the reference's only after the same call."""
+    import random
+    torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed_all(seed)
+    np.random.seed(seed)
+    random.seed(seed)
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+
+
+def as_intrinsics_matrix(intrinsics):
+    """common.py:40-50: (fx, fy, cx, cy) -> 3x3 numpy matrix."""
+    K = np.eye(3)
+    K[0, 0], K[1, 1], K[0, 2], K[1, 2] = intrinsics[0], intrinsics[1], intrinsics[2], intrinsics[3]
+    return K
+
+
 def raw2outputs_nerf_color(raw, z_vals, rays_d=None, occupancy=False, device="cuda:0", coef=0.1):
     """raw (R,S,4) [rgb, occupancy logit], z_vals (R,S) -> depth (R,), depth_var (R,), rgb (R,3), weights (R,S).
 
