@@ -734,3 +734,31 @@ def test_search_that_samples_on_the_fly_is_bit_identical(built, per_ray_z):
     torch.cuda.synchronize()
     for k in a:
         assert torch.equal(a[k], b[k]), k
+
+
+def test_loss_kernels_match_the_reference_statements(hps, golden):
+    """The fused loss kernels vs the fixture made by EXECUTING the reference's own loss statements (Mapper.py:793-856,
+    Tracker.py:213-231; oracle/make_golden_losses.py): a mapper batch mixing rays of four keyframes with their own
+    exposure affines (segments of 289 / 5 / ... rays), NaN depth, missing depth, invalid rays, all four stages; the
+    tracker loss with outlier rays.  Loss and the gradients to depth, colour and every keyframe's affine."""
+    fx = golden("losses_small.pt")
+    ids = fx["frame_ids"][fx["inside_mask"]]
+    frame = torch.unique_consecutive(ids, return_inverse=True)[1].to(DEV)        # keyframe slot 0..F-1 of every ray
+    valid, gt_d, gt_c = fx["valid"].to(DEV), fx["gt_depth"].to(DEV), fx["gt_color"].to(DEV)
+    for stage in ("geometry_mid", "geometry_fine", "color_mid", "color_fine"):
+        want = fx["mapper"][(stage, True)]
+        depth, color, aff = (fx[k].clone().to(DEV).requires_grad_(True) for k in ("depth", "color", "affine"))
+        loss = hps.mapper_loss(depth, color, valid, gt_d, gt_c, stage, fx["w_color_mapper"], aff, frame_index=frame)
+        loss.backward()
+        assert parity.rel(loss.detach().cpu(), want["loss"]) < 1e-5, stage
+        assert parity.rel(depth.grad.cpu(), want["g_depth"]) < 1e-6, stage
+        if stage.startswith("color"):
+            assert parity.rel(color.grad.cpu(), want["g_color"]) < 1e-5, stage
+            assert parity.rel(aff.grad.cpu(), want["g_affine"]) < 1e-5, stage
+    want = fx["tracker"][(True, True)]
+    depth = fx["tracker_depth"].clone().to(DEV).requires_grad_(True)
+    color = fx["tracker_color"].clone().to(DEV).requires_grad_(True)
+    loss = hps.tracker_loss(depth, fx["uncertainty"].to(DEV), color, gt_d, gt_c, fx["w_color_tracker"])
+    loss.backward()
+    assert parity.rel(loss.detach().cpu(), want["loss"]) < 1e-5
+    assert parity.rel(depth.grad.cpu(), want["g_depth"]) < 1e-5 and parity.rel(color.grad.cpu(), want["g_color"]) < 1e-6
