@@ -762,3 +762,34 @@ def test_loss_kernels_match_the_reference_statements(hps, golden):
     loss.backward()
     assert parity.rel(loss.detach().cpu(), want["loss"]) < 1e-5
     assert parity.rel(depth.grad.cpu(), want["g_depth"]) < 1e-5 and parity.rel(color.grad.cpu(), want["g_color"]) < 1e-6
+
+
+def test_add_neural_points_matches_the_reference_class(hps, golden):
+    """NeuralPointCloud.add_neural_points (density test + N_add points per accepted location, on the device) vs the
+    fixture made by running the UNMODIFIED reference class on the CPU (oracle/make_golden_insertion.py): seven
+    consecutive insertions into two levels - first frame, repeated + new rays under per-ray float64 radii, scalar
+    radius_add with a missing-depth ray, radius_min (is_pts_grad), mid level incl. a frame that adds nothing.  After every
+    call: the same count of accepted locations and the same cloud, point for point in the same order (<= 1e-6 m)."""
+    import numpy as np
+    fx = golden("insertion_small.pt")
+    npc = hps.NeuralPointCloud(hps.scannet_cfg(DEV))
+    assert npc.radius_add == fx["radius_add"] and npc.radius_min == fx["radius_min"]
+    ro, rd, gc = fx["rays_o"].to(DEV), fx["rays_d"].to(DEV), fx["gt_color"].to(DEV)
+    for c in fx["calls"]:
+        a, b = c["rays"]
+        depth = (fx["gt_depth_zero"] if c["zero"] else fx["gt_depth"])[a:b].to(DEV)
+        rad = None
+        if c["dynamic"]:
+            rad = ((fx["r_fine"] if c["level"] == "fine" else fx["r_mid"])[a:b] * c.get("scale", 1.0)).to(DEV)
+        n = npc.add_neural_points(ro[a:b], rd[a:b], depth, gc[a:b], train=False, is_pts_grad=c["is_pts_grad"],
+                                  dynamic_radius=rad, level=c["level"], idx=c["idx"])
+        tag = (c["level"], c["idx"])
+        assert int(n) == c["count"], tag
+        cloud = npc.cloud_pos_tensor(c["level"]).cpu()
+        assert cloud.shape == c["cloud"].shape, tag
+        # same fp32 expressions on both sides (expected bit-equal); the bar is 1e-6 m on positions of a few metres
+        assert float((cloud - c["cloud"]).abs().max()) <= 1e-6, (tag, float((cloud - c["cloud"]).abs().max()))
+        assert npc.index_ntotal(c["level"]) == c["cloud"].shape[0] == npc.pts_num()[c["level"]]
+        assert npc.get_geo_feats(c["level"]).shape == (c["cloud"].shape[0], 32) == npc.get_col_feats(c["level"]).shape
+        assert len(npc.input_pos()) == c["n_input_pos"]
+    assert np.array(npc.cloud_pos("mid")).shape == (fx["calls"][-1]["cloud"].shape[0], 3)
