@@ -133,3 +133,26 @@ def test_c_abi_empty_inputs_and_argument_checks_without_a_gpu(hps):
     # the Python wrapper turns the code into an exception carrying that message
     with pytest.raises(hps._lib.HpsError, match="bad decoder kind"):
         hps._lib.check(lib.hps_mlp_fwd(7, N, N, N, N, N, 0, N, N, N))
+
+
+def test_scannet_cfg_carries_the_reference_values(hps):
+    """hps_b200.scannet_cfg() (plain data) vs the reference's effective ScanNet configuration as its own load_config
+    produces it (tests/golden/scannet_cfg.json, oracle/make_golden_cfg.py): every key the product defines has the
+    reference's value (devices aside)."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "scannet_cfg.json")) as f:
+        ref = json.load(f)
+    mine = hps.scannet_cfg("cuda:0")
+    checked = 0
+    for key, val in mine.items():
+        if isinstance(val, dict):
+            for k, v in val.items():
+                if k == "device":
+                    continue
+                assert k in ref[key], (key, k)
+                assert ref[key][k] == v, (key, k, v, ref[key][k])
+                checked += 1
+        else:
+            assert ref[key] == val, (key, val, ref[key])
+            checked += 1
+    assert checked > 70
