@@ -90,6 +90,25 @@ class Renderer(object):
         """linspace(near_end, max(far)) for rays without a depth reading (Renderer.py:207-208)."""
         return _linspace32(self.near_end, self._far_end(gt_depth), self.N_surface, device)
 
+    def _z_rows_for_zero_depth(self, gt_depth, chunk, device):
+        """(R,S) z rows for render_img's widened chunks: ray r carries linspace(near_end, max(far)) of the REFERENCE's
+        chunk r // chunk - the far end of rays without a depth reading is a statistic of the 3000-ray chunk they are
+        rendered in (Renderer.py:133-134, 148-153, 207-208), so their colour / uncertainty depend on the chunking.  One
+        segmented reduction over the frame instead of one per chunk; device ops only."""
+        S = self.N_surface
+        gt = gt_depth.reshape(-1).float()
+        R = gt.shape[0]
+        n = (R + chunk - 1) // chunk
+        pad = n * chunk - R
+        g2 = (torch.cat([gt, gt.new_zeros(pad)]) if pad else gt).view(n, chunk)      # depths are >= 0: zeros are neutral
+        count = torch.full((n,), float(chunk), device=gt.device)
+        count[-1] = float(chunk - pad)
+        hi = (g2 * 1.2).max(1).values
+        far_bb = torch.minimum(5 * (g2.sum(1) / count), hi)
+        far = torch.where(hi > 0, torch.clamp(far_bb, min=0.0).minimum(hi), far_bb)
+        rows = _linspace32(self.near_end, far[:, None], S, device)                    # (n,S)
+        return rows.repeat_interleave(chunk, 0)[:R].contiguous()
+
     def _z_near_pcl(self, npc, rays_o, rays_d, gt_depth, radius, level):
         """sample_near_pcl mode (Renderer.py:196-206): rays without a depth reading are sampled between the first two
         of 25 probe positions that have neighbours in the cloud.  -> (z rows (R,S) - only the zero-depth rows are
@@ -125,7 +144,8 @@ class Renderer(object):
 
     def render_batch_ray(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None,
                          npc_geo_feats=None, npc_col_feats=None, is_tracker=False, cloud_pos=None,
-                         normals=None, dynamic_r_query=None, exposure_feat=None, prepared=None, _loss=None):
+                         normals=None, dynamic_r_query=None, exposure_feat=None, prepared=None, _loss=None,
+                         _z_zero_rows=None):
         """One fused kernel sequence (ops.render_rays): sampling, exact neighbour search, interpolation of both
         feature tables from one neighbour list, both decoders, compositing with the -100 overwrite.
         `prepared` (not in the reference): the ops.RayPrep of prepare_batch() for these very rays."""
@@ -154,6 +174,8 @@ class Renderer(object):
             z_zero = None
         elif self.sample_near_pcl:
             z_zero, near_mask = self._z_near_pcl(npc, rays_o, rays_d, gt_depth, radius, level)
+        elif _z_zero_rows is not None:      # render_img: rows computed per reference chunk (_z_rows_for_zero_depth)
+            z_zero = _z_zero_rows
         else:
             z_zero = self._z_for_zero_depth(gt_depth, device)
         geo = getattr(decoders, "geo_decoder_" + level)
@@ -305,15 +327,20 @@ class Renderer(object):
             gt_depth = gt_depth.reshape(-1) if gt_depth is not None else None
             depths, uncs, colors = [], [], []
             # Rays are independent and the reference only chunks to bound memory (ray_batch_size = 3000 -> 103 chunks
-            # per frame, host-bound here): chunks are widened to min_render_chunk rays; the outputs are the same.
+            # per frame, host-bound here): chunks are widened to min_render_chunk rays.  The one thing that depends on
+            # the chunking - the sampling range of rays without a depth reading - is computed per reference chunk.
             B = max(self.ray_batch_size, self.min_render_chunk)
+            z_rows = None
+            if (B > self.ray_batch_size and gt_depth is not None and not self.sample_near_pcl
+                    and not self.assume_positive_depth):
+                z_rows = self._z_rows_for_zero_depth(gt_depth, self.ray_batch_size, rays_o.device)
             for i in range(0, rays_d.shape[0], B):
                 rq = {k: v[i:i + B] for k, v in dynamic_r_query.items()} if self.use_dynamic_radius else None
                 d, u, c, _ = self.render_batch_ray(
                     npc, decoders, rays_d[i:i + B], rays_o[i:i + B], device, stage,
                     gt_depth=None if gt_depth is None else gt_depth[i:i + B], npc_geo_feats=npc_geo_feats,
                     npc_col_feats=npc_col_feats, normals=normals, cloud_pos=cloud_pos, dynamic_r_query=rq,
-                    exposure_feat=exposure_feat)
+                    exposure_feat=exposure_feat, _z_zero_rows=None if z_rows is None else z_rows[i:i + B])
                 depths.append(d.double())
                 uncs.append(u.double())
                 colors.append(c)

@@ -793,3 +793,34 @@ def test_add_neural_points_matches_the_reference_class(hps, golden):
         assert npc.get_geo_feats(c["level"]).shape == (c["cloud"].shape[0], 32) == npc.get_col_feats(c["level"]).shape
         assert len(npc.input_pos()) == c["n_input_pos"]
     assert np.array(npc.cloud_pos("mid")).shape == (fx["calls"][-1]["cloud"].shape[0], 3)
+
+
+@pytest.mark.parametrize("chunks", ["reference", "wide"])
+def test_render_img_matches_the_reference_frame(built, golden, chunks):
+    """Renderer.render_img vs the fixture made by running the reference's render_img on the CPU
+    (oracle/make_golden_render_img.py): 24 x 32 frame, perturbed pose, float64 radius maps, exposure latent, 87 pixels
+    without a depth reading.  'reference' = the reference's chunking (100 rays); 'wide' = the product's default widening,
+    where the sampling range of the depth-less pixels still has to follow the reference's chunks (without
+    Renderer._z_rows_for_zero_depth their colour is off by up to 0.6, tests/test_oracle_golden.py)."""
+    import types
+    scene, hps, npc, dec, renderer = built
+    fx = golden("render_img_small.pt")
+    cl = scene["clouds"]
+    small = hps.Renderer(hps.scannet_cfg(DEV), None, types.SimpleNamespace(H=fx["H"], W=fx["W"], **fx["intrinsics"]),
+                         ray_batch_size=fx["ray_batch_size"])
+    small.sigmoid_coefficient = scene["cfg"]["coef"]
+    small.min_render_chunk = 1 if chunks == "reference" else 65536
+    missing = fx["depth"] == 0
+    for stage, want in fx["stages"].items():
+        d, u, c = small.render_img(npc, dec, fx["c2w"].to(DEV), DEV, stage, gt_depth=fx["depth"].to(DEV),
+                                   npc_geo_feats={l: npc.get_geo_feats(l) for l in cl},
+                                   npc_col_feats={l: npc.get_col_feats(l) for l in cl},
+                                   dynamic_r_query={l: fx["radius"][l].clone().to(DEV) for l in cl},
+                                   cloud_pos={l: npc.cloud_pos_tensor(l) for l in cl},
+                                   exposure_feat=scene["exposure_feat"].to(DEV))
+        assert d.dtype == torch.float64 and u.dtype == torch.float64 and d.shape == (fx["H"], fx["W"])
+        d, u, c = d.cpu(), u.cpu(), c.cpu()
+        assert bool((d[missing] == 0).all())
+        assert parity.rel(d, want["depth"]) < parity.TOL, (stage, parity.rel(d, want["depth"]))
+        assert parity.rel(u, want["uncertainty"]) < parity.TOL, (stage, parity.rel(u, want["uncertainty"]))
+        assert float((c - want["color"]).abs().max()) < parity.TOL, (stage, float((c - want["color"]).abs().max()))

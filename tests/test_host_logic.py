@@ -384,3 +384,26 @@ def test_neural_point_cloud_reference_accessors():
     sph = npc.cart2sph(n)
     want = torch.tensor([[0.0, 0.0], [math.pi / 2, 0.0], [math.pi / 2, -math.pi / 2], [math.atan2(0.6, 0.8), 0.0]])
     assert torch.allclose(sph, want, atol=1e-7)
+
+
+def test_zero_depth_sampling_rows_follow_the_reference_chunks():
+    """render_img widens the reference's 3000-ray chunks; the sampling range of rays WITHOUT a depth reading is a statistic
+    of the reference chunk they fall into (Renderer.py:133-134, 148-153, 207-208).  The segmented computation of the
+    per-ray z rows must equal the chunk-by-chunk one (the expressions render_batch_ray uses for one chunk), including a
+    ragged last chunk, an all-missing chunk and a chunk whose bound is clamped by 1.2 max(d)."""
+    import types
+    r = hps.Renderer(hps.scannet_cfg("cpu"), None, types.SimpleNamespace(H=4, W=4, fx=1.0, fy=1.0, cx=2.0, cy=2.0))
+    g = torch.Generator().manual_seed(6)
+    chunk, R = 100, 100 * 7 + 37
+    gt = 0.5 + 4.0 * torch.rand(R, generator=g)
+    gt[torch.rand(R, generator=g) < 0.2] = 0.0
+    gt[200:300] = 0.0                                  # a chunk without any depth reading
+    gt[300:400] = 0.01
+    gt[333] = 9.0                                      # 5 mean(d) < 1.2 max(d): the mean term decides
+    rows = r._z_rows_for_zero_depth(gt, chunk, "cpu")
+    assert rows.shape == (R, 5) and rows.is_contiguous()
+    for i in range(0, R, chunk):
+        want = r._z_for_zero_depth(gt[i:i + chunk], "cpu")
+        assert torch.allclose(rows[i:i + chunk], want.expand(min(chunk, R - i), 5), rtol=2e-6, atol=0), i
+    assert torch.allclose(rows[200], torch.linspace(0.3, 0.0, 5), atol=1e-7)            # linspace(near_end, far = 0)
+    assert float(rows[0, 0]) == pytest.approx(0.3) and float(rows[0, -1]) > 3.0
