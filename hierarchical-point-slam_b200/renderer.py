@@ -155,6 +155,7 @@ class Renderer(object):
             raise NotImplementedError("stage %r is not live in the reference" % (stage,))
         level = "mid" if stage.endswith("mid") else "fine"
         color_stage = stage.startswith("color")
+        no_depth_given = gt_depth is None
         if gt_depth is None or torch.numel(gt_depth) == 0:
             gt_depth = torch.zeros(N_rays, device=device)
         gt_depth = gt_depth.reshape(-1)
@@ -176,6 +177,8 @@ class Renderer(object):
             z_zero, near_mask = self._z_near_pcl(npc, rays_o, rays_d, gt_depth, radius, level)
         elif _z_zero_rows is not None:      # render_img: rows computed per reference chunk (_z_rows_for_zero_depth)
             z_zero = _z_zero_rows
+        elif no_depth_given:                # Renderer.py:135-141: without a depth image the far bound is 10 m
+            z_zero = _linspace32(self.near_end, torch.full((), 10.0, device=device), S, device)
         else:
             z_zero = self._z_for_zero_depth(gt_depth, device)
         geo = getattr(decoders, "geo_decoder_" + level)
