@@ -24,6 +24,14 @@ def setup_seed(seed):
     torch.backends.cudnn.benchmark = False
 
 
+def depth_inside_mask(batch_gt_depth):
+    """The batch filter both loops apply right before render_batch_ray (Tracker.py:179-181, Mapper.py:766-768, `nice`
+    branch without a bound): keep rays whose depth is <= min(10 median(d), 1.2 max(d)).  A batch-global statistic: under
+    ray sharding compute it BEFORE the split.  Device ops only; torch.median = the lower median, as there."""
+    with torch.no_grad():
+        return batch_gt_depth <= torch.minimum(10 * batch_gt_depth.median(), 1.2 * torch.max(batch_gt_depth))
+
+
 def as_intrinsics_matrix(intrinsics):
     """common.py:40-50: (fx, fy, cx, cy) -> 3x3 numpy matrix."""
     K = np.eye(3)

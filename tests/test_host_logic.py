@@ -407,3 +407,27 @@ def test_zero_depth_sampling_rows_follow_the_reference_chunks():
         assert torch.allclose(rows[i:i + chunk], want.expand(min(chunk, R - i), 5), rtol=2e-6, atol=0), i
     assert torch.allclose(rows[200], torch.linspace(0.3, 0.0, 5), atol=1e-7)            # linspace(near_end, far = 0)
     assert float(rows[0, 0]) == pytest.approx(0.3) and float(rows[0, -1]) > 3.0
+
+
+def test_depth_inside_mask_is_the_reference_statement():
+    """common.depth_inside_mask vs the reference's own statement executed where it lies (Tracker.py:179-181,
+    Mapper.py:766-768); skipped when the reference tree is absent (GPU box)."""
+    import os
+    import textwrap
+    ref = os.environ.get("HPS_REFERENCE_ROOT", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "src")):
+        pytest.skip("reference tree not present")
+    g = torch.Generator().manual_seed(9)
+    cases = [1.0 + 3.0 * torch.rand(1000, generator=g), torch.cat([0.2 * torch.rand(900, generator=g), 40 * torch.ones(100)]),
+             torch.tensor([2.0, 2.0, 2.0, 50.0]), torch.rand(7, generator=g)]
+    for name, first, last in (("Tracker.py", 179, 181), ("Mapper.py", 766, 768)):
+        with open(os.path.join(ref, "src", name)) as f:
+            src = textwrap.dedent("".join(f.readlines()[first - 1:last]))
+        assert src.startswith("with torch.no_grad():") and "median" in src
+        code = compile(src, "%s:%d-%d" % (name, first, last), "exec")
+        for d in cases:
+            ns = {"torch": torch, "batch_gt_depth": d}
+            exec(code, ns)
+            got = hps.common.depth_inside_mask(d)
+            assert got.dtype == torch.bool and torch.equal(got, ns["inside_mask"])
+    assert not bool(hps.common.depth_inside_mask(cases[1]).all())           # the 10 x median bound does bind there
