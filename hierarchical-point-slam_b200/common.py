@@ -32,6 +32,11 @@ def depth_inside_mask(batch_gt_depth):
         return batch_gt_depth <= torch.minimum(10 * batch_gt_depth.median(), 1.2 * torch.max(batch_gt_depth))
 
 
+def clone_kf_dict(keyframes_dict):
+    """common.py:523-531: a list of keyframe dicts with every tensor cloned (what npc.get_keyframe_dict hands out)."""
+    return [{key: value.clone() for key, value in keyframe.items()} for keyframe in keyframes_dict]
+
+
 def as_intrinsics_matrix(intrinsics):
     """common.py:40-50: (fx, fy, cx, cy) -> 3x3 numpy matrix."""
     K = np.eye(3)

@@ -297,7 +297,8 @@ class NeuralPointCloud(object):
         self.keyframe_dict = value
 
     def get_keyframe_dict(self):
-        return self.keyframe_dict
+        """neural_point.py:118-119: clones, so that the tracker's copy does not alias the mapper's tensors."""
+        return [{key: value.clone() for key, value in keyframe.items()} for keyframe in self.keyframe_dict]
 
     def get_index(self, level=None):
         return self.index[level]

@@ -431,3 +431,15 @@ def test_depth_inside_mask_is_the_reference_statement():
             got = hps.common.depth_inside_mask(d)
             assert got.dtype == torch.bool and torch.equal(got, ns["inside_mask"])
     assert not bool(hps.common.depth_inside_mask(cases[1]).all())           # the 10 x median bound does bind there
+
+
+def test_keyframe_dict_is_handed_out_as_clones():
+    npc = hps.NeuralPointCloud(hps.scannet_cfg("cpu"))
+    kf = [{"idx": torch.tensor(3), "color": torch.rand(4, 4, 3), "est_c2w": torch.eye(4)}]
+    npc.set_keyframe_dict(kf)
+    out = npc.get_keyframe_dict()
+    assert len(out) == 1 and torch.equal(out[0]["color"], kf[0]["color"])
+    out[0]["color"].zero_()
+    assert float(kf[0]["color"].abs().sum()) > 0                    # the caller's copy does not alias ours
+    again = hps.common.clone_kf_dict(kf)
+    assert again[0]["est_c2w"].data_ptr() != kf[0]["est_c2w"].data_ptr()
