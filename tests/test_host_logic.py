@@ -443,3 +443,28 @@ def test_keyframe_dict_is_handed_out_as_clones():
     assert float(kf[0]["color"].abs().sum()) > 0                    # the caller's copy does not alias ours
     again = hps.common.clone_kf_dict(kf)
     assert again[0]["est_c2w"].data_ptr() != kf[0]["est_c2w"].data_ptr()
+
+
+def test_gradient_guided_paths_match_the_reference_code(golden):
+    """Pixel pre-selection by colour gradient and the dynamic radius maps vs the fixture made by running the
+    reference's own get_selected_index_with_grad (common.py:199-233) and executing Tracker.py:297-323
+    (oracle/make_golden_gradient_sampling.py).  Only scikit-image's rgb2gray / sobel_h / sobel_v were stand-ins there
+    (restated with scipy.ndimage; skimage is not installed) - the top-k selection, window and depth masks, clipping at
+    color_grad_threshold and the interp1d maps are the reference's code with the real numpy / scipy."""
+    import numpy as np
+    fx = golden("gradient_small.pt")
+    H0, H1, W0, W1 = fx["window"]
+    img, depth, n, ratio = fx["image"], fx["depth"], fx["n"], fx["ratio"]
+    for limit, want in fx["selected"].items():
+        kw = {} if limit is None else dict(gt_depth=depth, depth_limit=limit)
+        sel, mag = hps.common.get_selected_index_with_grad(H0, H1, W0, W1, n, img, ratio=ratio, **kw)
+        assert np.array_equal(np.sort(sel), want.numpy()), limit
+        assert np.allclose(mag, fx["grad_mag"].numpy(), rtol=0, atol=1e-14)
+    r_add, r_query = hps.frame.dynamic_radius(img, fx["radius_hierarchy"], fx["radius_query_ratio"],
+                                              fx["color_grad_threshold"])
+    assert set(r_add) == set(fx["dynamic_r_add"]) == {"mid", "fine"}
+    for level in r_add:
+        for mine, want in ((r_add[level], fx["dynamic_r_add"][level]), (r_query[level], fx["dynamic_r_query"][level])):
+            assert mine.dtype == torch.float64 and mine.shape == want.shape
+            assert float((mine - want).abs().max()) <= 1e-15 + 4e-16 * float(want.abs().max())
+        assert float(r_add[level].max()) > float(r_add[level].min())            # the flat patch gets the large radius
