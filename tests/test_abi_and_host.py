@@ -156,3 +156,25 @@ def test_scannet_cfg_carries_the_reference_values(hps):
             assert ref[key] == val, (key, val, ref[key])
             checked += 1
     assert checked > 70
+
+
+def test_product_path_never_touches_the_oracle():
+    """The oracle is test infrastructure: no module of the product package, the scene generator or the scripts imports
+    it; bench.py does only inside its CPU leg (cpu_baseline / --impl reference); importing the package leaves
+    `oracle` out of sys.modules."""
+    import subprocess
+    import sys
+    pat = re.compile(r"^\s*(from\s+oracle\b|import\s+oracle\b)", re.M)
+    pkg = os.path.join(ROOT, "hierarchical-point-slam_b200")
+    files = [os.path.join(pkg, f) for f in os.listdir(pkg) if f.endswith(".py")]
+    files += [os.path.join(ROOT, f) for f in ("synthetic.py", "hps_b200.py")]
+    files += [os.path.join(ROOT, "scripts", f) for f in os.listdir(os.path.join(ROOT, "scripts")) if f.endswith(".py")]
+    for path in files:
+        assert not pat.search(open(path).read()), path
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    hits = [m.start() for m in pat.finditer(bench)]
+    assert len(hits) == 1
+    head = bench[:hits[0]]
+    assert head.rfind("\ndef ") == head.rfind("\ndef cpu_step_fn")       # inside the CPU leg's step function only
+    code = "import sys; sys.path.insert(0, %r); import hps_b200; assert 'oracle' not in sys.modules" % ROOT
+    assert subprocess.run([sys.executable, "-c", code]).returncode == 0
