@@ -468,3 +468,106 @@ def test_gradient_guided_paths_match_the_reference_code(golden):
             assert mine.dtype == torch.float64 and mine.shape == want.shape
             assert float((mine - want).abs().max()) <= 1e-15 + 4e-16 * float(want.abs().max())
         assert float(r_add[level].max()) > float(r_add[level].min())            # the flat patch gets the large radius
+
+
+@pytest.mark.parametrize("separate_LR", [False, True])
+def test_tracker_optimizer_follows_the_reference_construction(monkeypatch, separate_LR):
+    """TrackerOptimizer vs the reference's own optimiser construction - Tracker.py:383-415 EXECUTED where it lies
+    (pose as one 7-vector or as translation + quaternion with lr / 5, exposure latent and both exposure MLPs at 0.001) -
+    over 14 iterations of a non-monotone loss, with the keep-the-best-pose rule of Tracker.py:435-437.  The Adam entry
+    point is emulated (numpy on the raw pointers, documented semantics of hps_adam_multi); the kernel itself is checked
+    in the GPU suite.  Skipped when the reference tree is absent."""
+    import contextlib
+    import copy
+    import ctypes
+    import math
+    import os
+    import textwrap
+    import types
+    import numpy as np
+    from torch.autograd import Variable
+    ref_root = os.environ.get("HPS_REFERENCE_ROOT", "/root/reference")
+    if not os.path.isdir(os.path.join(ref_root, "src")):
+        pytest.skip("reference tree not present")
+
+    def arr(ptr, n, dt=np.float32):
+        if isinstance(ptr, ctypes.c_void_p):
+            ptr = ptr.value
+        return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,))
+
+    def fake_call(name, *a):
+        assert name == "hps_adam_multi", name
+        n, ps, gs, ms, vs, numel, lrs, b1, b2, eps, step, zero_grad, _stream = a
+        st = arr(step, 2, np.int32)
+        t = int(st[0]) + 1
+        b1, b2 = np.float32(b1), np.float32(b2)
+        bc1, bc2 = np.float32(1 - float(b1) ** t), np.float32(1 - float(b2) ** t)
+        for i in range(n):
+            p, g, m, v = (arr(x[i], numel[i]) for x in (ps, gs, ms, vs))
+            m[:] = m + (g - m) * (np.float32(1) - b1)
+            v[:] = v * b2 + (np.float32(1) - b2) * g * g
+            p[:] = p - (np.float32(lrs[i]) / bc1) * (m / (np.sqrt(v) / np.sqrt(bc2) + np.float32(eps)))
+            if zero_grad:
+                g[:] = 0
+        st[0] = t
+
+    monkeypatch.setattr(ops, "_call", fake_call)
+    monkeypatch.setattr(ops, "_need_cuda", lambda *t: None)
+    monkeypatch.setattr(ops, "_stream", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "device", lambda d: contextlib.nullcontext())
+
+    cfg = hps.scannet_cfg("cpu")
+    tracking = dict(cfg["tracking"], separate_LR=separate_LR, iters=14)
+    torch.manual_seed(1219)
+    dec_mine = hps.get_model(cfg)
+    dec_ref = copy.deepcopy(dec_mine)
+    g = torch.Generator().manual_seed(3)
+    cam0 = torch.tensor([0.99, 0.05, -0.08, 0.03, 0.4, -0.2, 0.1]) + 0.01 * torch.randn(7, generator=g)
+    ef_mine = (0.3 * torch.randn(8, generator=g)).requires_grad_(True)
+    ef_ref = ef_mine.detach().clone().requires_grad_(True)
+    target = cam0 + 0.02 * torch.randn(7, generator=g)
+
+    # ---- the reference's construction, executed
+    with open(os.path.join(ref_root, "src", "Tracker.py")) as f:
+        src = textwrap.dedent("".join(f.readlines()[382:415]))
+    assert src.startswith("if self.separate_LR:") and src.rstrip().endswith("optimizer_camera = torch.optim.Adam(optim_para_list)")
+    me = types.SimpleNamespace(separate_LR=separate_LR, cam_lr=tracking["lr"], encode_exposure=True, exposure_feat=ef_ref,
+                               decoders=dec_ref, quad=None, T=None)
+    ns = dict(torch=torch, Variable=Variable, self=me, camera_tensor=cam0.clone(), device="cpu")
+    exec(compile(src, "Tracker.py:383-415", "exec"), ns)
+    topt = ns["optimizer_camera"]
+    assert [grp["lr"] for grp in topt.param_groups] == ([tracking["lr"], tracking["lr"] * 0.2] if separate_LR else
+                                                        [tracking["lr"]]) + [0.001] * 3
+
+    opt = hps.TrackerOptimizer(tracking, cam0.clone(), ef_mine, dec_mine)
+    assert [opt.stage(k) for k in (0, 6, 7, 13)] == ["color_mid", "color_mid", "color_fine", "color_fine"]
+
+    def loss_of(cam, ef, dec, k):
+        mlps = list(dec.color_decoder_mid.mlp_exposure.parameters()) + list(dec.color_decoder_fine.mlp_exposure.parameters())
+        wobble = 1.0 + 0.9 * math.sin(1.7 * k)                       # non-monotone: the best pose is an interior iteration
+        return (100 * wobble * ((cam - target) ** 2).sum() + (ef ** 2).sum()
+                + sum((p * p).sum() for p in mlps) * 0.1 + wobble)
+
+    current_min_loss, candidate = float(1e20), None
+    for k in range(opt.num_cam_iters):
+        cam = opt.camera_tensor()
+        loss = loss_of(cam, ef_mine, dec_mine, k)
+        loss.backward()
+        opt.step(loss)
+        # reference iteration: Tracker.py:428-437 (+ the zero_grad / backward / step of optimize_cam_in_batch)
+        rcam = torch.cat([me.quad, me.T], 0) if separate_LR else ns["camera_tensor"]
+        topt.zero_grad()
+        rloss = loss_of(rcam, ef_ref, dec_ref, k)
+        rloss.backward()
+        topt.step()
+        if rloss.item() < current_min_loss:
+            current_min_loss = rloss.item()
+            candidate = rcam.clone().detach()
+        mine_now = torch.cat(opt.leaves, 0).detach() if separate_LR else opt.leaves[0].detach()
+        ref_now = torch.cat([me.quad, me.T], 0).detach() if separate_LR else ns["camera_tensor"].detach()
+        assert float((mine_now - ref_now).abs().max()) < 2e-6, k
+        assert float((ef_mine.detach() - ef_ref.detach()).abs().max()) < 2e-6
+    assert abs(float(opt.best_loss) - current_min_loss) <= 1e-4 * abs(current_min_loss)
+    assert float((opt.best_camera_tensor - candidate).abs().max()) < 2e-6
+    for a, b in zip(dec_mine.color_decoder_fine.mlp_exposure.parameters(), dec_ref.color_decoder_fine.mlp_exposure.parameters()):
+        assert float((a.detach() - b.detach()).abs().max()) < 2e-6
