@@ -571,3 +571,53 @@ def test_tracker_optimizer_follows_the_reference_construction(monkeypatch, separ
     assert float((opt.best_camera_tensor - candidate).abs().max()) < 2e-6
     for a, b in zip(dec_mine.color_decoder_fine.mlp_exposure.parameters(), dec_ref.color_decoder_fine.mlp_exposure.parameters()):
         assert float((a.detach() - b.detach()).abs().max()) < 2e-6
+
+
+def test_mapper_optimizer_groups_follow_the_reference_construction(monkeypatch):
+    """MapperOptimizer's tensor -> learning-rate mapping vs the reference's own optimiser: Mapper.py:590-603 (the seven
+    parameter groups) and :633-666 (per-iteration learning rates) EXECUTED where they lie, for every iteration of a
+    600-iteration mapping with BA.  Every tensor must carry the learning rate of the reference group that holds it.
+    Skipped when the reference tree is absent."""
+    import os
+    import textwrap
+    import types
+    ref_root = os.environ.get("HPS_REFERENCE_ROOT", "/root/reference")
+    if not os.path.isdir(os.path.join(ref_root, "src")):
+        pytest.skip("reference tree not present")
+    monkeypatch.setattr(ops, "_need_cuda", lambda *t: None)
+    with open(os.path.join(ref_root, "src", "Mapper.py")) as f:
+        lines = f.readlines()
+    build_src = textwrap.dedent("".join(lines[589:603]))
+    loop_src = textwrap.dedent("".join(lines[632:666]))
+    assert build_src.startswith("if self.nice:") and build_src.rstrip().endswith("optimizer = torch.optim.Adam(optim_para_list)")
+    assert loop_src.startswith("if joint_iter <=")
+    mapping = hps.scannet_cfg("cpu")["mapping"]
+    mk = lambda *s: torch.randn(*s).requires_grad_(True)
+    dec = [mk(4, 3), mk(4), mk(2, 4)]
+    rows = {"geometry_mid": mk(10, 32), "geometry_fine": mk(12, 32), "color_mid": mk(10, 32), "color_fine": mk(12, 32)}
+    cams, expo = [mk(7), mk(7)], mk(8)
+    me = types.SimpleNamespace(nice=True, BA=True, encode_exposure=True, exposure_feat=expo, stage=None,
+                               geo_iter_first=mapping["geo_iter_first"], geo_iter_ratio=mapping["geo_iter_ratio"],
+                               n_img=100, color_refine=False, BA_cam_lr=mapping["BA_cam_lr"])
+    ns = dict(torch=torch, self=me, decoders_para_list=dec, geo_pcl_para_mid=[rows["geometry_mid"]],
+              geo_pcl_para_fine=[rows["geometry_fine"]], color_pcl_para_mid=[rows["color_mid"]],
+              color_pcl_para_fine=[rows["color_fine"]], camera_tensor_list=cams, cfg={"mapping": mapping}, idx=5,
+              init=False, color_refine=False)
+    exec(compile(build_src, "Mapper.py:590-603", "exec"), ns)
+    ref_opt = ns["optimizer"]
+    opt = hps.MapperOptimizer(mapping, decoder_params=dec, rows=rows, cameras=cams, exposure_feat=expo)
+    n_iters = mapping["iters"]
+    ns["num_mid_iters"], ns["num_fine_iters"] = hps.mapper_optim.split_iters(n_iters, mapping["mid_iter_ratio"])
+    loop_code = compile(loop_src, "Mapper.py:633-666", "exec")
+    for joint_iter in range(n_iters):
+        ns["joint_iter"] = joint_iter
+        exec(loop_code, ns)
+        assert opt.set_iteration(joint_iter, n_iters, BA=True) == me.stage
+        want = {}
+        for grp in ref_opt.param_groups:
+            for p in grp["params"]:
+                want[id(p)] = float(grp["lr"])
+        got = {id(p): lr for p, lr in zip(opt.small_opt.params, opt.small_opt.lrs)}
+        got.update({id(r.param): lr for r, lr in opt.row_opt.groups})
+        assert got == want, joint_iter
+    assert len(want) == len(dec) + 4 + len(cams) + 1
