@@ -178,3 +178,22 @@ def test_product_path_never_touches_the_oracle():
     assert head.rfind("\ndef ") == head.rfind("\ndef cpu_step_fn")       # inside the CPU leg's step function only
     code = "import sys; sys.path.insert(0, %r); import hps_b200; assert 'oracle' not in sys.modules" % ROOT
     assert subprocess.run([sys.executable, "-c", code]).returncode == 0
+
+
+def test_geometry_decoder_loads_the_reference_checkpoint(hps):
+    """The only checkpoint the reference ships, pretrained/color.pt (a hidden-32, 93-frequency decoder: fc_c.*,
+    embedder._B (3,93), pts_linears.*, output_linear (4,32)), loads into the product's geometry decoder under
+    the same parameter names - everything but its 4-channel output layer.  Skipped when the reference tree is absent."""
+    path = os.path.join(os.environ.get("HPS_REFERENCE_ROOT", "/root/reference"), "pretrained", "color.pt")
+    if not os.path.exists(path):
+        pytest.skip("reference checkpoint not present")
+    sd = torch.load(path, map_location="cpu", weights_only=False)
+    dec = hps.get_model(hps.scannet_cfg("cpu"))
+    for m in (dec.geo_decoder_mid, dec.geo_decoder_fine):          # Point_SLAM.py:257-260 loads one file into both levels
+        own = m.state_dict()
+        fit = {k: v for k, v in sd.items() if k in own and own[k].shape == v.shape}
+        assert sorted(set(sd) - set(fit)) == ["output_linear.bias", "output_linear.weight"]
+        assert set(sd) <= set(own)                                 # same names, the output layer differs in shape only
+        res = m.load_state_dict(fit, strict=False)
+        assert not res.unexpected_keys
+        assert torch.equal(m.embedder._B, sd["embedder._B"]) and torch.equal(m.pts_linears[3].weight, sd["pts_linears.3.weight"])
