@@ -357,6 +357,13 @@ def test_frustum_selection_arithmetic_matches_the_reference_method(golden):
     x[:4] = torch.tensor([float("nan"), float("inf"), -1e12, 639.0])
     mine = npm.remap_bilinear(fx["depth"], x, y)
     assert np.array_equal(mine.numpy(), O.remap_bilinear_cv2(fx["depth"].numpy(), x.numpy(), y.numpy()))
+    try:
+        import cv2
+    except ImportError:
+        return
+    ref = np.concatenate([cv2.remap(fx["depth"].numpy(), x.numpy()[i:i + 30000], y.numpy()[i:i + 30000],
+                                    interpolation=cv2.INTER_LINEAR)[:, 0] for i in range(0, 50_000, 30000)])
+    assert np.array_equal(mine.numpy(), ref)                       # the product's sampler IS cv2.remap, bit for bit
 
 
 def test_neural_point_cloud_reference_accessors():
