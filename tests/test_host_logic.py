@@ -628,3 +628,22 @@ def test_mapper_optimizer_groups_follow_the_reference_construction(monkeypatch):
         got.update({id(r.param): lr for r, lr in opt.row_opt.groups})
         assert got == want, joint_iter
     assert len(want) == len(dec) + 4 + len(cams) + 1
+
+
+def test_host_side_sampling_equals_the_oracle_bit_for_bit():
+    """Renderer.surface_samples + _z_for_zero_depth (the torch expressions the sampling kernel is held to in the GPU
+    suite) vs the oracle's surface_z_vals, which the fixtures pin to the reference (Renderer.py:131-208) with zero
+    error: positive depths, missing depths (their range is a batch statistic), an all-missing batch, a batch where
+    5 mean(d) undercuts 1.2 max(d)."""
+    import types
+    from oracle import hps_oracle as O
+    r = hps.Renderer(hps.scannet_cfg("cpu"), None, types.SimpleNamespace(H=4, W=4, fx=1.0, fy=1.0, cx=2.0, cy=2.0))
+    g = torch.Generator().manual_seed(12)
+    batches = [0.5 + 4.0 * torch.rand(300, generator=g), torch.zeros(40), torch.cat([torch.full((90,), 0.02), torch.tensor([7.0])])]
+    batches[0][torch.rand(300, generator=g) < 0.15] = 0.0
+    batches[2][::7] = 0.0
+    for gt in batches:
+        z, nz = r.surface_samples(gt, "cpu")
+        z = torch.where(nz[:, None], z, r._z_for_zero_depth(gt, "cpu")[None, :].expand_as(z))
+        want, want_nz = O.surface_z_vals(gt)
+        assert torch.equal(nz, want_nz) and torch.equal(z, want), float((z - want).abs().max())
