@@ -647,3 +647,28 @@ def test_host_side_sampling_equals_the_oracle_bit_for_bit():
         z = torch.where(nz[:, None], z, r._z_for_zero_depth(gt, "cpu")[None, :].expand_as(z))
         want, want_nz = O.surface_z_vals(gt)
         assert torch.equal(nz, want_nz) and torch.equal(z, want), float((z - want).abs().max())
+
+
+def test_host_side_pose_expressions_equal_the_oracle():
+    """The product's torch expressions for the pose / ray helpers (common.py:103-119, 304-346; what the GPU suite holds the
+    pose kernels to) vs the oracle, which the tracker fixtures pin to the reference (pose gradient error 0.0):
+    pose matrix, ray origins / directions and the gradient to the 7-vector, bit for bit."""
+    from oracle import hps_oracle as O
+    g = torch.Generator().manual_seed(14)
+    K = O.SCANNET_INTRINSICS
+    for _ in range(4):
+        cam = torch.cat([torch.randn(4, generator=g), torch.randn(3, generator=g)])
+        cam[:4] = cam[:4] / cam[:4].norm() * (1.0 + 0.05 * float(torch.randn((), generator=g)))     # not exactly unit
+        i = torch.randint(0, K["W"], (50,), generator=g).float()
+        j = torch.randint(0, K["H"], (50,), generator=g).float()
+        outs = []
+        for fn_cam, fn_rays in ((hps.get_camera_from_tensor, lambda i_, j_, c: hps.get_rays_from_uv(
+                i_, j_, c, K["H"], K["W"], K["fx"], K["fy"], K["cx"], K["cy"], "cpu")),
+                (O.camera_from_tensor, lambda i_, j_, c: O.rays_from_uv(i_, j_, c, K["fx"], K["fy"], K["cx"], K["cy"]))):
+            c = cam.clone().requires_grad_(True)
+            c2w = fn_cam(c)
+            ro, rd = fn_rays(i, j, c2w)
+            ((rd * torch.arange(1, 4)).sum() + (ro * torch.tensor([0.3, -0.2, 0.5])).sum()).backward()
+            outs.append((c2w.detach(), ro.detach(), rd.detach(), c.grad.clone()))
+        for a, b in zip(*outs):
+            assert a.shape == b.shape and torch.equal(a, b)
