@@ -197,3 +197,33 @@ def test_geometry_decoder_loads_the_reference_checkpoint(hps):
         res = m.load_state_dict(fit, strict=False)
         assert not res.unexpected_keys
         assert torch.equal(m.embedder._B, sd["embedder._B"]) and torch.equal(m.pts_linears[3].weight, sd["pts_linears.3.weight"])
+
+
+def test_header_is_plain_c_and_links_from_c(hps, tmp_path):
+    """include/hps_b200.h is a C header (no C++ / torch types in the signatures): it compiles as C99 and as C++17, and a
+    C program that includes it links against libhps_b200.so and calls the version / size / error entry points (no device
+    needed for those)."""
+    import shutil
+    import subprocess
+    gcc, gxx = shutil.which("gcc"), shutil.which("g++")
+    if not gcc or not gxx:
+        pytest.skip("no host compiler")
+    hdr = os.path.join(ROOT, "include", "hps_b200.h")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call([gxx, "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-x", "c++", hdr])
+    src = tmp_path / "use.c"
+    src.write_text('#include <stdio.h>\n#include <string.h>\n#include "hps_b200.h"\n'
+                   "int main(void) {\n"
+                   "    if (hps_version() < 1) return 1;\n"
+                   "    if (hps_mlp_act_floats(HPS_MLP_COL) != 1280) return 2;\n"
+                   "    if (hps_adam_rows(0, 0, 0, 0, 4, 30, 1e-3f, 0.9f, 0.999f, 1e-8f, 0, 0, 0, 0) >= 0) return 3;\n"
+                   '    if (!strstr(hps_last_error(), "C % 4 == 0")) return 4;\n'
+                   '    printf("ok %d\\n", hps_version());\n    return 0;\n}\n')
+    exe = tmp_path / "use"
+    libdir = os.path.dirname(hps._lib.LIB_PATH)
+    cuda_lib = "/usr/local/cuda/lib64"
+    subprocess.check_call([gcc, "-std=c99", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe), "-L", libdir,
+                           "-l:libhps_b200.so", "-Wl,-rpath," + libdir, "-Wl,-rpath," + cuda_lib,
+                           "-Wl,--allow-shlib-undefined"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("ok "), (out.returncode, out.stdout, out.stderr)
