@@ -672,3 +672,77 @@ def test_host_side_pose_expressions_equal_the_oracle():
             outs.append((c2w.detach(), ro.detach(), rd.detach(), c.grad.clone()))
         for a, b in zip(*outs):
             assert a.shape == b.shape and torch.equal(a, b)
+
+
+def test_point_insertion_host_logic_matches_the_reference_class(monkeypatch, golden):
+    """NeuralPointCloud.add_neural_points on CPU tensors with the neighbour search answered by the oracle (the one part
+    that is a CUDA kernel; it is checked bit-exact in the GPU suite): the masking, the float32 sample arithmetic, the
+    order of the appended points and the returned counts reproduce the fixture made by running the unmodified reference
+    class (oracle/make_golden_insertion.py) - the body of the GPU test, run here."""
+    from oracle import hps_oracle as O
+    npm = hps.neural_point
+
+    def radius_search(self, q, radius, want_cand=False):
+        q = q.detach().float().reshape(-1, 3)
+        D, I, n = O.find_neighbors(self._pos, q, radius)
+        t_up, t_dn = O.radius_thresholds(radius, q.shape[0])
+        return npm.NeighborQuery(I.int(), D, n, t_up, t_dn)
+
+    monkeypatch.setattr(npm.GridIndex, "radius_search", radius_search)
+    monkeypatch.setattr(ops, "_need_cuda", lambda *t: None)
+    from tests import test_gpu_render as T
+    monkeypatch.setattr(T, "DEV", "cpu")
+    T.test_add_neural_points_matches_the_reference_class(hps, golden)
+
+
+@pytest.mark.parametrize("min_chunk", [1, 300, 65536])
+def test_render_img_host_logic_matches_the_reference_frame(monkeypatch, golden, min_chunk):
+    """Renderer.render_img's own code - ray generation, the chunk loop, the per-reference-chunk sampling rows handed to
+    wide chunks, the float64 images - with render_batch_ray answered by the oracle (the fused kernels are what the GPU suite
+    checks): the reference's frame (tests/golden/render_img_small.pt) comes out for the reference's chunking (100 rays),
+    for 300-ray chunks that straddle reference chunks, and for one wide chunk."""
+    import types
+    from oracle import hps_oracle as O
+    fx, sc = golden("render_img_small.pt"), golden("scene_small.pt")
+    cl = sc["clouds"]
+    seen = []
+
+    def render_batch_ray(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None, npc_geo_feats=None,
+                         npc_col_feats=None, is_tracker=False, cloud_pos=None, normals=None, dynamic_r_query=None,
+                         exposure_feat=None, prepared=None, _loss=None, _z_zero_rows=None):
+        seen.append((rays_o.shape[0], _z_zero_rows is not None))
+        orig = O.surface_z_vals
+
+        def patched(gt, *a, **k):
+            z, nz = orig(gt, *a, **k)
+            if _z_zero_rows is not None:
+                assert _z_zero_rows.shape == z.shape and _z_zero_rows.is_contiguous()
+                z[~nz] = _z_zero_rows[~nz]
+            return z, nz
+        O.surface_z_vals = patched
+        try:
+            return O.render_batch_ray({l: cl[l]["points"] for l in cl}, sc["decoders"], rays_d, rays_o, stage, gt_depth,
+                                      npc_geo_feats, npc_col_feats, {l: v.reshape(-1) for l, v in dynamic_r_query.items()},
+                                      sc["c_fill_geo"], sc["c_fill_col"], exposure_feat=exposure_feat)
+        finally:
+            O.surface_z_vals = orig
+
+    monkeypatch.setattr(hps.Renderer, "render_batch_ray", render_batch_ray)
+    small = hps.Renderer(hps.scannet_cfg("cpu"), None, types.SimpleNamespace(H=fx["H"], W=fx["W"], **fx["intrinsics"]),
+                         ray_batch_size=fx["ray_batch_size"])
+    small.min_render_chunk = min_chunk
+    for stage, want in fx["stages"].items():
+        del seen[:]
+        d, u, c = small.render_img(None, None, fx["c2w"], "cpu", stage, gt_depth=fx["depth"].clone(),
+                                   npc_geo_feats={l: cl[l]["geo_feats"] for l in cl},
+                                   npc_col_feats={l: cl[l]["col_feats"] for l in cl},
+                                   dynamic_r_query={l: fx["radius"][l].clone() for l in cl}, exposure_feat=sc["exposure_feat"])
+        B = max(fx["ray_batch_size"], min_chunk)
+        assert [n for n, _ in seen] == [min(B, fx["H"] * fx["W"] - i) for i in range(0, fx["H"] * fx["W"], B)]
+        assert all(rows == (B > fx["ray_batch_size"]) for _, rows in seen)
+        assert d.dtype == torch.float64 and u.dtype == torch.float64 and d.shape == (fx["H"], fx["W"])
+        if min_chunk == 1:
+            assert torch.equal(d, want["depth"]) and torch.equal(c, want["color"]) and torch.equal(u, want["uncertainty"])
+        else:
+            assert float((d - want["depth"]).abs().max()) < 1e-5 and float((c - want["color"]).abs().max()) < 1e-5
+            assert float((u - want["uncertainty"]).abs().max()) < 1e-5 * float(want["uncertainty"].max())
