@@ -824,3 +824,58 @@ def test_render_img_matches_the_reference_frame(built, golden, chunks):
         assert parity.rel(d, want["depth"]) < parity.TOL, (stage, parity.rel(d, want["depth"]))
         assert parity.rel(u, want["uncertainty"]) < parity.TOL, (stage, parity.rel(u, want["uncertainty"]))
         assert float((c - want["color"]).abs().max()) < parity.TOL, (stage, float((c - want["color"]).abs().max()))
+
+
+@pytest.mark.parametrize("separate_LR", [False, True])
+def test_tracker_optimizer_on_the_device(hps, separate_LR):
+    """TrackerOptimizer (Tracker.py:383-415 as one FusedAdam launch + the keep-the-best-pose rule :435-437 on the device)
+    vs torch.optim.Adam over the same groups and the rule spelled out on the host, 14 iterations of a non-monotone loss.
+    (Its CPU twin, tests/test_host_logic.py, builds the reference optimiser by executing the reference's source.)"""
+    import copy
+    import math
+    cfg = hps.scannet_cfg(DEV)
+    tracking = dict(cfg["tracking"], separate_LR=separate_LR, iters=14)
+    torch.manual_seed(1219)
+    dec_mine = hps.get_model(cfg).to(DEV)
+    dec_ref = copy.deepcopy(dec_mine)
+    g = torch.Generator().manual_seed(3)
+    cam0 = (torch.tensor([0.99, 0.05, -0.08, 0.03, 0.4, -0.2, 0.1]) + 0.01 * torch.randn(7, generator=g)).to(DEV)
+    ef_mine = (0.3 * torch.randn(8, generator=g)).to(DEV).requires_grad_(True)
+    ef_ref = ef_mine.detach().clone().requires_grad_(True)
+    target = cam0 + 0.02 * torch.randn(7, generator=g).to(DEV)
+    opt = hps.TrackerOptimizer(tracking, cam0.clone(), ef_mine, dec_mine)
+    lr = tracking["lr"]
+    if separate_LR:
+        quad, T = cam0[:4].clone().requires_grad_(True), cam0[-3:].clone().requires_grad_(True)
+        groups = [{"params": [T], "lr": lr}, {"params": [quad], "lr": lr * 0.2}]
+    else:
+        rcam_leaf = cam0.clone().requires_grad_(True)
+        groups = [{"params": [rcam_leaf], "lr": lr}]
+    groups += [{"params": [ef_ref], "lr": 0.001},
+               {"params": list(dec_ref.color_decoder_mid.mlp_exposure.parameters()), "lr": 0.001},
+               {"params": list(dec_ref.color_decoder_fine.mlp_exposure.parameters()), "lr": 0.001}]
+    topt = torch.optim.Adam(groups)
+
+    def loss_of(cam, ef, dec, k):
+        mlps = list(dec.color_decoder_mid.mlp_exposure.parameters()) + list(dec.color_decoder_fine.mlp_exposure.parameters())
+        wobble = 1.0 + 0.9 * math.sin(1.7 * k)
+        return 100 * wobble * ((cam - target) ** 2).sum() + (ef ** 2).sum() + sum((p * p).sum() for p in mlps) * 0.1 + wobble
+
+    best, candidate = float(1e20), None
+    for k in range(opt.num_cam_iters):
+        loss = loss_of(opt.camera_tensor(), ef_mine, dec_mine, k)
+        loss.backward()
+        opt.step(loss)
+        rcam = torch.cat([quad, T], 0) if separate_LR else rcam_leaf
+        topt.zero_grad()
+        rloss = loss_of(rcam, ef_ref, dec_ref, k)
+        rloss.backward()
+        topt.step()
+        if rloss.item() < best:
+            best, candidate = rloss.item(), rcam.clone().detach()
+        mine_now = torch.cat(opt.leaves, 0).detach() if separate_LR else opt.leaves[0].detach()
+        ref_now = torch.cat([quad, T], 0).detach() if separate_LR else rcam_leaf.detach()
+        assert float((mine_now - ref_now).abs().max()) < 5e-6, k
+    assert abs(float(opt.best_loss) - best) <= 1e-4 * abs(best)
+    assert float((opt.best_camera_tensor - candidate).abs().max()) < 5e-6
+    assert float((ef_mine.detach() - ef_ref.detach()).abs().max()) < 5e-6
