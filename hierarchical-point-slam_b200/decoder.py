@@ -94,6 +94,12 @@ class PointDecoder(nn.Module):
         self.N_surface = cfg["rendering"]["N_surface"]
         self.use_dynamic_radius = cfg["use_dynamic_radius"]
         self.encode_exposure = cfg["model"].get("encode_exposure", False) if kind == "col" else False
+        if kind == "col" and not self.encode_exposure:
+            # decoder.py:615 ends the colour decoder with torch.sigmoid when encode_exposure is off (the default of
+            # configs/point_slam.yaml; every ScanNet / Replica / TUM config turns it on): that tail is not in the kernels,
+            # and silently returning the raw linear output would be wrong - loud instead
+            raise NotImplementedError("model.encode_exposure=False (sigmoid colour tail, decoder.py:615) is not built; "
+                                      "the reference's dataset configurations all set it True")
         if cfg["pointcloud"]["nn_weighting"] != "distance":
             raise NotImplementedError("only nn_weighting='distance' is built (the ScanNet configuration)")
         if cfg["model"].get("encode_rel_pos_in_col" if kind == "col" else "encode_rel_pos_in_geo", False):

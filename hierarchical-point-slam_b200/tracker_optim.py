@@ -64,8 +64,11 @@ class TrackerOptimizer:
         self.separate_LR = bool(tracking_cfg.get("separate_LR", False))
         groups, self.leaves = tracker_param_groups(float(tracking_cfg["lr"]), camera_tensor, self.separate_LR,
                                                    exposure_feat, decoders, encode_exposure)
-        # own_grads=False: backward hands its gradient buffers over, zero_grad() drops them (Tracker.py:233-235)
-        self.opt = FusedAdam(groups, own_grads=False)
+        # own_grads=False: backward hands its gradient buffers over, zero_grad() drops them (Tracker.py:233-235).
+        # per_tensor_steps: torch.optim.Adam keeps state[p]['step'] per parameter and skips parameters without a
+        # gradient - the fine level's exposure MLP sees its first gradient at cam_iter = iters / 2 (the mid level renders
+        # first, :190-212) and must then start its bias correction at t = 1, not at t = iters / 2 + 1.
+        self.opt = FusedAdam(groups, own_grads=False, per_tensor_steps=True)
         dev = camera_tensor.device
         self.best_loss = torch.full((), float(1e20), device=dev)          # current_min_loss, Tracker.py:419
         self.best_camera_tensor = camera_tensor.detach().clone()          # candidate_cam_tensor

@@ -857,7 +857,10 @@ def test_tracker_optimizer_on_the_device(hps, separate_LR):
     topt = torch.optim.Adam(groups)
 
     def loss_of(cam, ef, dec, k):
-        mlps = list(dec.color_decoder_mid.mlp_exposure.parameters()) + list(dec.color_decoder_fine.mlp_exposure.parameters())
+        # like the tracker: mid level (and only its exposure MLP) in the first half, fine level in the second - the fine
+        # MLP's first Adam step must use bias correction t = 1 (torch keeps state[p]['step'] per parameter)
+        level = "mid" if opt.stage(k) == "color_mid" else "fine"
+        mlps = list(getattr(dec, "color_decoder_" + level).mlp_exposure.parameters())
         wobble = 1.0 + 0.9 * math.sin(1.7 * k)
         return 100 * wobble * ((cam - target) ** 2).sum() + (ef ** 2).sum() + sum((p * p).sum() for p in mlps) * 0.1 + wobble
 
@@ -879,3 +882,9 @@ def test_tracker_optimizer_on_the_device(hps, separate_LR):
     assert abs(float(opt.best_loss) - best) <= 1e-4 * abs(best)
     assert float((opt.best_camera_tensor - candidate).abs().max()) < 5e-6
     assert float((ef_mine.detach() - ef_ref.detach()).abs().max()) < 5e-6
+    for level in ("mid", "fine"):
+        for a, b in zip(getattr(dec_mine, "color_decoder_" + level).mlp_exposure.parameters(),
+                        getattr(dec_ref, "color_decoder_" + level).mlp_exposure.parameters()):
+            assert float((a.detach() - b.detach()).abs().max()) < 5e-6, level
+    steps = opt.opt.tensor_steps.tolist()
+    assert max(steps) == opt.num_cam_iters and min(steps) == opt.num_cam_iters // 2

@@ -503,20 +503,21 @@ def test_tracker_optimizer_follows_the_reference_construction(monkeypatch, separ
         return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n,))
 
     def fake_call(name, *a):
-        assert name == "hps_adam_multi", name
-        n, ps, gs, ms, vs, numel, lrs, b1, b2, eps, step, zero_grad, _stream = a
-        st = arr(step, 2, np.int32)
-        t = int(st[0]) + 1
+        # per-parameter step counters (torch.optim.Adam's state[p]['step']): documented semantics of hps_adam_multi_own_steps
+        assert name == "hps_adam_multi_own_steps", name
+        n, ps, gs, ms, vs, numel, lrs, steps, b1, b2, eps, done, zero_grad, _stream = a
         b1, b2 = np.float32(b1), np.float32(b2)
-        bc1, bc2 = np.float32(1 - float(b1) ** t), np.float32(1 - float(b2) ** t)
         for i in range(n):
+            st = arr(steps[i], 1, np.int32)
+            t = int(st[0]) + 1
+            bc1, bc2 = np.float32(1 - float(b1) ** t), np.float32(1 - float(b2) ** t)
             p, g, m, v = (arr(x[i], numel[i]) for x in (ps, gs, ms, vs))
             m[:] = m + (g - m) * (np.float32(1) - b1)
             v[:] = v * b2 + (np.float32(1) - b2) * g * g
             p[:] = p - (np.float32(lrs[i]) / bc1) * (m / (np.sqrt(v) / np.sqrt(bc2) + np.float32(eps)))
             if zero_grad:
                 g[:] = 0
-        st[0] = t
+            st[0] = t
 
     monkeypatch.setattr(ops, "_call", fake_call)
     monkeypatch.setattr(ops, "_need_cuda", lambda *t: None)
@@ -550,7 +551,11 @@ def test_tracker_optimizer_follows_the_reference_construction(monkeypatch, separ
     assert [opt.stage(k) for k in (0, 6, 7, 13)] == ["color_mid", "color_mid", "color_fine", "color_fine"]
 
     def loss_of(cam, ef, dec, k):
-        mlps = list(dec.color_decoder_mid.mlp_exposure.parameters()) + list(dec.color_decoder_fine.mlp_exposure.parameters())
+        # as in the tracker (Tracker.py:190-212): the first half of the iterations renders the mid level, so only ITS
+        # exposure MLP receives a gradient; the fine level's MLP gets its first gradient at k = iters / 2 and
+        # torch.optim.Adam then starts that parameter's bias correction at step 1
+        level = "mid" if opt.stage(k) == "color_mid" else "fine"
+        mlps = list(getattr(dec, "color_decoder_" + level).mlp_exposure.parameters())
         wobble = 1.0 + 0.9 * math.sin(1.7 * k)                       # non-monotone: the best pose is an interior iteration
         return (100 * wobble * ((cam - target) ** 2).sum() + (ef ** 2).sum()
                 + sum((p * p).sum() for p in mlps) * 0.1 + wobble)
@@ -576,8 +581,13 @@ def test_tracker_optimizer_follows_the_reference_construction(monkeypatch, separ
         assert float((ef_mine.detach() - ef_ref.detach()).abs().max()) < 2e-6
     assert abs(float(opt.best_loss) - current_min_loss) <= 1e-4 * abs(current_min_loss)
     assert float((opt.best_camera_tensor - candidate).abs().max()) < 2e-6
-    for a, b in zip(dec_mine.color_decoder_fine.mlp_exposure.parameters(), dec_ref.color_decoder_fine.mlp_exposure.parameters()):
-        assert float((a.detach() - b.detach()).abs().max()) < 2e-6
+    for level in ("mid", "fine"):
+        for a, b in zip(getattr(dec_mine, "color_decoder_" + level).mlp_exposure.parameters(),
+                        getattr(dec_ref, "color_decoder_" + level).mlp_exposure.parameters()):
+            assert float((a.detach() - b.detach()).abs().max()) < 2e-6, level
+    # the fine MLP sat out the first half: its counter is iters / 2, the pose's is iters
+    steps = opt.opt.tensor_steps.tolist()
+    assert max(steps) == opt.num_cam_iters and min(steps) == opt.num_cam_iters // 2
 
 
 def test_mapper_optimizer_groups_follow_the_reference_construction(monkeypatch):
