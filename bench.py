@@ -1,6 +1,6 @@
 """Benchmark of the render-and-optimise hot path: mapping rays/sec (fwd+bwd).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--no-extras]
 
 A "step" = one mapper iteration of the reference's inner loop (Mapper.py:783-858) on one batch of
 synthetic rays: render_batch_ray (stage color_fine) -> L1 depth + colour loss -> backward to the point
@@ -8,14 +8,19 @@ features of the level, the colour decoder and (as in the reference) the geometry
 Workload at every N = BASELINE.json configs[1]: 5,000 rays (25,000 sample points) per GPU against a
 1M-point fine cloud (+250k mid), ScanNet intrinsics, synthetic data, random-init decoders (seed 1219).
 Weak scaling: every rank renders its own 5,000-ray shard of the global batch against the replicated cloud
-and the gradients are all-reduced (NCCL) - SURVEY 8e.  At N > 1 the iteration is issued as two CUDA graphs (the
-parameter-free head = sampling + neighbour search | the rest) so that the all-reduce of step i overlaps the head of
-step i+1; it is started after the untimed L2 flush (it overlaps nothing untimed) and the last one is timed on its own.
+and the gradients are all-reduced (NCCL) - SURVEY 8e.
+
+Issue: one CUDA graph per iteration.  The parameter-free head of iteration i+1 (sampling + neighbour search of the
+NEXT ray batch, which a mapper draws independently of the parameters) is issued inside iteration i's graph on a side
+stream beside the HBM-bound tail of its backward (`tail_work` of Renderer.render_batch_ray_loss), so every timed step
+does one head and one rest - of consecutive iterations.  At N > 1 the iteration is two graphs (head | rest) and the
+all-reduce of step i overlaps the head of step i+1; the last one is timed on its own.
 
 JSON line: see the driver's contract; `value` = rays/s with inputs resident in HBM (CUDA-event timed per
-step, L2 flushed between steps), `e2e` = same through the public API from pinned host buffers (double-buffered H2D on a copy stream) with the
-loss read back every step, `roofline` = dominant kernel vs MEASURED_PEAKS.json, `cpu_baseline` = the
-oracle port timed on the host cores on a bounded sample.
+step, L2 flushed between steps), `e2e` = same through the public API from pinned host buffers (double-buffered H2D on a
+copy stream) with the loss read back every step, `roofline` = dominant kernel vs MEASURED_PEAKS.json, `cpu_baseline` =
+the oracle port timed on the host cores, `parity` = this very workload (one 5,000-ray batch, 1M-point cloud) GPU vs the
+oracle port: the process exits non-zero when it is off, `sustained` = >= 2 s of back-to-back iterations.
 """
 import argparse
 import importlib
@@ -38,7 +43,10 @@ N_BATCHES = 8            # distinct ray batches cycled through
 STAGE = "color_fine"
 FUSED_LOSS = os.environ.get("HPS_BENCH_FUSED_LOSS", "1") != "0"   # renderer.render_batch_ray_loss vs render + mapper_loss
 EXTENT = 10.0            # cloud spread (in image-plane widths): ~2,700 pts/m^2, ScanNet-like
-CPU_SAMPLE_RAYS = 2500
+CPU_SAMPLE_RAYS = RAYS       # the CPU arm runs the same 5,000-ray batches
+EXTRAS_TIMEOUT_S = 300
+PARITY_TOL = 1e-4            # north star: <= 1e-4 relative (max-norm), neighbours bit-exact
+DTYPE = "f32 (decoders: 3x fp16-split tcgen05 MMA with fp32 accumulate; everything else fp32 SIMT)"
 
 
 def peaks():
@@ -109,11 +117,26 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores
 # --------------------------------------------------------------------------------------------------
+def frustum_live_rows(points, cam):
+    """Frustum feature selection of the bench scene (Mapper.py:194-250 with the identity pose and no depth test: the
+    synthetic surface is one sheet): rows of the fine level that project into the frame (+20 px).  Same expression on
+    both arms (torch ops on whatever device `points` lives on)."""
+    zc = -points[:, 2]
+    u = cam["cx"] + cam["fx"] * points[:, 0] / zc
+    v = cam["cy"] - cam["fy"] * points[:, 1] / zc
+    live = (zc > 0) & (u > -20) & (u < cam["W"] + 20) & (v > -20) & (v < cam["H"] + 20)
+    return live.nonzero().flatten()
+
+
 def cpu_step_fn(scene, n_rays):
+    """The reference's mapper iteration on the host cores (oracle port): like Mapper.py:512-536, 615-624 the optimised
+    leaves are the frustum-selected rows, written into the full tables (index_put) before the render call.
+    step(b) -> dict(loss, depth, color, valid, g_geo, g_col (leaf gradients), g_dec, g_geo_dec (name -> gradient))."""
     from oracle import hps_oracle as O
     torch.manual_seed(1219)
     hps = importlib.import_module("hierarchical-point-slam_b200")
-    dec_mod = hps.get_model(hps.scannet_cfg("cpu"))
+    cfg = hps.scannet_cfg("cpu")
+    dec_mod = hps.get_model(cfg)
     dec = {}
     for name in ("geo_decoder_fine", "color_decoder_fine"):
         m = getattr(dec_mod, name)
@@ -123,20 +146,29 @@ def cpu_step_fn(scene, n_rays):
     knn = O.KDTreeNeighbors()
     fine = scene["fine"]
     pos = {"fine": fine["points"]}
-    gf = {"fine": fine["geo_feats"].clone().requires_grad_(True)}
-    cf = {"fine": fine["col_feats"].clone().requires_grad_(True)}
+    live_idx = frustum_live_rows(fine["points"], cfg["cam"])
+    leaf_g = fine["geo_feats"][live_idx].clone().requires_grad_(True)
+    leaf_c = fine["col_feats"][live_idx].clone().requires_grad_(True)
+    tab_g, tab_c = fine["geo_feats"].clone(), fine["col_feats"].clone()
 
-    def step(b):
+    def step(b, keep=False):
         sl = slice(b * RAYS, b * RAYS + n_rays)
-        for t in (gf["fine"], cf["fine"]):
+        for t in [leaf_g, leaf_c] + [v for d in dec.values() for v in d.values()]:
             t.grad = None
+        gf = {"fine": tab_g.detach().index_put((live_idx,), leaf_g)}          # Mapper.py:621-624
+        cf = {"fine": tab_c.detach().index_put((live_idx,), leaf_c)}
         d, v, c, m = O.render_batch_ray(pos, dec, fine["rays_d"][sl], fine["rays_o"][sl], STAGE, fine["gt_depth"][sl],
                                         gf, cf, {"fine": fine["radius"][sl]}, scene["c_fill_geo"], scene["c_fill_col"],
                                         knn_fn=knn)
         aff = O.exposure_affine(dec["color_decoder_fine"], scene["exposure_feat"])
         loss = O.mapper_loss(d, c, m, fine["gt_depth"][sl], fine["gt_color"][sl], STAGE, 0.1, aff)
         loss.backward()
-        return float(loss.detach())
+        if not keep:
+            return float(loss.detach())
+        return dict(loss=loss.detach(), depth=d.detach(), color=c.detach(), valid=m, g_geo=leaf_g.grad, g_col=leaf_c.grad,
+                    g_dec={k: t.grad for k, t in dec["color_decoder_fine"].items() if t.grad is not None},
+                    g_geo_dec={k: t.grad for k, t in dec["geo_decoder_fine"].items() if t.grad is not None},
+                    live_idx=live_idx, knn=knn)
     return step
 
 
@@ -153,18 +185,26 @@ def time_cpu(scene, n_rays, steps, warmup):
 
 
 def run_reference(args, rank):
+    """The reference arm: the reference's own algorithm for this path on the host cores (oracle port; the reference
+    itself is not importable on the GPU box and its faiss wheel is not installable anywhere here).  Same workload as
+    the GPU arm - 5,000-ray batches, frustum-selected leaves, 1M-point cloud - a bounded number of steps."""
     if rank != 0:
         return
     scene = make_scene()
     steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
     rps, sps = time_cpu(scene, CPU_SAMPLE_RAYS, steps, warmup)
     cores = os.cpu_count() or 1
-    sample = ("%d-ray mapper iteration (stage %s, fwd+loss+bwd) vs the 1M-point fine cloud; oracle port of the "
-              "reference (torch CPU fp32) with scipy cKDTree(workers=-1) standing in for faiss-cpu" % (CPU_SAMPLE_RAYS, STAGE))
+    sample = ("%d timed + %d warm-up mapper iterations of %d rays (stage %s, fwd+loss+bwd, frustum-selected leaves) vs the "
+              "1M-point fine cloud; oracle port of the reference (torch CPU fp32, %d threads) with scipy cKDTree(workers=-1) "
+              "standing in for faiss-cpu" % (steps, warmup, CPU_SAMPLE_RAYS, STAGE, cores))
+    cfgd = dict(workload_config(1), ran={"rays_per_step": CPU_SAMPLE_RAYS, "steps": steps, "warmup": warmup,
+                                         "requested_steps": args.steps, "requested_warmup": args.warmup,
+                                         "note": "CPU arm: one process on the host cores whatever --gpus says; a rate "
+                                                 "(rays/s), so the step count does not enter the ratio"})
     line = {"impl": "reference", "metric": "mapping rays/sec (fwd+bwd)", "value": rps, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus),
+            "config": cfgd,
             "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
@@ -194,6 +234,36 @@ def workload_config(n_gpus):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
+OVERLAP_HEAD = os.environ.get("HPS_BENCH_OVERLAP", "1") != "0"   # N = 1: next iteration's head beside this one's tail
+
+
+def build_workload(hps, dev, scene=None):
+    """Scene, cloud, decoders, renderer and live rows of the bench workload on `dev` (shared by the extras)."""
+    import types
+    scene = scene or make_scene()
+    cfg = hps.scannet_cfg(dev)
+    npc = hps.NeuralPointCloud(cfg)
+    for level in ("fine", "mid"):
+        s = scene[level]
+        npc.set_cloud(level, s["points"].to(dev), s["geo_feats"].to(dev), s["col_feats"].to(dev))
+    torch.manual_seed(1219)
+    dec = hps.get_model(cfg).to(dev)
+    dec.c_fill_geo, dec.c_fill_col = scene["c_fill_geo"].to(dev), scene["c_fill_col"].to(dev)
+    renderer = hps.Renderer(cfg, None, types.SimpleNamespace(**{k: cfg["cam"][k] for k in ("H", "W", "fx", "fy", "cx", "cy")}))
+    renderer.sigmoid_coefficient = 0.1
+    renderer.assume_positive_depth = True      # mapper batches are depth-filtered (common.py:248-254)
+    renderer.write_back_radius = False         # nobody reads the repeated radii the reference writes into the dict
+    # Frustum feature selection (Mapper.py:194-250, 512-536): the rows of the fine level that project into the
+    # frame (+20 px) are the live, optimised rows; the others are frozen.  Identity pose, ScanNet intrinsics.
+    live_idx = frustum_live_rows(npc.cloud_pos_tensor("fine"), cfg["cam"])
+    lg, lc = hps.LiveRows.pair(npc.get_geo_feats("fine"), npc.get_col_feats("fine"), live_idx)
+    gf = {"fine": lg, "mid": npc.get_geo_feats("mid")}
+    cf = {"fine": lc, "mid": npc.get_col_feats("mid")}
+    pos = {l: npc.cloud_pos_tensor(l) for l in ("fine", "mid")}
+    return types.SimpleNamespace(scene=scene, cfg=cfg, npc=npc, dec=dec, renderer=renderer, live_idx=live_idx, lg=lg, lc=lc,
+                                 gf=gf, cf=cf, pos=pos, dev=dev)
+
+
 def run_ours(args, rank, world, local_rank):
     import __graft_entry__
     dist = None
@@ -208,53 +278,23 @@ def run_ours(args, rank, world, local_rank):
     if os.environ.get("HPS_BENCH_VERBOSE"):
         print("[rank %d] process group up, library built" % rank, file=sys.stderr, flush=True)
     hps = importlib.import_module("hierarchical-point-slam_b200")
-    allreduce_grads = hps.parallel.allreduce_grads
     dev = "cuda:%d" % local_rank
     torch.cuda.set_device(local_rank)
-    scene = make_scene()
-    cfg = hps.scannet_cfg(dev)
-    npc = hps.NeuralPointCloud(cfg)
-    for level in ("fine", "mid"):
-        s = scene[level]
-        npc.set_cloud(level, s["points"].to(dev), s["geo_feats"].to(dev), s["col_feats"].to(dev))
-    torch.manual_seed(1219)
-    dec = hps.get_model(cfg).to(dev)
-    dec.c_fill_geo, dec.c_fill_col = scene["c_fill_geo"].to(dev), scene["c_fill_col"].to(dev)
-    import types
-    renderer = hps.Renderer(cfg, None, types.SimpleNamespace(**{k: cfg["cam"][k] for k in ("H", "W", "fx", "fy", "cx", "cy")}))
-    renderer.sigmoid_coefficient = 0.1
+    wl = build_workload(hps, dev)
+    scene, cfg, npc, dec, renderer = wl.scene, wl.cfg, wl.npc, wl.dec, wl.renderer
+    lg, lc, gf, cf, pos, live_idx = wl.lg, wl.lc, wl.gf, wl.cf, wl.pos, wl.live_idx
     fine = scene["fine"]
-    # rank r takes every world-th batch offset so that ranks render different rays of the global batch
-    host = {k: fine[k].pin_memory() for k in ("rays_o", "rays_d", "gt_depth", "gt_color", "radius")}
-    host["radius_mid"] = scene["radius_mid"].pin_memory()
-    devb = {k: v.to(dev) for k, v in host.items()}
+    host = {k: fine[k] for k in ("rays_o", "rays_d", "gt_depth", "gt_color", "radius")}
+    host["radius_mid"] = scene["radius_mid"]
     exposure_feat = scene["exposure_feat"].to(dev)
-    # Frustum feature selection (Mapper.py:194-250, 512-536): the rows of the fine level that project into the
-    # frame (+20 px) are the live, optimised rows; the others are frozen.  Identity pose, ScanNet intrinsics.
-    K = cfg["cam"]
-    pf = npc.cloud_pos_tensor("fine")
-    zc = -pf[:, 2]
-    u = K["cx"] + K["fx"] * pf[:, 0] / zc
-    v = K["cy"] - K["fy"] * pf[:, 1] / zc
-    live = (zc > 0) & (u > -20) & (u < K["W"] + 20) & (v > -20) & (v < K["H"] + 20)
-    live_idx = live.nonzero().flatten()
-    lg, lc = hps.LiveRows.pair(npc.get_geo_feats("fine"), npc.get_col_feats("fine"), live_idx)
-    gf = {"fine": lg, "mid": npc.get_geo_feats("mid")}
-    cf = {"fine": lc, "mid": npc.get_col_feats("mid")}
-    pos = {l: npc.cloud_pos_tensor(l) for l in ("fine", "mid")}
     params = [p for p in dec.parameters()]
     grad_targets = [lg.param, lc.param] + params
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def batch_index(i):
+        # rank r takes every world-th batch offset so that ranks render different rays of the global batch
         return (i * world + rank) % N_BATCHES
 
-    def batch_slice(i):
-        b = batch_index(i)
-        return slice(b * RAYS, (b + 1) * RAYS)
-
-    renderer.assume_positive_depth = True      # mapper batches are depth-filtered (common.py:248-254)
-    renderer.write_back_radius = False         # nobody reads the repeated radii the reference writes into the dict
     # One ray batch travels as ONE packed byte buffer (fp32: rays_o | rays_d | gt_depth | gt_color, then fp64: the
     # two radius vectors) so that staging it costs one copy, not six; the iteration reads contiguous typed views.
     F32_KEYS = (("rays_o", 3), ("rays_d", 3), ("gt_depth", 1), ("gt_color", 3))
@@ -266,47 +306,56 @@ def run_ours(args, rank, world, local_rank):
         f64 = torch.cat([src["radius"][sl].reshape(-1).double(), src["radius_mid"][sl].reshape(-1).double()])
         return torch.cat([f32.view(torch.uint8), f64.view(torch.uint8)])
 
-    host_pk = {"bytes": torch.stack([pack(host, b) for b in range(N_BATCHES)]).pin_memory()}
-    dev_pk = {k: v.to(dev) for k, v in host_pk.items()}
-    static_pk = {"bytes": torch.empty_like(dev_pk["bytes"][0])}
-    s32 = static_pk["bytes"][:4 * N32].view(torch.float32)
-    s64 = static_pk["bytes"][4 * N32:].view(torch.float64)
-    static, off = {}, 0
-    for k, w in F32_KEYS:
-        static[k] = s32[off:off + w * RAYS].view(devb[k][:RAYS].shape)
-        off += w * RAYS
-    static["radius"] = s64[:RAYS].view(devb["radius"][:RAYS].shape)
-    static["radius_mid"] = s64[RAYS:].view(devb["radius_mid"][:RAYS].shape)
+    host_pk = torch.stack([pack(host, b) for b in range(N_BATCHES)]).pin_memory()
+    dev_pk = host_pk.to(dev)
 
-    prep_box = {"p": None}
+    def typed_views(buf):
+        s32 = buf[:4 * N32].view(torch.float32)
+        s64 = buf[4 * N32:].view(torch.float64)
+        out, off = {}, 0
+        for k, w in F32_KEYS:
+            out[k] = s32[off:off + w * RAYS].view(RAYS, w) if w > 1 else s32[off:off + RAYS]
+            off += w * RAYS
+        out["radius"], out["radius_mid"] = s64[:RAYS], s64[RAYS:]
+        return out
 
-    def head():
-        """Parameter-free head of the iteration (sampling + neighbour search): its own graph when ranks > 1, so that it
-        can run while the previous iteration's gradients are still being exchanged."""
-        rq = {"fine": static["radius"], "mid": static["radius_mid"]}
-        prep_box["p"] = renderer.prepare_batch(npc, static["rays_d"], static["rays_o"], STAGE, static["gt_depth"], rq,
-                                               out=prep_box["p"])
-        return prep_box["p"].cnt
+    overlap = OVERLAP_HEAD and world == 1
+    static_pk = [torch.empty_like(dev_pk[0]) for _ in range(2 if overlap else 1)]
+    views = [typed_views(b) for b in static_pk]
+    prep = [None] * len(static_pk)
 
-    def step(prepared=None):
-        """One mapper iteration on the rays held in `static` (reference Mapper.py:783-858)."""
+    def rq(k):
+        return {"fine": views[k]["radius"], "mid": views[k]["radius_mid"]}
+
+    def head(k=0):
+        """Parameter-free head of an iteration (sampling + neighbour search) on the rays in slot k."""
+        prep[k] = renderer.prepare_batch(npc, views[k]["rays_d"], views[k]["rays_o"], STAGE, views[k]["gt_depth"], rq(k),
+                                         out=prep[k])
+        return prep[k].cnt
+
+    def step(k=0, prepared=None, tail=None, keep=False):
+        """One mapper iteration on the rays held in slot k (reference Mapper.py:783-858)."""
         for t in grad_targets:
             t.grad = None
-        rq = {"fine": static["radius"], "mid": static["radius_mid"]}
+        v = views[k]
         if FUSED_LOSS:      # render + loss as one autograd node (compositing and loss in one kernel)
-            loss = renderer.render_batch_ray_loss(
-                npc, dec, static["rays_d"], static["rays_o"], dev, STAGE, static["gt_depth"], static["gt_color"], 0.1,
-                npc_geo_feats=gf, npc_col_feats=cf, cloud_pos=pos, dynamic_r_query=rq, exposure_feat=exposure_feat,
-                prepared=prepared)[0]
+            out = renderer.render_batch_ray_loss(
+                npc, dec, v["rays_d"], v["rays_o"], dev, STAGE, v["gt_depth"], v["gt_color"], 0.1,
+                npc_geo_feats=gf, npc_col_feats=cf, cloud_pos=pos, dynamic_r_query=rq(k), exposure_feat=exposure_feat,
+                prepared=prepared, tail_work=tail)
+            loss = out[0]
         else:               # the reference's seams: render_batch_ray, then the loss (HPS_BENCH_FUSED_LOSS=0)
             depth, unc, color, valid = renderer.render_batch_ray(
-                npc, dec, static["rays_d"], static["rays_o"], dev, STAGE, gt_depth=static["gt_depth"],
-                npc_geo_feats=gf, npc_col_feats=cf, is_tracker=False, cloud_pos=pos, dynamic_r_query=rq,
+                npc, dec, v["rays_d"], v["rays_o"], dev, STAGE, gt_depth=v["gt_depth"],
+                npc_geo_feats=gf, npc_col_feats=cf, is_tracker=False, cloud_pos=pos, dynamic_r_query=rq(k),
                 exposure_feat=None, prepared=prepared)
             affine = dec.color_decoder_fine.mlp_exposure(exposure_feat)
-            loss = hps.mapper_loss(depth, color, valid, static["gt_depth"], static["gt_color"], STAGE, 0.1, affine)
+            loss = hps.mapper_loss(depth, color, valid, v["gt_depth"], v["gt_color"], STAGE, 0.1, affine)
+            out = (loss, depth, unc, color, valid)
+            if tail is not None:
+                tail()
         loss.backward()
-        return loss
+        return out if keep else loss
 
     grad_exchange = hps.parallel.GradExchange(grad_targets, skip_missing=True)   # untouched (mid-level) decoders stay out
     comm = torch.cuda.Stream() if world > 1 else None
@@ -342,57 +391,94 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- capture the iteration in a CUDA graph (falls back to eager issue if capture is impossible) ----
-    for k in static_pk:
-        static_pk[k].copy_(dev_pk[k][batch_index(0)])
-    mode = "cuda-graph replay"
+    # ---- capture the iteration in CUDA graphs (falls back to eager issue if capture is impossible) ----
+    # need(i) = (which batch, into which slot) has to be loaded right before issue i
+    static_pk[0].copy_(dev_pk[batch_index(0)])
     try:
         hps.ops.LAUNCHES["n"] = 0
-        if world > 1:
+        if overlap:
+            # two graphs (even / odd iterations): rest of iteration i on slot i % 2, and beside the tail of its backward
+            # the head of iteration i + 1 on the other slot
+            static_pk[1].copy_(dev_pk[batch_index(1)])
+            head(0)
+            head(1)
+            hps.ops.LAUNCHES["n"] = 0
+            graphs = [hps.graphs.GraphedStep(lambda k=k: step(k, prep[k], tail=lambda: head(1 - k)), {}, warmup=3)
+                      for k in (0, 1)]
+            mode = "cuda-graph replay, the next iteration's head (sampling + neighbour search) beside this one's backward tail"
+            launches_per_step = hps.ops.LAUNCHES["n"] // 8      # 2 graphs x (3 warm-up passes + the captured one)
+
+            def need(i):
+                return i + 1, (i + 1) % 2
+
+            def replay(i):
+                graphs[i % 2].graph.replay()
+                return graphs[i % 2].outputs
+
+            def prime(i, src):
+                """slot i % 2 <- batch i and its head, issued eagerly (before the first replay of a sequence)"""
+                static_pk[i % 2].copy_(src[batch_index(i)], non_blocking=True)
+                head(i % 2)
+        elif world > 1:
             # two graphs: head (no parameters involved) | rest.  Iteration i+1's head overlaps iteration i's exchange;
             # the rest waits for it (a real mapper would put its optimiser step there).
-            g_head = hps.graphs.GraphedStep(head, static_pk, warmup=3)
-            g_tail = hps.graphs.GraphedStep(lambda: step(prep_box["p"]), {}, warmup=3)
+            g_head = hps.graphs.GraphedStep(lambda: head(0), {}, warmup=3)
+            g_tail = hps.graphs.GraphedStep(lambda: step(0, prep[0]), {}, warmup=3)
             mode = "cuda-graph replay (head | rest), exchange overlapped with the next head"
+            launches_per_step = hps.ops.LAUNCHES["n"] // 4
 
-            def run(i, src):
-                g_head(**{k: src[k][batch_index(i)] for k in static_pk})
-                drain()
-                return g_tail()
+            def need(i):
+                return i, 0
 
-            def replay():                      # inputs already in static_pk
+            def replay(i):
                 g_head.graph.replay()
                 drain()
                 g_tail.graph.replay()
                 return g_tail.outputs
+
+            def prime(i, src):
+                pass
         else:
-            graphed = hps.graphs.GraphedStep(step, static_pk, warmup=3)
+            graphed = hps.graphs.GraphedStep(lambda: step(0), {}, warmup=3)
+            mode = "cuda-graph replay"
+            launches_per_step = hps.ops.LAUNCHES["n"] // 4
 
-            def run(i, src):
-                return graphed(**{k: src[k][batch_index(i)] for k in static_pk})
+            def need(i):
+                return i, 0
 
-            def replay():
+            def replay(i):
                 graphed.graph.replay()
                 return graphed.outputs
-        launches_per_step = hps.ops.LAUNCHES["n"] // 4          # 3 warm-up passes + the captured one
+
+            def prime(i, src):
+                pass
     except Exception as e:                                        # pragma: no cover - reported in the JSON line
+        if os.environ.get("HPS_BENCH_STRICT"):
+            raise
         mode = "eager (graph capture failed: %s)" % str(e).splitlines()[0][:120]
+        overlap = False
         hps.ops.LAUNCHES["n"] = 0
-        step()
+        step(0)
         launches_per_step = hps.ops.LAUNCHES["n"]
 
-        def run(i, src):
-            for k in static_pk:
-                static_pk[k].copy_(src[k][batch_index(i)], non_blocking=True)
-            drain()
-            return step()
+        def need(i):
+            return i, 0
 
-        def replay():
+        def replay(i):
             drain()
-            return step()
+            return step(0)
+
+        def prime(i, src):
+            pass
+
+    def run(i, src):
+        j, slot = need(i)
+        static_pk[slot].copy_(src[batch_index(j)], non_blocking=True)
+        return replay(i)
 
     log("iteration ready: %s" % mode)
     # ---- warm-up ----
+    prime(0, dev_pk)
     for i in range(args.warmup):
         run(i, dev_pk)
         post()
@@ -425,35 +511,53 @@ def run_ours(args, rank, world, local_rank):
     log("timed region done")
     launches = launches_per_step * args.steps
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    # ---- sustained: >= 2 s of back-to-back iterations (no L2 flush, batches cycled), one event pair around all of
+    # them - what a mapper that runs 600 iterations per frame sees; the clock sampler keeps sampling through it ----
+    n_sus = max(200, int(2200.0 / max(dev_ms / args.steps, 0.05)))
+    prime(0, dev_pk)
+    run(0, dev_pk)
+    post()
+    sync_all()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(1, n_sus + 1):
+        run(i, dev_pk)
+        post()
+    drain()
+    b.record()
+    sync_all()
+    sus_ms = a.elapsed_time(b)
     # ---- e2e: every step's inputs come from pinned host memory and every step's loss is read back on the host, wall
-    # clock around the synchronised region.  The loop is pipelined like a real mapper loop would be: step i+1's H2D
-    # copy runs on a copy stream into the other of two staging buffers while step i computes, and the host reads the
-    # loss of step i-1 (pinned, event-ordered) after it has issued step i - the GPU never waits for the host. ----
+    # clock around the synchronised region.  The loop is pipelined like a real mapper loop would be: the H2D copy of
+    # the next batch runs on a copy stream into the other of two staging buffers while this step computes, and the host
+    # reads the loss of step i-1 (pinned, event-ordered) after it has issued step i - the GPU never waits for the host. ----
     copy_s = torch.cuda.Stream()
     main_s = torch.cuda.current_stream()
-    stage = [torch.empty_like(static_pk["bytes"]) for _ in range(2)]
+    stage = [torch.empty_like(static_pk[0]) for _ in range(2)]
     loss_host = torch.zeros(2, dtype=torch.float32).pin_memory()
     ev_in, ev_used, ev_out = [None, None], [None, None], [None, None]
     seen = []
 
     def feed(i):
-        """H2D copy of step i's ray batch (copy stream; waits until the staging buffer's previous reader is done)."""
+        """H2D copy of the batch issue i needs (copy stream; waits until the staging buffer's previous reader is done)."""
+        j, _slot = need(i)
         with torch.cuda.stream(copy_s):
             if ev_used[i % 2] is not None:
                 copy_s.wait_event(ev_used[i % 2])
-            stage[i % 2].copy_(host_pk["bytes"][batch_index(i)], non_blocking=True)
+            stage[i % 2].copy_(host_pk[batch_index(j)], non_blocking=True)
             ev_in[i % 2] = copy_s.record_event()
 
     def e2e_loop(n, first):
+        prime(first, dev_pk)             # (overlap mode) the first iteration's own rays: outside the loop like any warm-up
         feed(first)
         for k in range(n):
             i = first + k
             if k + 1 < n:
                 feed(i + 1)
             main_s.wait_event(ev_in[i % 2])
-            static_pk["bytes"].copy_(stage[i % 2], non_blocking=True)
+            static_pk[need(i)[1]].copy_(stage[i % 2], non_blocking=True)
             ev_used[i % 2] = main_s.record_event()
-            loss = replay()
+            loss = replay(i)
             post()                                                  # (ranks > 1) start the exchange
             loss_host[i % 2].copy_(loss.detach().reshape(()), non_blocking=True)      # D2H read of the loss
             ev_out[i % 2] = main_s.record_event()
@@ -467,6 +571,7 @@ def run_ours(args, rank, world, local_rank):
     drain()
     sync_all()
     seen.clear()
+    ev_in, ev_used, ev_out = [None, None], [None, None], [None, None]
     t0 = time.perf_counter()
     e2e_loop(args.steps, args.warmup)
     drain()
@@ -474,117 +579,183 @@ def run_ours(args, rank, world, local_rank):
     e2e_s = time.perf_counter() - t0
     assert len(seen) == args.steps and all(v == v for v in seen), "e2e: every step's loss must have been read back"
     clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s, sus_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s = float(t[0]), float(t[1])
+    dev_ms, e2e_s, sus_ms = float(t[0]), float(t[1]), float(t[2])
     # ---- per-kernel timing pass (eager, instrumented, separate from the timed region) ----
     roof = None
     hps.ops.TIMERS = {}
     n_prof = min(args.steps, 20)
     for i in range(n_prof):              # every rank takes part (the step contains the all-reduce)
         flush.zero_()
-        for k in static_pk:
-            static_pk[k].copy_(dev_pk[k][batch_index(args.warmup + i)])
-        step()
+        static_pk[0].copy_(dev_pk[batch_index(args.warmup + i)])
+        step(0)
         exchange()
     torch.cuda.synchronize()
     log("profiling pass done")
     per = {k: sum(a.elapsed_time(b) for a, b in v) / n_prof for k, v in hps.ops.TIMERS.items()}
     hps.ops.TIMERS = None
     if rank == 0:
-        roof = roofline(per, hps, npc, devb, batch_slice(0))
+        roof = roofline(per, hps, npc, {k: v.to(dev) for k, v in host.items()}, slice(0, RAYS))
     if world > 1:
         dist.barrier()
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    tracking = None
+    line, rc = None, 0
+    if rank == 0:
+        h2d = host_pk[0].numel() * host_pk.element_size()
+        line = {"metric": "mapping rays/sec (fwd+bwd)", "value": RAYS * world * args.steps / (dev_ms * 1e-3), "unit": "rays/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+                "config": dict(workload_config(world), issue=mode, n_live_rows=int(live_idx.numel()),
+                               api="renderer.render_batch_ray_loss + backward" if FUSED_LOSS else
+                               "renderer.render_batch_ray + mapper_loss + backward"), "clocks": clocks,
+                "e2e": {"value": RAYS * world * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": 4,
+                        "note": "every step: H2D of one ray batch from pinned memory (copy stream, two staging buffers) and "
+                                "D2H of its loss (read by the host one step behind); no L2 flush"},
+                "sustained": {"value": RAYS * world * n_sus / (sus_ms * 1e-3), "unit": "rays/s", "iterations": n_sus,
+                              "seconds": sus_ms * 1e-3, "ms_per_step": sus_ms / n_sus,
+                              "note": "back-to-back iterations, no L2 flush, one CUDA-event pair around all of them; the "
+                                      "clock sampler ('clocks') covers the timed region, this run and the e2e loop"},
+                "gpu_launches": launches, "roofline": roof["roofline"], "kernels_ms_per_step": roof["per_kernel"]}
     if world == 1:
-        tracking = time_tracker(hps, npc, dec, renderer, scene, cfg, dev, gf, cf, pos)
-    h2d = sum(v[0].numel() * v.element_size() for v in host_pk.values())
-    line = {"metric": "mapping rays/sec (fwd+bwd)", "value": RAYS * world * args.steps / (dev_ms * 1e-3), "unit": "rays/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(world), issue=mode, n_live_rows=int(live_idx.numel()),
-                           api="renderer.render_batch_ray_loss + backward" if FUSED_LOSS else
-                           "renderer.render_batch_ray + mapper_loss + backward"), "clocks": clocks,
-            "e2e": {"value": RAYS * world * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 4,
-                    "note": "every step: H2D of its ray batch from pinned memory (copy stream, two staging buffers) and "
-                            "D2H of its loss (read by the host one step behind); no L2 flush"},
-            "gpu_launches": launches, "roofline": roof["roofline"], "kernels_ms_per_step": roof["per_kernel"]}
-    if tracking is not None:
-        line["tracking"] = tracking
-    if world == 1:
-        rps, sps = time_cpu(scene, CPU_SAMPLE_RAYS, 3, 1)
-        line["cpu_baseline"] = {"value": rps, "unit": "rays/s", "cores": os.cpu_count() or 1, "kind": "port",
-                                "sample": "%d-ray mapper iteration of the same workload, oracle port (torch CPU fp32 + scipy "
-                                          "cKDTree for the neighbour search), 3 timed repeats" % CPU_SAMPLE_RAYS}
-    emit(line)
+        # ---- parity on this very workload: one 5,000-ray batch of the bench, GPU vs the oracle port ----
+        torch.set_num_threads(os.cpu_count() or 1)
+        cpu_step = cpu_step_fn(scene, CPU_SAMPLE_RAYS)
+        try:
+            line["parity"] = parity_check(hps, wl, cpu_step)
+        except Exception as e:                                    # pragma: no cover
+            line["parity"] = {"ok": False, "error": "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:200])}
+        if not line["parity"].get("ok"):
+            rc = 3
+        # ---- CPU baseline: the same step function, timed ----
+        for i in range(2):
+            cpu_step(i)
+        t0 = time.perf_counter()
+        n_cpu = 5
+        for i in range(n_cpu):
+            cpu_step((2 + i) % N_BATCHES)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": CPU_SAMPLE_RAYS * n_cpu / dt, "unit": "rays/s", "cores": os.cpu_count() or 1,
+                                "kind": "port",
+                                "sample": "%d timed mapper iterations of %d rays of the same workload (frustum-selected "
+                                          "leaves), oracle port (torch CPU fp32 + scipy cKDTree for the neighbour search)"
+                                          % (n_cpu, CPU_SAMPLE_RAYS)}
+    if not args.no_extras:
+        # Extra workloads (every rank takes part: two of them shard over the ranks).  They must never cost the line: a
+        # watchdog prints it without them if they overrun, and each of them reports its own failure.
+        import threading
+        import bench_extras
+
+        def give_up():
+            if line is not None:
+                line["extras"] = "timed out after %d s; the line above them is complete" % EXTRAS_TIMEOUT_S
+                emit(line)
+            os._exit(rc)
+        dog = threading.Timer(EXTRAS_TIMEOUT_S, give_up)
+        dog.daemon = True
+        dog.start()
+        extras = bench_extras.run(hps, wl, args, rank, world, dist)
+        dog.cancel()
+        if line is not None:
+            line.update(extras)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if line is not None:
+        emit(line)
+    if rc:
+        sys.stderr.write("bench: parity check FAILED: %s\n" % json.dumps(line.get("parity")))
+        sys.exit(rc)
 
 
-def time_tracker(hps, npc, dec, renderer, scene, cfg, dev, gf, cf, pos, iters=100):
-    """The second half of BASELINE.json's metric: tracking iterations / s (Tracker.py:190-235) on the same scene - R = 5000
-    rays, stage color_fine, pose 7-vector + exposure latent under Adam, decoders frozen; the whole iteration (pose -> rays
-    -> render -> loss -> backward -> Adam) replayed from one CUDA graph, timed with CUDA events.  Extra key of the JSON
-    line, not part of `value`."""
-    K = cfg["cam"]
-    fine = scene["fine"]
-    rd0 = fine["rays_d"][:RAYS]
-    pi = (rd0[:, 0] * K["fx"] + K["cx"]).to(dev)
-    pj = (K["cy"] - rd0[:, 1] * K["fy"]).to(dev)
-    gt_d, gt_c = fine["gt_depth"][:RAYS].to(dev), fine["gt_color"][:RAYS].to(dev)
-    rq = {"fine": fine["radius"][:RAYS].to(dev), "mid": scene["radius_mid"][:RAYS].to(dev)}
-    feats_g = {l: (v.table if isinstance(v, hps.LiveRows) else v) for l, v in gf.items()}
-    feats_c = {l: (v.table if isinstance(v, hps.LiveRows) else v) for l, v in cf.items()}
-    req = [p.requires_grad for p in dec.parameters()]
-    for p in dec.parameters():
-        p.requires_grad_(False)
-    try:
-        cam = torch.tensor([1.0, 0.0, 0.0, 0.0, 0.005, -0.004, 0.003], device=dev).requires_grad_(True)
-        ef = scene["exposure_feat"].to(dev).clone().requires_grad_(True)
-        opt = hps.FusedAdam([([cam, ef], 5e-4)], own_grads=False)      # torch.optim.Adam semantics, one kernel
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
-        def it():
-            opt.zero_grad()
-            c2w = hps.get_camera_from_tensor(cam)
-            ro, rd = hps.get_rays_from_uv(pi, pj, c2w, K["H"], K["W"], K["fx"], K["fy"], K["cx"], K["cy"], dev)
-            if FUSED_LOSS:
-                loss = renderer.render_batch_ray_tracker_loss(
-                    npc, dec, rd, ro, dev, STAGE, gt_d, gt_c, 0.5, npc_geo_feats=feats_g, npc_col_feats=feats_c,
-                    cloud_pos=pos, dynamic_r_query=dict(rq), exposure_feat=ef)[0]
-            else:
-                d, v, c, _ = renderer.render_batch_ray(npc, dec, rd, ro, dev, STAGE, gt_depth=gt_d, npc_geo_feats=feats_g,
-                                                       npc_col_feats=feats_c, is_tracker=True, cloud_pos=pos,
-                                                       dynamic_r_query=dict(rq), exposure_feat=ef)
-                loss = hps.tracker_loss(d, v, c, gt_d, gt_c, 0.5)
-            loss.backward()
-            opt.step()
-            return loss
 
-        g = hps.graphs.GraphedStep(it, {}, warmup=3)
-        for _ in range(5):
-            g()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        a.record()
-        for _ in range(iters):
-            g()
-        b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / iters
-        return {"value": 1e3 / ms, "unit": "iters/s", "ms_per_iter": ms, "rays": RAYS, "stage": STAGE,
-                "note": "pose (7) + exposure latent (8) under Adam, decoders frozen, whole iteration replayed from one "
-                        "CUDA graph, back to back (no L2 flush), 1 GPU"}
-    except Exception as e:                                    # pragma: no cover - reported, never fatal
-        return {"value": None, "unit": "iters/s", "error": str(e).splitlines()[0][:160]}
-    finally:
-        for p, r in zip(dec.parameters(), req):
-            p.requires_grad_(r)
+def _batch_on_device(wl, batch):
+    fine, dev = wl.scene["fine"], wl.dev
+    sl = slice(batch * RAYS, (batch + 1) * RAYS)
+    b = {k: fine[k][sl].to(dev).contiguous() for k in ("rays_o", "rays_d", "gt_depth", "gt_color", "radius")}
+    b["radius_mid"] = wl.scene["radius_mid"][sl].to(dev).contiguous()
+    return b
+
+
+def eager_mapper_step(hps, wl, batch):
+    """One eagerly issued mapper iteration of the bench workload on ray batch `batch` through the public API ->
+    (loss, depth, uncertainty, color, valid); gradients are left in .grad of the live rows and the decoders."""
+    b = _batch_on_device(wl, batch)
+    for t in [wl.lg.param, wl.lc.param] + list(wl.dec.parameters()):
+        t.grad = None
+    out = wl.renderer.render_batch_ray_loss(
+        wl.npc, wl.dec, b["rays_d"], b["rays_o"], wl.dev, STAGE, b["gt_depth"], b["gt_color"], 0.1, npc_geo_feats=wl.gf,
+        npc_col_feats=wl.cf, cloud_pos=wl.pos, dynamic_r_query={"fine": b["radius"], "mid": b["radius_mid"]},
+        exposure_feat=wl.scene["exposure_feat"].to(wl.dev))
+    out[0].backward()
+    return out
+
+
+def eager_head(hps, wl, batch):
+    """Sampling + neighbour search of ray batch `batch` (Renderer.prepare_batch) -> ops.RayPrep."""
+    b = _batch_on_device(wl, batch)
+    return wl.renderer.prepare_batch(wl.npc, b["rays_d"], b["rays_o"], STAGE, b["gt_depth"],
+                                     {"fine": b["radius"], "mid": b["radius_mid"]})
+
+
+def knn_parity(points, pts, rad, I, D, cnt, knn, spot=64):
+    """GPU neighbour lists (I int64, D, cnt; CPU tensors) vs the oracle on the same query points: every in-radius slot
+    (j < neighbor_num) must hold the same index and the bit-identical distance, and the counts must be equal.  First
+    against the k-d tree (fast, all queries); it ranks by float64 distance, so a query that differs is re-checked
+    against the exhaustive fp32 direct-difference search (= the reference forced to nprobe = nlist), as are `spot`
+    random queries regardless."""
+    from oracle import hps_oracle as O
+    Dr, Ir, nr = knn(points, pts, rad)
+    slot = torch.arange(8)[None, :] < nr[:, None].long()
+    bad = (cnt != nr) | ((I != Ir) & slot).any(1) | ((D != Dr) & slot).any(1)
+    n_bad = int(bad.sum())
+
+    def exhaustive_ok(idx):
+        De, Ie, ne = O.find_neighbors(points, pts[idx], rad[idx])
+        sl = torch.arange(8)[None, :] < ne[:, None].long()
+        return bool((cnt[idx] == ne).all() and not ((I[idx] != Ie) & sl).any() and not ((D[idx] != De) & sl).any())
+    exact = True
+    if n_bad:
+        exact = n_bad <= 256 and exhaustive_ok(bad.nonzero().flatten()[:256])
+    g = torch.Generator().manual_seed(7)
+    exact = exact and exhaustive_ok(torch.randperm(pts.shape[0], generator=g)[:spot])
+    return {"queries": int(pts.shape[0]), "kdtree_mismatches": n_bad, "bit_exact": bool(exact), "count": nr}
+
+
+def parity_check(hps, wl, cpu_step, batch=0):
+    ref = cpu_step(batch, keep=True)
+    out = eager_mapper_step(hps, wl, batch)
+    torch.cuda.synchronize()
+    loss, depth, unc, color, valid = out
+    res = {"rays": RAYS, "fine_points": N_FINE, "tolerance": PARITY_TOL, "batch": batch}
+    res["valid_equal"] = bool(torch.equal(valid.cpu().bool(), ref["valid"].bool()))
+    res["loss_rel"] = _rel(loss, ref["loss"])
+    res["depth_rel"] = _rel(depth, ref["depth"])
+    res["color_rel"] = _rel(color, ref["color"])
+    res["g_geo_rel"] = _rel(wl.lg.param.grad, ref["g_geo"])
+    res["g_col_rel"] = _rel(wl.lc.param.grad, ref["g_col"])
+    cn = dict(wl.dec.color_decoder_fine.named_parameters())
+    gn = dict(wl.dec.geo_decoder_fine.named_parameters())
+    res["g_dec_rel"] = max(_rel(cn[k].grad, g) for k, g in ref["g_dec"].items() if k in cn)
+    res["g_geo_dec_rel"] = max(_rel(gn[k].grad, g) for k, g in ref["g_geo_dec"].items() if k in gn)
+    # neighbour lists of the same 25,000 sample points
+    prep = eager_head(hps, wl, batch)
+    torch.cuda.synchronize()
+    fine = wl.scene["fine"]
+    rad = fine["radius"][batch * RAYS:(batch + 1) * RAYS].reshape(-1, 1).repeat_interleave(5, dim=0)
+    kn = knn_parity(fine["points"], prep.pts.cpu(), rad, prep.I.cpu().long(), prep.D.cpu(), prep.cnt.cpu(), ref["knn"])
+    res.update({"knn_queries": kn["queries"], "knn_kdtree_mismatches": kn["kdtree_mismatches"],
+                "knn_bit_exact": kn["bit_exact"]})
+    exact, nr = kn["bit_exact"], kn["count"]
+    res["mean_in_radius"] = float(nr.float().mean())
+    worst = max(res[k] for k in res if k.endswith("_rel"))
+    res["ok"] = bool(exact and res["valid_equal"] and worst <= PARITY_TOL)
+    return res
 
 
 def roofline(per, hps, npc, devb, sl):
@@ -645,6 +816,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra workloads (configs[0], [2], [4], strong scaling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -659,7 +831,7 @@ def main():
         # plain `python bench.py --gpus N`: re-launch under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__), "--gpus", str(args.gpus),
-               "--steps", str(args.steps), "--warmup", str(args.warmup)]
+               "--steps", str(args.steps), "--warmup", str(args.warmup)] + (["--no-extras"] if args.no_extras else [])
         os.dup2(_REAL_STDOUT, 1)                 # the ranks inherit the real stdout
         raise SystemExit(subprocess.call(cmd))
     run_ours(args, rank, world, local_rank)

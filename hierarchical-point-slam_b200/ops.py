@@ -341,6 +341,12 @@ def _sm_split(P, which):
     return best[1], best[2]
 
 
+# Debugging switch: verify every decoder output for inf / NaN (one host synchronisation per decoder call).  The
+# tensor-core decoders multiply fp16 hi/lo halves: operands beyond fp16's range (|activation| or |weight| > 65,504) overflow
+# to inf, which always reaches the output - never a plausible finite number ("dynamic range").
+CHECK_FINITE = os.environ.get("HPS_CHECK_FINITE", "0") != "0"
+
+
 def _mlp_forward(kind, arr, p_c, c_c, aff, P, out, need_grad, dev, stream=None, saved=None, packed=False, max_ctas=0):
     """pack + forward of one decoder on `stream` (default: current).  Returns the saved workspace ("tc"|"simt",
     tensor) that _mlp_backward consumes (None when no backward will follow)."""
@@ -364,6 +370,11 @@ def _mlp_forward(kind, arr, p_c, c_c, aff, P, out, need_grad, dev, stream=None, 
         _call("hps_mlp_pack", kind, arr, _lib.ptr(pk), _stream())
         _call("hps_mlp_fwd", kind, arr, _lib.ptr(pk), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), P, _lib.ptr(out),
               _lib.ptr(act), _stream())
+    if CHECK_FINITE:
+        (stream if stream is not None else torch.cuda.current_stream()).synchronize()
+        if not bool(torch.isfinite(out).all()):
+            raise _lib.HpsError("decoder %s: non-finite output - an operand left the range of the fp16-split tensor-core "
+                                "path (|x| <= 65,504); set HPS_USE_TC=0 for the fp32 SIMT decoders" % ("geo", "col")[kind])
     return saved
 
 
@@ -633,7 +644,8 @@ def _sample_and_search(grid, ro, rd, gd, rad_t, rad, zz, R, S, near, far, z, pts
 class RenderSpec:
     """Non-tensor arguments of render_rays (one per call)."""
     __slots__ = ("grid", "radius", "z_zero", "S", "near", "far", "coef", "min_nn", "min_valid", "color_stage",
-                 "tracker", "cloud_pos", "fill_geo", "fill_col", "live_geo", "live_col", "prep", "loss", "aff_mlp")
+                 "tracker", "cloud_pos", "fill_geo", "fill_col", "live_geo", "live_col", "prep", "loss", "aff_mlp",
+                 "tail_work")
 
     def __init__(self, **kw):
         for k in self.__slots__:
@@ -994,6 +1006,19 @@ class _RenderRays(torch.autograd.Function):
                 if any(m_need):
                     g_aff_mlp = _exposure_backward(ctx.aff_mlp_state[0], ctx.aff_mlp_state[1], daff, None, m_need,
                                                    ctx.aff_x_shape, None)
+            t_s = None
+            if spec.tail_work is not None:
+                # Work the caller wants issued beside the backward's HBM-bound tail (weight-gradient streams + feature
+                # scatter), typically the parameter-free head of the NEXT iteration (Renderer.prepare_batch: sampling +
+                # neighbour search, issue-bound and L2-resident; its CTAs fit beside the weight-gradient CTAs).  It starts
+                # once both decoders' data gradients are done and joins the main stream before backward returns.
+                if fork:
+                    t_s = _side_stream(dev, 4)
+                    t_s.wait_stream(main)
+                    with torch.cuda.stream(t_s):
+                        spec.tail_work()
+                else:
+                    spec.tail_work()
             if dfg is not None or dfc is not None or need_p:
                 _call("hps_interp_bwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(w), _lib.ptr(has), _lib.ptr(pos),
                       _lib.ptr(fg), _lib.ptr(fc), _lib.ptr(c_geo), _lib.ptr(c_col), _lib.ptr(dc_g), _lib.ptr(dc_c), P,
@@ -1018,6 +1043,8 @@ class _RenderRays(torch.autograd.Function):
                     main.wait_stream(e_s)
             for w_s in wgrad_streams:
                 main.wait_stream(w_s)
+            if t_s is not None:
+                main.wait_stream(t_s)
         gg = [(g if (g is not None and need[7 + i]) else None) for i, g in enumerate(dg)] if dg else [None] * N_PARAM
         if spec.color_stage:
             gcw = [(g if (g is not None and need[7 + N_PARAM + i]) else None) for i, g in enumerate(dcw)] \

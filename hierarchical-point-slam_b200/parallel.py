@@ -109,3 +109,30 @@ def allreduce_scalars(values, dist, group=None):
     t = t.to(dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
+
+
+def render_img_sharded(renderer, dist, *args, group=None, gather=True, **kwargs):
+    """Renderer.render_img (Renderer.py:256-337) with the image rows dealt out to the ranks ("shard the 103
+    chunks / image rows; outputs are disjoint slices"): rank r renders rows shard_bounds(H, r, world) through
+    render_img(row_range=...) against its replica of the cloud - no data-path collective.  gather=True: the row blocks
+    are all-gathered (6 MB per 640x480 frame) and every rank returns the full (H,W) depth, uncertainty and (H,W,3)
+    colour, equal to the single-process render; gather=False: the rank-local rows and their (r0, r1)."""
+    rank = dist.get_rank(group) if dist is not None else 0
+    world = dist.get_world_size(group) if dist is not None else 1
+    H, W = renderer.H, renderer.W
+    r0, r1 = shard_bounds(H, rank, world)
+    depth, unc, color = renderer.render_img(*args, row_range=(r0, r1), **kwargs)
+    if not gather or world == 1:
+        return (depth, unc, color) if gather else (depth, unc, color, (r0, r1))
+    rows = max(h - l for l, h in (shard_bounds(H, r, world) for r in range(world)))
+    # one packed block per rank: [depth | unc | r | g | b] per pixel as float64 (depth / unc are float64 in the reference)
+    block = torch.zeros(rows, W, 5, dtype=torch.float64, device=depth.device)
+    block[:r1 - r0, :, 0], block[:r1 - r0, :, 1], block[:r1 - r0, :, 2:] = depth, unc, color.double()
+    full = torch.empty(world * rows, W, 5, dtype=torch.float64, device=depth.device)
+    dist.all_gather_into_tensor(full, block, group=group)
+    parts = []
+    for r in range(world):
+        l, h = shard_bounds(H, r, world)
+        parts.append(full[r * rows:r * rows + (h - l)])
+    full = torch.cat(parts, 0)
+    return full[..., 0].contiguous(), full[..., 1].contiguous(), full[..., 2:].to(color.dtype).contiguous()

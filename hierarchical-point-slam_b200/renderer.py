@@ -145,7 +145,7 @@ class Renderer(object):
     def render_batch_ray(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None,
                          npc_geo_feats=None, npc_col_feats=None, is_tracker=False, cloud_pos=None,
                          normals=None, dynamic_r_query=None, exposure_feat=None, prepared=None, _loss=None,
-                         _z_zero_rows=None):
+                         _z_zero_rows=None, tail_work=None):
         """One fused kernel sequence (ops.render_rays): sampling, exact neighbour search, interpolation of both
         feature tables from one neighbour list, both decoders, compositing with the -100 overwrite.
         `prepared` (not in the reference): the ops.RayPrep of prepare_batch() for these very rays."""
@@ -199,7 +199,7 @@ class Renderer(object):
             min_nn=geo.min_nn_num, min_valid=int(S / 2 + 1), color_stage=color_stage, tracker=bool(is_tracker),
             cloud_pos=cloud_pos[level] if is_tracker else None, fill_geo=decoders._fill("geo", rays_o.device),
             fill_col=decoders._fill("col", rays_o.device) if color_stage else None, prep=prepared,
-            aff_mlp=aff_prm is not None)
+            aff_mlp=aff_prm is not None, tail_work=tail_work)
         loss = None
         if _loss is not None and _loss[0] == "tracker":
             _, gt_color, w_color, reduce_fn = _loss
@@ -243,7 +243,7 @@ class Renderer(object):
 
     def render_batch_ray_loss(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth, gt_color, w_color_loss,
                               npc_geo_feats=None, npc_col_feats=None, cloud_pos=None, dynamic_r_query=None,
-                              exposure_feat=None, prepared=None, affine=None, frame_index=None):
+                              exposure_feat=None, prepared=None, affine=None, frame_index=None, tail_work=None):
         """One mapper iteration's forward as ONE autograd node (not in the reference, which spells it out in
         Mapper.py:783-856): render_batch_ray(..., exposure_feat=None) followed by
             mask = (gt_depth > 0) & valid & ~isnan(depth)
@@ -255,11 +255,15 @@ class Renderer(object):
         -> (loss, depth, uncertainty, color, valid_ray_mask); only `loss` carries gradient (to the feature tables, the
         decoders, the exposure MLP and exposure_feat).  The compositing and loss kernels are one, the exposure MLP
         runs beside the neighbour search, and loss.backward() feeds the upstream gradient to the kernels as a device
-        scalar - ten launches fewer on the critical path than render_batch_ray + mapper_loss."""
+        scalar - ten launches fewer on the critical path than render_batch_ray + mapper_loss.
+        tail_work: a callable issued on a side stream beside the tail of loss.backward() (weight gradients + feature
+        scatter, HBM-bound) - e.g. `lambda: renderer.prepare_batch(<the next iteration's rays>, out=prep_next)`: the
+        next batch's pixels are drawn independently of the parameters (common.py:199-258), so its sampling + neighbour
+        search need not wait for this iteration's optimiser step."""
         return self.render_batch_ray(npc, decoders, rays_d, rays_o, device, stage, gt_depth=gt_depth,
                                      npc_geo_feats=npc_geo_feats, npc_col_feats=npc_col_feats, is_tracker=False,
                                      cloud_pos=cloud_pos, dynamic_r_query=dynamic_r_query, exposure_feat=None,
-                                     prepared=prepared,
+                                     prepared=prepared, tail_work=tail_work,
                                      _loss=("mapper", gt_color, w_color_loss, exposure_feat, affine, frame_index))
 
     def render_batch_ray_tracker_loss(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth, gt_color,
@@ -319,7 +323,12 @@ class Renderer(object):
 
     # Renderer.py:256-337
     def render_img(self, npc, decoders, c2w, device, stage, gt_depth=None, npc_geo_feats=None,
-                   npc_col_feats=None, normals=None, dynamic_r_query=None, cloud_pos=None, exposure_feat=None):
+                   npc_col_feats=None, normals=None, dynamic_r_query=None, cloud_pos=None, exposure_feat=None,
+                   row_range=None):
+        """row_range (not in the reference): (r0, r1) renders image rows [r0, r1) only and returns (r1 - r0, W) maps -
+        the unit parallel.render_img_sharded deals out to the ranks of a multi-GPU job.  Rays are independent, and the
+        one frame-level statistic (the far bound of rays without a depth reading, a statistic of the REFERENCE's
+        3000-ray chunk) is taken over the whole frame before the rows are cut, so the rows equal the full render's."""
         with torch.no_grad():
             H, W = self.H, self.W
             rays_o, rays_d = get_rays(H, W, self.fx, self.fy, self.cx, self.cy, c2w, device)
@@ -334,19 +343,31 @@ class Renderer(object):
             # the chunking - the sampling range of rays without a depth reading - is computed per reference chunk.
             B = max(self.ray_batch_size, self.min_render_chunk)
             z_rows = None
-            if (B > self.ray_batch_size and gt_depth is not None and not self.sample_near_pcl
+            if ((B > self.ray_batch_size or row_range is not None) and gt_depth is not None and not self.sample_near_pcl
                     and not self.assume_positive_depth):
                 z_rows = self._z_rows_for_zero_depth(gt_depth, self.ray_batch_size, rays_o.device)
-            for i in range(0, rays_d.shape[0], B):
-                rq = {k: v[i:i + B] for k, v in dynamic_r_query.items()} if self.use_dynamic_radius else None
+            lo, hi = 0, rays_d.shape[0]
+            if row_range is not None:
+                r0, r1 = int(row_range[0]), int(row_range[1])
+                if not 0 <= r0 <= r1 <= H:
+                    raise ValueError("row_range must satisfy 0 <= r0 <= r1 <= H")
+                if self.sample_near_pcl:
+                    raise NotImplementedError("row_range with sample_near_pcl (the probe far bound is a chunk statistic)")
+                lo, hi, H = r0 * W, r1 * W, r1 - r0
+            for i in range(lo, hi, B):
+                j = min(i + B, hi)
+                rq = {k: v[i:j] for k, v in dynamic_r_query.items()} if self.use_dynamic_radius else None
                 d, u, c, _ = self.render_batch_ray(
-                    npc, decoders, rays_d[i:i + B], rays_o[i:i + B], device, stage,
-                    gt_depth=None if gt_depth is None else gt_depth[i:i + B], npc_geo_feats=npc_geo_feats,
+                    npc, decoders, rays_d[i:j], rays_o[i:j], device, stage,
+                    gt_depth=None if gt_depth is None else gt_depth[i:j], npc_geo_feats=npc_geo_feats,
                     npc_col_feats=npc_col_feats, normals=normals, cloud_pos=cloud_pos, dynamic_r_query=rq,
-                    exposure_feat=exposure_feat, _z_zero_rows=None if z_rows is None else z_rows[i:i + B])
+                    exposure_feat=exposure_feat, _z_zero_rows=None if z_rows is None else z_rows[i:j])
                 depths.append(d.double())
                 uncs.append(u.double())
                 colors.append(c)
+            if not depths:
+                z = torch.zeros(0, W, dtype=torch.float64, device=device)
+                return z, z.clone(), torch.zeros(0, W, 3, device=device)
             depth = torch.cat(depths, 0).reshape(H, W)
             uncertainty = torch.cat(uncs, 0).reshape(H, W)
             color = torch.cat(colors, 0).reshape(H, W, 3)

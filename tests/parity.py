@@ -10,11 +10,23 @@ from oracle import hps_oracle as O
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 TOL = 1e-4
+ELEM_RTOL, ELEM_ATOL_FRAC = 1e-4, 2e-5      # elementwise bar beside the max-norm one (elem_off)
 
 
 def rel(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
+
+
+def elem_off(a, b, rtol=1e-4, atol_frac=1e-5):
+    """Elementwise companion of rel(): the fraction of entries with |a - b| > rtol |b| + atol_frac max|b|.  rel() is a
+    max-norm - an entry far below the largest one may be off by 100 % of itself and still pass; here every entry is held
+    to rtol of ITS OWN magnitude plus a floor of atol_frac of the largest one (fp32 sums of cancelling terms cannot do
+    better than a floor relative to the terms, not to the result)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    if b.numel() == 0:
+        return 0.0
+    return float(((a - b).abs() > rtol * b.abs() + atol_frac * b.abs().max()).double().mean())
 
 
 def load(name):
@@ -102,6 +114,12 @@ def check_mapper(stage, out, ref, dec, tol=TOL):
         gnamed = dict(getattr(dec, "geo_decoder_" + level).named_parameters())
         errs["g_geo_dec"] = max(rel(gnamed[k].grad, g) for k, g in ref["g_geo_dec"].items())
     bad = {k: v for k, v in errs.items() if not v < tol}
+    # elementwise (see elem_off): forward outputs and feature gradients, every entry on its own
+    for k in ("depth", "color", "g_geo", "g_col"):
+        if ref.get(k) is not None:
+            errs[k + "/elem_off"] = elem_off(out[k], ref[k], rtol=ELEM_RTOL, atol_frac=ELEM_ATOL_FRAC)
+            if errs[k + "/elem_off"] > 0:
+                bad[k + "/elem_off"] = errs[k + "/elem_off"]
     assert not bad, "stage %s over tolerance %g: %s (all: %s)" % (stage, tol, bad, errs)
     return errs
 

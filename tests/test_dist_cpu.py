@@ -114,3 +114,47 @@ def test_grad_exchange_coalesces_views_of_one_buffer(tmp_path):
             assert torch.allclose(r[k]["got"][i], a + b, rtol=0, atol=1e-6), i
     # 4 views of one buffer -> 1 collective; the 70000-element gradient and the float64 one on their own; 2 small -> 1 bucket
     assert r[0]["n_coll"] == 4
+
+
+class _RowRenderer:
+    """Stand-in with Renderer.render_img's row_range contract (no kernels on the CPU): pixel values are a fixed function
+    of the pixel coordinates, so the gathered frame can be compared with the one-process frame."""
+    H, W = 37, 16          # 37 rows: uneven shards
+
+    def render_img(self, scale, row_range=None):
+        r0, r1 = row_range if row_range is not None else (0, self.H)
+        v, u = torch.meshgrid(torch.arange(r0, r1, dtype=torch.float64), torch.arange(self.W, dtype=torch.float64), indexing="ij")
+        depth = scale * (v * 100 + u)
+        color = torch.stack([v, u, v + u], -1).float()
+        return depth, depth * 0.5, color
+
+
+def _render_worker(rank, world, port, out):
+    import importlib
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    hps = importlib.import_module("hierarchical-point-slam_b200")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    r = _RowRenderer()
+    full = hps.parallel.render_img_sharded(r, dist, 2.0)
+    local = hps.parallel.render_img_sharded(r, dist, 2.0, gather=False)
+    torch.save(dict(full=full, local=local), out % rank)
+    dist.destroy_process_group()
+
+
+def test_render_img_sharded_over_rows_equals_the_whole_frame(tmp_path):
+    """parallel.render_img_sharded (BASELINE configs[4]): rows dealt out to two ranks and all-gathered equal
+    the one-process frame on every rank; gather=False hands back the rank's own rows."""
+    out = str(tmp_path / "img%d.pt")
+    mp.spawn(_render_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    want = _RowRenderer().render_img(2.0)
+    bounds = [(0, 19), (19, 37)]
+    for k in range(2):
+        r = torch.load(out % k, weights_only=False)
+        for got, w in zip(r["full"], want):
+            assert got.dtype == w.dtype and torch.equal(got, w)
+        d, u, c, rows = r["local"]
+        assert tuple(rows) == bounds[k]
+        assert torch.equal(d, want[0][rows[0]:rows[1]]) and torch.equal(c, want[2][rows[0]:rows[1]])
