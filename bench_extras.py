@@ -387,11 +387,10 @@ def full_frame(hps, wl, bench, rank, world, dist):
         idx.reset(pts)
         idx.cell_hint = 0.08
         grid = idx._ensure_grid(None)
-        group = 5 if q.shape[0] >= hps.ops.KNN_GROUP_MIN_QUERIES else 1
-        grid.query(q, t_up, t_dn, group=group)
+        grid.query(q, t_up, t_dn)
         if d_ is not None:
             d_.barrier()
-        ms = _max_over_ranks(_timed(lambda: grid.query(q, t_up, t_dn, group=group), 5, warm=1), d_, dev)
+        ms = _max_over_ranks(_timed(lambda: grid.query(q, t_up, t_dn), 5, warm=1), d_, dev)
         sweep["%dM" % n_m] = {"ms": ms, "queries_per_s": H * W * 5 / (ms * 1e-3)}
         del idx, grid, pts
     res["knn_sweep"] = dict(sweep, queries=H * W * 5, note="fine radii 0.04-0.16 m, queries dealt out by image rows")

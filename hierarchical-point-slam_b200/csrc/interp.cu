@@ -116,16 +116,27 @@ interp_bwd_kernel(const float* __restrict__ p, const int32_t* __restrict__ I, co
         if (dc_a != nullptr) ca = ldg4(c_a + pi * kC + ch * 4);
         if (dc_b != nullptr) cb = ldg4(c_b + pi * kC + ch * 4);
     }
+    // Every lane reads the weight and index of its two neighbour slots itself (eight lanes share an address: one
+    // broadcast transaction) and the row-map entries right behind them, all issued before the first reduction: the
+    // r01o capture had 31 % of this kernel's stall samples on the shuffles that used to hand them out from lanes 0..7.
+    float wjs[kK / 4];
+    int ijs[kK / 4], gjs[kK / 4];
+#pragma unroll
+    for (int it = 0; it < kK / 4; ++it) {
+        wjs[it] = __ldg(w_in + pi * kK + it * 4 + nb);
+        ijs[it] = __ldg(I + pi * kK + it * 4 + nb);
+    }
+#pragma unroll
+    for (int it = 0; it < kK / 4; ++it)      // gradient row: the table row itself, or its slot in the compact live-row
+        gjs[it] = (row_map != nullptr && wjs[it] != 0.f) ? __ldg(row_map + ijs[it]) : ijs[it];   // buffer (-1 = frozen row)
     float gdot[kK / 4];
 #pragma unroll
     for (int it = 0; it < kK / 4; ++it) {
-        const int j = it * 4 + nb;
-        const float wj = __shfl_sync(kFull, w, j);
-        const int ij = __shfl_sync(kFull, idx, j);
+        const float wj = wjs[it];
+        const int ij = ijs[it];
         float part = 0.f;
         if (wj != 0.f) {
-            // gradient row: the table row itself, or its slot in the compact live-row buffer (-1 = frozen row)
-            const int gj = row_map != nullptr ? __ldg(row_map + ij) : ij;
+            const int gj = gjs[it];
             if (dc_a != nullptr) {
                 if (dfeats_a != nullptr && gj >= 0)
                     red_add_v4(dfeats_a + (int64_t)gj * kC + ch * 4,

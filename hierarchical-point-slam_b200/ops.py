@@ -49,10 +49,23 @@ _KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_sample_knn": 
 TIMERS = None   # set to {} to record (start, end) CUDA events per call name on the current stream
 
 
+# NVTX ranges: HPS_NVTX=1 wraps every C-ABI call in a range named after the entry point (decoder
+# calls carry the decoder kind) and the fused render's forward / backward in "hps.render_rays.fwd/bwd"; nsys / ncu
+# --nvtx then attribute kernels to calls.  Off by default: two extra Python calls per launch.
+NVTX = os.environ.get("HPS_NVTX", "0") != "0"
+
+
 def _call(name, *args):
     """Invoke one C-ABI entry point on the current stream (raises on a non-zero return code)."""
     fn = getattr(_lib.load(), name)
     LAUNCHES["n"] += _KERNELS_PER_CALL.get(name, 0)
+    if NVTX:
+        torch.cuda.nvtx.range_push("%s[%d]" % (name, args[0]) if name.startswith("hps_mlp") and isinstance(args[0], int) else name)
+        try:
+            _lib.check(fn(*args))
+        finally:
+            torch.cuda.nvtx.range_pop()
+        return
     if TIMERS is None:
         _lib.check(fn(*args))
         return
@@ -184,9 +197,12 @@ class VoxelHashGrid:
                                              ctypes.byref(cell), ctypes.byref(st), _stream()))
         return dict(n_points=n.value, table_size=T.value, n_cells=nc.value, cell_size=cell.value, status=st.value)
 
-    def query(self, q, t_up, t_dn, want_cand=False, group=1):
-        """q (Q,3) -> I (Q,8) int32, D (Q,8) f32, count (Q,) int32 [, cand (Q,) int32].  group=5: consecutive
-        queries in fives (the samples of a ray) share one sweep; the result is the same."""
+    def query(self, q, t_up, t_dn, want_cand=False, group=None):
+        """q (Q,3) -> I (Q,8) int32, D (Q,8) f32, count (Q,) int32 [, cand (Q,) int32].  group: which edition of the
+        search kernel answers - None / 0: four lanes per query (default); 1: one warp per query; 5: one warp per five
+        consecutive queries (the samples of a ray) sharing one sweep.  The result is the same."""
+        if group is None:
+            group = 0 if KNN_IMPL == "sub" else 1
         _need_cuda(q, t_up, t_dn)
         q = _f32c(q).reshape(-1, 3)
         Q = q.shape[0]
@@ -317,6 +333,9 @@ def _new_bwd_images(kind, dev):
 
 
 N_SM = 148
+# Edition of the neighbour-search kernel: "sub" = four lanes per query with a voxel-vs-ball cull (csrc/grid.cu, second
+# edition; default), "warp" = the first edition (one warp per query, ray-grouped from KNN_GROUP_MIN_QUERIES on).
+KNN_IMPL = os.environ.get("HPS_KNN_IMPL", "sub")
 # Ray-grouped neighbour search (one warp answers the 5 samples of a ray) trades parallelism for shared probes and
 # loads: measured on the bench cloud (scripts/knn_group_bench.py) 55 vs 47 us at 25,000 queries (too few warps to
 # hide latency), 143 vs 152 us at 100,000, 269 vs 292 us at 200,000.
@@ -629,7 +648,13 @@ def _sample_and_search(grid, ro, rd, gd, rad_t, rad, zz, R, S, near, far, z, pts
     KNN_GROUP_MIN_QUERIES queries on); with SAMPLE_IN_SEARCH one launch (the search computes its query points itself)."""
     P = R * S
     scalar = 0.0 if rad_t is not None else float(rad)
-    if (S == 5 and P >= KNN_GROUP_MIN_QUERIES) or not SAMPLE_IN_SEARCH:
+    if KNN_IMPL == "sub" and not SAMPLE_IN_SEARCH:
+        _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t), scalar, _lib.ptr(zz),
+              _z_zero_stride(zz, R, S), R, S, float(near), float(far), _lib.ptr(z), _lib.ptr(pts), _lib.ptr(t_up),
+              _lib.ptr(t_dn), stream)
+        _call("hps_knn_query", grid._h, _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), P, _lib.ptr(I), _lib.ptr(D),
+              _lib.ptr(cnt), None, 0, stream)
+    elif (S == 5 and P >= KNN_GROUP_MIN_QUERIES and KNN_IMPL != "sub") or not SAMPLE_IN_SEARCH:
         _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t), scalar, _lib.ptr(zz),
               _z_zero_stride(zz, R, S), R, S, float(near), float(far), _lib.ptr(z), _lib.ptr(pts), _lib.ptr(t_up),
               _lib.ptr(t_dn), stream)
@@ -715,6 +740,16 @@ class _RenderRays(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, *params):
+        if NVTX:
+            torch.cuda.nvtx.range_push("hps.render_rays.fwd")
+            try:
+                return _RenderRays._forward(ctx, spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, *params)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return _RenderRays._forward(ctx, spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, *params)
+
+    @staticmethod
+    def _forward(ctx, spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, *params):
         _need_cuda(rays_o, rays_d, gt_depth, feats_geo)
         dev = rays_o.device
         R, S = rays_o.shape[0], spec.S
@@ -914,6 +949,16 @@ class _RenderRays(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, *gouts):
+        if NVTX:
+            torch.cuda.nvtx.range_push("hps.render_rays.bwd")
+            try:
+                return _RenderRays._backward(ctx, *gouts)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return _RenderRays._backward(ctx, *gouts)
+
+    @staticmethod
+    def _backward(ctx, *gouts):
         spec = ctx.spec
         gscale = None
         if ctx.loss_state is not None:          # gradients of the fused loss, scaled by the upstream gradient in-kernel

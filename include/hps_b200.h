@@ -54,8 +54,10 @@ int hps_grid_info(const hps_grid_t* g, int64_t* n_points, int64_t* table_size, i
  *   D[nq][8]   fl(fl(dx*dx+dy*dy)+dz*dz) fp32 without FMA; unused slots FLT_MAX
  *   count[nq]  number of slots with D < t_up   (== reference neighbor_num)
  *   cand[nq]   optional (may be NULL): candidates examined for the query's group (for the roofline figure)
- *   group      1, or 5: consecutive queries [5g, 5g+5) - the samples of one ray - are answered by one warp that
- *              shares the voxel probes and candidate loads among them (results are independent of `group`)
+ *   group      which edition of the kernel answers (results are independent of it): 0 = four lanes per query, voxels
+ *              that cannot reach the query ball culled before their hash slot is read (default of the host layer; I
+ *              and D must be 16-byte aligned); 1 = one warp per query; 5 = consecutive queries [5g, 5g+5) - the
+ *              samples of one ray - are answered by one warp that shares the voxel probes and candidate loads
  * Slots j < count are bit-identical to the reference's exhaustive search.                           */
 int hps_knn_query(const hps_grid_t* g, const float* q, const float* t_up, const float* t_dn,
                   int64_t nq, int32_t* I, float* D, int32_t* count, int32_t* cand, int group, void* stream);
