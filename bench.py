@@ -128,28 +128,36 @@ def frustum_live_rows(points, cam):
     return live.nonzero().flatten()
 
 
-def cpu_step_fn(scene, n_rays):
+def cpu_step_fn(scene, n_rays, dtype=torch.float32):
     """The reference's mapper iteration on the host cores (oracle port): like Mapper.py:512-536, 615-624 the optimised
     leaves are the frustum-selected rows, written into the full tables (index_put) before the render call.
-    step(b) -> dict(loss, depth, color, valid, g_geo, g_col (leaf gradients), g_dec, g_geo_dec (name -> gradient))."""
+    step(b) -> dict(loss, depth, color, valid, g_geo, g_col (leaf gradients), g_dec, g_geo_dec (name -> gradient)).
+    dtype: float32 = the reference's arithmetic; float64 = the same computation as "truth" for the parity check (same
+    decoder values, same neighbour lists)."""
     from oracle import hps_oracle as O
     torch.manual_seed(1219)
     hps = importlib.import_module("hierarchical-point-slam_b200")
     cfg = hps.scannet_cfg("cpu")
     dec_mod = hps.get_model(cfg)
+    cv = lambda t: t.detach().to(dtype) if t.is_floating_point() else t
     dec = {}
     for name in ("geo_decoder_fine", "color_decoder_fine"):
         m = getattr(dec_mod, name)
-        d = {k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items() if v.is_floating_point()}
-        d["embedder._B"] = m.embedder._B.detach().clone().requires_grad_(name.startswith("geo"))
+        d = {k: cv(v).clone().requires_grad_(True) for k, v in m.state_dict().items() if v.is_floating_point()}
+        d["embedder._B"] = cv(m.embedder._B).clone().requires_grad_(name.startswith("geo"))
         dec[name] = d
     knn = O.KDTreeNeighbors()
     fine = scene["fine"]
-    pos = {"fine": fine["points"]}
+    pos = {"fine": fine["points"]}            # the search always runs on the fp32 positions (D in fp32, SURVEY A3)
     live_idx = frustum_live_rows(fine["points"], cfg["cam"])
-    leaf_g = fine["geo_feats"][live_idx].clone().requires_grad_(True)
-    leaf_c = fine["col_feats"][live_idx].clone().requires_grad_(True)
-    tab_g, tab_c = fine["geo_feats"].clone(), fine["col_feats"].clone()
+    leaf_g = cv(fine["geo_feats"][live_idx]).clone().requires_grad_(True)
+    leaf_c = cv(fine["col_feats"][live_idx]).clone().requires_grad_(True)
+    tab_g, tab_c = cv(fine["geo_feats"]).clone(), cv(fine["col_feats"]).clone()
+    fill_g, fill_c, ef = cv(scene["c_fill_geo"]), cv(scene["c_fill_col"]), cv(scene["exposure_feat"])
+
+    def knn_fn(points, queries, radius):       # neighbour lists from the fp32 query points, whatever dtype the rest runs in
+        D, I, n = knn(points, queries.float(), radius)
+        return D.to(dtype), I, n
 
     def step(b, keep=False):
         sl = slice(b * RAYS, b * RAYS + n_rays)
@@ -157,11 +165,10 @@ def cpu_step_fn(scene, n_rays):
             t.grad = None
         gf = {"fine": tab_g.detach().index_put((live_idx,), leaf_g)}          # Mapper.py:621-624
         cf = {"fine": tab_c.detach().index_put((live_idx,), leaf_c)}
-        d, v, c, m = O.render_batch_ray(pos, dec, fine["rays_d"][sl], fine["rays_o"][sl], STAGE, fine["gt_depth"][sl],
-                                        gf, cf, {"fine": fine["radius"][sl]}, scene["c_fill_geo"], scene["c_fill_col"],
-                                        knn_fn=knn)
-        aff = O.exposure_affine(dec["color_decoder_fine"], scene["exposure_feat"])
-        loss = O.mapper_loss(d, c, m, fine["gt_depth"][sl], fine["gt_color"][sl], STAGE, 0.1, aff)
+        d, v, c, m = O.render_batch_ray(pos, dec, cv(fine["rays_d"][sl]), cv(fine["rays_o"][sl]), STAGE, cv(fine["gt_depth"][sl]),
+                                        gf, cf, {"fine": fine["radius"][sl]}, fill_g, fill_c, knn_fn=knn_fn)
+        aff = O.exposure_affine(dec["color_decoder_fine"], ef)
+        loss = O.mapper_loss(d, c, m, cv(fine["gt_depth"][sl]), cv(fine["gt_color"][sl]), STAGE, 0.1, aff)
         loss.backward()
         if not keep:
             return float(loss.detach())
@@ -234,6 +241,7 @@ def workload_config(n_gpus):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
+HEAD_AT = os.environ.get("HPS_BENCH_HEAD_AT", "exchange")      # N > 1: next head beside the "exchange" or the backward "tail"
 OVERLAP_HEAD = os.environ.get("HPS_BENCH_OVERLAP", "1") != "0"   # N = 1: next iteration's head beside this one's tail
 
 
@@ -319,7 +327,27 @@ def run_ours(args, rank, world, local_rank):
         out["radius"], out["radius_mid"] = s64[:RAYS], s64[RAYS:]
         return out
 
-    overlap = OVERLAP_HEAD and world == 1
+    # Gradient exchange at N > 1: this package's peer-memory all-reduce kernel inside the iteration's graph (default), or
+    # NCCL issued eagerly behind the graph (HPS_BENCH_EXCHANGE=nccl, and the fallback when symmetric memory is unavailable)
+    peer, exchange_kind = None, "none"
+    if world > 1:
+        exchange_kind = "nccl all_reduce, eager, beside the next head"
+        if os.environ.get("HPS_BENCH_EXCHANGE", "peer") == "peer":
+            ok = 1
+            try:
+                peer = hps.parallel.PeerGradExchange(2 * int(live_idx.numel()) * 32 + 1_000_000, dev, dist)
+            except Exception as e:                                # pragma: no cover
+                ok = 0
+                log_err = "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:160])
+                print("[rank %d] peer exchange unavailable: %s" % (rank, log_err), file=sys.stderr, flush=True)
+            flag = torch.tensor([ok], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if not int(flag):
+                peer = None
+            else:
+                exchange_kind = "hps_peer_allreduce (%s) inside the iteration's graph" % peer.peer.default_variant()
+    wl.peer = peer
+    overlap = OVERLAP_HEAD and (world == 1 or peer is not None)
     static_pk = [torch.empty_like(dev_pk[0]) for _ in range(2 if overlap else 1)]
     views = [typed_views(b) for b in static_pk]
     prep = [None] * len(static_pk)
@@ -342,7 +370,11 @@ def run_ours(args, rank, world, local_rank):
             out = renderer.render_batch_ray_loss(
                 npc, dec, v["rays_d"], v["rays_o"], dev, STAGE, v["gt_depth"], v["gt_color"], 0.1,
                 npc_geo_feats=gf, npc_col_feats=cf, cloud_pos=pos, dynamic_r_query=rq(k), exposure_feat=exposure_feat,
-                prepared=prepared, tail_work=tail)
+                prepared=prepared, tail_work=tail if (peer is None or HEAD_AT == "tail") else None,
+                grad_buffer=peer.pool if peer is not None else None,
+                # N > 1: the peer-memory all-reduce, issued inside backward once every gradient is complete, with the
+                # next batch's head beside it (on one GPU the head goes beside the backward's tail instead: tail_work)
+                after_grads=(lambda: peer(beside=tail if HEAD_AT != "tail" else None)) if peer is not None else None)
             loss = out[0]
         else:               # the reference's seams: render_batch_ray, then the loss (HPS_BENCH_FUSED_LOSS=0)
             depth, unc, color, valid = renderer.render_batch_ray(
@@ -362,14 +394,15 @@ def run_ours(args, rank, world, local_rank):
     exch = {"ev": None}
 
     def exchange():
-        """Blocking form (instrumented pass): gradient all-reduce over NCCL on the iteration's stream."""
-        if world > 1:
+        """Blocking form (instrumented pass): the gradient all-reduce on the iteration's stream.  (The peer-memory
+        exchange is part of step() itself: after_grads.)"""
+        if world > 1 and peer is None:
             grad_exchange(dist)
 
     def post():
         """Start the gradient all-reduce of the iteration just issued on the communication stream.  The fused
         backward's gradients are views of one buffer, so this is one grouped NCCL launch."""
-        if world > 1:
+        if world > 1 and peer is None:
             main = torch.cuda.current_stream()
             comm.wait_stream(main)
             with torch.cuda.stream(comm):
@@ -406,6 +439,9 @@ def run_ours(args, rank, world, local_rank):
             graphs = [hps.graphs.GraphedStep(lambda k=k: step(k, prep[k], tail=lambda: head(1 - k)), {}, warmup=3)
                       for k in (0, 1)]
             mode = "cuda-graph replay, the next iteration's head (sampling + neighbour search) beside this one's backward tail"
+            if peer is not None:
+                mode = ("cuda-graph replay (one graph per iteration); gradient exchange = " + exchange_kind +
+                        ", the next iteration's head (sampling + neighbour search) beside it")
             launches_per_step = hps.ops.LAUNCHES["n"] // 8      # 2 graphs x (3 warm-up passes + the captured one)
 
             def need(i):
@@ -513,7 +549,10 @@ def run_ours(args, rank, world, local_rank):
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
     # ---- sustained: >= 2 s of back-to-back iterations (no L2 flush, batches cycled), one event pair around all of
     # them - what a mapper that runs 600 iterations per frame sees; the clock sampler keeps sampling through it ----
-    n_sus = max(200, int(2200.0 / max(dev_ms / args.steps, 0.05)))
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)          # every rank must run the same number of iterations
+    n_sus = max(200, int(2200.0 / max(float(t[0]) / args.steps, 0.05)))
     prime(0, dev_pk)
     run(0, dev_pk)
     post()
@@ -600,6 +639,12 @@ def run_ours(args, rank, world, local_rank):
         roof = roofline(per, hps, npc, {k: v.to(dev) for k, v in host.items()}, slice(0, RAYS))
     if world > 1:
         dist.barrier()
+    exchange_status = "ok"
+    if peer is not None:
+        try:
+            peer.check()
+        except Exception as e:                                    # pragma: no cover
+            exchange_status = str(e)[:200]
     line, rc = None, 0
     if rank == 0:
         h2d = host_pk[0].numel() * host_pk.element_size()
@@ -618,12 +663,14 @@ def run_ours(args, rank, world, local_rank):
                               "note": "back-to-back iterations, no L2 flush, one CUDA-event pair around all of them; the "
                                       "clock sampler ('clocks') covers the timed region, this run and the e2e loop"},
                 "gpu_launches": launches, "roofline": roof["roofline"], "kernels_ms_per_step": roof["per_kernel"]}
+        if world > 1:
+            line["exchange"] = {"kind": exchange_kind, "status": exchange_status}
     if world == 1:
         # ---- parity on this very workload: one 5,000-ray batch of the bench, GPU vs the oracle port ----
         torch.set_num_threads(os.cpu_count() or 1)
         cpu_step = cpu_step_fn(scene, CPU_SAMPLE_RAYS)
         try:
-            line["parity"] = parity_check(hps, wl, cpu_step)
+            line["parity"] = parity_check(hps, wl, cpu_step, cpu_step64=cpu_step_fn(scene, CPU_SAMPLE_RAYS, torch.float64))
         except Exception as e:                                    # pragma: no cover
             line["parity"] = {"ok": False, "error": "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:200])}
         if not line["parity"].get("ok"):
@@ -727,22 +774,48 @@ def knn_parity(points, pts, rad, I, D, cnt, knn, spot=64):
     return {"queries": int(pts.shape[0]), "kdtree_mismatches": n_bad, "bit_exact": bool(exact), "count": nr}
 
 
-def parity_check(hps, wl, cpu_step, batch=0):
+def parity_check(hps, wl, cpu_step, batch=0, cpu_step64=None):
+    """GPU arm vs CPU arm on ONE batch of the bench workload (5,000 rays x 5 samples, 1M-point fine cloud): neighbour
+    lists bit for bit (indices, distances and in-radius counts on every in-radius slot; a query whose k-d tree answer
+    differs is re-checked against the exhaustive fp32 search - the k-d tree ranks by float64 distance), forward outputs and
+    loss at 1e-4 relative (max-norm) against the fp32 oracle.
+    Gradients: `<q>_rel` is the distance to the fp32 oracle.  At this size that number alone is not a verdict for the
+    quantities behind the geometry decoder: its Fourier arguments 2 pi p B reach ~1e3 rad, so fp32 puts ~1e-4 of noise
+    into every pre-activation, and among 4 million ReLU pre-activations a few dozen sit closer to zero than that - the
+    fp32 REFERENCE ITSELF is 7e-3 (feature gradients) / 4e-3 (geometry-decoder gradients) away from its own float64
+    evaluation on this batch.  With cpu_step64 (the same oracle in float64) every gradient is therefore also held to
+    `<q>_vs_f64` <= max(1e-4, 3 x `<q>_ref32_vs_f64`): no further from the truth than the reference's own arithmetic."""
     ref = cpu_step(batch, keep=True)
     out = eager_mapper_step(hps, wl, batch)
     torch.cuda.synchronize()
     loss, depth, unc, color, valid = out
     res = {"rays": RAYS, "fine_points": N_FINE, "tolerance": PARITY_TOL, "batch": batch}
     res["valid_equal"] = bool(torch.equal(valid.cpu().bool(), ref["valid"].bool()))
-    res["loss_rel"] = _rel(loss, ref["loss"])
-    res["depth_rel"] = _rel(depth, ref["depth"])
-    res["color_rel"] = _rel(color, ref["color"])
-    res["g_geo_rel"] = _rel(wl.lg.param.grad, ref["g_geo"])
-    res["g_col_rel"] = _rel(wl.lc.param.grad, ref["g_col"])
     cn = dict(wl.dec.color_decoder_fine.named_parameters())
     gn = dict(wl.dec.geo_decoder_fine.named_parameters())
-    res["g_dec_rel"] = max(_rel(cn[k].grad, g) for k, g in ref["g_dec"].items() if k in cn)
-    res["g_geo_dec_rel"] = max(_rel(gn[k].grad, g) for k, g in ref["g_geo_dec"].items() if k in gn)
+
+    def against(r):
+        return {"loss": _rel(loss, r["loss"]), "depth": _rel(depth, r["depth"]), "color": _rel(color, r["color"]),
+                "g_geo": _rel(wl.lg.param.grad, r["g_geo"]), "g_col": _rel(wl.lc.param.grad, r["g_col"]),
+                "g_dec": max(_rel(cn[k].grad, g) for k, g in r["g_dec"].items() if k in cn),
+                "g_geo_dec": max(_rel(gn[k].grad, g) for k, g in r["g_geo_dec"].items() if k in gn)}
+    e32 = against(ref)
+    for k, v in e32.items():
+        res[k + "_rel"] = v
+    ok = all(e32[k] <= PARITY_TOL for k in ("loss", "depth", "color"))
+    grads = ("g_geo", "g_col", "g_dec", "g_geo_dec")
+    if cpu_step64 is not None:
+        truth = cpu_step64(batch, keep=True)
+        e64 = against(truth)
+        noise = {"g_geo": _rel(ref["g_geo"], truth["g_geo"]), "g_col": _rel(ref["g_col"], truth["g_col"]),
+                 "g_dec": max(_rel(g, truth["g_dec"][k]) for k, g in ref["g_dec"].items()),
+                 "g_geo_dec": max(_rel(g, truth["g_geo_dec"][k]) for k, g in ref["g_geo_dec"].items())}
+        for k in grads:
+            res[k + "_vs_f64"], res[k + "_ref32_vs_f64"] = e64[k], noise[k]
+            ok = ok and (e32[k] <= PARITY_TOL or e64[k] <= max(PARITY_TOL, 3.0 * noise[k]))
+        res["gradient_criterion"] = "rel <= 1e-4 vs the fp32 oracle, or vs_f64 <= max(1e-4, 3 x ref32_vs_f64)"
+    else:
+        ok = ok and all(e32[k] <= PARITY_TOL for k in grads)
     # neighbour lists of the same 25,000 sample points
     prep = eager_head(hps, wl, batch)
     torch.cuda.synchronize()
@@ -751,10 +824,8 @@ def parity_check(hps, wl, cpu_step, batch=0):
     kn = knn_parity(fine["points"], prep.pts.cpu(), rad, prep.I.cpu().long(), prep.D.cpu(), prep.cnt.cpu(), ref["knn"])
     res.update({"knn_queries": kn["queries"], "knn_kdtree_mismatches": kn["kdtree_mismatches"],
                 "knn_bit_exact": kn["bit_exact"]})
-    exact, nr = kn["bit_exact"], kn["count"]
-    res["mean_in_radius"] = float(nr.float().mean())
-    worst = max(res[k] for k in res if k.endswith("_rel"))
-    res["ok"] = bool(exact and res["valid_equal"] and worst <= PARITY_TOL)
+    res["mean_in_radius"] = float(kn["count"].float().mean())
+    res["ok"] = bool(ok and kn["bit_exact"] and res["valid_equal"])
     return res
 
 

@@ -122,9 +122,15 @@ def tracking(hps, wl, bench):
         t0 = time.perf_counter()
         cam_cpu = _oracle_tracker_run(wl, bench, 6, saved_mlp)
         cpu_s = time.perf_counter() - t0
-        moved = float((cam_cpu - torch.tensor(CAM0, dtype=torch.float64)).abs().max())
+        # compared as camera matrices: the 7-vector's quaternion is not normalised and the pose does not depend on its
+        # length (common.py:304-328 divides by |q|^2), so d loss / d |q| is pure rounding noise that Adam turns into
+        # +-lr steps of the quaternion's length on either side - invisible in [R | t]
+        c2w = lambda cam: hps.get_camera_from_tensor(cam.float()).double()
+        start = c2w(torch.tensor(CAM0, dtype=torch.float64))
         vs_oracle = {"iterations": "3 x color_mid + 3 x color_fine, %d rays, Adam on pose + exposure latent + both exposure MLPs" % R,
-                     "max_abs_pose_diff": float((cam_gpu - cam_cpu).abs().max()), "pose_moved_by": moved,
+                     "max_abs_c2w_diff": float((c2w(cam_gpu) - c2w(cam_cpu)).abs().max()),
+                     "c2w_moved_by": float((c2w(cam_cpu) - start).abs().max()),
+                     "max_abs_7vector_diff": float((cam_gpu - cam_cpu).abs().max()),
                      "cpu_s_per_iter": cpu_s / 6}
         # ---- (2) the 200-iteration run, one CUDA graph per level ----
         restore()
@@ -423,13 +429,17 @@ def strong_scaling(hps, wl, bench, rank, world, dist, steps):
                                            {"fine": static["radius"], "mid": static["radius_mid"]}, out=prep["p"])
         return prep["p"].cnt
 
+    peer = getattr(wl, "peer", None) if world > 1 else None
+
     def rest():
         for t in targets:
             t.grad = None
         loss = renderer.render_batch_ray_loss(npc, dec, static["rays_d"], static["rays_o"], dev, bench.STAGE, static["gt_depth"],
                                               static["gt_color"], 0.1, npc_geo_feats=wl.gf, npc_col_feats=wl.cf, cloud_pos=wl.pos,
                                               dynamic_r_query={"fine": static["radius"], "mid": static["radius_mid"]},
-                                              exposure_feat=ef, prepared=prep["p"])[0]
+                                              exposure_feat=ef, prepared=prep["p"],
+                                              grad_buffer=peer.pool if peer is not None else None,
+                                              after_grads=peer)[0]     # this package's peer-memory all-reduce, in the graph
         loss.backward()
         return loss
 
@@ -449,7 +459,7 @@ def strong_scaling(hps, wl, bench, rank, world, dist, steps):
             torch.cuda.current_stream().wait_event(state["ev"])
             state["ev"] = None
         g_rest.graph.replay()
-        if world > 1:
+        if world > 1 and peer is None:
             comm.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(comm):
                 ex(dist)
@@ -473,8 +483,8 @@ def strong_scaling(hps, wl, bench, rank, world, dist, steps):
     return {"global_rays": total, "rays_per_gpu": hi - lo, "n_gpus": world, "ms_per_step": ms, "value": total / (ms * 1e-3),
             "unit": "rays/s", "steps": steps, "scaling": "strong",
             "note": "ONE reference-sized batch (mapping.pixels = 10,000, Mapper.py:380) sharded contiguously over the ranks "
-                    "(SURVEY 8e), gradients all-reduced; back to back, no L2 flush; head | rest graphs, exchange beside the "
-                    "next head"}
+                    "(SURVEY 8e), gradients all-reduced (%s); back to back, no L2 flush; head | rest graphs"
+                    % ("hps_peer_allreduce inside the rest graph" if peer is not None else "NCCL beside the next head")}
 
 
 def run(hps, wl, args, rank, world, dist):

@@ -60,6 +60,9 @@ SIGNATURES = {
     "hps_adam_multi_own_steps": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _f32, _f32, _vp, _i32, _vp]),
     "hps_mapper_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f32, _i64, _vp, _vp, _vp, _vp, _vp]),
     "hps_tracker_loss_stats": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "hps_peer_allreduce_ctas": (_i32, []),
+    "hps_peer_allreduce_pad_words": (_i64, []),
+    "hps_peer_allreduce": (_i32, [_vp, _vp, _vp, _i32, _i32, _i64, _vp]),
     "hps_tracker_loss": (_i32, [_vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _f32, _i64, _vp, _vp, _vp, _vp]),
 }
 

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhps_b200.so")
-SOURCES = ["capi.cu", "grid.cu", "interp.cu", "composite.cu", "mlp.cu", "sample.cu", "loss.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "tc_selftest.cu", "optim.cu"]
+SOURCES = ["capi.cu", "grid.cu", "interp.cu", "composite.cu", "mlp.cu", "sample.cu", "loss.cu", "mlp_tc.cu", "mlp_tc_bwd.cu", "tc_selftest.cu", "optim.cu", "peer.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default"]
 

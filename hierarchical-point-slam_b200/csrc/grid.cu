@@ -187,7 +187,10 @@ __global__ void grid_scatter_kernel(const float* __restrict__ pos, int64_t n, co
 // query
 // ------------------------------------------------------------------------------------------------
 constexpr int kQueryWarps = 8;     // warps (= queries in flight) per CTA
-constexpr int kStageCells = 256;   // voxel ranges staged in shared memory per pass and warp
+constexpr int kStageCells = 128;   // voxel ranges staged in shared memory per pass and warp (a ball's bounding cube is
+                                   // <= 5^3 = 125 voxels at the host layer's voxel edge; larger cubes take more passes).
+                                   // 13 KB per CTA: search CTAs fit beside a 185 KB weight-gradient CTA (the mapper
+                                   // iteration runs the next batch's search beside this batch's backward tail)
 
 struct GridView {
     const float4* sorted;
@@ -438,183 +441,6 @@ knn_query_kernel(GridView g, const float* __restrict__ q, const float* __restric
 }
 
 
-// ------------------------------------------------------------------------------------------------
-// query, second edition: kSubLanes lanes per query
-// ------------------------------------------------------------------------------------------------
-// The warp-per-query kernel above spends ~1,150 warp instructions per query, most of them on warp-wide bookkeeping
-// (prefix scans over the probed voxels, owner look-ups, two 64-bit bitonic sorts) for ~7 results; at a mapper batch
-// (25,000 queries) it is issue-bound (ncu r01o: 2.3 MB of DRAM traffic, 55 % issue efficiency).  Here a query is
-// answered by kSubLanes = 4 lanes (8 queries per warp): the voxels overlapping the ball's bounding cube are dealt out
-// round-robin to the lanes, a voxel whose box cannot reach the ball is skipped before its hash slot is read
-// (minimum point-to-box distance in voxel units, conservative slack; ~45 % of the cube's voxels), each lane walks the
-// points of its own voxels and keeps a private sorted top-8 of 64-bit (distance bits, index) keys in registers, and
-// the four lists are merged at the end by two bitonic top-8 merges over sub-warp shuffles.  No shared memory, no warp
-// collectives in the main loop.  Results are the same set in the same (D, index) order: the search is exact, and a
-// top-8 does not depend on the order the candidates arrive in.
-constexpr int kSubLanes = 4;
-constexpr int kSubThreads = 256;
-
-__device__ __forceinline__ void top8_insert(unsigned long long (&bk)[kK], unsigned long long key) {   // key < bk[7]
-    bk[kK - 1] = key;
-#pragma unroll
-    for (int t = kK - 1; t > 0; --t) {
-        const unsigned long long a = bk[t - 1], b = bk[t];
-        const bool sw = b < a;
-        bk[t - 1] = sw ? b : a;
-        bk[t] = sw ? a : b;
-    }
-}
-
-__device__ __forceinline__ unsigned long long shfl_xor_u64_m(unsigned m, unsigned long long v, int x) {
-    return ((unsigned long long)__shfl_xor_sync(m, (unsigned)(v >> 32), x) << 32) | __shfl_xor_sync(m, (unsigned)v, x);
-}
-
-template <bool RAYS>
-__global__ void __launch_bounds__(kSubThreads)
-knn_query_sub_kernel(GridView g, const float* __restrict__ q, const float* __restrict__ t_up,
-                     const float* __restrict__ t_dn, int64_t nq, int32_t* __restrict__ I, float* __restrict__ D,
-                     int32_t* __restrict__ count, int32_t* __restrict__ cand, const RaySource src,
-                     float* __restrict__ z_out, float* __restrict__ pts_out, float* __restrict__ tup_out,
-                     float* __restrict__ tdn_out) {
-    constexpr int L = kSubLanes;
-    const int lane = threadIdx.x & 31, sub = lane & (L - 1);
-    const int64_t qi = ((int64_t)blockIdx.x * kSubThreads + threadIdx.x) / L;
-    if (qi >= nq) return;                                   // whole groups leave together
-    const unsigned gmask = ((1u << L) - 1u) << (lane & ~(L - 1));
-
-    float qx, qy, qz, tdn, tup;
-    if constexpr (RAYS) {
-        const int64_t r = qi / src.S;
-        const SamplePoint sp = sample_point(src, r, (int)(qi - r * src.S));
-        qx = sp.x; qy = sp.y; qz = sp.zc; tdn = sp.t_dn; tup = sp.t_up;
-        if (sub == 0) {
-            z_out[qi] = sp.z;
-            pts_out[qi * 3 + 0] = sp.x;
-            pts_out[qi * 3 + 1] = sp.y;
-            pts_out[qi * 3 + 2] = sp.zc;
-            tup_out[qi] = sp.t_up;
-            tdn_out[qi] = sp.t_dn;
-        }
-    } else {
-        qx = __ldg(q + qi * 3 + 0);
-        qy = __ldg(q + qi * 3 + 1);
-        qz = __ldg(q + qi * 3 + 2);
-        tdn = __ldg(t_dn + qi);
-        tup = __ldg(t_up + qi);
-    }
-    unsigned long long bk[kK];
-#pragma unroll
-    for (int t = 0; t < kK; ++t) bk[t] = kNoKey;
-    int examined = 0;
-
-    if (tdn >= 0.f) {
-        const float ox = g.meta->origin[0], oy = g.meta->origin[1], oz = g.meta->origin[2];
-        // conservative search radius: sqrt(t_dn) plus slack that dominates every fp32 rounding involved
-        const float rr = sqrtf(tdn) * 1.00001f + 1e-6f * (fabsf(qx) + fabsf(qy) + fabsf(qz) + 1.0f);
-        const int x0 = max(cell_coord(qx - rr, ox, g.inv_cell), 0), x1 = min(cell_coord(qx + rr, ox, g.inv_cell), g.meta->maxc[0]);
-        const int y0 = max(cell_coord(qy - rr, oy, g.inv_cell), 0), y1 = min(cell_coord(qy + rr, oy, g.inv_cell), g.meta->maxc[1]);
-        const int z0 = max(cell_coord(qz - rr, oz, g.inv_cell), 0), z1 = min(cell_coord(qz + rr, oz, g.inv_cell), g.meta->maxc[2]);
-        const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
-        if (nx > 0 && ny > 0 && nz > 0) {
-            // the query in voxel units (the expression of cell_coord before the floor) and the ball's radius there,
-            // with slack for the rounding of both the query's and a stored point's voxel coordinate (<= 3 ulp each)
-            const float ux = __fmul_rn(__fsub_rn(qx, ox), g.inv_cell), uy = __fmul_rn(__fsub_rn(qy, oy), g.inv_cell),
-                        uz = __fmul_rn(__fsub_rn(qz, oz), g.inv_cell);
-            const float umax = fmaxf(fmaxf(fabsf(ux), fabsf(uy)), fabsf(uz)) + (float)max(max(nx, ny), nz);
-            const float ru = rr * g.inv_cell * 1.0001f + 2e-3f + 4e-6f * umax;
-            const float ru2 = ru * ru;
-            // D <= t_dn  <=>  key < (bits(t_dn) + 1) << 32
-            const unsigned long long thr = ((unsigned long long)__float_as_uint(tdn) + 1ull) << 32;
-            // my voxels: index sub, sub + L, ... of the cube in x-fastest order, tracked as (ix, iy, iz) offsets
-            int ix = sub % nx, t = sub / nx;
-            int iy = t % ny, iz = t / ny;
-            while (iz < nz) {
-                const int cx = x0 + ix, cy = y0 + iy, cz = z0 + iz;
-                // minimum distance from the query to the voxel's box [c, c+1)^3, in voxel units
-                const float dx = fmaxf(fmaxf((float)cx - ux, ux - (float)(cx + 1)), 0.f);
-                const float dy = fmaxf(fmaxf((float)cy - uy, uy - (float)(cy + 1)), 0.f);
-                const float dz = fmaxf(fmaxf((float)cz - uz, uz - (float)(cz + 1)), 0.f);
-                if (dx * dx + dy * dy + dz * dz <= ru2) {
-                    const unsigned long long key = cell_key(cx, cy, cz);
-                    unsigned h = hash_key(key) & g.mask;
-                    int st = 0, cnt = 0;
-                    while (true) {
-                        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(g.table + h));
-                        const unsigned long long ck = (unsigned long long)raw.x | ((unsigned long long)raw.y << 32);
-                        if (ck == key) {
-                            st = (int)raw.z;
-                            cnt = (int)raw.w;
-                            break;
-                        }
-                        if (ck == kEmptyKey) break;
-                        h = (h + 1) & g.mask;
-                    }
-                    examined += cnt;
-                    const float4* pp = g.sorted + st;
-                    for (int j = 0; j < cnt; ++j) {
-                        const float4 p = __ldg(pp + j);
-                        const float d = sqdist_rn(qx, qy, qz, p.x, p.y, p.z);
-                        const unsigned long long k64 = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(p.w);
-                        if (k64 < thr && k64 < bk[kK - 1]) top8_insert(bk, k64);
-                    }
-                }
-                ix += L;
-                while (ix >= nx) {
-                    ix -= nx;
-                    if (++iy == ny) {
-                        iy = 0;
-                        ++iz;
-                    }
-                }
-            }
-        }
-    }
-    // merge the group's L sorted lists: lower half of the bitonic merge (min(a[t], b[7-t]) holds the 8 smallest of
-    // both as a bitonic sequence), then a 3-stage bitonic sort; both partners end up with the same list
-#pragma unroll
-    for (int m = 1; m < L; m <<= 1) {
-        unsigned long long pk[kK];
-#pragma unroll
-        for (int t = 0; t < kK; ++t) pk[t] = shfl_xor_u64_m(gmask, bk[t], m);
-#pragma unroll
-        for (int t = 0; t < kK; ++t) bk[t] = bk[t] < pk[kK - 1 - t] ? bk[t] : pk[kK - 1 - t];
-#pragma unroll
-        for (int j = kK / 2; j > 0; j >>= 1) {
-#pragma unroll
-            for (int t = 0; t < kK; ++t) {
-                if ((t & j) == 0) {
-                    const unsigned long long a = bk[t], b = bk[t + j];
-                    const bool sw = b < a;
-                    bk[t] = sw ? b : a;
-                    bk[t + j] = sw ? a : b;
-                }
-            }
-        }
-        examined += __shfl_xor_sync(gmask, examined, m);
-    }
-    if (sub == 0) {
-        int oi[kK];
-        float od[kK];
-        int n_in = 0;
-#pragma unroll
-        for (int t = 0; t < kK; ++t) {
-            const bool used = bk[t] != kNoKey;
-            const float bD = __uint_as_float((unsigned)(bk[t] >> 32));
-            oi[t] = used ? (int)(unsigned)bk[t] : -1;
-            od[t] = used ? bD : FLT_MAX;
-            n_in += (used && bD < tup) ? 1 : 0;
-        }
-        int4* Iv = reinterpret_cast<int4*>(I + qi * kK);
-        float4* Dv = reinterpret_cast<float4*>(D + qi * kK);
-        Iv[0] = make_int4(oi[0], oi[1], oi[2], oi[3]);
-        Iv[1] = make_int4(oi[4], oi[5], oi[6], oi[7]);
-        Dv[0] = make_float4(od[0], od[1], od[2], od[3]);
-        Dv[1] = make_float4(od[4], od[5], od[6], od[7]);
-        count[qi] = n_in;
-        if (cand) cand[qi] = examined;
-    }
-}
-
 }  // namespace hps
 
 // ------------------------------------------------------------------------------------------------
@@ -729,7 +555,7 @@ extern "C" int hps_knn_query(const hps_grid_t* g, const float* q, const float* t
     using namespace hps;
     HPS_REQUIRE(g != nullptr && g->T > 0, "grid not built");
     HPS_REQUIRE(nq >= 0, "negative query count");
-    HPS_REQUIRE(group == 0 || group == 1 || group == 5, "group must be 0 (default), 1 or 5");
+    HPS_REQUIRE(group == 1 || group == 5, "group must be 1 or 5");
     if (nq == 0) return 0;
     HPS_REQUIRE(q && t_up && t_dn && I && D && count, "null buffer");
     GridView v;
@@ -739,11 +565,9 @@ extern "C" int hps_knn_query(const hps_grid_t* g, const float* q, const float* t
     v.mask = (unsigned)(g->T - 1);
     v.inv_cell = 1.0f / g->cell;
     const RaySource none{};
-    if (group == 0) {     // default: four lanes per query (second edition)
-        HPS_REQUIRE(((reinterpret_cast<uintptr_t>(I) | reinterpret_cast<uintptr_t>(D)) & 15) == 0, "I and D must be 16-byte aligned");
-        knn_query_sub_kernel<false><<<(unsigned)ceil_div(nq * kSubLanes, kSubThreads), kSubThreads, 0, (cudaStream_t)stream_>>>(
-            v, q, t_up, t_dn, nq, I, D, count, cand, none, nullptr, nullptr, nullptr, nullptr);
-    } else if (group == 5) {     // the samples of one ray share a sweep
+    HPS_SHARE_SM((knn_query_kernel<5, false>));
+    HPS_SHARE_SM((knn_query_kernel<1, false>));
+    if (group == 5) {     // the samples of one ray share a sweep
         knn_query_kernel<5, false><<<(unsigned)ceil_div(ceil_div(nq, 5), kQueryWarps), kQueryWarps * 32, 0, (cudaStream_t)stream_>>>(
             v, q, t_up, t_dn, nq, I, D, count, cand, none, nullptr, nullptr, nullptr, nullptr);
     } else {
@@ -772,8 +596,8 @@ extern "C" int hps_sample_knn(const hps_grid_t* g, const float* rays_o, const fl
     v.inv_cell = 1.0f / g->cell;
     const RaySource src{rays_o, rays_d, gt_depth, radius, radius_scalar, z_zero, z_zero_stride, S, near, far};
     const int64_t nq = R * S;
-    HPS_REQUIRE(((reinterpret_cast<uintptr_t>(I) | reinterpret_cast<uintptr_t>(D)) & 15) == 0, "I and D must be 16-byte aligned");
-    knn_query_sub_kernel<true><<<(unsigned)ceil_div(nq * kSubLanes, kSubThreads), kSubThreads, 0, (cudaStream_t)stream_>>>(
+    HPS_SHARE_SM((knn_query_kernel<1, true>));
+    knn_query_kernel<1, true><<<(unsigned)ceil_div(nq, kQueryWarps), kQueryWarps * 32, 0, (cudaStream_t)stream_>>>(
         v, nullptr, nullptr, nullptr, nq, I, D, count, cand, src, z, pts, t_up, t_dn);
     HPS_LAUNCH_OK();
     return 0;

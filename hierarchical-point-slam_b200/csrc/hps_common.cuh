@@ -39,6 +39,23 @@ void set_error(const char* fmt, ...);
         }                                                                                   \
     } while (0)
 
+// Shared-memory carve-out of kernels that are meant to run beside other kernels.  An SM is configured (L1 / shared
+// split) for the first CTA that lands on it and is not re-split while CTAs are resident; a CTA whose kernel wants another
+// split waits until the SM has drained.  Round 2 timelines: behind a kernel without shared memory (the gradient exchange,
+// the feature scatter) the neighbour search of the next batch (13 KB per CTA) started when that kernel ENDED, not beside
+// it; behind the 185 KB weight-gradient CTAs (split 196 KB by default) likewise.  Every kernel of the backward tail,
+// the exchange and the search therefore ask for the same split - the largest, 228 KB shared - once before their first
+// launch: HPS_SHARE_SM(kernel).
+#define HPS_SHARE_SM(kernel)                                                                                      \
+    do {                                                                                                          \
+        static bool _shared_sm_done = false;                                                                      \
+        if (!_shared_sm_done) {                                                                                   \
+            HPS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,              \
+                                             cudaSharedmemCarveoutMaxShared));                                    \
+            _shared_sm_done = true;                                                                               \
+        }                                                                                                         \
+    } while (0)
+
 constexpr int kK = HPS_K;   // neighbours per query
 constexpr int kC = HPS_C;   // feature channels
 constexpr unsigned kFull = 0xffffffffu;

@@ -229,6 +229,7 @@ extern "C" int hps_interp_bwd(const float* p, const int32_t* I, const float* w, 
     HPS_REQUIRE(dp == nullptr || (p && cloud_pos), "dp needs p and cloud_pos");
     HPS_REQUIRE(dp == nullptr || dc_a == nullptr || (feats_a && c_a), "dp needs feats_a and c_a");
     HPS_REQUIRE(dp == nullptr || dc_b == nullptr || (feats_b && c_b), "dp needs feats_b and c_b");
+    HPS_SHARE_SM(interp_bwd_kernel);
     interp_bwd_kernel<<<(unsigned)ceil_div(P, kInterpWarps), kInterpWarps * 32, 0, (cudaStream_t)stream>>>(
         p, I, w, has, cloud_pos, feats_a, feats_b, c_a, c_b, dc_a, dc_b, P, dfeats_a, dfeats_b, dp, row_map);
     HPS_LAUNCH_OK();

@@ -164,14 +164,17 @@ __global__ void pack_bwd_kernel(Ptrs prm, uint16_t* __restrict__ img) {
 
 // Gradient scaling.  Upstream gradients can be tiny (1e-7 .. 1e-3); fp16 hi/lo operands would lose their low half
 // to subnormals.  The whole backward therefore runs on S * gradient with S a power of two chosen so that
-// max|dout| lands in [128, 256) (exact, overflow-safe through the five layers), and un-scales on output.
+// max|dout| lands in [8, 16) (exact), and un-scales on output.  Headroom: the gradients may grow 4,000-fold through the
+// five layers before an fp16 high half overflows (round 1 used [128, 256): weights scaled by 4 - a 1,000-fold growth -
+// overflowed to NaN, tests/test_gpu_scale.py); at the other end an element 2^-17 of the largest one still has a normal
+// high half, and the low halves' subnormal floor (2^-25) is 4e-9 of the largest element.
 // The max is reduced on the device into the 4 bytes behind the packed weight image (zeroed by the pack kernel).
 __device__ __forceinline__ float grad_scale(const uint32_t* maxbits) {
     const float m = __uint_as_float(*maxbits);
     if (!(m > 0.f) || m > 3.0e38f) return 1.0f;
     int e;
     frexpf(m, &e);
-    e = 8 - e;
+    e = 4 - e;
     e = e < -100 ? -100 : (e > 100 ? 100 : e);
     return ldexpf(1.0f, e);
 }
@@ -995,6 +998,11 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
                                          GB::SMEM_BYTES));
         HPS_CUDA_OK(cudaFuncSetAttribute(mlp_wgrad_tc_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          GeoW<KIND>::SMEM_BYTES));
+        // The weight-gradient CTAs ask for 153 / 185 KB.  With the default carve-out the SM is configured for the next
+        // size up (164 / 196 KB) and nothing that needs shared memory fits beside them; with the largest carve-out
+        // (228 KB) the neighbour search of the next batch (13 KB per CTA) runs beside this HBM-bound kernel.
+        HPS_CUDA_OK(cudaFuncSetAttribute(mlp_wgrad_tc_kernel<KIND>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                         cudaSharedmemCarveoutMaxShared));
         configured = true;
     }
     const int num_tiles = (int)ceil_div(P, TILE);
@@ -1028,6 +1036,7 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
         mlp_wgrad_tc_kernel<KIND><<<wgrid, GeoW<KIND>::NTHRW, GeoW<KIND>::SMEM_BYTES, w>>>(
             grd, reinterpret_cast<const uint8_t*>(ws), num_tiles, maxbits, scratch, split_roles<KIND>(wgrid));
         const int nout = 5 * (Cfg<KIND>::H * 32 + Cfg<KIND>::H);
+        HPS_SHARE_SM(mlp_wfinal_kernel<KIND>);
         mlp_wfinal_kernel<KIND><<<(WFINAL_PARTS * nout + 127) / 128, 128, 0, w>>>(prm, grd, scratch);
     }
     return 0;

@@ -59,6 +59,7 @@ extern "C" int hps_sample_rays(const float* rays_o, const float* rays_d, const f
     if (R == 0) return 0;
     HPS_REQUIRE(rays_o && rays_d && gt_depth && z && pts && t_up && t_dn, "null buffer");
     const RaySource src{rays_o, rays_d, gt_depth, radius, radius_scalar, z_zero, z_zero_stride, S, near, far};
+    HPS_SHARE_SM(sample_rays_kernel);
     sample_rays_kernel<<<(unsigned)ceil_div(R * S, 256), 256, 0, (cudaStream_t)stream>>>(src, R, z, pts, t_up, t_dn);
     HPS_LAUNCH_OK();
     return 0;

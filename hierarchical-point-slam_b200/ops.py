@@ -29,11 +29,11 @@ MULTI_STREAM = os.environ.get("HPS_STREAMS", "1") != "0"
 _side_streams = {}
 
 
-def _side_stream(dev, which=0):
-    key = (torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device(), which)
+def _side_stream(dev, which=0, priority=0):
+    key = (torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device(), which, priority)
     s = _side_streams.get(key)
     if s is None:
-        s = torch.cuda.Stream(device=dev)
+        s = torch.cuda.Stream(device=dev, priority=priority)
         _side_streams[key] = s
     return s
 
@@ -45,9 +45,18 @@ _KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_sample_knn": 
                      "hps_mlp_tc_bwd_pack": 2, "hps_mlp_tc_bwd": 3, "hps_tc_selftest": 1, "hps_composite_fwd": 1,
                      "hps_composite_bwd": 1, "hps_composite_mapper_loss": 1, "hps_sample_rays": 1, "hps_sample_rays_bwd": 1, "hps_mapper_loss": 1,
                      "hps_tracker_loss_stats": 1, "hps_tracker_loss": 1, "hps_exposure_fwd": 1, "hps_exposure_bwd": 1, "hps_camera_from_tensor": 1, "hps_adam_rows": 1, "hps_adam_multi": 1,
-                     "hps_camera_from_tensor_bwd": 1, "hps_rays_from_uv": 1, "hps_rays_from_uv_bwd": 1}
+                     "hps_camera_from_tensor_bwd": 1, "hps_rays_from_uv": 1, "hps_rays_from_uv_bwd": 1, "hps_peer_allreduce": 1}
 TIMERS = None   # set to {} to record (start, end) CUDA events per call name on the current stream
 
+
+# Scheduling of RenderSpec.tail_work (see _RenderRays._backward): stream priority and launch position.  Defaults from
+# scripts/tail_experiment.py on the B200 (round 2, mean of 60 flushed replays of the bench iteration): tail work at normal
+# priority in front of the feature scatter as ONE launch, weight-gradient streams at high priority: 0.2670 ms against
+# 0.2751 ms without any overlap; the other fifteen combinations lie between 0.2697 and 0.2806 ms.
+TAIL_PRIORITY = int(os.environ.get("HPS_TAIL_PRIORITY", "0"))
+TAIL_AFTER_SCATTER = os.environ.get("HPS_TAIL_AFTER_SCATTER", "0") != "0"
+WGRAD_PRIORITY = int(os.environ.get("HPS_WGRAD_PRIORITY", "-2"))
+SCATTER_PRIORITY = int(os.environ.get("HPS_SCATTER_PRIORITY", "-1"))
 
 # NVTX ranges: HPS_NVTX=1 wraps every C-ABI call in a range named after the entry point (decoder
 # calls carry the decoder kind) and the fused render's forward / backward in "hps.render_rays.fwd/bwd"; nsys / ncu
@@ -108,9 +117,21 @@ class _ZeroPool:
     def want_like(self, tensors, skip_first):
         return [None if (skip_first and i == 0) else self.want(t.shape) for i, t in enumerate(tensors)]
 
-    def alloc(self, stream=None):
+    def alloc(self, stream=None, into=None):
         """stream: issue the memset there (the caller orders it: that stream must already wait for the work that last
-        touched the allocator's block, and the consumers must wait for that stream)."""
+        touched the allocator's block, and the consumers must wait for that stream).  into: a GradPool whose tensor
+        provides the memory (e.g. a symmetric buffer the gradient exchange reduces in place) instead of the allocator."""
+        if into is not None:
+            if into.tensor.numel() < self.total or into.tensor.dtype != torch.float32 or not into.tensor.is_contiguous():
+                raise _lib.HpsError("grad_buffer: need %d contiguous fp32 elements, got %d" % (self.total, into.tensor.numel()))
+            self.flat = into.tensor[:max(self.total, 1)]
+            into.used = self.total
+            if stream is None:
+                self.flat.zero_()
+            else:
+                with torch.cuda.stream(stream):
+                    self.flat.zero_()
+            return self
         if stream is None:
             self.flat = torch.zeros(max(self.total, 1), dtype=torch.float32, device=self.device)
         else:
@@ -126,6 +147,16 @@ class _ZeroPool:
             return [self.get(x) for x in h]
         off, n, shape = self.reqs[h]
         return self.flat[off:off + n].view(shape)
+
+
+class GradPool:
+    """Caller-owned memory for the gradients of one fused backward (RenderSpec.grad_buffer): `tensor` is a contiguous
+    fp32 buffer, `used` the number of leading floats the last backward laid its gradients out in (every .grad of that
+    backward is a view of tensor[:used]).  With a symmetric-memory tensor (parallel.PeerAllReduce.buffer) the multi-GPU
+    exchange sums the gradients where backward wrote them."""
+
+    def __init__(self, tensor):
+        self.tensor, self.used = tensor, 0
 
 
 def _zero_grads_like(tensors, skip_first):
@@ -198,11 +229,10 @@ class VoxelHashGrid:
         return dict(n_points=n.value, table_size=T.value, n_cells=nc.value, cell_size=cell.value, status=st.value)
 
     def query(self, q, t_up, t_dn, want_cand=False, group=None):
-        """q (Q,3) -> I (Q,8) int32, D (Q,8) f32, count (Q,) int32 [, cand (Q,) int32].  group: which edition of the
-        search kernel answers - None / 0: four lanes per query (default); 1: one warp per query; 5: one warp per five
-        consecutive queries (the samples of a ray) sharing one sweep.  The result is the same."""
-        if group is None:
-            group = 0 if KNN_IMPL == "sub" else 1
+        """q (Q,3) -> I (Q,8) int32, D (Q,8) f32, count (Q,) int32 [, cand (Q,) int32].  group=5: consecutive
+        queries in fives (the samples of a ray) share one sweep over the bounding box of their five balls - only for
+        queries that are that close; the result is the same."""
+        group = group or 1
         _need_cuda(q, t_up, t_dn)
         q = _f32c(q).reshape(-1, 3)
         Q = q.shape[0]
@@ -333,9 +363,6 @@ def _new_bwd_images(kind, dev):
 
 
 N_SM = 148
-# Edition of the neighbour-search kernel: "sub" = four lanes per query with a voxel-vs-ball cull (csrc/grid.cu, second
-# edition; default), "warp" = the first edition (one warp per query, ray-grouped from KNN_GROUP_MIN_QUERIES on).
-KNN_IMPL = os.environ.get("HPS_KNN_IMPL", "sub")
 # Ray-grouped neighbour search (one warp answers the 5 samples of a ray) trades parallelism for shared probes and
 # loads: measured on the bench cloud (scripts/knn_group_bench.py) 55 vs 47 us at 25,000 queries (too few warps to
 # hide latency), 143 vs 152 us at 100,000, 269 vs 292 us at 200,000.
@@ -633,8 +660,10 @@ def prepare_rays(grid, rays_o, rays_d, gt_depth, radius, S, near, far, z_zero=No
         pr.D = torch.empty(P, K_NN, **f32)
         pr.cnt = torch.empty(P, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev):
+        # one launch (the search computes its query points itself) below the ray-grouped size: a prepared head is
+        # typically issued beside other work, where a second launch waits for thread slots a second time
         _sample_and_search(grid, ro, rd, gd, rad_t, radius, zz, R, S, near, far, pr.z, pr.pts, pr.t_up, pr.t_dn, pr.I,
-                           pr.D, pr.cnt, _stream())
+                           pr.D, pr.cnt, _stream(), fused=PREPARE_FUSED)
     return pr
 
 
@@ -643,18 +672,17 @@ def prepare_rays(grid, rays_o, rays_d, gt_depth, radius, S, near, far, z_zero=No
 SAMPLE_IN_SEARCH = os.environ.get("HPS_SAMPLE_IN_SEARCH", "0") != "0"
 
 
-def _sample_and_search(grid, ro, rd, gd, rad_t, rad, zz, R, S, near, far, z, pts, t_up, t_dn, I, D, cnt, stream):
+PREPARE_FUSED = os.environ.get("HPS_PREPARE_FUSED", "1") != "0"
+
+
+def _sample_and_search(grid, ro, rd, gd, rad_t, rad, zz, R, S, near, far, z, pts, t_up, t_dn, I, D, cnt, stream, fused=None):
     """Sample points + thresholds + exact neighbour search: the sampling kernel, then the search (ray-grouped from
     KNN_GROUP_MIN_QUERIES queries on); with SAMPLE_IN_SEARCH one launch (the search computes its query points itself)."""
     P = R * S
     scalar = 0.0 if rad_t is not None else float(rad)
-    if KNN_IMPL == "sub" and not SAMPLE_IN_SEARCH:
-        _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t), scalar, _lib.ptr(zz),
-              _z_zero_stride(zz, R, S), R, S, float(near), float(far), _lib.ptr(z), _lib.ptr(pts), _lib.ptr(t_up),
-              _lib.ptr(t_dn), stream)
-        _call("hps_knn_query", grid._h, _lib.ptr(pts), _lib.ptr(t_up), _lib.ptr(t_dn), P, _lib.ptr(I), _lib.ptr(D),
-              _lib.ptr(cnt), None, 0, stream)
-    elif (S == 5 and P >= KNN_GROUP_MIN_QUERIES and KNN_IMPL != "sub") or not SAMPLE_IN_SEARCH:
+    if fused is None:
+        fused = SAMPLE_IN_SEARCH
+    if (S == 5 and P >= KNN_GROUP_MIN_QUERIES) or not fused:
         _call("hps_sample_rays", _lib.ptr(ro), _lib.ptr(rd), _lib.ptr(gd), _lib.ptr(rad_t), scalar, _lib.ptr(zz),
               _z_zero_stride(zz, R, S), R, S, float(near), float(far), _lib.ptr(z), _lib.ptr(pts), _lib.ptr(t_up),
               _lib.ptr(t_dn), stream)
@@ -670,21 +698,28 @@ class RenderSpec:
     """Non-tensor arguments of render_rays (one per call)."""
     __slots__ = ("grid", "radius", "z_zero", "S", "near", "far", "coef", "min_nn", "min_valid", "color_stage",
                  "tracker", "cloud_pos", "fill_geo", "fill_col", "live_geo", "live_col", "prep", "loss", "aff_mlp",
-                 "tail_work")
+                 "tail_work", "grad_buffer", "after_grads")
 
     def __init__(self, **kw):
         for k in self.__slots__:
             setattr(self, k, kw.get(k))
 
 
-def _exposure_backward(eprm, a1, dout, gscale, e_need, x_shape, stream):
+def _exposure_grad_floats(eprm):
+    hidden, n_in = eprm[1].shape
+    return sum((n + 3) // 4 * 4 for n in (hidden * n_in, hidden, 12 * hidden, 12, n_in))
+
+
+def _exposure_backward(eprm, a1, dout, gscale, e_need, x_shape, stream, buf=None):
     """d/d(latent, W1, b1, W2, b2) of the exposure MLP from d/d affine (12 floats, times the device scalar `gscale`
-    when given): one kernel on `stream`, one allocation.  e_need: which of the five gradients are wanted."""
+    when given): one kernel on `stream`, one allocation (or `buf`: _exposure_grad_floats(eprm) floats, fully
+    overwritten).  e_need: which of the five gradients are wanted."""
     if not any(e_need):
         return (None,) * 5
     hidden, n_in = eprm[1].shape
     sizes = [hidden * n_in, hidden, 12 * hidden, 12, n_in]
-    buf = torch.empty(sum((n + 3) // 4 * 4 for n in sizes), dtype=torch.float32, device=a1.device)
+    if buf is None:
+        buf = torch.empty(sum((n + 3) // 4 * 4 for n in sizes), dtype=torch.float32, device=a1.device)
     parts, off = [], 0
     for n in sizes:
         parts.append(buf[off:off + n])
@@ -874,8 +909,6 @@ class _RenderRays(torch.autograd.Function):
                     aff_head(side)
                 packed_col = side.record_event()
                 _mlp_pack(MLP_GEO, garr, dev, side)
-                if lm is not None:
-                    loss_head(side)
                 aux = None
                 if bpk_c is not None:      # backward images on a third stream: nothing in the forward waits for them
                     aux = _side_stream(dev, 1)
@@ -902,6 +935,8 @@ class _RenderRays(torch.autograd.Function):
                                     max_ctas=n_c)
                 sv_g = _mlp_forward(MLP_GEO, garr, pts, c_geo, None, P, occ, need_grad, dev, side, ws_g, packed=True,
                                     max_ctas=n_g)
+                if lm is not None:      # behind the geometry decoder, not in front of it: that kernel is on the critical
+                    loss_head(side)     # path, the loss's accumulators and exposure affine are needed after the join
                 main.wait_stream(side)
                 if aux is not None:
                     main.wait_stream(aux)
@@ -997,15 +1032,22 @@ class _RenderRays(torch.autograd.Function):
         h_dfg = zp.want((n_rows, C_DIM)) if need[4] else None
         h_dfc = zp.want((n_rows, C_DIM)) if (spec.color_stage and need[5]) else None
         tc_dp = need_p and ctx.saved_kinds[0] == "tc"
+        # the exposure MLP's gradients (loss-side or decoder-side) come out of the same allocation, so that a caller-owned
+        # grad_buffer holds EVERY gradient of the iteration (one exchange, nothing left outside)
+        h_exp = None
+        if ctx.loss_state is not None and l_eprm and any(need[7 + len(gprm) + len(cprm):]):
+            h_exp = zp.want((_exposure_grad_floats(l_eprm),))
+        elif ctx.aff_mlp_state is not None and any(m_need):
+            h_exp = zp.want((_exposure_grad_floats(ctx.aff_mlp_state[0]),))
         h_dpg = zp.want((P, 3)) if tc_dp else None                          # accumulated by the dgrad kernels
         h_dpc = zp.want((P, 3)) if (tc_dp and spec.color_stage) else None
         with torch.cuda.device(dev):
             if fork:        # the memset runs beside the compositing backward instead of in front of it
                 main, side = torch.cuda.current_stream(dev), _side_stream(dev)
                 side.wait_stream(main)
-                zp.alloc(side)
+                zp.alloc(side, into=spec.grad_buffer)
             else:
-                zp.alloc()
+                zp.alloc(into=spec.grad_buffer)
         dg, dcw, daff = zp.get(h_dg), zp.get(h_dcw), zp.get(h_daff)
         dfg, dfc = zp.get(h_dfg), zp.get(h_dfc)
         dp_i = torch.empty(P, 3, **f32) if need_p else None
@@ -1027,8 +1069,11 @@ class _RenderRays(torch.autograd.Function):
                 n_c, n_g = _sm_split(P, "bwd")
                 # the HBM-bound weight-gradient kernels go to streams of their own: the feature scatter below needs
                 # only dc of both decoders and overlaps with them
-                w_c = _side_stream(dev, 1) if dcw is not None else None     # (no weight gradients: nothing to fork)
-                w_g = _side_stream(dev, 2) if dg is not None else None
+                # (highest priority: the two weight-gradient kernels are the critical path of the tail - the second can only
+                # be placed once the first has left the SMs (shared memory) - and must not queue behind the scatter's or the
+                # tail work's CTAs for shared memory and thread slots)
+                w_c = _side_stream(dev, 5, priority=WGRAD_PRIORITY) if dcw is not None else None     # (no weight gradients: nothing to fork)
+                w_g = _side_stream(dev, 2, priority=WGRAD_PRIORITY) if dg is not None else None
                 _mlp_backward(MLP_COL, cprm, "tc", act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c, need_p, daff, dev, main,
                               dp_c, packed=ctx.bwd_packed[1], absmax_done=folded, max_ctas=n_c, wgrad_stream=w_c)
                 e_s = None
@@ -1036,7 +1081,7 @@ class _RenderRays(torch.autograd.Function):
                     e_s = _side_stream(dev, 3)                                      # the feature scatter
                     e_s.wait_stream(main)
                     g_aff_mlp = _exposure_backward(ctx.aff_mlp_state[0], ctx.aff_mlp_state[1], daff, None, m_need,
-                                                   ctx.aff_x_shape, e_s)
+                                                   ctx.aff_x_shape, e_s, zp.get(h_exp))
                 _mlp_backward(MLP_GEO, gprm, "tc", act_g, pts, c_geo, None, d_occ, P, dg, dc_g, need_p, None, dev, side,
                               dp_g, packed=ctx.bwd_packed[0], absmax_done=folded, max_ctas=n_g, wgrad_stream=w_g)
                 main.wait_stream(side)
@@ -1050,24 +1095,42 @@ class _RenderRays(torch.autograd.Function):
                 e_s = None
                 if any(m_need):
                     g_aff_mlp = _exposure_backward(ctx.aff_mlp_state[0], ctx.aff_mlp_state[1], daff, None, m_need,
-                                                   ctx.aff_x_shape, None)
+                                                   ctx.aff_x_shape, None, zp.get(h_exp))
             t_s = None
-            if spec.tail_work is not None:
+            if spec.tail_work is not None and not TAIL_AFTER_SCATTER:
                 # Work the caller wants issued beside the backward's HBM-bound tail (weight-gradient streams + feature
                 # scatter), typically the parameter-free head of the NEXT iteration (Renderer.prepare_batch: sampling +
                 # neighbour search, issue-bound and L2-resident; its CTAs fit beside the weight-gradient CTAs).  It starts
                 # once both decoders' data gradients are done and joins the main stream before backward returns.
                 if fork:
-                    t_s = _side_stream(dev, 4)
+                    t_s = _side_stream(dev, 4, priority=TAIL_PRIORITY)
                     t_s.wait_stream(main)
                     with torch.cuda.stream(t_s):
                         spec.tail_work()
                 else:
                     spec.tail_work()
             if dfg is not None or dfc is not None or need_p:
+                # Beside tail work the scatter goes to a stream of higher priority than the tail's: it PRODUCES gradients
+                # (the multi-GPU exchange waits for it), the tail work is only needed by the next iteration - at equal
+                # priority the tail's grid, launched first, is placed first and the scatter finished last (round 2).
+                # (only with an exchange hook: on one GPU nothing waits for the scatter and the plain order is 4 % faster)
+                sc_s = _side_stream(dev, 6, priority=SCATTER_PRIORITY) \
+                    if (fork and t_s is not None and spec.after_grads is not None) else None
+                if sc_s is not None:
+                    sc_s.wait_stream(main)
                 _call("hps_interp_bwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(w), _lib.ptr(has), _lib.ptr(pos),
                       _lib.ptr(fg), _lib.ptr(fc), _lib.ptr(c_geo), _lib.ptr(c_col), _lib.ptr(dc_g), _lib.ptr(dc_c), P,
-                      _lib.ptr(dfg), _lib.ptr(dfc), _lib.ptr(dp_i), _lib.ptr(ctx.row_map), st())
+                      _lib.ptr(dfg), _lib.ptr(dfc), _lib.ptr(dp_i), _lib.ptr(ctx.row_map), st(sc_s))
+                if sc_s is not None:
+                    main.wait_stream(sc_s)
+            if spec.tail_work is not None and TAIL_AFTER_SCATTER:
+                if fork:
+                    t_s = _side_stream(dev, 4, priority=TAIL_PRIORITY)
+                    t_s.wait_stream(w_c if w_c is not None else main)      # (experiment: behind the colour weight gradients)
+                    with torch.cuda.stream(t_s):
+                        spec.tail_work()
+                else:
+                    spec.tail_work()
             g_ro = g_rd = None
             if need_p:
                 g_ro, g_rd = torch.empty(R, 3, **f32), torch.empty(R, 3, **f32)
@@ -1081,13 +1144,18 @@ class _RenderRays(torch.autograd.Function):
                 # exposure MLP backward from d loss / d affine (accumulated by the fused loss kernel); the main stream
                 # has slack here - the weight-gradient kernels on their own streams finish later
                 g_exp = _exposure_backward(l_eprm, l_a1, l_flat[4:], gscale, need[7 + len(gprm) + len(cprm):],
-                                           ctx.exp_x_shape, None)
+                                           ctx.exp_x_shape, None, zp.get(h_exp))
             if ctx.aff_mlp_state is not None:
                 g_exp = g_aff_mlp if any(m_need) else (None,) * 5
                 if e_s is not None:
                     main.wait_stream(e_s)
             for w_s in wgrad_streams:
                 main.wait_stream(w_s)
+            if spec.after_grads is not None:
+                # Every gradient of this backward is complete on the main stream here, while tail_work may still be
+                # running on its own: the caller's hook - the multi-GPU exchange over grad_buffer - is issued in front of
+                # the join, so that the exchange's latency hides behind the next batch's neighbour search.
+                spec.after_grads()
             if t_s is not None:
                 main.wait_stream(t_s)
         gg = [(g if (g is not None and need[7 + i]) else None) for i, g in enumerate(dg)] if dg else [None] * N_PARAM

@@ -4,6 +4,8 @@ NVLink on the GPU box, gloo in the CPU tests) makes every rank apply the identic
 
 The reference has no distributed code at all; this is the data-parallel form of Mapper.py:783-860.
 """
+import ctypes
+
 import torch
 
 
@@ -136,3 +138,113 @@ def render_img_sharded(renderer, dist, *args, group=None, gather=True, **kwargs)
         parts.append(full[r * rows:r * rows + (h - l)])
     full = torch.cat(parts, 0)
     return full[..., 0].contiguous(), full[..., 1].contiguous(), full[..., 2:].to(color.dtype).contiguous()
+
+
+class PeerAllReduce:
+    """In-place sum of a symmetric fp32 buffer over the ranks of one box by ONE kernel of this package
+    (csrc/peer.cu: barrier, reduce by slice owner over NVLink peer loads or one NVLS multimem.ld_reduce per vector,
+    broadcast, barrier) instead of a library collective.  PyTorch is plumbing here: torch.distributed._symmetric_memory
+    allocates the buffer and the signal pad, exchanges the handles and maps the peers' copies (and the multicast
+    address when the fabric has NVLS); no kernel of it runs.
+
+        ex = PeerAllReduce(n_floats, device, dist)     # collective: every rank constructs it
+        ex.buffer                                      # this rank's copy: write gradients here (RenderSpec.grad_buffer)
+        ex()                                           # every rank: sum in place, on the current stream, graph-capturable
+
+    Raises if symmetric memory cannot be set up (no peer access): callers fall back to GradExchange (NCCL)."""
+
+    def __init__(self, n_floats, device, dist, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self._lib = _lib
+        self.dist = dist
+        group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise _lib.HpsError("PeerAllReduce: at most 8 ranks (one NVSwitch box)")
+        self.n = (int(n_floats) + 3) // 4 * 4
+        lib = _lib.load()
+        pad_words = int(lib.hps_peer_allreduce_pad_words())
+        self.buffer = symm_mem.empty(self.n, dtype=torch.float32, device=device)
+        self._pad = symm_mem.empty(pad_words, dtype=torch.int32, device=device)
+        self._pad.zero_()
+        self.buffer.zero_()
+        torch.cuda.synchronize(device)
+        hb = symm_mem.rendezvous(self.buffer, group.group_name)
+        hp = symm_mem.rendezvous(self._pad, group.group_name)
+        self._handles = (hb, hp)
+        self._bufs = (ctypes.c_void_p * self.world)(*[int(p) for p in hb.buffer_ptrs])
+        self._pads = (ctypes.c_void_p * self.world)(*[int(p) for p in hp.buffer_ptrs])
+        self.multicast_ptr = int(getattr(hb, "multicast_ptr", 0) or 0)
+        dist.barrier(group)                 # every pad is zeroed before anybody raises a flag
+
+    def variants(self):
+        return ["p2p"] + (["multimem"] if self.multicast_ptr else [])
+
+    def default_variant(self):
+        """Measured on the B200 box (3.4 MB): with two ranks the P2P form is faster (33 vs 38 us: one remote load per
+        vector either way, and no switch reduction to pay for); from four ranks on one multimem.ld_reduce replaces W - 1
+        remote loads."""
+        return "multimem" if (self.multicast_ptr and self.world > 2) else "p2p"
+
+    def check(self):
+        """Host-side check (synchronises): raises if any exchange so far gave up waiting for a peer."""
+        lib = self._lib.load()
+        st = int(self._pad[int(lib.hps_peer_allreduce_ctas()) * 8].item())
+        if st:
+            raise self._lib.HpsError("PeerAllReduce: a peer did not arrive within 2 s (status %d); the sums are invalid" % st)
+
+    def __call__(self, variant=None, n_floats=None):
+        """Sum the first n_floats (default: all) of every rank's buffer in place.  variant: "multimem" (NVLS; the
+        default when the buffer has a multicast address) or "p2p"."""
+        from .ops import _call, _stream
+        if variant is None:
+            variant = self.default_variant()
+        n = self.n if n_floats is None else (int(n_floats) + 3) // 4 * 4
+        if n > self.n:
+            raise self._lib.HpsError("PeerAllReduce: %d floats asked, the buffer holds %d" % (n, self.n))
+        mc = ctypes.c_void_p(self.multicast_ptr) if variant == "multimem" else None
+        if variant == "multimem" and not self.multicast_ptr:
+            raise self._lib.HpsError("PeerAllReduce: no multicast address (NVLS) on this fabric")
+        with torch.cuda.device(self.buffer.device):
+            _call("hps_peer_allreduce", self._bufs, self._pads, mc, self.rank, self.world, n, _stream())
+
+
+class PeerGradExchange:
+    """The mapper's gradient exchange with nothing but this package's kernel on the wire: the fused backward lays every
+    gradient of the iteration out in `pool` (an ops.GradPool over a symmetric buffer - pass it as grad_buffer to
+    Renderer.render_batch_ray_loss) and `exchange()` sums the used prefix over the ranks in place (PeerAllReduce).  A
+    plain kernel launch: it can sit inside the iteration's CUDA graph.  capacity_floats: an upper bound of what one
+    backward needs (live rows x 32 x tables + decoder parameters + padding); every rank must run the same code path."""
+
+    def __init__(self, capacity_floats, device, dist, group=None):
+        from .ops import GradPool
+        self.peer = PeerAllReduce(capacity_floats, device, dist, group)
+        self.pool = GradPool(self.peer.buffer)
+        # The exchange kernel spends its time waiting for peers, and its 192 small CTAs must not queue behind the grid of
+        # whatever runs beside it (the next batch's neighbour search: 3,125 CTAs at the same priority pushed the
+        # exchange to the end of the step, round 2 measurement): its own stream, highest priority.
+        self.stream = torch.cuda.Stream(device=device, priority=-5)
+        self.side = torch.cuda.Stream(device=device)
+
+    def __call__(self, variant=None, beside=None):
+        """Issued from the current stream: the exchange waits for it, runs on the high-priority stream, and the current
+        stream waits for the exchange.  beside: a callable issued on a second stream at the same time - work that needs
+        neither the gradients nor the parameters, i.e. the next batch's Renderer.prepare_batch (sampling + neighbour
+        search): the exchange is latency-bound (~35 us of cross-GPU barriers for 3.4 MB), the search issue-bound, so the
+        two share the GPU well; the exchange is launched first so that its 192 CTAs are placed before the search's grid."""
+        cur = torch.cuda.current_stream(self.peer.buffer.device)
+        if self.pool.used:
+            self.stream.wait_stream(cur)
+            with torch.cuda.stream(self.stream):
+                self.peer(variant, n_floats=self.pool.used)
+        if beside is not None:
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                beside()
+            cur.wait_stream(self.side)
+        if self.pool.used:
+            cur.wait_stream(self.stream)
+
+    def check(self):
+        self.peer.check()

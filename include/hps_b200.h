@@ -54,10 +54,8 @@ int hps_grid_info(const hps_grid_t* g, int64_t* n_points, int64_t* table_size, i
  *   D[nq][8]   fl(fl(dx*dx+dy*dy)+dz*dz) fp32 without FMA; unused slots FLT_MAX
  *   count[nq]  number of slots with D < t_up   (== reference neighbor_num)
  *   cand[nq]   optional (may be NULL): candidates examined for the query's group (for the roofline figure)
- *   group      which edition of the kernel answers (results are independent of it): 0 = four lanes per query, voxels
- *              that cannot reach the query ball culled before their hash slot is read (default of the host layer; I
- *              and D must be 16-byte aligned); 1 = one warp per query; 5 = consecutive queries [5g, 5g+5) - the
- *              samples of one ray - are answered by one warp that shares the voxel probes and candidate loads
+ *   group      1, or 5: consecutive queries [5g, 5g+5) - the samples of one ray - are answered by one warp that
+ *              shares the voxel probes and candidate loads among them (results are independent of `group`)
  * Slots j < count are bit-identical to the reference's exhaustive search.                           */
 int hps_knn_query(const hps_grid_t* g, const float* q, const float* t_up, const float* t_dn,
                   int64_t nq, int32_t* I, float* D, int32_t* count, int32_t* cand, int group, void* stream);
@@ -274,6 +272,25 @@ int hps_tracker_loss_stats(const float* depth, const float* var, const float* gt
 int hps_tracker_loss(const float* depth, const float* var, const float* color, const float* gt_depth,
                      const float* gt_color, const float* sum_tmp, double count, float w_color, int64_t R,
                      float* loss, float* g_depth, float* g_color, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Gradient exchange over NVLink peer memory (the data-parallel form of Mapper.py:783-860: the ray batch is
+ * sharded over the GPUs of one box, point-feature and decoder gradients are summed over the ranks).  One kernel:
+ * cross-rank barrier, reduce-scatter by slice owner (P2P vector loads, or ONE multimem.ld_reduce per vector when the
+ * buffer has an NVLS multicast address), broadcast of the sums into every rank's copy (P2P stores / multimem.st),
+ * barrier.  In place; every rank ends up with bit-identical sums; capturable in a CUDA graph (binary-semaphore flags).
+ *   bufs[world]   HOST array of device pointers: rank p's copy of the symmetric buffer as mapped into THIS process
+ *   pads[world]   HOST array of device pointers: rank p's signal pad (hps_peer_allreduce_pad_words() uint32, zeroed
+ *                 once before the first call, never touched by anything else)
+ *   multicast     the buffer's multicast address, or NULL (P2P loads / stores)
+ *   n_floats      multiple of 4; every rank passes the same value
+ * Every rank of the group must call it once per exchange, the same number of times (the flags are launch counters): it
+ * waits for its peers' flags for at most two seconds - then it gives up and sets pad[ctas * 8] (this rank's pad, bit 1),
+ * and the buffer's contents are undefined.                                                                           */
+int hps_peer_allreduce_ctas(void);
+int64_t hps_peer_allreduce_pad_words(void);
+int hps_peer_allreduce(float* const* bufs, uint32_t* const* pads, float* multicast, int rank, int world,
+                       int64_t n_floats, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,5 +1,5 @@
-"""kNN query time of the three kernel editions - four lanes per query (group=0, default), one warp per query (group=1),
-one warp per ray (group=5) - over the query count, fine and mid level, with mean candidates examined (GPU box)."""
+"""kNN query time, one warp per query (group=1) vs one warp per ray (group=5), over the query count, fine and mid level,
+with mean candidates examined (GPU box)."""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -21,7 +21,7 @@ for R in (1000, 5000, 20000, 40000, 307200):
     q = (ro[:, None] + rd[:, None] * z[..., None]).reshape(-1, 3).contiguous()
     t_up, t_dn = hps.ops.radius_thresholds(rad.repeat_interleave(5), q.shape[0], dev)
     grid = idx._ensure_grid(t_dn)
-    for group in (0, 1, 5):
+    for group in (1, 5):
         for _ in range(3):
             grid.query(q, t_up, t_dn, group=group)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -44,7 +44,7 @@ z = gd[:, None] * torch.linspace(0.96, 1.04, 5, device=dev)[None]
 q = (ro[:, None] + rd[:, None] * z[..., None]).reshape(-1, 3).contiguous()
 t_up, t_dn = hps.ops.radius_thresholds(scene["radius_mid"][:R].to(dev).repeat_interleave(5), q.shape[0], dev)
 grid = idx._ensure_grid(None)
-for group in (0, 1, 5):
+for group in (1, 5):
     for _ in range(3):
         grid.query(q, t_up, t_dn, group=group)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

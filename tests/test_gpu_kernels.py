@@ -374,15 +374,9 @@ def test_knn_ray_grouped_sweep_equals_per_query(hps, Q):
     grid = idx._ensure_grid(t_dn)
     a = grid.query(q.to(DEV), t_up, t_dn, group=1)
     b = grid.query(q.to(DEV), t_up, t_dn, group=5)
-    c = grid.query(q.to(DEV), t_up, t_dn, group=0)            # four lanes per query + voxel-vs-ball cull (the default)
-    for x, y, w, name in zip(a, b, c, ("I", "D", "count")):
+    for x, y, name in zip(a, b, ("I", "D", "count")):
         assert torch.equal(x, y), name
-        assert torch.equal(x, w), name + " (sub-warp edition)"
     assert int(a[2].max()) > 0
-    # the cull only ever skips voxels that cannot hold an in-radius point: fewer candidates examined, same result
-    ca = grid.query(q.to(DEV), t_up, t_dn, want_cand=True, group=1)[3]
-    cc = grid.query(q.to(DEV), t_up, t_dn, want_cand=True, group=0)[3]
-    assert bool((cc <= ca).all()) and int(cc.sum()) < int(ca.sum())
 
 
 def test_pose_helpers_match_torch_expressions(hps):
