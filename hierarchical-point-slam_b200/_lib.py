@@ -19,6 +19,7 @@ SIGNATURES = {
     "hps_grid_create": (_i32, [ctypes.POINTER(_vp)]),
     "hps_grid_destroy": (_i32, [_vp]),
     "hps_grid_build": (_i32, [_vp, _vp, _i64, _f32, _vp]),
+    "hps_grid_append": (_i32, [_vp, _vp, _i64, _i64, ctypes.POINTER(_i32), _vp]),
     "hps_grid_info": (_i32, [_vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(_i64),
                              ctypes.POINTER(_f32), ctypes.POINTER(_i32), _vp]),
     "hps_knn_query": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),

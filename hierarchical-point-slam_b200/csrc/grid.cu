@@ -31,10 +31,18 @@ struct GridMeta {
     int max_enc[3];
     float origin[3];
     int maxc[3];
-    int status;
+    int minc[3];
+    int status;     // bit 0: a point outside the 21-bit cell range; appends: bit 2 `sorted` is full (the index is unusable
+                    // until it is rebuilt)
     int n_cells;
     int cursor;
 };
+
+// The grid's origin sits kMarginCells voxels below the bounding box of the points it was built over, so that points
+// appended later (hps_grid_append: a SLAM map grows in every direction) still get non-negative cell coordinates.
+constexpr int kMarginCells = 1024;
+// A cell's range in `sorted` is allocated with room to grow: count + max(2, count / 2) entries.
+__device__ __forceinline__ int cell_capacity(int count) { return count + max(2, count >> 1); }
 
 constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr int kCoordBits = 21;
@@ -78,6 +86,7 @@ __global__ void grid_init_kernel(Cell* table, int64_t T, GridMeta* meta) {
             meta->max_enc[a] = (int)0x80000000;
             meta->origin[a] = 0.f;
             meta->maxc[a] = -1;
+            meta->minc[a] = 0;
         }
         meta->status = 0;
         meta->n_cells = 0;
@@ -114,8 +123,9 @@ __global__ void grid_bbox_kernel(const float* __restrict__ pos, int64_t n, GridM
 __global__ void grid_origin_kernel(GridMeta* meta, float inv_cell) {
     if (threadIdx.x < 3) {
         int a = threadIdx.x;
-        float o = float_dec(meta->min_enc[a]);
+        const float lo = float_dec(meta->min_enc[a]);
         float m = float_dec(meta->max_enc[a]);
+        const float o = lo - (float)kMarginCells / inv_cell;
         meta->origin[a] = o;
         int c = cell_coord(m, o, inv_cell);
         if (c > kCoordMax || c < 0) {
@@ -123,6 +133,7 @@ __global__ void grid_origin_kernel(GridMeta* meta, float inv_cell) {
             c = kCoordMax;
         }
         meta->maxc[a] = c;
+        meta->minc[a] = max(cell_coord(lo, o, inv_cell), 0);
     }
 }
 
@@ -158,10 +169,12 @@ __global__ void grid_insert_kernel(const float* __restrict__ pos, int64_t n, flo
 
 // Give every occupied cell a contiguous range of `sorted`: warp-aggregated bump allocation (the
 // order of cells in memory is irrelevant to the search result).
-__global__ void grid_alloc_kernel(Cell* table, int64_t T, GridMeta* meta) {
+__global__ void grid_alloc_kernel(Cell* table, int64_t T, GridMeta* meta, int* __restrict__ cell_cap) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    int cnt = (i < T) ? table[i].count : 0;
+    const int count = (i < T) ? table[i].count : 0;
+    int cnt = count > 0 ? cell_capacity(count) : 0;          // entries reserved for the cell (room for appends)
+    if (i < T) cell_cap[i] = cnt;
     int incl = cnt;
     for (int o = 1; o < 32; o <<= 1) {
         int v = __shfl_up_sync(kFull, incl, o);
@@ -181,6 +194,89 @@ __global__ void grid_scatter_kernel(const float* __restrict__ pos, int64_t n, co
     if (i >= n) return;
     int dst = table[pt_slot[i]].start + pt_rank[i];
     sorted[dst] = make_float4(pos[i * 3 + 0], pos[i * 3 + 1], pos[i * 3 + 2], __int_as_float((int)i));
+}
+
+// ------------------------------------------------------------------------------------------------
+// append (index.add on an existing index, neural_point.py:327): hash ONLY the new points into the built structure
+// ------------------------------------------------------------------------------------------------
+// New point i (global index n_old + i): find or create its cell, take the next rank in it.
+__global__ void grid_append_insert_kernel(const float* __restrict__ pos, int64_t n_old, int64_t n_add, float inv_cell,
+                                          Cell* table, unsigned mask, GridMeta* meta, int* __restrict__ pt_slot,
+                                          int* __restrict__ pt_rank) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_add) return;
+    const float* p = pos + (n_old + i) * 3;
+    int c[3];
+    bool ok = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        c[a] = cell_coord(p[a], meta->origin[a], inv_cell);
+        ok = ok && c[a] >= 0 && c[a] <= kCoordMax;
+    }
+    if (!ok) {                      // outside the coordinate range of this origin: the host rebuilds
+        atomicOr(&meta->status, 1);
+        pt_slot[i] = -1;
+        return;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        atomicMax(&meta->maxc[a], c[a]);
+        atomicMin(&meta->minc[a], c[a]);
+    }
+    const unsigned long long key = cell_key(c[0], c[1], c[2]);
+    unsigned h = hash_key(key) & mask;
+    while (true) {
+        unsigned long long prev = atomicCAS(&table[h].key, kEmptyKey, key);
+        if (prev == kEmptyKey) {
+            atomicAdd(&meta->n_cells, 1);
+            break;
+        }
+        if (prev == key) break;
+        h = (h + 1) & mask;
+    }
+    pt_slot[i] = (int)h;
+    pt_rank[i] = atomicAdd(&table[h].count, 1);
+}
+
+// The last arrival of a cell (rank == count - 1) settles its range: a new cell gets one at the cursor; a cell that
+// outgrew its range MOVES to a larger one there (the old entries are copied, the old range becomes dead space until the
+// next rebuild compacts it - frontier cells of a growing map are sparse when first seen and fill up a frame later).  Only
+// a full `sorted` array is reported (status bit 2): the host rebuilds.
+__global__ void grid_append_alloc_kernel(int64_t n_add, Cell* table, int* __restrict__ cell_cap, GridMeta* meta,
+                                         const int* __restrict__ pt_slot, const int* __restrict__ pt_rank,
+                                         float4* __restrict__ sorted, int64_t sorted_cap) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_add) return;
+    const int h = pt_slot[i];
+    if (h < 0) return;
+    const int cnt = table[h].count;
+    const int old_cap = cell_cap[h];
+    if (pt_rank[i] != cnt - 1 || cnt <= old_cap) return;
+    const int want = max(cell_capacity(cnt), 2 * old_cap);
+    const int start = atomicAdd(&meta->cursor, want);
+    if ((int64_t)start + want > sorted_cap) {
+        atomicOr(&meta->status, 4);
+        return;
+    }
+    // entries [0, old count) are the cell's old points; [old count, count) belong to this append and are written by the
+    // scatter pass; copying min(old_cap, count) entries moves every old point (and some slack that gets overwritten)
+    const int old_start = table[h].start;
+    const int n_copy = min(old_cap, cnt);
+    for (int j = 0; j < n_copy; ++j) sorted[start + j] = sorted[old_start + j];
+    table[h].start = start;
+    cell_cap[h] = want;
+}
+
+__global__ void grid_append_scatter_kernel(const float* __restrict__ pos, int64_t n_old, int64_t n_add,
+                                           const Cell* __restrict__ table, const int* __restrict__ cell_cap,
+                                           const int* __restrict__ pt_slot, const int* __restrict__ pt_rank,
+                                           float4* __restrict__ sorted) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_add) return;
+    const int h = pt_slot[i];
+    if (h < 0 || pt_rank[i] >= cell_cap[h]) return;          // (reported by the alloc pass)
+    const float* p = pos + (n_old + i) * 3;
+    sorted[table[h].start + pt_rank[i]] = make_float4(p[0], p[1], p[2], __int_as_float((int)(n_old + i)));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -302,7 +398,7 @@ knn_query_kernel(GridView g, const float* __restrict__ q, const float* __restric
             z1 = max(z1, cell_coord(qz[k] + rr, oz, g.inv_cell));
         }
     }
-    x0 = max(x0, 0); y0 = max(y0, 0); z0 = max(z0, 0);
+    x0 = max(x0, g.meta->minc[0]); y0 = max(y0, g.meta->minc[1]); z0 = max(z0, g.meta->minc[2]);
     x1 = min(x1, g.meta->maxc[0]); y1 = min(y1, g.meta->maxc[1]); z1 = min(z1, g.meta->maxc[2]);
     const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
     const bool any = (nx > 0) && (ny > 0) && (nz > 0);
@@ -448,9 +544,11 @@ knn_query_kernel(GridView g, const float* __restrict__ q, const float* __restric
 // ------------------------------------------------------------------------------------------------
 struct hps_grid {
     int64_t n = 0, cap_n = 0, T = 0, cap_T = 0;
+    int64_t sorted_cap = 0;      // entries of `sorted` (cells keep room to grow: <= 3.5 n at build, plus room for appends)
     float cell = 0.f;
     float4* sorted = nullptr;
     hps::Cell* table = nullptr;
+    int* cell_cap = nullptr;     // [cap_T] entries reserved per cell (build / append only; the query never reads it)
     int* pt_slot = nullptr;
     int* pt_rank = nullptr;
     hps::GridMeta* meta = nullptr;
@@ -475,6 +573,7 @@ extern "C" int hps_grid_destroy(hps_grid_t* g) {
     if (!g) return 0;
     cudaFree(g->sorted);
     cudaFree(g->table);
+    cudaFree(g->cell_cap);
     cudaFree(g->pt_slot);
     cudaFree(g->pt_rank);
     cudaFree(g->meta);
@@ -489,16 +588,21 @@ extern "C" int hps_grid_build(hps_grid_t* g, const float* pos, int64_t n, float 
     HPS_REQUIRE(cell_size > 0.f, "cell_size must be positive");
     HPS_REQUIRE(n == 0 || pos != nullptr, "null positions");
     cudaStream_t stream = (cudaStream_t)stream_;
+    // capacities: room for half as many points again before an append has to give up (status 8) and the host rebuilds
+    const int64_t want_cap = n + n / 2 + 1024;
     int64_t T = 1024;
-    while (T < 2 * n) T <<= 1;
-    if (n > g->cap_n) {
+    while (T < 2 * want_cap) T <<= 1;
+    if (want_cap > g->cap_n) {
         HPS_CUDA_OK(cudaStreamSynchronize(stream));
         cudaFree(g->sorted);
         cudaFree(g->pt_slot);
         cudaFree(g->pt_rank);
         g->sorted = nullptr; g->pt_slot = nullptr; g->pt_rank = nullptr; g->cap_n = 0;
-        int64_t cap = n + n / 4 + 1024;
-        HPS_CUDA_OK(cudaMalloc(&g->sorted, cap * sizeof(float4)));
+        int64_t cap = want_cap;
+        // sum of the cells' reserved ranges <= n + n / 2 + 2 * cells <= 3.5 n; appended points need at most 3 entries each
+        // when every one of them opens a cell (capacity(1) = 3)
+        g->sorted_cap = 3 * n + n / 2 + 3 * (cap - n) + 65536;
+        HPS_CUDA_OK(cudaMalloc(&g->sorted, g->sorted_cap * sizeof(float4)));
         HPS_CUDA_OK(cudaMalloc(&g->pt_slot, cap * sizeof(int)));
         HPS_CUDA_OK(cudaMalloc(&g->pt_rank, cap * sizeof(int)));
         g->cap_n = cap;
@@ -506,8 +610,10 @@ extern "C" int hps_grid_build(hps_grid_t* g, const float* pos, int64_t n, float 
     if (T > g->cap_T) {
         HPS_CUDA_OK(cudaStreamSynchronize(stream));
         cudaFree(g->table);
-        g->table = nullptr; g->cap_T = 0;
+        cudaFree(g->cell_cap);
+        g->table = nullptr; g->cell_cap = nullptr; g->cap_T = 0;
         HPS_CUDA_OK(cudaMalloc(&g->table, T * sizeof(Cell)));
+        HPS_CUDA_OK(cudaMalloc(&g->cell_cap, T * sizeof(int)));
         g->cap_T = T;
     }
     g->n = n;
@@ -517,6 +623,7 @@ extern "C" int hps_grid_build(hps_grid_t* g, const float* pos, int64_t n, float 
     const int tb = 256;
     grid_init_kernel<<<(unsigned)ceil_div(T, tb), tb, 0, stream>>>(g->table, T, g->meta);
     HPS_LAUNCH_OK();
+    HPS_CUDA_OK(cudaMemsetAsync(g->cell_cap, 0, T * sizeof(int), stream));
     if (n > 0) {
         int64_t nb64 = ceil_div(n, tb);
         int nb = (int)(nb64 < kNumSMs * 8 ? nb64 : kNumSMs * 8);
@@ -527,12 +634,47 @@ extern "C" int hps_grid_build(hps_grid_t* g, const float* pos, int64_t n, float 
         grid_insert_kernel<<<(unsigned)ceil_div(n, tb), tb, 0, stream>>>(pos, n, inv, g->table, (unsigned)(T - 1),
                                                                          g->meta, g->pt_slot, g->pt_rank);
         HPS_LAUNCH_OK();
-        grid_alloc_kernel<<<(unsigned)ceil_div(T, tb), tb, 0, stream>>>(g->table, T, g->meta);
+        grid_alloc_kernel<<<(unsigned)ceil_div(T, tb), tb, 0, stream>>>(g->table, T, g->meta, g->cell_cap);
         HPS_LAUNCH_OK();
         grid_scatter_kernel<<<(unsigned)ceil_div(n, tb), tb, 0, stream>>>(pos, n, g->table, g->pt_slot, g->pt_rank,
                                                                           g->sorted);
         HPS_LAUNCH_OK();
     }
+    return 0;
+}
+
+extern "C" int hps_grid_append(hps_grid_t* g, const float* pos, int64_t n_old, int64_t n_new, int* status, void* stream_) {
+    using namespace hps;
+    HPS_REQUIRE(g != nullptr && g->T > 0, "grid not built");
+    HPS_REQUIRE(status != nullptr, "null status pointer");
+    HPS_REQUIRE(n_old == g->n, "n_old must be the point count the grid holds");
+    HPS_REQUIRE(n_new >= n_old && n_new < (1ll << 30), "point count out of range");
+    *status = 0;
+    const int64_t n_add = n_new - n_old;
+    if (n_add == 0) return 0;
+    HPS_REQUIRE(pos != nullptr, "null positions");
+    if (n_new > g->cap_n || 2 * n_new > g->T) {      // the build-time capacities are spent: the caller rebuilds
+        *status = 8;
+        return 0;
+    }
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const float inv = 1.0f / g->cell;
+    const int tb = 256;
+    const unsigned nb = (unsigned)ceil_div(n_add, tb);
+    grid_append_insert_kernel<<<nb, tb, 0, stream>>>(pos, n_old, n_add, inv, g->table, (unsigned)(g->T - 1), g->meta,
+                                                     g->pt_slot, g->pt_rank);
+    HPS_LAUNCH_OK();
+    grid_append_alloc_kernel<<<nb, tb, 0, stream>>>(n_add, g->table, g->cell_cap, g->meta, g->pt_slot, g->pt_rank,
+                                                    g->sorted, g->sorted_cap);
+    HPS_LAUNCH_OK();
+    grid_append_scatter_kernel<<<nb, tb, 0, stream>>>(pos, n_old, n_add, g->table, g->cell_cap, g->pt_slot, g->pt_rank,
+                                                      g->sorted);
+    HPS_LAUNCH_OK();
+    GridMeta h;
+    HPS_CUDA_OK(cudaMemcpyAsync(&h, g->meta, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    HPS_CUDA_OK(cudaStreamSynchronize(stream));
+    *status = h.status;
+    if (h.status == 0) g->n = n_new;
     return 0;
 }
 

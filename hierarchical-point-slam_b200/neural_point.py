@@ -36,59 +36,108 @@ class CloudPositions(torch.Tensor):
         return a.astype(dtype) if dtype is not None else a
 
 
+def _grown(buf, n, extra, width):
+    """Capacity-doubling append buffer: (buffer with room for n + extra rows, whether it was re-allocated)."""
+    need = n + extra
+    if buf is not None and buf.shape[0] >= need:
+        return buf, False
+    cap = max(need, 2 * (buf.shape[0] if buf is not None else 0), 1024)
+    new = torch.empty((cap, width), dtype=buf.dtype if buf is not None else torch.float32,
+                      device=buf.device if buf is not None else None)
+    if buf is not None and n:
+        new[:n] = buf[:n]
+    return new, True
+
+
 class GridIndex:
-    """faiss-like facade over ops.VoxelHashGrid for one level."""
+    """faiss-like facade over ops.VoxelHashGrid for one level.  Positions live in a capacity-doubling (cap,3) device
+    buffer (`positions` = its first ntotal rows); add() appends in place and the next query hashes only the new points
+    into the built grid (hps_grid_append) - an insertion costs O(new points), like the reference's index.add
+    (neural_point.py:327), not a re-hash and re-allocation of the whole cloud."""
 
     def __init__(self, device):
         self.device = torch.device(device)
         self.is_trained = False
         self.nprobe = 1                       # accepted and ignored: the search is exact
-        self._pos = torch.zeros(0, 3, dtype=torch.float32, device=self.device)
+        self._buf = torch.zeros(0, 3, dtype=torch.float32, device=self.device)
+        self._n = 0
         self._grid = None
         self._grid_n = -1
         self._cell = None
+        self.generation = 0                   # bumped whenever the position buffer is re-allocated (see storage_generation)
+        self.appends = self.rebuilds = 0      # bookkeeping for tests / diagnostics
+        self.last_append_status = 0
+        self.append_failures = []             # status words of appends that had to fall back to a rebuild
         # Voxel edge.  When set (NeuralPointCloud derives it from the level's largest query radius) no
         # host sync is needed per query; when None it is derived from each batch's largest radius.
         self.cell_hint = None
 
     @property
+    def _pos(self):
+        return self._buf[:self._n]
+
+    @property
     def ntotal(self):
-        return int(self._pos.shape[0])
+        return int(self._n)
 
     def train(self, x=None):
         self.is_trained = True
 
     def add(self, x):
-        x = torch.as_tensor(x, dtype=torch.float32, device=self.device).reshape(-1, 3)
-        self._pos = torch.cat([self._pos, x.detach()], 0)
+        x = torch.as_tensor(x, dtype=torch.float32, device=self.device).reshape(-1, 3).detach()
+        m = x.shape[0]
+        if m == 0:
+            return
+        self._buf, moved = _grown(self._buf, self._n, m, 3)
+        if moved:
+            self.generation += 1              # (the grid keeps its own copy of the points: it is still appended to)
+        self._buf[self._n:self._n + m] = x
+        self._n += m
 
     def reset(self, pos):
-        self._pos = torch.as_tensor(pos, dtype=torch.float32, device=self.device).reshape(-1, 3).detach().clone()
+        self._buf = torch.as_tensor(pos, dtype=torch.float32, device=self.device).reshape(-1, 3).detach().clone()
+        self._n = self._buf.shape[0]
         self.is_trained = True
         self._grid_n = -1
+        self.generation += 1
 
     @property
     def positions(self):
         return self._pos
 
+    @property
+    def storage_generation(self):
+        """Changes whenever a device address a captured CUDA graph may hold has changed (position buffer re-allocated,
+        grid rebuilt): re-capture graphs of iterations that query this index when it does."""
+        return (self.generation, self._grid.generation if self._grid is not None else 0)
+
     def _ensure_grid(self, t_dn):
-        """(Re)build when points were appended or the cell size is badly matched to the query radius."""
+        """Bring the grid up to date: append the points added since the last query (the usual case) or (re)build - first
+        use, a cell / the arrays outgrew their room, or the cell size is badly matched to the query radius."""
         stale = self._grid is None or self._grid_n != self.ntotal
         if self.cell_hint is not None:
             want = float(self.cell_hint)
-            stale = stale or want != self._cell
+            rebuild = self._grid is None or want != self._cell
         else:
             r_max = float(torch.sqrt(t_dn.max()).item()) if t_dn.numel() else 1.0   # one scalar sync
             want = max(r_max * 0.5, 1e-4)
-            if not stale and not (0.5 * self._cell <= want <= 2.0 * self._cell):
-                stale = True
-            elif not stale:
+            rebuild = self._grid is None or not (0.5 * self._cell <= want <= 2.0 * self._cell)
+            if not rebuild:
                 want = self._cell
-        if stale:
+        if stale and not rebuild and 0 < self._grid_n < self.ntotal:
+            self.last_append_status = self._grid.append(self._pos, self._grid_n)
+            if self.last_append_status == 0:
+                self._grid_n = self.ntotal
+                self.appends += 1
+                return self._grid
+            self.append_failures.append(self.last_append_status)
+            rebuild = True                    # out of room somewhere: start over with fresh capacities
+        if stale or rebuild:
             if self._grid is None:
                 self._grid = ops.VoxelHashGrid()
             self._grid.build(self._pos, want)
             self._grid_n, self._cell = self.ntotal, want
+            self.rebuilds += 1
         return self._grid
 
     def grid_for(self, radius):
@@ -215,6 +264,8 @@ class NeuralPointCloud(object):
         self.geo_feats = {}
         self.col_feats = {}
         self.index = {}
+        self._geo_buf, self._col_buf = {}, {}     # capacity buffers behind geo_feats / col_feats (add_neural_points)
+        self._storage_generation = 0
         self._cloud_normal = {}
         self._input_pos = []
         self._input_rgb = []
@@ -234,6 +285,14 @@ class NeuralPointCloud(object):
         frame and level (four times per frame, :506-509); here it is `frustum_select` over the resident positions.
         Feed the result to ops.LiveRows / LiveRows.pair."""
         return frustum_select(self.index[level].positions, c2w, depth, H, W, fx, fy, cx, cy, edge)
+
+    def storage_generation(self, level):
+        """A value that changes whenever a device address of this level may have changed - feature tables or position
+        buffer re-allocated (capacity doubling, set_cloud, update_*_feats with a whole table), neighbour grid rebuilt.
+        Point insertion normally changes NONE of them (everything is appended in place), so an iteration captured in a
+        CUDA graph (graphs.GraphedStep) stays valid across insertions; re-capture when this value differs from the one
+        seen at capture time."""
+        return (self._storage_generation, self.index[level].storage_generation if level in self.index else None)
 
     def cloud_pos_tensor(self, level):
         """The (N,3) device tensor itself (what Mapper.py:779 / Tracker.py:257 rebuild every time)."""
@@ -331,6 +390,7 @@ class NeuralPointCloud(object):
         else:
             assert feats.shape[0] == table[level].shape[0], "feature shape[0] mismatch"
             table[level] = feats.clone().detach()
+            self._storage_generation += 1
 
     def update_geo_feats(self, feats, indices=None, level=None):
         self._update(self.geo_feats, feats, indices, level)
@@ -368,6 +428,9 @@ class NeuralPointCloud(object):
         mk = lambda: torch.zeros(n, self.c_dim, device=dev).normal_(mean=0, std=0.1)
         self.geo_feats[level] = mk() if geo_feats is None else geo_feats.to(dev).float().contiguous()
         self.col_feats[level] = mk() if col_feats is None else col_feats.to(dev).float().contiguous()
+        self._geo_buf.pop(level, None)
+        self._col_buf.pop(level, None)
+        self._storage_generation += 1
 
     def add_neural_points(self, batch_rays_o, batch_rays_d, batch_gt_depth, batch_gt_color, normals=None,
                           train=False, is_pts_grad=False, dynamic_radius=None, level=None, idx=None):
@@ -405,12 +468,26 @@ class NeuralPointCloud(object):
         index.train()
         index.add(pts)
         self._pts_num[level] += pts.shape[0]
-        new = lambda: torch.zeros(pts.shape[0], self.c_dim, device=dev).normal_(mean=0, std=0.1)
-        if self.geo_feats[level] is None:
-            self.geo_feats[level], self.col_feats[level] = new(), new()
-        else:
-            self.geo_feats[level] = torch.cat([self.geo_feats[level], new()], 0)
-            self.col_feats[level] = torch.cat([self.col_feats[level], new()], 0)
+        # feature rows of the new points, N(0, 0.1^2) (neural_point.py:305-317), appended IN PLACE: the tables live in
+        # capacity-doubling buffers (the reference re-allocates both (N,32) tables with torch.cat on every insertion)
+        k = pts.shape[0]
+        for table, bufs in ((self.geo_feats, self._geo_buf), (self.col_feats, self._col_buf)):
+            cur = table[level]
+            n_old = 0 if cur is None else cur.shape[0]
+            buf = bufs.get(level)
+            if cur is not None and (buf is None or cur.data_ptr() != buf.data_ptr() or buf.shape[0] < n_old):
+                buf = None                    # the table was replaced from outside (update_*_feats): adopt it
+            if buf is None:
+                buf = torch.empty((max(2 * (n_old + k), 1024), self.c_dim), dtype=torch.float32, device=dev)
+                if n_old:
+                    buf[:n_old] = cur
+                self._storage_generation += 1
+            else:
+                buf, moved = _grown(buf, n_old, k, self.c_dim)
+                self._storage_generation += int(moved)
+            bufs[level] = buf
+            buf[n_old:n_old + k].normal_(mean=0, std=0.1)
+            table[level] = buf[:n_old + k]
         return torch.sum(keep)
 
     # ---- neighbour queries -----------------------------------------------------------------------

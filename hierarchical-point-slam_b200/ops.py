@@ -40,7 +40,7 @@ def _side_stream(dev, which=0, priority=0):
 
 # ---- instrumentation: kernel-launch counter and optional CUDA-event timers per C-ABI call -----------
 LAUNCHES = {"n": 0}
-_KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_knn_query": 1, "hps_sample_knn": 1, "hps_interp_fwd": 1, "hps_interp_bwd": 1,
+_KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_grid_append": 3, "hps_knn_query": 1, "hps_sample_knn": 1, "hps_interp_fwd": 1, "hps_interp_bwd": 1,
                      "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_mlp_tc_pack": 1, "hps_mlp_tc_fwd": 1,
                      "hps_mlp_tc_bwd_pack": 2, "hps_mlp_tc_bwd": 3, "hps_tc_selftest": 1, "hps_composite_fwd": 1,
                      "hps_composite_bwd": 1, "hps_composite_mapper_loss": 1, "hps_sample_rays": 1, "hps_sample_rays_bwd": 1, "hps_mapper_loss": 1,
@@ -204,6 +204,7 @@ class VoxelHashGrid:
         self._h = h
         self.n = 0
         self.cell = None
+        self.generation = 0
 
     def __del__(self):
         try:
@@ -213,14 +214,36 @@ class VoxelHashGrid:
         except Exception:
             pass
 
-    def build(self, pos, cell):
+    def build(self, pos, cell, check=True):
+        """(Re)build over pos (N,3).  check: read the status word back (one host synchronisation per build - builds are
+        rare: insertions go through append()) and raise if a point fell outside the 21-bit cell range, where the exact-
+        search guarantee would silently break (cell size far too small for the extent)."""
         _need_cuda(pos)
         pos = _f32c(pos).reshape(-1, 3)
         with torch.cuda.device(pos.device):
             _call("hps_grid_build", self._h, _lib.ptr(pos), pos.shape[0], float(cell), _stream())
-        self._keep = pos            # keep the source alive until the stream has consumed it
-        self.n = pos.shape[0]
-        self.cell = float(cell)
+            self._keep = pos            # keep the source alive until the stream has consumed it
+            self.n = pos.shape[0]
+            self.cell = float(cell)
+            self.generation += 1        # device addresses / hash mask may have changed: captured CUDA graphs are stale
+            if check and self.info()["status"] & 1:
+                raise _lib.HpsError("voxel grid: points outside the 21-bit cell range (cell %.3g m is too small for the "
+                                    "cloud's extent)" % self.cell)
+
+    def append(self, pos, n_old):
+        """pos (N,3): the first n_old rows are the points the grid holds, rows [n_old, N) are hashed into the existing
+        structure (O(new points); device addresses and the hash mask stay, so captured CUDA graphs remain valid).
+        -> status (host int, one synchronisation): 0 = done, otherwise the caller must build() again (a cell or the
+        arrays ran out of the room they were built with, or a point lies outside the origin's coordinate range)."""
+        _need_cuda(pos)
+        pos = _f32c(pos).reshape(-1, 3)
+        st = ctypes.c_int(0)
+        with torch.cuda.device(pos.device):
+            _call("hps_grid_append", self._h, _lib.ptr(pos), int(n_old), pos.shape[0], ctypes.byref(st), _stream())
+        if st.value == 0:
+            self._keep = pos
+            self.n = pos.shape[0]
+        return st.value
 
     def info(self):
         n, T, nc, cell, st = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_float(), ctypes.c_int()

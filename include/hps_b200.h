@@ -43,6 +43,14 @@ int hps_grid_create(hps_grid_t** out);
 int hps_grid_destroy(hps_grid_t* g);
 /* (Re)build over n points pos[n][3].  cell_size > 0.  May cudaMalloc (grow-only).  Stream-ordered.  */
 int hps_grid_build(hps_grid_t* g, const float* pos, int64_t n, float cell_size, void* stream);
+/* index.add(x) on a built index (neural_point.py:327): hashes ONLY points [n_old, n_new) of pos[n_new][3] (the first
+ * n_old rows are the points the grid already holds, unchanged) into the existing structure - cells are built with room to
+ * grow, new cells take ranges behind the old ones - so that an insertion costs O(new points), not O(cloud).  Keeps every
+ * device address and the hash mask (kernels captured in CUDA graphs stay valid).  Synchronises `stream` once to hand back
+ * *status (host int): 0 = done; otherwise the index is unusable until hps_grid_build is called again: bit 0 a new point
+ * lies outside the coordinate range of the grid's origin, bit 2 / bit 3 the point arrays / the hash table are full (bit 3
+ * is found before anything is touched).  A cell that outgrows its range moves to a larger one inside the point array.   */
+int hps_grid_append(hps_grid_t* g, const float* pos, int64_t n_old, int64_t n_new, int* status, void* stream);
 /* Host-visible facts; synchronises `stream` to read the device status word.
  * status bit0: a point fell outside the 21-bit cell range (cell_size too small for the extent).     */
 int hps_grid_info(const hps_grid_t* g, int64_t* n_points, int64_t* table_size, int64_t* n_cells,

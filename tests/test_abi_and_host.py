@@ -105,6 +105,9 @@ def test_c_abi_empty_inputs_and_argument_checks_without_a_gpu(hps):
     assert lib.hps_adam_rows(N, N, N, N, 0, 32, 1e-3, 0.9, 0.999, 1e-8, N, N, N, N) == 0
     assert lib.hps_adam_multi(0, N, N, N, N, N, N, 0.9, 0.999, 1e-8, N, 0, N) == 0
     assert lib.hps_adam_multi_own_steps(0, N, N, N, N, N, N, N, 0.9, 0.999, 1e-8, N, 0, N) == 0
+    assert lib.hps_peer_allreduce(N, N, N, 0, 1, 1024, N) == 0            # one rank: nothing to exchange
+    assert lib.hps_peer_allreduce(N, N, N, 1, 4, 0, N) == 0               # empty buffer
+    assert lib.hps_peer_allreduce_ctas() > 0 and lib.hps_peer_allreduce_pad_words() > 8 * lib.hps_peer_allreduce_ctas()
     for kind in (0, 1):
         assert lib.hps_mlp_fwd(kind, N, N, N, N, N, 0, N, N, N) == 0
         assert lib.hps_mlp_tc_fwd(kind, N, N, N, N, N, 0, N, N, N, 0, N) == 0
@@ -124,6 +127,10 @@ def test_c_abi_empty_inputs_and_argument_checks_without_a_gpu(hps):
         (lambda: lib.hps_mlp_fwd(7, N, N, N, N, N, 0, N, N, N), "bad decoder kind"),
         (lambda: lib.hps_mlp_tc_fwd(1, N, N, N, N, N, 16, N, N, N, 0, N), "null buffer"),
         (lambda: lib.hps_knn_query(N, N, N, N, 0, N, N, N, N, 1, N), "grid not built"),
+        (lambda: lib.hps_peer_allreduce(N, N, N, 0, 9, 1024, N), "world size must be 1..8"),
+        (lambda: lib.hps_peer_allreduce(N, N, N, 4, 4, 1024, N), "rank out of range"),
+        (lambda: lib.hps_peer_allreduce(N, N, N, 0, 2, 1022, N), "multiple of 4"),
+        (lambda: lib.hps_peer_allreduce(N, N, N, 0, 2, 1024, N), "null pointer table"),
         (lambda: lib.hps_exposure_fwd(N, N, N, N, N, 8, 4096, 12, N, N, N), "exposure MLP size"),
     ]
     for call, needle in cases:

@@ -691,3 +691,83 @@ def test_knn_largest_cloud_properties(hps):
         m = want_i.numel()
         assert int(used[j].sum()) == m, (j, m)
         assert torch.equal(I[j, :m].long(), want_i) and torch.equal(D[j, :m], want_d)
+
+
+def test_grid_append_equals_a_fresh_build(hps):
+    """hps_grid_append (index.add on a built index, neural_point.py:327): points hashed into the existing structure in
+    batches - new surface patches next to the old cloud (new cells), patches far outside the first bounding box (the
+    origin's margin), and a batch dropped INTO occupied cells until one outgrows its range (status -> rebuild) - must
+    answer every query exactly like an index built from scratch over the same points: indices, distances, counts."""
+    g = torch.Generator().manual_seed(5)
+
+    def patch(n, cx, cy, spread=1.0):
+        uv = torch.rand(n, 2, generator=g) * spread
+        return torch.stack([cx + uv[:, 0], cy + uv[:, 1], -2.0 + 0.05 * torch.sin(3 * uv[:, 0]) + 0.01 * torch.randn(n, generator=g)], 1)
+
+    batches = [patch(20000, 0.0, 0.0), patch(3000, 1.0, 0.0), patch(3000, 0.5, 1.0), patch(2000, -30.0, 12.0),
+               patch(500, 0.2, 0.2, 0.05),                       # 500 points into a 5 cm square of the first patch
+               patch(3000, 2.0, 0.0)]
+    idx = hps.GridIndex(DEV)
+    idx.cell_hint = 0.08
+    q_all, total = [], 0
+    for k, b in enumerate(batches):
+        idx.add(b.to(DEV)) if k else idx.reset(b.to(DEV))
+        total += b.shape[0]
+        q = torch.cat([b[:400] + 0.01 * torch.randn(400, 3, generator=g), batches[0][:200]])
+        q_all.append(q)
+        qs = torch.cat(q_all).to(DEV)
+        rad = (0.04 + 0.12 * torch.rand(qs.shape[0], generator=g, dtype=torch.float64)).to(DEV)
+        got = idx.radius_search(qs, rad)
+        fresh = hps.GridIndex(DEV)
+        fresh.cell_hint = 0.08
+        fresh.reset(torch.cat(batches[:k + 1]).to(DEV))
+        want = fresh.radius_search(qs, rad)
+        assert idx.ntotal == total
+        assert torch.equal(got.I, want.I) and torch.equal(got.D, want.D) and torch.equal(got.count, want.count), k
+        assert int(got.count.max()) > 0
+    # every batch was appended in place: new cells behind the old ones, the far patch inside the origin's margin, and the
+    # cells the dense batch overflowed moved to larger ranges
+    print("appends", idx.appends, "rebuilds", idx.rebuilds, "failed append status words", idx.append_failures)
+    # (status 8 = the build-time capacity, 1.5x the points it was built over, is spent: the one legitimate rebuild here)
+    assert idx.appends >= 4 and idx.rebuilds <= 2 and set(idx.append_failures) <= {8}, (idx.appends, idx.rebuilds, idx.append_failures)
+    # exhaustive oracle on the final cloud
+    pts = torch.cat(batches)
+    sub = torch.cat(q_all)[::37]
+    r = 0.04 + 0.12 * torch.rand(sub.shape[0], generator=g, dtype=torch.float64)
+    De, Ie, ne = O.find_neighbors(pts, sub, r.reshape(-1, 1))
+    got = idx.radius_search(sub.to(DEV), r.to(DEV))
+    sl = torch.arange(8)[None, :] < ne[:, None].long()
+    assert torch.equal(got.count.cpu(), ne)
+    assert not ((got.I.cpu().long() != Ie) & sl).any() and not ((got.D.cpu() != De) & sl).any()
+
+
+def test_point_insertion_appends_in_place(hps):
+    """NeuralPointCloud.add_neural_points over several frames: positions and both feature tables grow inside their
+    capacity buffers (same storage, old rows untouched), the neighbour grid is appended to, not rebuilt, and
+    storage_generation() only moves when a buffer is re-allocated."""
+    cfg = hps.scannet_cfg(DEV)
+    npc = hps.NeuralPointCloud(cfg)
+    sc = O.synthetic_scene(8, 6000, (0.04, 0.16), seed=3)
+    ro, rd, gd, gc = (sc[k].to(DEV) for k in ("rays_o", "rays_d", "gt_depth", "gt_color"))
+    n0 = int(npc.add_neural_points(ro[:2000], rd[:2000], gd[:2000], gc[:2000], level="fine", idx=0))
+    assert n0 > 0
+    npc.find_neighbors_faiss(npc.cloud_pos_tensor("fine")[:10], step="query", level="fine")       # builds the grid
+    gen, ptr_g, ptr_p = npc.storage_generation("fine"), npc.get_geo_feats("fine").data_ptr(), npc.cloud_pos_tensor("fine").data_ptr()
+    row0 = npc.get_geo_feats("fine")[:5].clone()
+    index = npc.get_index("fine")
+    rebuilds = index.rebuilds
+    grew = 0
+    for k in range(1, 3):
+        sl = slice(2000 * k, 2000 * (k + 1))
+        shift = torch.tensor([0.4 * k, 0.0, 0.0], device=DEV)
+        n = int(npc.add_neural_points(ro[sl] + shift, rd[sl], gd[sl], gc[sl], level="fine", idx=k))
+        grew += n
+        npc.find_neighbors_faiss(npc.cloud_pos_tensor("fine")[:10], step="query", level="fine")
+    assert grew > 0 and npc.index_ntotal("fine") == 3 * (n0 + grew) == npc.get_geo_feats("fine").shape[0]
+    # appended in place; a rebuild only when the grid's build-time capacity (1.5x its points) is spent (status 8)
+    assert index.appends >= 1 and set(index.append_failures) <= {8} and index.rebuilds - rebuilds == len(index.append_failures)
+    if npc.get_geo_feats("fine").data_ptr() == ptr_g and npc.cloud_pos_tensor("fine").data_ptr() == ptr_p:
+        assert npc.storage_generation("fine") == gen                 # nothing moved: captured graphs stay valid
+    else:
+        assert npc.storage_generation("fine") != gen
+    assert torch.equal(npc.get_geo_feats("fine")[:5], row0)

@@ -888,3 +888,68 @@ def test_tracker_optimizer_on_the_device(hps, separate_LR):
             assert float((a.detach() - b.detach()).abs().max()) < 5e-6, level
     steps = opt.opt.tensor_steps.tolist()
     assert max(steps) == opt.num_cam_iters and min(steps) == opt.num_cam_iters // 2
+
+
+def _peer_worker(rank, world, port, out):
+    import importlib
+    import os
+    import sys
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    hps = importlib.import_module("hierarchical-point-slam_b200")
+    n = 100_003 * 4
+    ex = hps.parallel.PeerAllReduce(n, dev, dist)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    res = {}
+    for variant in ex.variants():
+        mine = torch.randn(n, generator=g, device=dev)
+        ref = mine.clone()
+        dist.all_reduce(ref)
+        for n_used in (n, 4096, 4):                       # whole buffer, a prefix, one vector
+            ex.buffer.copy_(mine)
+            dist.barrier()
+            ex(variant, n_floats=n_used)
+            torch.cuda.synchronize()
+            ex.check()
+            res[(variant, n_used)] = (float((ex.buffer[:n_used] - ref[:n_used]).abs().max() / ref.abs().max()),
+                                      bool(torch.equal(ex.buffer[n_used:], mine[n_used:])))
+            dist.barrier()
+        # bit-identical on every rank (the owner of a slice computes its sums once and broadcasts them)
+        ex.buffer.copy_(mine)
+        dist.barrier()
+        ex(variant)
+        torch.cuda.synchronize()
+        gathered = [torch.empty_like(ex.buffer) for _ in range(world)]
+        dist.all_gather(gathered, ex.buffer.clone())
+        res[(variant, "identical")] = all(torch.equal(gathered[0], t) for t in gathered)
+    if rank == 0:
+        torch.save(res, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="the peer-memory exchange needs two GPUs on one box")
+def test_peer_allreduce_sums_symmetric_buffers_across_gpus(hps, tmp_path):
+    """hps_peer_allreduce (csrc/peer.cu; SURVEY 8e, the exchange step of the sharded mapper iteration): P2P and - where the
+    fabric has NVLS - multimem variant against NCCL's all_reduce on two GPUs: the sum within fp32 reordering, untouched
+    floats behind the reduced prefix, bit-identical results on both ranks, no timeouts."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    out = str(tmp_path / "peer.pt")
+    mp.spawn(_peer_worker, args=(2, port, out), nprocs=2, join=True)
+    res = torch.load(out, weights_only=False)
+    assert any(k[0] == "p2p" for k in res)
+    for key, val in res.items():
+        if key[1] == "identical":
+            assert val, key
+        else:
+            assert val[0] < 1e-6 and val[1], (key, val)
