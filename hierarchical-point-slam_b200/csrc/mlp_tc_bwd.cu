@@ -31,11 +31,16 @@ int set_trace_bwd(void* buf) {
     return 0;
 }
 
-constexpr int NSTB = 6;   // ring stages of the dgrad kernel
 
 struct GradPtrs {
     float* v[HPS_MLP_NPARAM];
 };
+
+// CTAs of the geometry decoder's dgrad kernel per SM (HPS_GEO_DGRAD_CTAS=1 restores one; read once)
+static const int GEO_DGRAD_CTAS_PER_SM = [] {
+    const char* e = getenv("HPS_GEO_DGRAD_CTAS");
+    return (e != nullptr && e[0] == '1') ? 1 : 2;
+}();
 
 template <int KIND> struct GeoB {
     using C = Cfg<KIND>;
@@ -63,6 +68,8 @@ template <int KIND> struct GeoB {
     static_assert(H + 32 + NE <= 256, "TMEM budget");
     // small fp32 tables in shared memory: Wo [NOUT][H], exposure affine [12], Fourier matrix [3][NF], Q4 [NOUT][32]
     static constexpr int TAB_FLOATS = NOUT * H + 12 + 3 * C::NF + NOUT * 32 + 2;
+    // ring stages: the geometry decoder keeps two CTAs per SM (see the kernel's launch bounds), with half the ring each
+    static constexpr int NSTB = KIND == HPS_MLP_GEO ? 3 : 6;
     static constexpr int SMEM_BYTES = 1024 + 2 * HS * SLAB + NSTB * STAGE_BYTES + TAB_FLOATS * 4 + 256;
     static_assert(SMEM_BYTES <= 232448, "shared memory budget");
     static constexpr int ECPT = NE / CG;                         // embedding columns per epilogue thread
@@ -215,7 +222,7 @@ __device__ __forceinline__ float ldg_pinned(const float* p) {   // a load the co
 }
 
 template <int KIND>
-__global__ void __launch_bounds__(NTHR, 1)
+__global__ void __launch_bounds__(NTHR, KIND == HPS_MLP_GEO ? 2 : 1)
 mlp_dgrad_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, uint8_t* __restrict__ ws,
                     const float* __restrict__ p, const float* __restrict__ affine,
                     const float* __restrict__ dout, int64_t P, int num_tiles, float* __restrict__ dc,
@@ -230,23 +237,23 @@ mlp_dgrad_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, uint8_t* __restr
     uint8_t* sDAhi = smem;
     uint8_t* sDAlo = sDAhi + HS * SLAB;
     uint8_t* sW = sDAlo + HS * SLAB;
-    float* sWo = reinterpret_cast<float*>(sW + NSTB * STG);         // [NOUT][H]
+    float* sWo = reinterpret_cast<float*>(sW + B::NSTB * STG);         // [NOUT][H]
     float* sAff = sWo + NOUT * H;                                   // [12]
     float* sB = sAff + 12;                                          // [3][NF]
     float* sQ4 = sB + 3 * NF;                                       // [NOUT][32]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sQ4 + NOUT * 32 + ((NOUT * H + 3 * NF + NOUT * 32) & 1));
     uint64_t* full = bars;
-    uint64_t* empty = bars + NSTB;
-    uint64_t* a_ready = bars + 2 * NSTB;
-    uint64_t* acc_ready = bars + 2 * NSTB + 1;
-    uint64_t* dump_done = bars + 2 * NSTB + 2;     // dump warp -> epilogue: operand slabs copied out, reusable
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTB + 3);
+    uint64_t* empty = bars + B::NSTB;
+    uint64_t* a_ready = bars + 2 * B::NSTB;
+    uint64_t* acc_ready = bars + 2 * B::NSTB + 1;
+    uint64_t* dump_done = bars + 2 * B::NSTB + 2;     // dump warp -> epilogue: operand slabs copied out, reusable
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * B::NSTB + 3);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float gS = grad_scale(B::maxbits(wimg));
     const float gInv = 1.0f / gS;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NSTB; ++s) {
+        for (int s = 0; s < B::NSTB; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], 1);
         }
@@ -278,8 +285,8 @@ mlp_dgrad_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, uint8_t* __restr
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             for (int j = 0; j < B::ENTRIES; ++j, ++it) {
-                const int st = it % NSTB;
-                mbar_wait(&empty[st], ((it / NSTB) & 1) ^ 1);
+                const int st = it % B::NSTB;
+                mbar_wait(&empty[st], ((it / B::NSTB) & 1) ^ 1);
                 if (elect_one()) {
                     mbar_expect_tx(&full[st], STG);
                     bulk_g2s(sW + st * STG, wimg + (size_t)j * STG, STG, &full[st]);
@@ -307,11 +314,11 @@ mlp_dgrad_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, uint8_t* __restr
                 if (layer >= 1) {   // [dx | dc part] = da_j . [W_j[:, hidden] | Q_{j-1}]
 #pragma unroll 1
                     for (int s = 0; s < HS; ++s) {
-                        const int st_hi = it % NSTB;
-                        mbar_wait(&full[st_hi], (it / NSTB) & 1);
+                        const int st_hi = it % B::NSTB;
+                        mbar_wait(&full[st_hi], (it / B::NSTB) & 1);
                         ++it;
-                        const int st_lo = it % NSTB;
-                        mbar_wait(&full[st_lo], (it / NSTB) & 1);
+                        const int st_lo = it % B::NSTB;
+                        mbar_wait(&full[st_lo], (it / B::NSTB) & 1);
                         ++it;
                         tc_fence_after();
                         if (elect_one()) {
@@ -331,11 +338,11 @@ mlp_dgrad_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, uint8_t* __restr
                     }
                 }
                 if (layer == 0 || layer == 3) {   // dx (embedding columns) += da_i . W_i[:, embedding]
-                    const int st_hi = it % NSTB;
-                    mbar_wait(&full[st_hi], (it / NSTB) & 1);
+                    const int st_hi = it % B::NSTB;
+                    mbar_wait(&full[st_hi], (it / B::NSTB) & 1);
                     ++it;
-                    const int st_lo = it % NSTB;
-                    mbar_wait(&full[st_lo], (it / NSTB) & 1);
+                    const int st_lo = it % B::NSTB;
+                    mbar_wait(&full[st_lo], (it / B::NSTB) & 1);
                     ++it;
                     tc_fence_after();
                     if (elect_one()) {
@@ -1006,7 +1013,12 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
         configured = true;
     }
     const int num_tiles = (int)ceil_div(P, TILE);
-    const int cap = (max_ctas > 0 && max_ctas < kNumSMs) ? max_ctas : kNumSMs;     // dgrad only; wgrad is HBM-bound
+    // dgrad only (wgrad is HBM-bound).  The geometry decoder's dgrad CTAs are small enough (48 registers, 83 KB, 256 TMEM
+    // columns) for two per SM: its tiles are latency-bound chains of tiny MMAs and 8-column epilogues, and a second
+    // resident CTA fills the bubbles of the first.
+    const int per_sm = KIND == HPS_MLP_GEO ? GEO_DGRAD_CTAS_PER_SM : 1;
+    const int lim = kNumSMs * per_sm;
+    const int cap = (max_ctas > 0 && max_ctas * per_sm < lim) ? max_ctas * per_sm : lim;
     int grid = num_tiles < cap ? num_tiles : cap;
     void* img_rw = const_cast<void*>(img);
     uint32_t* maxbits = const_cast<uint32_t*>(GB::maxbits(img));

@@ -159,7 +159,9 @@ class GridIndex:
 
     def search(self, x, k=ops.K_NN):
         """Unbounded k-NN (faiss Index.search semantics) by doubling the radius until every query has k
-        neighbours or the radius covers the whole cloud."""
+        neighbours or the radius covers the whole cloud.  A compatibility facade for callers that used the faiss index
+        directly: NOT on the hot path (find_neighbors_faiss goes through radius_search), one host synchronisation per
+        round."""
         assert k == ops.K_NN, "the kernels are built for nn_num = 8"
         x = x.detach().to(device=self.device, dtype=torch.float32).reshape(-1, 3)
         Q = x.shape[0]
@@ -171,8 +173,17 @@ class GridIndex:
         span = float(torch.maximum((hi - lo).norm() + (x - lo).norm(dim=1).max(), torch.tensor(1e-3)).item())
         todo = torch.arange(Q, device=self.device)
         r = max(span / 64.0, 1e-3)
+        coarse = None
         while todo.numel():
-            nq = self.radius_search(x[todo], r)
+            use = self
+            if self.cell_hint is not None and r > 4.0 * float(self.cell_hint):
+                # a ball much wider than this index's voxels would probe (2 r / cell)^3 hash slots per query (millions for a
+                # 20 m scene with 8 cm voxels): such rounds go to a private index whose voxel edge follows the radius
+                if coarse is None:
+                    coarse = GridIndex(self.device)
+                    coarse._buf, coarse._n, coarse.is_trained = self._buf, self._n, True
+                use = coarse
+            nq = use.radius_search(x[todo], r)
             full = (nq.count >= min(k, self.ntotal)) | (r > span)
             done = todo[full]
             D[done], I[done] = nq.D[full], nq.I[full].long()
