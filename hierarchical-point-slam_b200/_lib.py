@@ -36,7 +36,7 @@ SIGNATURES = {
     "hps_mlp_tc_bwd_packed_bytes": (_i64, [_i32]),
     "hps_mlp_tc_bwd_absmax_offset": (_i64, [_i32]),
     "hps_mlp_tc_bwd_pack": (_i32, [_i32, _vp, _vp, _vp]),
-    "hps_mlp_tc_bwd": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "hps_mlp_tc_bwd": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "hps_tc_selftest": (_i32, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "hps_tc_trace": (_i32, [_vp]),
     "hps_mlp_bwd": (_i32, [_i32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
@@ -45,7 +45,7 @@ SIGNATURES = {
     "hps_composite_bwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp,
                                  _i32, _vp, _vp, _vp]),
     "hps_composite_mapper_loss": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp,
-                                         _f32] + [_vp] * 9),
+                                         _f32] + [_vp] * 13),
     "hps_camera_from_tensor": (_i32, [_vp, _vp, _vp]),
     "hps_camera_from_tensor_bwd": (_i32, [_vp, _vp, _vp, _vp]),
     "hps_rays_from_uv": (_i32, [_vp, _vp, _vp, _i32, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),

@@ -209,7 +209,8 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
                              const int32_t* __restrict__ frame, float w_color, float* __restrict__ depth_out, float* __restrict__ var_out,
                              float* __restrict__ color_out, uint8_t* __restrict__ valid_ray,
                              float* __restrict__ loss, float* __restrict__ g_depth, float* __restrict__ g_color,
-                             float* __restrict__ d_affine) {
+                             float* __restrict__ d_affine, float* __restrict__ d_rgb, float* __restrict__ d_occ,
+                             unsigned* __restrict__ amax_rgb, unsigned* __restrict__ amax_occ) {
     constexpr int RPW = 32 / G, NACC = 13;
     __shared__ float red[NACC][8];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -255,6 +256,7 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
         const bool pm = active && (point_mask == nullptr || point_mask[ray * S + s] != 0);
         const unsigned grp = (G == 32) ? kFull : (((1u << G) - 1u) << (sub * G));
         const int n_has = __popc(__ballot_sync(kFull, pm) & grp);
+        float bgd = 0.f, bgr = 0.f, bgg = 0.f, bgb = 0.f;       // the lead lane's d loss / d depth, d colour (for the group)
         if (lead) {
             const bool ok = n_has >= min_valid;            // decoder.py:310-311
             valid_ray[ray] = ok ? 1 : 0;
@@ -300,6 +302,50 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
                 g_color[ray * 3 + 0] = gc[0];
                 g_color[ray * 3 + 1] = gc[1];
                 g_color[ray * 3 + 2] = gc[2];
+                bgr = gc[0]; bgg = gc[1]; bgb = gc[2];
+            }
+            bgd = gdep;
+        }
+        if (d_occ != nullptr) {
+            // The compositing backward right here (composite_bwd_kernel's expressions for an upstream gradient of 1): the
+            // loss is a scalar, so d loss / d raw for ANY upstream gradient is this times that scalar - the decoders'
+            // backward multiplies it in (hps_mlp_tc_bwd gscale) - and the separate compositing-backward launch between the
+            // decoders' forward and backward disappears from the critical path.
+            const int lane_base = sub * G;
+            const float gd_ = __shfl_sync(kFull, bgd, lane_base), gr = __shfl_sync(kFull, bgr, lane_base),
+                        gg = __shfl_sync(kFull, bgg, lane_base), gb = __shfl_sync(kFull, bgb, lane_base);
+            const float gw = active ? (gd_ * (me.z - depth) + gr * (me.r - cr) + gg * (me.g - cg) + gb * (me.b - cb)) / wsum : 0.f;
+            const float gww = gw * me.w;
+            float suffix = 0.f;
+            for (int j = S - 1; j > 0; --j) {
+                const float v = group_bcast<G>(gww, j, lane_base);
+                if (j > s) suffix += v;
+            }
+            const bool store = live && active;
+            const int64_t i = ray * S + s;
+            const float t = __fadd_rn(__fsub_rn(1.0f, me.alpha), 1e-10f);
+            const float dalpha = gw * me.trans - suffix / t;
+            const float v_occ = store ? dalpha * coef * me.alpha * (1.0f - me.alpha) : 0.f;
+            const float k = me.w / wsum;
+            const float v_r = store ? gr * k : 0.f, v_g = store ? gg * k : 0.f, v_b = store ? gb * k : 0.f;
+            if (store) {
+                d_occ[i] = v_occ;
+                if (d_rgb != nullptr) {
+                    d_rgb[i * 3 + 0] = v_r;
+                    d_rgb[i * 3 + 1] = v_g;
+                    d_rgb[i * 3 + 2] = v_b;
+                }
+            }
+            float mo = fabsf(v_occ), mc = fmaxf(fabsf(v_r), fmaxf(fabsf(v_g), fabsf(v_b)));
+            mo = mo <= 3.0e38f ? mo : 0.f;
+            mc = mc <= 3.0e38f ? mc : 0.f;
+            for (int o = 16; o; o >>= 1) {
+                mo = fmaxf(mo, __shfl_xor_sync(kFull, mo, o));
+                mc = fmaxf(mc, __shfl_xor_sync(kFull, mc, o));
+            }
+            if (lane == 0) {
+                if (amax_occ != nullptr && mo > 0.f) atomicMax(amax_occ, __float_as_uint(mo));
+                if (amax_rgb != nullptr && d_rgb != nullptr && mc > 0.f) atomicMax(amax_rgb, __float_as_uint(mc));
             }
         }
     }
@@ -332,23 +378,25 @@ extern "C" int hps_composite_mapper_loss(const float* rgb, int rgb_stride, const
                                          const float* affine, const int32_t* frame, float w_color, float* depth,
                                          float* var, float* color,
                                          uint8_t* valid_ray, float* loss, float* g_depth, float* g_color,
-                                         float* d_affine, void* stream) {
+                                         float* d_affine, float* d_rgb, float* d_occ, uint32_t* absmax_rgb,
+                                         uint32_t* absmax_occ, void* stream) {
     using namespace hps;
     HPS_REQUIRE(R >= 0 && S >= 1 && S <= 32, "need 1 <= S <= 32");
     if (R == 0) return 0;
     HPS_REQUIRE(occ && z && depth && var && color && valid_ray && gt_depth && loss && g_depth, "null buffer");
     HPS_REQUIRE(gt_color == nullptr || (rgb != nullptr && g_color != nullptr), "colour term needs rgb and g_color");
     HPS_REQUIRE(affine == nullptr || d_affine != nullptr, "affine needs d_affine");
+    HPS_REQUIRE(d_rgb == nullptr || (d_occ != nullptr && rgb != nullptr), "d_rgb needs d_occ and rgb");
     const int tb = 256;
     if (S <= 8) {
         const int64_t warps = ceil_div(R, 4);
         composite_mapper_loss_kernel<8><<<(unsigned)ceil_div(warps * 32, tb), tb, 0, (cudaStream_t)stream>>>(
             rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, min_valid, gt_depth, gt_color, affine, frame,
-            w_color, depth, var, color, valid_ray, loss, g_depth, g_color, d_affine);
+            w_color, depth, var, color, valid_ray, loss, g_depth, g_color, d_affine, d_rgb, d_occ, absmax_rgb, absmax_occ);
     } else {
         composite_mapper_loss_kernel<32><<<(unsigned)ceil_div(R * 32, tb), tb, 0, (cudaStream_t)stream>>>(
             rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, min_valid, gt_depth, gt_color, affine, frame,
-            w_color, depth, var, color, valid_ray, loss, g_depth, g_color, d_affine);
+            w_color, depth, var, color, valid_ray, loss, g_depth, g_color, d_affine, d_rgb, d_occ, absmax_rgb, absmax_occ);
     }
     HPS_LAUNCH_OK();
     return 0;

@@ -176,8 +176,10 @@ __global__ void pack_bwd_kernel(Ptrs prm, uint16_t* __restrict__ img) {
 // overflowed to NaN, tests/test_gpu_scale.py); at the other end an element 2^-17 of the largest one still has a normal
 // high half, and the low halves' subnormal floor (2^-25) is 4e-9 of the largest element.
 // The max is reduced on the device into the 4 bytes behind the packed weight image (zeroed by the pack kernel).
-__device__ __forceinline__ float grad_scale(const uint32_t* maxbits) {
-    const float m = __uint_as_float(*maxbits);
+// `up`: |upstream gradient| when `dout` holds d loss / d raw for an upstream gradient of 1 (the fused compositing + loss
+// kernel writes it in the forward pass) and the true gradient is that times a device scalar.
+__device__ __forceinline__ float grad_scale(const uint32_t* maxbits, float up = 1.0f) {
+    const float m = __uint_as_float(*maxbits) * up;
     if (!(m > 0.f) || m > 3.0e38f) return 1.0f;
     int e;
     frexpf(m, &e);
@@ -226,10 +228,12 @@ __global__ void __launch_bounds__(NTHR, KIND == HPS_MLP_GEO ? 2 : 1)
 mlp_dgrad_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, uint8_t* __restrict__ ws,
                     const float* __restrict__ p, const float* __restrict__ affine,
                     const float* __restrict__ dout, int64_t P, int num_tiles, float* __restrict__ dc,
-                    float* __restrict__ dp, float* __restrict__ daffine, float* __restrict__ dB, int want_w) {
+                    float* __restrict__ dp, float* __restrict__ daffine, float* __restrict__ dB, int want_w,
+                    const float* __restrict__ gscale) {
     using C = Cfg<KIND>;
     using G = Geo<KIND>;
     using B = GeoB<KIND>;
+    const float gu = gscale != nullptr ? __ldg(gscale) : 1.0f;      // upstream gradient of the scalar loss (see grad_scale)
     using W = Ws<KIND>;
     constexpr int H = C::H, E = C::E, NF = C::NF, NOUT = C::NOUT, HS = G::HS, NE = B::NE, STG = B::STAGE_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -249,7 +253,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, uint8_t* __restr
     uint64_t* dump_done = bars + 2 * B::NSTB + 2;     // dump warp -> epilogue: operand slabs copied out, reusable
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * B::NSTB + 3);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float gS = grad_scale(B::maxbits(wimg));
+    const float gS = grad_scale(B::maxbits(wimg), fabsf(gu));
     const float gInv = 1.0f / gS;
 
     if (threadIdx.x == 0) {
@@ -449,7 +453,7 @@ mlp_dgrad_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, uint8_t* __restr
                 load_a(4, a4);
                 if (live) {
 #pragma unroll
-                    for (int o = 0; o < NOUT; ++o) dr[o] = __ldg(dout + pt * NOUT + o);
+                    for (int o = 0; o < NOUT; ++o) dr[o] = __ldg(dout + pt * NOUT + o) * gu;
                 }
                 if (NOUT == 3 && affine != nullptr) {
                     const float4 r4 = *reinterpret_cast<const float4*>(W::raw_ptr(ws, tile) + row * 4);
@@ -684,7 +688,7 @@ template <int KIND> RoleSplit split_roles(int grid) {
 template <int KIND>
 __global__ void __launch_bounds__(GeoW<KIND>::NTHRW, 1)
 mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles, const uint32_t* __restrict__ maxbits,
-                    float* __restrict__ scratch, const RoleSplit split) {
+                    float* __restrict__ scratch, const RoleSplit split, const float* __restrict__ gscale) {
     using C = Cfg<KIND>;
     using GW = GeoW<KIND>;
     using GB = GeoB<KIND>;
@@ -840,7 +844,7 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
         const int quad = warp & 3, half = (warp - 2) >> 2;
         const int h = quad * 32 + lane;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-        const float gInv = 1.0f / grad_scale(maxbits);
+        const float gInv = 1.0f / grad_scale(maxbits, gscale != nullptr ? fabsf(__ldg(gscale)) : 1.0f);
         if (role == 5) {
             if (half == 0) {
                 float v[8], b[8];
@@ -989,7 +993,7 @@ template <int KIND> int launch_pack_bwd(const float* const* params, void* img, c
 template <int KIND>
 int launch_bwd(const float* const* params, const void* img, void* ws, const float* p, const float* affine,
                const float* dout, int64_t P, float* const* dparams, float* dc, float* dp, float* daffine,
-               int absmax_done, int max_ctas, cudaStream_t wstream, cudaStream_t s) {
+               int absmax_done, int max_ctas, cudaStream_t wstream, cudaStream_t s, const float* gscale) {
     using GB = GeoB<KIND>;
     Ptrs prm;
     GradPtrs grd;
@@ -1030,7 +1034,7 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
     }
     mlp_dgrad_tc_kernel<KIND><<<grid, NTHR, GB::SMEM_BYTES, s>>>(
         prm, reinterpret_cast<const uint8_t*>(img), reinterpret_cast<uint8_t*>(ws), p, affine, dout, P, num_tiles, dc, dp,
-        daffine, grd.v[0], dparams ? 1 : 0);
+        daffine, grd.v[0], dparams ? 1 : 0, gscale);
     if (dparams) {
         // The weight-gradient kernels may run on their own stream (ordered after the dgrad kernel by an event), so
         // that whatever the caller enqueues next on `s` - the feature scatter needs only dc - overlaps with them.
@@ -1046,7 +1050,7 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
         HPS_CUDA_OK(cudaMemsetAsync(scratch + GB::OFF_T, 0, (size_t)(GB::SCRATCH_FLOATS - GB::OFF_T) * 4, w));
         const int wgrid = GeoW<KIND>::NROLE * num_tiles < kNumSMs ? GeoW<KIND>::NROLE * num_tiles : kNumSMs;   // every role has a CTA
         mlp_wgrad_tc_kernel<KIND><<<wgrid, GeoW<KIND>::NTHRW, GeoW<KIND>::SMEM_BYTES, w>>>(
-            grd, reinterpret_cast<const uint8_t*>(ws), num_tiles, maxbits, scratch, split_roles<KIND>(wgrid));
+            grd, reinterpret_cast<const uint8_t*>(ws), num_tiles, maxbits, scratch, split_roles<KIND>(wgrid), gscale);
         const int nout = 5 * (Cfg<KIND>::H * 32 + Cfg<KIND>::H);
         HPS_SHARE_SM(mlp_wfinal_kernel<KIND>);
         mlp_wfinal_kernel<KIND><<<(WFINAL_PARTS * nout + 127) / 128, 128, 0, w>>>(prm, grd, scratch);
@@ -1082,19 +1086,20 @@ extern "C" int hps_mlp_tc_bwd_pack(int kind, const float* const* params, void* p
 extern "C" int hps_mlp_tc_bwd(int kind, const float* const* params, const void* packed, void* ws, const float* p,
                               const float* affine, const float* dout, int64_t P, float* const* dparams, float* dc,
                               float* dp, float* daffine, int absmax_done, int max_ctas, void* wgrad_stream,
-                              void* stream) {
+                              const float* gscale, void* stream) {
     using namespace hps;
     HPS_REQUIRE(kind == HPS_MLP_GEO || kind == HPS_MLP_COL, "bad decoder kind");
     HPS_REQUIRE(P >= 0, "negative point count");
     if (P == 0) return 0;
     HPS_REQUIRE(params && packed && ws && p && dout && dc, "null buffer");
+    HPS_REQUIRE(gscale == nullptr || (affine == nullptr && absmax_done), "gscale: without the exposure tail, with max|dout| folded");
     for (int i = 0; i < HPS_MLP_NPARAM; ++i) HPS_REQUIRE(params[i] != nullptr, "null parameter pointer");
     int rc = kind == HPS_MLP_GEO ? tc::launch_bwd<HPS_MLP_GEO>(params, packed, ws, p, affine, dout, P, dparams, dc, dp,
                                                                daffine, absmax_done, max_ctas, (cudaStream_t)wgrad_stream,
-                                                               (cudaStream_t)stream)
+                                                               (cudaStream_t)stream, gscale)
                                  : tc::launch_bwd<HPS_MLP_COL>(params, packed, ws, p, affine, dout, P, dparams, dc, dp,
                                                                daffine, absmax_done, max_ctas, (cudaStream_t)wgrad_stream,
-                                                               (cudaStream_t)stream);
+                                                               (cudaStream_t)stream, gscale);
     if (rc) return rc;
     HPS_LAUNCH_OK();
     return 0;

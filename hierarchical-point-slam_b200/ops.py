@@ -357,6 +357,10 @@ def _packed_buffer(kind, device, tc=False):
     return buf
 
 
+# Compositing backward inside the fused compositing + mapper-loss kernel of the forward pass (HPS_FUSE_COMPOSITE_BWD=0:
+# the separate hps_composite_bwd launch at the head of the backward).
+FUSE_COMPOSITE_BWD = os.environ.get("HPS_FUSE_COMPOSITE_BWD", "1") != "0"
+
 # True: the backward also runs on tensor cores (dgrad chain + streaming wgrad kernels); False: fp32 SIMT backward.
 USE_TC_BWD = os.environ.get("HPS_USE_TC_BWD", "1") != "0"
 
@@ -473,7 +477,7 @@ def _absmax_word(kind, packed):
 
 
 def _mlp_backward(kind, prm, saved_kind, saved, p_c, c_c, aff, dout, P, dprm, dc, need_dp, daff, dev, stream=None,
-                  dp=None, packed=None, absmax_done=False, max_ctas=0, wgrad_stream=None):
+                  dp=None, packed=None, absmax_done=False, max_ctas=0, wgrad_stream=None, gscale=None):
     """Backward of one decoder on `stream`; returns dp (P,3) or None.  dprm: list of gradient buffers (or None).
     dp: preallocated _mlp_dp_buffer (required when `stream` is not the current stream); packed: backward weight
     images built at forward time by _mlp_pack (None: build them now)."""
@@ -488,7 +492,8 @@ def _mlp_backward(kind, prm, saved_kind, saved, p_c, c_c, aff, dout, P, dprm, dc
             _call("hps_mlp_tc_bwd_pack", kind, arr, _lib.ptr(pk), _stream(stream))
         _call("hps_mlp_tc_bwd", kind, arr, _lib.ptr(pk), _lib.ptr(saved), _lib.ptr(p_c), _lib.ptr(aff), _lib.ptr(dout), P,
               darr, _lib.ptr(dc), _lib.ptr(dp), _lib.ptr(daff), 1 if (absmax_done and packed is not None) else 0,
-              int(max_ctas), _stream(wgrad_stream) if wgrad_stream is not None else None, _stream(stream))
+              int(max_ctas), _stream(wgrad_stream) if wgrad_stream is not None else None, _lib.ptr(gscale),
+              _stream(stream))
         return dp
     _call("hps_mlp_bwd", kind, _ptr_array(prm), _lib.ptr(p_c), _lib.ptr(c_c), _lib.ptr(aff), _lib.ptr(saved),
           _lib.ptr(dout), P, darr, _lib.ptr(dc), _lib.ptr(dp), _lib.ptr(daff), _stream(stream))
@@ -986,11 +991,26 @@ class _RenderRays(torch.autograd.Function):
                       _lib.ptr(gd), _lib.ptr(gtc), _lib.ptr(flat[4:]), count, lm.w_color, R, _lib.ptr(flat),
                       _lib.ptr(flat[16:]), _lib.ptr(flat[16 + R:]) if color_loss else None, st())
             else:
+                # with forward-time backward images (the fork path of a training iteration) the compositing backward is
+                # evaluated right here for an upstream gradient of 1 and max |d raw| lands in the images' scale words: the
+                # backward then starts with the decoders' dgrad kernels (gscale = the real upstream gradient)
+                fuse_bwd = (FUSE_COMPOSITE_BWD and fork and need_grad and bpk_g is not None and bpk_c is not None
+                            and aff is None and not spec.tracker)
+                if fuse_bwd:
+                    d_occ_f = torch.empty(P, **f32)
+                    d_rgb_f = torch.empty(P, 3, **f32) if spec.color_stage else None
                 _call("hps_composite_mapper_loss", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
                       float(spec.coef), int(spec.min_valid), _lib.ptr(gd), _lib.ptr(gtc), _lib.ptr(aff_l),
                       _lib.ptr(frm_l), lm.w_color, _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), _lib.ptr(valid),
                       _lib.ptr(flat), _lib.ptr(flat[head:]), _lib.ptr(flat[head + R:]) if color_loss else None,
-                      _lib.ptr(flat[4:]) if aff_l is not None else None, st())
+                      _lib.ptr(flat[4:]) if aff_l is not None else None,
+                      _lib.ptr(d_rgb_f) if fuse_bwd else None, _lib.ptr(d_occ_f) if fuse_bwd else None,
+                      _absmax_word(MLP_COL, bpk_c) if (fuse_bwd and d_rgb_f is not None) else None,
+                      _absmax_word(MLP_GEO, bpk_g) if fuse_bwd else None, st())
+                if fuse_bwd:
+                    ctx.fused_d_raw = (d_occ_f, d_rgb_f)
+        if not hasattr(ctx, "fused_d_raw"):
+            ctx.fused_d_raw = None
         ctx.loss_state = None if lm is None else (flat, a1_l, eprm, color_loss, head, n_aff, aff_in_shape)
         ctx.aff_mlp_state = (mprm, a1_d) if mprm else None
         ctx.spec = spec
@@ -1038,13 +1058,20 @@ class _RenderRays(torch.autograd.Function):
         need_p = spec.tracker and (need[1] or need[2])
         gd = _f32c(g_depth) if g_depth is not None else None
         gc = _f32c(g_color) if (g_color is not None and spec.color_stage) else None
-        d_occ = torch.empty(P, **f32)
-        d_rgb = torch.empty(P, 3, **f32) if spec.color_stage else None
+        fused_raw = ctx.fused_d_raw
+        if fused_raw is not None:
+            d_occ, d_rgb = fused_raw
+        else:
+            d_occ = torch.empty(P, **f32)
+            d_rgb = torch.empty(P, 3, **f32) if spec.color_stage else None
         dc_g = torch.empty(P, C_DIM, **f32)
         dc_c = torch.empty(P, C_DIM, **f32) if spec.color_stage else None
         want_gw = any(need[7 + i] for i in range(1, N_PARAM))
         want_cw = spec.color_stage and any(need[7 + N_PARAM + i] for i in range(1, N_PARAM))
         fork = MULTI_STREAM and TIMERS is None and spec.color_stage and ctx.saved_kinds == ("tc", "tc")
+        if fused_raw is not None and not fork:
+            raise _lib.HpsError("the forward fused the compositing backward but the backward is not on the multi-stream "
+                                "tensor-core path (HPS_STREAMS / TIMERS changed between forward and backward?)")
         # every zero-initialised buffer of the backward comes out of one allocation = one memset kernel
         zp = _ZeroPool(dev)
         h_dg = zp.want_like(gprm, skip_first=not need[7]) if want_gw else None
@@ -1079,10 +1106,12 @@ class _RenderRays(torch.autograd.Function):
             # forward-time backward images exist => their max|dout| words are zeroed: reduce into them right here
             bpk_g, bpk_c = ctx.bwd_packed
             folded = fork and bpk_g is not None and bpk_c is not None
-            _call("hps_composite_bwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
-                  float(spec.coef), _lib.ptr(gd), _lib.ptr(gc), _lib.ptr(gscale), _lib.ptr(d_rgb), 3, _lib.ptr(d_occ), 1,
-                  _absmax_word(MLP_COL, bpk_c) if folded else None, _absmax_word(MLP_GEO, bpk_g) if folded else None,
-                  st())
+            if fused_raw is None:
+                _call("hps_composite_bwd", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
+                      float(spec.coef), _lib.ptr(gd), _lib.ptr(gc), _lib.ptr(gscale), _lib.ptr(d_rgb), 3, _lib.ptr(d_occ), 1,
+                      _absmax_word(MLP_COL, bpk_c) if folded else None, _absmax_word(MLP_GEO, bpk_g) if folded else None,
+                      st())
+            up = gscale if fused_raw is not None else None      # d raw was written for an upstream gradient of 1
             dp_c = None
             wgrad_streams = ()
             if fork:
@@ -1098,7 +1127,7 @@ class _RenderRays(torch.autograd.Function):
                 w_c = _side_stream(dev, 5, priority=WGRAD_PRIORITY) if dcw is not None else None     # (no weight gradients: nothing to fork)
                 w_g = _side_stream(dev, 2, priority=WGRAD_PRIORITY) if dg is not None else None
                 _mlp_backward(MLP_COL, cprm, "tc", act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c, need_p, daff, dev, main,
-                              dp_c, packed=ctx.bwd_packed[1], absmax_done=folded, max_ctas=n_c, wgrad_stream=w_c)
+                              dp_c, packed=ctx.bwd_packed[1], absmax_done=folded, max_ctas=n_c, wgrad_stream=w_c, gscale=up)
                 e_s = None
                 if any(m_need):            # d affine is complete with the colour dgrad: the MLP's backward runs beside
                     e_s = _side_stream(dev, 3)                                      # the feature scatter
@@ -1106,7 +1135,7 @@ class _RenderRays(torch.autograd.Function):
                     g_aff_mlp = _exposure_backward(ctx.aff_mlp_state[0], ctx.aff_mlp_state[1], daff, None, m_need,
                                                    ctx.aff_x_shape, e_s, zp.get(h_exp))
                 _mlp_backward(MLP_GEO, gprm, "tc", act_g, pts, c_geo, None, d_occ, P, dg, dc_g, need_p, None, dev, side,
-                              dp_g, packed=ctx.bwd_packed[0], absmax_done=folded, max_ctas=n_g, wgrad_stream=w_g)
+                              dp_g, packed=ctx.bwd_packed[0], absmax_done=folded, max_ctas=n_g, wgrad_stream=w_g, gscale=up)
                 main.wait_stream(side)
                 wgrad_streams = tuple(w for w in (w_c, w_g) if w is not None)
             else:

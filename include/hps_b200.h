@@ -134,11 +134,13 @@ int hps_mlp_tc_bwd_pack(int kind, const float* const* params, void* packed, void
  * absmax_done != 0: the caller has already reduced max|dout| into that word (hps_composite_bwd can do it while
  * it writes dout), so the extra reduction kernel is skipped.  wgrad_stream: stream for the weight-gradient kernel
  * (ordered after the dgrad kernel through an event); dc / dp / daffine are complete on `stream`, the parameter
- * gradients on `wgrad_stream`.                                                                                */
+ * gradients on `wgrad_stream`.  gscale: device scalar g - `dout` then is d loss / d raw for an upstream gradient of 1
+ * (written in the forward pass by hps_composite_mapper_loss, max |dout| folded: absmax_done must be set) and every
+ * output is g times what it would be for that dout; only without the exposure tail (affine == NULL).            */
 int hps_mlp_tc_bwd(int kind, const float* const* params, const void* packed, void* ws, const float* p,
                    const float* affine, const float* dout, int64_t P, float* const* dparams, float* dc, float* dp,
                    float* daffine, int absmax_done, int max_ctas, void* wgrad_stream /* may be NULL = stream */,
-                   void* stream);
+                   const float* gscale /* may be NULL = 1 */, void* stream);
 /* Single-CTA tcgen05 self-test: D[128][N] = A . B^T with fp16 operands staged K-major (major = 0, source
  * [rows][K]) or MN-major (major = 1, source [K][rows]) - pins the shared-memory descriptor encodings.        */
 int hps_tc_selftest(const float* A, const float* B, float* D, int N, int K, int a_major, int b_major, void* stream);
@@ -181,14 +183,19 @@ int hps_composite_bwd(const float* rgb, int rgb_stride, const float* occ, int oc
  *         (+ w_color * |gt_color - sigmoid(color x affine[0:9] + affine[9:12])| when gt_color is given; affine may
  *         be NULL = identity without the sigmoid's affine, see hps_mapper_loss),
  * g_depth (R), g_color (R,3) = d loss / d depth, d color, and d_affine (12) += d loss / d affine.
- * loss and d_affine are ACCUMULATED: zero them first.                                                            */
+ * loss and d_affine are ACCUMULATED: zero them first.
+ * d_occ (R*S), d_rgb (R*S,3) (may be NULL): additionally the compositing BACKWARD for an upstream gradient of 1 -
+ * d loss / d occ, d loss / d rgb, what hps_composite_bwd would write from g_depth / g_color - with max |.| reduced
+ * into absmax_occ / absmax_rgb (may be NULL); pass them as `dout` of hps_mlp_tc_bwd with its gscale = the upstream
+ * gradient and the separate compositing-backward launch between the decoders' forward and backward is gone.      */
 int hps_composite_mapper_loss(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
                               const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
                               int min_valid, const float* gt_depth, const float* gt_color /* may be NULL */,
                               const float* affine /* may be NULL */, const int32_t* frame /* may be NULL */,
                               float w_color, float* depth, float* var,
                               float* color, uint8_t* valid_ray, float* loss, float* g_depth, float* g_color,
-                              float* d_affine, void* stream);
+                              float* d_affine, float* d_rgb, float* d_occ, uint32_t* absmax_rgb, uint32_t* absmax_occ,
+                              void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Adam over the live (frustum-selected) rows of a feature table, fused with the write-back into the table
