@@ -344,7 +344,7 @@ __device__ __forceinline__ unsigned long long merge_top8(unsigned long long best
 // RAYS: the queries are the sample points of rays and are computed here (sample_point.cuh) instead of being read -
 // the warp also writes z / point / thresholds for the kernels downstream, which saves the sampling launch.
 template <int G, bool RAYS>
-__global__ void __launch_bounds__(kQueryWarps * 32, 4)      // 4 CTAs = 32 warps per SM (G = 5 would take 80 registers otherwise)
+__global__ void __launch_bounds__(kQueryWarps * 32, G == 1 ? 5 : 4)      // G = 1: 48 registers, so that four CTAs fit beside a weight-gradient CTA (16 K of the 64 K registers); G = 5 would take 80 otherwise
 knn_query_kernel(GridView g, const float* __restrict__ q, const float* __restrict__ t_up,
                  const float* __restrict__ t_dn, int64_t nq, int32_t* __restrict__ I, float* __restrict__ D,
                  int32_t* __restrict__ count, int32_t* __restrict__ cand, const RaySource src,

@@ -985,8 +985,11 @@ template <int KIND> int launch_pack_bwd(const float* const* params, void* img, c
     Ptrs prm;
     for (int i = 0; i < HPS_MLP_NPARAM; ++i) prm.v[i] = params[i];
     float* q = GeoB<KIND>::scratch(img) + GeoB<KIND>::OFF_T;
-    pack_q_kernel<KIND><<<(4 * Cfg<KIND>::H * 32 + 255) / 256, 256, 0, s>>>(prm, q);
-    pack_bwd_kernel<KIND><<<148, 256, 0, s>>>(prm, reinterpret_cast<uint16_t*>(img));
+    // 128-thread CTAs (4 K registers): they fit beside a resident decoder CTA (58 of the SM's 64 K registers), so the
+    // images for the backward are packed WHILE the forward decoders run instead of queueing for a free SM behind them
+    // (round 2 timeline: with 256-thread CTAs this branch ended 20 us after the forward and held up the compositing)
+    pack_q_kernel<KIND><<<(4 * Cfg<KIND>::H * 32 + 127) / 128, 128, 0, s>>>(prm, q);
+    pack_bwd_kernel<KIND><<<296, 128, 0, s>>>(prm, reinterpret_cast<uint16_t*>(img));
     return 0;
 }
 

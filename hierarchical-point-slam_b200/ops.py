@@ -57,6 +57,7 @@ TAIL_PRIORITY = int(os.environ.get("HPS_TAIL_PRIORITY", "0"))
 TAIL_AFTER_SCATTER = os.environ.get("HPS_TAIL_AFTER_SCATTER", "0") != "0"
 WGRAD_PRIORITY = int(os.environ.get("HPS_WGRAD_PRIORITY", "-2"))
 SCATTER_PRIORITY = int(os.environ.get("HPS_SCATTER_PRIORITY", "-1"))
+COLOR_DGRAD_PRIORITY = int(os.environ.get("HPS_COLOR_DGRAD_PRIORITY", "-1"))
 
 # NVTX ranges: HPS_NVTX=1 wraps every C-ABI call in a range named after the entry point (decoder
 # calls carry the decoder kind) and the fused render's forward / backward in "hps.render_rays.fwd/bwd"; nsys / ncu
@@ -937,9 +938,16 @@ class _RenderRays(torch.autograd.Function):
                     aff_head(side)
                 packed_col = side.record_event()
                 _mlp_pack(MLP_GEO, garr, dev, side)
+                # the loss's accumulators and exposure affine (two tiny kernels) on a stream of their own: in front of or
+                # behind the geometry decoder on the side stream they sat on the critical path (that kernel finishes last)
+                lh_s = None
+                if lm is not None:
+                    lh_s = _side_stream(dev, 8)
+                    lh_s.wait_stream(main)
+                    loss_head(lh_s)
                 aux = None
-                if bpk_c is not None:      # backward images on a third stream: nothing in the forward waits for them
-                    aux = _side_stream(dev, 1)
+                if bpk_c is not None:      # backward images on a third stream: nothing in the forward waits for them but
+                    aux = _side_stream(dev, 1)      # the compositing (it folds max |d raw| into the images' scale words)
                     aux.wait_stream(main)
                     _call("hps_mlp_tc_bwd_pack", MLP_COL, carr, _lib.ptr(bpk_c), _stream(aux))
                     _call("hps_mlp_tc_bwd_pack", MLP_GEO, garr, _lib.ptr(bpk_g), _stream(aux))
@@ -963,9 +971,9 @@ class _RenderRays(torch.autograd.Function):
                                     max_ctas=n_c)
                 sv_g = _mlp_forward(MLP_GEO, garr, pts, c_geo, None, P, occ, need_grad, dev, side, ws_g, packed=True,
                                     max_ctas=n_g)
-                if lm is not None:      # behind the geometry decoder, not in front of it: that kernel is on the critical
-                    loss_head(side)     # path, the loss's accumulators and exposure affine are needed after the join
                 main.wait_stream(side)
+                if lh_s is not None:
+                    main.wait_stream(lh_s)
                 if aux is not None:
                     main.wait_stream(aux)
             else:
@@ -1126,17 +1134,23 @@ class _RenderRays(torch.autograd.Function):
                 # tail work's CTAs for shared memory and thread slots)
                 w_c = _side_stream(dev, 5, priority=WGRAD_PRIORITY) if dcw is not None else None     # (no weight gradients: nothing to fork)
                 w_g = _side_stream(dev, 2, priority=WGRAD_PRIORITY) if dg is not None else None
-                _mlp_backward(MLP_COL, cprm, "tc", act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c, need_p, daff, dev, main,
+                # The colour dgrad kernel goes to a stream of higher priority than the geometry one's: its 98 CTAs own an
+                # SM each and must all be placed before the geometry kernel's 100 half-size CTAs (two per SM) take the rest
+                # - placed in the other order, the geometry CTAs spread one per SM and the colour kernel waits for them.
+                c_s = _side_stream(dev, 7, priority=COLOR_DGRAD_PRIORITY)
+                c_s.wait_stream(main)
+                _mlp_backward(MLP_COL, cprm, "tc", act_c, pts, c_col, aff, d_rgb, P, dcw, dc_c, need_p, daff, dev, c_s,
                               dp_c, packed=ctx.bwd_packed[1], absmax_done=folded, max_ctas=n_c, wgrad_stream=w_c, gscale=up)
                 e_s = None
                 if any(m_need):            # d affine is complete with the colour dgrad: the MLP's backward runs beside
                     e_s = _side_stream(dev, 3)                                      # the feature scatter
-                    e_s.wait_stream(main)
+                    e_s.wait_stream(c_s)
                     g_aff_mlp = _exposure_backward(ctx.aff_mlp_state[0], ctx.aff_mlp_state[1], daff, None, m_need,
                                                    ctx.aff_x_shape, e_s, zp.get(h_exp))
                 _mlp_backward(MLP_GEO, gprm, "tc", act_g, pts, c_geo, None, d_occ, P, dg, dc_g, need_p, None, dev, side,
                               dp_g, packed=ctx.bwd_packed[0], absmax_done=folded, max_ctas=n_g, wgrad_stream=w_g, gscale=up)
                 main.wait_stream(side)
+                main.wait_stream(c_s)
                 wgrad_streams = tuple(w for w in (w_c, w_g) if w is not None)
             else:
                 dp_g = _mlp_backward(MLP_GEO, gprm, ctx.saved_kinds[0], act_g, pts, c_geo, None, d_occ, P, dg, dc_g,
