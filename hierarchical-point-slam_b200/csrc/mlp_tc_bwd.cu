@@ -742,6 +742,7 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
         const uint32_t bytes = role == 5 ? (uint32_t)CH * (2 * HS + 3)
                                          : (uint32_t)CH * (2 * HS + (has_h ? 2 * HS : 0) + (has_e ? 2 * ES : 0) + (has_c ? 1 : 0));
         uint32_t it = 0;
+        const uint64_t l2pol = l2_policy_evict_first();       // the slabs are read exactly once
         for (int tile = rank; tile < num_tiles; tile += gsize) {
             const uint8_t* xg = W::x_ptr(const_cast<uint8_t*>(ws), tile);
             const uint8_t* gt = W::g_ptr(const_cast<uint8_t*>(ws), tile);
@@ -754,28 +755,28 @@ mlp_wgrad_tc_kernel(GradPtrs grd, const uint8_t* __restrict__ ws, int num_tiles,
                     mbar_expect_tx(&full[st], bytes);
                     if (role == 5) {
                         for (int j = 0; j < 2 * HS; ++j)      // y4 hi[HS], lo[HS] are consecutive X slabs
-                            bulk_g2s(sa + j * CH, xg + (size_t)(W::x_y(4, 0, 0) + j) * SLAB + q * CH, CH, &full[st]);
-                        bulk_g2s(sb, xg + (size_t)W::x_c() * SLAB + q * CH, CH, &full[st]);
-                        bulk_g2s(sb + CH, gt + (size_t)W::g_dr(0) * SLAB + q * CH, CH, &full[st]);
-                        bulk_g2s(sb + 2 * CH, gt + (size_t)W::g_dr(1) * SLAB + q * CH, CH, &full[st]);
+                            bulk_g2s_hint(sa + j * CH, xg + (size_t)(W::x_y(4, 0, 0) + j) * SLAB + q * CH, CH, &full[st], l2pol);
+                        bulk_g2s_hint(sb, xg + (size_t)W::x_c() * SLAB + q * CH, CH, &full[st], l2pol);
+                        bulk_g2s_hint(sb + CH, gt + (size_t)W::g_dr(0) * SLAB + q * CH, CH, &full[st], l2pol);
+                        bulk_g2s_hint(sb + 2 * CH, gt + (size_t)W::g_dr(1) * SLAB + q * CH, CH, &full[st], l2pol);
                     } else {
                         const uint8_t* gg = gt + (size_t)W::g_da(layer, 0, 0) * SLAB;
-                        for (int j = 0; j < 2 * HS; ++j) bulk_g2s(sa + j * CH, gg + (size_t)j * SLAB + q * CH, CH, &full[st]);
+                        for (int j = 0; j < 2 * HS; ++j) bulk_g2s_hint(sa + j * CH, gg + (size_t)j * SLAB + q * CH, CH, &full[st], l2pol);
                         if (has_h) {
                             for (int s2 = 0; s2 < HS; ++s2) {
-                                bulk_g2s(sb + s2 * CH, xg + (size_t)W::x_y(layer - 1, 0, s2) * SLAB + q * CH, CH, &full[st]);
-                                bulk_g2s(sb + (HS + ES + s2) * CH, xg + (size_t)W::x_y(layer - 1, 1, s2) * SLAB + q * CH, CH,
-                                         &full[st]);
+                                bulk_g2s_hint(sb + s2 * CH, xg + (size_t)W::x_y(layer - 1, 0, s2) * SLAB + q * CH, CH, &full[st], l2pol);
+                                bulk_g2s_hint(sb + (HS + ES + s2) * CH, xg + (size_t)W::x_y(layer - 1, 1, s2) * SLAB + q * CH, CH,
+                                         &full[st], l2pol);
                             }
                         }
                         if (has_e) {
                             for (int s2 = 0; s2 < ES; ++s2) {
-                                bulk_g2s(sb + (HS + s2) * CH, xg + (size_t)W::x_e(0, s2) * SLAB + q * CH, CH, &full[st]);
-                                bulk_g2s(sb + (2 * HS + ES + s2) * CH, xg + (size_t)W::x_e(1, s2) * SLAB + q * CH, CH,
-                                         &full[st]);
+                                bulk_g2s_hint(sb + (HS + s2) * CH, xg + (size_t)W::x_e(0, s2) * SLAB + q * CH, CH, &full[st], l2pol);
+                                bulk_g2s_hint(sb + (2 * HS + ES + s2) * CH, xg + (size_t)W::x_e(1, s2) * SLAB + q * CH, CH,
+                                         &full[st], l2pol);
                             }
                         }
-                        if (has_c) bulk_g2s(sb + 2 * (HS + ES) * CH, xg + (size_t)W::x_c() * SLAB + q * CH, CH, &full[st]);
+                        if (has_c) bulk_g2s_hint(sb + 2 * (HS + ES) * CH, xg + (size_t)W::x_c() * SLAB + q * CH, CH, &full[st], l2pol);
                     }
                 }
                 __syncwarp();

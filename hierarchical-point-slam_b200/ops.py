@@ -57,6 +57,7 @@ TAIL_PRIORITY = int(os.environ.get("HPS_TAIL_PRIORITY", "0"))
 TAIL_AFTER_SCATTER = os.environ.get("HPS_TAIL_AFTER_SCATTER", "0") != "0"
 WGRAD_PRIORITY = int(os.environ.get("HPS_WGRAD_PRIORITY", "-2"))
 SCATTER_PRIORITY = int(os.environ.get("HPS_SCATTER_PRIORITY", "-1"))
+SCATTER_STREAM_ALWAYS = os.environ.get("HPS_SCATTER_STREAM", "0") != "0"
 COLOR_DGRAD_PRIORITY = int(os.environ.get("HPS_COLOR_DGRAD_PRIORITY", "-1"))
 
 # NVTX ranges: HPS_NVTX=1 wraps every C-ABI call in a range named after the entry point (decoder
@@ -1181,7 +1182,7 @@ class _RenderRays(torch.autograd.Function):
                 # priority the tail's grid, launched first, is placed first and the scatter finished last (round 2).
                 # (only with an exchange hook: on one GPU nothing waits for the scatter and the plain order is 4 % faster)
                 sc_s = _side_stream(dev, 6, priority=SCATTER_PRIORITY) \
-                    if (fork and t_s is not None and spec.after_grads is not None) else None
+                    if (fork and t_s is not None and (spec.after_grads is not None or SCATTER_STREAM_ALWAYS)) else None
                 if sc_s is not None:
                     sc_s.wait_stream(main)
                 _call("hps_interp_bwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(w), _lib.ptr(has), _lib.ptr(pos),
