@@ -11,10 +11,12 @@ Weak scaling: every rank renders its own 5,000-ray shard of the global batch aga
 and the gradients are all-reduced (NCCL) - SURVEY 8e.
 
 Issue: one CUDA graph per iteration.  The parameter-free head of iteration i+1 (sampling + neighbour search of the
-NEXT ray batch, which a mapper draws independently of the parameters) is issued inside iteration i's graph on a side
-stream beside the HBM-bound tail of its backward (`tail_work` of Renderer.render_batch_ray_loss), so every timed step
-does one head and one rest - of consecutive iterations.  At N > 1 the iteration is two graphs (head | rest) and the
-all-reduce of step i overlaps the head of step i+1; the last one is timed on its own.
+NEXT ray batch, which a mapper draws independently of the parameters) is issued inside iteration i's graph: on one GPU
+beside the HBM-bound tail of its backward (`tail_work` of Renderer.render_batch_ray_loss), at N > 1 beside the gradient
+exchange - this package's peer-memory all-reduce kernel (hps_peer_allreduce over a symmetric gradient pool), which the
+backward issues itself once its last gradient is complete (`after_grads`).  Every timed step does one head and one rest,
+of consecutive iterations.  HPS_BENCH_EXCHANGE=nccl (and the fallback when symmetric memory is unavailable): round 1's
+scheme - two graphs (head | rest), NCCL all-reduce issued eagerly beside the next head, the last one timed on its own.
 
 JSON line: see the driver's contract; `value` = rays/s with inputs resident in HBM (CUDA-event timed per
 step, L2 flushed between steps), `e2e` = same through the public API from pinned host buffers (double-buffered H2D on a
@@ -235,7 +237,8 @@ def workload_config(n_gpus):
             "cloud_density": "extent_scale %.0f (~2.7k pts/m^2)" % EXTENT,
             "l2": "flushed between steps (256 MiB memset, untimed); %d distinct ray batches cycled" % N_BATCHES,
             "live_rows": "frustum-selected rows of the fine level are the optimised leaves (reference frustum_feature_selection)",
-            "parallelism": "rays sharded x%d, cloud replicated, gradient all-reduce (NCCL)" % n_gpus if n_gpus > 1 else "single GPU"}
+            "parallelism": "rays sharded x%d, cloud replicated, gradient all-reduce over NVLink (see `exchange`)" % n_gpus
+                           if n_gpus > 1 else "single GPU"}
 
 
 # --------------------------------------------------------------------------------------------------
