@@ -338,7 +338,7 @@ def run_ours(args, rank, world, local_rank):
         if os.environ.get("HPS_BENCH_EXCHANGE", "peer") == "peer":
             ok = 1
             try:
-                peer = hps.parallel.PeerGradExchange(2 * int(live_idx.numel()) * 32 + 1_000_000, dev, dist)
+                peer = hps.parallel.PeerGradExchange(2 * int(live_idx.numel()) * 32 + 1_000_000, dev, dist, zero_in_forward=True)
             except Exception as e:                                # pragma: no cover
                 ok = 0
                 log_err = "%s: %s" % (type(e).__name__, str(e).splitlines()[0][:160])

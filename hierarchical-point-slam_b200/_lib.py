@@ -25,6 +25,7 @@ SIGNATURES = {
     "hps_knn_query": (_i32, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i32, _vp]),
     "hps_interp_fwd": (_i32, [_vp] * 10 + [_i64, _i32] + [_vp] * 5),
     "hps_interp_bwd": (_i32, [_vp] * 11 + [_i64] + [_vp] * 5),
+    "hps_rows_store": (_i32, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _vp]),
     "hps_mlp_act_floats": (_i64, [_i32]),
     "hps_mlp_packed_floats": (_i64, [_i32]),
     "hps_mlp_pack": (_i32, [_i32, _vp, _vp, _vp]),
@@ -45,7 +46,7 @@ SIGNATURES = {
     "hps_composite_bwd": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _vp, _vp, _vp, _vp, _i32, _vp,
                                  _i32, _vp, _vp, _vp]),
     "hps_composite_mapper_loss": (_i32, [_vp, _i32, _vp, _i32, _vp, _vp, _i64, _i32, _f32, _i32, _vp, _vp, _vp, _vp,
-                                         _f32] + [_vp] * 13),
+                                         _f32] + [_vp] * 13 + [_i64, _vp]),
     "hps_camera_from_tensor": (_i32, [_vp, _vp, _vp]),
     "hps_camera_from_tensor_bwd": (_i32, [_vp, _vp, _vp, _vp]),
     "hps_rays_from_uv": (_i32, [_vp, _vp, _vp, _i32, _i64, _f32, _f32, _f32, _f32, _vp, _vp, _vp]),

@@ -210,9 +210,15 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
                              float* __restrict__ color_out, uint8_t* __restrict__ valid_ray,
                              float* __restrict__ loss, float* __restrict__ g_depth, float* __restrict__ g_color,
                              float* __restrict__ d_affine, float* __restrict__ d_rgb, float* __restrict__ d_occ,
-                             unsigned* __restrict__ amax_rgb, unsigned* __restrict__ amax_occ) {
+                             unsigned* __restrict__ amax_rgb, unsigned* __restrict__ amax_occ,
+                             float4* __restrict__ zero, int64_t zero_n4) {
     constexpr int RPW = 32 / G, NACC = 13;
     __shared__ float red[NACC][8];
+    __shared__ float red_max[2][8];
+    // the backward's gradient buffers are cleared here, beside the compositing (16 bytes per thread and round), instead
+    // of by a memset between the loss and the first dgrad kernel
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < zero_n4; i += (int64_t)gridDim.x * blockDim.x)
+        zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int sub = lane / G, s = lane % G;
@@ -220,6 +226,7 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
     float acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+    float mo = 0.f, mc = 0.f;          // max |d occ|, max |d rgb| of this warp's samples
     const bool use_aff = gt_color != nullptr && affine != nullptr;
     // rays of several keyframes in one batch (Mapper.py:805-822): frame[ray] selects the ray's exposure affine
     int f = 0, f_block = 0;
@@ -336,18 +343,18 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
                     d_rgb[i * 3 + 2] = v_b;
                 }
             }
-            float mo = fabsf(v_occ), mc = fmaxf(fabsf(v_r), fmaxf(fabsf(v_g), fabsf(v_b)));
+            mo = fabsf(v_occ), mc = fmaxf(fabsf(v_r), fmaxf(fabsf(v_g), fabsf(v_b)));
             mo = mo <= 3.0e38f ? mo : 0.f;
             mc = mc <= 3.0e38f ? mc : 0.f;
             for (int o = 16; o; o >>= 1) {
                 mo = fmaxf(mo, __shfl_xor_sync(kFull, mo, o));
                 mc = fmaxf(mc, __shfl_xor_sync(kFull, mc, o));
             }
-            if (lane == 0) {
-                if (amax_occ != nullptr && mo > 0.f) atomicMax(amax_occ, __float_as_uint(mo));
-                if (amax_rgb != nullptr && d_rgb != nullptr && mc > 0.f) atomicMax(amax_rgb, __float_as_uint(mc));
-            }
         }
+    }
+    if (d_occ != nullptr && lane == 0) {       // one atomicMax pair per BLOCK below (per warp: 2,500 on one L2 line)
+        red_max[0][wib] = mo;
+        red_max[1][wib] = mc;
     }
     int n_acc = (use_aff && d_affine != nullptr) ? NACC : 1;
     if (n_acc == NACC && !__syncthreads_and(f == f_block)) {
@@ -368,6 +375,13 @@ composite_mapper_loss_kernel(const float* __restrict__ rgb, int rgb_stride, cons
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[threadIdx.x][w];
         red_add(threadIdx.x == 0 ? loss : d_affine + 12 * (int64_t)f_block + (threadIdx.x - 1), t);
     }
+    if (d_occ != nullptr && (threadIdx.x == 32 || threadIdx.x == 64)) {
+        const int which = threadIdx.x == 32 ? 0 : 1;
+        float m = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red_max[which][w]);
+        unsigned* dst = which == 0 ? amax_occ : (d_rgb != nullptr ? amax_rgb : nullptr);
+        if (dst != nullptr && m > 0.f) atomicMax(dst, __float_as_uint(m));
+    }
 }
 
 }  // namespace hps
@@ -379,7 +393,7 @@ extern "C" int hps_composite_mapper_loss(const float* rgb, int rgb_stride, const
                                          float* var, float* color,
                                          uint8_t* valid_ray, float* loss, float* g_depth, float* g_color,
                                          float* d_affine, float* d_rgb, float* d_occ, uint32_t* absmax_rgb,
-                                         uint32_t* absmax_occ, void* stream) {
+                                         uint32_t* absmax_occ, float* zero, int64_t zero_floats, void* stream) {
     using namespace hps;
     HPS_REQUIRE(R >= 0 && S >= 1 && S <= 32, "need 1 <= S <= 32");
     if (R == 0) return 0;
@@ -387,16 +401,25 @@ extern "C" int hps_composite_mapper_loss(const float* rgb, int rgb_stride, const
     HPS_REQUIRE(gt_color == nullptr || (rgb != nullptr && g_color != nullptr), "colour term needs rgb and g_color");
     HPS_REQUIRE(affine == nullptr || d_affine != nullptr, "affine needs d_affine");
     HPS_REQUIRE(d_rgb == nullptr || (d_occ != nullptr && rgb != nullptr), "d_rgb needs d_occ and rgb");
+    HPS_REQUIRE(zero_floats >= 0 && zero_floats % 4 == 0 && (zero_floats == 0 || zero != nullptr) &&
+                    (reinterpret_cast<uintptr_t>(zero) & 15) == 0,
+                "zero: 16-byte aligned buffer of a multiple of 4 floats");
     const int tb = 256;
+    float4* const zero4 = reinterpret_cast<float4*>(zero);
+    const int64_t zero_n4 = zero_floats / 4;
+    HPS_SHARE_SM(composite_mapper_loss_kernel<8>);
+    HPS_SHARE_SM(composite_mapper_loss_kernel<32>);
     if (S <= 8) {
         const int64_t warps = ceil_div(R, 4);
         composite_mapper_loss_kernel<8><<<(unsigned)ceil_div(warps * 32, tb), tb, 0, (cudaStream_t)stream>>>(
             rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, min_valid, gt_depth, gt_color, affine, frame,
-            w_color, depth, var, color, valid_ray, loss, g_depth, g_color, d_affine, d_rgb, d_occ, absmax_rgb, absmax_occ);
+            w_color, depth, var, color, valid_ray, loss, g_depth, g_color, d_affine, d_rgb, d_occ, absmax_rgb, absmax_occ,
+            zero4, zero_n4);
     } else {
         composite_mapper_loss_kernel<32><<<(unsigned)ceil_div(R * 32, tb), tb, 0, (cudaStream_t)stream>>>(
             rgb, rgb_stride, occ, occ_stride, point_mask, z, R, S, coef, min_valid, gt_depth, gt_color, affine, frame,
-            w_color, depth, var, color, valid_ray, loss, g_depth, g_color, d_affine, d_rgb, d_occ, absmax_rgb, absmax_occ);
+            w_color, depth, var, color, valid_ray, loss, g_depth, g_color, d_affine, d_rgb, d_occ, absmax_rgb, absmax_occ,
+            zero4, zero_n4);
     }
     HPS_LAUNCH_OK();
     return 0;

@@ -199,6 +199,22 @@ interp_bwd_kernel(const float* __restrict__ p, const int32_t* __restrict__ I, co
     }
 }
 
+// table[idx[r]] = rows[r] for up to two (table, rows, idx) triples in one launch: the per-iteration write-back of the
+// optimised leaves into the full feature tables (Mapper.py:615-630).  Eight lanes move one 128-byte row as float4.
+__global__ void __launch_bounds__(256) rows_store_kernel(float4* __restrict__ ta, const float4* __restrict__ ra,
+                                                         const int64_t* __restrict__ ia, int64_t na,
+                                                         float4* __restrict__ tb, const float4* __restrict__ rb,
+                                                         const int64_t* __restrict__ ib, int64_t nb) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t row = t >> 3;
+    const int lane = (int)(t & 7);
+    if (row < na) {
+        ta[__ldg(ia + row) * (kC / 4) + lane] = __ldg(ra + row * (kC / 4) + lane);
+    } else if ((row -= na) < nb) {
+        tb[__ldg(ib + row) * (kC / 4) + lane] = __ldg(rb + row * (kC / 4) + lane);
+    }
+}
+
 }  // namespace hps
 
 extern "C" int hps_interp_fwd(const float* p, const int32_t* I, const float* D, const float* t_dn,
@@ -211,8 +227,24 @@ extern "C" int hps_interp_fwd(const float* p, const int32_t* I, const float* D, 
     HPS_REQUIRE(I && D && t_dn && count && feats_a && fill_a && w && c_a && has, "null buffer");
     HPS_REQUIRE(cloud_pos == nullptr || p != nullptr, "tracker variant needs p");
     HPS_REQUIRE(feats_b == nullptr || (fill_b && c_b), "second table needs fill_b and c_b");
+    HPS_SHARE_SM(interp_fwd_kernel);
     interp_fwd_kernel<<<(unsigned)ceil_div(P, kInterpWarps), kInterpWarps * 32, 0, (cudaStream_t)stream>>>(
         p, I, D, t_dn, count, cloud_pos, feats_a, feats_b, fill_a, fill_b, P, min_nn, w, c_a, c_b, has);
+    HPS_LAUNCH_OK();
+    return 0;
+}
+
+extern "C" int hps_rows_store(float* table_a, const float* rows_a, const int64_t* idx_a, int64_t n_a, float* table_b,
+                              const float* rows_b, const int64_t* idx_b, int64_t n_b, void* stream) {
+    using namespace hps;
+    HPS_REQUIRE(n_a >= 0 && n_b >= 0, "negative row count");
+    HPS_REQUIRE(n_a == 0 || (table_a && rows_a && idx_a), "null buffer (first table)");
+    HPS_REQUIRE(n_b == 0 || (table_b && rows_b && idx_b), "null buffer (second table)");
+    if (n_a + n_b == 0) return 0;
+    HPS_SHARE_SM(rows_store_kernel);
+    rows_store_kernel<<<(unsigned)ceil_div((n_a + n_b) * (kC / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4*>(table_a), reinterpret_cast<const float4*>(rows_a), idx_a, n_a,
+        reinterpret_cast<float4*>(table_b), reinterpret_cast<const float4*>(rows_b), idx_b, n_b);
     HPS_LAUNCH_OK();
     return 0;
 }

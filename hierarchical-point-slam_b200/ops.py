@@ -40,7 +40,7 @@ def _side_stream(dev, which=0, priority=0):
 
 # ---- instrumentation: kernel-launch counter and optional CUDA-event timers per C-ABI call -----------
 LAUNCHES = {"n": 0}
-_KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_grid_append": 3, "hps_knn_query": 1, "hps_sample_knn": 1, "hps_interp_fwd": 1, "hps_interp_bwd": 1,
+_KERNELS_PER_CALL = {"hps_grid_build": 6, "hps_grid_append": 3, "hps_knn_query": 1, "hps_sample_knn": 1, "hps_interp_fwd": 1, "hps_interp_bwd": 1, "hps_rows_store": 1,
                      "hps_mlp_pack": 1, "hps_mlp_fwd": 1, "hps_mlp_bwd": 1, "hps_mlp_tc_pack": 1, "hps_mlp_tc_fwd": 1,
                      "hps_mlp_tc_bwd_pack": 2, "hps_mlp_tc_bwd": 3, "hps_tc_selftest": 1, "hps_composite_fwd": 1,
                      "hps_composite_bwd": 1, "hps_composite_mapper_loss": 1, "hps_sample_rays": 1, "hps_sample_rays_bwd": 1, "hps_mapper_loss": 1,
@@ -50,13 +50,16 @@ TIMERS = None   # set to {} to record (start, end) CUDA events per call name on 
 
 
 # Scheduling of RenderSpec.tail_work (see _RenderRays._backward): stream priority and launch position.  Defaults from
-# scripts/tail_experiment.py on the B200 (round 2, mean of 60 flushed replays of the bench iteration): tail work at normal
-# priority in front of the feature scatter as ONE launch, weight-gradient streams at high priority: 0.2670 ms against
-# 0.2751 ms without any overlap; the other fifteen combinations lie between 0.2697 and 0.2806 ms.
-TAIL_PRIORITY = int(os.environ.get("HPS_TAIL_PRIORITY", "0"))
+# scripts/tail_experiment.py on the B200 (round 2, mean of 60 flushed replays of the bench iteration): tail work in front
+# of the feature scatter as ONE launch, weight-gradient streams at high priority: 0.2670 ms against 0.2751 ms without any
+# overlap; the other fifteen combinations lie between 0.2697 and 0.2806 ms.  The tail work's priority is one step ABOVE
+# the scatter's: both become ready at the same instant (the dgrad kernels' end) and inside a replayed graph their launch
+# order is the driver's choice, not the program's - at equal priority a change elsewhere in the graph flipped it, the
+# scatter's 3,125 CTAs were placed first and the search started 40 us late (0.265 vs 0.256 ms).
+TAIL_PRIORITY = int(os.environ.get("HPS_TAIL_PRIORITY", "-1"))
 TAIL_AFTER_SCATTER = os.environ.get("HPS_TAIL_AFTER_SCATTER", "0") != "0"
 WGRAD_PRIORITY = int(os.environ.get("HPS_WGRAD_PRIORITY", "-2"))
-SCATTER_PRIORITY = int(os.environ.get("HPS_SCATTER_PRIORITY", "-1"))
+SCATTER_PRIORITY = int(os.environ.get("HPS_SCATTER_PRIORITY", "-2"))      # (above the tail work where an exchange waits for it)
 SCATTER_STREAM_ALWAYS = os.environ.get("HPS_SCATTER_STREAM", "0") != "0"
 COLOR_DGRAD_PRIORITY = int(os.environ.get("HPS_COLOR_DGRAD_PRIORITY", "-1"))
 
@@ -119,27 +122,25 @@ class _ZeroPool:
     def want_like(self, tensors, skip_first):
         return [None if (skip_first and i == 0) else self.want(t.shape) for i, t in enumerate(tensors)]
 
-    def alloc(self, stream=None, into=None):
+    def alloc(self, stream=None, into=None, clear=True):
         """stream: issue the memset there (the caller orders it: that stream must already wait for the work that last
         touched the allocator's block, and the consumers must wait for that stream).  into: a GradPool whose tensor
-        provides the memory (e.g. a symmetric buffer the gradient exchange reduces in place) instead of the allocator."""
+        provides the memory (e.g. a symmetric buffer the gradient exchange reduces in place) instead of the allocator.
+        clear=False: the caller clears `flat` itself (total is a multiple of 4 floats, flat is 16-byte aligned)."""
+        n = max(self.total, 4)
         if into is not None:
-            if into.tensor.numel() < self.total or into.tensor.dtype != torch.float32 or not into.tensor.is_contiguous():
-                raise _lib.HpsError("grad_buffer: need %d contiguous fp32 elements, got %d" % (self.total, into.tensor.numel()))
-            self.flat = into.tensor[:max(self.total, 1)]
+            if into.tensor.numel() < n or into.tensor.dtype != torch.float32 or not into.tensor.is_contiguous():
+                raise _lib.HpsError("grad_buffer: need %d contiguous fp32 elements, got %d" % (n, into.tensor.numel()))
+            self.flat = into.tensor[:n]
             into.used = self.total
+        else:
+            self.flat = torch.empty(n, dtype=torch.float32, device=self.device)
+        if clear:
             if stream is None:
                 self.flat.zero_()
             else:
                 with torch.cuda.stream(stream):
                     self.flat.zero_()
-            return self
-        if stream is None:
-            self.flat = torch.zeros(max(self.total, 1), dtype=torch.float32, device=self.device)
-        else:
-            self.flat = torch.empty(max(self.total, 1), dtype=torch.float32, device=self.device)
-            with torch.cuda.stream(stream):
-                self.flat.zero_()
         return self
 
     def get(self, h):
@@ -155,10 +156,14 @@ class GradPool:
     """Caller-owned memory for the gradients of one fused backward (RenderSpec.grad_buffer): `tensor` is a contiguous
     fp32 buffer, `used` the number of leading floats the last backward laid its gradients out in (every .grad of that
     backward is a view of tensor[:used]).  With a symmetric-memory tensor (parallel.PeerAllReduce.buffer) the multi-GPU
-    exchange sums the gradients where backward wrote them."""
+    exchange sums the gradients where backward wrote them.
+    zero_in_forward=True lets the FORWARD of a training iteration clear the buffer (its compositing kernel does it on the
+    side, which takes the memset out of the backward's critical path): only for callers that are done with the previous
+    iteration's gradients before they render again with parameters that require grad (forward -> backward -> exchange ->
+    optimiser step -> forward ...); the default leaves them alone until the next backward."""
 
-    def __init__(self, tensor):
-        self.tensor, self.used = tensor, 0
+    def __init__(self, tensor, zero_in_forward=False):
+        self.tensor, self.used, self.zero_in_forward = tensor, 0, bool(zero_in_forward)
 
 
 def _zero_grads_like(tensors, skip_first):
@@ -361,6 +366,7 @@ def _packed_buffer(kind, device, tc=False):
 
 # Compositing backward inside the fused compositing + mapper-loss kernel of the forward pass (HPS_FUSE_COMPOSITE_BWD=0:
 # the separate hps_composite_bwd launch at the head of the backward).
+ZERO_IN_COMPOSITE = os.environ.get("HPS_ZERO_IN_COMPOSITE", "1") != "0"   # gradient buffers cleared by the compositing kernel
 FUSE_COMPOSITE_BWD = os.environ.get("HPS_FUSE_COMPOSITE_BWD", "1") != "0"
 
 # True: the backward also runs on tensor cores (dgrad chain + streaming wgrad kernels); False: fp32 SIMT backward.
@@ -640,6 +646,23 @@ class LiveRows:
             return
         with torch.no_grad():
             self.table.index_copy_(0, self.indices, self.param)
+
+    @staticmethod
+    def refresh_pair(a, b, stream=None):
+        """refresh() of up to two LiveRows (either may be None) as ONE launch (hps_rows_store) instead of one torch
+        index_copy_ each: the write-back sits at the head of every iteration's critical path."""
+        todo = [r for r in (a, b) if r is not None and not r.fresh]
+        if not todo:
+            return
+        for r in todo:
+            _need_cuda(r.table, r.param)
+            if r.table.shape[1] != C_DIM or not r.param.is_contiguous():
+                raise _lib.HpsError("LiveRows: (M,%d) contiguous fp32 leaves expected" % C_DIM)
+        x, y = todo[0], (todo[1] if len(todo) > 1 else None)
+        with torch.cuda.device(x.table.device):
+            _call("hps_rows_store", _lib.ptr(x.table), _lib.ptr(x.param), _lib.ptr(x.indices), x.indices.numel(),
+                  _lib.ptr(y.table) if y else None, _lib.ptr(y.param) if y else None,
+                  _lib.ptr(y.indices) if y else None, y.indices.numel() if y else 0, _stream(stream))
 
     def dense(self):
         """Differentiable (N,32) view for code paths that want a plain tensor (reference semantics)."""
@@ -927,11 +950,7 @@ class _RenderRays(torch.autograd.Function):
                 side.wait_stream(main)
                 refreshed = None
                 if spec.live_geo is not None or spec.live_col is not None:
-                    with torch.cuda.stream(side):     # table[live rows] = leaves, off the critical path
-                        if spec.live_geo is not None:
-                            spec.live_geo.refresh()
-                        if spec.live_col is not None:
-                            spec.live_col.refresh()
+                    LiveRows.refresh_pair(spec.live_geo, spec.live_col, side)     # table[live rows] = leaves, one launch
                     refreshed = side.record_event()
                 # forward images first (the decoders wait for them), the backward images afterwards
                 _mlp_pack(MLP_COL, carr, dev, side)
@@ -1005,9 +1024,18 @@ class _RenderRays(torch.autograd.Function):
                 # backward then starts with the decoders' dgrad kernels (gscale = the real upstream gradient)
                 fuse_bwd = (FUSE_COMPOSITE_BWD and fork and need_grad and bpk_g is not None and bpk_c is not None
                             and aff is None and not spec.tracker)
+                zpool = None
                 if fuse_bwd:
                     d_occ_f = torch.empty(P, **f32)
                     d_rgb_f = torch.empty(P, 3, **f32) if spec.color_stage else None
+                    if ZERO_IN_COMPOSITE and (spec.grad_buffer is None or spec.grad_buffer.zero_in_forward):
+                        # the backward's gradient buffers, laid out now and cleared by the compositing kernel on the side:
+                        # no memset (and no stream hop) between the loss and the first dgrad kernel
+                        zpool = _RenderRays._plan_pool(
+                            spec, ctx.needs_input_grad, gprm, cprm, aff,
+                            feats_geo.shape[0] if row_map is not None else fg.shape[0], P, dev, eprm, mprm, sv_g[0])
+                        zpool[0].alloc(into=spec.grad_buffer, clear=False)
+                        ctx.zeroed_pool = zpool
                 _call("hps_composite_mapper_loss", _lib.ptr(rgb), 3, _lib.ptr(occ), 1, _lib.ptr(has), _lib.ptr(z), R, S,
                       float(spec.coef), int(spec.min_valid), _lib.ptr(gd), _lib.ptr(gtc), _lib.ptr(aff_l),
                       _lib.ptr(frm_l), lm.w_color, _lib.ptr(depth), _lib.ptr(var), _lib.ptr(color), _lib.ptr(valid),
@@ -1015,11 +1043,15 @@ class _RenderRays(torch.autograd.Function):
                       _lib.ptr(flat[4:]) if aff_l is not None else None,
                       _lib.ptr(d_rgb_f) if fuse_bwd else None, _lib.ptr(d_occ_f) if fuse_bwd else None,
                       _absmax_word(MLP_COL, bpk_c) if (fuse_bwd and d_rgb_f is not None) else None,
-                      _absmax_word(MLP_GEO, bpk_g) if fuse_bwd else None, st())
+                      _absmax_word(MLP_GEO, bpk_g) if fuse_bwd else None,
+                      _lib.ptr(zpool[0].flat) if zpool is not None else None,
+                      (zpool[0].total + 3) // 4 * 4 if zpool is not None else 0, st())
                 if fuse_bwd:
                     ctx.fused_d_raw = (d_occ_f, d_rgb_f)
         if not hasattr(ctx, "fused_d_raw"):
             ctx.fused_d_raw = None
+        if not hasattr(ctx, "zeroed_pool"):
+            ctx.zeroed_pool = None
         ctx.loss_state = None if lm is None else (flat, a1_l, eprm, color_loss, head, n_aff, aff_in_shape)
         ctx.aff_mlp_state = (mprm, a1_d) if mprm else None
         ctx.spec = spec
@@ -1033,6 +1065,34 @@ class _RenderRays(torch.autograd.Function):
             return flat[0], depth, var, color, valid
         ctx.mark_non_differentiable(var, valid)
         return depth, var, color, valid
+
+    @staticmethod
+    def _plan_pool(spec, need, gprm, cprm, aff, n_rows, P, dev, l_eprm, mprm, geo_kind):
+        """Layout of every zero-initialised buffer of the backward inside ONE allocation (_ZeroPool, not yet allocated)
+        and the handles: (dg, dcw, daff, dfg, dfc, exposure, dp_geo, dp_col).  Depends only on shapes and on which
+        inputs want a gradient (l_eprm / mprm: the loss-side / decoder-side exposure MLP's tensors or nothing; n_rows:
+        rows of the feature gradients), so the forward of a training iteration can lay it out ahead of the backward."""
+        zp = _ZeroPool(dev)
+        want_gw = any(need[7 + i] for i in range(1, N_PARAM))
+        want_cw = spec.color_stage and any(need[7 + N_PARAM + i] for i in range(1, N_PARAM))
+        need_p = spec.tracker and (need[1] or need[2])
+        h_dg = zp.want_like(gprm, skip_first=not need[7]) if want_gw else None
+        h_dcw = zp.want_like(cprm, skip_first=True) if want_cw else None   # colour _B is not a parameter
+        m_need = need[7 + len(gprm) + len(cprm):] if mprm else ()
+        h_daff = zp.want((12,)) if (aff is not None and (need[6] or any(m_need))) else None
+        h_dfg = zp.want((n_rows, C_DIM)) if need[4] else None
+        h_dfc = zp.want((n_rows, C_DIM)) if (spec.color_stage and need[5]) else None
+        tc_dp = need_p and geo_kind == "tc"
+        # the exposure MLP's gradients (loss-side or decoder-side) come out of the same allocation, so that a caller-owned
+        # grad_buffer holds EVERY gradient of the iteration (one exchange, nothing left outside)
+        h_exp = None
+        if l_eprm and any(need[7 + len(gprm) + len(cprm):]):
+            h_exp = zp.want((_exposure_grad_floats(l_eprm),))
+        elif mprm and any(m_need):
+            h_exp = zp.want((_exposure_grad_floats(mprm),))
+        h_dpg = zp.want((P, 3)) if tc_dp else None                          # accumulated by the dgrad kernels
+        h_dpc = zp.want((P, 3)) if (tc_dp and spec.color_stage) else None
+        return zp, (h_dg, h_dcw, h_daff, h_dfg, h_dfc, h_exp, h_dpg, h_dpc)
 
     @staticmethod
     def backward(ctx, *gouts):
@@ -1075,38 +1135,33 @@ class _RenderRays(torch.autograd.Function):
             d_rgb = torch.empty(P, 3, **f32) if spec.color_stage else None
         dc_g = torch.empty(P, C_DIM, **f32)
         dc_c = torch.empty(P, C_DIM, **f32) if spec.color_stage else None
-        want_gw = any(need[7 + i] for i in range(1, N_PARAM))
-        want_cw = spec.color_stage and any(need[7 + N_PARAM + i] for i in range(1, N_PARAM))
         fork = MULTI_STREAM and TIMERS is None and spec.color_stage and ctx.saved_kinds == ("tc", "tc")
         if fused_raw is not None and not fork:
             raise _lib.HpsError("the forward fused the compositing backward but the backward is not on the multi-stream "
                                 "tensor-core path (HPS_STREAMS / TIMERS changed between forward and backward?)")
-        # every zero-initialised buffer of the backward comes out of one allocation = one memset kernel
-        zp = _ZeroPool(dev)
-        h_dg = zp.want_like(gprm, skip_first=not need[7]) if want_gw else None
-        h_dcw = zp.want_like(cprm, skip_first=True) if want_cw else None   # colour _B is not a parameter
         m_need = need[7 + len(gprm) + len(cprm):] if ctx.aff_mlp_state is not None else ()
-        h_daff = zp.want((12,)) if (aff is not None and (need[6] or any(m_need))) else None
-        n_rows = ctx.n_live if ctx.row_map is not None else fg.shape[0]
-        h_dfg = zp.want((n_rows, C_DIM)) if need[4] else None
-        h_dfc = zp.want((n_rows, C_DIM)) if (spec.color_stage and need[5]) else None
-        tc_dp = need_p and ctx.saved_kinds[0] == "tc"
-        # the exposure MLP's gradients (loss-side or decoder-side) come out of the same allocation, so that a caller-owned
-        # grad_buffer holds EVERY gradient of the iteration (one exchange, nothing left outside)
-        h_exp = None
-        if ctx.loss_state is not None and l_eprm and any(need[7 + len(gprm) + len(cprm):]):
-            h_exp = zp.want((_exposure_grad_floats(l_eprm),))
-        elif ctx.aff_mlp_state is not None and any(m_need):
-            h_exp = zp.want((_exposure_grad_floats(ctx.aff_mlp_state[0]),))
-        h_dpg = zp.want((P, 3)) if tc_dp else None                          # accumulated by the dgrad kernels
-        h_dpc = zp.want((P, 3)) if (tc_dp and spec.color_stage) else None
-        with torch.cuda.device(dev):
-            if fork:        # the memset runs beside the compositing backward instead of in front of it
+        # every zero-initialised buffer of the backward comes out of one allocation, cleared by one memset kernel - or,
+        # in a training iteration on the fused path, by the forward's compositing kernel already (ctx.zeroed_pool).
+        # (Clearing it at the START of the forward, beside the decoders, was tried in round 2: the iteration gets 4-10 us
+        # SLOWER - by the time the scatter and the weight-gradient kernels add into the buffer the decoders' 100 MB of
+        # workspace writes have pushed the zero lines out of L2, and every red.add fetches from DRAM.)
+        ready, ctx.zeroed_pool = ctx.zeroed_pool, None
+        if ready is not None:
+            zp, (h_dg, h_dcw, h_daff, h_dfg, h_dfc, h_exp, h_dpg, h_dpc) = ready
+            if fork:
                 main, side = torch.cuda.current_stream(dev), _side_stream(dev)
-                side.wait_stream(main)
-                zp.alloc(side, into=spec.grad_buffer)
-            else:
-                zp.alloc(into=spec.grad_buffer)
+        else:
+            zp, (h_dg, h_dcw, h_daff, h_dfg, h_dfc, h_exp, h_dpg, h_dpc) = _RenderRays._plan_pool(
+                spec, need, gprm, cprm, aff, ctx.n_live if ctx.row_map is not None else fg.shape[0], P, dev,
+                ctx.loss_state[2] if ctx.loss_state is not None else None,
+                ctx.aff_mlp_state[0] if ctx.aff_mlp_state is not None else None, ctx.saved_kinds[0])
+            with torch.cuda.device(dev):
+                if fork:        # the memset runs beside the compositing backward instead of in front of it
+                    main, side = torch.cuda.current_stream(dev), _side_stream(dev)
+                    side.wait_stream(main)
+                    zp.alloc(side, into=spec.grad_buffer)
+                else:
+                    zp.alloc(into=spec.grad_buffer)
         dg, dcw, daff = zp.get(h_dg), zp.get(h_dcw), zp.get(h_daff)
         dfg, dfc = zp.get(h_dfg), zp.get(h_dfc)
         dp_i = torch.empty(P, 3, **f32) if need_p else None
@@ -1123,10 +1178,19 @@ class _RenderRays(torch.autograd.Function):
             up = gscale if fused_raw is not None else None      # d raw was written for an upstream gradient of 1
             dp_c = None
             wgrad_streams = ()
+            x_s = g_exp_early = None
             if fork:
                 dp_g, dp_c = zp.get(h_dpg), zp.get(h_dpc)
                 main.wait_stream(side)          # the zeroed buffers
                 side.wait_stream(main)
+                if ctx.loss_state is not None and l_eprm:
+                    # exposure MLP backward from d loss / d affine (accumulated by the forward's fused loss kernel): it
+                    # depends on nothing in this backward, so it goes first on a stream of its own - at the end of the
+                    # main stream (round 2 timeline) its single CTA was the last 5 us of the iteration
+                    x_s = _side_stream(dev, 3)
+                    x_s.wait_stream(main)
+                    g_exp_early = _exposure_backward(l_eprm, l_a1, l_flat[4:], gscale, need[7 + len(gprm) + len(cprm):],
+                                                     ctx.exp_x_shape, x_s, zp.get(h_exp))
                 n_c, n_g = _sm_split(P, "bwd")
                 # the HBM-bound weight-gradient kernels go to streams of their own: the feature scatter below needs
                 # only dc of both decoders and overlaps with them
@@ -1208,10 +1272,12 @@ class _RenderRays(torch.autograd.Function):
                 # the loss-side affine was an input: its gradient, scaled by the upstream gradient (main stream has slack)
                 g_exp = ((l_flat[4:4 + l_naff] * gscale).view(l_aff_shape) if need[7 + len(gprm) + len(cprm)] else None,)
             if ctx.loss_state is not None and l_eprm:
-                # exposure MLP backward from d loss / d affine (accumulated by the fused loss kernel); the main stream
-                # has slack here - the weight-gradient kernels on their own streams finish later
-                g_exp = _exposure_backward(l_eprm, l_a1, l_flat[4:], gscale, need[7 + len(gprm) + len(cprm):],
-                                           ctx.exp_x_shape, None, zp.get(h_exp))
+                if x_s is not None:
+                    g_exp = g_exp_early
+                    main.wait_stream(x_s)
+                else:
+                    g_exp = _exposure_backward(l_eprm, l_a1, l_flat[4:], gscale, need[7 + len(gprm) + len(cprm):],
+                                               ctx.exp_x_shape, None, zp.get(h_exp))
             if ctx.aff_mlp_state is not None:
                 g_exp = g_aff_mlp if any(m_need) else (None,) * 5
                 if e_s is not None:

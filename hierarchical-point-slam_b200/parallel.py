@@ -217,10 +217,10 @@ class PeerGradExchange:
     plain kernel launch: it can sit inside the iteration's CUDA graph.  capacity_floats: an upper bound of what one
     backward needs (live rows x 32 x tables + decoder parameters + padding); every rank must run the same code path."""
 
-    def __init__(self, capacity_floats, device, dist, group=None):
+    def __init__(self, capacity_floats, device, dist, group=None, zero_in_forward=False):
         from .ops import GradPool
         self.peer = PeerAllReduce(capacity_floats, device, dist, group)
-        self.pool = GradPool(self.peer.buffer)
+        self.pool = GradPool(self.peer.buffer, zero_in_forward)     # (see GradPool for what that asks of the caller)
         # The exchange kernel spends its time waiting for peers, and its 192 small CTAs must not queue behind the grid of
         # whatever runs beside it (the next batch's neighbour search: 3,125 CTAs at the same priority pushed the
         # exchange to the end of the step, round 2 measurement): its own stream, highest priority.

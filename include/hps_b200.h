@@ -89,6 +89,13 @@ int hps_interp_bwd(const float* p, const int32_t* I, const float* w, const uint8
                    const float* dc_a, const float* dc_b, int64_t P,
                    float* dfeats_a, float* dfeats_b, float* dp, const int32_t* row_map, void* stream);
 
+/* table[idx[r]] = rows[r] (32 floats per row) for up to two tables in ONE launch: the per-iteration write-back of the
+ * optimised leaves into the full feature tables, `self.npc.update_geo_feats(geo_feats, indices=indices)` +
+ * `update_col_feats` - Mapper.py:615-630 (neural_point.py:149-181).  idx_*: int64 table rows, no duplicates;
+ * either triple may be empty (n == 0, pointers NULL).                                                            */
+int hps_rows_store(float* table_a, const float* rows_a, const int64_t* idx_a, int64_t n_a,
+                   float* table_b, const float* rows_b, const int64_t* idx_b, int64_t n_b, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Decoder MLPs (decoder.py:274-342 MLP_geometry.forward, :561-618 MLP_color.forward; K3).
  *   params: HOST array of HPS_MLP_NPARAM device pointers in the reference's own layouts
@@ -187,7 +194,9 @@ int hps_composite_bwd(const float* rgb, int rgb_stride, const float* occ, int oc
  * d_occ (R*S), d_rgb (R*S,3) (may be NULL): additionally the compositing BACKWARD for an upstream gradient of 1 -
  * d loss / d occ, d loss / d rgb, what hps_composite_bwd would write from g_depth / g_color - with max |.| reduced
  * into absmax_occ / absmax_rgb (may be NULL); pass them as `dout` of hps_mlp_tc_bwd with its gscale = the upstream
- * gradient and the separate compositing-backward launch between the decoders' forward and backward is gone.      */
+ * gradient and the separate compositing-backward launch between the decoders' forward and backward is gone.
+ * zero / zero_floats (may be NULL / 0; 16-byte aligned, a multiple of 4 floats): a buffer this launch clears on the
+ * side - the gradient buffers of the backward that follows (no memset between the loss and the first dgrad kernel). */
 int hps_composite_mapper_loss(const float* rgb, int rgb_stride, const float* occ, int occ_stride,
                               const uint8_t* point_mask, const float* z, int64_t R, int S, float coef,
                               int min_valid, const float* gt_depth, const float* gt_color /* may be NULL */,
@@ -195,7 +204,7 @@ int hps_composite_mapper_loss(const float* rgb, int rgb_stride, const float* occ
                               float w_color, float* depth, float* var,
                               float* color, uint8_t* valid_ray, float* loss, float* g_depth, float* g_color,
                               float* d_affine, float* d_rgb, float* d_occ, uint32_t* absmax_rgb, uint32_t* absmax_occ,
-                              void* stream);
+                              float* zero, int64_t zero_floats, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Adam over the live (frustum-selected) rows of a feature table, fused with the write-back into the table

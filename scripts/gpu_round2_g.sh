@@ -1,0 +1,22 @@
+#!/bin/bash
+mkdir -p gpurun_out
+export HPS_TAIL_PRIORITY=-1
+HPS_TIMELINE_REPS=3 timeout 200 python scripts/step_timeline.py > gpurun_out/g_timeline_zero.txt 2> gpurun_out/g_err1.txt
+HPS_ZERO_IN_COMPOSITE=0 HPS_TIMELINE_REPS=3 timeout 200 python scripts/step_timeline.py > gpurun_out/g_timeline_nozero.txt 2> gpurun_out/g_err2.txt
+run() {  # name, env...
+    name=$1; shift
+    env "$@" timeout 300 python bench.py --no-extras --steps 200 --warmup 10 > gpurun_out/g_$name.json 2> gpurun_out/g_$name.err
+    python - "$name" <<'PY'
+import json, sys
+try:
+    d = json.loads(open("gpurun_out/g_%s.json" % sys.argv[1]).read().strip().splitlines()[-1])
+    print(sys.argv[1], "%.4f ms" % d["ms_per_step"], "sustained %.3f M" % (d["sustained"]["value"] / 1e6), "e2e %.3f M" % (d["e2e"]["value"] / 1e6), d["parity"].get("ok"))
+except Exception as e:
+    print(sys.argv[1], "unreadable", e)
+PY
+}
+run zero X=1
+run nozero HPS_ZERO_IN_COMPOSITE=0
+run zero2 X=1
+run nozero2 HPS_ZERO_IN_COMPOSITE=0
+grep span gpurun_out/g_timeline_*.txt

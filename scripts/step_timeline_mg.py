@@ -19,7 +19,7 @@ dev = "cuda:%d" % lr
 dist.init_process_group("nccl", device_id=torch.device(dev))
 hps = importlib.import_module("hierarchical-point-slam_b200")
 wl = bench.build_workload(hps, dev)
-peer = hps.parallel.PeerGradExchange(2 * int(wl.live_idx.numel()) * 32 + 1_000_000, torch.device(dev), dist)
+peer = hps.parallel.PeerGradExchange(2 * int(wl.live_idx.numel()) * 32 + 1_000_000, torch.device(dev), dist, zero_in_forward=True)
 slots = [bench._batch_on_device(wl, (2 * rank + b) % bench.N_BATCHES) for b in (0, 1)]
 prep = [None, None]
 ef = wl.scene["exposure_feat"].to(dev)

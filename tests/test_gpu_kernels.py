@@ -771,3 +771,34 @@ def test_point_insertion_appends_in_place(hps):
     else:
         assert npc.storage_generation("fine") != gen
     assert torch.equal(npc.get_geo_feats("fine")[:5], row0)
+
+
+def test_live_rows_write_back_in_one_launch(hps):
+    """LiveRows.refresh_pair (hps_rows_store: table[idx] = leaves for both feature tables in one launch, the per-iteration
+    write-back of Mapper.py:615-630) against torch's index_copy_, bit for bit: two tables with different row sets, one
+    table alone, rows already fresh (RowAdam owns the write-back) skipped, an empty row set."""
+    torch.manual_seed(11)
+    N, C = 40_000, 32
+    ta, tb = torch.randn(N, C, device=DEV), torch.randn(N, C, device=DEV)
+    ia, ib = torch.randperm(N, device=DEV)[:11_419], torch.randperm(N, device=DEV)[:777]
+    a, b = hps.LiveRows(ta.clone(), ia), hps.LiveRows(tb.clone(), ib)
+    with torch.no_grad():
+        a.param.copy_(torch.randn_like(a.param))
+        b.param.copy_(torch.randn_like(b.param))
+    want_a = ta.clone().index_copy_(0, ia, a.param.detach())
+    want_b = tb.clone().index_copy_(0, ib, b.param.detach())
+    hps.LiveRows.refresh_pair(a, b)
+    assert torch.equal(a.table, want_a) and torch.equal(b.table, want_b)
+    # one table alone / the other one fresh: untouched
+    with torch.no_grad():
+        a.param.mul_(2.0)
+        b.param.mul_(2.0)
+    b.fresh = True
+    hps.LiveRows.refresh_pair(a, b)
+    assert torch.equal(a.table, ta.clone().index_copy_(0, ia, a.param.detach())) and torch.equal(b.table, want_b)
+    b.fresh = False
+    hps.LiveRows.refresh_pair(None, b)
+    assert torch.equal(b.table, tb.clone().index_copy_(0, ib, b.param.detach()))
+    e = hps.LiveRows(tb.clone(), torch.empty(0, dtype=torch.long, device=DEV))
+    hps.LiveRows.refresh_pair(e, None)
+    assert torch.equal(e.table, tb)
