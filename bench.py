@@ -244,7 +244,8 @@ def workload_config(n_gpus):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
-HEAD_AT = os.environ.get("HPS_BENCH_HEAD_AT", "exchange")      # N > 1: next head beside the "exchange" or the backward "tail"
+HEAD_AT = os.environ.get("HPS_BENCH_HEAD_AT", "tail")      # N > 1: next head beside the backward "tail" or the "exchange"
+SPLIT_EXCHANGE = os.environ.get("HPS_BENCH_SPLIT_EXCHANGE", "0") != "0"   # N > 1: feature gradients exchanged behind the scatter (measured: slower)
 OVERLAP_HEAD = os.environ.get("HPS_BENCH_OVERLAP", "1") != "0"   # N = 1: next iteration's head beside this one's tail
 
 
@@ -348,7 +349,10 @@ def run_ours(args, rank, world, local_rank):
             if not int(flag):
                 peer = None
             else:
-                exchange_kind = "hps_peer_allreduce (%s) inside the iteration's graph" % peer.peer.default_variant()
+                exchange_kind = "hps_peer_allreduce (%s) inside the iteration's graph%s, next head beside the %s" % (
+                    peer.peer.default_variant(),
+                    ": feature gradients behind the scatter, the rest behind the weight gradients" if SPLIT_EXCHANGE else "",
+                    "backward tail" if HEAD_AT == "tail" else "exchange")
     wl.peer = peer
     overlap = OVERLAP_HEAD and (world == 1 or peer is not None)
     static_pk = [torch.empty_like(dev_pk[0]) for _ in range(2 if overlap else 1)]
@@ -375,8 +379,10 @@ def run_ours(args, rank, world, local_rank):
                 npc_geo_feats=gf, npc_col_feats=cf, cloud_pos=pos, dynamic_r_query=rq(k), exposure_feat=exposure_feat,
                 prepared=prepared, tail_work=tail if (peer is None or HEAD_AT == "tail") else None,
                 grad_buffer=peer.pool if peer is not None else None,
-                # N > 1: the peer-memory all-reduce, issued inside backward once every gradient is complete, with the
-                # next batch's head beside it (on one GPU the head goes beside the backward's tail instead: tail_work)
+                # N > 1: the peer-memory all-reduce inside backward - the feature-table gradients (85 % of the bytes) right
+                # behind the scatter, beside the weight-gradient kernels, the rest once every gradient is complete; the next
+                # batch's head beside the backward's tail as on one GPU (HPS_BENCH_HEAD_AT=exchange: beside the exchange)
+                after_feature_grads=peer.features if (peer is not None and SPLIT_EXCHANGE) else None,
                 after_grads=(lambda: peer(beside=tail if HEAD_AT != "tail" else None)) if peer is not None else None)
             loss = out[0]
         else:               # the reference's seams: render_batch_ray, then the loss (HPS_BENCH_FUSED_LOSS=0)

@@ -407,8 +407,6 @@ extern "C" int hps_composite_mapper_loss(const float* rgb, int rgb_stride, const
     const int tb = 256;
     float4* const zero4 = reinterpret_cast<float4*>(zero);
     const int64_t zero_n4 = zero_floats / 4;
-    HPS_SHARE_SM(composite_mapper_loss_kernel<8>);
-    HPS_SHARE_SM(composite_mapper_loss_kernel<32>);
     if (S <= 8) {
         const int64_t warps = ceil_div(R, 4);
         composite_mapper_loss_kernel<8><<<(unsigned)ceil_div(warps * 32, tb), tb, 0, (cudaStream_t)stream>>>(

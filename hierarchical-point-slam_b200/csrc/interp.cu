@@ -227,7 +227,6 @@ extern "C" int hps_interp_fwd(const float* p, const int32_t* I, const float* D, 
     HPS_REQUIRE(I && D && t_dn && count && feats_a && fill_a && w && c_a && has, "null buffer");
     HPS_REQUIRE(cloud_pos == nullptr || p != nullptr, "tracker variant needs p");
     HPS_REQUIRE(feats_b == nullptr || (fill_b && c_b), "second table needs fill_b and c_b");
-    HPS_SHARE_SM(interp_fwd_kernel);
     interp_fwd_kernel<<<(unsigned)ceil_div(P, kInterpWarps), kInterpWarps * 32, 0, (cudaStream_t)stream>>>(
         p, I, D, t_dn, count, cloud_pos, feats_a, feats_b, fill_a, fill_b, P, min_nn, w, c_a, c_b, has);
     HPS_LAUNCH_OK();
@@ -241,7 +240,6 @@ extern "C" int hps_rows_store(float* table_a, const float* rows_a, const int64_t
     HPS_REQUIRE(n_a == 0 || (table_a && rows_a && idx_a), "null buffer (first table)");
     HPS_REQUIRE(n_b == 0 || (table_b && rows_b && idx_b), "null buffer (second table)");
     if (n_a + n_b == 0) return 0;
-    HPS_SHARE_SM(rows_store_kernel);
     rows_store_kernel<<<(unsigned)ceil_div((n_a + n_b) * (kC / 4), 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<float4*>(table_a), reinterpret_cast<const float4*>(rows_a), idx_a, n_a,
         reinterpret_cast<float4*>(table_b), reinterpret_cast<const float4*>(rows_b), idx_b, n_b);

@@ -274,7 +274,6 @@ extern "C" int hps_exposure_fwd(const float* x, const float* W1, const float* b1
     HPS_REQUIRE(n_in >= 1 && n_in <= 64 && hidden >= 1 && hidden <= 1024 && n_out >= 1 && n_out <= 32, "exposure MLP size");
     HPS_REQUIRE(x && W1 && b1 && W2 && b2 && a1 && out, "null buffer");
     const int tb = (max(hidden, 32) + 31) / 32 * 32;
-    HPS_SHARE_SM(exposure_fwd_kernel);
     exposure_fwd_kernel<<<1, tb, hidden * sizeof(float), (cudaStream_t)stream>>>(x, W1, b1, W2, b2, n_in, hidden, n_out, a1,
                                                                               out);
     HPS_LAUNCH_OK();
@@ -288,7 +287,7 @@ extern "C" int hps_exposure_bwd(const float* x, const float* W1, const float* W2
     HPS_REQUIRE(n_in >= 1 && n_in <= 64 && hidden >= 1 && hidden <= 1024 && n_out >= 1 && n_out <= 32, "exposure MLP size");
     HPS_REQUIRE(x && W1 && W2 && a1 && dout && dW1 && db1 && dW2 && db2, "null buffer");
     const int tb = (max(hidden, 32) + 31) / 32 * 32;
-    HPS_SHARE_SM(exposure_bwd_kernel);
+    HPS_SHARE_SM(exposure_bwd_kernel);      // (it is issued beside the decoders' dgrad kernels and the backward tail)
     exposure_bwd_kernel<<<1, tb, hidden * sizeof(float), (cudaStream_t)stream>>>(x, W1, W2, a1, dout, gscale, n_in, hidden,
                                                                               n_out, dW1, db1, dW2, db2, dx);
     HPS_LAUNCH_OK();

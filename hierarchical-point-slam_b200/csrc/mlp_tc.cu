@@ -496,7 +496,6 @@ mlp_fwd_tc_kernel(Ptrs prm, const uint8_t* __restrict__ wimg, const float* __res
 template <int KIND> int launch_pack(const float* const* params, void* img, cudaStream_t s) {
     Ptrs prm;
     for (int i = 0; i < HPS_MLP_NPARAM; ++i) prm.v[i] = params[i];
-    HPS_SHARE_SM(pack_tc_kernel<KIND>);
     pack_tc_kernel<KIND><<<148, 256, 0, s>>>(prm, reinterpret_cast<uint16_t*>(img));
     return 0;
 }

@@ -989,8 +989,6 @@ template <int KIND> int launch_pack_bwd(const float* const* params, void* img, c
     // 128-thread CTAs (4 K registers): they fit beside a resident decoder CTA (58 of the SM's 64 K registers), so the
     // images for the backward are packed WHILE the forward decoders run instead of queueing for a free SM behind them
     // (round 2 timeline: with 256-thread CTAs this branch ended 20 us after the forward and held up the compositing)
-    HPS_SHARE_SM(pack_q_kernel<KIND>);
-    HPS_SHARE_SM(pack_bwd_kernel<KIND>);
     pack_q_kernel<KIND><<<(4 * Cfg<KIND>::H * 32 + 127) / 128, 128, 0, s>>>(prm, q);
     pack_bwd_kernel<KIND><<<296, 128, 0, s>>>(prm, reinterpret_cast<uint16_t*>(img));
     return 0;
@@ -1036,7 +1034,6 @@ int launch_bwd(const float* const* params, const void* img, void* ws, const floa
     if (!absmax_done) {
         const int64_t n = P * Cfg<KIND>::NOUT;
         const int nb = (int)(ceil_div(n, 1024) < kNumSMs ? ceil_div(n, 1024) : kNumSMs);
-        HPS_SHARE_SM(absmax_kernel);
         absmax_kernel<<<nb, 1024, 0, s>>>(dout, n, maxbits);
     }
     mlp_dgrad_tc_kernel<KIND><<<grid, NTHR, GB::SMEM_BYTES, s>>>(

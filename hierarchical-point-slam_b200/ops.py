@@ -110,6 +110,7 @@ class _ZeroPool:
 
     def __init__(self, device):
         self.device, self.total, self.reqs, self.flat = device, 0, [], None
+        self.features = 0       # floats of the leading feature-table gradients (see _RenderRays._plan_pool)
 
     def want(self, shape):
         n = 1
@@ -132,7 +133,7 @@ class _ZeroPool:
             if into.tensor.numel() < n or into.tensor.dtype != torch.float32 or not into.tensor.is_contiguous():
                 raise _lib.HpsError("grad_buffer: need %d contiguous fp32 elements, got %d" % (n, into.tensor.numel()))
             self.flat = into.tensor[:n]
-            into.used = self.total
+            into.used, into.features = self.total, self.features
         else:
             self.flat = torch.empty(n, dtype=torch.float32, device=self.device)
         if clear:
@@ -164,6 +165,7 @@ class GradPool:
 
     def __init__(self, tensor, zero_in_forward=False):
         self.tensor, self.used, self.zero_in_forward = tensor, 0, bool(zero_in_forward)
+        self.features = 0       # tensor[:features]: the feature-table gradients (complete first), tensor[features:used]: the rest
 
 
 def _zero_grads_like(tensors, skip_first):
@@ -751,7 +753,7 @@ class RenderSpec:
     """Non-tensor arguments of render_rays (one per call)."""
     __slots__ = ("grid", "radius", "z_zero", "S", "near", "far", "coef", "min_nn", "min_valid", "color_stage",
                  "tracker", "cloud_pos", "fill_geo", "fill_col", "live_geo", "live_col", "prep", "loss", "aff_mlp",
-                 "tail_work", "grad_buffer", "after_grads")
+                 "tail_work", "grad_buffer", "after_grads", "after_feature_grads")
 
     def __init__(self, **kw):
         for k in self.__slots__:
@@ -1076,12 +1078,15 @@ class _RenderRays(torch.autograd.Function):
         want_gw = any(need[7 + i] for i in range(1, N_PARAM))
         want_cw = spec.color_stage and any(need[7 + N_PARAM + i] for i in range(1, N_PARAM))
         need_p = spec.tracker and (need[1] or need[2])
+        # the feature-table gradients lead: they are complete with the scatter, long before the decoders' weight gradients,
+        # and a multi-GPU exchange can take that prefix early (GradPool.features, RenderSpec.after_feature_grads)
+        h_dfg = zp.want((n_rows, C_DIM)) if need[4] else None
+        h_dfc = zp.want((n_rows, C_DIM)) if (spec.color_stage and need[5]) else None
+        zp.features = zp.total
         h_dg = zp.want_like(gprm, skip_first=not need[7]) if want_gw else None
         h_dcw = zp.want_like(cprm, skip_first=True) if want_cw else None   # colour _B is not a parameter
         m_need = need[7 + len(gprm) + len(cprm):] if mprm else ()
         h_daff = zp.want((12,)) if (aff is not None and (need[6] or any(m_need))) else None
-        h_dfg = zp.want((n_rows, C_DIM)) if need[4] else None
-        h_dfc = zp.want((n_rows, C_DIM)) if (spec.color_stage and need[5]) else None
         tc_dp = need_p and geo_kind == "tc"
         # the exposure MLP's gradients (loss-side or decoder-side) come out of the same allocation, so that a caller-owned
         # grad_buffer holds EVERY gradient of the iteration (one exchange, nothing left outside)
@@ -1252,6 +1257,14 @@ class _RenderRays(torch.autograd.Function):
                 _call("hps_interp_bwd", _lib.ptr(pts), _lib.ptr(I), _lib.ptr(w), _lib.ptr(has), _lib.ptr(pos),
                       _lib.ptr(fg), _lib.ptr(fc), _lib.ptr(c_geo), _lib.ptr(c_col), _lib.ptr(dc_g), _lib.ptr(dc_c), P,
                       _lib.ptr(dfg), _lib.ptr(dfc), _lib.ptr(dp_i), _lib.ptr(ctx.row_map), st(sc_s))
+                if spec.after_feature_grads is not None:
+                    # the feature-table gradients (the bulk of what a multi-GPU exchange moves) are complete HERE, while
+                    # the weight-gradient kernels still run: the caller's hook can put them on the wire now
+                    if sc_s is not None:
+                        with torch.cuda.stream(sc_s):
+                            spec.after_feature_grads()
+                    else:
+                        spec.after_feature_grads()
                 if sc_s is not None:
                     main.wait_stream(sc_s)
             if spec.tail_work is not None and TAIL_AFTER_SCATTER:

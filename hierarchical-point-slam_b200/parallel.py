@@ -176,6 +176,7 @@ class PeerAllReduce:
         self._bufs = (ctypes.c_void_p * self.world)(*[int(p) for p in hb.buffer_ptrs])
         self._pads = (ctypes.c_void_p * self.world)(*[int(p) for p in hp.buffer_ptrs])
         self.multicast_ptr = int(getattr(hb, "multicast_ptr", 0) or 0)
+        self._shift_cache = {}
         dist.barrier(group)                 # every pad is zeroed before anybody raises a flag
 
     def variants(self):
@@ -194,20 +195,31 @@ class PeerAllReduce:
         if st:
             raise self._lib.HpsError("PeerAllReduce: a peer did not arrive within 2 s (status %d); the sums are invalid" % st)
 
-    def __call__(self, variant=None, n_floats=None):
-        """Sum the first n_floats (default: all) of every rank's buffer in place.  variant: "multimem" (NVLS; the
-        default when the buffer has a multicast address) or "p2p"."""
+    def __call__(self, variant=None, n_floats=None, offset_floats=0):
+        """Sum floats [offset_floats, offset_floats + n_floats) (default: all) of every rank's buffer in place.  variant:
+        "multimem" (NVLS; the default when the buffer has a multicast address) or "p2p".  offset_floats: a multiple of 4
+        (the kernel is handed the shifted peer addresses)."""
         from .ops import _call, _stream
         if variant is None:
             variant = self.default_variant()
-        n = self.n if n_floats is None else (int(n_floats) + 3) // 4 * 4
-        if n > self.n:
-            raise self._lib.HpsError("PeerAllReduce: %d floats asked, the buffer holds %d" % (n, self.n))
-        mc = ctypes.c_void_p(self.multicast_ptr) if variant == "multimem" else None
+        off = int(offset_floats)
+        n = self.n - off if n_floats is None else (int(n_floats) + 3) // 4 * 4
+        if off < 0 or off % 4 or n < 0 or off + n > self.n:
+            raise self._lib.HpsError("PeerAllReduce: floats [%d, %d) asked (offset must be a multiple of 4), the buffer "
+                                     "holds %d" % (off, off + n, self.n))
         if variant == "multimem" and not self.multicast_ptr:
             raise self._lib.HpsError("PeerAllReduce: no multicast address (NVLS) on this fabric")
+        mc = ctypes.c_void_p(self.multicast_ptr + 4 * off) if variant == "multimem" else None
+        bufs = self._bufs if off == 0 else self._shifted(off)
         with torch.cuda.device(self.buffer.device):
-            _call("hps_peer_allreduce", self._bufs, self._pads, mc, self.rank, self.world, n, _stream())
+            _call("hps_peer_allreduce", bufs, self._pads, mc, self.rank, self.world, n, _stream())
+
+    def _shifted(self, off):
+        tab = self._shift_cache.get(off)
+        if tab is None:
+            tab = (ctypes.c_void_p * self.world)(*[int(p) + 4 * off for p in self._handles[0].buffer_ptrs])
+            self._shift_cache[off] = tab
+        return tab
 
 
 class PeerGradExchange:
@@ -226,6 +238,18 @@ class PeerGradExchange:
         # exchange to the end of the step, round 2 measurement): its own stream, highest priority.
         self.stream = torch.cuda.Stream(device=device, priority=-5)
         self.side = torch.cuda.Stream(device=device)
+        self._features_sent = 0
+
+    def features(self, variant=None):
+        """The early half (RenderSpec.after_feature_grads): sums pool.tensor[:pool.features] - the feature-table gradients,
+        complete behind the scatter - on the exchange's stream while the backward goes on; the next __call__ then only
+        moves the rest and joins both.  Every rank must take the same path."""
+        n = self.pool.features
+        if n:
+            self.stream.wait_stream(torch.cuda.current_stream(self.peer.buffer.device))
+            with torch.cuda.stream(self.stream):
+                self.peer(variant, n_floats=n)
+        self._features_sent = n
 
     def __call__(self, variant=None, beside=None):
         """Issued from the current stream: the exchange waits for it, runs on the high-priority stream, and the current
@@ -234,10 +258,12 @@ class PeerGradExchange:
         search): the exchange is latency-bound (~35 us of cross-GPU barriers for 3.4 MB), the search issue-bound, so the
         two share the GPU well; the exchange is launched first so that its 192 CTAs are placed before the search's grid."""
         cur = torch.cuda.current_stream(self.peer.buffer.device)
+        sent, self._features_sent = self._features_sent, 0
         if self.pool.used:
             self.stream.wait_stream(cur)
             with torch.cuda.stream(self.stream):
-                self.peer(variant, n_floats=self.pool.used)
+                if self.pool.used > sent:
+                    self.peer(variant, n_floats=self.pool.used - sent, offset_floats=sent)
         if beside is not None:
             self.side.wait_stream(cur)
             with torch.cuda.stream(self.side):

@@ -145,7 +145,7 @@ class Renderer(object):
     def render_batch_ray(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth=None,
                          npc_geo_feats=None, npc_col_feats=None, is_tracker=False, cloud_pos=None,
                          normals=None, dynamic_r_query=None, exposure_feat=None, prepared=None, _loss=None,
-                         _z_zero_rows=None, tail_work=None, grad_buffer=None, after_grads=None):
+                         _z_zero_rows=None, tail_work=None, grad_buffer=None, after_grads=None, after_feature_grads=None):
         """One fused kernel sequence (ops.render_rays): sampling, exact neighbour search, interpolation of both
         feature tables from one neighbour list, both decoders, compositing with the -100 overwrite.
         `prepared` (not in the reference): the ops.RayPrep of prepare_batch() for these very rays."""
@@ -199,7 +199,8 @@ class Renderer(object):
             min_nn=geo.min_nn_num, min_valid=int(S / 2 + 1), color_stage=color_stage, tracker=bool(is_tracker),
             cloud_pos=cloud_pos[level] if is_tracker else None, fill_geo=decoders._fill("geo", rays_o.device),
             fill_col=decoders._fill("col", rays_o.device) if color_stage else None, prep=prepared,
-            aff_mlp=aff_prm is not None, tail_work=tail_work, grad_buffer=grad_buffer, after_grads=after_grads)
+            aff_mlp=aff_prm is not None, tail_work=tail_work, grad_buffer=grad_buffer, after_grads=after_grads,
+            after_feature_grads=after_feature_grads)
         loss = None
         if _loss is not None and _loss[0] == "tracker":
             _, gt_color, w_color, reduce_fn = _loss
@@ -244,7 +245,7 @@ class Renderer(object):
     def render_batch_ray_loss(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth, gt_color, w_color_loss,
                               npc_geo_feats=None, npc_col_feats=None, cloud_pos=None, dynamic_r_query=None,
                               exposure_feat=None, prepared=None, affine=None, frame_index=None, tail_work=None,
-                              grad_buffer=None, after_grads=None):
+                              grad_buffer=None, after_grads=None, after_feature_grads=None):
         """One mapper iteration's forward as ONE autograd node (not in the reference, which spells it out in
         Mapper.py:783-856): render_batch_ray(..., exposure_feat=None) followed by
             mask = (gt_depth > 0) & valid & ~isnan(depth)
@@ -264,11 +265,16 @@ class Renderer(object):
         grad_buffer: an ops.GradPool - every gradient of loss.backward() is laid out in its tensor (zeroed first) instead
         of a fresh allocation; with parallel.PeerGradExchange's pool the multi-GPU exchange sums them in place.
         after_grads: a callable issued on the main stream inside loss.backward() once every gradient is complete and before
-        tail_work is joined - the place for that exchange (`after_grads=exchange`), which then runs beside the tail work."""
+        tail_work is joined - the place for that exchange (`after_grads=exchange`), which then runs beside the tail work.
+        after_feature_grads: a callable issued inside loss.backward() right behind the feature scatter, i.e. when the
+        feature-table gradients (grad_buffer.tensor[:grad_buffer.features], 85 % of the exchange's bytes) are complete and
+        the decoders' weight-gradient kernels still run (`after_feature_grads=exchange.features`: that part of the exchange
+        is then off the critical path and `exchange()` in after_grads only moves the rest)."""
         return self.render_batch_ray(npc, decoders, rays_d, rays_o, device, stage, gt_depth=gt_depth,
                                      npc_geo_feats=npc_geo_feats, npc_col_feats=npc_col_feats, is_tracker=False,
                                      cloud_pos=cloud_pos, dynamic_r_query=dynamic_r_query, exposure_feat=None,
                                      prepared=prepared, tail_work=tail_work, grad_buffer=grad_buffer, after_grads=after_grads,
+                                     after_feature_grads=after_feature_grads,
                                      _loss=("mapper", gt_color, w_color_loss, exposure_feat, affine, frame_index))
 
     def render_batch_ray_tracker_loss(self, npc, decoders, rays_d, rays_o, device, stage, gt_depth, gt_color,

@@ -40,7 +40,10 @@ def step(k):
     loss = wl.renderer.render_batch_ray_loss(
         wl.npc, wl.dec, b["rays_d"], b["rays_o"], dev, bench.STAGE, b["gt_depth"], b["gt_color"], 0.1,
         npc_geo_feats=wl.gf, npc_col_feats=wl.cf, cloud_pos=wl.pos, dynamic_r_query={"fine": b["radius"], "mid": b["radius_mid"]},
-        exposure_feat=ef, prepared=prep[k], grad_buffer=peer.pool, after_grads=lambda: peer(beside=lambda: head(1 - k)))[0]
+        exposure_feat=ef, prepared=prep[k], grad_buffer=peer.pool,
+        tail_work=(lambda: head(1 - k)) if bench.HEAD_AT == "tail" else None,
+        after_feature_grads=peer.features if bench.SPLIT_EXCHANGE else None,
+        after_grads=lambda: peer(beside=(lambda: head(1 - k)) if bench.HEAD_AT != "tail" else None))[0]
     loss.backward()
     return loss
 
@@ -54,7 +57,7 @@ torch.cuda.synchronize()
 dist.barrier()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    for i in range(4):
+    for i in range(6):
         graphs[i % 2].graph.replay()
     torch.cuda.synchronize()
 peer.check()
@@ -62,10 +65,10 @@ if rank == 0:
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     evs = sorted({(e.time_range.start, e.time_range.end, e.name, getattr(e, "device_resource_id", -1)) for e in evs})
     t0 = evs[0][0]
-    print("# rank 0 of %d: four back-to-back replays (rest of iteration i + head of i+1 + peer exchange)" % world)
+    print("# rank 0 of %d: six back-to-back replays (rest of iteration i + head of i+1 + peer exchange)" % world)
     print("%9s %8s %4s  %s" % ("start_us", "dur_us", "strm", "kernel"))
     for s0, s1, name, strm in evs:
         print("%9.1f %8.1f %4s  %s" % (s0 - t0, s1 - s0, strm, name[:100]))
-    print("span %.1f us for 4 iterations" % (max(e[1] for e in evs) - t0))
+    print("span %.1f us for 6 iterations" % (max(e[1] for e in evs) - t0))
 dist.barrier()
 dist.destroy_process_group()
