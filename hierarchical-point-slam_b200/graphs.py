@@ -19,7 +19,7 @@ class GraphedStep:
     memory.  Pass `guard` = a callable returning a value that changes when that happens - e.g.
     `lambda: npc.storage_generation(level)` - and replay raises instead; re-capture (build a new GraphedStep) then."""
 
-    def __init__(self, fn, static_inputs, warmup=3, before_capture=None, guard=None, dump_dot=None):
+    def __init__(self, fn, static_inputs, warmup=3, before_capture=None, guard=None):
         self.fn = fn
         self.static = static_inputs
         self.guard = guard
@@ -33,12 +33,8 @@ class GraphedStep:
         if before_capture is not None:
             before_capture()
         self.graph = torch.cuda.CUDAGraph()
-        if dump_dot is not None:
-            self.graph.enable_debug_mode()
         with torch.cuda.graph(self.graph):
             self.outputs = fn()
-        if dump_dot is not None:           # nodes and dependency edges as captured (cudaGraphDebugDotPrint)
-            self.graph.debug_dump(dump_dot)
         self._guard_value = guard() if guard is not None else None
         del out
 

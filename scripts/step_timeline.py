@@ -45,8 +45,7 @@ def step(k, prepared=None, tail=None):
 if bench.OVERLAP_HEAD:
     head(0)
     head(1)
-    graphs = [hps.graphs.GraphedStep(lambda k=k: step(k, prep[k], tail=lambda: head(1 - k)), {}, warmup=3,
-                                     dump_dot=os.environ.get("HPS_GRAPH_DOT") if k == 0 else None) for k in (0, 1)]
+    graphs = [hps.graphs.GraphedStep(lambda k=k: step(k, prep[k], tail=lambda: head(1 - k)), {}, warmup=3) for k in (0, 1)]
 else:
     graphs = [hps.graphs.GraphedStep(lambda: step(0), {}, warmup=3)] * 2
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -919,6 +919,20 @@ def _peer_worker(rank, world, port, out):
             res[(variant, n_used)] = (float((ex.buffer[:n_used] - ref[:n_used]).abs().max() / ref.abs().max()),
                                       bool(torch.equal(ex.buffer[n_used:], mine[n_used:])))
             dist.barrier()
+        # a sub-range (the early exchange of the feature-table gradients / the rest behind it): floats in front of and
+        # behind it stay as they were
+        for off, n_used in ((4096, 20_000), (n - 4000, 4000)):
+            ex.buffer.copy_(mine)
+            dist.barrier()
+            ex(variant, n_floats=n_used, offset_floats=off)
+            torch.cuda.synchronize()
+            ex.check()
+            keep = torch.ones(n, dtype=torch.bool, device=dev)
+            keep[off:off + n_used] = False
+            res[(variant, "range", off)] = (
+                float((ex.buffer[off:off + n_used] - ref[off:off + n_used]).abs().max() / ref.abs().max()),
+                bool(torch.equal(ex.buffer[keep], mine[keep])))
+            dist.barrier()
         # bit-identical on every rank (the owner of a slice computes its sums once and broadcasts them)
         ex.buffer.copy_(mine)
         dist.barrier()
@@ -927,6 +941,25 @@ def _peer_worker(rank, world, port, out):
         gathered = [torch.empty_like(ex.buffer) for _ in range(world)]
         dist.all_gather(gathered, ex.buffer.clone())
         res[(variant, "identical")] = all(torch.equal(gathered[0], t) for t in gathered)
+    # PeerGradExchange in two halves (features() behind the scatter, the rest from after_grads) = the exchange in one
+    gx = hps.parallel.PeerGradExchange(n, dev, dist)
+    mine = torch.randn(n, generator=g, device=dev)
+    ref = mine.clone()
+    dist.all_reduce(ref)
+    used, feats = 300_000, 262_144
+    for split in (False, True):
+        gx.pool.tensor.copy_(mine)
+        gx.pool.used, gx.pool.features = used, feats
+        dist.barrier()
+        if split:
+            gx.features()
+        gx()
+        torch.cuda.synchronize()
+        gx.check()
+        res[("grad_exchange", "split" if split else "single")] = (
+            float((gx.pool.tensor[:used] - ref[:used]).abs().max() / ref.abs().max()),
+            bool(torch.equal(gx.pool.tensor[used:], mine[used:])))
+        dist.barrier()
     if rank == 0:
         torch.save(res, out)
     dist.barrier()
