@@ -283,10 +283,20 @@ __global__ void grid_append_scatter_kernel(const float* __restrict__ pos, int64_
 // query
 // ------------------------------------------------------------------------------------------------
 constexpr int kQueryWarps = 8;     // warps (= queries in flight) per CTA
-constexpr int kStageCells = 128;   // voxel ranges staged in shared memory per pass and warp (a ball's bounding cube is
-                                   // <= 5^3 = 125 voxels at the host layer's voxel edge; larger cubes take more passes).
-                                   // 13 KB per CTA: search CTAs fit beside a 185 KB weight-gradient CTA (the mapper
-                                   // iteration runs the next batch's search beside this batch's backward tail)
+// Shared memory and registers of the search CTA are sized for what runs BESIDE it: the mapper iteration issues the next
+// batch's search beside this batch's backward tail, where a weight-gradient CTA holds 186 KB of the SM's 228 KB of shared
+// memory and 18 K of its 64 K registers.  64 staged voxel ranges per pass and warp (9 KB per CTA; a fine-level ball's
+// bounding cube is 27-64 voxels, the mid level's up to 125 = two passes) and 40 registers (launch bound 6 CTAs per SM,
+// 40 bytes of spills) put FOUR search CTAs beside a weight-gradient CTA instead of three: the iteration 0.2515 -> 0.2475
+// ms, the search alone 44.8 -> 46.0 us, the mid level unchanged (163-167 us); 128 ranges / 5 CTAs: -DHPS_KNN_STAGE_CELLS=128
+// -DHPS_KNN_CTAS_PER_SM=5.
+#ifndef HPS_KNN_STAGE_CELLS
+#define HPS_KNN_STAGE_CELLS 64
+#endif
+#ifndef HPS_KNN_CTAS_PER_SM
+#define HPS_KNN_CTAS_PER_SM 6
+#endif
+constexpr int kStageCells = HPS_KNN_STAGE_CELLS;
 
 struct GridView {
     const float4* sorted;
@@ -344,7 +354,7 @@ __device__ __forceinline__ unsigned long long merge_top8(unsigned long long best
 // RAYS: the queries are the sample points of rays and are computed here (sample_point.cuh) instead of being read -
 // the warp also writes z / point / thresholds for the kernels downstream, which saves the sampling launch.
 template <int G, bool RAYS>
-__global__ void __launch_bounds__(kQueryWarps * 32, G == 1 ? 5 : 4)      // G = 1: 48 registers, so that four CTAs fit beside a weight-gradient CTA (16 K of the 64 K registers); G = 5 would take 80 otherwise
+__global__ void __launch_bounds__(kQueryWarps * 32, G == 1 ? HPS_KNN_CTAS_PER_SM : 4)      // G = 1: 40 registers (see kStageCells above); G = 5 would take 80 otherwise
 knn_query_kernel(GridView g, const float* __restrict__ q, const float* __restrict__ t_up,
                  const float* __restrict__ t_dn, int64_t nq, int32_t* __restrict__ I, float* __restrict__ D,
                  int32_t* __restrict__ count, int32_t* __restrict__ cand, const RaySource src,
