@@ -1,5 +1,5 @@
 #!/bin/bash
-# A/B of neighbour-search build variants (hierarchical-point-slam_b200/build/variants/libhps_<v>.so) on one box
+# A/B of neighbour-search build variants on one box (build them first, here: scripts/build_knn_variants.sh A:64:6 C:128:6)
 mkdir -p gpurun_out
 L=hierarchical-point-slam_b200/libhps_b200.so
 cp $L /tmp/libhps_base.so
