@@ -487,6 +487,68 @@ def strong_scaling(hps, wl, bench, rank, world, dist, steps):
                     % ("hps_peer_allreduce inside the rest graph" if peer is not None else "NCCL beside the next head")}
 
 
+def mapping_with_optimizer(hps, wl, bench, steps):
+    """The bench's mapper iteration INCLUDING the optimiser step (Mapper.py:783-860: zero_grad, render, loss, backward,
+    optimizer.step with the stage's learning rates) - MapperOptimizer: RowAdam over the live rows of both fine tables fused
+    with their write-back + one FusedAdam launch for decoders and exposure latent - captured like the bench's step (the next
+    batch's head beside the backward tail), replayed back to back.  Parameters are restored afterwards."""
+    dev, npc, dec, renderer = wl.dev, wl.npc, wl.dec, wl.renderer
+    used = list(dec.geo_decoder_fine.parameters()) + list(dec.color_decoder_fine.parameters())
+    ef = wl.scene["exposure_feat"].to(dev).clone().requires_grad_(True)
+    owned = [wl.lg.param, wl.lc.param] + used
+    keep = [t.detach().clone() for t in owned]
+    mo = hps.MapperOptimizer(wl.cfg["mapping"], decoder_params=used, rows={"geometry_fine": wl.lg, "color_fine": wl.lc},
+                             exposure_feat=ef)
+    mo.set_learning_rates(hps.mapper_optim.stage_learning_rates(wl.cfg["mapping"], bench.STAGE))
+    slots = [bench._batch_on_device(wl, b) for b in (0, 1)]
+    prep = [None, None]
+
+    def head(k):
+        b = slots[k]
+        prep[k] = renderer.prepare_batch(npc, b["rays_d"], b["rays_o"], bench.STAGE, b["gt_depth"],
+                                         {"fine": b["radius"], "mid": b["radius_mid"]}, out=prep[k])
+        return prep[k].cnt
+
+    def step(k):
+        mo.zero_grad()
+        b = slots[k]
+        loss = renderer.render_batch_ray_loss(
+            npc, dec, b["rays_d"], b["rays_o"], dev, bench.STAGE, b["gt_depth"], b["gt_color"], 0.1, npc_geo_feats=wl.gf,
+            npc_col_feats=wl.cf, cloud_pos=wl.pos, dynamic_r_query={"fine": b["radius"], "mid": b["radius_mid"]},
+            exposure_feat=ef, prepared=prep[k], tail_work=lambda: head(1 - k))[0]
+        loss.backward()
+        mo.step()
+        return loss
+
+    try:
+        head(0)
+        head(1)
+        graphs = [hps.graphs.GraphedStep(lambda k=k: step(k), {}, warmup=3) for k in (0, 1)]
+        for i in range(4):
+            graphs[i % 2].graph.replay()
+        torch.cuda.synchronize()
+        first = float(graphs[0].outputs.detach())      # (batch 0 after 5 optimiser steps on alternating batches)
+        a, b = _events()
+        a.record()
+        for i in range(steps):
+            graphs[i % 2].graph.replay()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        last = float(graphs[(steps - 1) % 2].outputs.detach())
+    finally:
+        with torch.no_grad():
+            for t, k in zip(owned, keep):
+                t.copy_(k)
+                t.grad = None
+        wl.lg.fresh = wl.lc.fresh = False          # the next render writes the restored leaves back into the tables
+    return {"ms_per_step": ms, "value": bench.RAYS / (ms * 1e-3), "unit": "rays/s", "steps": steps,
+            "iterations_per_s": 1e3 / ms, "loss_batch0_after_5_steps": first, "loss_last": last,
+            "note": "zero_grad + render + loss + backward + MapperOptimizer.step() (RowAdam on %d live rows x 2 tables fused "
+                    "with the table write-back, FusedAdam on the fine decoders + exposure latent) from one CUDA graph per "
+                    "iteration, back to back, no L2 flush: compare with `sustained`" % int(wl.live_idx.numel())}
+
+
 def run(hps, wl, args, rank, world, dist):
     bench = importlib.import_module("bench")
     out = {}
@@ -505,6 +567,11 @@ def run(hps, wl, args, rank, world, dist):
             out["single_frame"] = single_frame(hps, wl, bench)
         except Exception as e:                                           # noqa: BLE001
             out["single_frame"] = _err(e)
+    if world == 1 and want("mapping_with_optimizer"):
+        try:
+            out["mapping_with_optimizer"] = mapping_with_optimizer(hps, wl, bench, max(20, min(4 * args.steps, 400)))
+        except Exception as e:                                           # noqa: BLE001
+            out["mapping_with_optimizer"] = _err(e)
     if want("strong_scaling"):
         try:
             out["strong_scaling"] = strong_scaling(hps, wl, bench, rank, world, dist, max(10, min(args.steps, 100)))
