@@ -105,6 +105,7 @@ def test_c_abi_empty_inputs_and_argument_checks_without_a_gpu(hps):
     assert lib.hps_adam_rows(N, N, N, N, 0, 32, 1e-3, 0.9, 0.999, 1e-8, N, N, N, N) == 0
     assert lib.hps_adam_multi(0, N, N, N, N, N, N, 0.9, 0.999, 1e-8, N, 0, N) == 0
     assert lib.hps_adam_multi_own_steps(0, N, N, N, N, N, N, N, 0.9, 0.999, 1e-8, N, 0, N) == 0
+    assert lib.hps_rows_store(N, N, N, 0, N, N, N, 0, N) == 0                 # no rows in either table
     assert lib.hps_peer_allreduce(N, N, N, 0, 1, 1024, N) == 0            # one rank: nothing to exchange
     assert lib.hps_peer_allreduce(N, N, N, 1, 4, 0, N) == 0               # empty buffer
     assert lib.hps_peer_allreduce_ctas() > 0 and lib.hps_peer_allreduce_pad_words() > 8 * lib.hps_peer_allreduce_ctas()
@@ -127,6 +128,10 @@ def test_c_abi_empty_inputs_and_argument_checks_without_a_gpu(hps):
         (lambda: lib.hps_mlp_fwd(7, N, N, N, N, N, 0, N, N, N), "bad decoder kind"),
         (lambda: lib.hps_mlp_tc_fwd(1, N, N, N, N, N, 16, N, N, N, 0, N), "null buffer"),
         (lambda: lib.hps_knn_query(N, N, N, N, 0, N, N, N, N, 1, N), "grid not built"),
+        (lambda: lib.hps_rows_store(N, N, N, -1, N, N, N, 0, N), "negative row count"),
+        (lambda: lib.hps_rows_store(N, N, N, 0, N, N, N, 7, N), "null buffer (second table)"),
+        (lambda: lib.hps_composite_mapper_loss(N, 3, N, 1, N, N, 4, 5, 0.1, 3, N, N, N, N, 0.1, N, N, N, N, N, N, N, N, N, N, N,
+                                               N, N, 0, N), "null buffer"),
         (lambda: lib.hps_peer_allreduce(N, N, N, 0, 9, 1024, N), "world size must be 1..8"),
         (lambda: lib.hps_peer_allreduce(N, N, N, 4, 4, 1024, N), "rank out of range"),
         (lambda: lib.hps_peer_allreduce(N, N, N, 0, 2, 1022, N), "multiple of 4"),
