@@ -45,6 +45,44 @@ def test_zero_pool_views_are_aligned_and_disjoint():
     assert zp.get(None) is None
 
 
+def test_backward_pool_layout_puts_the_feature_gradients_first():
+    """_RenderRays._plan_pool: the layout of every zero-initialised buffer of the fused backward inside one allocation -
+    feature-table gradients first (GradPool.features: what a multi-GPU exchange can take early), everything 16-byte
+    aligned, a caller-owned GradPool told what was used; clear=False leaves the clearing to the caller's kernel."""
+    import types
+    n_p = ops.N_PARAM
+    gprm = [torch.empty(3, 4)] + [torch.empty(5, 7) for _ in range(n_p - 1)]
+    cprm = [torch.empty(3, 4)] + [torch.empty(2, 9) for _ in range(n_p - 1)]
+    eprm = [torch.empty(8), torch.empty(16, 8), torch.empty(16), torch.empty(12, 16), torch.empty(12)]
+    spec = types.SimpleNamespace(color_stage=True, tracker=False)
+    # (spec, rays_o, rays_d, gt_depth, feats_geo, feats_col, affine, *geo params, *colour params, *exposure params)
+    need = [False, False, False, False, True, True, False] + [False] + [True] * (n_p - 1) + [False] + [True] * (n_p - 1) \
+        + [True] * 5
+    zp, (h_dg, h_dcw, h_daff, h_dfg, h_dfc, h_exp, h_dpg, h_dpc) = ops._RenderRays._plan_pool(
+        spec, need, gprm, cprm, None, 1000, 640, "cpu", eprm, None, "tc")
+    assert zp.features == 2 * 1000 * ops.C_DIM and zp.total % 4 == 0 and zp.total > zp.features
+    assert h_daff is None and h_dpg is None and h_dpc is None and h_exp is not None
+    assert h_dg[0] is None and h_dcw[0] is None                       # the Fourier matrices are not parameters
+    pool = ops.GradPool(torch.full((zp.total + 64,), 7.0))
+    zp.alloc(into=pool, clear=False)
+    assert pool.used == zp.total and pool.features == zp.features and not pool.zero_in_forward
+    assert float(zp.flat.min()) == 7.0                                # untouched: the caller's kernel clears it
+    dfg, dfc = zp.get(h_dfg), zp.get(h_dfc)
+    base = pool.tensor.data_ptr()
+    assert dfg.data_ptr() == base and dfc.data_ptr() == base + 4 * 1000 * ops.C_DIM
+    for v in [dfg, dfc, zp.get(h_exp)] + [t for t in zp.get(h_dg) + zp.get(h_dcw) if t is not None]:
+        off = v.data_ptr() - base
+        assert off % 16 == 0 and off + 4 * v.numel() <= 4 * zp.total
+        assert (off < 4 * zp.features) == (v is dfg or v is dfc)
+    # a tracker call (pose gradients through the tensor-core dgrad kernels) adds the two (P,3) sums behind everything else
+    spec_t = types.SimpleNamespace(color_stage=True, tracker=True)
+    need_t = [False, True, True, False, False, False, False] + [False] * (2 * n_p)
+    zt, hs = ops._RenderRays._plan_pool(spec_t, need_t, gprm, cprm, None, 1000, 640, "cpu", None, None, "tc")
+    assert zt.features == 0 and hs[6] is not None and hs[7] is not None and zt.total == 2 * 640 * 3
+    with pytest.raises(hps._lib.HpsError, match="grad_buffer"):
+        zt.alloc(into=ops.GradPool(torch.zeros(16)))
+
+
 def test_live_rows_bookkeeping_on_cpu():
     table = torch.arange(40, dtype=torch.float32).reshape(10, 4).contiguous()
     idx = torch.tensor([7, 2, 5])
