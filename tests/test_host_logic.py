@@ -794,3 +794,22 @@ def test_render_img_host_logic_matches_the_reference_frame(monkeypatch, golden, 
         else:
             assert float((d - want["depth"]).abs().max()) < 1e-5 and float((c - want["color"]).abs().max()) < 1e-5
             assert float((u - want["uncertainty"]).abs().max()) < 1e-5 * float(want["uncertainty"].max())
+
+
+def test_peer_allreduce_range_arguments_are_validated_on_the_host():
+    """PeerAllReduce.__call__ hands the kernel shifted peer addresses for a sub-range: offsets that are not a multiple of
+    four floats, ranges that leave the buffer and a multicast request without a multicast address are refused before
+    anything is launched (the object is built without symmetric memory here: only the argument checks run)."""
+    par = hps.parallel
+    ex = object.__new__(par.PeerAllReduce)
+    ex._lib, ex.n, ex.rank, ex.world, ex.multicast_ptr, ex._shift_cache = hps._lib, 4096, 0, 2, 0, {}
+    ex.buffer = torch.zeros(4)
+    for kw in (dict(offset_floats=6, n_floats=16), dict(offset_floats=-4, n_floats=16), dict(offset_floats=4092, n_floats=8),
+               dict(n_floats=5000)):
+        with pytest.raises(hps._lib.HpsError, match="PeerAllReduce"):
+            ex("p2p", **kw)
+    with pytest.raises(hps._lib.HpsError, match="multicast"):
+        ex("multimem", n_floats=16)
+    assert ex.default_variant() == "p2p" and ex.variants() == ["p2p"]
+    ex.multicast_ptr, ex.world = 1 << 20, 8
+    assert ex.default_variant() == "multimem" and ex.variants() == ["p2p", "multimem"]
