@@ -11,11 +11,11 @@ Weak scaling: every rank renders its own 5,000-ray shard of the global batch aga
 and the gradients are all-reduced (NCCL) - SURVEY 8e.
 
 Issue: one CUDA graph per iteration.  The parameter-free head of iteration i+1 (sampling + neighbour search of the
-NEXT ray batch, which a mapper draws independently of the parameters) is issued inside iteration i's graph: on one GPU
-beside the HBM-bound tail of its backward (`tail_work` of Renderer.render_batch_ray_loss), at N > 1 beside the gradient
-exchange - this package's peer-memory all-reduce kernel (hps_peer_allreduce over a symmetric gradient pool), which the
-backward issues itself once its last gradient is complete (`after_grads`).  Every timed step does one head and one rest,
-of consecutive iterations.  HPS_BENCH_EXCHANGE=nccl (and the fallback when symmetric memory is unavailable): round 1's
+NEXT ray batch, which a mapper draws independently of the parameters) is issued inside iteration i's graph beside the
+HBM-bound tail of its backward (`tail_work` of Renderer.render_batch_ray_loss; HPS_BENCH_HEAD_AT=exchange at N > 1: beside
+the gradient exchange instead).  The exchange at N > 1 is this package's peer-memory all-reduce kernel
+(hps_peer_allreduce over a symmetric gradient pool), which the backward issues itself once its last gradient is complete
+(`after_grads`).  Every timed step does one head and one rest, of consecutive iterations.  HPS_BENCH_EXCHANGE=nccl (and the fallback when symmetric memory is unavailable): round 1's
 scheme - two graphs (head | rest), NCCL all-reduce issued eagerly beside the next head, the last one timed on its own.
 
 JSON line: see the driver's contract; `value` = rays/s with inputs resident in HBM (CUDA-event timed per
@@ -449,8 +449,7 @@ def run_ours(args, rank, world, local_rank):
                       for k in (0, 1)]
             mode = "cuda-graph replay, the next iteration's head (sampling + neighbour search) beside this one's backward tail"
             if peer is not None:
-                mode = ("cuda-graph replay (one graph per iteration); gradient exchange = " + exchange_kind +
-                        ", the next iteration's head (sampling + neighbour search) beside it")
+                mode = "cuda-graph replay (one graph per iteration); gradient exchange = " + exchange_kind
             launches_per_step = hps.ops.LAUNCHES["n"] // 8      # 2 graphs x (3 warm-up passes + the captured one)
 
             def need(i):
